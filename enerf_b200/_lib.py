@@ -1,0 +1,102 @@
+"""ctypes binding of the C-ABI library (include/enerf_b200.h).
+
+The library is the product: if it is missing or cannot be loaded every op raises — there is
+no CPU or PyTorch fallback anywhere in this package.
+"""
+import ctypes as C
+import os
+import re
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libenerf_b200.so")
+HEADER_PATH = os.path.join(_HERE, "..", "include", "enerf_b200.h")
+
+F32, F16 = 0, 1
+
+_lib = None
+
+_p, _u32, _f32, _int, _u64 = C.c_void_p, C.c_uint32, C.c_float, C.c_int, C.c_uint64
+
+# name -> argtypes (restype is int for all compute entry points)
+_SIGS = {
+    "enerf_near_far_from_aabb": [_p, _p, _p, _u32, _f32, _p, _p, _p],
+    "enerf_polar_from_ray": [_p, _p, _f32, _u32, _p, _p],
+    "enerf_morton3D": [_p, _u32, _p, _p],
+    "enerf_morton3D_invert": [_p, _u32, _p, _p],
+    "enerf_packbits": [_p, _u32, _f32, _p, _p],
+    "enerf_march_rays_train": [_p, _p, _p, _f32, _f32, _u32, _u32, _u32, _u32, _u32, _p, _p, _p, _p, _p, _p, _p, _u32, _p],
+    "enerf_composite_rays_train_forward": [_p, _p, _p, _p, _u32, _u32, _u32, _p, _p, _p, _p],
+    "enerf_composite_rays_train_backward": [_p, _p, _p, _p, _p, _p, _p, _p, _u32, _u32, _u32, _p, _p, _p],
+    "enerf_march_rays": [_u32, _u32, _p, _p, _p, _p, _f32, _f32, _u32, _u32, _u32, _p, _p, _p, _p, _p, _p, _u32, _p],
+    "enerf_composite_rays": [_u32, _u32, _p, _p, _p, _p, _p, _u32, _p, _p, _p, _p],
+    "enerf_compact_rays": [_u32, _p, _p, _p, _p, _p, _p],
+    "enerf_grid_encode_forward": [_p, _p, _p, _p, _u32, _u32, _u32, _u32, _f32, _u32, _int, _p, _u32, _int, _int, _p],
+    "enerf_grid_encode_backward": [_p, _p, _p, _p, _p, _u32, _u32, _u32, _u32, _f32, _u32, _int, _p, _p, _u32, _int, _int, _int, _p],
+    "enerf_sh_encode_forward": [_p, _p, _u32, _u32, _u32, _int, _p, _int, _p],
+    "enerf_sh_encode_backward": [_p, _p, _u32, _u32, _u32, _p, _p, _int, _p],
+    "enerf_ffmlp_forward": [_p, _p, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _p, _p, _p],
+    "enerf_ffmlp_inference": [_p, _p, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _p, _p, _p],
+    "enerf_ffmlp_backward": [_p, _p, _p, _p, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _int, _p, _p, _p, _int, _p, _p],
+    "enerf_allocate_splitk": [_u64],
+    "enerf_free_splitk": [],
+}
+
+
+def declared_symbols():
+    """Every function name include/enerf_b200.h declares."""
+    with open(HEADER_PATH) as f:
+        src = f.read()
+    return sorted(set(re.findall(r"\b(enerf_[A-Za-z0-9_]+)\s*\(", src)))
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m enerf_b200.build` "
+                "(enerf_b200 has no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.enerf_last_error.restype = C.c_char_p
+        L.enerf_abi_version.restype = C.c_int
+        L.enerf_launch_count.restype = C.c_uint64
+        for name, args in _SIGS.items():
+            fn = getattr(L, name)
+            fn.argtypes = args
+            fn.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError("enerf_b200: " + lib().enerf_last_error().decode())
+
+
+def launch_count():
+    return int(lib().enerf_launch_count())
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("enerf_b200: expected a CUDA tensor (there is no CPU path)")
+
+
+def dtype_code(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.float16:
+        return F16
+    raise RuntimeError(f"enerf_b200: unsupported dtype {t.dtype} (float32 / float16 only)")

@@ -1,0 +1,439 @@
+// Multiresolution hash-grid encoder (gather forward, scatter-add backward) for sm_100a.
+//
+// Replaces the reference's `_gridencoder` extension (gridencoder/src/gridencoder.h:12-13).
+// Arithmetic follows gridencoder/src/gridencoder.cu (index math :53-71, position :123-136,
+// corner order and the per-corner rounding of the accumulator :143-168, backward :258-310).
+//
+// Execution model (differs from the reference's one-thread-per-(sample,level) 1-D blocks):
+//   * a CTA owns 32 consecutive samples and ALL levels: blockDim = (32 lanes, W warps), warp w
+//     walks levels w, w+W, ...  Consecutive samples come from the same ray (marcher order), so a
+//     warp's 32 lanes hit the same or neighbouring cells of one level: the 8 corner gathers of a
+//     warp collapse into a few 32-B sectors on the coarse levels.
+//   * the 16 warps of a CTA read the sample coordinates once from HBM (the other 15 hit L1).
+//   * outputs are staged in shared memory and written as [B, L*C] rows with fully coalesced
+//     stores — the reference writes [L,B,C] and pays a separate permute copy (grid.py:52).
+//   * backward reads grad rows in the same [B, L*C] layout (no permute/contiguous copy,
+//     grid.py:70) and scatters with vector reductions (red.global.add.v2.f32 / .noftz.f16x2).
+#include "common.cuh"
+#include <math.h>
+
+namespace enerf {
+
+static constexpr unsigned kFull = 0xffffffffu;
+static constexpr int kSamplesPerCta = 32;
+
+// ---- element-type helpers: the accumulator is rounded to T after every corner -----------
+template <typename T> struct Elem;
+template <> struct Elem<float> {
+    static __device__ __forceinline__ float ld(const float* p) { return __ldg(p); }
+    static __device__ __forceinline__ float acc(float r, float w, float g) { return __fmaf_rn(w, g, r); }
+    static __device__ __forceinline__ float sub(float a, float b) { return a - b; }
+    static __device__ __forceinline__ float to_f(float v) { return v; }
+    static __device__ __forceinline__ float from_f(float v) { return v; }
+};
+template <> struct Elem<__half> {
+    static __device__ __forceinline__ __half ld(const __half* p) { return __ldg(p); }
+    // gridencoder.cu:164 with c10::Half: the fp32 product is rounded to half, added in fp32,
+    // rounded to half again.
+    static __device__ __forceinline__ __half acc(__half r, float w, __half g) {
+        const __half p = __float2half_rn(w * __half2float(g));
+        return __float2half_rn(__half2float(r) + __half2float(p));
+    }
+    static __device__ __forceinline__ __half sub(__half a, __half b) {
+        return __float2half_rn(__half2float(a) - __half2float(b));
+    }
+    static __device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
+    static __device__ __forceinline__ __half from_f(float v) { return __float2half_rn(v); }
+};
+
+struct LevelGeom {
+    float scale;
+    uint32_t resolution, hashmap_size, offset;
+    bool use_hash, pow2;
+};
+
+__device__ __forceinline__ LevelGeom level_geom(const int32_t* __restrict__ offsets, uint32_t level, float S,
+                                                uint32_t H, uint32_t gridtype, int D) {
+    LevelGeom g;
+    g.offset = (uint32_t)offsets[level];
+    g.hashmap_size = (uint32_t)offsets[level + 1] - g.offset;
+    g.scale = exp2f((float)level * S) * (float)H - 1.0f;       // gridencoder.cu:124
+    g.resolution = (uint32_t)ceilf(g.scale) + 1;               // gridencoder.cu:125
+    uint32_t stride = 1;
+    for (int d = 0; d < D && stride <= g.hashmap_size; ++d) stride *= (g.resolution + 1);
+    g.use_hash = (gridtype == 0) && (stride > g.hashmap_size);
+    g.pow2 = (g.hashmap_size & (g.hashmap_size - 1)) == 0;
+    return g;
+}
+
+// gridencoder.cu:53-71 (element index of channel 0)
+template <int D>
+__device__ __forceinline__ uint32_t grid_index(const LevelGeom& g, const uint32_t (&p)[D]) {
+    uint32_t index;
+    if (g.use_hash) {
+        constexpr uint32_t primes[7] = {1u, 2654435761u, 805459861u, 3674653429u, 2097192037u, 1434869437u, 2165219737u};
+        index = 0;
+#pragma unroll
+        for (int d = 0; d < D; ++d) index ^= p[d] * primes[d];
+    } else {
+        uint32_t stride = 1;
+        index = 0;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            if (stride <= g.hashmap_size) {
+                index += p[d] * stride;
+                stride *= (g.resolution + 1);
+            }
+        }
+    }
+    if (g.pow2) return index & (g.hashmap_size - 1);
+    return index < g.hashmap_size ? index : index % g.hashmap_size;
+}
+
+template <int D>
+__device__ __forceinline__ bool load_pos(const float* __restrict__ inputs, uint32_t b, float (&x)[D]) {
+    bool oob = false;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        x[d] = __ldg(inputs + (size_t)b * D + d);
+        oob |= (x[d] < 0.0f) || (x[d] > 1.0f);
+    }
+    return oob;
+}
+
+// ------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------
+template <typename T, int D, int C, bool BLC>
+__global__ void __launch_bounds__(512)
+k_grid_fwd(const float* __restrict__ inputs, const T* __restrict__ grid, const int32_t* __restrict__ offsets,
+           T* __restrict__ outputs, uint32_t B, uint32_t L, float S, uint32_t H, bool calc_grad_inputs,
+           T* __restrict__ dy_dx, uint32_t gridtype, uint32_t row_stride /* staging row, in T */) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* stage = reinterpret_cast<T*>(smem_raw);
+
+    const unsigned lane = threadIdx.x;
+    const uint32_t b0 = blockIdx.x * kSamplesPerCta;
+    const uint32_t b = b0 + lane;
+    const bool active = b < B;
+
+    float x[D];
+    bool oob = true;
+    if (active) oob = load_pos<D>(inputs, b, x);
+
+    for (uint32_t level = threadIdx.y; level < L; level += blockDim.y) {
+        T res[C];
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) res[ch] = Elem<T>::from_f(0.f);
+
+        if (active && !oob) {
+            const LevelGeom g = level_geom(offsets, level, S, H, gridtype, D);
+            const T* __restrict__ tab = grid + (size_t)g.offset * C;
+            float pos[D];
+            uint32_t pg[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                pos[d] = __fmaf_rn(x[d], g.scale, 0.5f);
+                const float fl = floorf(pos[d]);
+                pg[d] = (uint32_t)fl;
+                pos[d] -= fl;
+            }
+            // gather all corners first (independent loads in flight), then blend in order
+            T v[1 << D][C];
+            float w[1 << D];
+#pragma unroll
+            for (int idx = 0; idx < (1 << D); ++idx) {
+                float ww = 1.0f;
+                uint32_t pl[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    if ((idx & (1 << d)) == 0) { ww *= 1.0f - pos[d]; pl[d] = pg[d]; }
+                    else { ww *= pos[d]; pl[d] = pg[d] + 1; }
+                }
+                w[idx] = ww;
+                const uint32_t e = grid_index<D>(g, pl) * C;
+                if (C == 2 && sizeof(T) == 2) {
+                    const __half2 h2 = __ldg(reinterpret_cast<const __half2*>(tab + e));
+                    v[idx][0] = *reinterpret_cast<const T*>(&h2.x);
+                    v[idx][C - 1] = *reinterpret_cast<const T*>(&h2.y);
+                } else {
+#pragma unroll
+                    for (int ch = 0; ch < C; ++ch) v[idx][ch] = Elem<T>::ld(tab + e + ch);
+                }
+            }
+#pragma unroll
+            for (int idx = 0; idx < (1 << D); ++idx)
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) res[ch] = Elem<T>::acc(res[ch], w[idx], v[idx][ch]);
+
+            if (calc_grad_inputs) {
+                // gridencoder.cu:178-220: d(out)/d(x_gd), layout [B, L, D, C]
+                T* __restrict__ dd = dy_dx + ((size_t)b * L + level) * D * C;
+#pragma unroll
+                for (int gd = 0; gd < D; ++gd) {
+                    T rg[C];
+#pragma unroll
+                    for (int ch = 0; ch < C; ++ch) rg[ch] = Elem<T>::from_f(0.f);
+#pragma unroll
+                    for (int idx = 0; idx < (1 << (D - 1)); ++idx) {
+                        float ww = g.scale;
+                        uint32_t pl[D];
+#pragma unroll
+                        for (int nd = 0; nd < D - 1; ++nd) {
+                            const int d = (nd >= gd) ? (nd + 1) : nd;
+                            if ((idx & (1 << nd)) == 0) { ww *= 1.0f - pos[d]; pl[d] = pg[d]; }
+                            else { ww *= pos[d]; pl[d] = pg[d] + 1; }
+                        }
+                        pl[gd] = pg[gd];
+                        const uint32_t el = grid_index<D>(g, pl) * C;
+                        pl[gd] = pg[gd] + 1;
+                        const uint32_t er = grid_index<D>(g, pl) * C;
+#pragma unroll
+                        for (int ch = 0; ch < C; ++ch)
+                            rg[ch] = Elem<T>::acc(rg[ch], ww, Elem<T>::sub(Elem<T>::ld(tab + er + ch), Elem<T>::ld(tab + el + ch)));
+                    }
+#pragma unroll
+                    for (int ch = 0; ch < C; ++ch) dd[gd * C + ch] = rg[ch];
+                }
+            }
+        } else if (active && calc_grad_inputs) {
+            T* __restrict__ dd = dy_dx + ((size_t)b * L + level) * D * C;
+            for (int i = 0; i < D * C; ++i) dd[i] = Elem<T>::from_f(0.f);
+        }
+
+        if (BLC) {
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) stage[lane * row_stride + level * C + ch] = res[ch];
+        } else if (active) {
+            T* __restrict__ o = outputs + ((size_t)level * B + b) * C;
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) o[ch] = res[ch];
+        }
+    }
+
+    if (BLC) {
+        __syncthreads();
+        // [32, L*C] tile -> contiguous global rows; 4-byte words when the row is word-sized
+        const uint32_t row_elems = L * C;
+        const uint32_t n_rows = min((uint32_t)kSamplesPerCta, B - b0);
+        const uint32_t tid = threadIdx.y * 32 + lane, nthr = blockDim.y * 32;
+        T* __restrict__ out = outputs + (size_t)b0 * row_elems;
+        if (((row_elems * sizeof(T)) & 3u) == 0 && ((row_stride * sizeof(T)) & 3u) == 0) {
+            const uint32_t rw = row_elems * sizeof(T) / 4, sw = row_stride * sizeof(T) / 4;
+            const uint32_t* s32 = reinterpret_cast<const uint32_t*>(stage);
+            uint32_t* o32 = reinterpret_cast<uint32_t*>(out);
+            for (uint32_t k = tid; k < n_rows * rw; k += nthr) o32[k] = s32[(k / rw) * sw + (k % rw)];
+        } else {
+            for (uint32_t k = tid; k < n_rows * row_elems; k += nthr) out[k] = stage[(k / row_elems) * row_stride + (k % row_elems)];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward (scatter-add into the gradient table)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void red_add(float* addr, float a) { atomicAdd(addr, a); }
+__device__ __forceinline__ void red_add2(float* addr, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void red_add(__half* addr, float a) { atomicAdd(addr, __float2half_rn(a)); }
+__device__ __forceinline__ void red_add2(__half* addr, float a, float b) {
+    const __half2 v = __halves2half2(__float2half_rn(a), __float2half_rn(b));   // gridencoder.cu:300
+    atomicAdd(reinterpret_cast<__half2*>(addr), v);
+}
+
+// T = table / grad element type, G = gradient-table element type (T, or float for fp32 accumulation)
+template <typename T, typename G, int D, int C, bool BLC>
+__global__ void __launch_bounds__(512)
+k_grid_bwd(const T* __restrict__ grad, const float* __restrict__ inputs, const int32_t* __restrict__ offsets,
+           G* __restrict__ grad_grid, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype) {
+    const unsigned lane = threadIdx.x;
+    const uint32_t b = blockIdx.x * kSamplesPerCta + lane;
+    if (b >= B) return;
+    float x[D];
+    if (load_pos<D>(inputs, b, x)) return;  // gridencoder.cu:250-256
+
+    for (uint32_t level = threadIdx.y; level < L; level += blockDim.y) {
+        const LevelGeom g = level_geom(offsets, level, S, H, gridtype, D);
+        G* __restrict__ tab = grad_grid + (size_t)g.offset * C;
+        float pos[D];
+        uint32_t pg[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            pos[d] = __fmaf_rn(x[d], g.scale, 0.5f);
+            const float fl = floorf(pos[d]);
+            pg[d] = (uint32_t)fl;
+            pos[d] -= fl;
+        }
+        float gr[C];
+        const T* __restrict__ gp = BLC ? grad + ((size_t)b * L + level) * C : grad + ((size_t)level * B + b) * C;
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) gr[ch] = Elem<T>::to_f(gp[ch]);
+
+#pragma unroll
+        for (int idx = 0; idx < (1 << D); ++idx) {
+            float w = 1.0f;
+            uint32_t pl[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                if ((idx & (1 << d)) == 0) { w *= 1.0f - pos[d]; pl[d] = pg[d]; }
+                else { w *= pos[d]; pl[d] = pg[d] + 1; }
+            }
+            const uint32_t e = grid_index<D>(g, pl) * C;
+            if (C == 1) {
+                red_add(tab + e, w * gr[0]);
+            } else {
+#pragma unroll
+                for (int ch = 0; ch < C; ch += 2) red_add2(tab + e + ch, w * gr[ch], w * gr[ch + (C > 1 ? 1 : 0)]);
+            }
+        }
+    }
+}
+
+// gridencoder.cu:314-340
+template <typename T, int D, int C, bool BLC>
+__global__ void k_grid_input_bwd(const T* __restrict__ grad, const T* __restrict__ dy_dx, T* __restrict__ grad_inputs,
+                                 uint32_t B, uint32_t L) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B * D) return;
+    const uint32_t b = t / D, d = t - b * D;
+    const T* __restrict__ dd = dy_dx + (size_t)b * L * D * C;
+    T result = Elem<T>::from_f(0.f);
+    for (uint32_t l = 0; l < L; ++l) {
+        for (int ch = 0; ch < C; ++ch) {
+            const T gv = BLC ? grad[((size_t)b * L + l) * C + ch] : grad[((size_t)l * B + b) * C + ch];
+            const float prod = Elem<T>::to_f(gv) * Elem<T>::to_f(dd[(l * D + d) * C + ch]);
+            // `result += a * b` in scalar_t: product and sum each rounded to T (fp32: contracted)
+            if (sizeof(T) == 4) result = Elem<T>::from_f(__fmaf_rn(Elem<T>::to_f(gv), Elem<T>::to_f(dd[(l * D + d) * C + ch]), Elem<T>::to_f(result)));
+            else result = Elem<T>::from_f(Elem<T>::to_f(result) + Elem<T>::to_f(Elem<T>::from_f(prod)));
+        }
+    }
+    grad_inputs[t] = result;
+}
+
+// ------------------------------------------------------------------------------------------
+// launch plumbing
+// ------------------------------------------------------------------------------------------
+static inline uint32_t stage_row_stride(uint32_t L, uint32_t C, size_t elt) {
+    uint32_t row = L * C;
+    // make the row an odd number of 32-bit words so lanes (rows) fall in distinct banks
+    if ((row * elt) % 4 == 0) {
+        uint32_t words = row * elt / 4;
+        if (words % 2 == 0) row += 4 / elt;
+    }
+    return row;
+}
+
+template <typename T, int D, int C>
+static int launch_fwd(const float* inputs, const T* emb, const int32_t* offsets, T* outputs, uint32_t B, uint32_t L, float S,
+                      uint32_t H, bool cg, T* dy_dx, uint32_t gridtype, int out_layout, cudaStream_t st) {
+    const dim3 block(32, min(L, 16u));
+    const dim3 grid(ceil_div(B, (uint32_t)kSamplesPerCta));
+    if (out_layout == 1) {
+        const uint32_t rs = stage_row_stride(L, C, sizeof(T));
+        const size_t smem = (size_t)kSamplesPerCta * rs * sizeof(T);
+        if (smem > 48 * 1024) { set_error("grid_encode_forward: L*C too large for the staging tile"); return -2; }
+        k_grid_fwd<T, D, C, true><<<grid, block, smem, st>>>(inputs, emb, offsets, outputs, B, L, S, H, cg, dy_dx, gridtype, rs);
+    } else {
+        k_grid_fwd<T, D, C, false><<<grid, block, 0, st>>>(inputs, emb, offsets, outputs, B, L, S, H, cg, dy_dx, gridtype, 0);
+    }
+    ENERF_CHECK_LAUNCH("grid_encode_forward");
+    return 0;
+}
+
+template <typename T, typename G, int D, int C>
+static int launch_bwd(const T* grad, const float* inputs, const int32_t* offsets, G* gg, uint32_t B, uint32_t L, float S, uint32_t H,
+                      bool cg, const T* dy_dx, T* grad_inputs, uint32_t gridtype, int out_layout, cudaStream_t st) {
+    const dim3 block(32, min(L, 16u));
+    const dim3 grid(ceil_div(B, (uint32_t)kSamplesPerCta));
+    if (out_layout == 1) k_grid_bwd<T, G, D, C, true><<<grid, block, 0, st>>>(grad, inputs, offsets, gg, B, L, S, H, gridtype);
+    else k_grid_bwd<T, G, D, C, false><<<grid, block, 0, st>>>(grad, inputs, offsets, gg, B, L, S, H, gridtype);
+    ENERF_CHECK_LAUNCH("grid_encode_backward");
+    if (cg) {
+        const uint32_t n = B * D;
+        if (out_layout == 1) k_grid_input_bwd<T, D, C, true><<<ceil_div(n, 256u), 256, 0, st>>>(grad, dy_dx, grad_inputs, B, L);
+        else k_grid_input_bwd<T, D, C, false><<<ceil_div(n, 256u), 256, 0, st>>>(grad, dy_dx, grad_inputs, B, L);
+        ENERF_CHECK_LAUNCH("grid_encode_backward(input)");
+    }
+    return 0;
+}
+
+#define ENERF_DC_SWITCH(D, C, name, CALL)                                                           \
+    if (D == 3) {                                                                                   \
+        switch (C) {                                                                                \
+            case 1: { constexpr int DD = 3, CC = 1; CALL; } break;                                  \
+            case 2: { constexpr int DD = 3, CC = 2; CALL; } break;                                  \
+            case 4: { constexpr int DD = 3, CC = 4; CALL; } break;                                  \
+            case 8: { constexpr int DD = 3, CC = 8; CALL; } break;                                  \
+            default: set_error("%s: GridEncoding: C must be 1, 2, 4, or 8.", name); return -2;      \
+        }                                                                                           \
+    } else if (D == 2) {                                                                            \
+        switch (C) {                                                                                \
+            case 1: { constexpr int DD = 2, CC = 1; CALL; } break;                                  \
+            case 2: { constexpr int DD = 2, CC = 2; CALL; } break;                                  \
+            case 4: { constexpr int DD = 2, CC = 4; CALL; } break;                                  \
+            case 8: { constexpr int DD = 2, CC = 8; CALL; } break;                                  \
+            default: set_error("%s: GridEncoding: C must be 1, 2, 4, or 8.", name); return -2;      \
+        }                                                                                           \
+    } else {                                                                                        \
+        set_error("%s: GridEncoding: D must be 2 or 3.", name);                                     \
+        return -2;                                                                                  \
+    }
+
+}  // namespace enerf
+
+using namespace enerf;
+
+extern "C" {
+
+int enerf_grid_encode_forward(const float* inputs, const void* embeddings, const int32_t* offsets, void* outputs,
+                              uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, int calc_grad_inputs,
+                              void* dy_dx, uint32_t gridtype, int dtype, int out_layout, void* stream) {
+    if (B == 0) return 0;
+    ENERF_REQUIRE(dtype == ENERF_F32 || dtype == ENERF_F16, "grid_encode_forward", "dtype must be ENERF_F32 or ENERF_F16");
+    ENERF_REQUIRE(out_layout == 0 || out_layout == 1, "grid_encode_forward", "out_layout must be 0 or 1");
+    ENERF_REQUIRE(L >= 1 && L <= 64, "grid_encode_forward", "L must be in [1,64]");
+    cudaStream_t st = as_stream(stream);
+    int rc = 0;
+    if (dtype == ENERF_F16) {
+        ENERF_DC_SWITCH(D, C, "grid_encode_forward",
+                        rc = (launch_fwd<__half, DD, CC>(inputs, (const __half*)embeddings, offsets, (__half*)outputs, B, L, S, H,
+                                                         calc_grad_inputs != 0, (__half*)dy_dx, gridtype, out_layout, st)));
+    } else {
+        ENERF_DC_SWITCH(D, C, "grid_encode_forward",
+                        rc = (launch_fwd<float, DD, CC>(inputs, (const float*)embeddings, offsets, (float*)outputs, B, L, S, H,
+                                                        calc_grad_inputs != 0, (float*)dy_dx, gridtype, out_layout, st)));
+    }
+    return rc;
+}
+
+int enerf_grid_encode_backward(const void* grad, const float* inputs, const void* embeddings, const int32_t* offsets,
+                               void* grad_embeddings, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+                               int calc_grad_inputs, const void* dy_dx, void* grad_inputs, uint32_t gridtype, int dtype,
+                               int grad_dtype, int out_layout, void* stream) {
+    (void)embeddings;
+    if (B == 0) return 0;
+    ENERF_REQUIRE(dtype == ENERF_F32 || dtype == ENERF_F16, "grid_encode_backward", "dtype must be ENERF_F32 or ENERF_F16");
+    ENERF_REQUIRE(grad_dtype == ENERF_F32 || grad_dtype == dtype, "grid_encode_backward", "grad_dtype must be ENERF_F32 or equal dtype");
+    ENERF_REQUIRE(out_layout == 0 || out_layout == 1, "grid_encode_backward", "out_layout must be 0 or 1");
+    ENERF_REQUIRE(L >= 1 && L <= 64, "grid_encode_backward", "L must be in [1,64]");
+    cudaStream_t st = as_stream(stream);
+    const bool cg = calc_grad_inputs != 0;
+    int rc = 0;
+    if (dtype == ENERF_F16 && grad_dtype == ENERF_F16) {
+        ENERF_DC_SWITCH(D, C, "grid_encode_backward",
+                        rc = (launch_bwd<__half, __half, DD, CC>((const __half*)grad, inputs, offsets, (__half*)grad_embeddings, B, L, S, H,
+                                                                 cg, (const __half*)dy_dx, (__half*)grad_inputs, gridtype, out_layout, st)));
+    } else if (dtype == ENERF_F16) {
+        ENERF_DC_SWITCH(D, C, "grid_encode_backward",
+                        rc = (launch_bwd<__half, float, DD, CC>((const __half*)grad, inputs, offsets, (float*)grad_embeddings, B, L, S, H,
+                                                                cg, (const __half*)dy_dx, (__half*)grad_inputs, gridtype, out_layout, st)));
+    } else {
+        ENERF_DC_SWITCH(D, C, "grid_encode_backward",
+                        rc = (launch_bwd<float, float, DD, CC>((const float*)grad, inputs, offsets, (float*)grad_embeddings, B, L, S, H,
+                                                               cg, (const float*)dy_dx, (float*)grad_inputs, gridtype, out_layout, st)));
+    }
+    return rc;
+}
+
+}  // extern "C"

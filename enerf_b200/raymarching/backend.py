@@ -1,0 +1,4 @@
+"""Reference-compatible name (raymarching/backend.py:31): the prebuilt C-ABI shim, never a JIT build."""
+from ..backends import raymarching_backend as _backend
+
+__all__ = ['_backend']

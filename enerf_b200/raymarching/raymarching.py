@@ -1,0 +1,227 @@
+"""Drop-in for the reference's `raymarching` package (raymarching/raymarching.py).
+
+Same public callables, argument order, defaults, dtypes and return shapes:
+near_far_from_aabb (:49), polar_from_ray (:80), morton3D (:104), morton3D_invert (:126),
+packbits (:155), march_rays_train (:230), composite_rays_train (:286), march_rays (:337),
+composite_rays (:362), compact_rays (:382).  Every op runs a sm_100a kernel through the C-ABI
+(include/enerf_b200.h) on the current stream; CPU inputs are moved to the GPU exactly where the
+reference does so.  Extension over the reference: compositing accepts 1..4 colour channels
+(the reference kernels are hard-wired to 3, raymarching/src/raymarching.cu:549-551).
+"""
+import torch
+from torch.amp import custom_bwd, custom_fwd
+from torch.autograd import Function
+
+from .backend import _backend
+
+_fwd32 = custom_fwd(device_type='cuda', cast_inputs=torch.float32)
+_bwd = custom_bwd(device_type='cuda')
+
+
+def _rays(t):
+    if not t.is_cuda:
+        t = t.cuda()
+    return t.contiguous().view(-1, 3)
+
+
+# ---------------------------------------------------------------------------- utils
+class _near_far_from_aabb(Function):
+    @staticmethod
+    @_fwd32
+    def forward(ctx, rays_o, rays_d, aabb, min_near=0.2):
+        """rays_o/rays_d [N,3], aabb [6] -> nears [N], fars [N] (FLT_MAX for rays missing the box)."""
+        rays_o, rays_d = _rays(rays_o), _rays(rays_d)
+        if not aabb.is_cuda:
+            aabb = aabb.to(rays_o.device)
+        N = rays_o.shape[0]
+        nears = torch.empty(N, dtype=rays_o.dtype, device=rays_o.device)
+        fars = torch.empty(N, dtype=rays_o.dtype, device=rays_o.device)
+        _backend.near_far_from_aabb(rays_o, rays_d, aabb.contiguous(), N, min_near, nears, fars)
+        return nears, fars
+
+
+near_far_from_aabb = _near_far_from_aabb.apply
+
+
+class _polar_from_ray(Function):
+    @staticmethod
+    @_fwd32
+    def forward(ctx, rays_o, rays_d, radius):
+        """Intersection of each ray with the sphere of `radius` as (theta, phi) in [-1,1]^2."""
+        rays_o, rays_d = _rays(rays_o), _rays(rays_d)
+        N = rays_o.shape[0]
+        coords = torch.empty(N, 2, dtype=rays_o.dtype, device=rays_o.device)
+        _backend.polar_from_ray(rays_o, rays_d, radius, N, coords)
+        return coords
+
+
+polar_from_ray = _polar_from_ray.apply
+
+
+class _morton3D(Function):
+    @staticmethod
+    def forward(ctx, coords):
+        """coords int [N,3] in [0,128) -> Morton index int32 [N]."""
+        if not coords.is_cuda:
+            coords = coords.cuda()
+        N = coords.shape[0]
+        indices = torch.empty(N, dtype=torch.int32, device=coords.device)
+        _backend.morton3D(coords.int().contiguous(), N, indices)
+        return indices
+
+
+morton3D = _morton3D.apply
+
+
+class _morton3D_invert(Function):
+    @staticmethod
+    def forward(ctx, indices):
+        """Morton index [N] -> coords int32 [N,3]."""
+        if not indices.is_cuda:
+            indices = indices.cuda()
+        N = indices.shape[0]
+        coords = torch.empty(N, 3, dtype=torch.int32, device=indices.device)
+        _backend.morton3D_invert(indices.int().contiguous(), N, coords)
+        return coords
+
+
+morton3D_invert = _morton3D_invert.apply
+
+
+class _packbits(Function):
+    @staticmethod
+    @_fwd32
+    def forward(ctx, grid, thresh, bitfield=None):
+        """grid float [C, H^3] -> uint8 [C*H^3/8]; bit i of byte n is grid.flat[8n+i] > thresh."""
+        if not grid.is_cuda:
+            grid = grid.cuda()
+        grid = grid.contiguous()
+        N = grid.shape[0] * grid.shape[1] // 8
+        if bitfield is None:
+            bitfield = torch.empty(N, dtype=torch.uint8, device=grid.device)
+        _backend.packbits(grid, N, thresh, bitfield)
+        return bitfield
+
+
+packbits = _packbits.apply
+
+
+def _pad_up(m, align):
+    # the reference always adds a full `align` when m is already aligned (raymarching.py:201-203)
+    return m + (align - m % align) if align > 0 else m
+
+
+# ---------------------------------------------------------------------------- train
+class _march_rays_train(Function):
+    @staticmethod
+    @_fwd32
+    def forward(ctx, rays_o, rays_d, bound, density_bitfield, C, H, nears, fars, step_counter=None, mean_count=-1,
+                perturb=False, align=-1, force_all_rays=False, dt_gamma=0, max_steps=1024):
+        """Occupancy-grid marching.  Returns xyzs [M,3], dirs [M,3], deltas [M,2], rays [N,3] int32
+        (ray id, first sample, sample count); step_counter (int32[2]) += (samples, rays)."""
+        rays_o, rays_d = _rays(rays_o), _rays(rays_d)
+        if not density_bitfield.is_cuda:
+            density_bitfield = density_bitfield.cuda()
+        density_bitfield = density_bitfield.contiguous()
+        dev = rays_o.device
+        N = rays_o.shape[0]
+        exact = force_all_rays or mean_count <= 0
+        M = N * max_steps if exact else _pad_up(mean_count, align)
+
+        xyzs = torch.zeros(M, 3, dtype=torch.float32, device=dev)
+        dirs = torch.zeros(M, 3, dtype=torch.float32, device=dev)
+        deltas = torch.zeros(M, 2, dtype=torch.float32, device=dev)
+        rays = torch.empty(N, 3, dtype=torch.int32, device=dev)
+        if step_counter is None:
+            step_counter = torch.zeros(2, dtype=torch.int32, device=dev)
+
+        _backend.march_rays_train(rays_o, rays_d, density_bitfield, bound, dt_gamma, max_steps, N, C, H, M, nears, fars,
+                                  xyzs, dirs, deltas, rays, step_counter, perturb)
+
+        if exact:
+            # first epochs only: size the outputs to the real sample count (one D2H read)
+            m = _pad_up(int(step_counter[0].item()), align)
+            xyzs, dirs, deltas = xyzs[:m], dirs[:m], deltas[:m]
+        return xyzs, dirs, deltas, rays
+
+
+march_rays_train = _march_rays_train.apply
+
+
+class _composite_rays_train(Function):
+    @staticmethod
+    @_fwd32
+    def forward(ctx, sigmas, rgbs, deltas, rays):
+        """sigmas [M], rgbs [M,c], deltas [M,2], rays [N,3] -> weights_sum [N], depth [N], image [N,c]."""
+        sigmas = sigmas.contiguous()
+        rgbs = rgbs.contiguous()
+        deltas = deltas.contiguous()
+        M, N = sigmas.shape[0], rays.shape[0]
+        n_ch = rgbs.shape[1]
+        weights_sum = torch.empty(N, dtype=sigmas.dtype, device=sigmas.device)
+        depth = torch.empty(N, dtype=sigmas.dtype, device=sigmas.device)
+        image = torch.empty(N, n_ch, dtype=sigmas.dtype, device=sigmas.device)
+        _backend.composite_rays_train_forward(sigmas, rgbs, deltas, rays, M, N, weights_sum, depth, image)
+        ctx.save_for_backward(sigmas, rgbs, deltas, rays, weights_sum, image)
+        ctx.dims = (M, N)
+        return weights_sum, depth, image
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, grad_weights_sum, grad_depth, grad_image):
+        # grad_depth is not propagated (raymarching.py:270)
+        sigmas, rgbs, deltas, rays, weights_sum, image = ctx.saved_tensors
+        M, N = ctx.dims
+        grad_sigmas = torch.zeros_like(sigmas)
+        grad_rgbs = torch.zeros_like(rgbs)
+        _backend.composite_rays_train_backward(grad_weights_sum.contiguous(), grad_image.contiguous(), sigmas, rgbs, deltas, rays,
+                                               weights_sum, image, M, N, grad_sigmas, grad_rgbs)
+        return grad_sigmas, grad_rgbs, None, None
+
+
+composite_rays_train = _composite_rays_train.apply
+
+
+# ---------------------------------------------------------------------------- inference
+class _march_rays(Function):
+    @staticmethod
+    @_fwd32
+    def forward(ctx, n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, density_bitfield, C, H, near, far, align=-1,
+                perturb=False, dt_gamma=0, max_steps=1024):
+        """March each alive ray up to n_step samples from rays_t; slots without a sample stay zero."""
+        rays_o, rays_d = _rays(rays_o), _rays(rays_d)
+        M = _pad_up(n_alive * n_step, align)
+        dev = rays_o.device
+        xyzs = torch.zeros(M, 3, dtype=torch.float32, device=dev)
+        dirs = torch.zeros(M, 3, dtype=torch.float32, device=dev)
+        deltas = torch.zeros(M, 2, dtype=torch.float32, device=dev)
+        _backend.march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, density_bitfield,
+                            near, far, xyzs, dirs, deltas, perturb)
+        return xyzs, dirs, deltas
+
+
+march_rays = _march_rays.apply
+
+
+class _composite_rays(Function):
+    @staticmethod
+    @_fwd32
+    def forward(ctx, n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image):
+        """In-place accumulation into weights_sum/depth/image; rays_t <- -1 for terminated rays."""
+        _backend.composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas.contiguous(), rgbs.contiguous(), deltas, weights_sum, depth, image)
+        return tuple()
+
+
+composite_rays = _composite_rays.apply
+
+
+class _compact_rays(Function):
+    @staticmethod
+    @_fwd32
+    def forward(ctx, n_alive, rays_alive, rays_alive_old, rays_t, rays_t_old, alive_counter):
+        """Keep rays with rays_t_old >= 0; alive_counter[0] += number kept."""
+        _backend.compact_rays(n_alive, rays_alive, rays_alive_old, rays_t, rays_t_old, alive_counter)
+        return tuple()
+
+
+compact_rays = _compact_rays.apply

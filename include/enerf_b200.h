@@ -1,0 +1,187 @@
+/*
+ * enerf_b200.h — C ABI of the B200-native E-NeRF volume-rendering hot path.
+ *
+ * This is the drop-in boundary.  Every entry point replaces exactly one function of the
+ * reference's four pybind11 extensions (the only FFI the reference has for this path); the
+ * reference declaration each one stands in for is cited as file:line relative to the
+ * reference repository (knelk/enerf @ 3fb17cd).  The reference passes `at::Tensor` by value
+ * and launches on the legacy default stream; here every argument is a plain device pointer
+ * or scalar and every call takes the CUDA stream to launch on (`stream` is a cudaStream_t
+ * passed as void*; NULL = default stream).  All buffers are caller-owned and pre-allocated,
+ * exactly as in the reference (outputs are written in place).
+ *
+ * Return value: 0 on success, non-zero on failure (bad argument or CUDA error);
+ * enerf_last_error() returns a thread-local human-readable message for the last failure.
+ * Nothing here falls back to the CPU: without a CUDA device every compute call fails.
+ *
+ * dtype codes (for entry points whose reference counterpart dispatches on scalar type):
+ */
+#ifndef ENERF_B200_H
+#define ENERF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ENERF_F32 0
+#define ENERF_F16 1
+
+/* activation codes, ffmlp/ffmlp.py:87-96, ffmlp/src/ffmlp.cu:22-33 */
+#define ENERF_ACT_RELU 0
+#define ENERF_ACT_EXPONENTIAL 1
+#define ENERF_ACT_SINE 2
+#define ENERF_ACT_SIGMOID 3
+#define ENERF_ACT_SQUAREPLUS 4
+#define ENERF_ACT_SOFTPLUS 5
+#define ENERF_ACT_NONE 6
+
+const char* enerf_last_error(void);
+/* ABI version of this library (bumped on any signature change). */
+int enerf_abi_version(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+uint64_t enerf_launch_count(void);
+
+/* ------------------------------------------------------------------ raymarching ---- */
+/* raymarching/src/raymarching.h:7-18, raymarching/src/raymarching.cu. fp32 only: the
+ * reference's Python wrappers cast every float input to fp32 (raymarching.py:21,54,131,...). */
+
+/* raymarching.h:7 near_far_from_aabb; kernel raymarching.cu:93-158 */
+int enerf_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb,
+                             uint32_t N, float min_near, float* nears, float* fars, void* stream);
+/* raymarching.h:8 polar_from_ray; raymarching.cu:164-211 */
+int enerf_polar_from_ray(const float* rays_o, const float* rays_d, float radius, uint32_t N,
+                         float* coords, void* stream);
+/* raymarching.h:9 morton3D; raymarching.cu:216-234 */
+int enerf_morton3D(const int32_t* coords, uint32_t N, int32_t* indices, void* stream);
+/* raymarching.h:10 morton3D_invert; raymarching.cu:239-262 */
+int enerf_morton3D_invert(const int32_t* indices, uint32_t N, int32_t* coords, void* stream);
+/* raymarching.h:11 packbits; raymarching.cu:269-302. N = number of output bytes. */
+int enerf_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* bitfield,
+                   void* stream);
+/* raymarching.h:13 march_rays_train; raymarching.cu:313-490.
+ * xyzs/dirs [M,3], deltas [M,2], rays [N,3] = (ray id, sample offset, sample count),
+ * counter int32[2] += (samples, rays).  Sample ranges are reserved with one atomic per ray, so
+ * (as in the reference) the order of ranges is not deterministic. */
+int enerf_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid,
+                           float bound, float dt_gamma, uint32_t max_steps, uint32_t N,
+                           uint32_t C, uint32_t H, uint32_t M, const float* nears,
+                           const float* fars, float* xyzs, float* dirs, float* deltas,
+                           int32_t* rays, int32_t* counter, uint32_t perturb, void* stream);
+/* raymarching.h:14 composite_rays_train_forward; raymarching.cu:500-589.
+ * n_ch: colour channels per sample (the reference hard-wires 3, raymarching.cu:549-551;
+ * E-NeRF trains out_dim_color=1, so the channel count is a parameter here). */
+int enerf_composite_rays_train_forward(const float* sigmas, const float* rgbs,
+                                       const float* deltas, const int32_t* rays, uint32_t M,
+                                       uint32_t N, uint32_t n_ch, float* weights_sum,
+                                       float* depth, float* image, void* stream);
+/* raymarching.h:15 composite_rays_train_backward; raymarching.cu:602-693 */
+int enerf_composite_rays_train_backward(const float* grad_weights_sum, const float* grad_image,
+                                        const float* sigmas, const float* rgbs,
+                                        const float* deltas, const int32_t* rays,
+                                        const float* weights_sum, const float* image,
+                                        uint32_t M, uint32_t N, uint32_t n_ch,
+                                        float* grad_sigmas, float* grad_rgbs, void* stream);
+/* raymarching.h:16 march_rays (inference); raymarching.cu:700-813 */
+int enerf_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive,
+                     const float* rays_t, const float* rays_o, const float* rays_d, float bound,
+                     float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
+                     const uint8_t* grid, const float* nears, const float* fars, float* xyzs,
+                     float* dirs, float* deltas, uint32_t perturb, void* stream);
+/* raymarching.h:17 composite_rays (inference, in place); raymarching.cu:816-909 */
+int enerf_composite_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive,
+                         float* rays_t, const float* sigmas, const float* rgbs,
+                         const float* deltas, uint32_t n_ch, float* weights_sum, float* depth,
+                         float* image, void* stream);
+/* raymarching.h:18 compact_rays; raymarching.cu:912-939 */
+int enerf_compact_rays(uint32_t n_alive, int32_t* rays_alive, const int32_t* rays_alive_old,
+                       float* rays_t, const float* rays_t_old, int32_t* alive_counter,
+                       void* stream);
+
+/* ------------------------------------------------------------------ gridencoder ---- */
+/* gridencoder/src/gridencoder.h:12-13, gridencoder/src/gridencoder.cu.
+ * dtype = element type of embeddings/outputs/dy_dx/grad (ENERF_F32 | ENERF_F16); inputs are
+ * always fp32 in [0,1].  out_layout: 0 = [L,B,C] (the reference kernel's layout,
+ * gridencoder.cu:94), 1 = [B,L*C] (what gridencoder/grid.py:52 returns after its permute). */
+
+/* gridencoder.h:12 grid_encode_forward; gridencoder.cu:74-222,343-370,416-439 */
+int enerf_grid_encode_forward(const float* inputs, const void* embeddings, const int32_t* offsets,
+                              void* outputs, uint32_t B, uint32_t D, uint32_t C, uint32_t L,
+                              float S, uint32_t H, int calc_grad_inputs, void* dy_dx,
+                              uint32_t gridtype, int dtype, int out_layout, void* stream);
+/* gridencoder.h:13 grid_encode_backward; gridencoder.cu:225-340,372-412,441-471.
+ * grad has layout `out_layout`; grad_embeddings must be zero-initialised by the caller (as
+ * gridencoder/grid.py:72 does).  grad_dtype: element type of grad_embeddings — the reference
+ * uses `dtype`; ENERF_F32 with a half table accumulates in fp32 instead of fp16 atomics. */
+int enerf_grid_encode_backward(const void* grad, const float* inputs, const void* embeddings,
+                               const int32_t* offsets, void* grad_embeddings, uint32_t B,
+                               uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+                               int calc_grad_inputs, const void* dy_dx, void* grad_inputs,
+                               uint32_t gridtype, int dtype, int grad_dtype, int out_layout,
+                               void* stream);
+
+/* -------------------------------------------------------------------- shencoder ---- */
+/* shencoder/src/shencoder.h:10,13, shencoder/src/shencoder.cu.  degree C in [1,8], D == 3. */
+
+/* shencoder.h:10 sh_encode_forward; shencoder.cu:27-356,387-419 */
+int enerf_sh_encode_forward(const void* inputs, void* outputs, uint32_t B, uint32_t D, uint32_t C,
+                            int calc_grad_inputs, void* dy_dx, int dtype, void* stream);
+/* shencoder.h:13 sh_encode_backward; shencoder.cu:359-440.  grad_inputs is accumulated into
+ * (the reference does `+=` on a zero-initialised buffer, shencoder.cu:378). */
+int enerf_sh_encode_backward(const void* grad, const void* inputs, uint32_t B, uint32_t D,
+                             uint32_t C, const void* dy_dx, void* grad_inputs, int dtype,
+                             void* stream);
+
+/* ------------------------------------------------------------------------ ffmlp ---- */
+/* ffmlp/src/ffmlp.h:8-13, ffmlp/src/ffmlp.cu.  All tensors fp16 (uint16_t* here), row-major
+ * [B, width]; B must be a multiple of 128 (ffmlp/ffmlp.py:157-159 pads).  weights: flat
+ * [hidden,input] + (num_layers-1) x [hidden,hidden] + [output(16),hidden], each row-major
+ * [out,in] (ffmlp.cu:631-634).  Accumulation is fp32 (the reference accumulates in fp16). */
+
+/* ffmlp.h:8 ffmlp_forward; ffmlp.cu:635-672.  forward_buffer [num_layers,B,hidden]. */
+int enerf_ffmlp_forward(const uint16_t* inputs, const uint16_t* weights, uint32_t B,
+                        uint32_t input_dim, uint32_t output_dim, uint32_t hidden_dim,
+                        uint32_t num_layers, uint32_t activation, uint32_t output_activation,
+                        uint16_t* forward_buffer, uint16_t* outputs, void* stream);
+/* ffmlp.h:9 ffmlp_inference; ffmlp.cu:674-709.  inference_buffer [B,hidden] is scratch the
+ * reference needs; it is accepted and left untouched here. */
+int enerf_ffmlp_inference(const uint16_t* inputs, const uint16_t* weights, uint32_t B,
+                          uint32_t input_dim, uint32_t output_dim, uint32_t hidden_dim,
+                          uint32_t num_layers, uint32_t activation, uint32_t output_activation,
+                          uint16_t* inference_buffer, uint16_t* outputs, void* stream);
+/* ffmlp.h:11 ffmlp_backward; ffmlp.cu:742-894.  backward_buffer [num_layers,B,hidden] may be
+ * NULL (the activation gradients then never leave the SM).  grad_weights: fp16 when
+ * grad_weights_dtype == ENERF_F16 (reference), fp32 flat buffer when ENERF_F32; it is
+ * overwritten, not accumulated.  `scratch` = caller-owned fp32 buffer with as many elements as
+ * `weights` (used as the reduction target; may alias grad_weights when that is fp32). */
+int enerf_ffmlp_backward(const uint16_t* grad, const uint16_t* inputs, const uint16_t* weights,
+                         const uint16_t* forward_buffer, uint32_t B, uint32_t input_dim,
+                         uint32_t output_dim, uint32_t hidden_dim, uint32_t num_layers,
+                         uint32_t activation, uint32_t output_activation, int calc_grad_inputs,
+                         uint16_t* backward_buffer, uint16_t* grad_inputs, void* grad_weights,
+                         int grad_weights_dtype, float* scratch, void* stream);
+/* ffmlp.h:12-13 allocate_splitk / free_splitk; ffmlp.cu:711-740.  The reference creates one
+ * stream+event per layer for its CUTLASS split-K weight-gradient GEMMs.  The weight gradients
+ * are fused into the backward kernel here, so these only validate their argument. */
+int enerf_allocate_splitk(uint64_t size);
+int enerf_free_splitk(void);
+
+/* ---------------------------------------------------- fused extras (no reference ABI) ---- */
+/* Fixed-step integrator of NeRFRenderer.run (nerf/renderer.py:230-255), which the reference
+ * evaluates as ~25 ATen kernels.  sigmas [N,T] (already multiplied by density_scale),
+ * rgbs [N,T,n_ch], z_vals [N,T], nears/fars [N].  deltas follow renderer.py:230-231.
+ * Outputs: weights [N,T] (needed for the colour mask, renderer.py:236), weights_sum [N],
+ * depth [N] (renderer.py:251-252), image [N,n_ch] without background. */
+int enerf_composite_uniform_weights(const float* sigmas, const float* z_vals, const float* nears,
+                                    const float* fars, uint32_t N, uint32_t T, float* weights,
+                                    float* weights_sum, float* depth, void* stream);
+int enerf_composite_uniform_backward(const float* grad_weights, const float* sigmas,
+                                     const float* z_vals, const float* nears, const float* fars,
+                                     const float* weights, uint32_t N, uint32_t T,
+                                     float* grad_sigmas, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ENERF_B200_H */
