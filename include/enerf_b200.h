@@ -169,16 +169,21 @@ int enerf_free_splitk(void);
 
 /* ---------------------------------------------------- fused extras (no reference ABI) ---- */
 /* Fixed-step integrator of NeRFRenderer.run (nerf/renderer.py:230-255), which the reference
- * evaluates as ~25 ATen kernels.  sigmas [N,T] (already multiplied by density_scale),
- * rgbs [N,T,n_ch], z_vals [N,T], nears/fars [N].  deltas follow renderer.py:230-231.
- * Outputs: weights [N,T] (needed for the colour mask, renderer.py:236), weights_sum [N],
- * depth [N] (renderer.py:251-252), image [N,n_ch] without background. */
-int enerf_composite_uniform_weights(const float* sigmas, const float* z_vals, const float* nears,
-                                    const float* fars, uint32_t N, uint32_t T, float* weights,
-                                    float* weights_sum, float* depth, void* stream);
-int enerf_composite_uniform_backward(const float* grad_weights, const float* sigmas,
+ * evaluates as ~25 ATen kernels over [N,T] temporaries.  One warp per ray:
+ *   delta_i = z_{i+1}-z_i, last = (far-near)/T           (renderer.py:230-231)
+ *   alpha_i = 1-exp(-delta_i*density_scale*sigma_i)      (renderer.py:232)
+ *   w_i = alpha_i * prod_{j<i}(1-alpha_j+1e-15)          (renderer.py:233-234)
+ *   weights_sum = sum w, depth = sum w*clamp((z-near)/(far-near),0,1)   (renderer.py:248-252)
+ * sigmas, z_vals, weights: [N,T]; nears, fars, weights_sum, depth: [N]. */
+int enerf_composite_uniform_forward(const float* sigmas, const float* z_vals, const float* nears,
+                                    const float* fars, uint32_t N, uint32_t T, float density_scale,
+                                    float* weights, float* weights_sum, float* depth, void* stream);
+/* d(loss)/d(sigmas) given d(loss)/d(weights) [N,T], d/d(weights_sum) [N], d/d(depth) [N]
+ * (each may be NULL = zero). */
+int enerf_composite_uniform_backward(const float* grad_weights, const float* grad_weights_sum,
+                                     const float* grad_depth, const float* sigmas,
                                      const float* z_vals, const float* nears, const float* fars,
-                                     const float* weights, uint32_t N, uint32_t T,
+                                     uint32_t N, uint32_t T, float density_scale,
                                      float* grad_sigmas, void* stream);
 
 #ifdef __cplusplus

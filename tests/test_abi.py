@@ -1,0 +1,78 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol
+include/enerf_b200.h declares, and the product path refuses to run without a GPU."""
+import ctypes
+
+import pytest
+import torch
+
+from enerf_b200 import _lib
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.lib()
+    declared = _lib.declared_symbols()
+    assert len(declared) >= 23
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/enerf_b200.h but not exported"
+
+
+def test_ctypes_table_matches_header():
+    declared = set(_lib.declared_symbols())
+    bound = set(_lib._SIGS) | {"enerf_last_error", "enerf_abi_version", "enerf_launch_count"}
+    assert declared == bound, declared ^ bound
+
+
+def test_header_is_plain_c():
+    src = open(_lib.HEADER_PATH).read()
+    assert 'extern "C"' in src
+    includes = [l for l in src.splitlines() if l.strip().startswith("#include")]
+    assert includes == ["#include <stdint.h>"], includes   # no torch / ATen / CUDA types at the boundary
+
+
+def test_abi_version_and_error_string():
+    L = _lib.lib()
+    assert L.enerf_abi_version() == 1
+    assert isinstance(L.enerf_last_error(), bytes)
+    assert _lib.launch_count() >= 0
+
+
+def test_argument_validation_needs_no_gpu():
+    # bad arguments are rejected before any CUDA call, with a readable message
+    L = _lib.lib()
+    rc = L.enerf_sh_encode_forward(None, None, 4, 3, 9, 0, None, 0, None)
+    assert rc != 0 and b"degree" in L.enerf_last_error()
+    rc = L.enerf_ffmlp_forward(None, None, 128, 32, 16, 48, 2, 0, 6, None, None, None)
+    assert rc != 0 and b"hidden_dim" in L.enerf_last_error()
+    rc = L.enerf_grid_encode_forward(None, None, None, None, 8, 3, 3, 16, 0.5, 16, 0, None, 0, 0, 0, None)
+    assert rc != 0 and b"C must be" in L.enerf_last_error()
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful without a GPU")
+def test_product_path_has_no_cpu_fallback():
+    from enerf_b200 import gridencoder, raymarching, shencoder
+    enc = gridencoder.GridEncoder(num_levels=2, log2_hashmap_size=10)
+    with pytest.raises(RuntimeError):
+        enc(torch.rand(8, 3))
+    with pytest.raises(RuntimeError):
+        shencoder.SHEncoder()(torch.rand(8, 3))
+    with pytest.raises((RuntimeError, AssertionError)):
+        raymarching.near_far_from_aabb(torch.rand(8, 3), torch.rand(8, 3), torch.tensor([-1., -1, -1, 1, 1, 1]), 0.2)
+
+
+def test_dropin_packages_expose_reference_names():
+    from enerf_b200 import ffmlp, gridencoder, raymarching, shencoder
+    for name in ["near_far_from_aabb", "polar_from_ray", "morton3D", "morton3D_invert", "packbits", "march_rays_train",
+                 "composite_rays_train", "march_rays", "composite_rays", "compact_rays"]:
+        assert callable(getattr(raymarching, name))
+    assert hasattr(gridencoder, "GridEncoder") and hasattr(gridencoder, "grid_encode")
+    assert hasattr(shencoder, "SHEncoder") and hasattr(shencoder, "sh_encode")
+    assert hasattr(ffmlp, "FFMLP") and hasattr(ffmlp, "ffmlp_forward")
+    from enerf_b200 import backends
+    for obj, names in [(backends.raymarching_backend, ["packbits", "near_far_from_aabb", "polar_from_ray", "morton3D", "morton3D_invert",
+                                                       "march_rays_train", "composite_rays_train_forward", "composite_rays_train_backward",
+                                                       "march_rays", "composite_rays", "compact_rays"]),
+                       (backends.gridencoder_backend, ["grid_encode_forward", "grid_encode_backward"]),
+                       (backends.shencoder_backend, ["sh_encode_forward", "sh_encode_backward"]),
+                       (backends.ffmlp_backend, ["ffmlp_forward", "ffmlp_inference", "ffmlp_backward", "allocate_splitk", "free_splitk"])]:
+        for n in names:
+            assert callable(getattr(obj, n)), n

@@ -1,0 +1,139 @@
+"""GPU parity: fully-fused MLP vs the float64 oracle and the reference's CUDA build.
+
+Tolerance: operands are fp16, this implementation accumulates in fp32 and stores activations in
+fp16, the oracle accumulates exactly.  Outputs/activations: |diff| <= 2e-3 * max|value| + 1 fp16
+ulp; weight gradients (sums over the batch): <= 1e-3 * max|grad|.  The reference accumulates in
+fp16, so it is compared with a looser 3e-2 * max|value| bound and must not be closer to the exact
+result than this implementation by more than noise."""
+import numpy as np
+import pytest
+import torch
+
+from enerf_b200 import ffmlp
+from enerf_b200.backends import ffmlp_backend as FB
+from oracle import oracle
+from tests.gpu_common import DEV, n, ref_mod, t
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(B, I, W, nl, seed=0, gscale=0.1):
+    rng = np.random.default_rng(seed)
+    nw = W * (I + W * (nl - 1) + 16)
+    w = (rng.uniform(-1, 1, nw) * np.sqrt(3 / W)).astype(np.float16)
+    x = (rng.normal(size=(B, I)) * 0.5).astype(np.float16)
+    g = (rng.normal(size=(B, 16)) * gscale).astype(np.float16)
+    return w, x, g
+
+
+def _close(got, want, rel, name):
+    got = got.astype(np.float64)
+    lim = rel * np.abs(want).max() + 1e-3 * rel
+    err = np.abs(got - want).max()
+    assert err <= lim, f"{name}: max err {err:.3e} > {lim:.3e} (max |want| {np.abs(want).max():.3e})"
+
+
+@pytest.mark.parametrize("B,I,W,nl", [(1024, 32, 64, 2), (4096 + 128, 32, 64, 3), (256, 16, 16, 2), (384, 48, 32, 4), (512, 64, 128, 2),
+                                      (256, 32, 256, 2), (128, 128, 64, 2)])
+def test_forward_inference_backward_vs_oracle(B, I, W, nl):
+    w, x, g = _case(B, I, W, nl, seed=B + W)
+    y, fb = oracle.ffmlp_forward(x, w, I, W, nl)
+    gx, gw, bb = oracle.ffmlp_backward(g, x, w, fb, I, W, nl)
+    tx, tw, tg = t(x), t(w), t(g)
+    out = torch.empty(B, 16, device=DEV, dtype=torch.half)
+    fbuf = torch.empty(nl, B, W, device=DEV, dtype=torch.half)
+    FB.ffmlp_forward(tx, tw, B, I, 16, W, nl, 0, 6, fbuf, out)
+    _close(n(out), y, 2e-3, "outputs")
+    _close(n(fbuf), fb.astype(np.float64), 2e-3, "forward_buffer")
+    out2 = torch.empty_like(out)
+    FB.ffmlp_inference(tx, tw, B, I, 16, W, nl, 0, 6, torch.empty(B, W, device=DEV, dtype=torch.half), out2)
+    assert torch.equal(out, out2)
+    # backward on the oracle's forward_buffer so that ReLU masks are identical
+    tfb = t(fb)
+    bbuf = torch.empty(nl, B, W, device=DEV, dtype=torch.half)
+    gin = torch.empty(B, I, device=DEV, dtype=torch.half)
+    gwt = torch.empty(len(w), device=DEV, dtype=torch.float32)
+    FB.ffmlp_backward(tg, tx, tw, tfb, B, I, 16, W, nl, 0, 6, True, bbuf, gin, gwt)
+    _close(n(bbuf), bb.astype(np.float64), 3e-3, "backward_buffer")
+    _close(n(gin), gx, 3e-3, "grad_inputs")
+    _close(n(gwt), gw, 1e-3, "grad_weights(fp32)")
+    gwh = torch.empty(len(w), device=DEV, dtype=torch.half)
+    FB.ffmlp_backward(tg, tx, tw, tfb, B, I, 16, W, nl, 0, 6, False, bbuf, torch.empty(1, device=DEV, dtype=torch.half), gwh)
+    _close(n(gwh), gw, 2e-3, "grad_weights(fp16)")
+
+
+@pytest.mark.parametrize("nl", [2, 3])
+def test_vs_reference_build(nl):
+    R = ref_mod("_ffmlp")
+    if R is None:
+        pytest.skip("oracle/_ref not built")
+    B, I, W = 8192, 32, 64
+    w, x, g = _case(B, I, W, nl, seed=nl)
+    y, fb = oracle.ffmlp_forward(x, w, I, W, nl)
+    tx, tw, tg = t(x), t(w), t(g)
+    R.allocate_splitk(nl + 1)
+    rout, rfb = torch.empty(B, 16, device=DEV, dtype=torch.half), torch.empty(nl, B, W, device=DEV, dtype=torch.half)
+    R.ffmlp_forward(tx, tw, B, I, 16, W, nl, 0, 6, rfb, rout)
+    gout, gfb = torch.empty_like(rout), torch.empty_like(rfb)
+    FB.ffmlp_forward(tx, tw, B, I, 16, W, nl, 0, 6, gfb, gout)
+    torch.cuda.synchronize()
+    e_ref = np.abs(n(rout).astype(np.float64) - y).max()
+    e_our = np.abs(n(gout).astype(np.float64) - y).max()
+    assert e_our <= e_ref + 1e-3, f"ours {e_our} vs reference {e_ref} (distance to the exact result)"
+    _close(n(gout), n(rout).astype(np.float64), 3e-2, "outputs vs reference")
+    _close(n(gfb), n(rfb).astype(np.float64), 3e-2, "forward_buffer vs reference")
+    # backward from the same stored activations
+    rbb, rgi, rgw = torch.zeros(nl, B, W, device=DEV, dtype=torch.half), torch.zeros(B, I, device=DEV, dtype=torch.half), torch.zeros(len(w), device=DEV, dtype=torch.half)
+    R.ffmlp_backward(tg, tx, tw, rfb, B, I, 16, W, nl, 0, 6, True, rbb, rgi, rgw)
+    gbb, ggi, ggw = torch.empty_like(rbb), torch.empty_like(rgi), torch.empty(len(w), device=DEV, dtype=torch.float32)
+    FB.ffmlp_backward(tg, tx, tw, rfb, B, I, 16, W, nl, 0, 6, True, gbb, ggi, ggw)
+    torch.cuda.synchronize()
+    gx, gw, bb = oracle.ffmlp_backward(g, x, w, n(rfb), I, W, nl)
+    _close(n(gbb), n(rbb).astype(np.float64), 3e-2, "backward_buffer vs reference")
+    _close(n(ggi), n(rgi).astype(np.float64), 3e-2, "grad_inputs vs reference")
+    e_ref = np.abs(n(rgw).astype(np.float64) - gw).max()
+    e_our = np.abs(n(ggw).astype(np.float64) - gw).max()
+    assert e_our <= e_ref + 1e-3 * np.abs(gw).max(), f"grad_weights: ours {e_our} vs reference {e_ref}"
+    _close(n(ggw), n(rgw).astype(np.float64), 5e-2, "grad_weights vs reference")
+
+
+def test_module_matches_reference_semantics():
+    torch.manual_seed(123)
+    net = ffmlp.FFMLP(32, 3, 64, 3).to(DEV)
+    # same init as the reference: manual_seed(42), U(-sqrt(3/64), sqrt(3/64))   (ffmlp.py:141-144)
+    torch.manual_seed(42)
+    want_w = torch.empty(64 * (32 + 64 * 2 + 16)).uniform_(-(3 / 64) ** 0.5, (3 / 64) ** 0.5)
+    assert torch.equal(net.weights.detach().cpu(), want_w)
+    x = torch.randn(1000, 32, device=DEV, requires_grad=True)        # 1000 is not a multiple of 128: padded inside
+    net.train()
+    with torch.autocast("cuda", dtype=torch.float16):
+        y = net(x)
+    assert y.shape == (1000, 3) and y.dtype == torch.float16
+    gy = torch.randn_like(y, dtype=torch.float32)
+    (y.float() * gy).sum().backward()
+    wh = n(net.weights.detach().half())
+    yo, fb = oracle.ffmlp_forward(n(x.detach().half()), wh, 32, 64, 3)
+    _close(n(y), yo[:, :3], 2e-3, "module outputs")
+    g16 = np.zeros((1000, 16), np.float16)
+    g16[:, :3] = n(gy).astype(np.float16)
+    gx, gw, _ = oracle.ffmlp_backward(g16, n(x.detach().half()), wh, fb, 32, 64, 3)
+    _close(n(net.weights.grad), gw, 3e-3, "module grad_weights")
+    _close(n(x.grad), gx, 5e-3, "module grad_inputs")
+    net.eval()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        y2 = net(x.detach())
+    assert torch.equal(y2, y.detach())
+
+
+def test_bad_arguments_raise():
+    with pytest.raises(AssertionError):
+        ffmlp.FFMLP(32, 3, 48, 2)
+    with pytest.raises(AssertionError):
+        ffmlp.FFMLP(30, 3, 64, 2)
+    out = torch.empty(100, 16, device=DEV, dtype=torch.half)
+    with pytest.raises(RuntimeError, match="multiple of 128"):
+        FB.ffmlp_inference(torch.zeros(100, 32, device=DEV, dtype=torch.half), torch.zeros(64 * (32 + 64 + 16), device=DEV, dtype=torch.half),
+                           100, 32, 16, 64, 2, 0, 6, None, out)
+    with pytest.raises(RuntimeError, match="Half"):
+        FB.ffmlp_inference(torch.zeros(128, 32, device=DEV), torch.zeros(64 * (32 + 64 + 16), device=DEV, dtype=torch.half), 128, 32, 16, 64, 2, 0,
+                           6, None, torch.empty(128, 16, device=DEV, dtype=torch.half))
