@@ -77,6 +77,38 @@ def check(rc):
         raise RuntimeError("enerf_b200: " + lib().enerf_last_error().decode())
 
 
+# ---- optional per-call device timing (bench.py's roofline leg) --------------------------------
+_prof = None   # None, or dict name -> list of (start_event, end_event)
+
+
+def profile_start():
+    """Record a CUDA event pair around every C-ABI call from now on (current stream)."""
+    global _prof
+    _prof = {}
+
+
+def profile_stop():
+    """Stop recording; returns {entry point: (n_calls, total_ms)} after synchronising."""
+    global _prof
+    rec, _prof = _prof, None
+    torch.cuda.synchronize()
+    return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (rec or {}).items()}
+
+
+def call(name, *args):
+    """Invoke a C-ABI entry point and raise on failure."""
+    fn = getattr(lib(), name)
+    if _prof is None:
+        check(fn(*args))
+        return
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    rc = fn(*args)
+    b.record()
+    _prof.setdefault(name, []).append((a, b))
+    check(rc)
+
+
 def launch_count():
     return int(lib().enerf_launch_count())
 

@@ -24,69 +24,69 @@ class _Raymarching:
     @staticmethod
     def near_far_from_aabb(rays_o, rays_d, aabb, N, min_near, nears, fars):
         need_cuda(rays_o, rays_d, aabb, nears, fars)
-        check(_lib.lib().enerf_near_far_from_aabb(ptr(rays_o), ptr(rays_d), ptr(aabb), N, min_near, ptr(nears), ptr(fars), stream()))
+        _lib.call("enerf_near_far_from_aabb", ptr(rays_o), ptr(rays_d), ptr(aabb), N, min_near, ptr(nears), ptr(fars), stream())
 
     @staticmethod
     def polar_from_ray(rays_o, rays_d, radius, N, coords):
         need_cuda(rays_o, rays_d, coords)
-        check(_lib.lib().enerf_polar_from_ray(ptr(rays_o), ptr(rays_d), radius, N, ptr(coords), stream()))
+        _lib.call("enerf_polar_from_ray", ptr(rays_o), ptr(rays_d), radius, N, ptr(coords), stream())
 
     @staticmethod
     def morton3D(coords, N, indices):
         need_cuda(coords, indices)
-        check(_lib.lib().enerf_morton3D(ptr(coords), N, ptr(indices), stream()))
+        _lib.call("enerf_morton3D", ptr(coords), N, ptr(indices), stream())
 
     @staticmethod
     def morton3D_invert(indices, N, coords):
         need_cuda(indices, coords)
-        check(_lib.lib().enerf_morton3D_invert(ptr(indices), N, ptr(coords), stream()))
+        _lib.call("enerf_morton3D_invert", ptr(indices), N, ptr(coords), stream())
 
     @staticmethod
     def packbits(grid, N, density_thresh, bitfield):
         need_cuda(grid, bitfield)
-        check(_lib.lib().enerf_packbits(ptr(grid), N, density_thresh, ptr(bitfield), stream()))
+        _lib.call("enerf_packbits", ptr(grid), N, density_thresh, ptr(bitfield), stream())
 
     @staticmethod
     def march_rays_train(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, xyzs, dirs, deltas, rays, counter, perturb):
         need_cuda(rays_o, rays_d, grid, nears, fars, xyzs, dirs, deltas, rays, counter)
-        check(_lib.lib().enerf_march_rays_train(ptr(rays_o), ptr(rays_d), ptr(grid), bound, dt_gamma, max_steps, N, C, H, M,
+        _lib.call("enerf_march_rays_train", ptr(rays_o), ptr(rays_d), ptr(grid), bound, dt_gamma, max_steps, N, C, H, M,
                                                 ptr(nears), ptr(fars), ptr(xyzs), ptr(dirs), ptr(deltas), ptr(rays), ptr(counter),
-                                                int(perturb), stream()))
+                                                int(perturb), stream())
 
     @staticmethod
     def composite_rays_train_forward(sigmas, rgbs, deltas, rays, M, N, weights_sum, depth, image):
         need_cuda(sigmas, rgbs, deltas, rays, weights_sum, depth, image)
         n_ch = rgbs.shape[-1] if rgbs.dim() > 1 else 1
-        check(_lib.lib().enerf_composite_rays_train_forward(ptr(sigmas), ptr(rgbs), ptr(deltas), ptr(rays), M, N, n_ch,
-                                                            ptr(weights_sum), ptr(depth), ptr(image), stream()))
+        _lib.call("enerf_composite_rays_train_forward", ptr(sigmas), ptr(rgbs), ptr(deltas), ptr(rays), M, N, n_ch,
+                                                            ptr(weights_sum), ptr(depth), ptr(image), stream())
 
     @staticmethod
     def composite_rays_train_backward(grad_weights_sum, grad_image, sigmas, rgbs, deltas, rays, weights_sum, image, M, N, grad_sigmas, grad_rgbs):
         need_cuda(grad_weights_sum, grad_image, sigmas, rgbs, deltas, rays, weights_sum, image, grad_sigmas, grad_rgbs)
         n_ch = rgbs.shape[-1] if rgbs.dim() > 1 else 1
-        check(_lib.lib().enerf_composite_rays_train_backward(ptr(grad_weights_sum), ptr(grad_image), ptr(sigmas), ptr(rgbs), ptr(deltas),
+        _lib.call("enerf_composite_rays_train_backward", ptr(grad_weights_sum), ptr(grad_image), ptr(sigmas), ptr(rgbs), ptr(deltas),
                                                              ptr(rays), ptr(weights_sum), ptr(image), M, N, n_ch, ptr(grad_sigmas),
-                                                             ptr(grad_rgbs), stream()))
+                                                             ptr(grad_rgbs), stream())
 
     @staticmethod
     def march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid, nears, fars, xyzs, dirs, deltas, perturb):
         need_cuda(rays_alive, rays_t, rays_o, rays_d, grid, nears, fars, xyzs, dirs, deltas)
-        check(_lib.lib().enerf_march_rays(n_alive, n_step, ptr(rays_alive), ptr(rays_t), ptr(rays_o), ptr(rays_d), bound, dt_gamma,
+        _lib.call("enerf_march_rays", n_alive, n_step, ptr(rays_alive), ptr(rays_t), ptr(rays_o), ptr(rays_d), bound, dt_gamma,
                                           max_steps, C, H, ptr(grid), ptr(nears), ptr(fars), ptr(xyzs), ptr(dirs), ptr(deltas),
-                                          int(perturb), stream()))
+                                          int(perturb), stream())
 
     @staticmethod
     def composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image):
         need_cuda(rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image)
         n_ch = rgbs.shape[-1] if rgbs.dim() > 1 else 1
-        check(_lib.lib().enerf_composite_rays(n_alive, n_step, ptr(rays_alive), ptr(rays_t), ptr(sigmas), ptr(rgbs), ptr(deltas), n_ch,
-                                              ptr(weights_sum), ptr(depth), ptr(image), stream()))
+        _lib.call("enerf_composite_rays", n_alive, n_step, ptr(rays_alive), ptr(rays_t), ptr(sigmas), ptr(rgbs), ptr(deltas), n_ch,
+                                              ptr(weights_sum), ptr(depth), ptr(image), stream())
 
     @staticmethod
     def compact_rays(n_alive, rays_alive, rays_alive_old, rays_t, rays_t_old, alive_counter):
         need_cuda(rays_alive, rays_alive_old, rays_t, rays_t_old, alive_counter)
-        check(_lib.lib().enerf_compact_rays(n_alive, ptr(rays_alive), ptr(rays_alive_old), ptr(rays_t), ptr(rays_t_old),
-                                            ptr(alive_counter), stream()))
+        _lib.call("enerf_compact_rays", n_alive, ptr(rays_alive), ptr(rays_alive_old), ptr(rays_t), ptr(rays_t_old),
+                                            ptr(alive_counter), stream())
 
 
 class _GridEncoder:
@@ -108,17 +108,17 @@ class _GridEncoder:
     def grid_encode_forward(inputs, embeddings, offsets, outputs, B, D, C, L, S, H, calc_grad_inputs, dy_dx, gridtype, out_layout=0):
         _GridEncoder._check(inputs, embeddings, offsets, outputs, dy_dx)
         _contig("outputs", outputs)
-        check(_lib.lib().enerf_grid_encode_forward(ptr(inputs), ptr(embeddings), ptr(offsets), ptr(outputs), B, D, C, L, float(S), H,
-                                                   int(calc_grad_inputs), ptr(dy_dx), gridtype, dtype_code(embeddings), out_layout, stream()))
+        _lib.call("enerf_grid_encode_forward", ptr(inputs), ptr(embeddings), ptr(offsets), ptr(outputs), B, D, C, L, float(S), H,
+                                                   int(calc_grad_inputs), ptr(dy_dx), gridtype, dtype_code(embeddings), out_layout, stream())
 
     @staticmethod
     def grid_encode_backward(grad, inputs, embeddings, offsets, grad_embeddings, B, D, C, L, S, H, calc_grad_inputs, dy_dx, grad_inputs, gridtype, out_layout=0):
         _GridEncoder._check(inputs, embeddings, offsets, grad, grad_embeddings, dy_dx, grad_inputs)
         _contig("grad", grad)
         _contig("grad_embeddings", grad_embeddings)
-        check(_lib.lib().enerf_grid_encode_backward(ptr(grad), ptr(inputs), ptr(embeddings), ptr(offsets), ptr(grad_embeddings), B, D, C, L,
+        _lib.call("enerf_grid_encode_backward", ptr(grad), ptr(inputs), ptr(embeddings), ptr(offsets), ptr(grad_embeddings), B, D, C, L,
                                                     float(S), H, int(calc_grad_inputs), ptr(dy_dx), ptr(grad_inputs), gridtype,
-                                                    dtype_code(grad), dtype_code(grad_embeddings), out_layout, stream()))
+                                                    dtype_code(grad), dtype_code(grad_embeddings), out_layout, stream())
 
 
 class _SHEncoder:
@@ -129,13 +129,13 @@ class _SHEncoder:
         need_cuda(inputs, outputs, dy_dx)
         _contig("inputs", inputs)
         _contig("outputs", outputs)
-        check(_lib.lib().enerf_sh_encode_forward(ptr(inputs), ptr(outputs), B, D, C, int(calc_grad_inputs), ptr(dy_dx), dtype_code(inputs), stream()))
+        _lib.call("enerf_sh_encode_forward", ptr(inputs), ptr(outputs), B, D, C, int(calc_grad_inputs), ptr(dy_dx), dtype_code(inputs), stream())
 
     @staticmethod
     def sh_encode_backward(grad, inputs, B, D, C, dy_dx, grad_inputs):
         need_cuda(grad, inputs, dy_dx, grad_inputs)
         _contig("grad", grad)
-        check(_lib.lib().enerf_sh_encode_backward(ptr(grad), ptr(inputs), B, D, C, ptr(dy_dx), ptr(grad_inputs), dtype_code(grad), stream()))
+        _lib.call("enerf_sh_encode_backward", ptr(grad), ptr(inputs), B, D, C, ptr(dy_dx), ptr(grad_inputs), dtype_code(grad), stream())
 
 
 class _FFMLP:
@@ -154,15 +154,15 @@ class _FFMLP:
     def ffmlp_forward(inputs, weights, B, input_dim, output_dim, hidden_dim, num_layers, activation, output_activation, forward_buffer, outputs):
         _FFMLP._half("inputs", inputs)
         _FFMLP._half("weights", weights)
-        check(_lib.lib().enerf_ffmlp_forward(ptr(inputs), ptr(weights), B, input_dim, output_dim, hidden_dim, num_layers, activation,
-                                             output_activation, ptr(forward_buffer), ptr(outputs), stream()))
+        _lib.call("enerf_ffmlp_forward", ptr(inputs), ptr(weights), B, input_dim, output_dim, hidden_dim, num_layers, activation,
+                                             output_activation, ptr(forward_buffer), ptr(outputs), stream())
 
     @staticmethod
     def ffmlp_inference(inputs, weights, B, input_dim, output_dim, hidden_dim, num_layers, activation, output_activation, inference_buffer, outputs):
         _FFMLP._half("inputs", inputs)
         _FFMLP._half("weights", weights)
-        check(_lib.lib().enerf_ffmlp_inference(ptr(inputs), ptr(weights), B, input_dim, output_dim, hidden_dim, num_layers, activation,
-                                               output_activation, ptr(inference_buffer), ptr(outputs), stream()))
+        _lib.call("enerf_ffmlp_inference", ptr(inputs), ptr(weights), B, input_dim, output_dim, hidden_dim, num_layers, activation,
+                                               output_activation, ptr(inference_buffer), ptr(outputs), stream())
 
     @staticmethod
     def ffmlp_backward(grad, inputs, weights, forward_buffer, B, input_dim, output_dim, hidden_dim, num_layers, activation, output_activation,
@@ -176,17 +176,17 @@ class _FFMLP:
             scratch = grad_weights
         else:
             scratch = torch.empty(weights.numel(), dtype=torch.float32, device=weights.device)
-        check(_lib.lib().enerf_ffmlp_backward(ptr(grad), ptr(inputs), ptr(weights), ptr(forward_buffer), B, input_dim, output_dim, hidden_dim,
+        _lib.call("enerf_ffmlp_backward", ptr(grad), ptr(inputs), ptr(weights), ptr(forward_buffer), B, input_dim, output_dim, hidden_dim,
                                               num_layers, activation, output_activation, int(calc_grad_inputs), ptr(backward_buffer),
-                                              ptr(grad_inputs), ptr(grad_weights), dtype_code(grad_weights), ptr(scratch), stream()))
+                                              ptr(grad_inputs), ptr(grad_weights), dtype_code(grad_weights), ptr(scratch), stream())
 
     @staticmethod
     def allocate_splitk(size):
-        check(_lib.lib().enerf_allocate_splitk(int(size)))
+        _lib.call("enerf_allocate_splitk", int(size))
 
     @staticmethod
     def free_splitk():
-        check(_lib.lib().enerf_free_splitk())
+        _lib.call("enerf_free_splitk", )
 
 
 raymarching_backend = _Raymarching()

@@ -299,7 +299,7 @@ k_march_rays_train(const float* __restrict__ rays_o, const float* __restrict__ r
     float t0 = near;
     if (perturb) {
         Pcg32 rng((uint64_t)n, 1u);
-        t0 += c.dt_min * rng.next_float();
+        t0 = __fmaf_rn(c.dt_min, rng.next_float(), t0);   // the reference's `t0 += dt_min * r` is contracted by nvcc
     }
     const uint32_t num_steps = march_warp<false>(r, c, grid, t0, far, max_steps, nullptr, nullptr, nullptr);
 
@@ -333,7 +333,7 @@ k_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* __restrict__ rays
     const float far = fars[index];
     if (perturb) {
         Pcg32 rng((uint64_t)n, (uint64_t)perturb);  // seeded by the alive SLOT, raymarching.cu:743
-        t += c.dt_min * rng.next_float();
+        t = __fmaf_rn(c.dt_min, rng.next_float(), t);
     }
     const size_t base = (size_t)n * n_step;
     march_warp<true>(r, c, grid, t, far, n_step, xyzs + base * 3, dirs + base * 3, deltas + base * 2);

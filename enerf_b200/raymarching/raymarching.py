@@ -225,3 +225,46 @@ class _compact_rays(Function):
 
 
 compact_rays = _compact_rays.apply
+
+
+# ---------------------------------------------------------------------------- fused run() integrator
+class _composite_uniform(Function):
+    """Fixed-step integrator of NeRFRenderer.run (nerf/renderer.py:230-255) as one kernel:
+    (sigmas [N,T], z_vals [N,T], nears [N], fars [N], density_scale) -> weights [N,T],
+    weights_sum [N], depth [N].  Differentiable in sigmas.  No reference ABI (extension)."""
+
+    @staticmethod
+    @_fwd32
+    def forward(ctx, sigmas, z_vals, nears, fars, density_scale=1.0):
+        from .. import _lib
+        sigmas, z_vals = sigmas.contiguous(), z_vals.contiguous()
+        nears, fars = nears.contiguous().view(-1), fars.contiguous().view(-1)
+        _lib.need_cuda(sigmas, z_vals, nears, fars)
+        N, T = sigmas.shape
+        weights = torch.empty_like(sigmas)
+        weights_sum = torch.empty(N, dtype=sigmas.dtype, device=sigmas.device)
+        depth = torch.empty(N, dtype=sigmas.dtype, device=sigmas.device)
+        _lib._lib.call("enerf_composite_uniform_forward", _lib.ptr(sigmas), _lib.ptr(z_vals), _lib.ptr(nears), _lib.ptr(fars), N, T,
+                                                              float(density_scale), _lib.ptr(weights), _lib.ptr(weights_sum),
+                                                              _lib.ptr(depth), _lib.stream())
+        ctx.save_for_backward(sigmas, z_vals, nears, fars)
+        ctx.density_scale = float(density_scale)
+        return weights, weights_sum, depth
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, grad_weights, grad_weights_sum, grad_depth):
+        from .. import _lib
+        sigmas, z_vals, nears, fars = ctx.saved_tensors
+        N, T = sigmas.shape
+        gw = None if grad_weights is None else grad_weights.contiguous().float()
+        gs = None if grad_weights_sum is None else grad_weights_sum.contiguous().float()
+        gd = None if grad_depth is None else grad_depth.contiguous().float()
+        grad_sigmas = torch.empty_like(sigmas)
+        _lib._lib.call("enerf_composite_uniform_backward", _lib.ptr(gw), _lib.ptr(gs), _lib.ptr(gd), _lib.ptr(sigmas), _lib.ptr(z_vals),
+                                                               _lib.ptr(nears), _lib.ptr(fars), N, T, ctx.density_scale,
+                                                               _lib.ptr(grad_sigmas), _lib.stream())
+        return grad_sigmas, None, None, None, None
+
+
+composite_uniform = _composite_uniform.apply

@@ -226,7 +226,7 @@ void oracle_march_rays_train(const float* rays_o, const float* rays_d, const uin
         if (perturb) {
             pcg32_t rng;
             pcg32_seed(&rng, (uint64_t)n, 1u);
-            t0 += m.dt_min * pcg32_float(&rng);
+            t0 = fmaf(m.dt_min, pcg32_float(&rng), t0);   /* nvcc contracts `t0 += dt_min * r` (verified against the reference build) */
         }
         const uint32_t num_steps = march_one(&m, t0, fars[n], max_steps, NULL, NULL, NULL);
         const uint32_t point_index = (uint32_t)counter[0];
@@ -257,7 +257,7 @@ void oracle_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_al
         if (perturb) {
             pcg32_t rng;
             pcg32_seed(&rng, (uint64_t)n, (uint64_t)perturb);
-            t += m.dt_min * pcg32_float(&rng);
+            t = fmaf(m.dt_min, pcg32_float(&rng), t);
         }
         march_one(&m, t, fars[index], n_step, xyzs + 3 * (size_t)n * n_step, dirs + 3 * (size_t)n * n_step, deltas + 2 * (size_t)n * n_step);
     }
@@ -465,7 +465,9 @@ GRID_IMPL(oracle_grid_encode_forward_f16, half_t, *r = (half_t)((float)*r + (flo
 void oracle_grid_encode_backward(const float* grad, const float* inputs, const int32_t* offsets, double* grad_grid, uint32_t B,
                                  uint32_t D, uint32_t Cc, uint32_t L, float S, uint32_t H, uint32_t gridtype, int mode,
                                  const float* level_scales) {
-    for (uint32_t level = 0; level < L; level++) {
+    /* levels own disjoint slices of grad_grid -> race-free across threads */
+    _Pragma("omp parallel for schedule(dynamic, 1)") for (int64_t lv = 0; lv < (int64_t)L; lv++) {
+        const uint32_t level = (uint32_t)lv;
         double* gg = grad_grid + (size_t)(uint32_t)offsets[level] * Cc;
         const uint32_t hashmap_size = (uint32_t)(offsets[level + 1] - offsets[level]);
         const float scale = level_scales ? level_scales[level] : exp2f(level * S) * H - 1.0f;
