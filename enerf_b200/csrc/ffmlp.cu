@@ -347,6 +347,16 @@ static int check_dims(const char* name, uint32_t B, uint32_t input_dim, uint32_t
     }
 
 }  // namespace mlp
+
+namespace tcm {
+int tc_forward(const __half* in, const __half* W, uint32_t B, int in_dim, int n_hidden_mm, __half* fwd_buf, __half* out, cudaStream_t st,
+               const char* name);
+}
+static int g_mlp_path = 0;   // 0: tcgen05 kernels when eligible, 1: always the generic mma.sync kernels
+static bool tc_eligible(uint32_t input_dim, uint32_t hidden_dim, uint32_t num_layers, uint32_t activation, uint32_t output_activation) {
+    return g_mlp_path == 0 && hidden_dim == 64 && input_dim <= 64 && activation == ENERF_ACT_RELU && output_activation == ENERF_ACT_NONE &&
+           num_layers <= 8;
+}
 }  // namespace enerf
 
 using namespace enerf;
@@ -360,6 +370,9 @@ int enerf_ffmlp_forward(const uint16_t* inputs, const uint16_t* weights, uint32_
     if (int rc = check_dims("ffmlp_forward", B, input_dim, output_dim, hidden_dim, num_layers)) return rc;
     if (B == 0) return 0;
     ENERF_REQUIRE(forward_buffer != nullptr, "ffmlp_forward", "forward_buffer must not be NULL (use ffmlp_inference)");
+    if (tc_eligible(input_dim, hidden_dim, num_layers, activation, output_activation))
+        return tcm::tc_forward((const __half*)inputs, (const __half*)weights, B, (int)input_dim, (int)num_layers - 1, (__half*)forward_buffer,
+                               (__half*)outputs, as_stream(stream), "ffmlp_forward");
     int rc = 0;
     ENERF_WIDTH_SWITCH(hidden_dim, rc = run_fwd<WW>((const __half*)inputs, (const __half*)weights, B, (int)input_dim, (int)num_layers - 1, activation,
                                                     output_activation, (__half*)forward_buffer, (__half*)outputs, as_stream(stream), "ffmlp_forward"));
@@ -372,6 +385,9 @@ int enerf_ffmlp_inference(const uint16_t* inputs, const uint16_t* weights, uint3
     (void)inference_buffer;
     if (int rc = check_dims("ffmlp_inference", B, input_dim, output_dim, hidden_dim, num_layers)) return rc;
     if (B == 0) return 0;
+    if (tc_eligible(input_dim, hidden_dim, num_layers, activation, output_activation))
+        return tcm::tc_forward((const __half*)inputs, (const __half*)weights, B, (int)input_dim, (int)num_layers - 1, nullptr, (__half*)outputs,
+                               as_stream(stream), "ffmlp_inference");
     int rc = 0;
     ENERF_WIDTH_SWITCH(hidden_dim, rc = run_fwd<WW>((const __half*)inputs, (const __half*)weights, B, (int)input_dim, (int)num_layers - 1, activation,
                                                     output_activation, nullptr, (__half*)outputs, as_stream(stream), "ffmlp_inference"));
@@ -416,6 +432,12 @@ int enerf_ffmlp_backward(const uint16_t* grad, const uint16_t* inputs, const uin
     } else if ((void*)scratch != grad_weights) {
         ENERF_CUDA(cudaMemcpyAsync(grad_weights, scratch, n_w * sizeof(float), cudaMemcpyDeviceToDevice, st), "ffmlp_backward");
     }
+    return 0;
+}
+
+int enerf_ffmlp_set_path(int path) {
+    ENERF_REQUIRE(path == 0 || path == 1, "ffmlp_set_path", "path must be 0 (auto) or 1 (generic mma.sync kernels)");
+    g_mlp_path = path;
     return 0;
 }
 

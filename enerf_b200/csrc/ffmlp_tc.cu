@@ -1,0 +1,190 @@
+// Fully-fused 64-wide MLP on the 5th-generation tensor cores (tcgen05) with TMEM-resident
+// activations — the path E-NeRF's networks (sigma-net 32-64-64-16, colour-net 32-64-64-64-16)
+// take.  Other shapes use the mma.sync kernels in ffmlp.cu.
+//
+// Forward / inference (k_tc_fwd)
+//   CTA = 1 MMA warp + NSLOTS x 4 epilogue warps, persistent over 128-sample tiles; NSLOTS tiles
+//   are in flight per CTA so the tensor pipe works on one tile while the epilogue warps of the
+//   other(s) run.  Per tile:
+//     epilogue warps: global row (fp16) -> registers -> tcgen05.st -> A operand in TMEM
+//     MMA thread    : tcgen05.mma  D[128 x 64] (TMEM, fp32) = A[TMEM] x W_k^T [smem, K-major]
+//     epilogue warps: tcgen05.ld D -> ReLU -> fp16 pack -> tcgen05.st (next layer's A, never
+//                     leaves the SM) [+ 128-B row store to forward_buffer when training]
+//     ... last layer N = 16 -> fp16 row store of the 16 outputs.
+//   Weights are staged once per CTA in shared memory in the no-swizzle canonical layout
+//   (tc_common.cuh); hand-offs use mbarriers (128 arrivals: "A ready"; tcgen05.commit: "D full").
+#include "tc_common.cuh"
+
+namespace enerf {
+namespace tcm {
+
+using namespace tc;
+
+static constexpr int kW = 64;            // hidden width
+static constexpr int kTile = 128;        // samples per tile = UMMA M
+static constexpr int kSlotCols = 96;     // TMEM columns per slot: D (64, fp32) + A (32 = 64 fp16)
+
+// copy a row-major [rows, K] fp16 matrix into the canonical chunked layout tile[c][r] (16-B chunks)
+__device__ __forceinline__ void stage_matrix(uint8_t* dst, const __half* __restrict__ src, int rows, int K, int tid, int nthreads) {
+    const int cpr = K >> 3;   // chunks per row
+    for (int i = tid; i < rows * cpr; i += nthreads) {
+        const int r = i / cpr, c = i - r * cpr;
+        *reinterpret_cast<int4*>(dst + (size_t)c * rows * 16 + (size_t)r * 16) = __ldg(reinterpret_cast<const int4*>(src) + i);
+    }
+}
+
+template <int NSLOTS>
+__global__ void __launch_bounds__(32 + NSLOTS * 128, 1)
+k_tc_fwd(const __half* __restrict__ in, const __half* __restrict__ W, __half* __restrict__ fwd_buf, __half* __restrict__ out,
+         uint32_t n_tiles, uint32_t B, int in_dim, int n_hidden_mm) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* w0s = smem;                                  // [in_dim/8][64][16 B]
+    uint8_t* whs = w0s + in_dim * 128;                    // n_hidden_mm x [8][64][16 B]
+    uint8_t* wls = whs + n_hidden_mm * 8192;              // [8][16][16 B]
+    uint64_t* a_ready = reinterpret_cast<uint64_t*>(wls + 2048);
+    uint64_t* d_full = a_ready + NSLOTS;
+    uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(d_full + NSLOTS);
+
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    constexpr uint32_t kCols = (NSLOTS * kSlotCols <= 256) ? 256 : 512;
+
+    stage_matrix(w0s, W, kW, in_dim, tid, nthreads);
+    for (int j = 0; j < n_hidden_mm; ++j) stage_matrix(whs + j * 8192, W + kW * in_dim + j * kW * kW, kW, kW, tid, nthreads);
+    stage_matrix(wls, W + kW * in_dim + n_hidden_mm * kW * kW, 16, kW, tid, nthreads);
+    if (tid == 0) {
+        for (int s = 0; s < NSLOTS; ++s) {
+            mbar_init(&a_ready[s], 128);
+            mbar_init(&d_full[s], 1);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_base_ptr, kCols);
+    fence_proxy_async_smem();      // weights written with st.shared are read by the tensor core
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem0 = *tmem_base_ptr;
+
+    const int S = n_hidden_mm + 2;                                     // matmuls per network
+    const uint32_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (warp == 0) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            uint32_t pa[NSLOTS];
+#pragma unroll
+            for (int s = 0; s < NSLOTS; ++s) pa[s] = 0;
+            const uint32_t idesc64 = idesc_f16(kTile, 64, false, false), idesc16 = idesc_f16(kTile, 16, false, false);
+            for (uint32_t j0 = 0; j0 < my_tiles; j0 += NSLOTS) {
+                for (int i = 0; i < S; ++i) {
+                    const int K = (i == 0) ? in_dim : kW;
+                    const bool last = (i == S - 1);
+                    const uint32_t lbo = last ? 16 * 16 : kW * 16;
+                    const uint8_t* wb = (i == 0) ? w0s : (last ? wls : whs + (i - 1) * 8192);
+                    const uint32_t wbase = smem_u32(wb);
+#pragma unroll
+                    for (int s = 0; s < NSLOTS; ++s) {
+                        if (j0 + s >= my_tiles) break;
+                        mbar_wait(&a_ready[s], pa[s]);
+                        pa[s] ^= 1;
+                        tc_fence_after();
+                        const uint32_t d_t = tmem0 + s * kSlotCols, a_t = d_t + 64;
+                        for (int k = 0; k < K / 16; ++k)
+                            mma_ts(d_t, a_t + k * 8, smem_desc(wbase + k * 2 * lbo, lbo, 128), last ? idesc16 : idesc64, k > 0);
+                        tc_commit(&d_full[s]);
+                    }
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue warps =====================
+        const int s = (warp - 1) >> 2;                 // slot
+        const int q = warp & 3;                        // TMEM quarter this warp may access
+        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+        const uint32_t d_t = tmem0 + lane_sel + s * kSlotCols, a_t = d_t + 64;
+        uint32_t pd = 0;
+        for (uint32_t j = s; j < my_tiles; j += NSLOTS) {
+            const size_t tile = (size_t)blockIdx.x + (size_t)j * gridDim.x;
+            const size_t row = tile * kTile + q * 32 + lane;
+            // ---- input row -> TMEM A
+            {
+                const int4* src = reinterpret_cast<const int4*>(in + row * in_dim);
+                for (int c = 0; c < in_dim / 16; ++c) {            // 16 halves = 8 TMEM columns per step
+                    const int4 v0 = __ldg(src + 2 * c), v1 = __ldg(src + 2 * c + 1);
+                    const uint32_t r[8] = {(uint32_t)v0.x, (uint32_t)v0.y, (uint32_t)v0.z, (uint32_t)v0.w,
+                                           (uint32_t)v1.x, (uint32_t)v1.y, (uint32_t)v1.z, (uint32_t)v1.w};
+                    tmem_st8(a_t + c * 8, r);
+                }
+                tc_wait_st();
+                tc_fence_before();
+                mbar_arrive(&a_ready[s]);
+            }
+            for (int i = 0; i < S; ++i) {
+                mbar_wait(&d_full[s], pd);
+                pd ^= 1;
+                tc_fence_after();
+                if (i < S - 1) {
+                    __half* fb = fwd_buf ? fwd_buf + ((size_t)i * B + row) * kW : nullptr;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint32_t acc[32];
+                        tmem_ld32(d_t + h * 32, acc);
+                        tc_wait_ld();
+                        uint32_t p[16];
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) p[e] = pack2(relu(__uint_as_float(acc[2 * e])), relu(__uint_as_float(acc[2 * e + 1])));
+                        tmem_st16(a_t + h * 16, p);
+                        if (fb) {
+                            int4* dst = reinterpret_cast<int4*>(fb + h * 32);
+#pragma unroll
+                            for (int v = 0; v < 4; ++v) dst[v] = make_int4((int)p[4 * v], (int)p[4 * v + 1], (int)p[4 * v + 2], (int)p[4 * v + 3]);
+                        }
+                    }
+                    tc_wait_st();
+                    tc_fence_before();
+                    mbar_arrive(&a_ready[s]);
+                } else {
+                    uint32_t acc[16];
+                    tmem_ld16(d_t, acc);
+                    tc_wait_ld();
+                    uint32_t p[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) p[e] = pack2(__uint_as_float(acc[2 * e]), __uint_as_float(acc[2 * e + 1]));
+                    int4* dst = reinterpret_cast<int4*>(out + row * 16);
+                    dst[0] = make_int4((int)p[0], (int)p[1], (int)p[2], (int)p[3]);
+                    dst[1] = make_int4((int)p[4], (int)p[5], (int)p[6], (int)p[7]);
+                    tc_fence_before();
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem0, kCols);
+}
+
+static size_t fwd_smem_bytes(int in_dim, int n_hidden_mm, int nslots) {
+    return (size_t)in_dim * 128 + (size_t)n_hidden_mm * 8192 + 2048 + (size_t)nslots * 16 + 16;
+}
+
+int tc_forward(const __half* in, const __half* W, uint32_t B, int in_dim, int n_hidden_mm, __half* fwd_buf, __half* out, cudaStream_t st,
+               const char* name) {
+    constexpr int NSLOTS = 4;
+    size_t smem = fwd_smem_bytes(in_dim, n_hidden_mm, NSLOTS);
+    if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: it allocates all 512 TMEM columns
+    if (smem > 200 * 1024) { set_error("%s: network too deep for the tcgen05 path", name); return -2; }
+    static size_t configured = 0;
+    if (smem > configured) {
+        ENERF_CUDA(cudaFuncSetAttribute(k_tc_fwd<NSLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
+        configured = smem;
+    }
+    const uint32_t n_tiles = B / kTile;
+    const uint32_t grid = n_tiles < (uint32_t)kNumSM ? n_tiles : (uint32_t)kNumSM;
+    k_tc_fwd<NSLOTS><<<grid, 32 + NSLOTS * 128, smem, st>>>(in, W, fwd_buf, out, n_tiles, B, in_dim, n_hidden_mm);
+    ENERF_CHECK_LAUNCH(name);
+    return 0;
+}
+
+}  // namespace tcm
+}  // namespace enerf

@@ -244,7 +244,7 @@ class _composite_uniform(Function):
         weights = torch.empty_like(sigmas)
         weights_sum = torch.empty(N, dtype=sigmas.dtype, device=sigmas.device)
         depth = torch.empty(N, dtype=sigmas.dtype, device=sigmas.device)
-        _lib._lib.call("enerf_composite_uniform_forward", _lib.ptr(sigmas), _lib.ptr(z_vals), _lib.ptr(nears), _lib.ptr(fars), N, T,
+        _lib.call("enerf_composite_uniform_forward", _lib.ptr(sigmas), _lib.ptr(z_vals), _lib.ptr(nears), _lib.ptr(fars), N, T,
                                                               float(density_scale), _lib.ptr(weights), _lib.ptr(weights_sum),
                                                               _lib.ptr(depth), _lib.stream())
         ctx.save_for_backward(sigmas, z_vals, nears, fars)
@@ -261,7 +261,7 @@ class _composite_uniform(Function):
         gs = None if grad_weights_sum is None else grad_weights_sum.contiguous().float()
         gd = None if grad_depth is None else grad_depth.contiguous().float()
         grad_sigmas = torch.empty_like(sigmas)
-        _lib._lib.call("enerf_composite_uniform_backward", _lib.ptr(gw), _lib.ptr(gs), _lib.ptr(gd), _lib.ptr(sigmas), _lib.ptr(z_vals),
+        _lib.call("enerf_composite_uniform_backward", _lib.ptr(gw), _lib.ptr(gs), _lib.ptr(gd), _lib.ptr(sigmas), _lib.ptr(z_vals),
                                                                _lib.ptr(nears), _lib.ptr(fars), N, T, ctx.density_scale,
                                                                _lib.ptr(grad_sigmas), _lib.stream())
         return grad_sigmas, None, None, None, None

@@ -165,6 +165,10 @@ int enerf_ffmlp_backward(const uint16_t* grad, const uint16_t* inputs, const uin
  * stream+event per layer for its CUTLASS split-K weight-gradient GEMMs.  The weight gradients
  * are fused into the backward kernel here, so these only validate their argument. */
 int enerf_allocate_splitk(uint64_t size);
+/* Kernel-family selector (no reference counterpart): 0 = automatic — the tcgen05/TMEM kernels for
+ * 64-wide ReLU networks with input_dim <= 64, the mma.sync kernels otherwise; 1 = always the
+ * generic mma.sync kernels (used by the parity tests to cross-check the two families). */
+int enerf_ffmlp_set_path(int path);
 int enerf_free_splitk(void);
 
 /* ---------------------------------------------------- fused extras (no reference ABI) ---- */

@@ -97,6 +97,37 @@ def test_vs_reference_build(nl):
     _close(n(ggw), n(rgw).astype(np.float64), 5e-2, "grad_weights vs reference")
 
 
+@pytest.mark.parametrize("I,nl", [(32, 2), (32, 3), (64, 2), (16, 4), (48, 2)])
+def test_tcgen05_and_mma_sync_paths_agree(I, nl):
+    """The two kernel families (tcgen05/TMEM for 64-wide ReLU nets, generic mma.sync) against the
+    oracle and against each other.  Run under a watchdog: a wrong mbarrier phase would hang."""
+    from enerf_b200 import _lib
+    B, W = 128 * 301, 64          # 301 tiles: more tiles than SMs, odd count per CTA
+    w, x, g = _case(B, I, W, nl, seed=I + nl)
+    y, fb = oracle.ffmlp_forward(x[:2048], w, I, W, nl)
+    tx, tw = t(x), t(w)
+    outs = {}
+    try:
+        for path in (0, 1):
+            _lib.call("enerf_ffmlp_set_path", path)
+            out = torch.zeros(B, 16, device=DEV, dtype=torch.half)
+            fbuf = torch.zeros(nl, B, W, device=DEV, dtype=torch.half)
+            FB.ffmlp_forward(tx, tw, B, I, 16, W, nl, 0, 6, fbuf, out)
+            out_inf = torch.zeros_like(out)
+            FB.ffmlp_inference(tx, tw, B, I, 16, W, nl, 0, 6, None, out_inf)
+            torch.cuda.synchronize()
+            assert torch.equal(out, out_inf)
+            _close(n(out[:2048]), y, 2e-3, f"outputs path {path}")
+            _close(n(fbuf[:, :2048]), fb.astype(np.float64), 2e-3, f"forward_buffer path {path}")
+            outs[path] = (out, fbuf)
+    finally:
+        _lib.call("enerf_ffmlp_set_path", 0)
+    d_out = (outs[0][0].float() - outs[1][0].float()).abs().max().item()
+    d_fb = (outs[0][1].float() - outs[1][1].float()).abs().max().item()
+    assert d_out <= 4e-3 * float(outs[1][0].float().abs().max()) + 1e-3, d_out
+    assert d_fb <= 4e-3 * float(outs[1][1].float().abs().max()) + 1e-3, d_fb
+
+
 def test_module_matches_reference_semantics():
     torch.manual_seed(123)
     net = ffmlp.FFMLP(32, 3, 64, 3).to(DEV)
