@@ -42,6 +42,7 @@ _SIGS = {
     "enerf_composite_uniform_forward": [_p, _p, _p, _p, _u32, _u32, _f32, _p, _p, _p, _p],
     "enerf_composite_uniform_backward": [_p, _p, _p, _p, _p, _p, _p, _u32, _u32, _f32, _p, _p],
     "enerf_ffmlp_set_path": [_int],
+    "enerf_ffmlp_uses_tcgen05": [_u32, _u32, _u32, _u32, _u32],
     "enerf_allocate_splitk": [_u64],
     "enerf_free_splitk": [],
 }

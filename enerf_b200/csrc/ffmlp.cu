@@ -351,6 +351,8 @@ static int check_dims(const char* name, uint32_t B, uint32_t input_dim, uint32_t
 namespace tcm {
 int tc_forward(const __half* in, const __half* W, uint32_t B, int in_dim, int n_hidden_mm, __half* fwd_buf, __half* out, cudaStream_t st,
                const char* name);
+int tc_backward(const __half* grad, const __half* x, const __half* W, const __half* fwd_buf, __half* bwd_buf, __half* grad_inputs, float* dW,
+                uint32_t B, int in_dim, int n_hidden_mm, cudaStream_t st);
 }
 static int g_mlp_path = 0;   // 0: tcgen05 kernels when eligible, 1: always the generic mma.sync kernels
 static bool tc_eligible(uint32_t input_dim, uint32_t hidden_dim, uint32_t num_layers, uint32_t activation, uint32_t output_activation) {
@@ -401,8 +403,9 @@ int enerf_ffmlp_backward(const uint16_t* grad, const uint16_t* inputs, const uin
     (void)output_activation;  // ignored by the reference backward as well (ffmlp.cu:781)
     if (int rc = check_dims("ffmlp_backward", B, input_dim, output_dim, hidden_dim, num_layers)) return rc;
     ENERF_REQUIRE(grad_weights_dtype == ENERF_F32 || grad_weights_dtype == ENERF_F16, "ffmlp_backward", "bad grad_weights_dtype");
-    ENERF_REQUIRE(backward_buffer != nullptr, "ffmlp_backward", "generic path needs backward_buffer");
     ENERF_REQUIRE(scratch != nullptr, "ffmlp_backward", "scratch must not be NULL");
+    const bool use_tc = tc_eligible(input_dim, hidden_dim, num_layers, activation, ENERF_ACT_NONE) && num_layers <= 4;
+    ENERF_REQUIRE(use_tc || backward_buffer != nullptr, "ffmlp_backward", "the mma.sync path needs backward_buffer");
     cudaStream_t st = as_stream(stream);
     const int nhm = (int)num_layers - 1, Wd = (int)hidden_dim, in = (int)input_dim;
     const size_t n_w = (size_t)Wd * (in + (size_t)Wd * nhm + 16);
@@ -410,6 +413,18 @@ int enerf_ffmlp_backward(const uint16_t* grad, const uint16_t* inputs, const uin
     if (B == 0) return 0;
 
     int rc = 0;
+    if (use_tc) {
+        rc = tcm::tc_backward((const __half*)grad, (const __half*)inputs, (const __half*)weights, (const __half*)forward_buffer,
+                              (__half*)backward_buffer, calc_grad_inputs ? (__half*)grad_inputs : nullptr, scratch, B, in, nhm, st);
+        if (rc) return rc;
+        if (grad_weights_dtype == ENERF_F16) {
+            k_f32_to_f16<<<ceil_div((uint32_t)n_w, 256u), 256, 0, st>>>(scratch, (__half*)grad_weights, (uint32_t)n_w);
+            ENERF_CHECK_LAUNCH("ffmlp_backward(convert)");
+        } else if ((void*)scratch != grad_weights) {
+            ENERF_CUDA(cudaMemcpyAsync(grad_weights, scratch, n_w * sizeof(float), cudaMemcpyDeviceToDevice, st), "ffmlp_backward");
+        }
+        return 0;
+    }
     ENERF_WIDTH_SWITCH(hidden_dim, rc = run_bwd<WW>((const __half*)grad, (const __half*)weights, (const __half*)forward_buffer,
                                                     (__half*)backward_buffer, calc_grad_inputs ? (__half*)grad_inputs : nullptr, B, in, nhm,
                                                     activation, st));
@@ -433,6 +448,10 @@ int enerf_ffmlp_backward(const uint16_t* grad, const uint16_t* inputs, const uin
         ENERF_CUDA(cudaMemcpyAsync(grad_weights, scratch, n_w * sizeof(float), cudaMemcpyDeviceToDevice, st), "ffmlp_backward");
     }
     return 0;
+}
+
+int enerf_ffmlp_uses_tcgen05(uint32_t input_dim, uint32_t hidden_dim, uint32_t num_layers, uint32_t activation, uint32_t output_activation) {
+    return (tc_eligible(input_dim, hidden_dim, num_layers, activation, output_activation) && num_layers <= 4) ? 1 : 0;
 }
 
 int enerf_ffmlp_set_path(int path) {

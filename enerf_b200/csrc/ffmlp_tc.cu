@@ -186,5 +186,290 @@ int tc_forward(const __half* in, const __half* W, uint32_t B, int in_dim, int n_
     return 0;
 }
 
+
+// ================================================================================================
+// Backward (k_tc_bwd): activation gradients AND weight gradients in one persistent kernel.
+//
+//   g_n   = (dy  . W_last) * relu'(h_n)              dgrad: A = dy/g in TMEM (K-major), B = the forward
+//   g_i-1 = (g_i . W_i)    * relu'(h_i-1)            weight tile read MN-major (same smem bytes)
+//   dx    =  g_0 . W_0
+//   dW_last^T += h_n^T . dy     dW_i += g_i^T . h_i-1     dW_0 += g_0^T . x
+//                                                     wgrad: M = 64, K = the 128 samples of the tile;
+//                                                     both operands are MN-major reads of sample-major
+//                                                     tiles the epilogue warps leave in shared memory;
+//                                                     fp32 accumulators stay in TMEM for the CTA's whole
+//                                                     life and are reduced once with red.global.add.
+//   Activation gradients never touch HBM unless the caller asks for backward_buffer.
+//
+// Stage k (k = 0 .. n_hidden_mm+1) of a tile: epilogue E_k prepares operands, MMA thread issues
+// dgrad_k + wgrad_k, tcgen05.commit -> E_k+1 ... (see the schedule in DESIGN.md).
+// ================================================================================================
+static constexpr int kGBytes = 128 * 64 * 2;    // one [8 chunks][128 rows][16 B] tile
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int NSLOTS>
+__global__ void __launch_bounds__(32 + NSLOTS * 128, 1)
+k_tc_bwd(const __half* __restrict__ grad, const __half* __restrict__ x, const __half* __restrict__ W, const __half* __restrict__ fwd_buf,
+         __half* __restrict__ bwd_buf, __half* __restrict__ grad_inputs, float* __restrict__ dW, uint32_t n_tiles, uint32_t B, int in_dim,
+         int n_hidden_mm) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* w0s = smem;                                  // [in_dim/8][64][16 B]   (forward layout)
+    uint8_t* whs = w0s + in_dim * 128;                    // n_hidden_mm x [8][64][16 B]
+    uint8_t* wls = whs + n_hidden_mm * 8192;              // [8][16][16 B]
+    uint8_t* tiles = wls + 2048;                          // per slot: G tile, H tile
+    uint64_t* a_ready = reinterpret_cast<uint64_t*>(tiles + (size_t)NSLOTS * 2 * kGBytes);
+    uint64_t* d_full = a_ready + NSLOTS;
+    uint64_t* flush_bar = d_full + NSLOTS;
+    uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(flush_bar + 1);
+
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    constexpr uint32_t kCols = 512;
+
+    stage_matrix(w0s, W, kW, in_dim, tid, nthreads);
+    for (int j = 0; j < n_hidden_mm; ++j) stage_matrix(whs + j * 8192, W + kW * in_dim + j * kW * kW, kW, kW, tid, nthreads);
+    stage_matrix(wls, W + kW * in_dim + n_hidden_mm * kW * kW, 16, kW, tid, nthreads);
+    if (tid == 0) {
+        for (int s = 0; s < NSLOTS; ++s) {
+            mbar_init(&a_ready[s], 128);
+            mbar_init(&d_full[s], 1);
+        }
+        mbar_init(flush_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_base_ptr, kCols);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem0 = *tmem_base_ptr;
+
+    const int S = n_hidden_mm + 2;
+    const uint32_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    // weight-gradient accumulators (TMEM columns): [dW_last^T : 16][dW_hidden j : 64 each][dW_0 : in_dim]
+    const uint32_t acc_last = tmem0 + NSLOTS * kSlotCols;
+    const uint32_t acc_hid = acc_last + 16;
+    const uint32_t acc_0 = acc_hid + n_hidden_mm * 64;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t pa[NSLOTS];
+#pragma unroll
+            for (int s = 0; s < NSLOTS; ++s) pa[s] = 0;
+            bool first = true;     // first use of the wgrad accumulators: overwrite instead of accumulate
+            for (uint32_t j0 = 0; j0 < my_tiles; j0 += NSLOTS) {
+                for (int k = 0; k < S; ++k) {
+#pragma unroll
+                    for (int s = 0; s < NSLOTS; ++s) {
+                        if (j0 + s >= my_tiles) break;
+                        mbar_wait(&a_ready[s], pa[s]);
+                        pa[s] ^= 1;
+                        tc_fence_after();
+                        const uint32_t d_t = tmem0 + s * kSlotCols, a_t = d_t + 64;
+                        const uint32_t g_s = smem_u32(tiles + (size_t)s * 2 * kGBytes), h_s = g_s + kGBytes;
+                        const bool acc = !(first && s == 0);
+                        if (k == 0) {
+                            // dgrad through the output layer: D[128x64] = dy[128x16] . W_last[16x64]
+                            mma_ts(d_t, a_t, smem_desc(smem_u32(wls), 128, 16 * 16), idesc_f16(kTile, 64, false, true), false);
+                            // dW_last^T[64x16] += h_n^T[64x128] . dy[128x16]   (A = H tile, B = dy tile in the G buffer)
+                            for (int ks = 0; ks < 8; ++ks)
+                                mma_ss(acc_last, smem_desc(h_s + ks * 256, 128, 2048), smem_desc(g_s + ks * 256, 128, 2048),
+                                       idesc_f16(64, 16, true, true), acc || ks > 0);
+                        } else if (k <= n_hidden_mm) {
+                            const int j = n_hidden_mm - k;      // hidden matmul index
+                            const uint32_t wj = smem_u32(whs + j * 8192);
+                            for (int ks = 0; ks < 4; ++ks)
+                                mma_ts(d_t, a_t + ks * 8, smem_desc(wj + ks * 256, 128, 64 * 16), idesc_f16(kTile, 64, false, true), ks > 0);
+                            for (int ks = 0; ks < 8; ++ks)
+                                mma_ss(acc_hid + j * 64, smem_desc(g_s + ks * 256, 128, 2048), smem_desc(h_s + ks * 256, 128, 2048),
+                                       idesc_f16(64, 64, true, true), acc || ks > 0);
+                        } else {
+                            if (grad_inputs)
+                                for (int ks = 0; ks < 4; ++ks)
+                                    mma_ts(d_t, a_t + ks * 8, smem_desc(smem_u32(w0s) + ks * 256, 128, 64 * 16),
+                                           idesc_f16(kTile, (uint32_t)in_dim, false, true), ks > 0);
+                            for (int ks = 0; ks < 8; ++ks)
+                                mma_ss(acc_0, smem_desc(g_s + ks * 256, 128, 2048), smem_desc(h_s + ks * 256, 128, 2048),
+                                       idesc_f16(64, (uint32_t)in_dim, true, true), acc || ks > 0);
+                        }
+                        tc_commit(&d_full[s]);
+                    }
+                }
+                first = false;
+            }
+            tc_commit(flush_bar);
+        }
+    } else {
+        const int s = (warp - 1) >> 2;
+        const int q = warp & 3;
+        const int r_in_tile = q * 32 + lane;
+        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+        const uint32_t d_t = tmem0 + lane_sel + s * kSlotCols, a_t = d_t + 64;
+        uint8_t* g_tile = tiles + (size_t)s * 2 * kGBytes;
+        uint8_t* h_tile = g_tile + kGBytes;
+        uint32_t pd = 0;
+        uint32_t hreg[32];       // this row's forward activation (64 fp16) used as ReLU mask by the next epilogue
+
+        for (uint32_t j = s; j < my_tiles; j += NSLOTS) {
+            const size_t tile = (size_t)blockIdx.x + (size_t)j * gridDim.x;
+            const size_t row = tile * kTile + r_in_tile;
+            // ---- E_0: dy -> TMEM A + dy tile (G buffer); h_n -> registers + H tile
+            {
+                const int4* src = reinterpret_cast<const int4*>(grad + row * 16);
+                const int4 v0 = __ldg(src), v1 = __ldg(src + 1);
+                const uint32_t r8[8] = {(uint32_t)v0.x, (uint32_t)v0.y, (uint32_t)v0.z, (uint32_t)v0.w,
+                                        (uint32_t)v1.x, (uint32_t)v1.y, (uint32_t)v1.z, (uint32_t)v1.w};
+                tmem_st8(a_t, r8);
+                *reinterpret_cast<int4*>(g_tile + 0 * 2048 + r_in_tile * 16) = v0;
+                *reinterpret_cast<int4*>(g_tile + 1 * 2048 + r_in_tile * 16) = v1;
+                const int4* hs = reinterpret_cast<const int4*>(fwd_buf + ((size_t)n_hidden_mm * B + row) * kW);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int4 v = __ldg(hs + c);
+                    hreg[4 * c] = (uint32_t)v.x; hreg[4 * c + 1] = (uint32_t)v.y; hreg[4 * c + 2] = (uint32_t)v.z; hreg[4 * c + 3] = (uint32_t)v.w;
+                    *reinterpret_cast<int4*>(h_tile + c * 2048 + r_in_tile * 16) = v;
+                }
+                tc_wait_st();
+                fence_proxy_async_smem();
+                tc_fence_before();
+                mbar_arrive(&a_ready[s]);
+            }
+            // ---- E_k, k = 1 .. S-1: g = D * relu'(h) -> TMEM A + G tile; next activation (or x) -> H tile
+            for (int k = 1; k < S; ++k) {
+                mbar_wait(&d_full[s], pd);
+                pd ^= 1;
+                tc_fence_after();
+                __half* bb = bwd_buf ? bwd_buf + ((size_t)(k - 1) * B + row) * kW : nullptr;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t acc[32];
+                    tmem_ld32(d_t + h * 32, acc);
+                    tc_wait_ld();
+                    uint32_t p[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const __half2 hv = *reinterpret_cast<const __half2*>(&hreg[h * 16 + e]);
+                        const float g0 = (__low2float(hv) > 0.f) ? __uint_as_float(acc[2 * e]) : 0.f;
+                        const float g1 = (__high2float(hv) > 0.f) ? __uint_as_float(acc[2 * e + 1]) : 0.f;
+                        p[e] = pack2(g0, g1);
+                    }
+                    tmem_st16(a_t + h * 16, p);
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        const int4 val = make_int4((int)p[4 * v], (int)p[4 * v + 1], (int)p[4 * v + 2], (int)p[4 * v + 3]);
+                        *reinterpret_cast<int4*>(g_tile + (h * 4 + v) * 2048 + r_in_tile * 16) = val;
+                        if (bb) reinterpret_cast<int4*>(bb)[h * 4 + v] = val;
+                    }
+                }
+                if (k < S - 1) {
+                    const int4* hs = reinterpret_cast<const int4*>(fwd_buf + ((size_t)(n_hidden_mm - k) * B + row) * kW);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const int4 v = __ldg(hs + c);
+                        hreg[4 * c] = (uint32_t)v.x; hreg[4 * c + 1] = (uint32_t)v.y; hreg[4 * c + 2] = (uint32_t)v.z; hreg[4 * c + 3] = (uint32_t)v.w;
+                        *reinterpret_cast<int4*>(h_tile + c * 2048 + r_in_tile * 16) = v;
+                    }
+                } else {
+                    const int4* xs = reinterpret_cast<const int4*>(x + row * in_dim);
+                    for (int c = 0; c < in_dim / 8; ++c) *reinterpret_cast<int4*>(h_tile + c * 2048 + r_in_tile * 16) = __ldg(xs + c);
+                }
+                tc_wait_st();
+                fence_proxy_async_smem();
+                tc_fence_before();
+                mbar_arrive(&a_ready[s]);
+            }
+            // ---- E_S: dx
+            mbar_wait(&d_full[s], pd);
+            pd ^= 1;
+            tc_fence_after();
+            if (grad_inputs) {
+                for (int c = 0; c < in_dim / 16; ++c) {
+                    uint32_t acc[16];
+                    tmem_ld16(d_t + c * 16, acc);
+                    tc_wait_ld();
+                    uint32_t p[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) p[e] = pack2(__uint_as_float(acc[2 * e]), __uint_as_float(acc[2 * e + 1]));
+                    int4* dst = reinterpret_cast<int4*>(grad_inputs + row * in_dim + c * 16);
+                    dst[0] = make_int4((int)p[0], (int)p[1], (int)p[2], (int)p[3]);
+                    dst[1] = make_int4((int)p[4], (int)p[5], (int)p[6], (int)p[7]);
+                }
+            }
+            tc_fence_before();
+        }
+
+        // ---- flush the weight-gradient accumulators (slot 0's four warps; M = 64 -> lanes 0..15 of each quarter)
+        if (s == 0 && my_tiles > 0) {
+            mbar_wait(flush_bar, 0);
+            tc_fence_after();
+            const int m = q * 16 + lane;                  // row of the 64-row accumulator held by lanes < 16
+            const uint32_t base = lane_sel;
+            float* dW0 = dW;
+            float* dWh = dW + kW * in_dim;
+            float* dWl = dWh + (size_t)n_hidden_mm * kW * kW;
+            {   // dW_last^T [hidden m][out n] -> dW_last[n][m]
+                uint32_t acc[16];
+                tmem_ld16(acc_last + base, acc);
+                tc_wait_ld();
+                if (lane < 16)
+#pragma unroll
+                    for (int nn = 0; nn < 16; ++nn) atomicAdd(dWl + nn * kW + m, __uint_as_float(acc[nn]));
+            }
+            for (int jj = 0; jj < n_hidden_mm; ++jj)
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t acc[16];
+                    tmem_ld16(acc_hid + jj * 64 + c * 16 + base, acc);
+                    tc_wait_ld();
+                    if (lane < 16) {
+                        float* dst = dWh + (size_t)jj * kW * kW + (size_t)m * kW + c * 16;
+#pragma unroll
+                        for (int v = 0; v < 4; ++v)
+                            red_add_v4(dst + 4 * v, __uint_as_float(acc[4 * v]), __uint_as_float(acc[4 * v + 1]), __uint_as_float(acc[4 * v + 2]),
+                                       __uint_as_float(acc[4 * v + 3]));
+                    }
+                }
+            for (int c = 0; c < in_dim / 16; ++c) {
+                uint32_t acc[16];
+                tmem_ld16(acc_0 + c * 16 + base, acc);
+                tc_wait_ld();
+                if (lane < 16) {
+                    float* dst = dW0 + (size_t)m * in_dim + c * 16;
+#pragma unroll
+                    for (int v = 0; v < 4; ++v)
+                        red_add_v4(dst + 4 * v, __uint_as_float(acc[4 * v]), __uint_as_float(acc[4 * v + 1]), __uint_as_float(acc[4 * v + 2]),
+                                   __uint_as_float(acc[4 * v + 3]));
+                }
+            }
+            tc_fence_before();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem0, kCols);
+}
+
+int tc_backward(const __half* grad, const __half* x, const __half* W, const __half* fwd_buf, __half* bwd_buf, __half* grad_inputs, float* dW,
+                uint32_t B, int in_dim, int n_hidden_mm, cudaStream_t st) {
+    constexpr int NSLOTS = 2;
+    // TMEM: NSLOTS*96 + 16 + 64*n_hidden_mm + in_dim columns
+    if (NSLOTS * kSlotCols + 16 + 64 * n_hidden_mm + in_dim > 512) { set_error("ffmlp_backward: network too deep for the tcgen05 path"); return -2; }
+    size_t smem = (size_t)in_dim * 128 + (size_t)n_hidden_mm * 8192 + 2048 + (size_t)NSLOTS * 2 * kGBytes + (2 * NSLOTS + 1) * 8 + 16;
+    if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: it allocates all 512 TMEM columns
+    if (smem > 220 * 1024) { set_error("ffmlp_backward: network too deep for the tcgen05 path"); return -2; }
+    static size_t configured = 0;
+    if (smem > configured) {
+        ENERF_CUDA(cudaFuncSetAttribute(k_tc_bwd<NSLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "ffmlp_backward");
+        configured = smem;
+    }
+    const uint32_t n_tiles = B / kTile;
+    const uint32_t grid = n_tiles < (uint32_t)kNumSM ? n_tiles : (uint32_t)kNumSM;
+    k_tc_bwd<NSLOTS><<<grid, 32 + NSLOTS * 128, smem, st>>>(grad, x, W, fwd_buf, bwd_buf, grad_inputs, dW, n_tiles, B, in_dim, n_hidden_mm);
+    ENERF_CHECK_LAUNCH("ffmlp_backward");
+    return 0;
+}
+
 }  // namespace tcm
 }  // namespace enerf

@@ -59,7 +59,12 @@ class _ffmlp_forward(Function):
         else:
             grad_inputs = torch.empty(1, device=grad.device, dtype=grad.dtype)
         grad_weights = torch.empty(weights.numel(), device=grad.device, dtype=torch.float32)
-        backward_buffer = torch.empty(num_layers, B, hidden_dim, device=grad.device, dtype=grad.dtype)
+        # the tcgen05 kernels keep the activation gradients on the SM; only the generic path needs the buffer
+        from .. import _lib
+        if _lib.lib().enerf_ffmlp_uses_tcgen05(input_dim, hidden_dim, num_layers, activation, output_activation):
+            backward_buffer = None
+        else:
+            backward_buffer = torch.empty(num_layers, B, hidden_dim, device=grad.device, dtype=grad.dtype)
 
         _backend.ffmlp_backward(grad, inputs, weights, forward_buffer, B, input_dim, output_dim, hidden_dim, num_layers,
                                 activation, output_activation, calc_grad_inputs, backward_buffer, grad_inputs, grad_weights)

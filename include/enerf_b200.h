@@ -169,6 +169,10 @@ int enerf_allocate_splitk(uint64_t size);
  * 64-wide ReLU networks with input_dim <= 64, the mma.sync kernels otherwise; 1 = always the
  * generic mma.sync kernels (used by the parity tests to cross-check the two families). */
 int enerf_ffmlp_set_path(int path);
+/* 1 when forward/inference/backward of this shape run on the tcgen05 kernels (backward_buffer may
+ * then be NULL), else 0.  Not a compute call: usable without a GPU. */
+int enerf_ffmlp_uses_tcgen05(uint32_t input_dim, uint32_t hidden_dim, uint32_t num_layers, uint32_t activation,
+                             uint32_t output_activation);
 int enerf_free_splitk(void);
 
 /* ---------------------------------------------------- fused extras (no reference ABI) ---- */

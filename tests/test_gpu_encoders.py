@@ -219,7 +219,8 @@ def test_sh_matches_oracle_and_reference(degree):
         exact = torch.empty(B2, C2, device=DEV)
         SB.sh_encode_forward(t(dd).half().float(), exact, B2, 3, degree, False, torch.empty(1, device=DEV))
         assert float((gh.float() - exact).abs().max()) <= float((rh.float() - exact).abs().max()) + 1e-3
-        assert torch.allclose(gh.float(), rh.float(), atol=2e-2, rtol=2e-2)
+        if degree <= 4:     # higher degrees: the reference's fp16 polynomial evaluation itself is off by > 2e-2
+            assert torch.allclose(gh.float(), rh.float(), atol=2e-2, rtol=2e-2)
 
 
 def test_sh_module_forward_backward():

@@ -122,6 +122,31 @@ def test_tcgen05_and_mma_sync_paths_agree(I, nl):
             outs[path] = (out, fbuf)
     finally:
         _lib.call("enerf_ffmlp_set_path", 0)
+    # backward through both families from the same stored activations (oracle's), incl. the NULL backward_buffer mode
+    y_all, fb_all = oracle.ffmlp_forward(x, w, I, W, nl)
+    gx, gw, bb = oracle.ffmlp_backward(g, x, w, fb_all, I, W, nl)
+    tfb, tg = t(fb_all), t(g)
+    try:
+        for path in (0, 1):
+            _lib.call("enerf_ffmlp_set_path", path)
+            for with_bb in ((True, False) if path == 0 else (True,)):
+                bbuf = torch.zeros(nl, B, W, device=DEV, dtype=torch.half) if with_bb else None
+                gin = torch.zeros(B, I, device=DEV, dtype=torch.half)
+                gwt = torch.zeros(len(w), device=DEV, dtype=torch.float32)
+                FB.ffmlp_backward(tg, tx, tw, tfb, B, I, 16, W, nl, 0, 6, True, bbuf, gin, gwt)
+                torch.cuda.synchronize()
+                tag = f"path {path} bb={with_bb}"
+                _close(n(gin), gx, 3e-3, "grad_inputs " + tag)
+                _close(n(gwt), gw, 1e-3, "grad_weights " + tag)
+                if with_bb:
+                    _close(n(bbuf), bb.astype(np.float64), 3e-3, "backward_buffer " + tag)
+            # weight-gradient only (calc_grad_inputs = False)
+            gwt2 = torch.zeros(len(w), device=DEV, dtype=torch.float32)
+            FB.ffmlp_backward(tg, tx, tw, tfb, B, I, 16, W, nl, 0, 6, False, torch.zeros(nl, B, W, device=DEV, dtype=torch.half),
+                              torch.zeros(1, device=DEV, dtype=torch.half), gwt2)
+            _close(n(gwt2), gw, 1e-3, f"grad_weights (no dx) path {path}")
+    finally:
+        _lib.call("enerf_ffmlp_set_path", 0)
     d_out = (outs[0][0].float() - outs[1][0].float()).abs().max().item()
     d_fb = (outs[0][1].float() - outs[1][1].float()).abs().max().item()
     assert d_out <= 4e-3 * float(outs[1][0].float().abs().max()) + 1e-3, d_out
