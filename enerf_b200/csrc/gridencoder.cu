@@ -21,6 +21,7 @@ namespace enerf {
 
 static constexpr unsigned kFull = 0xffffffffu;
 static constexpr int kSamplesPerCta = 32;
+static int g_bwd_walk = 1;   // 1: walking scatter (register aggregation along rays), 0: one reduction per corner
 
 // ---- element-type helpers: the accumulator is rounded to T after every corner -----------
 template <typename T> struct Elem;
@@ -290,6 +291,91 @@ k_grid_bwd(const T* __restrict__ grad, const float* __restrict__ inputs, const i
     }
 }
 
+// Scatter-add, "walking" formulation.  A thread owns ONE level and a run of SEG consecutive samples.
+// Consecutive samples come from the same ray (the marcher emits them in order), so on coarse and
+// middle levels they fall into the same cell for many steps: the thread accumulates the 2^D corner
+// contributions in registers and only touches memory (2^D vector reductions) when the cell
+// changes.  Lanes of a warp are (level = lane % L, run = lane / L): the L lanes of one run read
+// one contiguous L*C-element row of `grad` per step (coalesced) and broadcast-load the position.
+// Atomic traffic drops by the mean run length per level (~25x on level 0, none on the finest
+// hashed levels) and, more importantly, the same-address contention on the small coarse tables
+// disappears.  Same sums as k_grid_bwd up to fp32 reassociation.
+template <typename T, typename G, int D, int C, bool BLC, int SEG>
+__global__ void __launch_bounds__(256)
+k_grid_bwd_walk(const T* __restrict__ grad, const float* __restrict__ inputs, const int32_t* __restrict__ offsets,
+                G* __restrict__ grad_grid, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t level = t % L;
+    const uint32_t run = t / L;
+    const uint64_t b0 = (uint64_t)run * SEG;
+    if (b0 >= B) return;
+    const uint32_t b1 = (uint32_t)min((uint64_t)B, b0 + SEG);
+
+    const LevelGeom g = level_geom(offsets, level, S, H, gridtype, D);
+    G* __restrict__ tab = grad_grid + (size_t)g.offset * C;
+
+    uint32_t cell[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) cell[d] = 0xffffffffu;
+    bool have = false;
+    float acc[1 << D][C];
+
+    auto flush = [&]() {
+#pragma unroll
+        for (int idx = 0; idx < (1 << D); ++idx) {
+            uint32_t pl[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) pl[d] = cell[d] + ((idx >> d) & 1);
+            const uint32_t e = grid_index<D>(g, pl) * C;
+            if (C == 1) {
+                red_add(tab + e, acc[idx][0]);
+            } else {
+#pragma unroll
+                for (int ch = 0; ch < C; ch += 2) red_add2(tab + e + ch, acc[idx][ch], acc[idx][ch + (C > 1 ? 1 : 0)]);
+            }
+        }
+    };
+
+    for (uint32_t b = (uint32_t)b0; b < b1; ++b) {
+        float x[D];
+        if (load_pos<D>(inputs, b, x)) continue;         // out-of-range samples contribute nothing
+        float pos[D];
+        uint32_t pg[D];
+        bool same = have;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            pos[d] = __fmaf_rn(x[d], g.scale, 0.5f);
+            const float fl = floorf(pos[d]);
+            pg[d] = (uint32_t)fl;
+            pos[d] -= fl;
+            same = same && (pg[d] == cell[d]);
+        }
+        if (!same) {
+            if (have) flush();
+#pragma unroll
+            for (int d = 0; d < D; ++d) cell[d] = pg[d];
+#pragma unroll
+            for (int idx = 0; idx < (1 << D); ++idx)
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) acc[idx][ch] = 0.f;
+            have = true;
+        }
+        float gr[C];
+        const T* __restrict__ gp = BLC ? grad + ((size_t)b * L + level) * C : grad + ((size_t)level * B + b) * C;
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) gr[ch] = Elem<T>::to_f(gp[ch]);
+#pragma unroll
+        for (int idx = 0; idx < (1 << D); ++idx) {
+            float w = 1.0f;
+#pragma unroll
+            for (int d = 0; d < D; ++d) w *= ((idx >> d) & 1) ? pos[d] : 1.0f - pos[d];
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) acc[idx][ch] = __fmaf_rn(w, gr[ch], acc[idx][ch]);
+        }
+    }
+    if (have) flush();
+}
+
 // gridencoder.cu:314-340
 template <typename T, int D, int C, bool BLC>
 __global__ void k_grid_input_bwd(const T* __restrict__ grad, const T* __restrict__ dy_dx, T* __restrict__ grad_inputs,
@@ -344,10 +430,18 @@ static int launch_fwd(const float* inputs, const T* emb, const int32_t* offsets,
 template <typename T, typename G, int D, int C>
 static int launch_bwd(const T* grad, const float* inputs, const int32_t* offsets, G* gg, uint32_t B, uint32_t L, float S, uint32_t H,
                       bool cg, const T* dy_dx, T* grad_inputs, uint32_t gridtype, int out_layout, cudaStream_t st) {
-    const dim3 block(32, min(L, 16u));
-    const dim3 grid(ceil_div(B, (uint32_t)kSamplesPerCta));
-    if (out_layout == 1) k_grid_bwd<T, G, D, C, true><<<grid, block, 0, st>>>(grad, inputs, offsets, gg, B, L, S, H, gridtype);
-    else k_grid_bwd<T, G, D, C, false><<<grid, block, 0, st>>>(grad, inputs, offsets, gg, B, L, S, H, gridtype);
+    if (g_bwd_walk && L <= 32 && (32 % L) == 0) {
+        constexpr int SEG = 32;
+        const uint64_t threads = (uint64_t)ceil_div(B, (uint32_t)SEG) * L;
+        const dim3 grid((uint32_t)ceil_div(threads, (uint64_t)256));
+        if (out_layout == 1) k_grid_bwd_walk<T, G, D, C, true, SEG><<<grid, 256, 0, st>>>(grad, inputs, offsets, gg, B, L, S, H, gridtype);
+        else k_grid_bwd_walk<T, G, D, C, false, SEG><<<grid, 256, 0, st>>>(grad, inputs, offsets, gg, B, L, S, H, gridtype);
+    } else {
+        const dim3 block(32, min(L, 16u));
+        const dim3 grid(ceil_div(B, (uint32_t)kSamplesPerCta));
+        if (out_layout == 1) k_grid_bwd<T, G, D, C, true><<<grid, block, 0, st>>>(grad, inputs, offsets, gg, B, L, S, H, gridtype);
+        else k_grid_bwd<T, G, D, C, false><<<grid, block, 0, st>>>(grad, inputs, offsets, gg, B, L, S, H, gridtype);
+    }
     ENERF_CHECK_LAUNCH("grid_encode_backward");
     if (cg) {
         const uint32_t n = B * D;
@@ -385,6 +479,12 @@ static int launch_bwd(const T* grad, const float* inputs, const int32_t* offsets
 using namespace enerf;
 
 extern "C" {
+
+int enerf_grid_set_backward_mode(int mode) {
+    ENERF_REQUIRE(mode == 0 || mode == 1, "grid_set_backward_mode", "mode must be 0 (per-corner reductions) or 1 (walking aggregation)");
+    g_bwd_walk = mode;
+    return 0;
+}
 
 int enerf_grid_encode_forward(const float* inputs, const void* embeddings, const int32_t* offsets, void* outputs,
                               uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, int calc_grad_inputs,

@@ -121,6 +121,11 @@ int enerf_grid_encode_backward(const void* grad, const float* inputs, const void
                                uint32_t gridtype, int dtype, int grad_dtype, int out_layout,
                                void* stream);
 
+/* Scatter strategy of grid_encode_backward (no reference counterpart): 1 (default) = a thread walks
+ * 32 consecutive samples of one level and aggregates in registers while they stay in one cell;
+ * 0 = one reduction per corner per sample (the reference's strategy).  Same sums either way. */
+int enerf_grid_set_backward_mode(int mode);
+
 /* -------------------------------------------------------------------- shencoder ---- */
 /* shencoder/src/shencoder.h:10,13, shencoder/src/shencoder.cu.  degree C in [1,8], D == 3. */
 

@@ -103,8 +103,16 @@ def test_grid_forward_generic_shapes():
         assert np.allclose(n(dy).reshape(B, L, D, C), wdy, atol=1e-3, rtol=1e-4), (D, C, L, gridtype)
 
 
+@pytest.fixture(params=[1, 0], ids=["walk", "percorner"])
+def scatter_mode(request):
+    from enerf_b200 import _lib
+    _lib.call("enerf_grid_set_backward_mode", request.param)
+    yield request.param
+    _lib.call("enerf_grid_set_backward_mode", 1)
+
+
 @pytest.mark.parametrize("dtype,grad_dtype,tol", [(np.float32, torch.float32, 1e-4), (np.float16, torch.float32, 1e-4), (np.float16, torch.float16, 2e-2)])
-def test_grid_backward_matches_exact_sum(dtype, grad_dtype, tol):
+def test_grid_backward_matches_exact_sum(dtype, grad_dtype, tol, scatter_mode):
     bound = 3
     pls, offsets, emb = _table(bound, dtype, seed=3)
     x = _marched_points(bound, 192, seed=2)[:60000]
@@ -131,6 +139,26 @@ def test_grid_backward_matches_exact_sum(dtype, grad_dtype, tol):
         ours = np.abs(n(gg).astype(np.float64) - n(rg).astype(np.float64)).max()
         lim = (2e-2 if dtype == np.float16 else 1e-4) * np.abs(want).max()
         assert ours <= 2 * lim, f"ours vs reference {ours}, reference vs exact {ref_err}"
+
+
+def test_grid_backward_generic_shapes(scatter_mode):
+    rng = np.random.default_rng(6)
+    for D, C, L, gridtype, log2T in [(2, 2, 4, 0, 19), (3, 1, 5, 0, 12), (3, 4, 6, 0, 14), (3, 8, 3, 1, 10), (2, 4, 8, 1, 8), (3, 2, 32, 0, 10)]:
+        pls = 1.3
+        offsets = oracle.grid_offsets(D, L, pls, 16, log2T)
+        emb = rng.uniform(-1, 1, (offsets[-1], C)).astype(np.float32)
+        x = np.sort(rng.random((1999, D)).astype(np.float32), axis=0)          # sorted -> long same-cell runs
+        x[7] = 1.5                                                              # one out-of-range sample
+        B = len(x)
+        grad = rng.normal(size=(L, B, C)).astype(np.float32)
+        want = oracle.grid_encode_backward(grad, x, offsets, offsets[-1], C, pls, 16, gridtype=gridtype, level_scales=gpu_level_scales(pls, 16, L))
+        dummy = torch.zeros(1, device=DEV)
+        for layout in (0, 1):
+            g = grad if layout == 0 else np.ascontiguousarray(grad.transpose(1, 0, 2)).reshape(B, L * C)
+            gg = torch.zeros(int(offsets[-1]), C, device=DEV)
+            GB.grid_encode_backward(t(g), t(x), t(emb), t(offsets), gg, B, D, C, L, np.log2(pls), 16, False, dummy, dummy, gridtype, layout)
+            err = np.abs(n(gg) - want).max()
+            assert err <= 1e-4 * np.abs(want).max(), (D, C, L, gridtype, layout, err)
 
 
 def test_grid_input_gradient_matches_oracle_and_reference():

@@ -83,11 +83,15 @@ def main():
             res[f"grid_fwd_{str(dt)[6:]}"] = {"ms": med, "min_ms": mn, "GBps": nbytes / med / 1e6, "frac": nbytes / med / 1e6 / peak}
             grad = torch.randn(S, 32, device=dev).to(dt)
             for gdt in ((torch.float32, torch.float16) if dt == torch.float16 else (torch.float32,)):
-                gg = torch.zeros(emb.shape, device=dev, dtype=gdt)
-                med, mn = timeit(lambda: GB.grid_encode_backward(grad, x01, emb, enc.offsets, gg, S, 3, 2, 16, Sx, 16, False, dummy, dummy, 0, 1),
-                                 args.iters, flush)
-                nbytes = (12 + 32 * emb.element_size() + 2 * 16 * 8 * 2 * emb.element_size()) * S
-                res[f"grid_bwd_{str(dt)[6:]}_acc{str(gdt)[6:]}"] = {"ms": med, "min_ms": mn, "GBps": nbytes / med / 1e6, "frac": nbytes / med / 1e6 / peak}
+                for mode in (1, 0):
+                    _lib.call("enerf_grid_set_backward_mode", mode)
+                    gg = torch.zeros(emb.shape, device=dev, dtype=gdt)
+                    med, mn = timeit(lambda: GB.grid_encode_backward(grad, x01, emb, enc.offsets, gg, S, 3, 2, 16, Sx, 16, False, dummy, dummy, 0, 1),
+                                     args.iters, flush)
+                    nbytes = (12 + 32 * emb.element_size() + 2 * 16 * 8 * 2 * emb.element_size()) * S
+                    res[f"grid_bwd_{str(dt)[6:]}_acc{str(gdt)[6:]}_{'walk' if mode else 'percorner'}"] = {
+                        "ms": med, "min_ms": mn, "GBps": nbytes / med / 1e6, "frac": nbytes / med / 1e6 / peak}
+                _lib.call("enerf_grid_set_backward_mode", 1)
         # random (incoherent) points for comparison
         xr = torch.rand(S, 3, device=dev)
         emb = enc.embeddings.detach().half().contiguous()
