@@ -40,6 +40,10 @@ _SIGS = {
     "enerf_ffmlp_forward": [_p, _p, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _p, _p, _p],
     "enerf_ffmlp_inference": [_p, _p, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _p, _p, _p],
     "enerf_ffmlp_backward": [_p, _p, _p, _p, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _int, _p, _p, _p, _int, _p, _p],
+    "enerf_field_sigma_forward": [_p, _p, _p, _u32, _u32, _p, _p, _p, _p],
+    "enerf_field_color_forward": [_p, _p, _u32, _u32, _u32, _p, _p, _p],
+    "enerf_field_color_backward": [_p, _p, _u32, _p, _p, _p, _u32, _u32, _p, _p, _p],
+    "enerf_field_sigma_backward": [_p, _p, _p, _p, _p, _p, _u32, _u32, _p, _p, _p],
     "enerf_composite_uniform_forward": [_p, _p, _p, _p, _u32, _u32, _f32, _p, _p, _p, _p],
     "enerf_composite_uniform_backward": [_p, _p, _p, _p, _p, _p, _p, _u32, _u32, _f32, _p, _p],
     "enerf_ffmlp_set_path": [_int],

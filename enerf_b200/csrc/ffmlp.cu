@@ -353,6 +353,13 @@ int tc_forward(const __half* in, const __half* W, uint32_t B, int in_dim, int n_
                const char* name);
 int tc_backward(const __half* grad, const __half* x, const __half* W, const __half* fwd_buf, __half* bwd_buf, __half* grad_inputs, float* dW,
                 uint32_t B, int in_dim, int n_hidden_mm, cudaStream_t st);
+int tc_forward_sigma_head(const __half* feat, const __half* W, uint32_t B, int n_hidden_mm, __half* fwd_buf, const float* dirs, float* sigma,
+                          __half* cin, cudaStream_t st);
+int tc_forward_rgb_head(const __half* cin, const __half* W, uint32_t B, int n_hidden_mm, __half* fwd_buf, float* rgb, int n_ch, cudaStream_t st);
+int tc_backward_rgb(const float* g_rgb, const float* rgb, int n_ch, const __half* cin, const __half* W, const __half* fwd_buf, __half* dcin, float* dW,
+                    uint32_t B, int n_hidden_mm, cudaStream_t st);
+int tc_backward_sigma(const float* g_sigma, const float* sigma, const __half* dcin, const __half* feat, const __half* W, const __half* fwd_buf,
+                      __half* dfeat, float* dW, uint32_t B, int n_hidden_mm, cudaStream_t st);
 }
 static int g_mlp_path = 0;   // 0: tcgen05 kernels when eligible, 1: always the generic mma.sync kernels
 static bool tc_eligible(uint32_t input_dim, uint32_t hidden_dim, uint32_t num_layers, uint32_t activation, uint32_t output_activation) {
@@ -448,6 +455,53 @@ int enerf_ffmlp_backward(const uint16_t* grad, const uint16_t* inputs, const uin
         ENERF_CUDA(cudaMemcpyAsync(grad_weights, scratch, n_w * sizeof(float), cudaMemcpyDeviceToDevice, st), "ffmlp_backward");
     }
     return 0;
+}
+
+// ---- fused E-NeRF field heads (64-wide ReLU networks, 32 inputs) on the tcgen05 kernels ------------------
+static int field_check(const char* name, uint32_t B, uint32_t num_layers) {
+    ENERF_REQUIRE(B % 128 == 0, name, "batch size must be a multiple of 128");
+    ENERF_REQUIRE(num_layers >= 2 && num_layers <= 4, name, "num_layers must be in [2,4]");
+    return 0;
+}
+
+int enerf_field_sigma_forward(const uint16_t* feat, const uint16_t* weights, const float* dirs, uint32_t B, uint32_t num_layers,
+                              uint16_t* forward_buffer, float* sigma, uint16_t* cin, void* stream) {
+    if (int rc = field_check("field_sigma_forward", B, num_layers)) return rc;
+    if (B == 0) return 0;
+    return tcm::tc_forward_sigma_head((const __half*)feat, (const __half*)weights, B, (int)num_layers - 1, (__half*)forward_buffer, dirs, sigma,
+                                      (__half*)cin, as_stream(stream));
+}
+
+int enerf_field_color_forward(const uint16_t* cin, const uint16_t* weights, uint32_t B, uint32_t num_layers, uint32_t n_ch,
+                              uint16_t* forward_buffer, float* rgb, void* stream) {
+    if (int rc = field_check("field_color_forward", B, num_layers)) return rc;
+    ENERF_REQUIRE(n_ch >= 1 && n_ch <= 4, "field_color_forward", "n_ch must be in [1,4]");
+    if (B == 0) return 0;
+    return tcm::tc_forward_rgb_head((const __half*)cin, (const __half*)weights, B, (int)num_layers - 1, (__half*)forward_buffer, rgb, (int)n_ch,
+                                    as_stream(stream));
+}
+
+int enerf_field_color_backward(const float* grad_rgb, const float* rgb, uint32_t n_ch, const uint16_t* cin, const uint16_t* weights,
+                               const uint16_t* forward_buffer, uint32_t B, uint32_t num_layers, uint16_t* grad_cin, float* grad_weights,
+                               void* stream) {
+    if (int rc = field_check("field_color_backward", B, num_layers)) return rc;
+    ENERF_REQUIRE(n_ch >= 1 && n_ch <= 4, "field_color_backward", "n_ch must be in [1,4]");
+    const size_t n_w = (size_t)64 * (32 + (size_t)64 * (num_layers - 1) + 16);
+    ENERF_CUDA(cudaMemsetAsync(grad_weights, 0, n_w * sizeof(float), as_stream(stream)), "field_color_backward");
+    if (B == 0) return 0;
+    return tcm::tc_backward_rgb(grad_rgb, rgb, (int)n_ch, (const __half*)cin, (const __half*)weights, (const __half*)forward_buffer,
+                                (__half*)grad_cin, grad_weights, B, (int)num_layers - 1, as_stream(stream));
+}
+
+int enerf_field_sigma_backward(const float* grad_sigma, const float* sigma, const uint16_t* grad_cin, const uint16_t* feat,
+                               const uint16_t* weights, const uint16_t* forward_buffer, uint32_t B, uint32_t num_layers, uint16_t* grad_feat,
+                               float* grad_weights, void* stream) {
+    if (int rc = field_check("field_sigma_backward", B, num_layers)) return rc;
+    const size_t n_w = (size_t)64 * (32 + (size_t)64 * (num_layers - 1) + 16);
+    ENERF_CUDA(cudaMemsetAsync(grad_weights, 0, n_w * sizeof(float), as_stream(stream)), "field_sigma_backward");
+    if (B == 0) return 0;
+    return tcm::tc_backward_sigma(grad_sigma, sigma, (const __half*)grad_cin, (const __half*)feat, (const __half*)weights,
+                                  (const __half*)forward_buffer, (__half*)grad_feat, grad_weights, B, (int)num_layers - 1, as_stream(stream));
 }
 
 int enerf_ffmlp_uses_tcgen05(uint32_t input_dim, uint32_t hidden_dim, uint32_t num_layers, uint32_t activation, uint32_t output_activation) {

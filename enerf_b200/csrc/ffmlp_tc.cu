@@ -33,10 +33,45 @@ __device__ __forceinline__ void stage_matrix(uint8_t* dst, const __half* __restr
     }
 }
 
-template <int NSLOTS>
+// Optional fused heads of the last layer (the E-NeRF field, nerf/network_ff.py:51-73):
+//   HEAD 1 (sigma-net): h = fp16(y); sigma = exp(h[0]) (fp32, `trunc_exp`); the colour-net input row
+//           [SH_4(dir) (16) | h[1:16] (15) | 0] is written directly (no SH kernel, no cat, no zeros_like)
+//   HEAD 2 (colour-net): rgb[c] = sigmoid(fp16(y[c])) for c < n_ch, written as fp32 [B, n_ch]
+struct HeadArgs {
+    const float* dirs;   // [B,3] fp32                    (HEAD 1)
+    float* sigma;        // [B] fp32                      (HEAD 1)
+    __half* cin;         // [B,32] fp16                   (HEAD 1)
+    float* rgb;          // [B,n_ch] fp32                 (HEAD 2)
+    int n_ch;
+};
+
+// real spherical harmonics up to l = 3 of (x,y,z) — the basis of shencoder.cu:51-69, fp32
+__device__ __forceinline__ void sh_deg4(float x, float y, float z, float (&o)[16]) {
+    const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+    o[0] = 0.28209479177387814f;                         // 1/(2 sqrt(pi))
+    o[1] = -0.48860251190291987f * y;                    // sqrt(3/(4 pi))
+    o[2] = 0.48860251190291987f * z;
+    o[3] = -0.48860251190291987f * x;
+    o[4] = 1.0925484305920792f * xy;                     // sqrt(15/(4 pi))
+    o[5] = -1.0925484305920792f * yz;
+    o[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;   // sqrt(5/(16 pi)) (3 z^2 - 1)
+    o[7] = -1.0925484305920792f * xz;
+    o[8] = 0.54627421529603959f * (x2 - y2);             // sqrt(15/(16 pi))
+    o[9] = 0.59004358992664352f * y * (y2 - 3.0f * x2);  // sqrt(35/(32 pi))
+    o[10] = 2.8906114426405538f * xy * z;                // sqrt(105/(4 pi))
+    o[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2);   // sqrt(21/(32 pi))
+    o[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);    // sqrt(7/(16 pi))
+    o[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
+    o[14] = 1.4453057213202769f * z * (x2 - y2);         // sqrt(105/(16 pi))
+    o[15] = 0.59004358992664352f * x * (3.0f * y2 - x2);
+}
+__device__ __forceinline__ float f16_round(float v) { return __half2float(__float2half_rn(v)); }
+
+template <int NSLOTS, int IN_DIM, int HEAD>
 __global__ void __launch_bounds__(32 + NSLOTS * 128, 1)
 k_tc_fwd(const __half* __restrict__ in, const __half* __restrict__ W, __half* __restrict__ fwd_buf, __half* __restrict__ out,
-         uint32_t n_tiles, uint32_t B, int in_dim, int n_hidden_mm) {
+         uint32_t n_tiles, uint32_t B, int n_hidden_mm, HeadArgs head) {
+    constexpr int in_dim = IN_DIM;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* w0s = smem;                                  // [in_dim/8][64][16 B]
     uint8_t* whs = w0s + in_dim * 128;                    // n_hidden_mm x [8][64][16 B]
@@ -104,14 +139,21 @@ k_tc_fwd(const __half* __restrict__ in, const __half* __restrict__ W, __half* __
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
         const uint32_t d_t = tmem0 + lane_sel + s * kSlotCols, a_t = d_t + 64;
         uint32_t pd = 0;
+        // the input row of the NEXT tile is fetched while the current tile's layers run
+        int4 xin[IN_DIM / 8];
+        if ((uint32_t)s < my_tiles) {
+            const size_t row0 = ((size_t)blockIdx.x + (size_t)s * gridDim.x) * kTile + q * 32 + lane;
+#pragma unroll
+            for (int c = 0; c < IN_DIM / 8; ++c) xin[c] = __ldg(reinterpret_cast<const int4*>(in + row0 * in_dim) + c);
+        }
         for (uint32_t j = s; j < my_tiles; j += NSLOTS) {
             const size_t tile = (size_t)blockIdx.x + (size_t)j * gridDim.x;
             const size_t row = tile * kTile + q * 32 + lane;
             // ---- input row -> TMEM A
             {
-                const int4* src = reinterpret_cast<const int4*>(in + row * in_dim);
-                for (int c = 0; c < in_dim / 16; ++c) {            // 16 halves = 8 TMEM columns per step
-                    const int4 v0 = __ldg(src + 2 * c), v1 = __ldg(src + 2 * c + 1);
+#pragma unroll
+                for (int c = 0; c < IN_DIM / 16; ++c) {            // 16 halves = 8 TMEM columns per step
+                    const int4 v0 = xin[2 * c], v1 = xin[2 * c + 1];
                     const uint32_t r[8] = {(uint32_t)v0.x, (uint32_t)v0.y, (uint32_t)v0.z, (uint32_t)v0.w,
                                            (uint32_t)v1.x, (uint32_t)v1.y, (uint32_t)v1.z, (uint32_t)v1.w};
                     tmem_st8(a_t + c * 8, r);
@@ -119,6 +161,11 @@ k_tc_fwd(const __half* __restrict__ in, const __half* __restrict__ W, __half* __
                 tc_wait_st();
                 tc_fence_before();
                 mbar_arrive(&a_ready[s]);
+                if (j + NSLOTS < my_tiles) {
+                    const size_t nrow = ((size_t)blockIdx.x + (size_t)(j + NSLOTS) * gridDim.x) * kTile + q * 32 + lane;
+#pragma unroll
+                    for (int c = 0; c < IN_DIM / 8; ++c) xin[c] = __ldg(reinterpret_cast<const int4*>(in + nrow * in_dim) + c);
+                }
             }
             for (int i = 0; i < S; ++i) {
                 mbar_wait(&d_full[s], pd);
@@ -148,12 +195,34 @@ k_tc_fwd(const __half* __restrict__ in, const __half* __restrict__ W, __half* __
                     uint32_t acc[16];
                     tmem_ld16(d_t, acc);
                     tc_wait_ld();
-                    uint32_t p[8];
+                    if (HEAD == 0) {
+                        uint32_t p[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) p[e] = pack2(__uint_as_float(acc[2 * e]), __uint_as_float(acc[2 * e + 1]));
-                    int4* dst = reinterpret_cast<int4*>(out + row * 16);
-                    dst[0] = make_int4((int)p[0], (int)p[1], (int)p[2], (int)p[3]);
-                    dst[1] = make_int4((int)p[4], (int)p[5], (int)p[6], (int)p[7]);
+                        for (int e = 0; e < 8; ++e) p[e] = pack2(__uint_as_float(acc[2 * e]), __uint_as_float(acc[2 * e + 1]));
+                        int4* dst = reinterpret_cast<int4*>(out + row * 16);
+                        dst[0] = make_int4((int)p[0], (int)p[1], (int)p[2], (int)p[3]);
+                        dst[1] = make_int4((int)p[4], (int)p[5], (int)p[6], (int)p[7]);
+                    } else if (HEAD == 1) {
+                        head.sigma[row] = expf(f16_round(__uint_as_float(acc[0])));
+                        // directions reach the SH encoder as fp16 under autocast (sphere_harmonics.py:16)
+                        const float dx = f16_round(head.dirs[row * 3]), dy = f16_round(head.dirs[row * 3 + 1]), dz = f16_round(head.dirs[row * 3 + 2]);
+                        float sh[16];
+                        sh_deg4(dx, dy, dz, sh);
+                        uint32_t p[16];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) p[e] = pack2(sh[2 * e], sh[2 * e + 1]);
+#pragma unroll
+                        for (int e = 0; e < 7; ++e) p[8 + e] = pack2(__uint_as_float(acc[1 + 2 * e]), __uint_as_float(acc[2 + 2 * e]));
+                        p[15] = pack2(__uint_as_float(acc[15]), 0.0f);
+                        int4* dst = reinterpret_cast<int4*>(head.cin + row * 32);
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) dst[v] = make_int4((int)p[4 * v], (int)p[4 * v + 1], (int)p[4 * v + 2], (int)p[4 * v + 3]);
+                    } else {
+                        for (int c = 0; c < head.n_ch; ++c) {
+                            const float y = f16_round(__uint_as_float(acc[c]));
+                            head.rgb[row * head.n_ch + c] = f16_round(1.0f / (1.0f + expf(-y)));
+                        }
+                    }
                     tc_fence_before();
                 }
             }
@@ -168,24 +237,49 @@ static size_t fwd_smem_bytes(int in_dim, int n_hidden_mm, int nslots) {
     return (size_t)in_dim * 128 + (size_t)n_hidden_mm * 8192 + 2048 + (size_t)nslots * 16 + 16;
 }
 
-int tc_forward(const __half* in, const __half* W, uint32_t B, int in_dim, int n_hidden_mm, __half* fwd_buf, __half* out, cudaStream_t st,
-               const char* name) {
+template <int IN_DIM, int HEAD>
+static int launch_fwd(const __half* in, const __half* W, uint32_t B, int n_hidden_mm, __half* fwd_buf, __half* out, HeadArgs head, cudaStream_t st,
+                      const char* name) {
     constexpr int NSLOTS = 4;
-    size_t smem = fwd_smem_bytes(in_dim, n_hidden_mm, NSLOTS);
+    size_t smem = fwd_smem_bytes(IN_DIM, n_hidden_mm, NSLOTS);
     if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: it allocates all 512 TMEM columns
     if (smem > 200 * 1024) { set_error("%s: network too deep for the tcgen05 path", name); return -2; }
     static size_t configured = 0;
     if (smem > configured) {
-        ENERF_CUDA(cudaFuncSetAttribute(k_tc_fwd<NSLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
+        ENERF_CUDA(cudaFuncSetAttribute(k_tc_fwd<NSLOTS, IN_DIM, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
         configured = smem;
     }
     const uint32_t n_tiles = B / kTile;
     const uint32_t grid = n_tiles < (uint32_t)kNumSM ? n_tiles : (uint32_t)kNumSM;
-    k_tc_fwd<NSLOTS><<<grid, 32 + NSLOTS * 128, smem, st>>>(in, W, fwd_buf, out, n_tiles, B, in_dim, n_hidden_mm);
+    k_tc_fwd<NSLOTS, IN_DIM, HEAD><<<grid, 32 + NSLOTS * 128, smem, st>>>(in, W, fwd_buf, out, n_tiles, B, n_hidden_mm, head);
     ENERF_CHECK_LAUNCH(name);
     return 0;
 }
 
+int tc_forward(const __half* in, const __half* W, uint32_t B, int in_dim, int n_hidden_mm, __half* fwd_buf, __half* out, cudaStream_t st,
+               const char* name) {
+    HeadArgs none = {nullptr, nullptr, nullptr, nullptr, 0};
+    switch (in_dim) {
+        case 16: return launch_fwd<16, 0>(in, W, B, n_hidden_mm, fwd_buf, out, none, st, name);
+        case 32: return launch_fwd<32, 0>(in, W, B, n_hidden_mm, fwd_buf, out, none, st, name);
+        case 48: return launch_fwd<48, 0>(in, W, B, n_hidden_mm, fwd_buf, out, none, st, name);
+        case 64: return launch_fwd<64, 0>(in, W, B, n_hidden_mm, fwd_buf, out, none, st, name);
+    }
+    set_error("%s: input_dim must be 16, 32, 48 or 64 on the tcgen05 path", name);
+    return -2;
+}
+
+// sigma-net with fused exp / SH / colour-input head (input_dim 32)
+int tc_forward_sigma_head(const __half* feat, const __half* W, uint32_t B, int n_hidden_mm, __half* fwd_buf, const float* dirs, float* sigma,
+                          __half* cin, cudaStream_t st) {
+    HeadArgs h = {dirs, sigma, cin, nullptr, 0};
+    return launch_fwd<32, 1>(feat, W, B, n_hidden_mm, fwd_buf, nullptr, h, st, "field_sigma_forward");
+}
+// colour-net with fused sigmoid head (input_dim 32)
+int tc_forward_rgb_head(const __half* cin, const __half* W, uint32_t B, int n_hidden_mm, __half* fwd_buf, float* rgb, int n_ch, cudaStream_t st) {
+    HeadArgs h = {nullptr, nullptr, nullptr, rgb, n_ch};
+    return launch_fwd<32, 2>(cin, W, B, n_hidden_mm, fwd_buf, nullptr, h, st, "field_color_forward");
+}
 
 // ================================================================================================
 // Backward (k_tc_bwd): activation gradients AND weight gradients in one persistent kernel.
@@ -210,11 +304,25 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int NSLOTS>
+// Optional fused prologues (where dL/dy of the network comes from):
+//   PRO 0: dy [B,16] fp16 as given
+//   PRO 1 (colour-net): dy[c] = fp16(g_rgb[c]) * rgb[c] * (1 - rgb[c]) for c < n_ch (sigmoid'), 0 otherwise
+//   PRO 2 (sigma-net) : dy[0] = g_sigma * exp(clamp(h0, -15, 15)) (trunc_exp', activation.py:15-18; h0 = log sigma),
+//                       dy[1:16] = dL/d(colour-net input)[16:31] (the geo_feat columns)
+struct ProArgs {
+    const float* g_rgb;     // [B,n_ch]  (PRO 1)
+    const float* rgb;       // [B,n_ch]  (PRO 1)
+    int n_ch;
+    const float* g_sigma;   // [B]       (PRO 2)
+    const float* sigma;     // [B]       (PRO 2)
+    const __half* dcin;     // [B,32]    (PRO 2)
+};
+
+template <int NSLOTS, int PRO>
 __global__ void __launch_bounds__(32 + NSLOTS * 128, 1)
 k_tc_bwd(const __half* __restrict__ grad, const __half* __restrict__ x, const __half* __restrict__ W, const __half* __restrict__ fwd_buf,
          __half* __restrict__ bwd_buf, __half* __restrict__ grad_inputs, float* __restrict__ dW, uint32_t n_tiles, uint32_t B, int in_dim,
-         int n_hidden_mm) {
+         int n_hidden_mm, ProArgs pro) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* w0s = smem;                                  // [in_dim/8][64][16 B]   (forward layout)
     uint8_t* whs = w0s + in_dim * 128;                    // n_hidden_mm x [8][64][16 B]
@@ -318,8 +426,33 @@ k_tc_bwd(const __half* __restrict__ grad, const __half* __restrict__ x, const __
             const size_t row = tile * kTile + r_in_tile;
             // ---- E_0: dy -> TMEM A + dy tile (G buffer); h_n -> registers + H tile
             {
-                const int4* src = reinterpret_cast<const int4*>(grad + row * 16);
-                const int4 v0 = __ldg(src), v1 = __ldg(src + 1);
+                int4 v0, v1;
+                if (PRO == 0) {
+                    const int4* src = reinterpret_cast<const int4*>(grad + row * 16);
+                    v0 = __ldg(src);
+                    v1 = __ldg(src + 1);
+                } else if (PRO == 1) {
+                    float dyv[4] = {0.f, 0.f, 0.f, 0.f};
+                    for (int c = 0; c < pro.n_ch; ++c) {
+                        const float y = pro.rgb[row * pro.n_ch + c];
+                        dyv[c] = f16_round(pro.g_rgb[row * pro.n_ch + c]) * (1.0f - y) * y;
+                    }
+                    v0 = make_int4((int)pack2(dyv[0], dyv[1]), (int)pack2(dyv[2], dyv[3]), 0, 0);
+                    v1 = make_int4(0, 0, 0, 0);
+                } else {
+                    const float sg = fminf(fmaxf(pro.sigma[row], 3.0590232050182579e-07f), 3269017.3724721107f);   // exp(-15), exp(15)
+                    const __half d0 = __float2half_rn(pro.g_sigma[row] * sg);
+                    // dcin columns 16..30 -> dy columns 1..15 (shift by one fp16)
+                    const int4* src = reinterpret_cast<const int4*>(pro.dcin + row * 32 + 16);
+                    const int4 a = __ldg(src), b = __ldg(src + 1);
+                    const uint32_t w[8] = {(uint32_t)a.x, (uint32_t)a.y, (uint32_t)a.z, (uint32_t)a.w, (uint32_t)b.x, (uint32_t)b.y, (uint32_t)b.z, (uint32_t)b.w};
+                    uint32_t o[8];
+                    o[0] = (uint32_t)__half_as_ushort(d0) | (w[0] << 16);
+#pragma unroll
+                    for (int e = 1; e < 8; ++e) o[e] = (w[e - 1] >> 16) | (w[e] << 16);
+                    v0 = make_int4((int)o[0], (int)o[1], (int)o[2], (int)o[3]);
+                    v1 = make_int4((int)o[4], (int)o[5], (int)o[6], (int)o[7]);
+                }
                 const uint32_t r8[8] = {(uint32_t)v0.x, (uint32_t)v0.y, (uint32_t)v0.z, (uint32_t)v0.w,
                                         (uint32_t)v1.x, (uint32_t)v1.y, (uint32_t)v1.z, (uint32_t)v1.w};
                 tmem_st8(a_t, r8);
@@ -451,24 +584,41 @@ k_tc_bwd(const __half* __restrict__ grad, const __half* __restrict__ x, const __
     if (warp == 0) tmem_dealloc(tmem0, kCols);
 }
 
-int tc_backward(const __half* grad, const __half* x, const __half* W, const __half* fwd_buf, __half* bwd_buf, __half* grad_inputs, float* dW,
-                uint32_t B, int in_dim, int n_hidden_mm, cudaStream_t st) {
+template <int PRO>
+static int launch_bwd(const __half* grad, const __half* x, const __half* W, const __half* fwd_buf, __half* bwd_buf, __half* grad_inputs, float* dW,
+                      uint32_t B, int in_dim, int n_hidden_mm, ProArgs pro, cudaStream_t st, const char* name) {
     constexpr int NSLOTS = 2;
     // TMEM: NSLOTS*96 + 16 + 64*n_hidden_mm + in_dim columns
-    if (NSLOTS * kSlotCols + 16 + 64 * n_hidden_mm + in_dim > 512) { set_error("ffmlp_backward: network too deep for the tcgen05 path"); return -2; }
+    if (NSLOTS * kSlotCols + 16 + 64 * n_hidden_mm + in_dim > 512) { set_error("%s: network too deep for the tcgen05 path", name); return -2; }
     size_t smem = (size_t)in_dim * 128 + (size_t)n_hidden_mm * 8192 + 2048 + (size_t)NSLOTS * 2 * kGBytes + (2 * NSLOTS + 1) * 8 + 16;
     if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: it allocates all 512 TMEM columns
-    if (smem > 220 * 1024) { set_error("ffmlp_backward: network too deep for the tcgen05 path"); return -2; }
+    if (smem > 220 * 1024) { set_error("%s: network too deep for the tcgen05 path", name); return -2; }
     static size_t configured = 0;
     if (smem > configured) {
-        ENERF_CUDA(cudaFuncSetAttribute(k_tc_bwd<NSLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "ffmlp_backward");
+        ENERF_CUDA(cudaFuncSetAttribute(k_tc_bwd<NSLOTS, PRO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
         configured = smem;
     }
     const uint32_t n_tiles = B / kTile;
     const uint32_t grid = n_tiles < (uint32_t)kNumSM ? n_tiles : (uint32_t)kNumSM;
-    k_tc_bwd<NSLOTS><<<grid, 32 + NSLOTS * 128, smem, st>>>(grad, x, W, fwd_buf, bwd_buf, grad_inputs, dW, n_tiles, B, in_dim, n_hidden_mm);
-    ENERF_CHECK_LAUNCH("ffmlp_backward");
+    k_tc_bwd<NSLOTS, PRO><<<grid, 32 + NSLOTS * 128, smem, st>>>(grad, x, W, fwd_buf, bwd_buf, grad_inputs, dW, n_tiles, B, in_dim, n_hidden_mm, pro);
+    ENERF_CHECK_LAUNCH(name);
     return 0;
+}
+
+int tc_backward(const __half* grad, const __half* x, const __half* W, const __half* fwd_buf, __half* bwd_buf, __half* grad_inputs, float* dW,
+                uint32_t B, int in_dim, int n_hidden_mm, cudaStream_t st) {
+    ProArgs none = {nullptr, nullptr, 0, nullptr, nullptr, nullptr};
+    return launch_bwd<0>(grad, x, W, fwd_buf, bwd_buf, grad_inputs, dW, B, in_dim, n_hidden_mm, none, st, "ffmlp_backward");
+}
+int tc_backward_rgb(const float* g_rgb, const float* rgb, int n_ch, const __half* cin, const __half* W, const __half* fwd_buf, __half* dcin, float* dW,
+                    uint32_t B, int n_hidden_mm, cudaStream_t st) {
+    ProArgs p = {g_rgb, rgb, n_ch, nullptr, nullptr, nullptr};
+    return launch_bwd<1>(nullptr, cin, W, fwd_buf, nullptr, dcin, dW, B, 32, n_hidden_mm, p, st, "field_color_backward");
+}
+int tc_backward_sigma(const float* g_sigma, const float* sigma, const __half* dcin, const __half* feat, const __half* W, const __half* fwd_buf,
+                      __half* dfeat, float* dW, uint32_t B, int n_hidden_mm, cudaStream_t st) {
+    ProArgs p = {nullptr, nullptr, 0, g_sigma, sigma, dcin};
+    return launch_bwd<2>(nullptr, feat, W, fwd_buf, nullptr, dfeat, dW, B, 32, n_hidden_mm, p, st, "field_sigma_backward");
 }
 
 }  // namespace tcm

@@ -1,0 +1,62 @@
+"""Fused E-NeRF field (nerf/network_ff.py:51-73): sigma-net -> trunc_exp -> [SH | geo_feat | 0] ->
+colour-net -> sigmoid, with the glue (exp, SH encoder, cat, zeros_like, sigmoid and their
+backward) folded into the heads / prologues of the tcgen05 MLP kernels.  Values follow the
+unfused module chain step by step (same fp16 rounding points); what disappears is ~1 GB of HBM
+traffic and ~20 small kernels per step.
+
+`fused_field(feat, dirs, w_sigma, w_color, nl_sigma, nl_color, n_ch, training)` ->
+(sigma [S] fp32, rgb [S,n_ch] fp32).  Differentiable in feat, w_sigma, w_color.
+"""
+import torch
+from torch.autograd import Function
+
+from . import _lib
+from ._lib import ptr, stream
+
+
+def eligible(feat, dirs, hidden_dim, hidden_dim_color, in_dim, in_dim_color, geo_feat_dim, sh_degree, n_ch, activation):
+    return (feat.is_cuda and feat.dtype == torch.float16 and feat.shape[0] % 128 == 0 and feat.shape[0] > 0 and hidden_dim == 64
+            and hidden_dim_color == 64 and in_dim == 32 and in_dim_color == 32 and geo_feat_dim == 15 and sh_degree == 4 and 1 <= n_ch <= 4
+            and activation == 0 and dirs.shape[0] == feat.shape[0])
+
+
+class _FusedField(Function):
+    @staticmethod
+    def forward(ctx, feat, dirs, w_sigma, w_color, nl_sigma, nl_color, n_ch, training):
+        S = feat.shape[0]
+        dev = feat.device
+        feat = feat.contiguous()
+        dirs = dirs.contiguous().float()
+        ws, wc = w_sigma.detach().half().contiguous(), w_color.detach().half().contiguous()
+        sigma = torch.empty(S, dtype=torch.float32, device=dev)
+        cin = torch.empty(S, 32, dtype=torch.float16, device=dev)
+        rgb = torch.empty(S, n_ch, dtype=torch.float32, device=dev)
+        fb_s = torch.empty(nl_sigma, S, 64, dtype=torch.float16, device=dev) if training else None
+        fb_c = torch.empty(nl_color, S, 64, dtype=torch.float16, device=dev) if training else None
+        _lib.call("enerf_field_sigma_forward", ptr(feat), ptr(ws), ptr(dirs), S, nl_sigma, ptr(fb_s), ptr(sigma), ptr(cin), stream())
+        _lib.call("enerf_field_color_forward", ptr(cin), ptr(wc), S, nl_color, n_ch, ptr(fb_c), ptr(rgb), stream())
+        if training:
+            ctx.save_for_backward(feat, ws, wc, sigma, cin, rgb, fb_s, fb_c)
+            ctx.meta = (nl_sigma, nl_color, n_ch, w_sigma.dtype, w_color.dtype)
+        return sigma, rgb
+
+    @staticmethod
+    def backward(ctx, g_sigma, g_rgb):
+        feat, ws, wc, sigma, cin, rgb, fb_s, fb_c = ctx.saved_tensors
+        nl_sigma, nl_color, n_ch, dt_s, dt_c = ctx.meta
+        S = feat.shape[0]
+        dev = feat.device
+        g_sigma = torch.zeros_like(sigma) if g_sigma is None else g_sigma.contiguous().float()
+        g_rgb = torch.zeros_like(rgb) if g_rgb is None else g_rgb.contiguous().float()
+        dcin = torch.empty(S, 32, dtype=torch.float16, device=dev)
+        dfeat = torch.empty(S, 32, dtype=torch.float16, device=dev)
+        gw_c = torch.empty(wc.numel(), dtype=torch.float32, device=dev)
+        gw_s = torch.empty(ws.numel(), dtype=torch.float32, device=dev)
+        _lib.call("enerf_field_color_backward", ptr(g_rgb), ptr(rgb), n_ch, ptr(cin), ptr(wc), ptr(fb_c), S, nl_color, ptr(dcin), ptr(gw_c), stream())
+        _lib.call("enerf_field_sigma_backward", ptr(g_sigma), ptr(sigma), ptr(dcin), ptr(feat), ptr(ws), ptr(fb_s), S, nl_sigma, ptr(dfeat),
+                  ptr(gw_s), stream())
+        return dfeat, None, gw_s.to(dt_s), gw_c.to(dt_c), None, None, None, None
+
+
+def fused_field(feat, dirs, w_sigma, w_color, nl_sigma, nl_color, n_ch, training):
+    return _FusedField.apply(feat, dirs, w_sigma, w_color, nl_sigma, nl_color, n_ch, training)

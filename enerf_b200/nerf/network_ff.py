@@ -7,6 +7,7 @@ Unlike the reference at HEAD (whose ff variant crashes on `out_dim_color` /
 """
 import torch
 
+from .. import field
 from ..activation import trunc_exp
 from ..encoding import get_encoder
 from ..ffmlp import FFMLP
@@ -22,6 +23,7 @@ class NeRFNetwork(NeRFRenderer):
         self.geo_feat_dim = geo_feat_dim
         self.out_dim_color = out_dim_color
         self.disable_view_direction = disable_view_direction
+        self.fuse_field = True      # fused sigma/colour heads (enerf_b200.field) when shapes allow; False = module chain
         self.encoder, self.in_dim = get_encoder(encoding, desired_resolution=2048 * bound)
         self.sigma_net = FFMLP(input_dim=self.in_dim, output_dim=1 + self.geo_feat_dim, hidden_dim=self.hidden_dim, num_layers=self.num_layers)
 
@@ -41,7 +43,15 @@ class NeRFNetwork(NeRFRenderer):
 
     def forward(self, x, d):
         # x [N,3] in [-bound,bound], d [N,3] unit -> sigma [N] fp32, rgb [N,C]
-        h = self.sigma_net(self.encoder(x, bound=self.bound))
+        if self.fuse_field and torch.is_autocast_enabled('cuda') and not self.disable_view_direction:
+            feat = self.encoder(x, bound=self.bound)
+            if field.eligible(feat, d, self.hidden_dim, self.hidden_dim_color, self.in_dim, self.in_dim_color, self.geo_feat_dim,
+                              getattr(self.encoder_dir, 'degree', -1), self.out_dim_color, self.sigma_net.activation):
+                return field.fused_field(feat, d, self.sigma_net.weights, self.color_net.weights, self.num_layers, self.num_layers_color,
+                                         self.out_dim_color, self.training and torch.is_grad_enabled())
+            h = self.sigma_net(feat)
+        else:
+            h = self.sigma_net(self.encoder(x, bound=self.bound))
         sigma = trunc_exp(h[..., 0])
         geo_feat = h[..., 1:]
         rgb = torch.sigmoid(self.color_net(self._color_inputs(d, geo_feat)))

@@ -181,6 +181,27 @@ int enerf_ffmlp_uses_tcgen05(uint32_t input_dim, uint32_t hidden_dim, uint32_t n
 int enerf_free_splitk(void);
 
 /* ---------------------------------------------------- fused extras (no reference ABI) ---- */
+/* The E-NeRF field of nerf/network_ff.py:51-73 with its glue fused into the MLP kernels (tcgen05
+ * path: hidden 64, ReLU, 32 inputs, B % 128 == 0, fp16 operands):
+ *   sigma-net head : h = fp16(sigma_net(feat)); sigma = exp(h[0]) (trunc_exp, activation.py:10);
+ *                    cin = [SH_4(fp16(dir)) | h[1:16] | 0]   (shencoder + torch.cat + zeros_like)
+ *   colour-net head: rgb[c] = sigmoid(fp16(color_net(cin))[c]), c < n_ch, as fp32
+ *   backward       : the prologues apply sigmoid' / trunc_exp' and pick the geo_feat columns.
+ * forward_buffer [num_layers,B,64] may be NULL for inference.  grad_weights: fp32, overwritten. */
+int enerf_field_sigma_forward(const uint16_t* feat, const uint16_t* weights, const float* dirs, uint32_t B,
+                              uint32_t num_layers, uint16_t* forward_buffer, float* sigma, uint16_t* cin,
+                              void* stream);
+int enerf_field_color_forward(const uint16_t* cin, const uint16_t* weights, uint32_t B, uint32_t num_layers,
+                              uint32_t n_ch, uint16_t* forward_buffer, float* rgb, void* stream);
+int enerf_field_color_backward(const float* grad_rgb, const float* rgb, uint32_t n_ch, const uint16_t* cin,
+                               const uint16_t* weights, const uint16_t* forward_buffer, uint32_t B,
+                               uint32_t num_layers, uint16_t* grad_cin, float* grad_weights, void* stream);
+int enerf_field_sigma_backward(const float* grad_sigma, const float* sigma, const uint16_t* grad_cin,
+                               const uint16_t* feat, const uint16_t* weights, const uint16_t* forward_buffer,
+                               uint32_t B, uint32_t num_layers, uint16_t* grad_feat, float* grad_weights,
+                               void* stream);
+
+
 /* Fixed-step integrator of NeRFRenderer.run (nerf/renderer.py:230-255), which the reference
  * evaluates as ~25 ATen kernels over [N,T] temporaries.  One warp per ray:
  *   delta_i = z_{i+1}-z_i, last = (far-near)/T           (renderer.py:230-231)

@@ -196,3 +196,44 @@ def test_density_grid_maintenance():
     with torch.autocast("cuda", dtype=torch.float16):
         model.update_extra_state()
     assert model.mean_count > 0 and model.local_step == 0
+
+
+@pytest.mark.parametrize("n_ch", [1, 3])
+def test_fused_field_matches_module_chain(n_ch):
+    """enerf_b200.field (heads/prologues fused into the tcgen05 MLP kernels) vs the unfused module chain
+    (encoder -> FFMLP -> trunc_exp -> SHEncoder -> cat -> FFMLP -> sigmoid): same values up to one fp16 ulp of the
+    intermediate activations, same gradients up to fp16 rounding of the activation gradients."""
+    bound = 2
+    torch.manual_seed(4)
+    model = FFNet(bound=bound, cuda_ray=True, out_dim_color=n_ch).to(DEV).train()
+    with torch.no_grad():
+        model.encoder.embeddings.uniform_(-0.5, 0.5)
+    S = 128 * 37
+    x = (torch.rand(S, 3, device=DEV) * 2 - 1) * bound
+    d = torch.randn(S, 3, device=DEV)
+    d = d / d.norm(dim=-1, keepdim=True)
+    gs = torch.randn(S, device=DEV) * 0.1
+    gr = torch.randn(S, n_ch, device=DEV)
+    res = {}
+    for fused in (True, False):
+        model.fuse_field = fused
+        model.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.float16):
+            sigma, rgb = model(x, d)
+        ((sigma * gs).sum() + (rgb.float() * gr).sum()).backward()
+        res[fused] = (sigma.detach().float(), rgb.detach().float(), model.encoder.embeddings.grad.clone(), model.sigma_net.weights.grad.clone(),
+                      model.color_net.weights.grad.clone())
+    model.fuse_field = True
+    a, b = res[True], res[False]
+    assert a[1].dtype == torch.float32 and a[1].shape == (S, n_ch)
+    assert torch.allclose(a[0], b[0], rtol=2e-3, atol=1e-6), float((a[0] - b[0]).abs().max())
+    assert torch.allclose(a[1], b[1], atol=2e-3), float((a[1] - b[1]).abs().max())
+    for i, name in ((2, "embeddings"), (3, "sigma_net"), (4, "color_net")):
+        ga, gb = a[i].double().reshape(-1), b[i].double().reshape(-1)
+        cos = float(ga @ gb / (ga.norm() * gb.norm() + 1e-300))
+        assert cos > 0.999 and float((ga - gb).abs().max()) <= 3e-2 * float(gb.abs().max()) + 1e-12, (name, cos)
+    # inference mode: same values, no autograd state kept
+    model.eval()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        s2, r2 = model(x, d)
+    assert torch.allclose(s2, a[0], rtol=1e-6) and torch.allclose(r2, a[1], atol=1e-6)
