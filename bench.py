@@ -239,6 +239,10 @@ def our_arm(args):
         "enerf_grid_encode_backward": ("hbm", 1100.0 * S),
         "enerf_ffmlp_forward": ("tensor", 36864.0 * S),
         "enerf_ffmlp_backward": ("tensor", 73728.0 * S),
+        "enerf_field_sigma_forward": ("tensor", 14336.0 * S),
+        "enerf_field_color_forward": ("tensor", 22528.0 * S),
+        "enerf_field_sigma_backward": ("tensor", 2 * 14336.0 * S),
+        "enerf_field_color_backward": ("tensor", 2 * 22528.0 * S),
         "enerf_march_rays_train": ("hbm", 32.0 * S + 44.0 * n_rays),
         "enerf_composite_rays_train_forward": ("hbm", 16.0 * S + 32.0 * n_rays),
         "enerf_composite_rays_train_backward": ("hbm", 24.0 * S + 44.0 * n_rays),

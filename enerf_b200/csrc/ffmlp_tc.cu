@@ -420,6 +420,15 @@ k_tc_bwd(const __half* __restrict__ grad, const __half* __restrict__ x, const __
         uint8_t* h_tile = g_tile + kGBytes;
         uint32_t pd = 0;
         uint32_t hreg[32];       // this row's forward activation (64 fp16) used as ReLU mask by the next epilogue
+        // Global rows needed by the NEXT epilogue stage are requested before waiting for the tensor core, so
+        // their HBM latency overlaps the MMAs: `pre` = h_n row of the tile about to start, `nxt` = next stage's row.
+        int4 pre[8];
+        if ((uint32_t)s < my_tiles) {
+            const size_t row0 = ((size_t)blockIdx.x + (size_t)s * gridDim.x) * kTile + r_in_tile;
+            const int4* hs0 = reinterpret_cast<const int4*>(fwd_buf + ((size_t)n_hidden_mm * B + row0) * kW);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) pre[c] = __ldg(hs0 + c);
+        }
 
         for (uint32_t j = s; j < my_tiles; j += NSLOTS) {
             const size_t tile = (size_t)blockIdx.x + (size_t)j * gridDim.x;
@@ -458,10 +467,9 @@ k_tc_bwd(const __half* __restrict__ grad, const __half* __restrict__ x, const __
                 tmem_st8(a_t, r8);
                 *reinterpret_cast<int4*>(g_tile + 0 * 2048 + r_in_tile * 16) = v0;
                 *reinterpret_cast<int4*>(g_tile + 1 * 2048 + r_in_tile * 16) = v1;
-                const int4* hs = reinterpret_cast<const int4*>(fwd_buf + ((size_t)n_hidden_mm * B + row) * kW);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    const int4 v = __ldg(hs + c);
+                    const int4 v = pre[c];
                     hreg[4 * c] = (uint32_t)v.x; hreg[4 * c + 1] = (uint32_t)v.y; hreg[4 * c + 2] = (uint32_t)v.z; hreg[4 * c + 3] = (uint32_t)v.w;
                     *reinterpret_cast<int4*>(h_tile + c * 2048 + r_in_tile * 16) = v;
                 }
@@ -472,6 +480,16 @@ k_tc_bwd(const __half* __restrict__ grad, const __half* __restrict__ x, const __
             }
             // ---- E_k, k = 1 .. S-1: g = D * relu'(h) -> TMEM A + G tile; next activation (or x) -> H tile
             for (int k = 1; k < S; ++k) {
+                int4 nxt[8];
+                if (k < S - 1) {
+                    const int4* hs = reinterpret_cast<const int4*>(fwd_buf + ((size_t)(n_hidden_mm - k) * B + row) * kW);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) nxt[c] = __ldg(hs + c);
+                } else {
+                    const int4* xs = reinterpret_cast<const int4*>(x + row * in_dim);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) nxt[c] = (c < in_dim / 8) ? __ldg(xs + c) : make_int4(0, 0, 0, 0);
+                }
                 mbar_wait(&d_full[s], pd);
                 pd ^= 1;
                 tc_fence_after();
@@ -497,17 +515,11 @@ k_tc_bwd(const __half* __restrict__ grad, const __half* __restrict__ x, const __
                         if (bb) reinterpret_cast<int4*>(bb)[h * 4 + v] = val;
                     }
                 }
-                if (k < S - 1) {
-                    const int4* hs = reinterpret_cast<const int4*>(fwd_buf + ((size_t)(n_hidden_mm - k) * B + row) * kW);
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const int4 v = __ldg(hs + c);
-                        hreg[4 * c] = (uint32_t)v.x; hreg[4 * c + 1] = (uint32_t)v.y; hreg[4 * c + 2] = (uint32_t)v.z; hreg[4 * c + 3] = (uint32_t)v.w;
-                        *reinterpret_cast<int4*>(h_tile + c * 2048 + r_in_tile * 16) = v;
-                    }
-                } else {
-                    const int4* xs = reinterpret_cast<const int4*>(x + row * in_dim);
-                    for (int c = 0; c < in_dim / 8; ++c) *reinterpret_cast<int4*>(h_tile + c * 2048 + r_in_tile * 16) = __ldg(xs + c);
+                for (int c = 0; c < 8; ++c) {
+                    const int4 v = nxt[c];
+                    hreg[4 * c] = (uint32_t)v.x; hreg[4 * c + 1] = (uint32_t)v.y; hreg[4 * c + 2] = (uint32_t)v.z; hreg[4 * c + 3] = (uint32_t)v.w;
+                    if (k < S - 1 || c < in_dim / 8) *reinterpret_cast<int4*>(h_tile + c * 2048 + r_in_tile * 16) = v;
                 }
                 tc_wait_st();
                 fence_proxy_async_smem();
@@ -515,6 +527,12 @@ k_tc_bwd(const __half* __restrict__ grad, const __half* __restrict__ x, const __
                 mbar_arrive(&a_ready[s]);
             }
             // ---- E_S: dx
+            if (j + NSLOTS < my_tiles) {
+                const size_t nrow = ((size_t)blockIdx.x + (size_t)(j + NSLOTS) * gridDim.x) * kTile + r_in_tile;
+                const int4* hs0 = reinterpret_cast<const int4*>(fwd_buf + ((size_t)n_hidden_mm * B + nrow) * kW);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) pre[c] = __ldg(hs0 + c);
+            }
             mbar_wait(&d_full[s], pd);
             pd ^= 1;
             tc_fence_after();
