@@ -35,6 +35,7 @@ _SIGS = {
     "enerf_grid_encode_forward": [_p, _p, _p, _p, _u32, _u32, _u32, _u32, _f32, _u32, _int, _p, _u32, _int, _int, _p],
     "enerf_grid_encode_backward": [_p, _p, _p, _p, _p, _u32, _u32, _u32, _u32, _f32, _u32, _int, _p, _p, _u32, _int, _int, _int, _p],
     "enerf_grid_set_backward_mode": [_int],
+    "enerf_grid_set_forward_mode": [_int],
     "enerf_sh_encode_forward": [_p, _p, _u32, _u32, _u32, _int, _p, _int, _p],
     "enerf_sh_encode_backward": [_p, _p, _u32, _u32, _u32, _p, _p, _int, _p],
     "enerf_ffmlp_forward": [_p, _p, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _p, _p, _p],

@@ -21,6 +21,7 @@ namespace enerf {
 
 static constexpr unsigned kFull = 0xffffffffu;
 static constexpr int kSamplesPerCta = 32;
+static int g_fwd_fast = 1;   // 1: k_grid_fwd3 for D = 3 without input gradients, 0: always the generic kernel
 static int g_bwd_walk = 1;   // 1: walking scatter (register aggregation along rays), 0: one reduction per corner
 
 // ---- element-type helpers: the accumulator is rounded to T after every corner -----------
@@ -231,6 +232,143 @@ k_grid_fwd(const float* __restrict__ inputs, const T* __restrict__ grid, const i
 }
 
 // ------------------------------------------------------------------------------------------
+// forward, hot path (D = 3, no input gradients): same arithmetic as k_grid_fwd with the per-level
+// constants computed once per CTA (shared memory), per-axis index terms and weights hoisted out
+// of the corner loop (w = (wx*wy)*wz in the reference's order), and packed fp16x2 arithmetic for
+// the fp16/C=2 table: cvt.rn.f16x2.f32 of the two fp32 products + one HADD2 per corner is
+// bit-identical to the reference's "round the product, add in fp32, round again" because the sum
+// of two fp16 numbers is either exact in fp32 or dominated by the larger operand.
+// ------------------------------------------------------------------------------------------
+struct LevelTab {
+    float scale;
+    uint32_t hs, offset, m1, m2, flags;   // flags: bit0 = hashed, bit1 = table size is a power of two
+};
+
+template <typename T, int C, bool BLC>
+__global__ void __launch_bounds__(512)
+k_grid_fwd3(const float* __restrict__ inputs, const T* __restrict__ grid, const int32_t* __restrict__ offsets,
+            T* __restrict__ outputs, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype, uint32_t row_stride) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* stage = reinterpret_cast<T*>(smem_raw);
+    __shared__ LevelTab ltab[64];
+
+    const unsigned lane = threadIdx.x;
+    const uint32_t tid = threadIdx.y * 32 + lane;
+    if (tid < L) {
+        const LevelGeom g = level_geom(offsets, tid, S, H, gridtype, 3);
+        LevelTab t;
+        t.scale = g.scale;
+        t.hs = g.hashmap_size;
+        t.offset = g.offset;
+        const uint32_t r1 = g.resolution + 1;
+        if (g.use_hash) {
+            t.m1 = 2654435761u;
+            t.m2 = 805459861u;
+        } else {                                 // the stride loop of gridencoder.cu:58-62, dimension by dimension
+            t.m1 = (r1 <= g.hashmap_size) ? r1 : 0u;
+            t.m2 = (t.m1 != 0u && r1 * r1 <= g.hashmap_size) ? r1 * r1 : 0u;
+        }
+        t.flags = (g.use_hash ? 1u : 0u) | (g.pow2 ? 2u : 0u);
+        ltab[tid] = t;
+    }
+    __syncthreads();
+
+    const uint32_t b0 = blockIdx.x * kSamplesPerCta;
+    const uint32_t b = b0 + lane;
+    const bool active = b < B;
+    float x[3];
+    bool oob = true;
+    if (active) oob = load_pos<3>(inputs, b, x);
+
+    for (uint32_t level = threadIdx.y; level < L; level += blockDim.y) {
+        T res[C];
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) res[ch] = Elem<T>::from_f(0.f);
+        __half2 res2 = __floats2half2_rn(0.f, 0.f);
+
+        if (active && !oob) {
+            const LevelTab lt = ltab[level];
+            const T* __restrict__ tab = grid + (size_t)lt.offset * C;
+            float fr[3];
+            uint32_t pg[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const float p = __fmaf_rn(x[d], lt.scale, 0.5f);
+                const float fl = floorf(p);
+                pg[d] = (uint32_t)fl;
+                fr[d] = p - fl;
+            }
+            const float wx[2] = {1.0f - fr[0], fr[0]}, wy[2] = {1.0f - fr[1], fr[1]}, wz[2] = {1.0f - fr[2], fr[2]};
+            const float wxy[4] = {wx[0] * wy[0], wx[1] * wy[0], wx[0] * wy[1], wx[1] * wy[1]};
+            const uint32_t ax[2] = {pg[0], pg[0] + 1};
+            const uint32_t ay[2] = {pg[1] * lt.m1, (pg[1] + 1) * lt.m1};
+            const uint32_t az[2] = {pg[2] * lt.m2, (pg[2] + 1) * lt.m2};
+            const bool hashed = lt.flags & 1u, pow2 = lt.flags & 2u;
+            uint32_t e[8];
+#pragma unroll
+            for (int idx = 0; idx < 8; ++idx) {
+                const uint32_t a = ax[idx & 1], bq = ay[(idx >> 1) & 1], c = az[idx >> 2];
+                uint32_t i = hashed ? (a ^ bq ^ c) : (a + bq + c);
+                i = pow2 ? (i & (lt.hs - 1)) : (i < lt.hs ? i : i % lt.hs);
+                e[idx] = i * C;
+            }
+            if (C == 2 && sizeof(T) == 2) {
+                __half2 v[8];
+#pragma unroll
+                for (int idx = 0; idx < 8; ++idx) v[idx] = __ldg(reinterpret_cast<const __half2*>(tab + e[idx]));
+#pragma unroll
+                for (int idx = 0; idx < 8; ++idx) {
+                    const float w = wxy[idx & 3] * wz[idx >> 2];
+                    const float2 g = __half22float2(v[idx]);
+                    res2 = __hadd2(res2, __floats2half2_rn(w * g.x, w * g.y));
+                }
+            } else {
+                T v[8][C];
+#pragma unroll
+                for (int idx = 0; idx < 8; ++idx)
+#pragma unroll
+                    for (int ch = 0; ch < C; ++ch) v[idx][ch] = Elem<T>::ld(tab + e[idx] + ch);
+#pragma unroll
+                for (int idx = 0; idx < 8; ++idx) {
+                    const float w = wxy[idx & 3] * wz[idx >> 2];
+#pragma unroll
+                    for (int ch = 0; ch < C; ++ch) res[ch] = Elem<T>::acc(res[ch], w, v[idx][ch]);
+                }
+            }
+        }
+        if (C == 2 && sizeof(T) == 2) {
+            res[0] = *reinterpret_cast<const T*>(&res2.x);
+            res[C - 1] = *reinterpret_cast<const T*>(&res2.y);
+        }
+
+        if (BLC) {
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) stage[lane * row_stride + level * C + ch] = res[ch];
+        } else if (active) {
+            T* __restrict__ o = outputs + ((size_t)level * B + b) * C;
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) o[ch] = res[ch];
+        }
+    }
+
+    if (BLC) {
+        __syncthreads();
+        const uint32_t row_elems = L * C;
+        const uint32_t n_rows = min((uint32_t)kSamplesPerCta, B - b0);
+        const uint32_t nthr = blockDim.y * 32;
+        T* __restrict__ out = outputs + (size_t)b0 * row_elems;
+        if (((row_elems * sizeof(T)) & 3u) == 0 && ((row_stride * sizeof(T)) & 3u) == 0) {
+            const uint32_t rw = row_elems * sizeof(T) / 4, sw = row_stride * sizeof(T) / 4;
+            const uint32_t* s32 = reinterpret_cast<const uint32_t*>(stage);
+            uint32_t* o32 = reinterpret_cast<uint32_t*>(out);
+            for (uint32_t k = tid; k < n_rows * rw; k += nthr) o32[k] = s32[(k / rw) * sw + (k % rw)];
+        } else {
+            for (uint32_t k = tid; k < n_rows * row_elems; k += nthr) out[k] = stage[(k / row_elems) * row_stride + (k % row_elems)];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // backward (scatter-add into the gradient table)
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void red_add(float* addr, float a) { atomicAdd(addr, a); }
@@ -415,13 +553,16 @@ static int launch_fwd(const float* inputs, const T* emb, const int32_t* offsets,
                       uint32_t H, bool cg, T* dy_dx, uint32_t gridtype, int out_layout, cudaStream_t st) {
     const dim3 block(32, min(L, 16u));
     const dim3 grid(ceil_div(B, (uint32_t)kSamplesPerCta));
+    const bool fast = (D == 3) && !cg && g_fwd_fast;
     if (out_layout == 1) {
         const uint32_t rs = stage_row_stride(L, C, sizeof(T));
         const size_t smem = (size_t)kSamplesPerCta * rs * sizeof(T);
-        if (smem > 48 * 1024) { set_error("grid_encode_forward: L*C too large for the staging tile"); return -2; }
-        k_grid_fwd<T, D, C, true><<<grid, block, smem, st>>>(inputs, emb, offsets, outputs, B, L, S, H, cg, dy_dx, gridtype, rs);
+        if (smem > 40 * 1024) { set_error("grid_encode_forward: L*C too large for the staging tile"); return -2; }
+        if (fast) k_grid_fwd3<T, C, true><<<grid, block, smem, st>>>(inputs, emb, offsets, outputs, B, L, S, H, gridtype, rs);
+        else k_grid_fwd<T, D, C, true><<<grid, block, smem, st>>>(inputs, emb, offsets, outputs, B, L, S, H, cg, dy_dx, gridtype, rs);
     } else {
-        k_grid_fwd<T, D, C, false><<<grid, block, 0, st>>>(inputs, emb, offsets, outputs, B, L, S, H, cg, dy_dx, gridtype, 0);
+        if (fast) k_grid_fwd3<T, C, false><<<grid, block, 0, st>>>(inputs, emb, offsets, outputs, B, L, S, H, gridtype, 0);
+        else k_grid_fwd<T, D, C, false><<<grid, block, 0, st>>>(inputs, emb, offsets, outputs, B, L, S, H, cg, dy_dx, gridtype, 0);
     }
     ENERF_CHECK_LAUNCH("grid_encode_forward");
     return 0;
@@ -479,6 +620,12 @@ static int launch_bwd(const T* grad, const float* inputs, const int32_t* offsets
 using namespace enerf;
 
 extern "C" {
+
+int enerf_grid_set_forward_mode(int mode) {
+    ENERF_REQUIRE(mode == 0 || mode == 1, "grid_set_forward_mode", "mode must be 0 (generic kernel) or 1 (hoisted D=3 kernel)");
+    g_fwd_fast = mode;
+    return 0;
+}
 
 int enerf_grid_set_backward_mode(int mode) {
     ENERF_REQUIRE(mode == 0 || mode == 1, "grid_set_backward_mode", "mode must be 0 (per-corner reductions) or 1 (walking aggregation)");

@@ -85,6 +85,39 @@ def test_grid_forward_matches_reference_build(dtype):
         assert torch.equal(rdy, gdy), f"dy_dx differs from reference: max {float((rdy.float() - gdy.float()).abs().max())}"
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float16])
+def test_grid_forward_hoisted_kernel_is_bit_identical_to_generic(dtype):
+    """k_grid_fwd3 (per-level constants in smem, hoisted index/weight terms, packed fp16x2 arithmetic) vs k_grid_fwd, and both vs the
+    reference build when it is available."""
+    from enerf_b200 import _lib
+    R = ref_mod("_gridencoder")
+    rng = np.random.default_rng(12)
+    for bound, C, L, gridtype, log2T in [(3, 2, 16, 0, 19), (1, 2, 16, 0, 19), (2, 2, 16, 1, 19), (1, 4, 8, 0, 14), (2, 1, 16, 0, 12), (1, 8, 4, 1, 9)]:
+        pls = oracle.per_level_scale_for(2048 * bound, 16, L)
+        offsets = oracle.grid_offsets(3, L, pls, 16, log2T)
+        emb = rng.uniform(-1, 1, (offsets[-1], C)).astype(dtype)
+        x = np.concatenate([_marched_points(bound, 96, seed=3)[:30000], rng.random((10001, 3)).astype(np.float32),
+                            np.array([[0, 0, 0], [1, 1, 1], [1.0001, 0.5, 0.5]], np.float32)])
+        B = len(x)
+        outs = {}
+        try:
+            for mode in (1, 0):
+                _lib.call("enerf_grid_set_forward_mode", mode)
+                for layout in (0, 1):
+                    o, _ = _fwd(x, emb, offsets, pls, layout, gridtype=gridtype)
+                    outs[(mode, layout)] = o
+        finally:
+            _lib.call("enerf_grid_set_forward_mode", 1)
+        assert torch.equal(outs[(1, 0)], outs[(0, 0)]), (bound, C, L, gridtype)
+        assert torch.equal(outs[(1, 1)], outs[(0, 1)]), (bound, C, L, gridtype)
+        assert torch.equal(outs[(1, 1)].view(B, L, C).permute(1, 0, 2), outs[(1, 0)])
+        if R is not None:
+            te = t(emb)
+            rout = torch.empty(L, B, C, device=DEV, dtype=te.dtype)
+            R.grid_encode_forward(t(x), te, t(offsets), rout, B, 3, C, L, float(np.log2(pls)), 16, False, torch.empty(1, device=DEV, dtype=te.dtype), gridtype)
+            assert torch.equal(rout, outs[(1, 0)]), f"hoisted kernel differs from the reference build {(bound, C, L, gridtype)}"
+
+
 def test_grid_forward_generic_shapes():
     # D=2 (background encoder), C in {1,4,8}, L=4, tiled grid, small tables
     rng = np.random.default_rng(5)
