@@ -107,27 +107,38 @@ k_tc_fwd(const __half* __restrict__ in, const __half* __restrict__ W, __half* __
     if (warp == 0) {
         // ===================== MMA issuer (one thread) =====================
         if (lane == 0) {
-            uint32_t pa[NSLOTS];
+            // Serve whichever slot has its A operand ready (no fixed slot order: a slow epilogue must not
+            // stall the other tiles in flight).
+            uint32_t pa[NSLOTS], stage[NSLOTS], left[NSLOTS];
+            uint32_t remaining = 0;
 #pragma unroll
-            for (int s = 0; s < NSLOTS; ++s) pa[s] = 0;
+            for (int s = 0; s < NSLOTS; ++s) {
+                pa[s] = 0;
+                stage[s] = 0;
+                left[s] = (my_tiles > (uint32_t)s) ? (my_tiles - s + NSLOTS - 1) / NSLOTS : 0;   // tiles this slot will process
+                remaining += left[s] * S;
+            }
             const uint32_t idesc64 = idesc_f16(kTile, 64, false, false), idesc16 = idesc_f16(kTile, 16, false, false);
-            for (uint32_t j0 = 0; j0 < my_tiles; j0 += NSLOTS) {
-                for (int i = 0; i < S; ++i) {
+            while (remaining > 0) {
+#pragma unroll
+                for (int s = 0; s < NSLOTS; ++s) {
+                    if (left[s] == 0 || !mbar_test(&a_ready[s], pa[s])) continue;
+                    pa[s] ^= 1;
+                    tc_fence_after();
+                    const int i = (int)stage[s];
                     const int K = (i == 0) ? in_dim : kW;
                     const bool last = (i == S - 1);
                     const uint32_t lbo = last ? 16 * 16 : kW * 16;
                     const uint8_t* wb = (i == 0) ? w0s : (last ? wls : whs + (i - 1) * 8192);
                     const uint32_t wbase = smem_u32(wb);
-#pragma unroll
-                    for (int s = 0; s < NSLOTS; ++s) {
-                        if (j0 + s >= my_tiles) break;
-                        mbar_wait(&a_ready[s], pa[s]);
-                        pa[s] ^= 1;
-                        tc_fence_after();
-                        const uint32_t d_t = tmem0 + s * kSlotCols, a_t = d_t + 64;
-                        for (int k = 0; k < K / 16; ++k)
-                            mma_ts(d_t, a_t + k * 8, smem_desc(wbase + k * 2 * lbo, lbo, 128), last ? idesc16 : idesc64, k > 0);
-                        tc_commit(&d_full[s]);
+                    const uint32_t d_t = tmem0 + s * kSlotCols, a_t = d_t + 64;
+                    for (int k = 0; k < K / 16; ++k)
+                        mma_ts(d_t, a_t + k * 8, smem_desc(wbase + k * 2 * lbo, lbo, 128), last ? idesc16 : idesc64, k > 0);
+                    tc_commit(&d_full[s]);
+                    --remaining;
+                    if (++stage[s] == (uint32_t)S) {
+                        stage[s] = 0;
+                        --left[s];
                     }
                 }
             }
@@ -364,49 +375,57 @@ k_tc_bwd(const __half* __restrict__ grad, const __half* __restrict__ x, const __
 
     if (warp == 0) {
         if (lane == 0) {
-            uint32_t pa[NSLOTS];
+            uint32_t pa[NSLOTS], stage[NSLOTS], left[NSLOTS];
+            uint32_t remaining = 0, started = 0;   // bit k of `started`: stage k's wgrad accumulator has been written once
 #pragma unroll
-            for (int s = 0; s < NSLOTS; ++s) pa[s] = 0;
-            bool first = true;     // first use of the wgrad accumulators: overwrite instead of accumulate
-            for (uint32_t j0 = 0; j0 < my_tiles; j0 += NSLOTS) {
-                for (int k = 0; k < S; ++k) {
+            for (int s = 0; s < NSLOTS; ++s) {
+                pa[s] = 0;
+                stage[s] = 0;
+                left[s] = (my_tiles > (uint32_t)s) ? (my_tiles - s + NSLOTS - 1) / NSLOTS : 0;
+                remaining += left[s] * S;
+            }
+            while (remaining > 0) {
 #pragma unroll
-                    for (int s = 0; s < NSLOTS; ++s) {
-                        if (j0 + s >= my_tiles) break;
-                        mbar_wait(&a_ready[s], pa[s]);
-                        pa[s] ^= 1;
-                        tc_fence_after();
-                        const uint32_t d_t = tmem0 + s * kSlotCols, a_t = d_t + 64;
-                        const uint32_t g_s = smem_u32(tiles + (size_t)s * 2 * kGBytes), h_s = g_s + kGBytes;
-                        const bool acc = !(first && s == 0);
-                        if (k == 0) {
-                            // dgrad through the output layer: D[128x64] = dy[128x16] . W_last[16x64]
-                            mma_ts(d_t, a_t, smem_desc(smem_u32(wls), 128, 16 * 16), idesc_f16(kTile, 64, false, true), false);
-                            // dW_last^T[64x16] += h_n^T[64x128] . dy[128x16]   (A = H tile, B = dy tile in the G buffer)
-                            for (int ks = 0; ks < 8; ++ks)
-                                mma_ss(acc_last, smem_desc(h_s + ks * 256, 128, 2048), smem_desc(g_s + ks * 256, 128, 2048),
-                                       idesc_f16(64, 16, true, true), acc || ks > 0);
-                        } else if (k <= n_hidden_mm) {
-                            const int j = n_hidden_mm - k;      // hidden matmul index
-                            const uint32_t wj = smem_u32(whs + j * 8192);
+                for (int s = 0; s < NSLOTS; ++s) {
+                    if (left[s] == 0 || !mbar_test(&a_ready[s], pa[s])) continue;
+                    pa[s] ^= 1;
+                    tc_fence_after();
+                    const int k = (int)stage[s];
+                    const uint32_t d_t = tmem0 + s * kSlotCols, a_t = d_t + 64;
+                    const uint32_t g_s = smem_u32(tiles + (size_t)s * 2 * kGBytes), h_s = g_s + kGBytes;
+                    const bool acc = (started >> k) & 1u;
+                    started |= 1u << k;
+                    if (k == 0) {
+                        // dgrad through the output layer: D[128x64] = dy[128x16] . W_last[16x64]
+                        mma_ts(d_t, a_t, smem_desc(smem_u32(wls), 128, 16 * 16), idesc_f16(kTile, 64, false, true), false);
+                        // dW_last^T[64x16] += h_n^T[64x128] . dy[128x16]   (A = H tile, B = dy tile in the G buffer)
+                        for (int ks = 0; ks < 8; ++ks)
+                            mma_ss(acc_last, smem_desc(h_s + ks * 256, 128, 2048), smem_desc(g_s + ks * 256, 128, 2048),
+                                   idesc_f16(64, 16, true, true), acc || ks > 0);
+                    } else if (k <= n_hidden_mm) {
+                        const int jm = n_hidden_mm - k;      // hidden matmul index
+                        const uint32_t wj = smem_u32(whs + jm * 8192);
+                        for (int ks = 0; ks < 4; ++ks)
+                            mma_ts(d_t, a_t + ks * 8, smem_desc(wj + ks * 256, 128, 64 * 16), idesc_f16(kTile, 64, false, true), ks > 0);
+                        for (int ks = 0; ks < 8; ++ks)
+                            mma_ss(acc_hid + jm * 64, smem_desc(g_s + ks * 256, 128, 2048), smem_desc(h_s + ks * 256, 128, 2048),
+                                   idesc_f16(64, 64, true, true), acc || ks > 0);
+                    } else {
+                        if (grad_inputs)
                             for (int ks = 0; ks < 4; ++ks)
-                                mma_ts(d_t, a_t + ks * 8, smem_desc(wj + ks * 256, 128, 64 * 16), idesc_f16(kTile, 64, false, true), ks > 0);
-                            for (int ks = 0; ks < 8; ++ks)
-                                mma_ss(acc_hid + j * 64, smem_desc(g_s + ks * 256, 128, 2048), smem_desc(h_s + ks * 256, 128, 2048),
-                                       idesc_f16(64, 64, true, true), acc || ks > 0);
-                        } else {
-                            if (grad_inputs)
-                                for (int ks = 0; ks < 4; ++ks)
-                                    mma_ts(d_t, a_t + ks * 8, smem_desc(smem_u32(w0s) + ks * 256, 128, 64 * 16),
-                                           idesc_f16(kTile, (uint32_t)in_dim, false, true), ks > 0);
-                            for (int ks = 0; ks < 8; ++ks)
-                                mma_ss(acc_0, smem_desc(g_s + ks * 256, 128, 2048), smem_desc(h_s + ks * 256, 128, 2048),
-                                       idesc_f16(64, (uint32_t)in_dim, true, true), acc || ks > 0);
-                        }
-                        tc_commit(&d_full[s]);
+                                mma_ts(d_t, a_t + ks * 8, smem_desc(smem_u32(w0s) + ks * 256, 128, 64 * 16),
+                                       idesc_f16(kTile, (uint32_t)in_dim, false, true), ks > 0);
+                        for (int ks = 0; ks < 8; ++ks)
+                            mma_ss(acc_0, smem_desc(g_s + ks * 256, 128, 2048), smem_desc(h_s + ks * 256, 128, 2048),
+                                   idesc_f16(64, (uint32_t)in_dim, true, true), acc || ks > 0);
+                    }
+                    tc_commit(&d_full[s]);
+                    --remaining;
+                    if (++stage[s] == (uint32_t)S) {
+                        stage[s] = 0;
+                        --left[s];
                     }
                 }
-                first = false;
             }
             tc_commit(flush_bar);
         }
