@@ -190,8 +190,10 @@ def our_arm(args):
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    h0 = time.perf_counter()
     for _ in range(K):
         loss = step(rays_o, rays_d, target)
+    host_enqueue_ms = (time.perf_counter() - h0) * 1e3 / K      # CPU time to enqueue one step (no sync inside)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -282,7 +284,7 @@ def our_arm(args):
             "config": workload_config(n_rays, {"samples_per_step_per_gpu": S, "parallelism": f"dp{world} (ray-sharded, NCCL grad allreduce)",
                                                "l2": "per-step working set (samples x ~1.7 KB of activations + 52 MB grad table) is >> 126 MB L2; no explicit flush"}),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "kernels": kernels,
-            "cpu_baseline": cpu_baseline, "final_loss": float(loss_host)}
+            "cpu_baseline": cpu_baseline, "final_loss": float(loss_host), "host_enqueue_ms_per_step": host_enqueue_ms}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

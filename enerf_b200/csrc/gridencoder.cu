@@ -449,8 +449,22 @@ k_grid_bwd_walk(const T* __restrict__ grad, const float* __restrict__ inputs, co
     if (b0 >= B) return;
     const uint32_t b1 = (uint32_t)min((uint64_t)B, b0 + SEG);
 
+    // per-level constants (one level per thread): index = (x*1 (+|^) y*m[1] (+|^) z*m[2]) mod table size
     const LevelGeom g = level_geom(offsets, level, S, H, gridtype, D);
     G* __restrict__ tab = grad_grid + (size_t)g.offset * C;
+    uint32_t mult[D];
+    {
+        constexpr uint32_t primes[7] = {1u, 2654435761u, 805459861u, 3674653429u, 2097192037u, 1434869437u, 2165219737u};
+        uint32_t stride = 1;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            if (g.use_hash) mult[d] = primes[d];
+            else {                                          // the stride loop of gridencoder.cu:58-62
+                mult[d] = (stride <= g.hashmap_size) ? stride : 0u;
+                if (stride <= g.hashmap_size) stride *= (g.resolution + 1);
+            }
+        }
+    }
 
     uint32_t cell[D];
 #pragma unroll
@@ -459,12 +473,19 @@ k_grid_bwd_walk(const T* __restrict__ grad, const float* __restrict__ inputs, co
     float acc[1 << D][C];
 
     auto flush = [&]() {
+        uint32_t term[D][2];
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            term[d][0] = cell[d] * mult[d];
+            term[d][1] = (cell[d] + 1) * mult[d];
+        }
 #pragma unroll
         for (int idx = 0; idx < (1 << D); ++idx) {
-            uint32_t pl[D];
+            uint32_t i = 0;
 #pragma unroll
-            for (int d = 0; d < D; ++d) pl[d] = cell[d] + ((idx >> d) & 1);
-            const uint32_t e = grid_index<D>(g, pl) * C;
+            for (int d = 0; d < D; ++d) i = g.use_hash ? (i ^ term[d][(idx >> d) & 1]) : (i + term[d][(idx >> d) & 1]);
+            i = g.pow2 ? (i & (g.hashmap_size - 1)) : (i < g.hashmap_size ? i : i % g.hashmap_size);
+            const uint32_t e = i * C;
             if (C == 1) {
                 red_add(tab + e, acc[idx][0]);
             } else {
@@ -477,15 +498,15 @@ k_grid_bwd_walk(const T* __restrict__ grad, const float* __restrict__ inputs, co
     for (uint32_t b = (uint32_t)b0; b < b1; ++b) {
         float x[D];
         if (load_pos<D>(inputs, b, x)) continue;         // out-of-range samples contribute nothing
-        float pos[D];
+        float fr[D];
         uint32_t pg[D];
         bool same = have;
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-            pos[d] = __fmaf_rn(x[d], g.scale, 0.5f);
-            const float fl = floorf(pos[d]);
+            const float p = __fmaf_rn(x[d], g.scale, 0.5f);
+            const float fl = floorf(p);
             pg[d] = (uint32_t)fl;
-            pos[d] -= fl;
+            fr[d] = p - fl;
             same = same && (pg[d] == cell[d]);
         }
         if (!same) {
@@ -502,11 +523,18 @@ k_grid_bwd_walk(const T* __restrict__ grad, const float* __restrict__ inputs, co
         const T* __restrict__ gp = BLC ? grad + ((size_t)b * L + level) * C : grad + ((size_t)level * B + b) * C;
 #pragma unroll
         for (int ch = 0; ch < C; ++ch) gr[ch] = Elem<T>::to_f(gp[ch]);
+        // corner weights in the reference's multiplication order: ((w0 * w1) * w2), partial products shared
+        float wpart[1 << (D - 1)];
 #pragma unroll
-        for (int idx = 0; idx < (1 << D); ++idx) {
+        for (int q = 0; q < (1 << (D - 1)); ++q) {
             float w = 1.0f;
 #pragma unroll
-            for (int d = 0; d < D; ++d) w *= ((idx >> d) & 1) ? pos[d] : 1.0f - pos[d];
+            for (int d = 0; d < D - 1; ++d) w *= ((q >> d) & 1) ? fr[d] : 1.0f - fr[d];
+            wpart[q] = w;
+        }
+#pragma unroll
+        for (int idx = 0; idx < (1 << D); ++idx) {
+            const float w = wpart[idx & ((1 << (D - 1)) - 1)] * ((idx >> (D - 1)) ? fr[D - 1] : 1.0f - fr[D - 1]);
 #pragma unroll
             for (int ch = 0; ch < C; ++ch) acc[idx][ch] = __fmaf_rn(w, gr[ch], acc[idx][ch]);
         }
