@@ -76,7 +76,8 @@ k_tc_fwd(const __half* __restrict__ in, const __half* __restrict__ W, __half* __
     uint8_t* w0s = smem;                                  // [in_dim/8][64][16 B]
     uint8_t* whs = w0s + in_dim * 128;                    // n_hidden_mm x [8][64][16 B]
     uint8_t* wls = whs + n_hidden_mm * 8192;              // [8][16][16 B]
-    uint64_t* a_ready = reinterpret_cast<uint64_t*>(wls + 2048);
+    uint8_t* stage_base = wls + 2048;                     // 4 KB per epilogue warp (row <-> coalesced transposition)
+    uint64_t* a_ready = reinterpret_cast<uint64_t*>(stage_base + (size_t)NSLOTS * 4 * 4096);
     uint64_t* d_full = a_ready + NSLOTS;
     uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(d_full + NSLOTS);
 
@@ -145,23 +146,44 @@ k_tc_fwd(const __half* __restrict__ in, const __half* __restrict__ W, __half* __
         }
     } else {
         // ===================== epilogue warps =====================
+        // Every global access of a warp is a fully coalesced 512-byte request: the warp's 32 rows are
+        // moved between "coalesced" and "row per lane" form through a swizzled, warp-private staging tile.
         const int s = (warp - 1) >> 2;                 // slot
         const int q = warp & 3;                        // TMEM quarter this warp may access
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
         const uint32_t d_t = tmem0 + lane_sel + s * kSlotCols, a_t = d_t + 64;
+        uint8_t* stg = stage_base + (size_t)(warp - 1) * 4096;
+        constexpr int NVI = IN_DIM / 8;                // 16-byte chunks per input row
+        constexpr bool kCoalIn = (NVI == 2 || NVI == 4 || NVI == 8);
         uint32_t pd = 0;
-        // the input row of the NEXT tile is fetched while the current tile's layers run
-        int4 xin[IN_DIM / 8];
-        if ((uint32_t)s < my_tiles) {
-            const size_t row0 = ((size_t)blockIdx.x + (size_t)s * gridDim.x) * kTile + q * 32 + lane;
+        // the input rows of the NEXT tile are fetched while the current tile's layers run
+        int4 xco[NVI];
+        auto fetch_input = [&](uint32_t jj) {
+            const size_t wrow0 = ((size_t)blockIdx.x + (size_t)jj * gridDim.x) * kTile + q * 32;     // first row of this warp
+            if (kCoalIn) {
+                const int4* g = reinterpret_cast<const int4*>(in + wrow0 * in_dim);
 #pragma unroll
-            for (int c = 0; c < IN_DIM / 8; ++c) xin[c] = __ldg(reinterpret_cast<const int4*>(in + row0 * in_dim) + c);
-        }
+                for (int i = 0; i < NVI; ++i) xco[i] = __ldg(g + i * 32 + lane);
+            } else {
+                const int4* g = reinterpret_cast<const int4*>(in + (wrow0 + lane) * in_dim);
+#pragma unroll
+                for (int c = 0; c < NVI; ++c) xco[c] = __ldg(g + c);
+            }
+        };
+        if ((uint32_t)s < my_tiles) fetch_input(s);
         for (uint32_t j = s; j < my_tiles; j += NSLOTS) {
             const size_t tile = (size_t)blockIdx.x + (size_t)j * gridDim.x;
-            const size_t row = tile * kTile + q * 32 + lane;
+            const size_t wrow0 = tile * kTile + q * 32;
+            const size_t row = wrow0 + lane;
             // ---- input row -> TMEM A
             {
+                int4 xin[NVI];
+                if (kCoalIn) {
+                    if constexpr (kCoalIn) coalesced_to_rows<NVI>(xco, xin, stg, lane);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < NVI; ++c) xin[c] = xco[c];
+                }
 #pragma unroll
                 for (int c = 0; c < IN_DIM / 16; ++c) {            // 16 halves = 8 TMEM columns per step
                     const int4 v0 = xin[2 * c], v1 = xin[2 * c + 1];
@@ -172,18 +194,14 @@ k_tc_fwd(const __half* __restrict__ in, const __half* __restrict__ W, __half* __
                 tc_wait_st();
                 tc_fence_before();
                 mbar_arrive(&a_ready[s]);
-                if (j + NSLOTS < my_tiles) {
-                    const size_t nrow = ((size_t)blockIdx.x + (size_t)(j + NSLOTS) * gridDim.x) * kTile + q * 32 + lane;
-#pragma unroll
-                    for (int c = 0; c < IN_DIM / 8; ++c) xin[c] = __ldg(reinterpret_cast<const int4*>(in + nrow * in_dim) + c);
-                }
+                if (j + NSLOTS < my_tiles) fetch_input(j + NSLOTS);
             }
             for (int i = 0; i < S; ++i) {
                 mbar_wait(&d_full[s], pd);
                 pd ^= 1;
                 tc_fence_after();
                 if (i < S - 1) {
-                    __half* fb = fwd_buf ? fwd_buf + ((size_t)i * B + row) * kW : nullptr;
+                    int4 hrow[8];                                  // this lane's 64 fp16 activations
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         uint32_t acc[32];
@@ -193,26 +211,25 @@ k_tc_fwd(const __half* __restrict__ in, const __half* __restrict__ W, __half* __
 #pragma unroll
                         for (int e = 0; e < 16; ++e) p[e] = pack2(relu(__uint_as_float(acc[2 * e])), relu(__uint_as_float(acc[2 * e + 1])));
                         tmem_st16(a_t + h * 16, p);
-                        if (fb) {
-                            int4* dst = reinterpret_cast<int4*>(fb + h * 32);
 #pragma unroll
-                            for (int v = 0; v < 4; ++v) dst[v] = make_int4((int)p[4 * v], (int)p[4 * v + 1], (int)p[4 * v + 2], (int)p[4 * v + 3]);
-                        }
+                        for (int v = 0; v < 4; ++v) hrow[h * 4 + v] = make_int4((int)p[4 * v], (int)p[4 * v + 1], (int)p[4 * v + 2], (int)p[4 * v + 3]);
                     }
                     tc_wait_st();
                     tc_fence_before();
                     mbar_arrive(&a_ready[s]);
+                    // the forward_buffer rows leave after the hand-off, off the critical path of the next MMA
+                    if (fwd_buf) store_rows<8>(reinterpret_cast<int4*>(fwd_buf + ((size_t)i * B + wrow0) * kW), hrow, stg, lane);
                 } else {
                     uint32_t acc[16];
                     tmem_ld16(d_t, acc);
                     tc_wait_ld();
                     if (HEAD == 0) {
-                        uint32_t p[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) p[e] = pack2(__uint_as_float(acc[2 * e]), __uint_as_float(acc[2 * e + 1]));
-                        int4* dst = reinterpret_cast<int4*>(out + row * 16);
-                        dst[0] = make_int4((int)p[0], (int)p[1], (int)p[2], (int)p[3]);
-                        dst[1] = make_int4((int)p[4], (int)p[5], (int)p[6], (int)p[7]);
+                        int4 orow[2];
+                        orow[0] = make_int4((int)pack2(__uint_as_float(acc[0]), __uint_as_float(acc[1])), (int)pack2(__uint_as_float(acc[2]), __uint_as_float(acc[3])),
+                                            (int)pack2(__uint_as_float(acc[4]), __uint_as_float(acc[5])), (int)pack2(__uint_as_float(acc[6]), __uint_as_float(acc[7])));
+                        orow[1] = make_int4((int)pack2(__uint_as_float(acc[8]), __uint_as_float(acc[9])), (int)pack2(__uint_as_float(acc[10]), __uint_as_float(acc[11])),
+                                            (int)pack2(__uint_as_float(acc[12]), __uint_as_float(acc[13])), (int)pack2(__uint_as_float(acc[14]), __uint_as_float(acc[15])));
+                        store_rows<2>(reinterpret_cast<int4*>(out + wrow0 * 16), orow, stg, lane);
                     } else if (HEAD == 1) {
                         head.sigma[row] = expf(f16_round(__uint_as_float(acc[0])));
                         // directions reach the SH encoder as fp16 under autocast (sphere_harmonics.py:16)
@@ -225,9 +242,10 @@ k_tc_fwd(const __half* __restrict__ in, const __half* __restrict__ W, __half* __
 #pragma unroll
                         for (int e = 0; e < 7; ++e) p[8 + e] = pack2(__uint_as_float(acc[1 + 2 * e]), __uint_as_float(acc[2 + 2 * e]));
                         p[15] = pack2(__uint_as_float(acc[15]), 0.0f);
-                        int4* dst = reinterpret_cast<int4*>(head.cin + row * 32);
+                        int4 crow[4];
 #pragma unroll
-                        for (int v = 0; v < 4; ++v) dst[v] = make_int4((int)p[4 * v], (int)p[4 * v + 1], (int)p[4 * v + 2], (int)p[4 * v + 3]);
+                        for (int v = 0; v < 4; ++v) crow[v] = make_int4((int)p[4 * v], (int)p[4 * v + 1], (int)p[4 * v + 2], (int)p[4 * v + 3]);
+                        store_rows<4>(reinterpret_cast<int4*>(head.cin + wrow0 * 32), crow, stg, lane);
                     } else {
                         for (int c = 0; c < head.n_ch; ++c) {
                             const float y = f16_round(__uint_as_float(acc[c]));
@@ -245,7 +263,7 @@ k_tc_fwd(const __half* __restrict__ in, const __half* __restrict__ W, __half* __
 }
 
 static size_t fwd_smem_bytes(int in_dim, int n_hidden_mm, int nslots) {
-    return (size_t)in_dim * 128 + (size_t)n_hidden_mm * 8192 + 2048 + (size_t)nslots * 16 + 16;
+    return (size_t)in_dim * 128 + (size_t)n_hidden_mm * 8192 + 2048 + (size_t)nslots * 4 * 4096 + (size_t)nslots * 16 + 16;
 }
 
 template <int IN_DIM, int HEAD>
@@ -339,7 +357,8 @@ k_tc_bwd(const __half* __restrict__ grad, const __half* __restrict__ x, const __
     uint8_t* whs = w0s + in_dim * 128;                    // n_hidden_mm x [8][64][16 B]
     uint8_t* wls = whs + n_hidden_mm * 8192;              // [8][16][16 B]
     uint8_t* tiles = wls + 2048;                          // per slot: G tile, H tile
-    uint64_t* a_ready = reinterpret_cast<uint64_t*>(tiles + (size_t)NSLOTS * 2 * kGBytes);
+    uint8_t* stage_base = tiles + (size_t)NSLOTS * 2 * kGBytes;   // 4 KB per epilogue warp (row <-> coalesced transposition)
+    uint64_t* a_ready = reinterpret_cast<uint64_t*>(stage_base + (size_t)NSLOTS * 4 * 4096);
     uint64_t* d_full = a_ready + NSLOTS;
     uint64_t* flush_bar = d_full + NSLOTS;
     uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(flush_bar + 1);
@@ -441,17 +460,19 @@ k_tc_bwd(const __half* __restrict__ grad, const __half* __restrict__ x, const __
         uint32_t hreg[32];       // this row's forward activation (64 fp16) used as ReLU mask by the next epilogue
         // Global rows needed by the NEXT epilogue stage are requested before waiting for the tensor core, so
         // their HBM latency overlaps the MMAs: `pre` = h_n row of the tile about to start, `nxt` = next stage's row.
+        // All of these loads are fully coalesced (512 B per warp instruction); the rows are brought into
+        // "row per lane" form through the warp's swizzled staging tile when they are consumed.
+        uint8_t* stg = stage_base + (size_t)(warp - 1) * 4096;
         int4 pre[8];
         if ((uint32_t)s < my_tiles) {
-            const size_t row0 = ((size_t)blockIdx.x + (size_t)s * gridDim.x) * kTile + r_in_tile;
-            const int4* hs0 = reinterpret_cast<const int4*>(fwd_buf + ((size_t)n_hidden_mm * B + row0) * kW);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) pre[c] = __ldg(hs0 + c);
+            const size_t wrow0 = ((size_t)blockIdx.x + (size_t)s * gridDim.x) * kTile + q * 32;
+            ld_coalesced<8>(pre, reinterpret_cast<const int4*>(fwd_buf + ((size_t)n_hidden_mm * B + wrow0) * kW), lane);
         }
 
         for (uint32_t j = s; j < my_tiles; j += NSLOTS) {
             const size_t tile = (size_t)blockIdx.x + (size_t)j * gridDim.x;
             const size_t row = tile * kTile + r_in_tile;
+            const size_t wrow0 = tile * kTile + q * 32;
             // ---- E_0: dy -> TMEM A + dy tile (G buffer); h_n -> registers + H tile
             {
                 int4 v0, v1;
@@ -486,9 +507,11 @@ k_tc_bwd(const __half* __restrict__ grad, const __half* __restrict__ x, const __
                 tmem_st8(a_t, r8);
                 *reinterpret_cast<int4*>(g_tile + 0 * 2048 + r_in_tile * 16) = v0;
                 *reinterpret_cast<int4*>(g_tile + 1 * 2048 + r_in_tile * 16) = v1;
+                int4 hrow[8];
+                coalesced_to_rows<8>(pre, hrow, stg, lane);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    const int4 v = pre[c];
+                    const int4 v = hrow[c];
                     hreg[4 * c] = (uint32_t)v.x; hreg[4 * c + 1] = (uint32_t)v.y; hreg[4 * c + 2] = (uint32_t)v.z; hreg[4 * c + 3] = (uint32_t)v.w;
                     *reinterpret_cast<int4*>(h_tile + c * 2048 + r_in_tile * 16) = v;
                 }
@@ -500,14 +523,18 @@ k_tc_bwd(const __half* __restrict__ grad, const __half* __restrict__ x, const __
             // ---- E_k, k = 1 .. S-1: g = D * relu'(h) -> TMEM A + G tile; next activation (or x) -> H tile
             for (int k = 1; k < S; ++k) {
                 int4 nxt[8];
+                const int nv_x = in_dim / 8;                      // chunks per input row (last stage)
+                const bool coal_x = (nv_x == 4 || nv_x == 8);
                 if (k < S - 1) {
-                    const int4* hs = reinterpret_cast<const int4*>(fwd_buf + ((size_t)(n_hidden_mm - k) * B + row) * kW);
+                    ld_coalesced<8>(nxt, reinterpret_cast<const int4*>(fwd_buf + ((size_t)(n_hidden_mm - k) * B + wrow0) * kW), lane);
+                } else if (coal_x) {
+                    const int4* xg = reinterpret_cast<const int4*>(x + wrow0 * in_dim);
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) nxt[c] = __ldg(hs + c);
+                    for (int i = 0; i < 8; ++i) nxt[i] = (i < nv_x) ? __ldg(xg + i * 32 + lane) : make_int4(0, 0, 0, 0);
                 } else {
                     const int4* xs = reinterpret_cast<const int4*>(x + row * in_dim);
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) nxt[c] = (c < in_dim / 8) ? __ldg(xs + c) : make_int4(0, 0, 0, 0);
+                    for (int c = 0; c < 8; ++c) nxt[c] = (c < nv_x) ? __ldg(xs + c) : make_int4(0, 0, 0, 0);
                 }
                 mbar_wait(&d_full[s], pd);
                 pd ^= 1;
@@ -534,11 +561,25 @@ k_tc_bwd(const __half* __restrict__ grad, const __half* __restrict__ x, const __
                         if (bb) reinterpret_cast<int4*>(bb)[h * 4 + v] = val;
                     }
                 }
+                {
+                    int4 nrow[8];
+                    if (k < S - 1 || nv_x == 8) {
+                        coalesced_to_rows<8>(nxt, nrow, stg, lane);
+                    } else if (nv_x == 4) {
+                        int4 c4[4] = {nxt[0], nxt[1], nxt[2], nxt[3]}, r4[4];
+                        coalesced_to_rows<4>(c4, r4, stg, lane);
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const int4 v = nxt[c];
-                    hreg[4 * c] = (uint32_t)v.x; hreg[4 * c + 1] = (uint32_t)v.y; hreg[4 * c + 2] = (uint32_t)v.z; hreg[4 * c + 3] = (uint32_t)v.w;
-                    if (k < S - 1 || c < in_dim / 8) *reinterpret_cast<int4*>(h_tile + c * 2048 + r_in_tile * 16) = v;
+                        for (int c = 0; c < 8; ++c) nrow[c] = (c < 4) ? r4[c & 3] : make_int4(0, 0, 0, 0);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) nrow[c] = nxt[c];
+                    }
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const int4 v = nrow[c];
+                        hreg[4 * c] = (uint32_t)v.x; hreg[4 * c + 1] = (uint32_t)v.y; hreg[4 * c + 2] = (uint32_t)v.z; hreg[4 * c + 3] = (uint32_t)v.w;
+                        if (k < S - 1 || c < nv_x) *reinterpret_cast<int4*>(h_tile + c * 2048 + r_in_tile * 16) = v;
+                    }
                 }
                 tc_wait_st();
                 fence_proxy_async_smem();
@@ -547,25 +588,37 @@ k_tc_bwd(const __half* __restrict__ grad, const __half* __restrict__ x, const __
             }
             // ---- E_S: dx
             if (j + NSLOTS < my_tiles) {
-                const size_t nrow = ((size_t)blockIdx.x + (size_t)(j + NSLOTS) * gridDim.x) * kTile + r_in_tile;
-                const int4* hs0 = reinterpret_cast<const int4*>(fwd_buf + ((size_t)n_hidden_mm * B + nrow) * kW);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) pre[c] = __ldg(hs0 + c);
+                const size_t nwrow0 = ((size_t)blockIdx.x + (size_t)(j + NSLOTS) * gridDim.x) * kTile + q * 32;
+                ld_coalesced<8>(pre, reinterpret_cast<const int4*>(fwd_buf + ((size_t)n_hidden_mm * B + nwrow0) * kW), lane);
             }
             mbar_wait(&d_full[s], pd);
             pd ^= 1;
             tc_fence_after();
             if (grad_inputs) {
-                for (int c = 0; c < in_dim / 16; ++c) {
-                    uint32_t acc[16];
-                    tmem_ld16(d_t + c * 16, acc);
-                    tc_wait_ld();
-                    uint32_t p[8];
+                int4 xrow[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) p[e] = pack2(__uint_as_float(acc[2 * e]), __uint_as_float(acc[2 * e + 1]));
-                    int4* dst = reinterpret_cast<int4*>(grad_inputs + row * in_dim + c * 16);
-                    dst[0] = make_int4((int)p[0], (int)p[1], (int)p[2], (int)p[3]);
-                    dst[1] = make_int4((int)p[4], (int)p[5], (int)p[6], (int)p[7]);
+                for (int c = 0; c < 4; ++c) {
+                    if (c < in_dim / 16) {
+                        uint32_t acc[16];
+                        tmem_ld16(d_t + c * 16, acc);
+                        tc_wait_ld();
+                        uint32_t p[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) p[e] = pack2(__uint_as_float(acc[2 * e]), __uint_as_float(acc[2 * e + 1]));
+                        xrow[2 * c] = make_int4((int)p[0], (int)p[1], (int)p[2], (int)p[3]);
+                        xrow[2 * c + 1] = make_int4((int)p[4], (int)p[5], (int)p[6], (int)p[7]);
+                    }
+                }
+                if (in_dim == 32) {
+                    int4 r4[4] = {xrow[0], xrow[1], xrow[2], xrow[3]};
+                    store_rows<4>(reinterpret_cast<int4*>(grad_inputs + wrow0 * 32), r4, stg, lane);
+                } else if (in_dim == 64) {
+                    store_rows<8>(reinterpret_cast<int4*>(grad_inputs + wrow0 * 64), xrow, stg, lane);
+                } else {
+                    int4* dst = reinterpret_cast<int4*>(grad_inputs + row * in_dim);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        if (c < in_dim / 8) dst[c] = xrow[c];
                 }
             }
             tc_fence_before();
@@ -627,7 +680,8 @@ static int launch_bwd(const __half* grad, const __half* x, const __half* W, cons
     constexpr int NSLOTS = 2;
     // TMEM: NSLOTS*96 + 16 + 64*n_hidden_mm + in_dim columns
     if (NSLOTS * kSlotCols + 16 + 64 * n_hidden_mm + in_dim > 512) { set_error("%s: network too deep for the tcgen05 path", name); return -2; }
-    size_t smem = (size_t)in_dim * 128 + (size_t)n_hidden_mm * 8192 + 2048 + (size_t)NSLOTS * 2 * kGBytes + (2 * NSLOTS + 1) * 8 + 16;
+    size_t smem = (size_t)in_dim * 128 + (size_t)n_hidden_mm * 8192 + 2048 + (size_t)NSLOTS * 2 * kGBytes + (size_t)NSLOTS * 4 * 4096 +
+                  (2 * NSLOTS + 1) * 8 + 16;
     if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: it allocates all 512 TMEM columns
     if (smem > 220 * 1024) { set_error("%s: network too deep for the tcgen05 path", name); return -2; }
     static size_t configured = 0;

@@ -137,6 +137,60 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
                  ::"r"(taddr), ENERF_W8(r, 0), ENERF_W8(r, 8) : "memory");
 }
 
+// ---- warp-cooperative row <-> coalesced transposition through swizzled shared memory ---------------
+// A warp owns 32 consecutive rows of NV 16-byte chunks (row-major, contiguous in global memory).
+//   coalesced form: piece i of lane l is chunk (i*32 + l) of the 32*NV-chunk block  -> every global
+//                   access of the warp covers 512 contiguous bytes (4 L1 wavefronts instead of 32)
+//   row form      : lane l holds the NV chunks of row l (what the TMEM epilogue works on)
+// `stage` is a warp-private 32*NV*16-byte region; the XOR swizzle makes both access patterns
+// bank-conflict free.
+template <int NV>
+__device__ __forceinline__ uint32_t swz(int row, int c) {
+    constexpr int SH = (NV == 8) ? 0 : (NV == 4) ? 1 : 2;
+    return (uint32_t)(row * NV + (c ^ ((row >> SH) & (NV - 1)))) * 16u;
+}
+template <int NV>
+__device__ __forceinline__ void ld_coalesced(int4 (&co)[NV], const int4* __restrict__ g, int lane) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) co[i] = __ldg(g + i * 32 + lane);
+}
+template <int NV>
+__device__ __forceinline__ void st_coalesced(int4* __restrict__ g, const int4 (&co)[NV], int lane) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) g[i * 32 + lane] = co[i];
+}
+template <int NV>
+__device__ __forceinline__ void coalesced_to_rows(const int4 (&co)[NV], int4 (&rows)[NV], uint8_t* stage, int lane) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int idx = i * 32 + lane;
+        *reinterpret_cast<int4*>(stage + swz<NV>(idx / NV, idx % NV)) = co[i];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < NV; ++c) rows[c] = *reinterpret_cast<const int4*>(stage + swz<NV>(lane, c));
+    __syncwarp();
+}
+template <int NV>
+__device__ __forceinline__ void rows_to_coalesced(const int4 (&rows)[NV], int4 (&co)[NV], uint8_t* stage, int lane) {
+#pragma unroll
+    for (int c = 0; c < NV; ++c) *reinterpret_cast<int4*>(stage + swz<NV>(lane, c)) = rows[c];
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int idx = i * 32 + lane;
+        co[i] = *reinterpret_cast<const int4*>(stage + swz<NV>(idx / NV, idx % NV));
+    }
+    __syncwarp();
+}
+// rows (this lane's row) -> global, coalesced
+template <int NV>
+__device__ __forceinline__ void store_rows(int4* __restrict__ g_warp, const int4 (&rows)[NV], uint8_t* stage, int lane) {
+    int4 co[NV];
+    rows_to_coalesced<NV>(rows, co, stage, lane);
+    st_coalesced<NV>(g_warp, co, lane);
+}
+
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
     const __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<const uint32_t*>(&h);
