@@ -14,6 +14,7 @@
 //   Weights are staged once per CTA in shared memory in the no-swizzle canonical layout
 //   (tc_common.cuh); hand-offs use mbarriers (128 arrivals: "A ready"; tcgen05.commit: "D full").
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace enerf {
 namespace tcm {
@@ -473,6 +474,24 @@ k_tc_bwd(const __half* __restrict__ grad, const __half* __restrict__ x, const __
             const size_t tile = (size_t)blockIdx.x + (size_t)j * gridDim.x;
             const size_t row = tile * kTile + r_in_tile;
             const size_t wrow0 = tile * kTile + q * 32;
+            // `nxt`: coalesced pieces of the rows the NEXT epilogue stage needs (h_{n-k} for k < S-1, the network input for k = S-1),
+            // requested one stage ahead so that HBM latency and the transposition overlap the tensor-core work
+            int4 nxt[8];
+            const int nv_x = in_dim / 8;
+            const bool coal_x = (nv_x == 4 || nv_x == 8);
+            auto issue_next = [&](int k) {
+                if (k < S - 1) {
+                    ld_coalesced<8>(nxt, reinterpret_cast<const int4*>(fwd_buf + ((size_t)(n_hidden_mm - k) * B + wrow0) * kW), lane);
+                } else if (coal_x) {
+                    const int4* xg = reinterpret_cast<const int4*>(x + wrow0 * in_dim);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) nxt[i] = (i < nv_x) ? __ldg(xg + i * 32 + lane) : make_int4(0, 0, 0, 0);
+                } else {
+                    const int4* xs = reinterpret_cast<const int4*>(x + row * in_dim);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) nxt[c] = (c < nv_x) ? __ldg(xs + c) : make_int4(0, 0, 0, 0);
+                }
+            };
             // ---- E_0: dy -> TMEM A + dy tile (G buffer); h_n -> registers + H tile
             {
                 int4 v0, v1;
@@ -519,22 +538,22 @@ k_tc_bwd(const __half* __restrict__ grad, const __half* __restrict__ x, const __
                 fence_proxy_async_smem();
                 tc_fence_before();
                 mbar_arrive(&a_ready[s]);
+                issue_next(1);
             }
             // ---- E_k, k = 1 .. S-1: g = D * relu'(h) -> TMEM A + G tile; next activation (or x) -> H tile
             for (int k = 1; k < S; ++k) {
-                int4 nxt[8];
-                const int nv_x = in_dim / 8;                      // chunks per input row (last stage)
-                const bool coal_x = (nv_x == 4 || nv_x == 8);
-                if (k < S - 1) {
-                    ld_coalesced<8>(nxt, reinterpret_cast<const int4*>(fwd_buf + ((size_t)(n_hidden_mm - k) * B + wrow0) * kW), lane);
-                } else if (coal_x) {
-                    const int4* xg = reinterpret_cast<const int4*>(x + wrow0 * in_dim);
+                // rows requested during the previous stage -> "row per lane" registers, while the MMAs of stage k-1 run
+                int4 nrow[8];
+                if (k < S - 1 || nv_x == 8) {
+                    coalesced_to_rows<8>(nxt, nrow, stg, lane);
+                } else if (nv_x == 4) {
+                    int4 c4[4] = {nxt[0], nxt[1], nxt[2], nxt[3]}, r4[4];
+                    coalesced_to_rows<4>(c4, r4, stg, lane);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) nxt[i] = (i < nv_x) ? __ldg(xg + i * 32 + lane) : make_int4(0, 0, 0, 0);
+                    for (int c = 0; c < 8; ++c) nrow[c] = (c < 4) ? r4[c & 3] : make_int4(0, 0, 0, 0);
                 } else {
-                    const int4* xs = reinterpret_cast<const int4*>(x + row * in_dim);
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) nxt[c] = (c < nv_x) ? __ldg(xs + c) : make_int4(0, 0, 0, 0);
+                    for (int c = 0; c < 8; ++c) nrow[c] = nxt[c];
                 }
                 mbar_wait(&d_full[s], pd);
                 pd ^= 1;
@@ -561,30 +580,17 @@ k_tc_bwd(const __half* __restrict__ grad, const __half* __restrict__ x, const __
                         if (bb) reinterpret_cast<int4*>(bb)[h * 4 + v] = val;
                     }
                 }
-                {
-                    int4 nrow[8];
-                    if (k < S - 1 || nv_x == 8) {
-                        coalesced_to_rows<8>(nxt, nrow, stg, lane);
-                    } else if (nv_x == 4) {
-                        int4 c4[4] = {nxt[0], nxt[1], nxt[2], nxt[3]}, r4[4];
-                        coalesced_to_rows<4>(c4, r4, stg, lane);
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) nrow[c] = (c < 4) ? r4[c & 3] : make_int4(0, 0, 0, 0);
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) nrow[c] = nxt[c];
-                    }
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const int4 v = nrow[c];
-                        hreg[4 * c] = (uint32_t)v.x; hreg[4 * c + 1] = (uint32_t)v.y; hreg[4 * c + 2] = (uint32_t)v.z; hreg[4 * c + 3] = (uint32_t)v.w;
-                        if (k < S - 1 || c < nv_x) *reinterpret_cast<int4*>(h_tile + c * 2048 + r_in_tile * 16) = v;
-                    }
+                for (int c = 0; c < 8; ++c) {
+                    const int4 v = nrow[c];
+                    hreg[4 * c] = (uint32_t)v.x; hreg[4 * c + 1] = (uint32_t)v.y; hreg[4 * c + 2] = (uint32_t)v.z; hreg[4 * c + 3] = (uint32_t)v.w;
+                    if (k < S - 1 || c < nv_x) *reinterpret_cast<int4*>(h_tile + c * 2048 + r_in_tile * 16) = v;
                 }
                 tc_wait_st();
                 fence_proxy_async_smem();
                 tc_fence_before();
                 mbar_arrive(&a_ready[s]);
+                if (k + 1 < S) issue_next(k + 1);
             }
             // ---- E_S: dx
             if (j + NSLOTS < my_tiles) {
@@ -674,10 +680,9 @@ k_tc_bwd(const __half* __restrict__ grad, const __half* __restrict__ x, const __
     if (warp == 0) tmem_dealloc(tmem0, kCols);
 }
 
-template <int PRO>
-static int launch_bwd(const __half* grad, const __half* x, const __half* W, const __half* fwd_buf, __half* bwd_buf, __half* grad_inputs, float* dW,
-                      uint32_t B, int in_dim, int n_hidden_mm, ProArgs pro, cudaStream_t st, const char* name) {
-    constexpr int NSLOTS = 2;
+template <int PRO, int NSLOTS>
+static int launch_bwd_n(const __half* grad, const __half* x, const __half* W, const __half* fwd_buf, __half* bwd_buf, __half* grad_inputs, float* dW,
+                        uint32_t B, int in_dim, int n_hidden_mm, ProArgs pro, cudaStream_t st, const char* name) {
     // TMEM: NSLOTS*96 + 16 + 64*n_hidden_mm + in_dim columns
     if (NSLOTS * kSlotCols + 16 + 64 * n_hidden_mm + in_dim > 512) { set_error("%s: network too deep for the tcgen05 path", name); return -2; }
     size_t smem = (size_t)in_dim * 128 + (size_t)n_hidden_mm * 8192 + 2048 + (size_t)NSLOTS * 2 * kGBytes + (size_t)NSLOTS * 4 * 4096 +
@@ -694,6 +699,23 @@ static int launch_bwd(const __half* grad, const __half* x, const __half* W, cons
     k_tc_bwd<NSLOTS, PRO><<<grid, 32 + NSLOTS * 128, smem, st>>>(grad, x, W, fwd_buf, bwd_buf, grad_inputs, dW, n_tiles, B, in_dim, n_hidden_mm, pro);
     ENERF_CHECK_LAUNCH(name);
     return 0;
+}
+
+static int bwd_slots() {
+    static int n = -1;
+    if (n < 0) {
+        const char* e = getenv("ENERF_TC_BWD_SLOTS");
+        n = (e && e[0] == '3') ? 3 : 2;
+    }
+    return n;
+}
+template <int PRO>
+static int launch_bwd(const __half* grad, const __half* x, const __half* W, const __half* fwd_buf, __half* bwd_buf, __half* grad_inputs, float* dW,
+                      uint32_t B, int in_dim, int n_hidden_mm, ProArgs pro, cudaStream_t st, const char* name) {
+    // 3 tiles in flight need 3*96 + 16 + 64*n_hidden_mm + in_dim <= 512 TMEM columns
+    if (bwd_slots() == 3 && 3 * kSlotCols + 16 + 64 * n_hidden_mm + in_dim <= 512)
+        return launch_bwd_n<PRO, 3>(grad, x, W, fwd_buf, bwd_buf, grad_inputs, dW, B, in_dim, n_hidden_mm, pro, st, name);
+    return launch_bwd_n<PRO, 2>(grad, x, W, fwd_buf, bwd_buf, grad_inputs, dW, B, in_dim, n_hidden_mm, pro, st, name);
 }
 
 int tc_backward(const __half* grad, const __half* x, const __half* W, const __half* fwd_buf, __half* bwd_buf, __half* grad_inputs, float* dW,
