@@ -358,8 +358,7 @@ k_tc_bwd(const __half* __restrict__ grad, const __half* __restrict__ x, const __
     uint8_t* whs = w0s + in_dim * 128;                    // n_hidden_mm x [8][64][16 B]
     uint8_t* wls = whs + n_hidden_mm * 8192;              // [8][16][16 B]
     uint8_t* tiles = wls + 2048;                          // per slot: G tile, H tile
-    uint8_t* stage_base = tiles + (size_t)NSLOTS * 2 * kGBytes;   // 4 KB per epilogue warp (row <-> coalesced transposition)
-    uint64_t* a_ready = reinterpret_cast<uint64_t*>(stage_base + (size_t)NSLOTS * 4 * 4096);
+    uint64_t* a_ready = reinterpret_cast<uint64_t*>(tiles + (size_t)NSLOTS * 2 * kGBytes);
     uint64_t* d_full = a_ready + NSLOTS;
     uint64_t* flush_bar = d_full + NSLOTS;
     uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(flush_bar + 1);
@@ -461,37 +460,17 @@ k_tc_bwd(const __half* __restrict__ grad, const __half* __restrict__ x, const __
         uint32_t hreg[32];       // this row's forward activation (64 fp16) used as ReLU mask by the next epilogue
         // Global rows needed by the NEXT epilogue stage are requested before waiting for the tensor core, so
         // their HBM latency overlaps the MMAs: `pre` = h_n row of the tile about to start, `nxt` = next stage's row.
-        // All of these loads are fully coalesced (512 B per warp instruction); the rows are brought into
-        // "row per lane" form through the warp's swizzled staging tile when they are consumed.
-        uint8_t* stg = stage_base + (size_t)(warp - 1) * 4096;
         int4 pre[8];
         if ((uint32_t)s < my_tiles) {
-            const size_t wrow0 = ((size_t)blockIdx.x + (size_t)s * gridDim.x) * kTile + q * 32;
-            ld_coalesced<8>(pre, reinterpret_cast<const int4*>(fwd_buf + ((size_t)n_hidden_mm * B + wrow0) * kW), lane);
+            const size_t row0 = ((size_t)blockIdx.x + (size_t)s * gridDim.x) * kTile + r_in_tile;
+            const int4* hs0 = reinterpret_cast<const int4*>(fwd_buf + ((size_t)n_hidden_mm * B + row0) * kW);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) pre[c] = __ldg(hs0 + c);
         }
 
         for (uint32_t j = s; j < my_tiles; j += NSLOTS) {
             const size_t tile = (size_t)blockIdx.x + (size_t)j * gridDim.x;
             const size_t row = tile * kTile + r_in_tile;
-            const size_t wrow0 = tile * kTile + q * 32;
-            // `nxt`: coalesced pieces of the rows the NEXT epilogue stage needs (h_{n-k} for k < S-1, the network input for k = S-1),
-            // requested one stage ahead so that HBM latency and the transposition overlap the tensor-core work
-            int4 nxt[8];
-            const int nv_x = in_dim / 8;
-            const bool coal_x = (nv_x == 4 || nv_x == 8);
-            auto issue_next = [&](int k) {
-                if (k < S - 1) {
-                    ld_coalesced<8>(nxt, reinterpret_cast<const int4*>(fwd_buf + ((size_t)(n_hidden_mm - k) * B + wrow0) * kW), lane);
-                } else if (coal_x) {
-                    const int4* xg = reinterpret_cast<const int4*>(x + wrow0 * in_dim);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) nxt[i] = (i < nv_x) ? __ldg(xg + i * 32 + lane) : make_int4(0, 0, 0, 0);
-                } else {
-                    const int4* xs = reinterpret_cast<const int4*>(x + row * in_dim);
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) nxt[c] = (c < nv_x) ? __ldg(xs + c) : make_int4(0, 0, 0, 0);
-                }
-            };
             // ---- E_0: dy -> TMEM A + dy tile (G buffer); h_n -> registers + H tile
             {
                 int4 v0, v1;
@@ -526,11 +505,9 @@ k_tc_bwd(const __half* __restrict__ grad, const __half* __restrict__ x, const __
                 tmem_st8(a_t, r8);
                 *reinterpret_cast<int4*>(g_tile + 0 * 2048 + r_in_tile * 16) = v0;
                 *reinterpret_cast<int4*>(g_tile + 1 * 2048 + r_in_tile * 16) = v1;
-                int4 hrow[8];
-                coalesced_to_rows<8>(pre, hrow, stg, lane);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    const int4 v = hrow[c];
+                    const int4 v = pre[c];
                     hreg[4 * c] = (uint32_t)v.x; hreg[4 * c + 1] = (uint32_t)v.y; hreg[4 * c + 2] = (uint32_t)v.z; hreg[4 * c + 3] = (uint32_t)v.w;
                     *reinterpret_cast<int4*>(h_tile + c * 2048 + r_in_tile * 16) = v;
                 }
@@ -538,22 +515,18 @@ k_tc_bwd(const __half* __restrict__ grad, const __half* __restrict__ x, const __
                 fence_proxy_async_smem();
                 tc_fence_before();
                 mbar_arrive(&a_ready[s]);
-                issue_next(1);
             }
             // ---- E_k, k = 1 .. S-1: g = D * relu'(h) -> TMEM A + G tile; next activation (or x) -> H tile
             for (int k = 1; k < S; ++k) {
-                // rows requested during the previous stage -> "row per lane" registers, while the MMAs of stage k-1 run
-                int4 nrow[8];
-                if (k < S - 1 || nv_x == 8) {
-                    coalesced_to_rows<8>(nxt, nrow, stg, lane);
-                } else if (nv_x == 4) {
-                    int4 c4[4] = {nxt[0], nxt[1], nxt[2], nxt[3]}, r4[4];
-                    coalesced_to_rows<4>(c4, r4, stg, lane);
+                int4 nxt[8];
+                if (k < S - 1) {
+                    const int4* hs = reinterpret_cast<const int4*>(fwd_buf + ((size_t)(n_hidden_mm - k) * B + row) * kW);
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) nrow[c] = (c < 4) ? r4[c & 3] : make_int4(0, 0, 0, 0);
+                    for (int c = 0; c < 8; ++c) nxt[c] = __ldg(hs + c);
                 } else {
+                    const int4* xs = reinterpret_cast<const int4*>(x + row * in_dim);
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) nrow[c] = nxt[c];
+                    for (int c = 0; c < 8; ++c) nxt[c] = (c < in_dim / 8) ? __ldg(xs + c) : make_int4(0, 0, 0, 0);
                 }
                 mbar_wait(&d_full[s], pd);
                 pd ^= 1;
@@ -582,49 +555,36 @@ k_tc_bwd(const __half* __restrict__ grad, const __half* __restrict__ x, const __
                 }
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    const int4 v = nrow[c];
+                    const int4 v = nxt[c];
                     hreg[4 * c] = (uint32_t)v.x; hreg[4 * c + 1] = (uint32_t)v.y; hreg[4 * c + 2] = (uint32_t)v.z; hreg[4 * c + 3] = (uint32_t)v.w;
-                    if (k < S - 1 || c < nv_x) *reinterpret_cast<int4*>(h_tile + c * 2048 + r_in_tile * 16) = v;
+                    if (k < S - 1 || c < in_dim / 8) *reinterpret_cast<int4*>(h_tile + c * 2048 + r_in_tile * 16) = v;
                 }
                 tc_wait_st();
                 fence_proxy_async_smem();
                 tc_fence_before();
                 mbar_arrive(&a_ready[s]);
-                if (k + 1 < S) issue_next(k + 1);
             }
             // ---- E_S: dx
             if (j + NSLOTS < my_tiles) {
-                const size_t nwrow0 = ((size_t)blockIdx.x + (size_t)(j + NSLOTS) * gridDim.x) * kTile + q * 32;
-                ld_coalesced<8>(pre, reinterpret_cast<const int4*>(fwd_buf + ((size_t)n_hidden_mm * B + nwrow0) * kW), lane);
+                const size_t nrow = ((size_t)blockIdx.x + (size_t)(j + NSLOTS) * gridDim.x) * kTile + r_in_tile;
+                const int4* hs0 = reinterpret_cast<const int4*>(fwd_buf + ((size_t)n_hidden_mm * B + nrow) * kW);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) pre[c] = __ldg(hs0 + c);
             }
             mbar_wait(&d_full[s], pd);
             pd ^= 1;
             tc_fence_after();
             if (grad_inputs) {
-                int4 xrow[8];
+                for (int c = 0; c < in_dim / 16; ++c) {
+                    uint32_t acc[16];
+                    tmem_ld16(d_t + c * 16, acc);
+                    tc_wait_ld();
+                    uint32_t p[8];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    if (c < in_dim / 16) {
-                        uint32_t acc[16];
-                        tmem_ld16(d_t + c * 16, acc);
-                        tc_wait_ld();
-                        uint32_t p[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) p[e] = pack2(__uint_as_float(acc[2 * e]), __uint_as_float(acc[2 * e + 1]));
-                        xrow[2 * c] = make_int4((int)p[0], (int)p[1], (int)p[2], (int)p[3]);
-                        xrow[2 * c + 1] = make_int4((int)p[4], (int)p[5], (int)p[6], (int)p[7]);
-                    }
-                }
-                if (in_dim == 32) {
-                    int4 r4[4] = {xrow[0], xrow[1], xrow[2], xrow[3]};
-                    store_rows<4>(reinterpret_cast<int4*>(grad_inputs + wrow0 * 32), r4, stg, lane);
-                } else if (in_dim == 64) {
-                    store_rows<8>(reinterpret_cast<int4*>(grad_inputs + wrow0 * 64), xrow, stg, lane);
-                } else {
-                    int4* dst = reinterpret_cast<int4*>(grad_inputs + row * in_dim);
-#pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        if (c < in_dim / 8) dst[c] = xrow[c];
+                    for (int e = 0; e < 8; ++e) p[e] = pack2(__uint_as_float(acc[2 * e]), __uint_as_float(acc[2 * e + 1]));
+                    int4* dst = reinterpret_cast<int4*>(grad_inputs + row * in_dim + c * 16);
+                    dst[0] = make_int4((int)p[0], (int)p[1], (int)p[2], (int)p[3]);
+                    dst[1] = make_int4((int)p[4], (int)p[5], (int)p[6], (int)p[7]);
                 }
             }
             tc_fence_before();
@@ -680,13 +640,13 @@ k_tc_bwd(const __half* __restrict__ grad, const __half* __restrict__ x, const __
     if (warp == 0) tmem_dealloc(tmem0, kCols);
 }
 
-template <int PRO, int NSLOTS>
-static int launch_bwd_n(const __half* grad, const __half* x, const __half* W, const __half* fwd_buf, __half* bwd_buf, __half* grad_inputs, float* dW,
-                        uint32_t B, int in_dim, int n_hidden_mm, ProArgs pro, cudaStream_t st, const char* name) {
+template <int PRO>
+static int launch_bwd(const __half* grad, const __half* x, const __half* W, const __half* fwd_buf, __half* bwd_buf, __half* grad_inputs, float* dW,
+                      uint32_t B, int in_dim, int n_hidden_mm, ProArgs pro, cudaStream_t st, const char* name) {
+    constexpr int NSLOTS = 2;
     // TMEM: NSLOTS*96 + 16 + 64*n_hidden_mm + in_dim columns
     if (NSLOTS * kSlotCols + 16 + 64 * n_hidden_mm + in_dim > 512) { set_error("%s: network too deep for the tcgen05 path", name); return -2; }
-    size_t smem = (size_t)in_dim * 128 + (size_t)n_hidden_mm * 8192 + 2048 + (size_t)NSLOTS * 2 * kGBytes + (size_t)NSLOTS * 4 * 4096 +
-                  (2 * NSLOTS + 1) * 8 + 16;
+    size_t smem = (size_t)in_dim * 128 + (size_t)n_hidden_mm * 8192 + 2048 + (size_t)NSLOTS * 2 * kGBytes + (2 * NSLOTS + 1) * 8 + 16;
     if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: it allocates all 512 TMEM columns
     if (smem > 220 * 1024) { set_error("%s: network too deep for the tcgen05 path", name); return -2; }
     static size_t configured = 0;
@@ -699,23 +659,6 @@ static int launch_bwd_n(const __half* grad, const __half* x, const __half* W, co
     k_tc_bwd<NSLOTS, PRO><<<grid, 32 + NSLOTS * 128, smem, st>>>(grad, x, W, fwd_buf, bwd_buf, grad_inputs, dW, n_tiles, B, in_dim, n_hidden_mm, pro);
     ENERF_CHECK_LAUNCH(name);
     return 0;
-}
-
-static int bwd_slots() {
-    static int n = -1;
-    if (n < 0) {
-        const char* e = getenv("ENERF_TC_BWD_SLOTS");
-        n = (e && e[0] == '3') ? 3 : 2;
-    }
-    return n;
-}
-template <int PRO>
-static int launch_bwd(const __half* grad, const __half* x, const __half* W, const __half* fwd_buf, __half* bwd_buf, __half* grad_inputs, float* dW,
-                      uint32_t B, int in_dim, int n_hidden_mm, ProArgs pro, cudaStream_t st, const char* name) {
-    // 3 tiles in flight need 3*96 + 16 + 64*n_hidden_mm + in_dim <= 512 TMEM columns
-    if (bwd_slots() == 3 && 3 * kSlotCols + 16 + 64 * n_hidden_mm + in_dim <= 512)
-        return launch_bwd_n<PRO, 3>(grad, x, W, fwd_buf, bwd_buf, grad_inputs, dW, B, in_dim, n_hidden_mm, pro, st, name);
-    return launch_bwd_n<PRO, 2>(grad, x, W, fwd_buf, bwd_buf, grad_inputs, dW, B, in_dim, n_hidden_mm, pro, st, name);
 }
 
 int tc_backward(const __half* grad, const __half* x, const __half* W, const __half* fwd_buf, __half* bwd_buf, __half* grad_inputs, float* dW,

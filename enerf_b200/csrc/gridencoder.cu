@@ -375,6 +375,9 @@ __device__ __forceinline__ void red_add(float* addr, float a) { atomicAdd(addr, 
 __device__ __forceinline__ void red_add2(float* addr, float a, float b) {
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
 }
+__device__ __forceinline__ void red_add4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ void red_add(__half* addr, float a) { atomicAdd(addr, __float2half_rn(a)); }
 __device__ __forceinline__ void red_add2(__half* addr, float a, float b) {
     const __half2 v = __halves2half2(__float2half_rn(a), __float2half_rn(b));   // gridencoder.cu:300
@@ -479,18 +482,39 @@ k_grid_bwd_walk(const T* __restrict__ grad, const float* __restrict__ inputs, co
             term[d][0] = cell[d] * mult[d];
             term[d][1] = (cell[d] + 1) * mult[d];
         }
+        uint32_t e[1 << D];
 #pragma unroll
         for (int idx = 0; idx < (1 << D); ++idx) {
             uint32_t i = 0;
 #pragma unroll
             for (int d = 0; d < D; ++d) i = g.use_hash ? (i ^ term[d][(idx >> d) & 1]) : (i + term[d][(idx >> d) & 1]);
             i = g.pow2 ? (i & (g.hashmap_size - 1)) : (i < g.hashmap_size ? i : i % g.hashmap_size);
-            const uint32_t e = i * C;
-            if (C == 1) {
-                red_add(tab + e, acc[idx][0]);
-            } else {
+            e[idx] = i * C;
+        }
+        if (C == 2 && sizeof(G) == 4) {
+            // The two corners along x are neighbouring table entries (index ^ 1 when hashed with prime 1, index + 1
+            // when dense): whenever they share an aligned 16-byte block one 128-bit reduction updates both.
 #pragma unroll
-                for (int ch = 0; ch < C; ch += 2) red_add2(tab + e + ch, acc[idx][ch], acc[idx][ch + (C > 1 ? 1 : 0)]);
+            for (int idx = 0; idx < (1 << D); idx += 2) {
+                const uint32_t e0 = e[idx], e1 = e[idx + 1];
+                if ((e0 ^ e1) == 2u) {
+                    const bool lo = e0 < e1;
+                    red_add4(reinterpret_cast<float*>(tab) + (lo ? e0 : e1), lo ? acc[idx][0] : acc[idx + 1][0], lo ? acc[idx][1] : acc[idx + 1][1],
+                             lo ? acc[idx + 1][0] : acc[idx][0], lo ? acc[idx + 1][1] : acc[idx][1]);
+                } else {
+                    red_add2(tab + e0, acc[idx][0], acc[idx][1]);
+                    red_add2(tab + e1, acc[idx + 1][0], acc[idx + 1][1]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int idx = 0; idx < (1 << D); ++idx) {
+                if (C == 1) {
+                    red_add(tab + e[idx], acc[idx][0]);
+                } else {
+#pragma unroll
+                    for (int ch = 0; ch < C; ch += 2) red_add2(tab + e[idx] + ch, acc[idx][ch], acc[idx][ch + (C > 1 ? 1 : 0)]);
+                }
             }
         }
     };

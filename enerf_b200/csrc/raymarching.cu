@@ -178,13 +178,23 @@ __device__ __forceinline__ bool probe(const Ray& r, const MarchCfg& c, const uin
 // Marches one ray with one warp.  Emits at most `limit` samples, starting at t0; returns the
 // number emitted (warp-uniform).  With WRITE, sample i of this ray goes to row i of
 // xyzs/dirs/deltas (already offset to the ray's range).
+// Log of the batches that emitted samples during the counting pass (per warp, in shared memory): with it the
+// writing pass only regenerates t for those batches and never touches the grid again.
+static constexpr int kLogBatches = 96;
+struct BatchLog {
+    float tb[kLogBatches];        // candidate 0 of the batch
+    uint32_t emit[kLogBatches];   // lanes that emitted
+};
+
 template <bool WRITE>
 __device__ uint32_t march_warp(const Ray& r, const MarchCfg& c, const uint8_t* __restrict__ grid,
                                float t0, float far, uint32_t limit, float* __restrict__ xyzs,
-                               float* __restrict__ dirs, float* __restrict__ deltas) {
+                               float* __restrict__ dirs, float* __restrict__ deltas, BatchLog* log = nullptr,
+                               uint32_t* n_logged = nullptr) {
     const unsigned lane = lane_id();
     const unsigned lt_mask = (1u << lane) - 1u;
     uint32_t count = 0;
+    uint32_t logged = 0;          // kLogBatches + 1 = overflow (log unusable)
     float tb = t0;                // candidate 0 of the current batch
     float skip_to = -FLT_MAX;     // pending "skip until t >= skip_to" from an empty voxel
     float last_t = t0;            // t after the previously emitted sample (raymarching.cu:425,462)
@@ -269,11 +279,69 @@ __device__ uint32_t march_warp(const Ray& r, const MarchCfg& c, const uint8_t* _
             last_t = __shfl_sync(kFull, tnext, 31 - __clz(emit));
         }
         count += (uint32_t)__popc(emit);
+        if (!WRITE && log != nullptr && emit) {
+            if (logged < (uint32_t)kLogBatches) {
+                if (lane == 0) {
+                    log->tb[logged] = tb;
+                    log->emit[logged] = emit;
+                }
+                ++logged;
+            } else {
+                logged = kLogBatches + 1;
+            }
+        }
 
         if (~m_range) break;                      // some candidate reached `far`: ray finished
         tb = __shfl_sync(kFull, tnext, 31);       // candidate 32 = next batch's candidate 0
     }
+    if (n_logged) *n_logged = logged;
     return count;
+}
+
+// Writing pass from the batch log: same t values (same repeated adds), same outputs, no grid probes.
+__device__ void replay_warp(const Ray& r, const MarchCfg& c, float t0, const BatchLog* log, uint32_t n_logged,
+                            float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas) {
+    const unsigned lane = lane_id();
+    const unsigned lt_mask = (1u << lane) - 1u;
+    uint32_t count = 0;
+    float last_t = t0;
+    for (uint32_t b = 0; b < n_logged; ++b) {
+        const float tb = log->tb[b];
+        const unsigned emit = log->emit[b];
+        float t = tb;
+        if (c.dt_gamma == 0.0f) {
+            const float cstep = clampf(0.0f, c.dt_min, c.dt_max);
+#pragma unroll
+            for (int j = 0; j < 31; ++j) {
+                const float tn = t + cstep;
+                t = ((unsigned)j < lane) ? tn : t;
+            }
+        } else {
+            for (int j = 0; j < 31; ++j) {
+                const float tn = t + step_of(t, c);
+                t = ((unsigned)j < lane) ? tn : t;
+            }
+        }
+        const float dt = step_of(t, c);
+        const float tnext = t + dt;
+        const bool me = (emit >> lane) & 1u;
+        const unsigned below = emit & lt_mask;
+        const int prev = below ? (31 - __clz(below)) : 0;
+        const float prev_tnext = __shfl_sync(kFull, tnext, prev);
+        if (me) {
+            const size_t row = (size_t)count + (size_t)__popc(below);
+            xyzs[row * 3 + 0] = clampf(__fmaf_rn(t, r.dx, r.ox), -c.bound, c.bound);
+            xyzs[row * 3 + 1] = clampf(__fmaf_rn(t, r.dy, r.oy), -c.bound, c.bound);
+            xyzs[row * 3 + 2] = clampf(__fmaf_rn(t, r.dz, r.oz), -c.bound, c.bound);
+            dirs[row * 3 + 0] = r.dx;
+            dirs[row * 3 + 1] = r.dy;
+            dirs[row * 3 + 2] = r.dz;
+            deltas[row * 2 + 0] = dt;
+            deltas[row * 2 + 1] = tnext - (below ? prev_tnext : last_t);
+        }
+        last_t = __shfl_sync(kFull, tnext, 31 - __clz(emit));
+        count += (uint32_t)__popc(emit);
+    }
 }
 
 __device__ __forceinline__ Ray load_ray(const float* __restrict__ rays_o, const float* __restrict__ rays_d, uint32_t n) {
@@ -301,7 +369,11 @@ k_march_rays_train(const float* __restrict__ rays_o, const float* __restrict__ r
         Pcg32 rng((uint64_t)n, 1u);
         t0 = __fmaf_rn(c.dt_min, rng.next_float(), t0);   // the reference's `t0 += dt_min * r` is contracted by nvcc
     }
-    const uint32_t num_steps = march_warp<false>(r, c, grid, t0, far, max_steps, nullptr, nullptr, nullptr);
+    __shared__ BatchLog logs[8];
+    BatchLog* log = &logs[threadIdx.x >> 5];
+    uint32_t n_logged = 0;
+    const uint32_t num_steps = march_warp<false>(r, c, grid, t0, far, max_steps, nullptr, nullptr, nullptr, log, &n_logged);
+    __syncwarp();
 
     uint32_t point_index = 0;
     if (lane == 0) {
@@ -314,8 +386,11 @@ k_march_rays_train(const float* __restrict__ rays_o, const float* __restrict__ r
     point_index = __shfl_sync(kFull, point_index, 0);
     if (num_steps == 0) return;
     if (point_index + num_steps >= M) return;  // `>=` as raymarching.cu:416
-    march_warp<true>(r, c, grid, t0, far, num_steps, xyzs + (size_t)point_index * 3,
-                     dirs + (size_t)point_index * 3, deltas + (size_t)point_index * 2);
+    float* px = xyzs + (size_t)point_index * 3;
+    float* pd = dirs + (size_t)point_index * 3;
+    float* pl = deltas + (size_t)point_index * 2;
+    if (n_logged <= (uint32_t)kLogBatches) replay_warp(r, c, t0, log, n_logged, px, pd, pl);
+    else march_warp<true>(r, c, grid, t0, far, num_steps, px, pd, pl);     // more emitting batches than the log holds: re-march
 }
 
 // raymarching.cu:700-804.  One warp per alive ray, at most n_step samples from rays_t.
