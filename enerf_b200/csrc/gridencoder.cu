@@ -16,12 +16,13 @@
 //     grid.py:70) and scatters with vector reductions (red.global.add.v2.f32 / .noftz.f16x2).
 #include "common.cuh"
 #include <math.h>
+#include <type_traits>
 
 namespace enerf {
 
 static constexpr unsigned kFull = 0xffffffffu;
 static constexpr int kSamplesPerCta = 32;
-static int g_fwd_fast = 1;   // 1: k_grid_fwd3 for D = 3 without input gradients, 0: always the generic kernel
+static int g_fwd_fast = 1;   // D = 3 without input gradients: 1 = k_grid_fwd_w (warp walks the levels), 2 = k_grid_fwd3; 0 = always the generic kernel
 static int g_bwd_walk = 1;   // 1: walking scatter (register aggregation along rays), 0: one reduction per corner
 
 // ---- element-type helpers: the accumulator is rounded to T after every corner -----------
@@ -369,6 +370,228 @@ k_grid_fwd3(const float* __restrict__ inputs, const T* __restrict__ grid, const 
 }
 
 // ------------------------------------------------------------------------------------------
+// forward, hot path v2 (D = 3, no input gradients): "a warp owns 32 consecutive samples and walks
+// all levels".  Differences to k_grid_fwd3 (one warp per (32 samples, level)):
+//   * persistent CTAs: the level table is built once per CTA, not once per 32 samples, and there is
+//     no CTA-wide barrier in the sample loop (staging tiles are warp-private);
+//   * sample coordinates are read once per sample instead of once per (sample, level);
+//   * the corner index comes from one of three branch-free forms chosen per level (warp-uniform):
+//     hashed & power-of-two table (xor, and), dense without wrap-around (add), generic;
+//   * two levels are in flight per thread (16 independent gathers) before the first blend.
+// Arithmetic (fma position, corner order, per-corner fp16 rounding) is unchanged: bit-identical.
+// ------------------------------------------------------------------------------------------
+struct LevelTabW {
+    float scale;
+    uint32_t hs;       // table entries
+    uint32_t offset;   // first entry of the level
+    uint32_t m1, m2;   // index = x*1 (+|^) y*m1 (+|^) z*m2
+    uint32_t mode;     // 0: hashed, pow2 table; 1: dense, index < hs always; 2: generic (bit0 of flags = hashed, bit1 = pow2)
+    uint32_t flags;
+    uint32_t pad;
+};
+
+template <int C, int MODE>
+__device__ __forceinline__ void corner_index(const LevelTabW& lt, const uint32_t (&pg)[3], uint32_t (&e)[8]) {
+    const uint32_t ax[2] = {pg[0], pg[0] + 1};
+    const uint32_t ay[2] = {pg[1] * lt.m1, pg[1] * lt.m1 + lt.m1};
+    const uint32_t az[2] = {pg[2] * lt.m2, pg[2] * lt.m2 + lt.m2};
+    if (MODE == 0) {
+        const uint32_t mask = lt.hs - 1;
+#pragma unroll
+        for (int idx = 0; idx < 8; ++idx) e[idx] = ((ax[idx & 1] ^ ay[(idx >> 1) & 1] ^ az[idx >> 2]) & mask) * C;
+    } else if (MODE == 1) {
+#pragma unroll
+        for (int idx = 0; idx < 8; ++idx) e[idx] = (ax[idx & 1] + ay[(idx >> 1) & 1] + az[idx >> 2]) * C;
+    } else {
+        const bool hashed = lt.flags & 1u, pow2 = lt.flags & 2u;
+#pragma unroll
+        for (int idx = 0; idx < 8; ++idx) {
+            const uint32_t a = ax[idx & 1], bq = ay[(idx >> 1) & 1], c = az[idx >> 2];
+            uint32_t i = hashed ? (a ^ bq ^ c) : (a + bq + c);
+            i = pow2 ? (i & (lt.hs - 1)) : (i < lt.hs ? i : i % lt.hs);
+            e[idx] = i * C;
+        }
+    }
+}
+
+// one (sample, level): corner values fetched (`fetch`), then blended in the reference's order (`blend`)
+template <typename T, int C>
+struct LevelWork {
+    float wxy[4], wz[2];
+    T v[8][C];
+    template <int MODE>
+    __device__ __forceinline__ void fetch(const LevelTabW& lt, const T* __restrict__ grid, const float (&x)[3]) {
+        const T* __restrict__ tab = grid + (size_t)lt.offset * C;
+        float fr[3];
+        uint32_t pg[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const float p = __fmaf_rn(x[d], lt.scale, 0.5f);
+            const float fl = floorf(p);
+            pg[d] = (uint32_t)fl;
+            fr[d] = p - fl;
+        }
+        uint32_t e[8];
+        corner_index<C, MODE>(lt, pg, e);
+        if (C == 2 && sizeof(T) == 2) {
+#pragma unroll
+            for (int idx = 0; idx < 8; ++idx) {
+                const __half2 h2 = __ldg(reinterpret_cast<const __half2*>(tab + e[idx]));
+                v[idx][0] = *reinterpret_cast<const T*>(&h2.x);
+                v[idx][C - 1] = *reinterpret_cast<const T*>(&h2.y);
+            }
+        } else {
+#pragma unroll
+            for (int idx = 0; idx < 8; ++idx)
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) v[idx][ch] = Elem<T>::ld(tab + e[idx] + ch);
+        }
+        const float wx0 = 1.0f - fr[0], wy0 = 1.0f - fr[1];
+        wxy[0] = wx0 * wy0; wxy[1] = fr[0] * wy0; wxy[2] = wx0 * fr[1]; wxy[3] = fr[0] * fr[1];
+        wz[0] = 1.0f - fr[2]; wz[1] = fr[2];
+    }
+    __device__ __forceinline__ void blend(uint32_t (&ow)[(C * (int)sizeof(T)) / 4], bool zero) const {
+        constexpr int WPL = (C * (int)sizeof(T)) / 4;
+        if (C == 2 && sizeof(T) == 2) {
+            __half2 res2 = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+            for (int idx = 0; idx < 8; ++idx) {
+                const float w = wxy[idx & 3] * wz[idx >> 2];
+                const float gx = Elem<T>::to_f(v[idx][0]), gy = Elem<T>::to_f(v[idx][C - 1]);
+                res2 = __hadd2(res2, __floats2half2_rn(w * gx, w * gy));
+            }
+            ow[0] = zero ? 0u : *reinterpret_cast<const uint32_t*>(&res2);
+        } else {
+            T res[C];
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) res[ch] = Elem<T>::from_f(0.f);
+#pragma unroll
+            for (int idx = 0; idx < 8; ++idx) {
+                const float w = wxy[idx & 3] * wz[idx >> 2];
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) res[ch] = Elem<T>::acc(res[ch], w, v[idx][ch]);
+            }
+            const uint32_t* rwords = reinterpret_cast<const uint32_t*>(res);
+#pragma unroll
+            for (int w = 0; w < WPL; ++w) ow[w] = zero ? 0u : rwords[w];
+        }
+    }
+};
+
+template <typename T, int C, bool BLC>
+__global__ void __launch_bounds__(256)
+k_grid_fwd_w(const float* __restrict__ inputs, const T* __restrict__ grid, const int32_t* __restrict__ offsets,
+             T* __restrict__ outputs, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype, uint32_t n_groups,
+             uint32_t row_words /* staging row stride in 32-bit words (odd) */) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ LevelTabW ltab[64];
+    __shared__ uint32_t s_plan[2];                     // [0]: number of leading dense (mode 1) levels, [1]: 1 = some level needs the generic form
+    constexpr int WPL = (C * (int)sizeof(T)) / 4;      // 32-bit words per level in an output row (>= 1 on this path)
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (tid < L) {
+        const LevelGeom g = level_geom(offsets, tid, S, H, gridtype, 3);
+        LevelTabW t;
+        t.scale = g.scale;
+        t.hs = g.hashmap_size;
+        t.offset = g.offset;
+        const uint32_t r1 = g.resolution + 1;
+        bool nowrap = false;
+        if (g.use_hash) {
+            t.m1 = 2654435761u;
+            t.m2 = 805459861u;
+        } else {                                 // the stride loop of gridencoder.cu:58-62, dimension by dimension
+            t.m1 = (r1 <= g.hashmap_size) ? r1 : 0u;
+            t.m2 = (t.m1 != 0u && r1 * r1 <= g.hashmap_size) ? r1 * r1 : 0u;
+            // corner coordinates are <= resolution, so the largest dense index is resolution*(1+m1+m2)
+            nowrap = (uint64_t)g.resolution * (1ull + t.m1 + t.m2) < (uint64_t)g.hashmap_size;
+        }
+        t.flags = (g.use_hash ? 1u : 0u) | (g.pow2 ? 2u : 0u);
+        t.mode = (g.use_hash && g.pow2) ? 0u : (nowrap ? 1u : 2u);
+        t.pad = 0;
+        ltab[tid] = t;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // the usual table is "dense levels first, hashed power-of-two levels after": two branch-free loops
+        uint32_t nd = 0, generic = 0;
+        while (nd < L && ltab[nd].mode == 1u) ++nd;
+        for (uint32_t l = nd; l < L; ++l) generic |= (ltab[l].mode != 0u) ? 1u : 0u;
+        s_plan[0] = nd;
+        s_plan[1] = generic;
+    }
+    __syncthreads();
+    const uint32_t n_dense = s_plan[1] ? 0u : s_plan[0];
+    const bool generic = s_plan[1] != 0u;
+
+    uint32_t* stage = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)warp * 32 * row_words;
+    const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
+    const uint32_t rw = L * WPL;
+    const int rw_shift = ((rw & (rw - 1)) == 0) ? (31 - __clz(rw)) : -1;
+
+    for (uint32_t group = blockIdx.x * (blockDim.x >> 5) + warp; group < n_groups; group += warps_total) {
+        const uint32_t b0 = group * 32u;
+        const uint32_t b = b0 + lane;
+        const bool active = b < B;
+        float x[3] = {0.f, 0.f, 0.f};
+        bool oob = true;
+        if (active) oob = load_pos<3>(inputs, b, x);
+        if (oob) x[0] = x[1] = x[2] = 0.f;         // keep the address arithmetic in range; the result is zeroed below
+
+        auto emit = [&](uint32_t level, const uint32_t (&ow)[WPL]) {
+            if (BLC) {
+#pragma unroll
+                for (int w = 0; w < WPL; ++w) stage[lane * row_words + level * WPL + w] = ow[w];
+            } else if (active) {
+                uint32_t* __restrict__ o = reinterpret_cast<uint32_t*>(outputs + ((size_t)level * B + b) * C);
+#pragma unroll
+                for (int w = 0; w < WPL; ++w) o[w] = ow[w];
+            }
+        };
+        // levels [lo, hi) with the index form MODE, two levels (16 gathers) in flight per thread
+        auto run = [&](auto mode_tag, uint32_t lo, uint32_t hi) {
+            constexpr int MODE = decltype(mode_tag)::value;
+            uint32_t level = lo;
+            for (; level + 1 < hi; level += 2) {
+                LevelWork<T, C> wa, wb;
+                wa.template fetch<MODE>(ltab[level], grid, x);
+                wb.template fetch<MODE>(ltab[level + 1], grid, x);
+                uint32_t oa[WPL], ob[WPL];
+                wa.blend(oa, oob);
+                wb.blend(ob, oob);
+                emit(level, oa);
+                emit(level + 1, ob);
+            }
+            if (level < hi) {
+                LevelWork<T, C> wa;
+                wa.template fetch<MODE>(ltab[level], grid, x);
+                uint32_t oa[WPL];
+                wa.blend(oa, oob);
+                emit(level, oa);
+            }
+        };
+        if (generic) {
+            run(std::integral_constant<int, 2>{}, 0u, L);
+        } else {
+            run(std::integral_constant<int, 1>{}, 0u, n_dense);
+            run(std::integral_constant<int, 0>{}, n_dense, L);
+        }
+
+        if (BLC) {
+            __syncwarp();
+            const uint32_t n_words = min(32u, B - b0) * rw;
+            uint32_t* __restrict__ o32 = reinterpret_cast<uint32_t*>(outputs + (size_t)b0 * L * C);
+            if (rw_shift >= 0) {
+                for (uint32_t k = lane; k < n_words; k += 32) o32[k] = stage[(k >> rw_shift) * row_words + (k & (rw - 1))];
+            } else {
+                for (uint32_t k = lane; k < n_words; k += 32) o32[k] = stage[(k / rw) * row_words + (k % rw)];
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // backward (scatter-add into the gradient table)
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void red_add(float* addr, float a) { atomicAdd(addr, a); }
@@ -606,6 +829,18 @@ static int launch_fwd(const float* inputs, const T* emb, const int32_t* offsets,
     const dim3 block(32, min(L, 16u));
     const dim3 grid(ceil_div(B, (uint32_t)kSamplesPerCta));
     const bool fast = (D == 3) && !cg && g_fwd_fast;
+    constexpr int kWpl = (C * (int)sizeof(T)) / 4;
+    if (fast && g_fwd_fast == 1 && kWpl >= 1 && L * kWpl <= 64) {
+        // v2: warp walks all levels of its 32 samples (persistent CTAs of 8 warps)
+        const uint32_t n_groups = ceil_div(B, 32u);
+        const uint32_t row_words = (L * kWpl) | 1u;
+        const size_t smem = (out_layout == 1) ? (size_t)8 * 32 * row_words * 4 : 0;
+        const uint32_t ctas = min(ceil_div(n_groups, 8u), (uint32_t)kNumSM * 6u);
+        if (out_layout == 1) k_grid_fwd_w<T, (kWpl >= 1 ? C : 2), true><<<ctas, 256, smem, st>>>(inputs, emb, offsets, outputs, B, L, S, H, gridtype, n_groups, row_words);
+        else k_grid_fwd_w<T, (kWpl >= 1 ? C : 2), false><<<ctas, 256, 0, st>>>(inputs, emb, offsets, outputs, B, L, S, H, gridtype, n_groups, row_words);
+        ENERF_CHECK_LAUNCH("grid_encode_forward");
+        return 0;
+    }
     if (out_layout == 1) {
         const uint32_t rs = stage_row_stride(L, C, sizeof(T));
         const size_t smem = (size_t)kSamplesPerCta * rs * sizeof(T);
@@ -674,7 +909,7 @@ using namespace enerf;
 extern "C" {
 
 int enerf_grid_set_forward_mode(int mode) {
-    ENERF_REQUIRE(mode == 0 || mode == 1, "grid_set_forward_mode", "mode must be 0 (generic kernel) or 1 (hoisted D=3 kernel)");
+    ENERF_REQUIRE(mode >= 0 && mode <= 2, "grid_set_forward_mode", "mode must be 0 (generic kernel), 1 (warp-walks-levels D=3 kernel) or 2 (per-level D=3 kernel)");
     g_fwd_fast = mode;
     return 0;
 }

@@ -125,8 +125,9 @@ int enerf_grid_encode_backward(const void* grad, const float* inputs, const void
  * 32 consecutive samples of one level and aggregates in registers while they stay in one cell;
  * 0 = one reduction per corner per sample (the reference's strategy).  Same sums either way. */
 int enerf_grid_set_backward_mode(int mode);
-/* Forward kernel selector (tests): 1 (default) = hoisted D=3 kernel when no input gradient is asked for,
- * 0 = always the generic kernel.  Bit-identical outputs. */
+/* Forward kernel selector (tests), D = 3 without input gradients: 1 (default) = a warp walks all levels of its
+ * 32 samples (persistent CTAs), 2 = one warp per (32 samples, level), 0 = always the generic kernel.
+ * Bit-identical outputs. */
 int enerf_grid_set_forward_mode(int mode);
 
 /* -------------------------------------------------------------------- shencoder ---- */

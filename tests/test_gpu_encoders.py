@@ -87,8 +87,8 @@ def test_grid_forward_matches_reference_build(dtype):
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float16])
 def test_grid_forward_hoisted_kernel_is_bit_identical_to_generic(dtype):
-    """k_grid_fwd3 (per-level constants in smem, hoisted index/weight terms, packed fp16x2 arithmetic) vs k_grid_fwd, and both vs the
-    reference build when it is available."""
+    """The two hot-path kernels — k_grid_fwd_w (mode 1: a warp walks all levels of its 32 samples) and k_grid_fwd3 (mode 2: one warp per
+    (32 samples, level)) — vs the generic k_grid_fwd (mode 0), and all vs the reference build when it is available."""
     from enerf_b200 import _lib
     R = ref_mod("_gridencoder")
     rng = np.random.default_rng(12)
@@ -101,15 +101,16 @@ def test_grid_forward_hoisted_kernel_is_bit_identical_to_generic(dtype):
         B = len(x)
         outs = {}
         try:
-            for mode in (1, 0):
+            for mode in (1, 2, 0):
                 _lib.call("enerf_grid_set_forward_mode", mode)
                 for layout in (0, 1):
                     o, _ = _fwd(x, emb, offsets, pls, layout, gridtype=gridtype)
                     outs[(mode, layout)] = o
         finally:
             _lib.call("enerf_grid_set_forward_mode", 1)
-        assert torch.equal(outs[(1, 0)], outs[(0, 0)]), (bound, C, L, gridtype)
-        assert torch.equal(outs[(1, 1)], outs[(0, 1)]), (bound, C, L, gridtype)
+        for mode in (1, 2):
+            assert torch.equal(outs[(mode, 0)], outs[(0, 0)]), (mode, bound, C, L, gridtype)
+            assert torch.equal(outs[(mode, 1)], outs[(0, 1)]), (mode, bound, C, L, gridtype)
         assert torch.equal(outs[(1, 1)].view(B, L, C).permute(1, 0, 2), outs[(1, 0)])
         if R is not None:
             te = t(emb)
