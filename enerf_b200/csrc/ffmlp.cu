@@ -358,6 +358,7 @@ int tc_forward_sigma_head(const __half* feat, const __half* W, uint32_t B, int n
 int tc_forward_rgb_head(const __half* cin, const __half* W, uint32_t B, int n_hidden_mm, __half* fwd_buf, float* rgb, int n_ch, cudaStream_t st);
 int tc_backward_rgb(const float* g_rgb, const float* rgb, int n_ch, const __half* cin, const __half* W, const __half* fwd_buf, __half* dcin, float* dW,
                     uint32_t B, int n_hidden_mm, cudaStream_t st);
+void tc_set_bwd_tma(int on);
 int tc_backward_sigma(const float* g_sigma, const float* sigma, const __half* dcin, const __half* feat, const __half* W, const __half* fwd_buf,
                       __half* dfeat, float* dW, uint32_t B, int n_hidden_mm, cudaStream_t st);
 }
@@ -509,8 +510,9 @@ int enerf_ffmlp_uses_tcgen05(uint32_t input_dim, uint32_t hidden_dim, uint32_t n
 }
 
 int enerf_ffmlp_set_path(int path) {
-    ENERF_REQUIRE(path == 0 || path == 1, "ffmlp_set_path", "path must be 0 (auto) or 1 (generic mma.sync kernels)");
-    g_mlp_path = path;
+    ENERF_REQUIRE(path >= 0 && path <= 2, "ffmlp_set_path", "path must be 0 (auto), 1 (generic mma.sync kernels) or 2 (tcgen05 without TMA operand loads)");
+    g_mlp_path = (path == 1) ? 1 : 0;
+    tcm::tc_set_bwd_tma(path != 2);
     return 0;
 }
 

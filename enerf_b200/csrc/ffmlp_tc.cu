@@ -14,6 +14,7 @@
 //   Weights are staged once per CTA in shared memory in the no-swizzle canonical layout
 //   (tc_common.cuh); hand-offs use mbarriers (128 arrivals: "A ready"; tcgen05.commit: "D full").
 #include "tc_common.cuh"
+#include <cuda.h>
 #include <stdlib.h>
 
 namespace enerf {
@@ -661,19 +662,430 @@ static int launch_bwd(const __half* grad, const __half* x, const __half* W, cons
     return 0;
 }
 
+
+// ================================================================================================
+// Backward, TMA variant (k_tc_bwd_tma).  Same mathematics and the same TMEM plan as k_tc_bwd; what
+// changes is how the stored forward activations reach the SM.  k_tc_bwd has every epilogue thread
+// read its own 128-byte row (8 strided 16-byte loads per stage: 32 L1 wavefronts per request, the LSU
+// data pipe sat at 75-80 % in ncu) and copy it into the canonical operand tile.  Here the MMA thread
+// issues ONE cp.async.bulk.tensor per stage: the [128 x 64] fp16 tile of forward_buffer (or the
+// [128 x in_dim] input tile for the last stage) lands in shared memory in the 128-byte (64-byte)
+// TMA swizzle, which tcgen05.mma reads directly as the MN-major wgrad operand; a two-deep ring per
+// slot lets the load of stage i+1 fly while stage i computes.  Epilogue threads only read their row's
+// ReLU mask from that tile (8 conflict-free LDS.128) and never touch global memory for activations.
+//   ring protocol (per slot, stage counter i runs across tiles): load(i) -> buffer i&1, signalled on
+//   h_full[slot][i&1]; buffer i&1 is free again when E_{i+1} has read its mask (a_ready of stage i+1)
+//   and wgrad(i) has completed (d_full of stage i, which E_{i+1} waited for) -> the MMA thread issues
+//   load(i+2) right after it observes a_ready(i+1).
+// ================================================================================================
+struct alignas(64) TmaDesc { uint8_t bytes[128]; };     // CUtensorMap (opaque here; encoded on the host)
+
+template <int NSLOTS, int PRO, int IN_DIM>
+__global__ void __launch_bounds__(32 + NSLOTS * 128, 1)
+k_tc_bwd_tma(const __grid_constant__ TmaDesc tm_h, const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ grad,
+             const __half* __restrict__ W, __half* __restrict__ grad_inputs, float* __restrict__ dW, uint32_t n_tiles, uint32_t B,
+             int n_hidden_mm, ProArgs pro) {
+    constexpr int in_dim = IN_DIM;
+    constexpr uint32_t kXSw = IN_DIM * 2;                  // swizzle bytes of the input tile (row bytes): 64 or 128
+    extern __shared__ uint8_t smem_dyn[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    uint8_t* hring = smem;                                          // NSLOTS x 2 x 16 KB, 1024-byte aligned (TMA swizzle atoms)
+    uint8_t* gtiles = hring + (size_t)NSLOTS * 2 * kGBytes;         // NSLOTS x 16 KB, canonical [chunk][row][16 B]
+    uint8_t* w0s = gtiles + (size_t)NSLOTS * kGBytes;               // [in_dim/8][64][16 B]   (forward layout)
+    uint8_t* whs = w0s + in_dim * 128;                              // n_hidden_mm x [8][64][16 B]
+    uint8_t* wls = whs + n_hidden_mm * 8192;                        // [8][16][16 B]
+    uint64_t* a_ready = reinterpret_cast<uint64_t*>(wls + 2048);
+    uint64_t* d_full = a_ready + NSLOTS;
+    uint64_t* h_full = d_full + NSLOTS;                             // [NSLOTS][2]
+    uint64_t* flush_bar = h_full + 2 * NSLOTS;
+    uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(flush_bar + 1);
+
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    constexpr uint32_t kCols = 512;
+
+    stage_matrix(w0s, W, kW, in_dim, tid, nthreads);
+    for (int j = 0; j < n_hidden_mm; ++j) stage_matrix(whs + j * 8192, W + kW * in_dim + j * kW * kW, kW, kW, tid, nthreads);
+    stage_matrix(wls, W + kW * in_dim + n_hidden_mm * kW * kW, 16, kW, tid, nthreads);
+    if (tid == 0) {
+        for (int s = 0; s < NSLOTS; ++s) {
+            mbar_init(&a_ready[s], 128);
+            mbar_init(&d_full[s], 1);
+            mbar_init(&h_full[2 * s], 1);
+            mbar_init(&h_full[2 * s + 1], 1);
+        }
+        mbar_init(flush_bar, 1);
+        mbar_fence_init();
+        tma_prefetch_desc(&tm_h);
+        tma_prefetch_desc(&tm_x);
+    }
+    if (warp == 0) tmem_alloc(tmem_base_ptr, kCols);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem0 = *tmem_base_ptr;
+
+    const int S = n_hidden_mm + 2;
+    const uint32_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const uint32_t acc_last = tmem0 + NSLOTS * kSlotCols;
+    const uint32_t acc_hid = acc_last + 16;
+    const uint32_t acc_0 = acc_hid + n_hidden_mm * 64;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t pa[NSLOTS], cons[NSLOTS], total[NSLOTS], issued[NSLOTS], phase[NSLOTS];
+            uint32_t remaining = 0, started = 0;
+            // load i of slot s: stage k = i % S of the slot's (i / S)-th tile
+            auto issue_load = [&](int s) {
+                const uint32_t i = issued[s]++;
+                const uint32_t tl = i / (uint32_t)S, k = i - tl * (uint32_t)S;
+                const uint32_t tile = blockIdx.x + ((uint32_t)s + tl * NSLOTS) * gridDim.x;
+                const uint32_t dst = smem_u32(hring + ((size_t)s * 2 + (i & 1u)) * kGBytes);
+                uint64_t* bar = &h_full[2 * s + (i & 1u)];
+                if (k + 1 < (uint32_t)S) {
+                    mbar_arrive_expect_tx(bar, kGBytes);
+                    tma_load_2d(dst, &tm_h, 0, (int32_t)((uint32_t)(n_hidden_mm - (int)k) * B + tile * kTile), bar);
+                } else {
+                    mbar_arrive_expect_tx(bar, kTile * in_dim * 2);
+                    tma_load_2d(dst, &tm_x, 0, (int32_t)(tile * kTile), bar);
+                }
+            };
+#pragma unroll
+            for (int s = 0; s < NSLOTS; ++s) {
+                pa[s] = 0;
+                cons[s] = 0;
+                phase[s] = 0;
+                issued[s] = 0;
+                const uint32_t left = (my_tiles > (uint32_t)s) ? (my_tiles - s + NSLOTS - 1) / NSLOTS : 0;
+                total[s] = left * S;
+                remaining += total[s];
+                if (total[s] > 0) issue_load(s);
+                if (total[s] > 1) issue_load(s);
+            }
+            while (remaining > 0) {
+#pragma unroll
+                for (int s = 0; s < NSLOTS; ++s) {
+                    if (cons[s] == total[s]) continue;
+                    const uint32_t i = cons[s];
+                    const int k = (int)(i % (uint32_t)S);
+                    const uint32_t d_t = tmem0 + s * kSlotCols, a_t = d_t + 64;
+                    const uint32_t g_s = smem_u32(gtiles + (size_t)s * kGBytes);
+                    const uint32_t h_s = smem_u32(hring + ((size_t)s * 2 + (i & 1u)) * kGBytes);
+                    if (phase[s] == 0) {
+                        if (!mbar_test(&a_ready[s], pa[s])) continue;
+                        pa[s] ^= 1;
+                        tc_fence_after();
+                        // E_i is done: it has read its ReLU mask from the buffer of stage i-1, whose wgrad completed before E_i started
+                        if (i >= 1 && issued[s] < total[s]) issue_load(s);
+                        if (k == 0) {
+                            // dgrad through the output layer: D[128x64] = dy[128x16] . W_last[16x64]
+                            mma_ts(d_t, a_t, smem_desc(smem_u32(wls), 128, 16 * 16), idesc_f16(kTile, 64, false, true), false);
+                        } else if (k <= n_hidden_mm) {
+                            const uint32_t wj = smem_u32(whs + (n_hidden_mm - k) * 8192);
+                            for (int ks = 0; ks < 4; ++ks)
+                                mma_ts(d_t, a_t + ks * 8, smem_desc(wj + ks * 256, 128, 64 * 16), idesc_f16(kTile, 64, false, true), ks > 0);
+                        } else {
+                            // dx = g_0 . W_0 — issued even when the caller does not ask for grad_inputs (4 small MMAs): a
+                            // `grad_inputs != nullptr` guard here gets if-converted by ptxas 12.9 into predicated UTCHMMAs whose
+                            // descriptor R2UR for the second K step is skipped (observed: K rows 16..31 read the rows 0..15 tile).
+                            for (int ks = 0; ks < 4; ++ks)
+                                mma_ts(d_t, a_t + ks * 8, smem_desc(smem_u32(w0s) + ks * 256, 128, 64 * 16),
+                                       idesc_f16(kTile, (uint32_t)in_dim, false, true), ks > 0);
+                        }
+                        phase[s] = 1;
+                    }
+                    // wgrad needs the activation tile of this stage
+                    if (!mbar_test(&h_full[2 * s + (i & 1u)], (i >> 1) & 1u)) continue;
+                    tc_fence_after();
+                    const bool acc = (started >> k) & 1u;
+                    started |= 1u << k;
+                    if (k == 0) {
+                        // dW_last^T[64x16] += h_n^T[64x128] . dy[128x16]   (A = activation tile, B = dy tile in the G buffer)
+                        for (int ks = 0; ks < 8; ++ks)
+                            mma_ss(acc_last, smem_desc_sw(h_s + ks * 2048, 128), smem_desc(g_s + ks * 256, 128, 2048),
+                                   idesc_f16(64, 16, true, true), acc || ks > 0);
+                    } else if (k <= n_hidden_mm) {
+                        for (int ks = 0; ks < 8; ++ks)
+                            mma_ss(acc_hid + (n_hidden_mm - k) * 64, smem_desc(g_s + ks * 256, 128, 2048), smem_desc_sw(h_s + ks * 2048, 128),
+                                   idesc_f16(64, 64, true, true), acc || ks > 0);
+                    } else {
+                        for (int ks = 0; ks < 8; ++ks)
+                            mma_ss(acc_0, smem_desc(g_s + ks * 256, 128, 2048), smem_desc_sw(h_s + ks * 16 * kXSw, kXSw),
+                                   idesc_f16(64, (uint32_t)in_dim, true, true), acc || ks > 0);
+                    }
+                    tc_commit(&d_full[s]);
+                    phase[s] = 0;
+                    ++cons[s];
+                    --remaining;
+                }
+            }
+            tc_commit(flush_bar);
+        }
+    } else {
+        const int s = (warp - 1) >> 2;
+        const int q = warp & 3;
+        const int r_in_tile = q * 32 + lane;
+        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+        const uint32_t d_t = tmem0 + lane_sel + s * kSlotCols, a_t = d_t + 64;
+        uint8_t* g_tile = gtiles + (size_t)s * kGBytes;
+        uint32_t pd = 0;
+        uint32_t i = 0;                                 // slot-local stage counter (mirrors the MMA thread's)
+
+        for (uint32_t j = s; j < my_tiles; j += NSLOTS) {
+            const size_t tile = (size_t)blockIdx.x + (size_t)j * gridDim.x;
+            const size_t row = tile * kTile + r_in_tile;
+            // ---- E_0: dy -> TMEM A + dy tile (G buffer)
+            {
+                int4 v0, v1;
+                if (PRO == 0) {
+                    const int4* src = reinterpret_cast<const int4*>(grad + row * 16);
+                    v0 = __ldg(src);
+                    v1 = __ldg(src + 1);
+                } else if (PRO == 1) {
+                    float dyv[4] = {0.f, 0.f, 0.f, 0.f};
+                    for (int c = 0; c < pro.n_ch; ++c) {
+                        const float y = pro.rgb[row * pro.n_ch + c];
+                        dyv[c] = f16_round(pro.g_rgb[row * pro.n_ch + c]) * (1.0f - y) * y;
+                    }
+                    v0 = make_int4((int)pack2(dyv[0], dyv[1]), (int)pack2(dyv[2], dyv[3]), 0, 0);
+                    v1 = make_int4(0, 0, 0, 0);
+                } else {
+                    const float sg = fminf(fmaxf(pro.sigma[row], 3.0590232050182579e-07f), 3269017.3724721107f);   // exp(-15), exp(15)
+                    const __half d0 = __float2half_rn(pro.g_sigma[row] * sg);
+                    const int4* src = reinterpret_cast<const int4*>(pro.dcin + row * 32 + 16);
+                    const int4 a = __ldg(src), b = __ldg(src + 1);
+                    const uint32_t w[8] = {(uint32_t)a.x, (uint32_t)a.y, (uint32_t)a.z, (uint32_t)a.w, (uint32_t)b.x, (uint32_t)b.y, (uint32_t)b.z, (uint32_t)b.w};
+                    uint32_t o[8];
+                    o[0] = (uint32_t)__half_as_ushort(d0) | (w[0] << 16);
+#pragma unroll
+                    for (int e = 1; e < 8; ++e) o[e] = (w[e - 1] >> 16) | (w[e] << 16);
+                    v0 = make_int4((int)o[0], (int)o[1], (int)o[2], (int)o[3]);
+                    v1 = make_int4((int)o[4], (int)o[5], (int)o[6], (int)o[7]);
+                }
+                const uint32_t r8[8] = {(uint32_t)v0.x, (uint32_t)v0.y, (uint32_t)v0.z, (uint32_t)v0.w,
+                                        (uint32_t)v1.x, (uint32_t)v1.y, (uint32_t)v1.z, (uint32_t)v1.w};
+                tmem_st8(a_t, r8);
+                *reinterpret_cast<int4*>(g_tile + 0 * 2048 + r_in_tile * 16) = v0;
+                *reinterpret_cast<int4*>(g_tile + 1 * 2048 + r_in_tile * 16) = v1;
+                tc_wait_st();
+                fence_proxy_async_smem();
+                tc_fence_before();
+                mbar_arrive(&a_ready[s]);
+            }
+            // ---- E_k, k = 1 .. S-1: g = D * relu'(h of stage k-1) -> TMEM A + G tile
+            for (int k = 1; k < S; ++k) {
+                mbar_wait(&d_full[s], pd);
+                pd ^= 1;
+                tc_fence_after();
+                const uint32_t ip = i + (uint32_t)k - 1;                                // stage whose activation tile masks this gradient
+                mbar_wait(&h_full[2 * s + (ip & 1u)], (ip >> 1) & 1u);                 // complete long ago; orders our reads after the TMA writes
+                const uint8_t* hrow = hring + ((size_t)s * 2 + (ip & 1u)) * kGBytes;
+                int4 hv[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) hv[c] = *reinterpret_cast<const int4*>(hrow + sw_off((uint32_t)r_in_tile, (uint32_t)c, 128));
+                const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t acc[32];
+                    tmem_ld32(d_t + h * 32, acc);
+                    tc_wait_ld();
+                    uint32_t p[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const uint32_t hw = reinterpret_cast<const uint32_t*>(hv)[h * 16 + e];
+                        const unsigned m = __hgt2_mask(*reinterpret_cast<const __half2*>(&hw), zero2);    // 0xffff per half where h > 0
+                        p[e] = pack2(__uint_as_float(acc[2 * e]), __uint_as_float(acc[2 * e + 1])) & m;
+                    }
+                    tmem_st16(a_t + h * 16, p);
+#pragma unroll
+                    for (int v = 0; v < 4; ++v)
+                        *reinterpret_cast<int4*>(g_tile + (h * 4 + v) * 2048 + r_in_tile * 16) =
+                            make_int4((int)p[4 * v], (int)p[4 * v + 1], (int)p[4 * v + 2], (int)p[4 * v + 3]);
+                }
+                tc_wait_st();
+                fence_proxy_async_smem();
+                tc_fence_before();
+                mbar_arrive(&a_ready[s]);
+            }
+            // ---- E_S: dx
+            mbar_wait(&d_full[s], pd);
+            pd ^= 1;
+            tc_fence_after();
+            if (grad_inputs) {
+#pragma unroll
+                for (int c = 0; c < in_dim / 16; ++c) {
+                    uint32_t acc[16];
+                    tmem_ld16(d_t + c * 16, acc);
+                    tc_wait_ld();
+                    uint32_t p[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) p[e] = pack2(__uint_as_float(acc[2 * e]), __uint_as_float(acc[2 * e + 1]));
+                    int4* dst = reinterpret_cast<int4*>(grad_inputs + row * in_dim + c * 16);
+                    dst[0] = make_int4((int)p[0], (int)p[1], (int)p[2], (int)p[3]);
+                    dst[1] = make_int4((int)p[4], (int)p[5], (int)p[6], (int)p[7]);
+                }
+            }
+            tc_fence_before();
+            i += (uint32_t)S;
+        }
+
+        // ---- flush the weight-gradient accumulators (slot 0's four warps; M = 64 -> lanes 0..15 of each quarter)
+        if (s == 0 && my_tiles > 0) {
+            mbar_wait(flush_bar, 0);
+            tc_fence_after();
+            const int m = q * 16 + lane;
+            const uint32_t base = lane_sel;
+            float* dW0 = dW;
+            float* dWh = dW + kW * in_dim;
+            float* dWl = dWh + (size_t)n_hidden_mm * kW * kW;
+            {
+                uint32_t acc[16];
+                tmem_ld16(acc_last + base, acc);
+                tc_wait_ld();
+                if (lane < 16)
+#pragma unroll
+                    for (int nn = 0; nn < 16; ++nn) atomicAdd(dWl + nn * kW + m, __uint_as_float(acc[nn]));
+            }
+            for (int jj = 0; jj < n_hidden_mm; ++jj)
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t acc[16];
+                    tmem_ld16(acc_hid + jj * 64 + c * 16 + base, acc);
+                    tc_wait_ld();
+                    if (lane < 16) {
+                        float* dst = dWh + (size_t)jj * kW * kW + (size_t)m * kW + c * 16;
+#pragma unroll
+                        for (int v = 0; v < 4; ++v)
+                            red_add_v4(dst + 4 * v, __uint_as_float(acc[4 * v]), __uint_as_float(acc[4 * v + 1]), __uint_as_float(acc[4 * v + 2]),
+                                       __uint_as_float(acc[4 * v + 3]));
+                    }
+                }
+            for (int c = 0; c < in_dim / 16; ++c) {
+                uint32_t acc[16];
+                tmem_ld16(acc_0 + c * 16 + base, acc);
+                tc_wait_ld();
+                if (lane < 16) {
+                    float* dst = dW0 + (size_t)m * in_dim + c * 16;
+#pragma unroll
+                    for (int v = 0; v < 4; ++v)
+                        red_add_v4(dst + 4 * v, __uint_as_float(acc[4 * v]), __uint_as_float(acc[4 * v + 1]), __uint_as_float(acc[4 * v + 2]),
+                                   __uint_as_float(acc[4 * v + 3]));
+                }
+            }
+            tc_fence_before();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem0, kCols);
+}
+
+// ---- host: tensor maps (driver entry point resolved through the runtime; no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+// fp16 row-major [rows, cols] matrix, box = [box_rows, cols]; swizzle = the row size in bytes (32 / 64 / 128)
+static bool make_tmap_rows(TmaDesc* out, const void* base, uint64_t rows, uint32_t cols, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn || (reinterpret_cast<uintptr_t>(base) & 15u)) return false;
+    const uint32_t row_bytes = cols * 2;
+    const CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    if (row_bytes != 128 && row_bytes != 64 && row_bytes != 32) return false;
+    const cuuint64_t gdim[2] = {cols, rows};
+    const cuuint64_t gstride[1] = {row_bytes};
+    const cuuint32_t box[2] = {cols, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    static_assert(sizeof(CUtensorMap) == sizeof(TmaDesc), "CUtensorMap size");
+    return fn(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int g_bwd_tma = -1;    // -1: read ENERF_TC_BWD_TMA (default on); 0: k_tc_bwd; 1: k_tc_bwd_tma
+static int g_bwd_slots = 0;   // 0: read ENERF_TC_BWD_SLOTS (default 3)
+void tc_set_bwd_tma(int on) { g_bwd_tma = on ? 1 : 0; }
+
+template <int NSLOTS, int PRO, int IN_DIM>
+static int launch_bwd_tma_n(const TmaDesc& th, const TmaDesc& tx, const __half* grad, const __half* W, __half* grad_inputs, float* dW, uint32_t B,
+                            int n_hidden_mm, ProArgs pro, cudaStream_t st, const char* name) {
+    size_t smem = 1024 + (size_t)NSLOTS * 3 * kGBytes + (size_t)IN_DIM * 128 + (size_t)n_hidden_mm * 8192 + 2048 + (4 * NSLOTS + 1) * 8 + 16;
+    if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: it allocates all 512 TMEM columns
+    if (smem > 227 * 1024) { set_error("%s: network too deep for the tcgen05 path", name); return -2; }
+    static size_t configured = 0;
+    if (smem > configured) {
+        ENERF_CUDA(cudaFuncSetAttribute(k_tc_bwd_tma<NSLOTS, PRO, IN_DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
+        configured = smem;
+    }
+    const uint32_t n_tiles = B / kTile;
+    const uint32_t grid = n_tiles < (uint32_t)kNumSM ? n_tiles : (uint32_t)kNumSM;
+    k_tc_bwd_tma<NSLOTS, PRO, IN_DIM><<<grid, 32 + NSLOTS * 128, smem, st>>>(th, tx, grad, W, grad_inputs, dW, n_tiles, B, n_hidden_mm, pro);
+    ENERF_CHECK_LAUNCH(name);
+    return 0;
+}
+
+// returns 1 when the TMA kernel is not applicable (caller falls back to k_tc_bwd), 0 on success, <0 / CUDA error otherwise
+template <int PRO>
+static int launch_bwd_tma(const __half* grad, const __half* x, const __half* W, const __half* fwd_buf, __half* grad_inputs, float* dW, uint32_t B,
+                          int in_dim, int n_hidden_mm, ProArgs pro, cudaStream_t st, const char* name) {
+    if (g_bwd_tma < 0) {
+        const char* e = getenv("ENERF_TC_BWD_TMA");
+        g_bwd_tma = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (g_bwd_slots == 0) {
+        const char* e = getenv("ENERF_TC_BWD_SLOTS");
+        g_bwd_slots = e ? atoi(e) : 3;
+        if (g_bwd_slots < 2 || g_bwd_slots > 4) g_bwd_slots = 3;
+    }
+    if (!g_bwd_tma || (in_dim != 32 && in_dim != 64) || (uint64_t)(n_hidden_mm + 1) * B >= (1ull << 31)) return 1;
+    TmaDesc th, tx;
+    if (!make_tmap_rows(&th, fwd_buf, (uint64_t)(n_hidden_mm + 1) * B, 64, kTile) || !make_tmap_rows(&tx, x, B, (uint32_t)in_dim, kTile)) return 1;
+    // TMEM: NSLOTS*96 + 16 + 64*n_hidden_mm + in_dim columns <= 512
+    int slots = g_bwd_slots;
+    while (slots > 2 && slots * kSlotCols + 16 + 64 * n_hidden_mm + in_dim > 512) --slots;
+    if (slots * kSlotCols + 16 + 64 * n_hidden_mm + in_dim > 512) return 1;
+#define ENERF_BWD_TMA_CASE(NS, ID) \
+    if (slots == NS && in_dim == ID) return launch_bwd_tma_n<NS, PRO, ID>(th, tx, grad, W, grad_inputs, dW, B, n_hidden_mm, pro, st, name);
+    ENERF_BWD_TMA_CASE(2, 32) ENERF_BWD_TMA_CASE(3, 32) ENERF_BWD_TMA_CASE(4, 32)
+    ENERF_BWD_TMA_CASE(2, 64) ENERF_BWD_TMA_CASE(3, 64) ENERF_BWD_TMA_CASE(4, 64)
+#undef ENERF_BWD_TMA_CASE
+    return 1;
+}
+
 int tc_backward(const __half* grad, const __half* x, const __half* W, const __half* fwd_buf, __half* bwd_buf, __half* grad_inputs, float* dW,
                 uint32_t B, int in_dim, int n_hidden_mm, cudaStream_t st) {
     ProArgs none = {nullptr, nullptr, 0, nullptr, nullptr, nullptr};
+    if (!bwd_buf) {
+        const int rc = launch_bwd_tma<0>(grad, x, W, fwd_buf, grad_inputs, dW, B, in_dim, n_hidden_mm, none, st, "ffmlp_backward");
+        if (rc != 1) return rc;
+    }
     return launch_bwd<0>(grad, x, W, fwd_buf, bwd_buf, grad_inputs, dW, B, in_dim, n_hidden_mm, none, st, "ffmlp_backward");
 }
 int tc_backward_rgb(const float* g_rgb, const float* rgb, int n_ch, const __half* cin, const __half* W, const __half* fwd_buf, __half* dcin, float* dW,
                     uint32_t B, int n_hidden_mm, cudaStream_t st) {
     ProArgs p = {g_rgb, rgb, n_ch, nullptr, nullptr, nullptr};
+    {
+        const int rc = launch_bwd_tma<1>(nullptr, cin, W, fwd_buf, dcin, dW, B, 32, n_hidden_mm, p, st, "field_color_backward");
+        if (rc != 1) return rc;
+    }
     return launch_bwd<1>(nullptr, cin, W, fwd_buf, nullptr, dcin, dW, B, 32, n_hidden_mm, p, st, "field_color_backward");
 }
 int tc_backward_sigma(const float* g_sigma, const float* sigma, const __half* dcin, const __half* feat, const __half* W, const __half* fwd_buf,
                       __half* dfeat, float* dW, uint32_t B, int n_hidden_mm, cudaStream_t st) {
     ProArgs p = {nullptr, nullptr, 0, g_sigma, sigma, dcin};
+    {
+        const int rc = launch_bwd_tma<2>(nullptr, feat, W, fwd_buf, dfeat, dW, B, 32, n_hidden_mm, p, st, "field_sigma_backward");
+        if (rc != 1) return rc;
+    }
     return launch_bwd<2>(nullptr, feat, W, fwd_buf, nullptr, dfeat, dW, B, 32, n_hidden_mm, p, st, "field_sigma_backward");
 }
 

@@ -74,6 +74,37 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---- TMA (cp.async.bulk.tensor) -------------------------------------------------------------------
+// expect `bytes` of async-proxy writes on the barrier and count one arrival (the issuing thread's)
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 2-D tiled load global -> shared; c0 = element index in the row, c1 = row index; completion is signalled on `bar`
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* tmap, int32_t c0, int32_t c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+// 2-D tiled store shared -> global (bulk async group of the issuing thread)
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t smem_src, int32_t c0, int32_t c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the newest N store groups of this thread have finished READING shared memory
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+// named barrier over `nthreads` threads (ids 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // ---- descriptors --------------------------------------------------------------------------------
 // shared-memory matrix descriptor, SWIZZLE_NONE; lbo/sbo in bytes (see the layout note on top)
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -83,6 +114,26 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
     d |= (uint64_t)1 << 46;   // descriptor version for sm_100
     return d;                 // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (0)
+}
+// shared-memory matrix descriptor for a TMA-swizzled tile (rows of `swizzle_bytes` = 128 / 64 / 32 bytes, densely
+// packed, 8-row swizzle atoms; the tile base must be aligned to 8*swizzle_bytes).  Serves both readings of such a
+// tile: K-major (rows = M/N, the row bytes = K) and MN-major (rows = K, the row bytes = M/N); in both the stride
+// between 8-row atoms is SBO = 8*swizzle_bytes and LBO is not used (one atom wide).
+__device__ __forceinline__ uint64_t smem_desc_sw(uint32_t saddr, uint32_t swizzle_bytes) {
+    const uint64_t layout = (swizzle_bytes == 128) ? 2ull : (swizzle_bytes == 64) ? 4ull : 6ull;
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;                                       // LBO (ignored for one-atom-wide swizzled tiles)
+    d |= (uint64_t)(((8u * swizzle_bytes) >> 4) & 0x3FFFu) << 32;  // SBO
+    d |= (uint64_t)1 << 46;                                       // descriptor version for sm_100
+    d |= layout << 61;
+    return d;
+}
+// byte offset of 16-byte chunk `c` of row `r` inside a TMA-swizzled tile with dense rows of `swizzle_bytes`:
+// Swizzle<B,4,3> XORs address bits [7,7+B) into bits [4,4+B), B = log2(swizzle_bytes/16)
+__device__ __forceinline__ uint32_t sw_off(uint32_t r, uint32_t c, uint32_t swizzle_bytes) {
+    const uint32_t lin = r * swizzle_bytes + (c << 4);
+    return lin ^ (((lin >> 7) & (swizzle_bytes / 16u - 1u)) << 4);
 }
 // instruction descriptor for kind::f16: fp16 A/B, fp32 accumulate
 __host__ __device__ constexpr uint32_t idesc_f16(uint32_t M, uint32_t N, bool a_mn_major, bool b_mn_major) {

@@ -175,8 +175,9 @@ int enerf_ffmlp_backward(const uint16_t* grad, const uint16_t* inputs, const uin
  * are fused into the backward kernel here, so these only validate their argument. */
 int enerf_allocate_splitk(uint64_t size);
 /* Kernel-family selector (no reference counterpart): 0 = automatic — the tcgen05/TMEM kernels for
- * 64-wide ReLU networks with input_dim <= 64, the mma.sync kernels otherwise; 1 = always the
- * generic mma.sync kernels (used by the parity tests to cross-check the two families). */
+ * 64-wide ReLU networks with input_dim <= 64 (backward operands staged by TMA), the mma.sync kernels
+ * otherwise; 1 = always the generic mma.sync kernels; 2 = tcgen05 kernels with per-thread operand loads
+ * instead of TMA (used by the parity tests to cross-check the families). */
 int enerf_ffmlp_set_path(int path);
 /* 1 when forward/inference/backward of this shape run on the tcgen05 kernels (backward_buffer may
  * then be NULL), else 0.  Not a compute call: usable without a GPU. */
