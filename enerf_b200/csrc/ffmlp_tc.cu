@@ -108,8 +108,8 @@ k_tc_fwd(const __half* __restrict__ in, const __half* __restrict__ W, __half* __
     const uint32_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     if (warp == 0) {
-        // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
+        {
             // Serve whichever slot has its A operand ready (no fixed slot order: a slow epilogue must not
             // stall the other tiles in flight).
             uint32_t pa[NSLOTS], stage[NSLOTS], left[NSLOTS];
@@ -121,23 +121,34 @@ k_tc_fwd(const __half* __restrict__ in, const __half* __restrict__ W, __half* __
                 left[s] = (my_tiles > (uint32_t)s) ? (my_tiles - s + NSLOTS - 1) / NSLOTS : 0;   // tiles this slot will process
                 remaining += left[s] * S;
             }
+            const uint32_t tm = __shfl_sync(0xffffffffu, tmem0, 0);
             const uint32_t idesc64 = idesc_f16(kTile, 64, false, false), idesc16 = idesc_f16(kTile, 16, false, false);
+            const uint32_t w0b = smem_u32(w0s), whb = smem_u32(whs), wlb = smem_u32(wls);
             while (remaining > 0) {
 #pragma unroll
                 for (int s = 0; s < NSLOTS; ++s) {
-                    if (left[s] == 0 || !mbar_test(&a_ready[s], pa[s])) continue;
+                    if (left[s] == 0) continue;
+                    if (!__all_sync(0xffffffffu, mbar_test(&a_ready[s], pa[s]))) continue;
                     pa[s] ^= 1;
                     tc_fence_after();
                     const int i = (int)stage[s];
-                    const int K = (i == 0) ? in_dim : kW;
                     const bool last = (i == S - 1);
-                    const uint32_t lbo = last ? 16 * 16 : kW * 16;
-                    const uint8_t* wb = (i == 0) ? w0s : (last ? wls : whs + (i - 1) * 8192);
-                    const uint32_t wbase = smem_u32(wb);
-                    const uint32_t d_t = tmem0 + s * kSlotCols, a_t = d_t + 64;
-                    for (int k = 0; k < K / 16; ++k)
-                        mma_ts(d_t, a_t + k * 8, smem_desc(wbase + k * 2 * lbo, lbo, 128), last ? idesc16 : idesc64, k > 0);
-                    tc_commit(&d_full[s]);
+                    const uint32_t d_t = tm + s * kSlotCols, a_t = d_t + 64;
+                    if (elect_one()) {
+                        if (i == 0) {
+#pragma unroll
+                            for (int k = 0; k < in_dim / 16; ++k) mma_ts(d_t, a_t + k * 8, smem_desc(w0b + k * 2 * (kW * 16), kW * 16, 128), idesc64, k > 0);
+                        } else if (!last) {
+                            const uint32_t wb = whb + (uint32_t)(i - 1) * 8192u;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) mma_ts(d_t, a_t + k * 8, smem_desc(wb + k * 2 * (kW * 16), kW * 16, 128), idesc64, k > 0);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) mma_ts(d_t, a_t + k * 8, smem_desc(wlb + k * 2 * (16 * 16), 16 * 16, 128), idesc16, k > 0);
+                        }
+                        tc_commit(&d_full[s]);
+                    }
+                    __syncwarp();
                     --remaining;
                     if (++stage[s] == (uint32_t)S) {
                         stage[s] = 0;
@@ -670,17 +681,17 @@ static int launch_bwd(const __half* grad, const __half* x, const __half* W, cons
 // data pipe sat at 75-80 % in ncu) and copy it into the canonical operand tile.  Here the MMA thread
 // issues ONE cp.async.bulk.tensor per stage: the [128 x 64] fp16 tile of forward_buffer (or the
 // [128 x in_dim] input tile for the last stage) lands in shared memory in the 128-byte (64-byte)
-// TMA swizzle, which tcgen05.mma reads directly as the MN-major wgrad operand; a two-deep ring per
-// slot lets the load of stage i+1 fly while stage i computes.  Epilogue threads only read their row's
+// TMA swizzle, which tcgen05.mma reads directly as the MN-major wgrad operand; a RING-deep ring per
+// slot keeps the loads of the next RING-1 stages in flight while stage i computes.  Epilogue threads only read their row's
 // ReLU mask from that tile (8 conflict-free LDS.128) and never touch global memory for activations.
-//   ring protocol (per slot, stage counter i runs across tiles): load(i) -> buffer i&1, signalled on
-//   h_full[slot][i&1]; buffer i&1 is free again when E_{i+1} has read its mask (a_ready of stage i+1)
-//   and wgrad(i) has completed (d_full of stage i, which E_{i+1} waited for) -> the MMA thread issues
-//   load(i+2) right after it observes a_ready(i+1).
+//   ring protocol (per slot, stage counter i runs across tiles): load(i) -> buffer i%RING, signalled on
+//   h_full[slot][i%RING]; the buffer is free again when E_{i+1} has read its mask (a_ready of stage i+1)
+//   and wgrad(i) has completed (d_full of stage i, which E_{i+1} waited for) -> the issuing warp launches
+//   load(i+RING) right after it observes a_ready(i+1).
 // ================================================================================================
 struct alignas(64) TmaDesc { uint8_t bytes[128]; };     // CUtensorMap (opaque here; encoded on the host)
 
-template <int NSLOTS, int PRO, int IN_DIM>
+template <int NSLOTS, int RING, int PRO, int IN_DIM>
 __global__ void __launch_bounds__(32 + NSLOTS * 128, 1)
 k_tc_bwd_tma(const __grid_constant__ TmaDesc tm_h, const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ grad,
              const __half* __restrict__ W, __half* __restrict__ grad_inputs, float* __restrict__ dW, uint32_t n_tiles, uint32_t B,
@@ -689,15 +700,15 @@ k_tc_bwd_tma(const __grid_constant__ TmaDesc tm_h, const __grid_constant__ TmaDe
     constexpr uint32_t kXSw = IN_DIM * 2;                  // swizzle bytes of the input tile (row bytes): 64 or 128
     extern __shared__ uint8_t smem_dyn[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-    uint8_t* hring = smem;                                          // NSLOTS x 2 x 16 KB, 1024-byte aligned (TMA swizzle atoms)
-    uint8_t* gtiles = hring + (size_t)NSLOTS * 2 * kGBytes;         // NSLOTS x 16 KB, canonical [chunk][row][16 B]
+    uint8_t* hring = smem;                                          // NSLOTS x RING x 16 KB, 1024-byte aligned (TMA swizzle atoms)
+    uint8_t* gtiles = hring + (size_t)NSLOTS * RING * kGBytes;         // NSLOTS x 16 KB, canonical [chunk][row][16 B]
     uint8_t* w0s = gtiles + (size_t)NSLOTS * kGBytes;               // [in_dim/8][64][16 B]   (forward layout)
     uint8_t* whs = w0s + in_dim * 128;                              // n_hidden_mm x [8][64][16 B]
     uint8_t* wls = whs + n_hidden_mm * 8192;                        // [8][16][16 B]
     uint64_t* a_ready = reinterpret_cast<uint64_t*>(wls + 2048);
     uint64_t* d_full = a_ready + NSLOTS;
-    uint64_t* h_full = d_full + NSLOTS;                             // [NSLOTS][2]
-    uint64_t* flush_bar = h_full + 2 * NSLOTS;
+    uint64_t* h_full = d_full + NSLOTS;                             // [NSLOTS][RING]
+    uint64_t* flush_bar = h_full + RING * NSLOTS;
     uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(flush_bar + 1);
 
     const int tid = threadIdx.x, nthreads = blockDim.x;
@@ -711,8 +722,7 @@ k_tc_bwd_tma(const __grid_constant__ TmaDesc tm_h, const __grid_constant__ TmaDe
         for (int s = 0; s < NSLOTS; ++s) {
             mbar_init(&a_ready[s], 128);
             mbar_init(&d_full[s], 1);
-            mbar_init(&h_full[2 * s], 1);
-            mbar_init(&h_full[2 * s + 1], 1);
+            for (int r = 0; r < RING; ++r) mbar_init(&h_full[RING * s + r], 1);
         }
         mbar_init(flush_bar, 1);
         mbar_fence_init();
@@ -733,95 +743,113 @@ k_tc_bwd_tma(const __grid_constant__ TmaDesc tm_h, const __grid_constant__ TmaDe
     const uint32_t acc_0 = acc_hid + n_hidden_mm * 64;
 
     if (warp == 0) {
-        if (lane == 0) {
-            uint32_t pa[NSLOTS], cons[NSLOTS], total[NSLOTS], issued[NSLOTS], phase[NSLOTS];
-            uint32_t remaining = 0, started = 0;
-            // load i of slot s: stage k = i % S of the slot's (i / S)-th tile
-            auto issue_load = [&](int s) {
-                const uint32_t i = issued[s]++;
-                const uint32_t tl = i / (uint32_t)S, k = i - tl * (uint32_t)S;
-                const uint32_t tile = blockIdx.x + ((uint32_t)s + tl * NSLOTS) * gridDim.x;
-                const uint32_t dst = smem_u32(hring + ((size_t)s * 2 + (i & 1u)) * kGBytes);
-                uint64_t* bar = &h_full[2 * s + (i & 1u)];
-                if (k + 1 < (uint32_t)S) {
-                    mbar_arrive_expect_tx(bar, kGBytes);
-                    tma_load_2d(dst, &tm_h, 0, (int32_t)((uint32_t)(n_hidden_mm - (int)k) * B + tile * kTile), bar);
-                } else {
-                    mbar_arrive_expect_tx(bar, kTile * in_dim * 2);
-                    tma_load_2d(dst, &tm_x, 0, (int32_t)(tile * kTile), bar);
-                }
-            };
+        // MMA / TMA issuer: warp-uniform control flow, one elected lane issues (see elect_one()).
+        uint32_t pa[NSLOTS], cons[NSLOTS], total[NSLOTS], issued[NSLOTS], phase[NSLOTS];
+        uint32_t remaining = 0, started = 0;
+        const uint32_t tm = __shfl_sync(0xffffffffu, tmem0, 0);
+        const uint32_t hring_b = smem_u32(hring), gt_b = smem_u32(gtiles), w0b = smem_u32(w0s), whb = smem_u32(whs), wlb = smem_u32(wls);
+        const uint32_t acc_last_u = tm + NSLOTS * kSlotCols, acc_hid_u = acc_last_u + 16, acc_0_u = acc_hid_u + n_hidden_mm * 64;
+#pragma unroll
+        for (int s = 0; s < NSLOTS; ++s) {
+            pa[s] = 0;
+            cons[s] = 0;
+            phase[s] = 0;
+            issued[s] = 0;
+            const uint32_t left = (my_tiles > (uint32_t)s) ? (my_tiles - s + NSLOTS - 1) / NSLOTS : 0;
+            total[s] = left * S;
+            remaining += total[s];
+        }
+        // load i of slot s: stage k = i % S of the slot's (i / S)-th tile   (called by the elected lane only)
+        auto issue_load = [&](int s, uint32_t i) {
+            const uint32_t tl = i / (uint32_t)S, k = i - tl * (uint32_t)S;
+            const uint32_t tile = blockIdx.x + ((uint32_t)s + tl * NSLOTS) * gridDim.x;
+            const uint32_t dst = hring_b + ((uint32_t)s * RING + (i % RING)) * kGBytes;
+            uint64_t* bar = &h_full[RING * s + (i % RING)];
+            if (k + 1 < (uint32_t)S) {
+                mbar_arrive_expect_tx(bar, kGBytes);
+                tma_load_2d(dst, &tm_h, 0, (int32_t)((uint32_t)(n_hidden_mm - (int)k) * B + tile * kTile), bar);
+            } else {
+                mbar_arrive_expect_tx(bar, kTile * in_dim * 2);
+                tma_load_2d(dst, &tm_x, 0, (int32_t)(tile * kTile), bar);
+            }
+        };
+#pragma unroll
+        for (int s = 0; s < NSLOTS; ++s) {
+            const uint32_t pre = total[s] < (uint32_t)RING ? total[s] : (uint32_t)RING;
+            if (elect_one())
+                for (uint32_t i = 0; i < pre; ++i) issue_load(s, i);
+            __syncwarp();
+            issued[s] = pre;
+        }
+        while (remaining > 0) {
 #pragma unroll
             for (int s = 0; s < NSLOTS; ++s) {
-                pa[s] = 0;
-                cons[s] = 0;
-                phase[s] = 0;
-                issued[s] = 0;
-                const uint32_t left = (my_tiles > (uint32_t)s) ? (my_tiles - s + NSLOTS - 1) / NSLOTS : 0;
-                total[s] = left * S;
-                remaining += total[s];
-                if (total[s] > 0) issue_load(s);
-                if (total[s] > 1) issue_load(s);
-            }
-            while (remaining > 0) {
-#pragma unroll
-                for (int s = 0; s < NSLOTS; ++s) {
-                    if (cons[s] == total[s]) continue;
-                    const uint32_t i = cons[s];
-                    const int k = (int)(i % (uint32_t)S);
-                    const uint32_t d_t = tmem0 + s * kSlotCols, a_t = d_t + 64;
-                    const uint32_t g_s = smem_u32(gtiles + (size_t)s * kGBytes);
-                    const uint32_t h_s = smem_u32(hring + ((size_t)s * 2 + (i & 1u)) * kGBytes);
-                    if (phase[s] == 0) {
-                        if (!mbar_test(&a_ready[s], pa[s])) continue;
-                        pa[s] ^= 1;
-                        tc_fence_after();
-                        // E_i is done: it has read its ReLU mask from the buffer of stage i-1, whose wgrad completed before E_i started
-                        if (i >= 1 && issued[s] < total[s]) issue_load(s);
+                if (cons[s] == total[s]) continue;
+                const uint32_t i = cons[s];
+                const int k = (int)(i % (uint32_t)S);
+                const uint32_t d_t = tm + s * kSlotCols, a_t = d_t + 64;
+                const uint32_t g_s = gt_b + (uint32_t)s * kGBytes;
+                const uint32_t h_s = hring_b + ((uint32_t)s * RING + (i % RING)) * kGBytes;
+                if (phase[s] == 0) {
+                    if (!__all_sync(0xffffffffu, mbar_test(&a_ready[s], pa[s]))) continue;
+                    pa[s] ^= 1;
+                    tc_fence_after();
+                    // E_i is done: it has read its ReLU mask from the buffer of stage i-1, whose wgrad completed before E_i started,
+                    // so that buffer can take load i-1+RING
+                    const bool do_load = (i >= 1 && issued[s] < total[s]);
+                    if (elect_one()) {
+                        if (do_load) issue_load(s, issued[s]);
                         if (k == 0) {
                             // dgrad through the output layer: D[128x64] = dy[128x16] . W_last[16x64]
-                            mma_ts(d_t, a_t, smem_desc(smem_u32(wls), 128, 16 * 16), idesc_f16(kTile, 64, false, true), false);
+                            mma_ts(d_t, a_t, smem_desc(wlb, 128, 16 * 16), idesc_f16(kTile, 64, false, true), false);
                         } else if (k <= n_hidden_mm) {
-                            const uint32_t wj = smem_u32(whs + (n_hidden_mm - k) * 8192);
+                            const uint32_t wj = whb + (uint32_t)(n_hidden_mm - k) * 8192u;
+#pragma unroll
                             for (int ks = 0; ks < 4; ++ks)
                                 mma_ts(d_t, a_t + ks * 8, smem_desc(wj + ks * 256, 128, 64 * 16), idesc_f16(kTile, 64, false, true), ks > 0);
                         } else {
-                            // dx = g_0 . W_0 — issued even when the caller does not ask for grad_inputs (4 small MMAs): a
-                            // `grad_inputs != nullptr` guard here gets if-converted by ptxas 12.9 into predicated UTCHMMAs whose
-                            // descriptor R2UR for the second K step is skipped (observed: K rows 16..31 read the rows 0..15 tile).
+                            // dx = g_0 . W_0 — issued even when the caller does not ask for grad_inputs (4 small MMAs)
+#pragma unroll
                             for (int ks = 0; ks < 4; ++ks)
-                                mma_ts(d_t, a_t + ks * 8, smem_desc(smem_u32(w0s) + ks * 256, 128, 64 * 16),
-                                       idesc_f16(kTile, (uint32_t)in_dim, false, true), ks > 0);
+                                mma_ts(d_t, a_t + ks * 8, smem_desc(w0b + ks * 256, 128, 64 * 16), idesc_f16(kTile, (uint32_t)in_dim, false, true), ks > 0);
                         }
-                        phase[s] = 1;
                     }
-                    // wgrad needs the activation tile of this stage
-                    if (!mbar_test(&h_full[2 * s + (i & 1u)], (i >> 1) & 1u)) continue;
-                    tc_fence_after();
-                    const bool acc = (started >> k) & 1u;
-                    started |= 1u << k;
+                    __syncwarp();
+                    if (do_load) ++issued[s];
+                    phase[s] = 1;
+                }
+                // wgrad needs the activation tile of this stage
+                if (!__all_sync(0xffffffffu, mbar_test(&h_full[RING * s + (i % RING)], (i / RING) & 1u))) continue;
+                tc_fence_after();
+                const bool acc = (started >> k) & 1u;
+                started |= 1u << k;
+                if (elect_one()) {
                     if (k == 0) {
                         // dW_last^T[64x16] += h_n^T[64x128] . dy[128x16]   (A = activation tile, B = dy tile in the G buffer)
+#pragma unroll
                         for (int ks = 0; ks < 8; ++ks)
-                            mma_ss(acc_last, smem_desc_sw(h_s + ks * 2048, 128), smem_desc(g_s + ks * 256, 128, 2048),
-                                   idesc_f16(64, 16, true, true), acc || ks > 0);
+                            mma_ss(acc_last_u, smem_desc_sw(h_s + ks * 2048, 128), smem_desc(g_s + ks * 256, 128, 2048), idesc_f16(64, 16, true, true), acc || ks > 0);
                     } else if (k <= n_hidden_mm) {
+                        const uint32_t accj = acc_hid_u + (uint32_t)(n_hidden_mm - k) * 64u;
+#pragma unroll
                         for (int ks = 0; ks < 8; ++ks)
-                            mma_ss(acc_hid + (n_hidden_mm - k) * 64, smem_desc(g_s + ks * 256, 128, 2048), smem_desc_sw(h_s + ks * 2048, 128),
-                                   idesc_f16(64, 64, true, true), acc || ks > 0);
+                            mma_ss(accj, smem_desc(g_s + ks * 256, 128, 2048), smem_desc_sw(h_s + ks * 2048, 128), idesc_f16(64, 64, true, true), acc || ks > 0);
                     } else {
+#pragma unroll
                         for (int ks = 0; ks < 8; ++ks)
-                            mma_ss(acc_0, smem_desc(g_s + ks * 256, 128, 2048), smem_desc_sw(h_s + ks * 16 * kXSw, kXSw),
-                                   idesc_f16(64, (uint32_t)in_dim, true, true), acc || ks > 0);
+                            mma_ss(acc_0_u, smem_desc(g_s + ks * 256, 128, 2048), smem_desc_sw(h_s + ks * 16 * kXSw, kXSw), idesc_f16(64, (uint32_t)in_dim, true, true),
+                                   acc || ks > 0);
                     }
                     tc_commit(&d_full[s]);
-                    phase[s] = 0;
-                    ++cons[s];
-                    --remaining;
                 }
+                __syncwarp();
+                phase[s] = 0;
+                ++cons[s];
+                --remaining;
             }
-            tc_commit(flush_bar);
         }
+        if (elect_one()) tc_commit(flush_bar);
+        __syncwarp();
     } else {
         const int s = (warp - 1) >> 2;
         const int q = warp & 3;
@@ -879,8 +907,8 @@ k_tc_bwd_tma(const __grid_constant__ TmaDesc tm_h, const __grid_constant__ TmaDe
                 pd ^= 1;
                 tc_fence_after();
                 const uint32_t ip = i + (uint32_t)k - 1;                                // stage whose activation tile masks this gradient
-                mbar_wait(&h_full[2 * s + (ip & 1u)], (ip >> 1) & 1u);                 // complete long ago; orders our reads after the TMA writes
-                const uint8_t* hrow = hring + ((size_t)s * 2 + (ip & 1u)) * kGBytes;
+                mbar_wait(&h_full[RING * s + (ip % RING)], (ip / RING) & 1u);          // complete long ago; orders our reads after the TMA writes
+                const uint8_t* hrow = hring + ((size_t)s * RING + (ip % RING)) * kGBytes;
                 int4 hv[8];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) hv[c] = *reinterpret_cast<const int4*>(hrow + sw_off((uint32_t)r_in_tile, (uint32_t)c, 128));
@@ -1013,22 +1041,23 @@ static bool make_tmap_rows(TmaDesc* out, const void* base, uint64_t rows, uint32
 
 static int g_bwd_tma = -1;    // -1: read ENERF_TC_BWD_TMA (default on); 0: k_tc_bwd; 1: k_tc_bwd_tma
 static int g_bwd_slots = 0;   // 0: read ENERF_TC_BWD_SLOTS (default 3)
+static int g_bwd_ring = 0;    // 0: read ENERF_TC_BWD_RING (default 2)
 void tc_set_bwd_tma(int on) { g_bwd_tma = on ? 1 : 0; }
 
-template <int NSLOTS, int PRO, int IN_DIM>
+template <int NSLOTS, int RING, int PRO, int IN_DIM>
 static int launch_bwd_tma_n(const TmaDesc& th, const TmaDesc& tx, const __half* grad, const __half* W, __half* grad_inputs, float* dW, uint32_t B,
                             int n_hidden_mm, ProArgs pro, cudaStream_t st, const char* name) {
-    size_t smem = 1024 + (size_t)NSLOTS * 3 * kGBytes + (size_t)IN_DIM * 128 + (size_t)n_hidden_mm * 8192 + 2048 + (4 * NSLOTS + 1) * 8 + 16;
+    size_t smem = 1024 + (size_t)NSLOTS * (RING + 1) * kGBytes + (size_t)IN_DIM * 128 + (size_t)n_hidden_mm * 8192 + 2048 + ((2 + RING) * NSLOTS + 1) * 8 + 16;
     if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: it allocates all 512 TMEM columns
-    if (smem > 227 * 1024) { set_error("%s: network too deep for the tcgen05 path", name); return -2; }
+    if (smem > 227 * 1024) return 1;
     static size_t configured = 0;
     if (smem > configured) {
-        ENERF_CUDA(cudaFuncSetAttribute(k_tc_bwd_tma<NSLOTS, PRO, IN_DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
+        ENERF_CUDA(cudaFuncSetAttribute(k_tc_bwd_tma<NSLOTS, RING, PRO, IN_DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
         configured = smem;
     }
     const uint32_t n_tiles = B / kTile;
     const uint32_t grid = n_tiles < (uint32_t)kNumSM ? n_tiles : (uint32_t)kNumSM;
-    k_tc_bwd_tma<NSLOTS, PRO, IN_DIM><<<grid, 32 + NSLOTS * 128, smem, st>>>(th, tx, grad, W, grad_inputs, dW, n_tiles, B, n_hidden_mm, pro);
+    k_tc_bwd_tma<NSLOTS, RING, PRO, IN_DIM><<<grid, 32 + NSLOTS * 128, smem, st>>>(th, tx, grad, W, grad_inputs, dW, n_tiles, B, n_hidden_mm, pro);
     ENERF_CHECK_LAUNCH(name);
     return 0;
 }
@@ -1045,6 +1074,9 @@ static int launch_bwd_tma(const __half* grad, const __half* x, const __half* W, 
         const char* e = getenv("ENERF_TC_BWD_SLOTS");
         g_bwd_slots = e ? atoi(e) : 3;
         if (g_bwd_slots < 2 || g_bwd_slots > 4) g_bwd_slots = 3;
+        e = getenv("ENERF_TC_BWD_RING");
+        g_bwd_ring = e ? atoi(e) : 2;
+        if (g_bwd_ring < 2 || g_bwd_ring > 4) g_bwd_ring = 2;
     }
     if (!g_bwd_tma || (in_dim != 32 && in_dim != 64) || (uint64_t)(n_hidden_mm + 1) * B >= (1ull << 31)) return 1;
     TmaDesc th, tx;
@@ -1053,10 +1085,17 @@ static int launch_bwd_tma(const __half* grad, const __half* x, const __half* W, 
     int slots = g_bwd_slots;
     while (slots > 2 && slots * kSlotCols + 16 + 64 * n_hidden_mm + in_dim > 512) --slots;
     if (slots * kSlotCols + 16 + 64 * n_hidden_mm + in_dim > 512) return 1;
-#define ENERF_BWD_TMA_CASE(NS, ID) \
-    if (slots == NS && in_dim == ID) return launch_bwd_tma_n<NS, PRO, ID>(th, tx, grad, W, grad_inputs, dW, B, n_hidden_mm, pro, st, name);
-    ENERF_BWD_TMA_CASE(2, 32) ENERF_BWD_TMA_CASE(3, 32) ENERF_BWD_TMA_CASE(4, 32)
-    ENERF_BWD_TMA_CASE(2, 64) ENERF_BWD_TMA_CASE(3, 64) ENERF_BWD_TMA_CASE(4, 64)
+#define ENERF_BWD_TMA_CASE(NS, RG) \
+    if (slots == NS && g_bwd_ring == RG) return launch_bwd_tma_n<NS, RG, PRO, 32>(th, tx, grad, W, grad_inputs, dW, B, n_hidden_mm, pro, st, name);
+    if (in_dim == 32) {
+        ENERF_BWD_TMA_CASE(2, 2) ENERF_BWD_TMA_CASE(3, 2) ENERF_BWD_TMA_CASE(4, 2)
+        ENERF_BWD_TMA_CASE(2, 3) ENERF_BWD_TMA_CASE(3, 3) ENERF_BWD_TMA_CASE(4, 3)
+        ENERF_BWD_TMA_CASE(2, 4) ENERF_BWD_TMA_CASE(3, 4)
+    } else if (slots >= 3) {
+        return launch_bwd_tma_n<3, 2, PRO, 64>(th, tx, grad, W, grad_inputs, dW, B, n_hidden_mm, pro, st, name);
+    } else {
+        return launch_bwd_tma_n<2, 2, PRO, 64>(th, tx, grad, W, grad_inputs, dW, B, n_hidden_mm, pro, st, name);
+    }
 #undef ENERF_BWD_TMA_CASE
     return 1;
 }

@@ -53,6 +53,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// one lane of the (converged) warp; the same lane every time for the full mask.  MMA-issuing warps run their
+// control flow warp-uniformly and wrap only the issue itself in `if (elect_one())`: under a divergent
+// `if (lane == 0)` ptxas cannot prove the descriptor operands uniform and emits an ELECT / R2UR waterfall loop
+// in front of every UTCHMMA (~150 cycles per MMA on the single issuing thread — measured as THE limiter of the
+// fused-MLP kernels).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred)::"memory");
+    return pred != 0;
+}
+
 // ---- TMEM allocation (one full warp) ------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");

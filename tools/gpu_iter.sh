@@ -5,16 +5,19 @@ out=gpurun_out
 mkdir -p $out
 timeout 600 python -m pytest tests -m gpu -x -q -k "${TESTS:-ffmlp or field or grid or golden or renderer}" > $out/${tag}_pytest.log 2>&1
 echo "pytest exit $?"; tail -15 $out/${tag}_pytest.log
-for slots in ${SLOTS:-3}; do
+for cfg in ${SLOTS:-3:2}; do
+  slots=${cfg%%:*}; ring=${cfg##*:}; [ "$ring" = "$cfg" ] && ring=2
+  export ENERF_TC_BWD_RING=$ring
   ENERF_TC_BWD_SLOTS=$slots timeout 300 python tools/bench_kernels.py --iters 10 --only ${ONLY:-mlp,grid} > $out/${tag}_kernels_s${slots}.json 2> $out/${tag}_kernels_s${slots}.err
-  echo "bench_kernels slots=$slots exit $?"; tail -3 $out/${tag}_kernels_s${slots}.err
+  echo "bench_kernels slots=$slots ring=$ring exit $?"; tail -3 $out/${tag}_kernels_s${slots}.err
   python - <<PY
 import json
 d=json.load(open("$out/${tag}_kernels_s${slots}.json"))
 for k,v in d.items():
-    if isinstance(v,dict) and ('tc' in k or 'grid_fwd' in k or 'walk' in k): print(f"{k:45s} {v['ms']:.3f} ms  frac={v.get('frac')}")
+    if isinstance(v,dict) and (('tc' in k and '${BRIEF:-}' in k) or 'grid_fwd' in k or 'walk' in k): print(f"{k:45s} {v['ms']:.3f} ms  frac={v.get('frac')}")
 PY
 done
+unset ENERF_TC_BWD_RING
 timeout 600 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > $out/${tag}_bench.json 2> $out/${tag}_bench.err
 echo "bench exit $?"; tail -3 $out/${tag}_bench.err
 python - <<PY
