@@ -691,20 +691,24 @@ static int launch_bwd(const __half* grad, const __half* x, const __half* W, cons
 // ================================================================================================
 struct alignas(64) TmaDesc { uint8_t bytes[128]; };     // CUtensorMap (opaque here; encoded on the host)
 
-template <int NSLOTS, int RING, int PRO, int IN_DIM>
+template <int NSLOTS, int RING, int NH, int PRO, int IN_DIM>
 __global__ void __launch_bounds__(32 + NSLOTS * 128, 1)
 k_tc_bwd_tma(const __grid_constant__ TmaDesc tm_h, const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ grad,
-             const __half* __restrict__ W, __half* __restrict__ grad_inputs, float* __restrict__ dW, uint32_t n_tiles, uint32_t B,
-             int n_hidden_mm, ProArgs pro) {
+             const __half* __restrict__ W, __half* __restrict__ grad_inputs, float* __restrict__ dW, uint32_t n_tiles, uint32_t B, ProArgs pro) {
+    // NH = hidden-to-hidden matmuls (compile time): every stage of a tile is unrolled, so descriptors, ring buffers and
+    // accumulator columns are constants relative to a handful of uniform registers and the issuing warp spends a few
+    // instructions per MMA (with run-time stage dispatch it needed ~300 instructions per stage and was the bottleneck).
     constexpr int in_dim = IN_DIM;
+    constexpr int S = NH + 2;                              // stages per tile
+    static_assert(S % RING == 0 && RING >= 2, "the ring depth must divide the stage count (static buffer indices)");
     constexpr uint32_t kXSw = IN_DIM * 2;                  // swizzle bytes of the input tile (row bytes): 64 or 128
     extern __shared__ uint8_t smem_dyn[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     uint8_t* hring = smem;                                          // NSLOTS x RING x 16 KB, 1024-byte aligned (TMA swizzle atoms)
-    uint8_t* gtiles = hring + (size_t)NSLOTS * RING * kGBytes;         // NSLOTS x 16 KB, canonical [chunk][row][16 B]
+    uint8_t* gtiles = hring + (size_t)NSLOTS * RING * kGBytes;      // NSLOTS x 16 KB, canonical [chunk][row][16 B]
     uint8_t* w0s = gtiles + (size_t)NSLOTS * kGBytes;               // [in_dim/8][64][16 B]   (forward layout)
-    uint8_t* whs = w0s + in_dim * 128;                              // n_hidden_mm x [8][64][16 B]
-    uint8_t* wls = whs + n_hidden_mm * 8192;                        // [8][16][16 B]
+    uint8_t* whs = w0s + in_dim * 128;                              // NH x [8][64][16 B]
+    uint8_t* wls = whs + NH * 8192;                                 // [8][16][16 B]
     uint64_t* a_ready = reinterpret_cast<uint64_t*>(wls + 2048);
     uint64_t* d_full = a_ready + NSLOTS;
     uint64_t* h_full = d_full + NSLOTS;                             // [NSLOTS][RING]
@@ -716,8 +720,8 @@ k_tc_bwd_tma(const __grid_constant__ TmaDesc tm_h, const __grid_constant__ TmaDe
     constexpr uint32_t kCols = 512;
 
     stage_matrix(w0s, W, kW, in_dim, tid, nthreads);
-    for (int j = 0; j < n_hidden_mm; ++j) stage_matrix(whs + j * 8192, W + kW * in_dim + j * kW * kW, kW, kW, tid, nthreads);
-    stage_matrix(wls, W + kW * in_dim + n_hidden_mm * kW * kW, 16, kW, tid, nthreads);
+    for (int j = 0; j < NH; ++j) stage_matrix(whs + j * 8192, W + kW * in_dim + j * kW * kW, kW, kW, tid, nthreads);
+    stage_matrix(wls, W + kW * in_dim + NH * kW * kW, 16, kW, tid, nthreads);
     if (tid == 0) {
         for (int s = 0; s < NSLOTS; ++s) {
             mbar_init(&a_ready[s], 128);
@@ -736,38 +740,26 @@ k_tc_bwd_tma(const __grid_constant__ TmaDesc tm_h, const __grid_constant__ TmaDe
     tc_fence_after();
     const uint32_t tmem0 = *tmem_base_ptr;
 
-    const int S = n_hidden_mm + 2;
     const uint32_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const uint32_t acc_last = tmem0 + NSLOTS * kSlotCols;
-    const uint32_t acc_hid = acc_last + 16;
-    const uint32_t acc_0 = acc_hid + n_hidden_mm * 64;
+    // TMEM columns: [slot s: D 64 | A 32] x NSLOTS, then the weight-gradient accumulators [dW_last^T : 16][dW_hidden j : 64 each][dW_0 : in_dim]
+    constexpr uint32_t kAccLast = NSLOTS * kSlotCols, kAccHid = kAccLast + 16, kAcc0 = kAccHid + NH * 64;
+    static_assert(kAcc0 + IN_DIM <= 512, "TMEM budget");
 
     if (warp == 0) {
-        // MMA / TMA issuer: warp-uniform control flow, one elected lane issues (see elect_one()).
-        uint32_t pa[NSLOTS], cons[NSLOTS], total[NSLOTS], issued[NSLOTS], phase[NSLOTS];
-        uint32_t remaining = 0, started = 0;
+        // ===================== MMA / TMA issuer: warp-uniform control flow, one elected lane issues =====================
         const uint32_t tm = __shfl_sync(0xffffffffu, tmem0, 0);
         const uint32_t hring_b = smem_u32(hring), gt_b = smem_u32(gtiles), w0b = smem_u32(w0s), whb = smem_u32(whs), wlb = smem_u32(wls);
-        const uint32_t acc_last_u = tm + NSLOTS * kSlotCols, acc_hid_u = acc_last_u + 16, acc_0_u = acc_hid_u + n_hidden_mm * 64;
+        uint32_t nt[NSLOTS];
 #pragma unroll
-        for (int s = 0; s < NSLOTS; ++s) {
-            pa[s] = 0;
-            cons[s] = 0;
-            phase[s] = 0;
-            issued[s] = 0;
-            const uint32_t left = (my_tiles > (uint32_t)s) ? (my_tiles - s + NSLOTS - 1) / NSLOTS : 0;
-            total[s] = left * S;
-            remaining += total[s];
-        }
-        // load i of slot s: stage k = i % S of the slot's (i / S)-th tile   (called by the elected lane only)
-        auto issue_load = [&](int s, uint32_t i) {
-            const uint32_t tl = i / (uint32_t)S, k = i - tl * (uint32_t)S;
+        for (int s = 0; s < NSLOTS; ++s) nt[s] = (my_tiles > (uint32_t)s) ? (my_tiles - s + NSLOTS - 1) / NSLOTS : 0;
+        // activation tile of stage k of the slot's tl-th tile -> ring buffer k % RING   (elected lane only)
+        auto issue_load = [&](int s, uint32_t tl, int k) {
             const uint32_t tile = blockIdx.x + ((uint32_t)s + tl * NSLOTS) * gridDim.x;
-            const uint32_t dst = hring_b + ((uint32_t)s * RING + (i % RING)) * kGBytes;
-            uint64_t* bar = &h_full[RING * s + (i % RING)];
-            if (k + 1 < (uint32_t)S) {
+            const uint32_t dst = hring_b + (uint32_t)(s * RING + (k % RING)) * kGBytes;
+            uint64_t* bar = &h_full[RING * s + (k % RING)];
+            if (k < S - 1) {
                 mbar_arrive_expect_tx(bar, kGBytes);
-                tma_load_2d(dst, &tm_h, 0, (int32_t)((uint32_t)(n_hidden_mm - (int)k) * B + tile * kTile), bar);
+                tma_load_2d(dst, &tm_h, 0, (int32_t)((uint32_t)(NH - k) * B + tile * kTile), bar);
             } else {
                 mbar_arrive_expect_tx(bar, kTile * in_dim * 2);
                 tma_load_2d(dst, &tm_x, 0, (int32_t)(tile * kTile), bar);
@@ -775,115 +767,131 @@ k_tc_bwd_tma(const __grid_constant__ TmaDesc tm_h, const __grid_constant__ TmaDe
         };
 #pragma unroll
         for (int s = 0; s < NSLOTS; ++s) {
-            const uint32_t pre = total[s] < (uint32_t)RING ? total[s] : (uint32_t)RING;
-            if (elect_one())
-                for (uint32_t i = 0; i < pre; ++i) issue_load(s, i);
-            __syncwarp();
-            issued[s] = pre;
-        }
-        while (remaining > 0) {
+            if (nt[s] > 0 && elect_one()) {
 #pragma unroll
-            for (int s = 0; s < NSLOTS; ++s) {
-                if (cons[s] == total[s]) continue;
-                const uint32_t i = cons[s];
-                const int k = (int)(i % (uint32_t)S);
-                const uint32_t d_t = tm + s * kSlotCols, a_t = d_t + 64;
-                const uint32_t g_s = gt_b + (uint32_t)s * kGBytes;
-                const uint32_t h_s = hring_b + ((uint32_t)s * RING + (i % RING)) * kGBytes;
-                if (phase[s] == 0) {
-                    if (!__all_sync(0xffffffffu, mbar_test(&a_ready[s], pa[s]))) continue;
-                    pa[s] ^= 1;
+                for (int k = 0; k < RING; ++k) issue_load(s, 0, k);
+            }
+            __syncwarp();
+        }
+        constexpr uint32_t idD64 = idesc_f16(kTile, 64, false, true), idDx = idesc_f16(kTile, (uint32_t)IN_DIM, false, true);
+        constexpr uint32_t idWl = idesc_f16(64, 16, true, true), idWh = idesc_f16(64, 64, true, true), idW0 = idesc_f16(64, (uint32_t)IN_DIM, true, true);
+        for (uint32_t tl = 0; tl < nt[0]; ++tl) {
+#pragma unroll
+            for (int k = 0; k < S; ++k) {
+#pragma unroll
+                for (int s = 0; s < NSLOTS; ++s) {
+                    if (tl >= nt[s]) continue;
+                    const uint32_t i = tl * S + k;                       // slot-local stage counter
+                    const uint32_t d_t = tm + s * kSlotCols, a_t = d_t + 64;
+                    const uint32_t g_s = gt_b + (uint32_t)s * kGBytes;
+                    const uint32_t h_s = hring_b + (uint32_t)(s * RING + (k % RING)) * kGBytes;
+                    mbar_wait(&a_ready[s], i & 1u);
                     tc_fence_after();
                     // E_i is done: it has read its ReLU mask from the buffer of stage i-1, whose wgrad completed before E_i started,
-                    // so that buffer can take load i-1+RING
-                    const bool do_load = (i >= 1 && issued[s] < total[s]);
+                    // so that buffer takes load i-1+RING = stage (k-1+RING) % S of tile tl + (k-1+RING) / S
+                    const int kl = (k - 1 + RING) % S, dt = (k - 1 + RING) / S;
+                    const bool do_load = (i >= 1) && (tl + dt < nt[s]);
                     if (elect_one()) {
-                        if (do_load) issue_load(s, issued[s]);
+                        if (do_load) issue_load(s, tl + dt, kl);
                         if (k == 0) {
                             // dgrad through the output layer: D[128x64] = dy[128x16] . W_last[16x64]
-                            mma_ts(d_t, a_t, smem_desc(wlb, 128, 16 * 16), idesc_f16(kTile, 64, false, true), false);
-                        } else if (k <= n_hidden_mm) {
-                            const uint32_t wj = whb + (uint32_t)(n_hidden_mm - k) * 8192u;
+                            mma_ts(d_t, a_t, smem_desc(wlb, 128, 16 * 16), idD64, false);
+                        } else if (k <= NH) {
+                            const uint32_t wj = whb + (uint32_t)(NH - k) * 8192u;
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks)
-                                mma_ts(d_t, a_t + ks * 8, smem_desc(wj + ks * 256, 128, 64 * 16), idesc_f16(kTile, 64, false, true), ks > 0);
+                            for (int ks = 0; ks < 4; ++ks) mma_ts(d_t, a_t + ks * 8, smem_desc(wj + ks * 256, 128, 64 * 16), idD64, ks > 0);
                         } else {
-                            // dx = g_0 . W_0 — issued even when the caller does not ask for grad_inputs (4 small MMAs)
+                            // dx = g_0 . W_0 (issued even when the caller does not ask for grad_inputs: 4 small MMAs)
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks)
-                                mma_ts(d_t, a_t + ks * 8, smem_desc(w0b + ks * 256, 128, 64 * 16), idesc_f16(kTile, (uint32_t)in_dim, false, true), ks > 0);
+                            for (int ks = 0; ks < 4; ++ks) mma_ts(d_t, a_t + ks * 8, smem_desc(w0b + ks * 256, 128, 64 * 16), idDx, ks > 0);
                         }
                     }
                     __syncwarp();
-                    if (do_load) ++issued[s];
-                    phase[s] = 1;
-                }
-                // wgrad needs the activation tile of this stage
-                if (!__all_sync(0xffffffffu, mbar_test(&h_full[RING * s + (i % RING)], (i / RING) & 1u))) continue;
-                tc_fence_after();
-                const bool acc = (started >> k) & 1u;
-                started |= 1u << k;
-                if (elect_one()) {
-                    if (k == 0) {
-                        // dW_last^T[64x16] += h_n^T[64x128] . dy[128x16]   (A = activation tile, B = dy tile in the G buffer)
+                    // wgrad needs the activation tile of this stage: fill number tl*(S/RING) + k/RING of its ring buffer
+                    mbar_wait(&h_full[RING * s + (k % RING)], (tl * (S / RING) + (uint32_t)(k / RING)) & 1u);
+                    tc_fence_after();
+                    const bool acc = !(tl == 0 && s == 0);               // the very first issue on an accumulator overwrites it
+                    if (elect_one()) {
+                        if (k == 0) {
+                            // dW_last^T[64x16] += h_n^T[64x128] . dy[128x16]   (A = activation tile, B = dy tile in the G buffer)
 #pragma unroll
-                        for (int ks = 0; ks < 8; ++ks)
-                            mma_ss(acc_last_u, smem_desc_sw(h_s + ks * 2048, 128), smem_desc(g_s + ks * 256, 128, 2048), idesc_f16(64, 16, true, true), acc || ks > 0);
-                    } else if (k <= n_hidden_mm) {
-                        const uint32_t accj = acc_hid_u + (uint32_t)(n_hidden_mm - k) * 64u;
+                            for (int ks = 0; ks < 8; ++ks)
+                                mma_ss(tm + kAccLast, smem_desc_sw(h_s + ks * 2048, 128), smem_desc(g_s + ks * 256, 128, 2048), idWl, acc || ks > 0);
+                        } else if (k <= NH) {
 #pragma unroll
-                        for (int ks = 0; ks < 8; ++ks)
-                            mma_ss(accj, smem_desc(g_s + ks * 256, 128, 2048), smem_desc_sw(h_s + ks * 2048, 128), idesc_f16(64, 64, true, true), acc || ks > 0);
-                    } else {
+                            for (int ks = 0; ks < 8; ++ks)
+                                mma_ss(tm + kAccHid + (uint32_t)(NH - k) * 64u, smem_desc(g_s + ks * 256, 128, 2048), smem_desc_sw(h_s + ks * 2048, 128), idWh,
+                                       acc || ks > 0);
+                        } else {
 #pragma unroll
-                        for (int ks = 0; ks < 8; ++ks)
-                            mma_ss(acc_0_u, smem_desc(g_s + ks * 256, 128, 2048), smem_desc_sw(h_s + ks * 16 * kXSw, kXSw), idesc_f16(64, (uint32_t)in_dim, true, true),
-                                   acc || ks > 0);
+                            for (int ks = 0; ks < 8; ++ks)
+                                mma_ss(tm + kAcc0, smem_desc(g_s + ks * 256, 128, 2048), smem_desc_sw(h_s + ks * 16 * kXSw, kXSw), idW0, acc || ks > 0);
+                        }
+                        tc_commit(&d_full[s]);
                     }
-                    tc_commit(&d_full[s]);
+                    __syncwarp();
                 }
-                __syncwarp();
-                phase[s] = 0;
-                ++cons[s];
-                --remaining;
             }
         }
         if (elect_one()) tc_commit(flush_bar);
         __syncwarp();
     } else {
+        // ===================== epilogue warps (4 per slot) =====================
         const int s = (warp - 1) >> 2;
         const int q = warp & 3;
         const int r_in_tile = q * 32 + lane;
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
         const uint32_t d_t = tmem0 + lane_sel + s * kSlotCols, a_t = d_t + 64;
         uint8_t* g_tile = gtiles + (size_t)s * kGBytes;
-        uint32_t pd = 0;
-        uint32_t i = 0;                                 // slot-local stage counter (mirrors the MMA thread's)
 
-        for (uint32_t j = s; j < my_tiles; j += NSLOTS) {
+        // dL/dy of this row: raw operands are fetched one tile ahead (their HBM latency would otherwise sit at the head of every tile)
+        int4 pv0 = make_int4(0, 0, 0, 0), pv1 = make_int4(0, 0, 0, 0);
+        float pf[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        auto fetch = [&](size_t row) {
+            if (PRO == 0) {
+                const int4* src = reinterpret_cast<const int4*>(grad + row * 16);
+                pv0 = __ldg(src);
+                pv1 = __ldg(src + 1);
+            } else if (PRO == 1) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (c < pro.n_ch) {
+                        pf[c] = __ldg(pro.rgb + row * pro.n_ch + c);
+                        pf[4 + c] = __ldg(pro.g_rgb + row * pro.n_ch + c);
+                    }
+            } else {
+                pf[0] = __ldg(pro.sigma + row);
+                pf[1] = __ldg(pro.g_sigma + row);
+                const int4* src = reinterpret_cast<const int4*>(pro.dcin + row * 32 + 16);
+                pv0 = __ldg(src);
+                pv1 = __ldg(src + 1);
+            }
+        };
+        if ((uint32_t)s < my_tiles) fetch(((size_t)blockIdx.x + (size_t)s * gridDim.x) * kTile + r_in_tile);
+
+        uint32_t tl = 0;
+        for (uint32_t j = s; j < my_tiles; j += NSLOTS, ++tl) {
             const size_t tile = (size_t)blockIdx.x + (size_t)j * gridDim.x;
             const size_t row = tile * kTile + r_in_tile;
             // ---- E_0: dy -> TMEM A + dy tile (G buffer)
             {
                 int4 v0, v1;
                 if (PRO == 0) {
-                    const int4* src = reinterpret_cast<const int4*>(grad + row * 16);
-                    v0 = __ldg(src);
-                    v1 = __ldg(src + 1);
+                    v0 = pv0;
+                    v1 = pv1;
                 } else if (PRO == 1) {
                     float dyv[4] = {0.f, 0.f, 0.f, 0.f};
-                    for (int c = 0; c < pro.n_ch; ++c) {
-                        const float y = pro.rgb[row * pro.n_ch + c];
-                        dyv[c] = f16_round(pro.g_rgb[row * pro.n_ch + c]) * (1.0f - y) * y;
-                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (c < pro.n_ch) dyv[c] = f16_round(pf[4 + c]) * (1.0f - pf[c]) * pf[c];
                     v0 = make_int4((int)pack2(dyv[0], dyv[1]), (int)pack2(dyv[2], dyv[3]), 0, 0);
                     v1 = make_int4(0, 0, 0, 0);
                 } else {
-                    const float sg = fminf(fmaxf(pro.sigma[row], 3.0590232050182579e-07f), 3269017.3724721107f);   // exp(-15), exp(15)
-                    const __half d0 = __float2half_rn(pro.g_sigma[row] * sg);
-                    const int4* src = reinterpret_cast<const int4*>(pro.dcin + row * 32 + 16);
-                    const int4 a = __ldg(src), b = __ldg(src + 1);
-                    const uint32_t w[8] = {(uint32_t)a.x, (uint32_t)a.y, (uint32_t)a.z, (uint32_t)a.w, (uint32_t)b.x, (uint32_t)b.y, (uint32_t)b.z, (uint32_t)b.w};
+                    const float sg = fminf(fmaxf(pf[0], 3.0590232050182579e-07f), 3269017.3724721107f);   // exp(-15), exp(15)
+                    const __half d0 = __float2half_rn(pf[1] * sg);
+                    // dcin columns 16..30 -> dy columns 1..15 (shift by one fp16)
+                    const uint32_t w[8] = {(uint32_t)pv0.x, (uint32_t)pv0.y, (uint32_t)pv0.z, (uint32_t)pv0.w,
+                                           (uint32_t)pv1.x, (uint32_t)pv1.y, (uint32_t)pv1.z, (uint32_t)pv1.w};
                     uint32_t o[8];
                     o[0] = (uint32_t)__half_as_ushort(d0) | (w[0] << 16);
 #pragma unroll
@@ -900,15 +908,16 @@ k_tc_bwd_tma(const __grid_constant__ TmaDesc tm_h, const __grid_constant__ TmaDe
                 fence_proxy_async_smem();
                 tc_fence_before();
                 mbar_arrive(&a_ready[s]);
+                if (j + NSLOTS < my_tiles) fetch(((size_t)blockIdx.x + (size_t)(j + NSLOTS) * gridDim.x) * kTile + r_in_tile);
             }
             // ---- E_k, k = 1 .. S-1: g = D * relu'(h of stage k-1) -> TMEM A + G tile
+#pragma unroll
             for (int k = 1; k < S; ++k) {
-                mbar_wait(&d_full[s], pd);
-                pd ^= 1;
+                mbar_wait(&d_full[s], (tl * S + (uint32_t)(k - 1)) & 1u);
                 tc_fence_after();
-                const uint32_t ip = i + (uint32_t)k - 1;                                // stage whose activation tile masks this gradient
-                mbar_wait(&h_full[RING * s + (ip % RING)], (ip / RING) & 1u);          // complete long ago; orders our reads after the TMA writes
-                const uint8_t* hrow = hring + ((size_t)s * RING + (ip % RING)) * kGBytes;
+                const int hb = (k - 1) % RING;                                                           // ring buffer of stage k-1
+                mbar_wait(&h_full[RING * s + hb], (tl * (S / RING) + (uint32_t)((k - 1) / RING)) & 1u);   // complete long ago; orders our reads after the TMA writes
+                const uint8_t* hrow = hring + (size_t)(s * RING + hb) * kGBytes;
                 int4 hv[8];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) hv[c] = *reinterpret_cast<const int4*>(hrow + sw_off((uint32_t)r_in_tile, (uint32_t)c, 128));
@@ -937,8 +946,7 @@ k_tc_bwd_tma(const __grid_constant__ TmaDesc tm_h, const __grid_constant__ TmaDe
                 mbar_arrive(&a_ready[s]);
             }
             // ---- E_S: dx
-            mbar_wait(&d_full[s], pd);
-            pd ^= 1;
+            mbar_wait(&d_full[s], (tl * S + (uint32_t)(S - 1)) & 1u);
             tc_fence_after();
             if (grad_inputs) {
 #pragma unroll
@@ -955,7 +963,6 @@ k_tc_bwd_tma(const __grid_constant__ TmaDesc tm_h, const __grid_constant__ TmaDe
                 }
             }
             tc_fence_before();
-            i += (uint32_t)S;
         }
 
         // ---- flush the weight-gradient accumulators (slot 0's four warps; M = 64 -> lanes 0..15 of each quarter)
@@ -963,22 +970,22 @@ k_tc_bwd_tma(const __grid_constant__ TmaDesc tm_h, const __grid_constant__ TmaDe
             mbar_wait(flush_bar, 0);
             tc_fence_after();
             const int m = q * 16 + lane;
-            const uint32_t base = lane_sel;
+            const uint32_t base = tmem0 + lane_sel;
             float* dW0 = dW;
             float* dWh = dW + kW * in_dim;
-            float* dWl = dWh + (size_t)n_hidden_mm * kW * kW;
+            float* dWl = dWh + (size_t)NH * kW * kW;
             {
                 uint32_t acc[16];
-                tmem_ld16(acc_last + base, acc);
+                tmem_ld16(base + kAccLast, acc);
                 tc_wait_ld();
                 if (lane < 16)
 #pragma unroll
                     for (int nn = 0; nn < 16; ++nn) atomicAdd(dWl + nn * kW + m, __uint_as_float(acc[nn]));
             }
-            for (int jj = 0; jj < n_hidden_mm; ++jj)
+            for (int jj = 0; jj < NH; ++jj)
                 for (int c = 0; c < 4; ++c) {
                     uint32_t acc[16];
-                    tmem_ld16(acc_hid + jj * 64 + c * 16 + base, acc);
+                    tmem_ld16(base + kAccHid + jj * 64 + c * 16, acc);
                     tc_wait_ld();
                     if (lane < 16) {
                         float* dst = dWh + (size_t)jj * kW * kW + (size_t)m * kW + c * 16;
@@ -990,7 +997,7 @@ k_tc_bwd_tma(const __grid_constant__ TmaDesc tm_h, const __grid_constant__ TmaDe
                 }
             for (int c = 0; c < in_dim / 16; ++c) {
                 uint32_t acc[16];
-                tmem_ld16(acc_0 + c * 16 + base, acc);
+                tmem_ld16(base + kAcc0 + c * 16, acc);
                 tc_wait_ld();
                 if (lane < 16) {
                     float* dst = dW0 + (size_t)m * in_dim + c * 16;
@@ -1044,22 +1051,26 @@ static int g_bwd_slots = 0;   // 0: read ENERF_TC_BWD_SLOTS (default 3)
 static int g_bwd_ring = 0;    // 0: read ENERF_TC_BWD_RING (default 2)
 void tc_set_bwd_tma(int on) { g_bwd_tma = on ? 1 : 0; }
 
-template <int NSLOTS, int RING, int PRO, int IN_DIM>
+template <int NSLOTS, int RING, int NH, int PRO, int IN_DIM>
 static int launch_bwd_tma_n(const TmaDesc& th, const TmaDesc& tx, const __half* grad, const __half* W, __half* grad_inputs, float* dW, uint32_t B,
-                            int n_hidden_mm, ProArgs pro, cudaStream_t st, const char* name) {
-    size_t smem = 1024 + (size_t)NSLOTS * (RING + 1) * kGBytes + (size_t)IN_DIM * 128 + (size_t)n_hidden_mm * 8192 + 2048 + ((2 + RING) * NSLOTS + 1) * 8 + 16;
-    if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: it allocates all 512 TMEM columns
-    if (smem > 227 * 1024) return 1;
-    static size_t configured = 0;
-    if (smem > configured) {
-        ENERF_CUDA(cudaFuncSetAttribute(k_tc_bwd_tma<NSLOTS, RING, PRO, IN_DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
-        configured = smem;
+                            ProArgs pro, cudaStream_t st, const char* name) {
+    if constexpr ((NH + 2) % RING != 0 || NSLOTS * kSlotCols + 16 + 64 * NH + IN_DIM > 512) {
+        return 1;
+    } else {
+        size_t smem = 1024 + (size_t)NSLOTS * (RING + 1) * kGBytes + (size_t)IN_DIM * 128 + (size_t)NH * 8192 + 2048 + ((2 + RING) * NSLOTS + 1) * 8 + 16;
+        if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: it allocates all 512 TMEM columns
+        if (smem > 227 * 1024) return 1;
+        static bool configured = false;
+        if (!configured) {
+            ENERF_CUDA(cudaFuncSetAttribute(k_tc_bwd_tma<NSLOTS, RING, NH, PRO, IN_DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
+            configured = true;
+        }
+        const uint32_t n_tiles = B / kTile;
+        const uint32_t grid = n_tiles < (uint32_t)kNumSM ? n_tiles : (uint32_t)kNumSM;
+        k_tc_bwd_tma<NSLOTS, RING, NH, PRO, IN_DIM><<<grid, 32 + NSLOTS * 128, smem, st>>>(th, tx, grad, W, grad_inputs, dW, n_tiles, B, pro);
+        ENERF_CHECK_LAUNCH(name);
+        return 0;
     }
-    const uint32_t n_tiles = B / kTile;
-    const uint32_t grid = n_tiles < (uint32_t)kNumSM ? n_tiles : (uint32_t)kNumSM;
-    k_tc_bwd_tma<NSLOTS, RING, PRO, IN_DIM><<<grid, 32 + NSLOTS * 128, smem, st>>>(th, tx, grad, W, grad_inputs, dW, n_tiles, B, n_hidden_mm, pro);
-    ENERF_CHECK_LAUNCH(name);
-    return 0;
 }
 
 // returns 1 when the TMA kernel is not applicable (caller falls back to k_tc_bwd), 0 on success, <0 / CUDA error otherwise
@@ -1075,28 +1086,25 @@ static int launch_bwd_tma(const __half* grad, const __half* x, const __half* W, 
         g_bwd_slots = e ? atoi(e) : 3;
         if (g_bwd_slots < 2 || g_bwd_slots > 4) g_bwd_slots = 3;
         e = getenv("ENERF_TC_BWD_RING");
-        g_bwd_ring = e ? atoi(e) : 2;
-        if (g_bwd_ring < 2 || g_bwd_ring > 4) g_bwd_ring = 2;
+        g_bwd_ring = e ? atoi(e) : 0;       // 0 = automatic: 3 for three-stage networks, 2 for four-stage networks
     }
-    if (!g_bwd_tma || (in_dim != 32 && in_dim != 64) || (uint64_t)(n_hidden_mm + 1) * B >= (1ull << 31)) return 1;
+    if (!g_bwd_tma || in_dim != 32 || (n_hidden_mm != 1 && n_hidden_mm != 2) || (uint64_t)(n_hidden_mm + 1) * B >= (1ull << 31)) return 1;
     TmaDesc th, tx;
     if (!make_tmap_rows(&th, fwd_buf, (uint64_t)(n_hidden_mm + 1) * B, 64, kTile) || !make_tmap_rows(&tx, x, B, (uint32_t)in_dim, kTile)) return 1;
-    // TMEM: NSLOTS*96 + 16 + 64*n_hidden_mm + in_dim columns <= 512
-    int slots = g_bwd_slots;
-    while (slots > 2 && slots * kSlotCols + 16 + 64 * n_hidden_mm + in_dim > 512) --slots;
-    if (slots * kSlotCols + 16 + 64 * n_hidden_mm + in_dim > 512) return 1;
-#define ENERF_BWD_TMA_CASE(NS, RG) \
-    if (slots == NS && g_bwd_ring == RG) return launch_bwd_tma_n<NS, RG, PRO, 32>(th, tx, grad, W, grad_inputs, dW, B, n_hidden_mm, pro, st, name);
-    if (in_dim == 32) {
-        ENERF_BWD_TMA_CASE(2, 2) ENERF_BWD_TMA_CASE(3, 2) ENERF_BWD_TMA_CASE(4, 2)
-        ENERF_BWD_TMA_CASE(2, 3) ENERF_BWD_TMA_CASE(3, 3) ENERF_BWD_TMA_CASE(4, 3)
-        ENERF_BWD_TMA_CASE(2, 4) ENERF_BWD_TMA_CASE(3, 4)
-    } else if (slots >= 3) {
-        return launch_bwd_tma_n<3, 2, PRO, 64>(th, tx, grad, W, grad_inputs, dW, B, n_hidden_mm, pro, st, name);
-    } else {
-        return launch_bwd_tma_n<2, 2, PRO, 64>(th, tx, grad, W, grad_inputs, dW, B, n_hidden_mm, pro, st, name);
-    }
+    const int slots = g_bwd_slots;
+    if (n_hidden_mm == 1) {           // 3 stages per tile: ring of 3
+#define ENERF_BWD_TMA_CASE(NS) \
+    if (slots == NS) return launch_bwd_tma_n<NS, 3, 1, PRO, 32>(th, tx, grad, W, grad_inputs, dW, B, pro, st, name);
+        ENERF_BWD_TMA_CASE(2) ENERF_BWD_TMA_CASE(3) ENERF_BWD_TMA_CASE(4)
 #undef ENERF_BWD_TMA_CASE
+    } else {                          // 4 stages per tile: ring of 2 (or 4 with ENERF_TC_BWD_RING=4)
+        if (g_bwd_ring == 4) {
+            if (slots == 2) return launch_bwd_tma_n<2, 4, 2, PRO, 32>(th, tx, grad, W, grad_inputs, dW, B, pro, st, name);
+            return 1;
+        }
+        if (slots == 2) return launch_bwd_tma_n<2, 2, 2, PRO, 32>(th, tx, grad, W, grad_inputs, dW, B, pro, st, name);
+        return launch_bwd_tma_n<3, 2, 2, PRO, 32>(th, tx, grad, W, grad_inputs, dW, B, pro, st, name);
+    }
     return 1;
 }
 

@@ -126,10 +126,13 @@ def test_tcgen05_and_mma_sync_paths_agree(I, nl):
     y_all, fb_all = oracle.ffmlp_forward(x, w, I, W, nl)
     gx, gw, bb = oracle.ffmlp_backward(g, x, w, fb_all, I, W, nl)
     tfb, tg = t(fb_all), t(g)
+    nobuf = {}
     try:
-        for path in (0, 1):
+        # path 0 = tcgen05 with TMA-staged operands (taken when no backward_buffer is asked for), 2 = tcgen05 with per-thread
+        # operand loads, 1 = mma.sync
+        for path in (0, 2, 1):
             _lib.call("enerf_ffmlp_set_path", path)
-            for with_bb in ((True, False) if path == 0 else (True,)):
+            for with_bb in ((True, False) if path != 1 else (True,)):
                 bbuf = torch.zeros(nl, B, W, device=DEV, dtype=torch.half) if with_bb else None
                 gin = torch.zeros(B, I, device=DEV, dtype=torch.half)
                 gwt = torch.zeros(len(w), device=DEV, dtype=torch.float32)
@@ -140,6 +143,13 @@ def test_tcgen05_and_mma_sync_paths_agree(I, nl):
                 _close(n(gwt), gw, 1e-3, "grad_weights " + tag)
                 if with_bb:
                     _close(n(bbuf), bb.astype(np.float64), 3e-3, "backward_buffer " + tag)
+                else:
+                    nobuf[path] = (gin, gwt)
+            if path != 1:
+                # weight gradients only, activation gradients kept on the SM
+                gwt3 = torch.zeros(len(w), device=DEV, dtype=torch.float32)
+                FB.ffmlp_backward(tg, tx, tw, tfb, B, I, 16, W, nl, 0, 6, False, None, torch.zeros(1, device=DEV, dtype=torch.half), gwt3)
+                _close(n(gwt3), gw, 1e-3, f"grad_weights (no dx, no buffer) path {path}")
             # weight-gradient only (calc_grad_inputs = False)
             gwt2 = torch.zeros(len(w), device=DEV, dtype=torch.float32)
             FB.ffmlp_backward(tg, tx, tw, tfb, B, I, 16, W, nl, 0, 6, False, torch.zeros(nl, B, W, device=DEV, dtype=torch.half),
@@ -147,6 +157,8 @@ def test_tcgen05_and_mma_sync_paths_agree(I, nl):
             _close(n(gwt2), gw, 1e-3, f"grad_weights (no dx) path {path}")
     finally:
         _lib.call("enerf_ffmlp_set_path", 0)
+    # the two tcgen05 backward kernels issue the same MMAs on the same tiles: activation gradients are bit-identical
+    assert torch.equal(nobuf[0][0], nobuf[2][0]), "grad_inputs: TMA-staged vs per-thread operand loads"
     d_out = (outs[0][0].float() - outs[1][0].float()).abs().max().item()
     d_fb = (outs[0][1].float() - outs[1][1].float()).abs().max().item()
     assert d_out <= 4e-3 * float(outs[1][0].float().abs().max()) + 1e-3, d_out
