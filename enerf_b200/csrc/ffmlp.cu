@@ -359,6 +359,7 @@ int tc_forward_rgb_head(const __half* cin, const __half* W, uint32_t B, int n_hi
 int tc_backward_rgb(const float* g_rgb, const float* rgb, int n_ch, const __half* cin, const __half* W, const __half* fwd_buf, __half* dcin, float* dW,
                     uint32_t B, int n_hidden_mm, cudaStream_t st);
 void tc_set_bwd_tma(int on);
+void tc_set_fwd_tma(int on);
 int tc_backward_sigma(const float* g_sigma, const float* sigma, const __half* dcin, const __half* feat, const __half* W, const __half* fwd_buf,
                       __half* dfeat, float* dW, uint32_t B, int n_hidden_mm, cudaStream_t st);
 }
@@ -513,6 +514,7 @@ int enerf_ffmlp_set_path(int path) {
     ENERF_REQUIRE(path >= 0 && path <= 2, "ffmlp_set_path", "path must be 0 (auto), 1 (generic mma.sync kernels) or 2 (tcgen05 without TMA operand loads)");
     g_mlp_path = (path == 1) ? 1 : 0;
     tcm::tc_set_bwd_tma(path != 2);
+    tcm::tc_set_fwd_tma(path != 2);
     return 0;
 }
 

@@ -26,6 +26,41 @@ static constexpr int kW = 64;            // hidden width
 static constexpr int kTile = 128;        // samples per tile = UMMA M
 static constexpr int kSlotCols = 96;     // TMEM columns per slot: D (64, fp32) + A (32 = 64 fp16)
 
+static constexpr int kGBytes = 128 * 64 * 2;    // one 128-sample x 64-wide fp16 tile
+struct alignas(64) TmaDesc { uint8_t bytes[128]; };     // CUtensorMap (opaque in device code; encoded on the host)
+
+// ---- host: tensor maps (driver entry point resolved through the runtime; no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+// fp16 row-major [rows, cols] matrix, box = [box_rows, cols]; swizzle = the row size in bytes (32 / 64 / 128)
+static bool make_tmap_rows(TmaDesc* out, const void* base, uint64_t rows, uint32_t cols, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn || (reinterpret_cast<uintptr_t>(base) & 15u)) return false;
+    const uint32_t row_bytes = cols * 2;
+    const CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    if (row_bytes != 128 && row_bytes != 64 && row_bytes != 32) return false;
+    const cuuint64_t gdim[2] = {cols, rows};
+    const cuuint64_t gstride[1] = {row_bytes};
+    const cuuint32_t box[2] = {cols, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    static_assert(sizeof(CUtensorMap) == sizeof(TmaDesc), "CUtensorMap size");
+    return fn(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+
 // copy a row-major [rows, K] fp16 matrix into the canonical chunked layout tile[c][r] (16-B chunks)
 __device__ __forceinline__ void stage_matrix(uint8_t* dst, const __half* __restrict__ src, int rows, int K, int tid, int nthreads) {
     const int cpr = K >> 3;   // chunks per row
@@ -275,6 +310,284 @@ k_tc_fwd(const __half* __restrict__ in, const __half* __restrict__ W, __half* __
     if (warp == 0) tmem_dealloc(tmem0, kCols);
 }
 
+// ================================================================================================
+// Forward / inference, TMA variant (k_tc_fwd_tma): the E-NeRF shapes (32 or 64 inputs, 1 or 2 hidden-to-hidden
+// matmuls).  Differences to k_tc_fwd:
+//   * the [128 x in_dim] input tile arrives by cp.async.bulk.tensor (two-deep ring per slot) in the TMA swizzle and
+//     is the layer-0 A operand straight from shared memory (K-major swizzled descriptor) — no per-thread loads,
+//     no row transposition, no tcgen05.st for the inputs;
+//   * training: every hidden activation tile is written to forward_buffer by one TMA store from a swizzled,
+//     double-buffered staging tile (8 conflict-free STS.128 per thread instead of STS + LDS + STG);
+//   * sigma-net head: the colour-net input tile leaves by TMA store as well;
+//   * compile-time layer schedule (templated depth), warp-uniform issue, fixed slot order.
+//   a_ready[s] counts, per tile, one phase per hidden epilogue ("A operand ready") plus one when the last
+//   accumulator has been read ("slot free for the next tile"); d_full[s] one phase per layer.
+// ================================================================================================
+template <int NSLOTS, int NH, int IN_DIM, int HEAD, bool TRAIN>
+__global__ void __launch_bounds__(32 + NSLOTS * 128, 1)
+k_tc_fwd_tma(const __grid_constant__ TmaDesc tm_x, const __grid_constant__ TmaDesc tm_fb, const __grid_constant__ TmaDesc tm_cin,
+             const __half* __restrict__ W, __half* __restrict__ out, uint32_t n_tiles, uint32_t B, HeadArgs head) {
+    constexpr int S = NH + 2;                                   // matmuls per network
+    constexpr uint32_t kXSw = IN_DIM * 2;                       // input row bytes = swizzle span (64 or 128)
+    constexpr uint32_t kXBytes = kTile * IN_DIM * 2;
+    constexpr uint32_t kCinBytes = kTile * 32 * 2;
+    extern __shared__ uint8_t smem_dyn[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    uint8_t* xring = smem;                                                          // NSLOTS x 2 input tiles
+    uint8_t* stg = xring + (size_t)NSLOTS * 2 * kXBytes;                            // TRAIN: NSLOTS x 2 activation tiles (128-byte swizzle)
+    uint8_t* cst = stg + (TRAIN ? (size_t)NSLOTS * 2 * kGBytes : 0);                // HEAD 1: NSLOTS colour-input tiles (64-byte swizzle)
+    uint8_t* w0s = cst + (HEAD == 1 ? (size_t)NSLOTS * kCinBytes : 0);              // [in_dim/8][64][16 B]
+    uint8_t* whs = w0s + IN_DIM * 128;                                              // NH x [8][64][16 B]
+    uint8_t* wls = whs + NH * 8192;                                                 // [8][16][16 B]
+    uint64_t* a_ready = reinterpret_cast<uint64_t*>(wls + 2048);
+    uint64_t* d_full = a_ready + NSLOTS;
+    uint64_t* x_full = d_full + NSLOTS;                                             // [NSLOTS][2]
+    uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(x_full + 2 * NSLOTS);
+
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    constexpr uint32_t kCols = (NSLOTS * kSlotCols <= 256) ? 256 : 512;
+
+    stage_matrix(w0s, W, kW, IN_DIM, tid, nthreads);
+    for (int j = 0; j < NH; ++j) stage_matrix(whs + j * 8192, W + kW * IN_DIM + j * kW * kW, kW, kW, tid, nthreads);
+    stage_matrix(wls, W + kW * IN_DIM + NH * kW * kW, 16, kW, tid, nthreads);
+    if (tid == 0) {
+        for (int s = 0; s < NSLOTS; ++s) {
+            mbar_init(&a_ready[s], 128);
+            mbar_init(&d_full[s], 1);
+            mbar_init(&x_full[2 * s], 1);
+            mbar_init(&x_full[2 * s + 1], 1);
+        }
+        mbar_fence_init();
+        tma_prefetch_desc(&tm_x);
+        if (TRAIN) tma_prefetch_desc(&tm_fb);
+        if (HEAD == 1) tma_prefetch_desc(&tm_cin);
+    }
+    if (warp == 0) tmem_alloc(tmem_base_ptr, kCols);
+    fence_proxy_async_smem();      // weights written with st.shared are read by the tensor core
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem0 = *tmem_base_ptr;
+    const uint32_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (warp == 0) {
+        // ===================== MMA / TMA-load issuer (warp-uniform, one elected lane issues) =====================
+        const uint32_t tm = __shfl_sync(0xffffffffu, tmem0, 0);
+        const uint32_t xr_b = smem_u32(xring), w0b = smem_u32(w0s), whb = smem_u32(whs), wlb = smem_u32(wls);
+        uint32_t nt[NSLOTS];
+#pragma unroll
+        for (int s = 0; s < NSLOTS; ++s) nt[s] = (my_tiles > (uint32_t)s) ? (my_tiles - s + NSLOTS - 1) / NSLOTS : 0;
+        auto issue_x = [&](int s, uint32_t tl) {               // elected lane only
+            const uint32_t tile = blockIdx.x + ((uint32_t)s + tl * NSLOTS) * gridDim.x;
+            uint64_t* bar = &x_full[2 * s + (tl & 1u)];
+            mbar_arrive_expect_tx(bar, kXBytes);
+            tma_load_2d(xr_b + ((uint32_t)s * 2 + (tl & 1u)) * kXBytes, &tm_x, 0, (int32_t)(tile * kTile), bar);
+        };
+#pragma unroll
+        for (int s = 0; s < NSLOTS; ++s) {
+            if (elect_one()) {
+                if (nt[s] > 0) issue_x(s, 0);
+                if (nt[s] > 1) issue_x(s, 1);
+            }
+            __syncwarp();
+        }
+        constexpr uint32_t idesc64 = idesc_f16(kTile, 64, false, false), idesc16 = idesc_f16(kTile, 16, false, false);
+        for (uint32_t tl = 0; tl < nt[0]; ++tl) {
+#pragma unroll
+            for (int L = 0; L < S; ++L) {
+#pragma unroll
+                for (int s = 0; s < NSLOTS; ++s) {
+                    if (tl >= nt[s]) continue;
+                    const uint32_t d_t = tm + s * kSlotCols, a_t = d_t + 64;
+                    if (L == 0) {
+                        if (tl > 0) mbar_wait(&a_ready[s], (tl * S - 1u) & 1u);          // the previous tile's last accumulator has been read
+                        mbar_wait(&x_full[2 * s + (tl & 1u)], (tl >> 1) & 1u);
+                        tc_fence_after();
+                        const uint32_t xb = xr_b + ((uint32_t)s * 2 + (tl & 1u)) * kXBytes;
+                        if (elect_one()) {
+#pragma unroll
+                            for (int k = 0; k < IN_DIM / 16; ++k)
+                                mma_ss(d_t, smem_desc_sw(xb + k * 32, kXSw), smem_desc(w0b + k * 2 * (kW * 16), kW * 16, 128), idesc64, k > 0);
+                            tc_commit(&d_full[s]);
+                        }
+                        __syncwarp();
+                    } else {
+                        mbar_wait(&a_ready[s], (tl * S + (uint32_t)(L - 1)) & 1u);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            // layer 0 of this tile has completed (its epilogue ran): the input buffer can take the tile after next
+                            if (L == 1 && tl + 2 < nt[s]) issue_x(s, tl + 2);
+                            if (L < S - 1) {
+                                const uint32_t wb = whb + (uint32_t)(L - 1) * 8192u;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) mma_ts(d_t, a_t + k * 8, smem_desc(wb + k * 2 * (kW * 16), kW * 16, 128), idesc64, k > 0);
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) mma_ts(d_t, a_t + k * 8, smem_desc(wlb + k * 2 * (16 * 16), 16 * 16, 128), idesc16, k > 0);
+                            }
+                            tc_commit(&d_full[s]);
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue warps (4 per slot) =====================
+        const int s = (warp - 1) >> 2;                 // slot
+        const int q = warp & 3;                        // TMEM quarter this warp may access
+        const int r = q * 32 + lane;                   // row of the tile
+        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+        const uint32_t d_t = tmem0 + lane_sel + s * kSlotCols, a_t = d_t + 64;
+        const bool issuer = (q == 0 && lane == 0);     // issues this slot's TMA stores
+        uint32_t n_store = 0;                          // activation tiles stored so far by this slot (staging buffer = n_store & 1)
+        uint32_t tl = 0;
+        for (uint32_t j = s; j < my_tiles; j += NSLOTS, ++tl) {
+            const size_t tile = (size_t)blockIdx.x + (size_t)j * gridDim.x;
+            const size_t row = tile * kTile + r;
+            float dx = 0.f, dy = 0.f, dz = 0.f;
+            if (HEAD == 1) {                           // requested now, used after the last layer
+                dx = __ldg(head.dirs + row * 3);
+                dy = __ldg(head.dirs + row * 3 + 1);
+                dz = __ldg(head.dirs + row * 3 + 2);
+            }
+#pragma unroll
+            for (int L = 0; L < S; ++L) {
+                mbar_wait(&d_full[s], (tl * S + (uint32_t)L) & 1u);
+                tc_fence_after();
+                if (L < S - 1) {
+                    uint8_t* sb = stg + ((size_t)s * 2 + (n_store & 1u)) * kGBytes;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint32_t acc[32];
+                        tmem_ld32(d_t + h * 32, acc);
+                        tc_wait_ld();
+                        uint32_t p[16];
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) p[e] = pack2(relu(__uint_as_float(acc[2 * e])), relu(__uint_as_float(acc[2 * e + 1])));
+                        tmem_st16(a_t + h * 16, p);
+                        if (TRAIN) {
+#pragma unroll
+                            for (int v = 0; v < 4; ++v)
+                                *reinterpret_cast<int4*>(sb + sw_off((uint32_t)r, (uint32_t)(h * 4 + v), 128)) =
+                                    make_int4((int)p[4 * v], (int)p[4 * v + 1], (int)p[4 * v + 2], (int)p[4 * v + 3]);
+                        }
+                    }
+                    tc_wait_st();
+                    if (TRAIN) fence_proxy_async_smem();
+                    tc_fence_before();
+                    mbar_arrive(&a_ready[s]);
+                    if (TRAIN) {
+                        // the store issued one layer ago has long finished reading its buffer; waiting for it here (before the barrier)
+                        // tells every thread of the slot that the buffer they will fill NEXT is free
+                        if (issuer) tma_store_wait_read<0>();
+                        named_bar_sync(1 + s, 128);
+                        if (issuer) {
+                            tma_store_2d(&tm_fb, smem_u32(sb), 0, (int32_t)((uint32_t)L * B + (uint32_t)tile * kTile));
+                            tma_store_commit();
+                        }
+                        ++n_store;
+                    }
+                } else {
+                    uint32_t acc[16];
+                    tmem_ld16(d_t, acc);
+                    tc_wait_ld();
+                    tc_fence_before();
+                    mbar_arrive(&a_ready[s]);              // accumulator read: the slot can start its next tile
+                    if (HEAD == 0) {
+                        // 32-byte output rows: two 16-byte stores per lane (consecutive lanes -> consecutive rows)
+                        int4* o = reinterpret_cast<int4*>(out + row * 16);
+                        o[0] = make_int4((int)pack2(__uint_as_float(acc[0]), __uint_as_float(acc[1])), (int)pack2(__uint_as_float(acc[2]), __uint_as_float(acc[3])),
+                                         (int)pack2(__uint_as_float(acc[4]), __uint_as_float(acc[5])), (int)pack2(__uint_as_float(acc[6]), __uint_as_float(acc[7])));
+                        o[1] = make_int4((int)pack2(__uint_as_float(acc[8]), __uint_as_float(acc[9])), (int)pack2(__uint_as_float(acc[10]), __uint_as_float(acc[11])),
+                                         (int)pack2(__uint_as_float(acc[12]), __uint_as_float(acc[13])), (int)pack2(__uint_as_float(acc[14]), __uint_as_float(acc[15])));
+                    } else if (HEAD == 1) {
+                        head.sigma[row] = expf(f16_round(__uint_as_float(acc[0])));
+                        // directions reach the SH encoder as fp16 under autocast (sphere_harmonics.py:16)
+                        float sh[16];
+                        sh_deg4(f16_round(dx), f16_round(dy), f16_round(dz), sh);
+                        uint32_t p[16];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) p[e] = pack2(sh[2 * e], sh[2 * e + 1]);
+#pragma unroll
+                        for (int e = 0; e < 7; ++e) p[8 + e] = pack2(__uint_as_float(acc[1 + 2 * e]), __uint_as_float(acc[2 + 2 * e]));
+                        p[15] = pack2(__uint_as_float(acc[15]), 0.0f);
+                        uint8_t* cb = cst + (size_t)s * kCinBytes;
+                        if (issuer) tma_store_wait_read<0>();      // the previous tile's colour-input store has finished reading cb
+                        named_bar_sync(1 + s, 128);
+#pragma unroll
+                        for (int v = 0; v < 4; ++v)
+                            *reinterpret_cast<int4*>(cb + sw_off((uint32_t)r, (uint32_t)v, 64)) =
+                                make_int4((int)p[4 * v], (int)p[4 * v + 1], (int)p[4 * v + 2], (int)p[4 * v + 3]);
+                        fence_proxy_async_smem();
+                        named_bar_sync(1 + s, 128);
+                        if (issuer) {
+                            tma_store_2d(&tm_cin, smem_u32(cb), 0, (int32_t)((uint32_t)tile * kTile));
+                            tma_store_commit();
+                        }
+                    } else {
+                        for (int c = 0; c < head.n_ch; ++c) {
+                            const float y = f16_round(__uint_as_float(acc[c]));
+                            head.rgb[row * head.n_ch + c] = f16_round(1.0f / (1.0f + expf(-y)));
+                        }
+                    }
+                }
+            }
+        }
+        if (issuer) tma_store_wait<0>();               // all bulk stores of this slot have completed before the CTA exits
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem0, kCols);
+}
+
+static int g_fwd_tma = -1;    // -1: read ENERF_TC_FWD_TMA (default on); 0: k_tc_fwd; 1: k_tc_fwd_tma when applicable
+void tc_set_fwd_tma(int on) { g_fwd_tma = on ? 1 : 0; }
+
+template <int NSLOTS, int NH, int IN_DIM, int HEAD, bool TRAIN>
+static int launch_fwd_tma_n(const TmaDesc& tx, const TmaDesc& tfb, const TmaDesc& tcin, const __half* W, __half* out, uint32_t B, HeadArgs head,
+                            cudaStream_t st, const char* name) {
+    size_t smem = 1024 + (size_t)NSLOTS * 2 * kTile * IN_DIM * 2 + (TRAIN ? (size_t)NSLOTS * 2 * kGBytes : 0) + (HEAD == 1 ? (size_t)NSLOTS * kTile * 64 : 0) +
+                  (size_t)IN_DIM * 128 + (size_t)NH * 8192 + 2048 + 4 * NSLOTS * 8 + 16;
+    if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM (TMEM)
+    if (smem > 227 * 1024) return 1;
+    static bool configured = false;
+    if (!configured) {
+        ENERF_CUDA(cudaFuncSetAttribute(k_tc_fwd_tma<NSLOTS, NH, IN_DIM, HEAD, TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
+        configured = true;
+    }
+    const uint32_t n_tiles = B / kTile;
+    const uint32_t grid = n_tiles < (uint32_t)kNumSM ? n_tiles : (uint32_t)kNumSM;
+    k_tc_fwd_tma<NSLOTS, NH, IN_DIM, HEAD, TRAIN><<<grid, 32 + NSLOTS * 128, smem, st>>>(tx, tfb, tcin, W, out, n_tiles, B, head);
+    ENERF_CHECK_LAUNCH(name);
+    return 0;
+}
+
+// returns 1 when the TMA kernel is not applicable (the caller then launches k_tc_fwd)
+template <int IN_DIM, int HEAD>
+static int launch_fwd_tma(const __half* in, const __half* W, uint32_t B, int n_hidden_mm, __half* fwd_buf, __half* out, HeadArgs head, cudaStream_t st,
+                          const char* name) {
+    if (g_fwd_tma < 0) {
+        const char* e = getenv("ENERF_TC_FWD_TMA");
+        g_fwd_tma = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (!g_fwd_tma || (n_hidden_mm != 1 && n_hidden_mm != 2) || (uint64_t)(n_hidden_mm + 1) * B >= (1ull << 31)) return 1;
+    if (HEAD == 0 && (reinterpret_cast<uintptr_t>(out) & 15u)) return 1;
+    TmaDesc tx, tfb, tcin;
+    if (!make_tmap_rows(&tx, in, B, IN_DIM, kTile)) return 1;
+    tfb = tx;
+    tcin = tx;
+    if (fwd_buf && !make_tmap_rows(&tfb, fwd_buf, (uint64_t)(n_hidden_mm + 1) * B, 64, kTile)) return 1;
+    if (HEAD == 1 && !make_tmap_rows(&tcin, head.cin, B, 32, kTile)) return 1;
+    if (fwd_buf) {
+        if (n_hidden_mm == 1) return launch_fwd_tma_n<3, 1, IN_DIM, HEAD, true>(tx, tfb, tcin, W, out, B, head, st, name);
+        return launch_fwd_tma_n<3, 2, IN_DIM, HEAD, true>(tx, tfb, tcin, W, out, B, head, st, name);
+    }
+    if (n_hidden_mm == 1) return launch_fwd_tma_n<4, 1, IN_DIM, HEAD, false>(tx, tfb, tcin, W, out, B, head, st, name);
+    return launch_fwd_tma_n<4, 2, IN_DIM, HEAD, false>(tx, tfb, tcin, W, out, B, head, st, name);
+}
+
 static size_t fwd_smem_bytes(int in_dim, int n_hidden_mm, int nslots) {
     return (size_t)in_dim * 128 + (size_t)n_hidden_mm * 8192 + 2048 + (size_t)nslots * 4 * 4096 + (size_t)nslots * 16 + 16;
 }
@@ -282,6 +595,10 @@ static size_t fwd_smem_bytes(int in_dim, int n_hidden_mm, int nslots) {
 template <int IN_DIM, int HEAD>
 static int launch_fwd(const __half* in, const __half* W, uint32_t B, int n_hidden_mm, __half* fwd_buf, __half* out, HeadArgs head, cudaStream_t st,
                       const char* name) {
+    if constexpr (IN_DIM == 32 || IN_DIM == 64) {
+        const int rc = launch_fwd_tma<IN_DIM, HEAD>(in, W, B, n_hidden_mm, fwd_buf, out, head, st, name);
+        if (rc != 1) return rc;
+    }
     constexpr int NSLOTS = 4;
     size_t smem = fwd_smem_bytes(IN_DIM, n_hidden_mm, NSLOTS);
     if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: it allocates all 512 TMEM columns
@@ -340,7 +657,6 @@ int tc_forward_rgb_head(const __half* cin, const __half* W, uint32_t B, int n_hi
 // Stage k (k = 0 .. n_hidden_mm+1) of a tile: epilogue E_k prepares operands, MMA thread issues
 // dgrad_k + wgrad_k, tcgen05.commit -> E_k+1 ... (see the schedule in DESIGN.md).
 // ================================================================================================
-static constexpr int kGBytes = 128 * 64 * 2;    // one [8 chunks][128 rows][16 B] tile
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -689,7 +1005,6 @@ static int launch_bwd(const __half* grad, const __half* x, const __half* W, cons
 //   and wgrad(i) has completed (d_full of stage i, which E_{i+1} waited for) -> the issuing warp launches
 //   load(i+RING) right after it observes a_ready(i+1).
 // ================================================================================================
-struct alignas(64) TmaDesc { uint8_t bytes[128]; };     // CUtensorMap (opaque here; encoded on the host)
 
 template <int NSLOTS, int RING, int NH, int PRO, int IN_DIM>
 __global__ void __launch_bounds__(32 + NSLOTS * 128, 1)
@@ -1013,37 +1328,6 @@ k_tc_bwd_tma(const __grid_constant__ TmaDesc tm_h, const __grid_constant__ TmaDe
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem0, kCols);
-}
-
-// ---- host: tensor maps (driver entry point resolved through the runtime; no link-time libcuda dependency)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_tiled_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-// fp16 row-major [rows, cols] matrix, box = [box_rows, cols]; swizzle = the row size in bytes (32 / 64 / 128)
-static bool make_tmap_rows(TmaDesc* out, const void* base, uint64_t rows, uint32_t cols, uint32_t box_rows) {
-    EncodeTiledFn fn = encode_tiled_fn();
-    if (!fn || (reinterpret_cast<uintptr_t>(base) & 15u)) return false;
-    const uint32_t row_bytes = cols * 2;
-    const CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
-    if (row_bytes != 128 && row_bytes != 64 && row_bytes != 32) return false;
-    const cuuint64_t gdim[2] = {cols, rows};
-    const cuuint64_t gstride[1] = {row_bytes};
-    const cuuint32_t box[2] = {cols, box_rows};
-    const cuuint32_t estr[2] = {1, 1};
-    static_assert(sizeof(CUtensorMap) == sizeof(TmaDesc), "CUtensorMap size");
-    return fn(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 static int g_bwd_tma = -1;    // -1: read ENERF_TC_BWD_TMA (default on); 0: k_tc_bwd; 1: k_tc_bwd_tma
