@@ -28,6 +28,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC, UNIT = "train_rays_per_sec", "rays/s"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this workload (bytes)
+NCU_TRAFFIC_SRC = "profiles/r1_04_ncu_full_step_kernels.md (3.29 M samples/launch)"
+NCU_TRAFFIC = {"grid_encode_backward": 0.292428e9 + 0.008309e9, "grid_encode_forward": 0.062685e9 + 0.166211e9,
+               "march_rays_train": 0.000848e9 + 0.049901e9}
 RAYS = 4096
 BOUND = 3
 
@@ -35,13 +39,14 @@ BOUND = 3
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rays", type=int, default=RAYS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"], help="replay the step from a CUDA graph (auto: fall back to eager launches if capture fails)")
     ap.add_argument("--cpu-rays", type=int, default=256, help="rays per CPU-baseline step (bounded sample)")
+    ap.add_argument("--no-render", action="store_true", help="skip the full-frame inference measurement (the `render` object of the line)")
     return ap.parse_args()
 
 
@@ -77,19 +82,22 @@ def reference_arm(args):
 
 # --------------------------------------------------------------------------------------------
 class ClockSampler:
-    QUERY = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+    """nvidia-smi sampled every 20 ms in the background; `stop(t0, t1)` keeps the samples whose timestamp falls inside the
+    timed region [t0, t1] (host wall clock, taken right after the synchronisations that bracket it)."""
+    QUERY = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown," \
             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu_index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(gpu_index)],
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(gpu_index)],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:  # noqa: BLE001
             self.p = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
             return out
@@ -100,24 +108,74 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        rows = []
         for line in self.f.read().splitlines():
             parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 9:
+            if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[1]))
-                mx.append(float(parts[2]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(parts[1]), float(parts[2]), float(parts[3]), parts[4:8]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+        os.unlink(self.f.name)
+        inside = [r for r in rows if t0 is not None and t0 <= r[0] <= t1]
+        window = "timed region"
+        if len(inside) < 3:          # region shorter than a few sampling periods: fall back to every sample taken under load
+            inside, window = rows, "whole run (timed region shorter than 3 samples)"
+        if not inside:
+            return out
+        sm = sorted(r[1] for r in inside)
+        reasons = set()
+        for r in inside:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        if sm:
-            sm.sort()
-            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
-        os.unlink(self.f.name)
-        return out
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": max(r[2] for r in inside), "power_w_max": max(r[3] for r in inside),
+                "reasons": sorted(reasons), "samples": len(inside), "window": window}
+
+
+def render_bench(model, dev, world, rank, frames=3, res=800):
+    """BASELINE configs[3]: full-frame inference render (eval mode, perturb off, max_steps 1024), image rows sharded over
+    the ranks.  Returns Msamples/s (samples actually shaded) and ms per frame, device-timed, max over ranks."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from enerf_b200 import synthetic
+    pose = synthetic.look_at_poses(1, 0.6 * BOUND, seed=7)[0]
+    rows = res // world
+    pix = np.arange(rank * rows * res, (rank + 1) * rows * res)
+    o_np, d_np = synthetic.pinhole_rays(pose, res, res, 50.0, pix)
+    o, d = torch.from_numpy(o_np).to(dev), torch.from_numpy(d_np).to(dev)
+    was_training = model.training
+    model.eval()
+    samples = 0
+    ms = []
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        for f in range(frames + 1):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = model.render(o.unsqueeze(0), d.unsqueeze(0), staged=False, bg_color=1, perturb=False, dt_gamma=0, max_steps=1024, out_dim_color=1)
+            e1.record()
+            torch.cuda.synchronize()
+            if f > 0:
+                ms.append(e0.elapsed_time(e1))
+                samples = model.last_render_stats["samples"]
+    model.train(was_training)
+    t = torch.tensor([float(np.median(ms)), float(samples)], device=dev)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        frame_ms, total_samples = float(tmax[0]), float(t[1])
+    else:
+        frame_ms, total_samples = float(t[0]), float(t[1])
+    return {"workload": f"BASELINE configs[3]: {res}x{res} full-frame inference, rows sharded over {world} GPU(s)", "frame_ms": frame_ms,
+            "msamples_per_s": total_samples / (frame_ms * 1e-3) / 1e6, "samples_shaded": int(total_samples),
+            "iterations": int(model.last_render_stats["iterations"]), "image_finite": bool(torch.isfinite(out["image"]).all())}
 
 
 def our_arm(args):
@@ -201,8 +259,11 @@ def our_arm(args):
         step(rays_o, rays_d, target)
 
     # ---------------- timed region: inputs resident in HBM
-    barrier()
     clocks = ClockSampler(local_rank) if rank == 0 else None
+    for _ in range(2):
+        step(rays_o, rays_d, target)
+    barrier()
+    wall0 = time.time()
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -212,11 +273,12 @@ def our_arm(args):
     host_enqueue_ms = (time.perf_counter() - h0) * 1e3 / K      # CPU time to enqueue one step (no sync inside)
     e1.record()
     barrier()
+    wall1 = time.time()
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count() - launches0
     if graphed is not None:
         launches = K * graphed.launches_per_replay
-    clock_info = clocks.stop() if clocks else None
+    clock_info = clocks.stop(wall0, wall1) if clocks else None
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -282,9 +344,17 @@ def our_arm(args):
         kernels[name.replace("enerf_", "")] = entry
     top = max((k for k in kernels if "frac" in kernels[k]), key=lambda k: kernels[k]["ms_per_step"])
     roofline = {"kernel": top, "bound": kernels[top]["bound"], "achieved": kernels[top]["achieved"], "peak": kernels[top]["peak"],
-                "unit": kernels[top]["unit"], "frac": kernels[top]["frac"], "traffic": None, "peak_source": peaks["src"],
+                "unit": kernels[top]["unit"], "frac": kernels[top]["frac"], "traffic": NCU_TRAFFIC.get(top), "traffic_source": NCU_TRAFFIC_SRC,
+                "peak_source": peaks["src"],
                 "ms_per_launch": kernels[top]["ms_per_step"] / kernels[top]["calls_per_step"],
                 "share_of_step": kernels[top]["ms_per_step"] / (ms / K)}
+
+    render = None
+    if not args.no_render:
+        try:
+            render = render_bench(model, dev, world, rank)
+        except Exception as e:  # noqa: BLE001
+            render = {"error": f"{type(e).__name__}: {e}"}
 
     if rank != 0:
         if world > 1:
@@ -302,7 +372,7 @@ def our_arm(args):
             "config": workload_config(n_rays, {"samples_per_step_per_gpu": S, "parallelism": f"dp{world} (ray-sharded, NCCL grad allreduce)", "launch": "cuda-graph replay" if graphed is not None else "eager",
                                                "l2": "per-step working set (samples x ~1.7 KB of activations + 52 MB grad table) is >> 126 MB L2; no explicit flush"}),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "kernels": kernels,
-            "cpu_baseline": cpu_baseline, "final_loss": float(loss_host), "host_enqueue_ms_per_step": host_enqueue_ms}
+            "cpu_baseline": cpu_baseline, "render": render, "final_loss": float(loss_host), "host_enqueue_ms_per_step": host_enqueue_ms}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

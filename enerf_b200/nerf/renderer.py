@@ -190,6 +190,7 @@ class NeRFRenderer(nn.Module):
             rays_alive = torch.zeros(2, n_alive, dtype=torch.int32, device=device)
             rays_t = torch.zeros(2, n_alive, dtype=torch.float32, device=device)
             step, i = 0, 0
+            self.last_render_stats = {'samples': 0, 'iterations': 0}    # bookkeeping for bench.py (not in the reference)
             while step < 1024:   # hard-coded in the reference as well (renderer.py:364)
                 if step == 0:
                     torch.arange(n_alive, out=rays_alive[0])
@@ -210,6 +211,8 @@ class NeRFRenderer(nn.Module):
                     n_ch = rgbs.shape[-1]
                     image = torch.zeros(N, n_ch, dtype=torch.float32, device=device)
                 raymarching.composite_rays(n_alive, n_step, rays_alive[i % 2], rays_t[i % 2], sigmas, rgbs, deltas, weights_sum, depth, image)
+                self.last_render_stats['samples'] += n_alive * n_step
+                self.last_render_stats['iterations'] += 1
                 step += n_step
                 i += 1
             if image is None:
