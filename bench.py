@@ -178,6 +178,28 @@ def render_bench(model, dev, world, rank, frames=3, res=800):
             "iterations": int(model.last_render_stats["iterations"]), "image_finite": bool(torch.isfinite(out["image"]).all())}
 
 
+def shutdown(world, graphed):
+    """Leave without hanging: a captured graph that contains NCCL kernels must be released before the communicator goes away, and a
+    communicator teardown that blocks (seen after graph capture) must not keep the job alive — a watchdog ends the process."""
+    import threading
+    import torch
+    import torch.distributed as dist
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world <= 1:
+        return
+    threading.Timer(15.0, lambda: os._exit(0)).start()
+    if graphed is not None:
+        graphed.graph = None
+        graphed.static_out = None
+    torch.cuda.synchronize()
+    try:
+        dist.barrier()
+        dist.destroy_process_group()
+    finally:
+        os._exit(0)
+
+
 def our_arm(args):
     import numpy as np
     import torch
@@ -195,6 +217,8 @@ def our_arm(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL's version banner goes to stdout; this script prints exactly one line there
         dist.init_process_group("nccl", device_id=dev)
     n_rays, K, W = args.rays, args.steps, max(3, args.warmup)
 
@@ -243,7 +267,7 @@ def our_arm(args):
     # ---------------- optional: capture the whole iteration in a CUDA graph (same kernels, one launch per step)
     eager_step = step
     graphed = None
-    if args.graph == "on" or (args.graph == "auto" and world == 1):
+    if args.graph in ("on", "auto"):           # NCCL collectives are capturable: the allreduce is part of the graph at N > 1
         try:
             from enerf_b200.graphs import GraphedStep
             graphed = GraphedStep(eager_step, [rays_o, rays_d, target], warmup=3)
@@ -253,7 +277,12 @@ def our_arm(args):
                 raise
             print(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); running eager launches", file=sys.stderr)
             torch.cuda.synchronize()
-            step = eager_step
+            graphed, step = None, eager_step
+        if world > 1:                       # all ranks replay, or none does
+            ok = torch.tensor([1 if graphed is not None else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok[0]) == 0:
+                graphed, step = None, eager_step
 
     for _ in range(W):
         step(rays_o, rays_d, target)
@@ -357,8 +386,7 @@ def our_arm(args):
             render = {"error": f"{type(e).__name__}: {e}"}
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        shutdown(world, graphed)
         return
 
     cpu_baseline = None
@@ -374,8 +402,7 @@ def our_arm(args):
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "kernels": kernels,
             "cpu_baseline": cpu_baseline, "render": render, "final_loss": float(loss_host), "host_enqueue_ms_per_step": host_enqueue_ms}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown(world, graphed)
 
 
 if __name__ == "__main__":

@@ -164,6 +164,16 @@ def test_run_cuda_inference_matches_training_composite():
     assert torch.allclose(a["image"], b["image"], atol=2e-3)
     # depth: training integrates t from the first sample, inference uses absolute t: compare via weights only
     assert torch.isfinite(b["depth"]).all()
+    # grouping more marching steps into one round (the B200 default) vs the reference's n_step <= 8 policy: same samples, same image
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        model.inference_batch_samples = 0
+        c = model.render(t(o)[None], t(d)[None], bg_color=1, perturb=False, out_dim_color=1)
+        rounds_ref = model.last_render_stats["iterations"]
+        model.inference_batch_samples = 1 << 23
+        e = model.render(t(o)[None], t(d)[None], bg_color=1, perturb=False, out_dim_color=1)
+        rounds_big = model.last_render_stats["iterations"]
+    assert torch.equal(c["image"], e["image"]) and torch.equal(c["depth"], e["depth"])
+    assert rounds_big < rounds_ref
 
 
 def test_density_grid_maintenance():
