@@ -170,7 +170,8 @@ class _FFMLP:
         _FFMLP._half("grad", grad)
         _FFMLP._half("inputs", inputs)
         _FFMLP._half("weights", weights)
-        _FFMLP._half("forward_buffer", forward_buffer)
+        if forward_buffer is not None:          # None: the tcgen05 kernel recomputes the hidden activations from `inputs`
+            _FFMLP._half("forward_buffer", forward_buffer)
         need_cuda(backward_buffer, grad_inputs, grad_weights)
         if grad_weights.dtype == torch.float32:
             scratch = grad_weights

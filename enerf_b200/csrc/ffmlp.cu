@@ -415,6 +415,7 @@ int enerf_ffmlp_backward(const uint16_t* grad, const uint16_t* inputs, const uin
     ENERF_REQUIRE(scratch != nullptr, "ffmlp_backward", "scratch must not be NULL");
     const bool use_tc = tc_eligible(input_dim, hidden_dim, num_layers, activation, ENERF_ACT_NONE) && num_layers <= 4;
     ENERF_REQUIRE(use_tc || backward_buffer != nullptr, "ffmlp_backward", "the mma.sync path needs backward_buffer");
+    ENERF_REQUIRE(use_tc || forward_buffer != nullptr, "ffmlp_backward", "the mma.sync path needs forward_buffer (recomputation exists on the tcgen05 path only)");
     cudaStream_t st = as_stream(stream);
     const int nhm = (int)num_layers - 1, Wd = (int)hidden_dim, in = (int)input_dim;
     const size_t n_w = (size_t)Wd * (in + (size_t)Wd * nhm + 16);

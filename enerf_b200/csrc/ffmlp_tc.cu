@@ -1392,9 +1392,407 @@ static int launch_bwd_tma(const __half* grad, const __half* x, const __half* W, 
     return 1;
 }
 
+// ================================================================================================
+// Backward with recomputation (k_tc_bwd_rc): the stored-activation kernels above are bound by HBM — the training
+// forward writes [num_layers, B, 64] fp16 of forward_buffer and the backward reads it back (2.2 + 2.8 GB per step on
+// the bench workload), while re-running the hidden layers of a tile costs a few hundred tensor-core cycles.  This
+// kernel takes only the network input and dL/dy:
+//   F_0 .. F_NH : h_L = relu(h_{L-1} . W_L^T)  — SS MMAs; the epilogue writes h_L (fp16) into a shared-memory tile in the
+//                 128-byte swizzle, which serves three readers without another copy: the next forward MMA (K-major A
+//                 operand), the weight-gradient MMA (MN-major operand) and the ReLU mask of the backward epilogue.
+//   B_0 .. B_S-1: exactly the stages of k_tc_bwd_tma (dgrad with A in TMEM, wgrad into TMEM accumulators).
+// The recomputed activations are bit-identical to what the training forward would have stored (same MMAs, same K
+// order, same rounding point), so the gradients match the stored-activation path.  Input width 32.
+//   a_ready[s] / d_full[s] advance 2*NH+3 phases per tile (one per MMA stage; a_ready's last one = "accumulator read,
+//   slot free for the next tile").
+// ================================================================================================
+template <int NSLOTS, int NH, int PRO>
+__global__ void __launch_bounds__(32 + NSLOTS * 128, 1)
+k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ grad, const __half* __restrict__ W, __half* __restrict__ grad_inputs,
+            float* __restrict__ dW, uint32_t n_tiles, uint32_t B, ProArgs pro) {
+    constexpr int in_dim = 32;
+    constexpr int S = NH + 2;                              // backward stages per tile
+    constexpr int T = 2 * NH + 3;                          // MMA stages per tile (NH+1 forward, S backward)
+    constexpr uint32_t kXBytes = kTile * in_dim * 2;
+    constexpr uint32_t kSlotBytes = 2 * kXBytes + (NH + 1) * kGBytes + kGBytes;     // x ring, h_0..h_NH, G
+    extern __shared__ uint8_t smem_dyn[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    uint8_t* w0s = smem + (size_t)NSLOTS * kSlotBytes;     // [in_dim/8][64][16 B]   (forward layout)
+    uint8_t* whs = w0s + in_dim * 128;                     // NH x [8][64][16 B]
+    uint8_t* wls = whs + NH * 8192;                        // [8][16][16 B]
+    uint64_t* a_ready = reinterpret_cast<uint64_t*>(wls + 2048);
+    uint64_t* d_full = a_ready + NSLOTS;
+    uint64_t* x_full = d_full + NSLOTS;                    // [NSLOTS][2]
+    uint64_t* flush_bar = x_full + 2 * NSLOTS;
+    uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(flush_bar + 1);
+    // per-slot regions: [x0 | x1 | h_0 .. h_NH | G]
+    auto slot_x = [&](int s, uint32_t b) { return smem + (size_t)s * kSlotBytes + (size_t)b * kXBytes; };
+    auto slot_h = [&](int s, int L) { return smem + (size_t)s * kSlotBytes + 2 * kXBytes + (size_t)L * kGBytes; };
+    auto slot_g = [&](int s) { return smem + (size_t)s * kSlotBytes + 2 * kXBytes + (size_t)(NH + 1) * kGBytes; };
+
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    constexpr uint32_t kCols = 512;
+
+    stage_matrix(w0s, W, kW, in_dim, tid, nthreads);
+    for (int j = 0; j < NH; ++j) stage_matrix(whs + j * 8192, W + kW * in_dim + j * kW * kW, kW, kW, tid, nthreads);
+    stage_matrix(wls, W + kW * in_dim + NH * kW * kW, 16, kW, tid, nthreads);
+    if (tid == 0) {
+        for (int s = 0; s < NSLOTS; ++s) {
+            mbar_init(&a_ready[s], 128);
+            mbar_init(&d_full[s], 1);
+            mbar_init(&x_full[2 * s], 1);
+            mbar_init(&x_full[2 * s + 1], 1);
+        }
+        mbar_init(flush_bar, 1);
+        mbar_fence_init();
+        tma_prefetch_desc(&tm_x);
+    }
+    if (warp == 0) tmem_alloc(tmem_base_ptr, kCols);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem0 = *tmem_base_ptr;
+
+    const uint32_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    constexpr uint32_t kAccLast = NSLOTS * kSlotCols, kAccHid = kAccLast + 16, kAcc0 = kAccHid + NH * 64;
+    static_assert(kAcc0 + in_dim <= 512, "TMEM budget");
+
+    if (warp == 0) {
+        // ===================== MMA / TMA issuer: warp-uniform control flow, one elected lane issues =====================
+        const uint32_t tm = __shfl_sync(0xffffffffu, tmem0, 0);
+        const uint32_t sm_b = smem_u32(smem), w0b = smem_u32(w0s), whb = smem_u32(whs), wlb = smem_u32(wls);
+        uint32_t nt[NSLOTS];
+#pragma unroll
+        for (int s = 0; s < NSLOTS; ++s) nt[s] = (my_tiles > (uint32_t)s) ? (my_tiles - s + NSLOTS - 1) / NSLOTS : 0;
+        auto issue_x = [&](int s, uint32_t tl) {               // elected lane only
+            const uint32_t tile = blockIdx.x + ((uint32_t)s + tl * NSLOTS) * gridDim.x;
+            uint64_t* bar = &x_full[2 * s + (tl & 1u)];
+            mbar_arrive_expect_tx(bar, kXBytes);
+            tma_load_2d(sm_b + (uint32_t)s * kSlotBytes + (tl & 1u) * kXBytes, &tm_x, 0, (int32_t)(tile * kTile), bar);
+        };
+#pragma unroll
+        for (int s = 0; s < NSLOTS; ++s) {
+            if (nt[s] > 0 && elect_one()) issue_x(s, 0);
+            __syncwarp();
+        }
+        constexpr uint32_t idF = idesc_f16(kTile, 64, false, false);
+        constexpr uint32_t idD64 = idesc_f16(kTile, 64, false, true), idDx = idesc_f16(kTile, (uint32_t)in_dim, false, true);
+        constexpr uint32_t idWl = idesc_f16(64, 16, true, true), idWh = idesc_f16(64, 64, true, true), idW0 = idesc_f16(64, (uint32_t)in_dim, true, true);
+        for (uint32_t tl = 0; tl < nt[0]; ++tl) {
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+#pragma unroll
+                for (int s = 0; s < NSLOTS; ++s) {
+                    if (tl >= nt[s]) continue;
+                    const uint32_t tb = tl * T;                          // phase index of this tile's first stage
+                    const uint32_t d_t = tm + s * kSlotCols, a_t = d_t + 64;
+                    const uint32_t slot_b = sm_b + (uint32_t)s * kSlotBytes;
+                    const uint32_t xb = slot_b + (tl & 1u) * kXBytes;
+                    const uint32_t h0b = slot_b + 2 * kXBytes;           // h_L at h0b + L*kGBytes
+                    const uint32_t g_s = h0b + (uint32_t)(NH + 1) * kGBytes;
+                    if (t == 0) {
+                        // ---- F_0: h_0 pre-activation = x . W_0^T
+                        if (tl > 0) mbar_wait(&a_ready[s], (tb - 1u) & 1u);              // the previous tile's dx accumulator has been read
+                        mbar_wait(&x_full[2 * s + (tl & 1u)], (tl >> 1) & 1u);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            if (tl + 1 < nt[s]) issue_x(s, tl + 1);                     // the other input buffer belonged to the finished tile tl-1
+#pragma unroll
+                            for (int k = 0; k < in_dim / 16; ++k)
+                                mma_ss(d_t, smem_desc_sw(xb + k * 32, 64), smem_desc(w0b + k * 2 * (kW * 16), kW * 16, 128), idF, k > 0);
+                            tc_commit(&d_full[s]);
+                        }
+                        __syncwarp();
+                    } else if (t <= NH) {
+                        // ---- F_t: h_t pre-activation = h_{t-1} . W_t^T   (A = the swizzled activation tile, K-major)
+                        mbar_wait(&a_ready[s], (tb + (uint32_t)(t - 1)) & 1u);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint32_t ab = h0b + (uint32_t)(t - 1) * kGBytes, wb = whb + (uint32_t)(t - 1) * 8192u;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) mma_ss(d_t, smem_desc_sw(ab + k * 32, 128), smem_desc(wb + k * 2 * (kW * 16), kW * 16, 128), idF, k > 0);
+                            tc_commit(&d_full[s]);
+                        }
+                        __syncwarp();
+                    } else {
+                        // ---- B_k: backward stage k (see k_tc_bwd_tma); its activation tile is h_{NH-k}, or x for the last stage
+                        const int k = t - (NH + 1);
+                        mbar_wait(&a_ready[s], (tb + (uint32_t)(t - 1)) & 1u);
+                        tc_fence_after();
+                        const bool acc = !(tl == 0 && s == 0);           // the very first issue on an accumulator overwrites it
+                        if (elect_one()) {
+                            if (k == 0) {
+                                mma_ts(d_t, a_t, smem_desc(wlb, 128, 16 * 16), idD64, false);
+                                const uint32_t h_s = h0b + (uint32_t)NH * kGBytes;
+#pragma unroll
+                                for (int ks = 0; ks < 8; ++ks)
+                                    mma_ss(tm + kAccLast, smem_desc_sw(h_s + ks * 2048, 128), smem_desc(g_s + ks * 256, 128, 2048), idWl, acc || ks > 0);
+                            } else if (k <= NH) {
+                                const uint32_t wj = whb + (uint32_t)(NH - k) * 8192u;
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) mma_ts(d_t, a_t + ks * 8, smem_desc(wj + ks * 256, 128, 64 * 16), idD64, ks > 0);
+                                const uint32_t h_s = h0b + (uint32_t)(NH - k) * kGBytes;
+#pragma unroll
+                                for (int ks = 0; ks < 8; ++ks)
+                                    mma_ss(tm + kAccHid + (uint32_t)(NH - k) * 64u, smem_desc(g_s + ks * 256, 128, 2048), smem_desc_sw(h_s + ks * 2048, 128), idWh,
+                                           acc || ks > 0);
+                            } else {
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) mma_ts(d_t, a_t + ks * 8, smem_desc(w0b + ks * 256, 128, 64 * 16), idDx, ks > 0);
+#pragma unroll
+                                for (int ks = 0; ks < 8; ++ks)
+                                    mma_ss(tm + kAcc0, smem_desc(g_s + ks * 256, 128, 2048), smem_desc_sw(xb + ks * 16 * 64, 64), idW0, acc || ks > 0);
+                            }
+                            tc_commit(&d_full[s]);
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+        if (elect_one()) tc_commit(flush_bar);
+        __syncwarp();
+    } else {
+        // ===================== epilogue warps (4 per slot) =====================
+        const int s = (warp - 1) >> 2;
+        const int q = warp & 3;
+        const int r_in_tile = q * 32 + lane;
+        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+        const uint32_t d_t = tmem0 + lane_sel + s * kSlotCols, a_t = d_t + 64;
+        uint8_t* g_tile = slot_g(s);
+
+        int4 pv0 = make_int4(0, 0, 0, 0), pv1 = make_int4(0, 0, 0, 0);
+        float pf[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        auto fetch = [&](size_t row) {                     // raw dL/dy operands of a row, one tile ahead
+            if (PRO == 0) {
+                const int4* src = reinterpret_cast<const int4*>(grad + row * 16);
+                pv0 = __ldg(src);
+                pv1 = __ldg(src + 1);
+            } else if (PRO == 1) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (c < pro.n_ch) {
+                        pf[c] = __ldg(pro.rgb + row * pro.n_ch + c);
+                        pf[4 + c] = __ldg(pro.g_rgb + row * pro.n_ch + c);
+                    }
+            } else {
+                pf[0] = __ldg(pro.sigma + row);
+                pf[1] = __ldg(pro.g_sigma + row);
+                const int4* src = reinterpret_cast<const int4*>(pro.dcin + row * 32 + 16);
+                pv0 = __ldg(src);
+                pv1 = __ldg(src + 1);
+            }
+        };
+        if ((uint32_t)s < my_tiles) fetch(((size_t)blockIdx.x + (size_t)s * gridDim.x) * kTile + r_in_tile);
+
+        uint32_t tl = 0;
+        for (uint32_t j = s; j < my_tiles; j += NSLOTS, ++tl) {
+            const size_t tile = (size_t)blockIdx.x + (size_t)j * gridDim.x;
+            const size_t row = tile * kTile + r_in_tile;
+            const uint32_t tb = tl * T;
+            // ---- E(F_L), L = 0 .. NH: h_L = relu(D) -> swizzled activation tile; the last one also prepares dy
+#pragma unroll
+            for (int L = 0; L <= NH; ++L) {
+                mbar_wait(&d_full[s], (tb + (uint32_t)L) & 1u);
+                tc_fence_after();
+                uint8_t* hb = slot_h(s, L);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t acc[32];
+                    tmem_ld32(d_t + h * 32, acc);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        uint32_t p[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) p[e] = pack2(relu(__uint_as_float(acc[8 * v + 2 * e])), relu(__uint_as_float(acc[8 * v + 2 * e + 1])));
+                        *reinterpret_cast<int4*>(hb + sw_off((uint32_t)r_in_tile, (uint32_t)(h * 4 + v), 128)) = make_int4((int)p[0], (int)p[1], (int)p[2], (int)p[3]);
+                    }
+                }
+                if (L == NH) {
+                    // dy -> TMEM A + dy tile (G buffer): E_0 of the backward
+                    int4 v0, v1;
+                    if (PRO == 0) {
+                        v0 = pv0;
+                        v1 = pv1;
+                    } else if (PRO == 1) {
+                        float dyv[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            if (c < pro.n_ch) dyv[c] = f16_round(pf[4 + c]) * (1.0f - pf[c]) * pf[c];
+                        v0 = make_int4((int)pack2(dyv[0], dyv[1]), (int)pack2(dyv[2], dyv[3]), 0, 0);
+                        v1 = make_int4(0, 0, 0, 0);
+                    } else {
+                        const float sg = fminf(fmaxf(pf[0], 3.0590232050182579e-07f), 3269017.3724721107f);   // exp(-15), exp(15)
+                        const __half d0 = __float2half_rn(pf[1] * sg);
+                        const uint32_t w[8] = {(uint32_t)pv0.x, (uint32_t)pv0.y, (uint32_t)pv0.z, (uint32_t)pv0.w,
+                                               (uint32_t)pv1.x, (uint32_t)pv1.y, (uint32_t)pv1.z, (uint32_t)pv1.w};
+                        uint32_t o[8];
+                        o[0] = (uint32_t)__half_as_ushort(d0) | (w[0] << 16);
+#pragma unroll
+                        for (int e = 1; e < 8; ++e) o[e] = (w[e - 1] >> 16) | (w[e] << 16);
+                        v0 = make_int4((int)o[0], (int)o[1], (int)o[2], (int)o[3]);
+                        v1 = make_int4((int)o[4], (int)o[5], (int)o[6], (int)o[7]);
+                    }
+                    const uint32_t r8[8] = {(uint32_t)v0.x, (uint32_t)v0.y, (uint32_t)v0.z, (uint32_t)v0.w,
+                                            (uint32_t)v1.x, (uint32_t)v1.y, (uint32_t)v1.z, (uint32_t)v1.w};
+                    tmem_st8(a_t, r8);
+                    *reinterpret_cast<int4*>(g_tile + 0 * 2048 + r_in_tile * 16) = v0;
+                    *reinterpret_cast<int4*>(g_tile + 1 * 2048 + r_in_tile * 16) = v1;
+                    tc_wait_st();
+                }
+                fence_proxy_async_smem();
+                tc_fence_before();
+                mbar_arrive(&a_ready[s]);
+                if (L == NH && j + NSLOTS < my_tiles) fetch(((size_t)blockIdx.x + (size_t)(j + NSLOTS) * gridDim.x) * kTile + r_in_tile);
+            }
+            // ---- E_k, k = 1 .. S-1: g = D * relu'(h_{NH-(k-1)}) -> TMEM A + G tile
+#pragma unroll
+            for (int k = 1; k < S; ++k) {
+                mbar_wait(&d_full[s], (tb + (uint32_t)(NH + k)) & 1u);
+                tc_fence_after();
+                const uint8_t* hrow = slot_h(s, NH - (k - 1));
+                int4 hv[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) hv[c] = *reinterpret_cast<const int4*>(hrow + sw_off((uint32_t)r_in_tile, (uint32_t)c, 128));
+                const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t acc[32];
+                    tmem_ld32(d_t + h * 32, acc);
+                    tc_wait_ld();
+                    uint32_t p[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const uint32_t hw = reinterpret_cast<const uint32_t*>(hv)[h * 16 + e];
+                        const unsigned m = __hgt2_mask(*reinterpret_cast<const __half2*>(&hw), zero2);
+                        p[e] = pack2(__uint_as_float(acc[2 * e]), __uint_as_float(acc[2 * e + 1])) & m;
+                    }
+                    tmem_st16(a_t + h * 16, p);
+#pragma unroll
+                    for (int v = 0; v < 4; ++v)
+                        *reinterpret_cast<int4*>(g_tile + (h * 4 + v) * 2048 + r_in_tile * 16) =
+                            make_int4((int)p[4 * v], (int)p[4 * v + 1], (int)p[4 * v + 2], (int)p[4 * v + 3]);
+                }
+                tc_wait_st();
+                fence_proxy_async_smem();
+                tc_fence_before();
+                mbar_arrive(&a_ready[s]);
+            }
+            // ---- E_S: dx
+            mbar_wait(&d_full[s], (tb + (uint32_t)(T - 1)) & 1u);
+            tc_fence_after();
+            {
+                uint32_t acc0[16], acc1[16];
+                tmem_ld16(d_t, acc0);
+                tmem_ld16(d_t + 16, acc1);
+                tc_wait_ld();
+                tc_fence_before();
+                mbar_arrive(&a_ready[s]);                  // accumulator read: the slot can start its next tile
+                if (grad_inputs) {
+                    uint32_t p[16];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        p[e] = pack2(__uint_as_float(acc0[2 * e]), __uint_as_float(acc0[2 * e + 1]));
+                        p[8 + e] = pack2(__uint_as_float(acc1[2 * e]), __uint_as_float(acc1[2 * e + 1]));
+                    }
+                    int4* dst = reinterpret_cast<int4*>(grad_inputs + row * in_dim);
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) dst[v] = make_int4((int)p[4 * v], (int)p[4 * v + 1], (int)p[4 * v + 2], (int)p[4 * v + 3]);
+                }
+            }
+        }
+
+        // ---- flush the weight-gradient accumulators (slot 0's four warps; M = 64 -> lanes 0..15 of each quarter)
+        if (s == 0 && my_tiles > 0) {
+            mbar_wait(flush_bar, 0);
+            tc_fence_after();
+            const int m = q * 16 + lane;
+            const uint32_t base = tmem0 + lane_sel;
+            float* dW0 = dW;
+            float* dWh = dW + kW * in_dim;
+            float* dWl = dWh + (size_t)NH * kW * kW;
+            {
+                uint32_t acc[16];
+                tmem_ld16(base + kAccLast, acc);
+                tc_wait_ld();
+                if (lane < 16)
+#pragma unroll
+                    for (int nn = 0; nn < 16; ++nn) atomicAdd(dWl + nn * kW + m, __uint_as_float(acc[nn]));
+            }
+            for (int jj = 0; jj < NH; ++jj)
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t acc[16];
+                    tmem_ld16(base + kAccHid + jj * 64 + c * 16, acc);
+                    tc_wait_ld();
+                    if (lane < 16) {
+                        float* dst = dWh + (size_t)jj * kW * kW + (size_t)m * kW + c * 16;
+#pragma unroll
+                        for (int v = 0; v < 4; ++v)
+                            red_add_v4(dst + 4 * v, __uint_as_float(acc[4 * v]), __uint_as_float(acc[4 * v + 1]), __uint_as_float(acc[4 * v + 2]),
+                                       __uint_as_float(acc[4 * v + 3]));
+                    }
+                }
+            for (int c = 0; c < in_dim / 16; ++c) {
+                uint32_t acc[16];
+                tmem_ld16(base + kAcc0 + c * 16, acc);
+                tc_wait_ld();
+                if (lane < 16) {
+                    float* dst = dW0 + (size_t)m * in_dim + c * 16;
+#pragma unroll
+                    for (int v = 0; v < 4; ++v)
+                        red_add_v4(dst + 4 * v, __uint_as_float(acc[4 * v]), __uint_as_float(acc[4 * v + 1]), __uint_as_float(acc[4 * v + 2]),
+                                   __uint_as_float(acc[4 * v + 3]));
+                }
+            }
+            tc_fence_before();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem0, kCols);
+}
+
+template <int NSLOTS, int NH, int PRO>
+static int launch_bwd_rc_n(const TmaDesc& tx, const __half* grad, const __half* W, __half* grad_inputs, float* dW, uint32_t B, ProArgs pro,
+                           cudaStream_t st, const char* name) {
+    constexpr size_t kSlot = 2 * (size_t)kTile * 32 * 2 + (size_t)(NH + 2) * kGBytes;
+    size_t smem = 1024 + NSLOTS * kSlot + 32 * 128 + (size_t)NH * 8192 + 2048 + (4 * NSLOTS + 1) * 8 + 16;
+    if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: it allocates all 512 TMEM columns
+    if (smem > 227 * 1024) return 1;
+    static bool configured = false;
+    if (!configured) {
+        ENERF_CUDA(cudaFuncSetAttribute(k_tc_bwd_rc<NSLOTS, NH, PRO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
+        configured = true;
+    }
+    const uint32_t n_tiles = B / kTile;
+    const uint32_t grid = n_tiles < (uint32_t)kNumSM ? n_tiles : (uint32_t)kNumSM;
+    k_tc_bwd_rc<NSLOTS, NH, PRO><<<grid, 32 + NSLOTS * 128, smem, st>>>(tx, grad, W, grad_inputs, dW, n_tiles, B, pro);
+    ENERF_CHECK_LAUNCH(name);
+    return 0;
+}
+
+// backward from the network input alone (hidden activations recomputed per tile); 1 = not applicable
+template <int PRO>
+static int launch_bwd_rc(const __half* grad, const __half* x, const __half* W, __half* grad_inputs, float* dW, uint32_t B, int in_dim, int n_hidden_mm,
+                         ProArgs pro, cudaStream_t st, const char* name) {
+    if (in_dim != 32 || (n_hidden_mm != 1 && n_hidden_mm != 2) || (uint64_t)B >= (1ull << 31)) return 1;
+    TmaDesc tx;
+    if (!make_tmap_rows(&tx, x, B, 32, kTile)) return 1;
+    if (n_hidden_mm == 1) return launch_bwd_rc_n<3, 1, PRO>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
+    return launch_bwd_rc_n<2, 2, PRO>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
+}
+
 int tc_backward(const __half* grad, const __half* x, const __half* W, const __half* fwd_buf, __half* bwd_buf, __half* grad_inputs, float* dW,
                 uint32_t B, int in_dim, int n_hidden_mm, cudaStream_t st) {
     ProArgs none = {nullptr, nullptr, 0, nullptr, nullptr, nullptr};
+    if (!fwd_buf) {
+        const int rc = launch_bwd_rc<0>(grad, x, W, grad_inputs, dW, B, in_dim, n_hidden_mm, none, st, "ffmlp_backward");
+        if (rc == 1) set_error("ffmlp_backward: forward_buffer may only be NULL (recomputation) for 32 inputs and 2 or 3 layers on the tcgen05 path");
+        return rc == 1 ? -2 : rc;
+    }
     if (!bwd_buf) {
         const int rc = launch_bwd_tma<0>(grad, x, W, fwd_buf, grad_inputs, dW, B, in_dim, n_hidden_mm, none, st, "ffmlp_backward");
         if (rc != 1) return rc;
@@ -1404,6 +1802,11 @@ int tc_backward(const __half* grad, const __half* x, const __half* W, const __ha
 int tc_backward_rgb(const float* g_rgb, const float* rgb, int n_ch, const __half* cin, const __half* W, const __half* fwd_buf, __half* dcin, float* dW,
                     uint32_t B, int n_hidden_mm, cudaStream_t st) {
     ProArgs p = {g_rgb, rgb, n_ch, nullptr, nullptr, nullptr};
+    if (!fwd_buf) {
+        const int rc = launch_bwd_rc<1>(nullptr, cin, W, dcin, dW, B, 32, n_hidden_mm, p, st, "field_color_backward");
+        if (rc == 1) set_error("field_color_backward: recomputation needs 2 or 3 layers");
+        return rc == 1 ? -2 : rc;
+    }
     {
         const int rc = launch_bwd_tma<1>(nullptr, cin, W, fwd_buf, dcin, dW, B, 32, n_hidden_mm, p, st, "field_color_backward");
         if (rc != 1) return rc;
@@ -1413,6 +1816,11 @@ int tc_backward_rgb(const float* g_rgb, const float* rgb, int n_ch, const __half
 int tc_backward_sigma(const float* g_sigma, const float* sigma, const __half* dcin, const __half* feat, const __half* W, const __half* fwd_buf,
                       __half* dfeat, float* dW, uint32_t B, int n_hidden_mm, cudaStream_t st) {
     ProArgs p = {nullptr, nullptr, 0, g_sigma, sigma, dcin};
+    if (!fwd_buf) {
+        const int rc = launch_bwd_rc<2>(nullptr, feat, W, dfeat, dW, B, 32, n_hidden_mm, p, st, "field_sigma_backward");
+        if (rc == 1) set_error("field_sigma_backward: recomputation needs 2 or 3 layers");
+        return rc == 1 ? -2 : rc;
+    }
     {
         const int rc = launch_bwd_tma<2>(nullptr, feat, W, fwd_buf, dfeat, dW, B, 32, n_hidden_mm, p, st, "field_sigma_backward");
         if (rc != 1) return rc;

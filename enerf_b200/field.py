@@ -20,6 +20,12 @@ def eligible(feat, dirs, hidden_dim, hidden_dim_color, in_dim, in_dim_color, geo
             and activation == 0 and dirs.shape[0] == feat.shape[0])
 
 
+# True (default): the training forward stores nothing but its inputs and outputs; the backward kernels recompute the hidden
+# activations of every 128-sample tile on the tensor cores (bit-identical values).  False: store / reload forward_buffer
+# (2.2 GB written + 2.8 GB read per step on the bench workload, which made the MLP kernels HBM-bound).
+RECOMPUTE = True
+
+
 class _FusedField(Function):
     @staticmethod
     def forward(ctx, feat, dirs, w_sigma, w_color, nl_sigma, nl_color, n_ch, training):
@@ -31,18 +37,22 @@ class _FusedField(Function):
         sigma = torch.empty(S, dtype=torch.float32, device=dev)
         cin = torch.empty(S, 32, dtype=torch.float16, device=dev)
         rgb = torch.empty(S, n_ch, dtype=torch.float32, device=dev)
-        fb_s = torch.empty(nl_sigma, S, 64, dtype=torch.float16, device=dev) if training else None
-        fb_c = torch.empty(nl_color, S, 64, dtype=torch.float16, device=dev) if training else None
+        store = training and not RECOMPUTE
+        fb_s = torch.empty(nl_sigma, S, 64, dtype=torch.float16, device=dev) if store else None
+        fb_c = torch.empty(nl_color, S, 64, dtype=torch.float16, device=dev) if store else None
         _lib.call("enerf_field_sigma_forward", ptr(feat), ptr(ws), ptr(dirs), S, nl_sigma, ptr(fb_s), ptr(sigma), ptr(cin), stream())
         _lib.call("enerf_field_color_forward", ptr(cin), ptr(wc), S, nl_color, n_ch, ptr(fb_c), ptr(rgb), stream())
         if training:
-            ctx.save_for_backward(feat, ws, wc, sigma, cin, rgb, fb_s, fb_c)
+            saved = [feat, ws, wc, sigma, cin, rgb] + ([fb_s, fb_c] if store else [])
+            ctx.save_for_backward(*saved)
             ctx.meta = (nl_sigma, nl_color, n_ch, w_sigma.dtype, w_color.dtype)
         return sigma, rgb
 
     @staticmethod
     def backward(ctx, g_sigma, g_rgb):
-        feat, ws, wc, sigma, cin, rgb, fb_s, fb_c = ctx.saved_tensors
+        saved = ctx.saved_tensors
+        feat, ws, wc, sigma, cin, rgb = saved[:6]
+        fb_s, fb_c = (saved[6], saved[7]) if len(saved) == 8 else (None, None)
         nl_sigma, nl_color, n_ch, dt_s, dt_c = ctx.meta
         S = feat.shape[0]
         dev = feat.device

@@ -160,7 +160,9 @@ int enerf_ffmlp_inference(const uint16_t* inputs, const uint16_t* weights, uint3
                           uint32_t num_layers, uint32_t activation, uint32_t output_activation,
                           uint16_t* inference_buffer, uint16_t* outputs, void* stream);
 /* ffmlp.h:11 ffmlp_backward; ffmlp.cu:742-894.  backward_buffer [num_layers,B,hidden] may be
- * NULL (the activation gradients then never leave the SM).  grad_weights: fp16 when
+ * NULL (the activation gradients then never leave the SM).  forward_buffer may be NULL for 32-input,
+ * 64-wide ReLU networks with 2 or 3 layers: the kernel then recomputes the hidden activations of each
+ * 128-sample tile from `inputs` (bit-identical to the stored ones) instead of reading them from HBM.  grad_weights: fp16 when
  * grad_weights_dtype == ENERF_F16 (reference), fp32 flat buffer when ENERF_F32; it is
  * overwritten, not accumulated.  `scratch` = caller-owned fp32 buffer with as many elements as
  * `weights` (used as the reduction target; may alias grad_weights when that is fp32). */
@@ -192,7 +194,9 @@ int enerf_free_splitk(void);
  *                    cin = [SH_4(fp16(dir)) | h[1:16] | 0]   (shencoder + torch.cat + zeros_like)
  *   colour-net head: rgb[c] = sigmoid(fp16(color_net(cin))[c]), c < n_ch, as fp32
  *   backward       : the prologues apply sigmoid' / trunc_exp' and pick the geo_feat columns.
- * forward_buffer [num_layers,B,64] may be NULL for inference.  grad_weights: fp32, overwritten. */
+ * forward_buffer [num_layers,B,64] may be NULL in the forward calls (inference, or training with
+ * recomputation) and in the backward calls (the hidden activations are then recomputed per tile from
+ * cin / feat; same gradients, no forward_buffer traffic).  grad_weights: fp32, overwritten. */
 int enerf_field_sigma_forward(const uint16_t* feat, const uint16_t* weights, const float* dirs, uint32_t B,
                               uint32_t num_layers, uint16_t* forward_buffer, float* sigma, uint16_t* cin,
                               void* stream);

@@ -249,6 +249,22 @@ def test_fused_field_matches_module_chain(n_ch):
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
         s2, r2 = model(x, d)
     assert torch.allclose(s2, a[0], rtol=1e-6) and torch.allclose(r2, a[1], atol=1e-6)
+    # stored activations (forward_buffer) vs recomputation in the backward kernels (the default): identical values and
+    # activation gradients, weight gradients equal up to fp32 summation order
+    from enerf_b200 import field
+    model.train()
+    try:
+        field.RECOMPUTE = False
+        model.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.float16):
+            sigma, rgb = model(x, d)
+        ((sigma * gs).sum() + (rgb.float() * gr).sum()).backward()
+    finally:
+        field.RECOMPUTE = True
+    assert torch.equal(sigma.detach().float(), a[0]) and torch.equal(rgb.detach().float(), a[1])
+    assert torch.equal(model.encoder.embeddings.grad, a[2]) or torch.allclose(model.encoder.embeddings.grad, a[2], rtol=1e-4, atol=1e-9)
+    for got, want in ((model.sigma_net.weights.grad, a[3]), (model.color_net.weights.grad, a[4])):
+        assert float((got - want).abs().max()) <= 1e-4 * float(want.abs().max()) + 1e-12
 
 
 def test_psnr_parity_tiny_scene():

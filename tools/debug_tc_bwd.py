@@ -22,16 +22,18 @@ for B in (128, 256, 128 * 148 * 3 + 128 * 5):
             fb = torch.empty(nl, B, 64, device=dev, dtype=torch.half)
             FB.ffmlp_forward(x, w, B, 32, 16, 64, nl, 0, 6, fb, out)
             res = {}
-            for path in (2, 0):
-                _lib.call("enerf_ffmlp_set_path", path)
+            for path in (2, 0, "rc"):
+                _lib.call("enerf_ffmlp_set_path", 0 if path == "rc" else path)
                 gi = torch.zeros(B, 32, device=dev, dtype=torch.half)
                 gw = torch.zeros(nw, device=dev, dtype=torch.float32)
-                FB.ffmlp_backward(g, x, w, fb, B, 32, 16, 64, nl, 0, 6, True, None, gi, gw)
+                FB.ffmlp_backward(g, x, w, None if path == "rc" else fb, B, 32, 16, 64, nl, 0, 6, True, None, gi, gw)
                 torch.cuda.synchronize()
                 res[path] = (gi.float().cpu(), gw.cpu())
             _lib.call("enerf_ffmlp_set_path", 0)
             gi_ref, gw_ref = res[2]
             gi_new, gw_new = res[0]
+            gi_rc, gw_rc = res["rc"]
+            print(f"   recompute vs stored (TMA): gi err {float((gi_rc - gi_new).abs().max()):.4g}  gw err {float((gw_rc - gw_new).abs().max()):.4g} / {float(gw_new.abs().max()):.4g}")
             seg = [("W0", 0, 64 * 32)] + [(f"Wh{j}", 64 * 32 + j * 4096, 64 * 32 + (j + 1) * 4096) for j in range(nl - 1)] + [("Wl", nw - 1024, nw)]
             msg = f"B={B} nl={nl} positive={positive}: gi err {float((gi_new - gi_ref).abs().max()):.4g} / {float(gi_ref.abs().max()):.4g}"
             for name, a, b in seg:
