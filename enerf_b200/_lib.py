@@ -10,7 +10,7 @@ import re
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libenerf_b200.so")
+LIB_PATH = os.environ.get("ENERF_B200_LIB") or os.path.join(_HERE, "libenerf_b200.so")     # override: instrumented builds (tools/)
 HEADER_PATH = os.path.join(_HERE, "..", "include", "enerf_b200.h")
 
 F32, F16 = 0, 1

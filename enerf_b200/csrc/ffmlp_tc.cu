@@ -27,6 +27,26 @@ static constexpr int kTile = 128;        // samples per tile = UMMA M
 static constexpr int kSlotCols = 96;     // TMEM columns per slot: D (64, fp32) + A (32 = 64 fp16)
 
 static constexpr int kGBytes = 128 * 64 * 2;    // one 128-sample x 64-wide fp16 tile
+
+// Optional cycle trace (tools/build_trace.sh builds a second library with -DENERF_TC_TRACE; the product build compiles it out):
+// CTA 0 appends (tag, clock64) pairs of slot 0's issuing warp and first epilogue thread to a global buffer.
+#ifdef ENERF_TC_TRACE
+__device__ unsigned long long* g_trace = nullptr;
+// each tracing thread owns a region of the buffer and a private counter (no atomics: a stamp costs a store and a clock read)
+#define ENERF_TRACE_DECL(region) unsigned int trace_n__ = 0; const unsigned int trace_base__ = (region) * 4096u
+#define ENERF_TRACE(tag)                                                                        \
+    do {                                                                                        \
+        if (g_trace && blockIdx.x == 0 && trace_n__ < 2048u) {                                  \
+            g_trace[2 * (trace_base__ + trace_n__)] = (unsigned long long)(tag);                \
+            g_trace[2 * (trace_base__ + trace_n__) + 1] = clock64();                            \
+        }                                                                                       \
+        ++trace_n__;                                                                            \
+    } while (0)
+#else
+#define ENERF_TRACE_DECL(region) do { } while (0)
+#define ENERF_TRACE(tag) do { } while (0)
+#endif
+
 struct alignas(64) TmaDesc { uint8_t bytes[128]; };     // CUtensorMap (opaque in device code; encoded on the host)
 
 // ---- host: tensor maps (driver entry point resolved through the runtime; no link-time libcuda dependency)
@@ -353,7 +373,7 @@ k_tc_fwd_tma(const __grid_constant__ TmaDesc tm_x, const __grid_constant__ TmaDe
     stage_matrix(wls, W + kW * IN_DIM + NH * kW * kW, 16, kW, tid, nthreads);
     if (tid == 0) {
         for (int s = 0; s < NSLOTS; ++s) {
-            mbar_init(&a_ready[s], 128);
+            mbar_init(&a_ready[s], 4);      // one arrival per epilogue warp
             mbar_init(&d_full[s], 1);
             mbar_init(&x_full[2 * s], 1);
             mbar_init(&x_full[2 * s + 1], 1);
@@ -465,7 +485,7 @@ k_tc_fwd_tma(const __grid_constant__ TmaDesc tm_x, const __grid_constant__ TmaDe
                         tc_wait_ld();
                         uint32_t p[16];
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) p[e] = pack2(relu(__uint_as_float(acc[2 * e])), relu(__uint_as_float(acc[2 * e + 1])));
+                        for (int e = 0; e < 16; ++e) p[e] = pack2_relu(__uint_as_float(acc[2 * e]), __uint_as_float(acc[2 * e + 1]));
                         tmem_st16(a_t + h * 16, p);
                         if (TRAIN) {
 #pragma unroll
@@ -477,7 +497,7 @@ k_tc_fwd_tma(const __grid_constant__ TmaDesc tm_x, const __grid_constant__ TmaDe
                     tc_wait_st();
                     if (TRAIN) fence_proxy_async_smem();
                     tc_fence_before();
-                    mbar_arrive(&a_ready[s]);
+                    warp_arrive(&a_ready[s], lane);
                     if (TRAIN) {
                         // the store issued one layer ago has long finished reading its buffer; waiting for it here (before the barrier)
                         // tells every thread of the slot that the buffer they will fill NEXT is free
@@ -494,7 +514,7 @@ k_tc_fwd_tma(const __grid_constant__ TmaDesc tm_x, const __grid_constant__ TmaDe
                     tmem_ld16(d_t, acc);
                     tc_wait_ld();
                     tc_fence_before();
-                    mbar_arrive(&a_ready[s]);              // accumulator read: the slot can start its next tile
+                    warp_arrive(&a_ready[s], lane);              // accumulator read: the slot can start its next tile
                     if (HEAD == 0) {
                         // 32-byte output rows: two 16-byte stores per lane (consecutive lanes -> consecutive rows)
                         int4* o = reinterpret_cast<int4*>(out + row * 16);
@@ -1039,7 +1059,7 @@ k_tc_bwd_tma(const __grid_constant__ TmaDesc tm_h, const __grid_constant__ TmaDe
     stage_matrix(wls, W + kW * in_dim + NH * kW * kW, 16, kW, tid, nthreads);
     if (tid == 0) {
         for (int s = 0; s < NSLOTS; ++s) {
-            mbar_init(&a_ready[s], 128);
+            mbar_init(&a_ready[s], 4);      // one arrival per epilogue warp
             mbar_init(&d_full[s], 1);
             for (int r = 0; r < RING; ++r) mbar_init(&h_full[RING * s + r], 1);
         }
@@ -1222,7 +1242,7 @@ k_tc_bwd_tma(const __grid_constant__ TmaDesc tm_h, const __grid_constant__ TmaDe
                 tc_wait_st();
                 fence_proxy_async_smem();
                 tc_fence_before();
-                mbar_arrive(&a_ready[s]);
+                warp_arrive(&a_ready[s], lane);
                 if (j + NSLOTS < my_tiles) fetch(((size_t)blockIdx.x + (size_t)(j + NSLOTS) * gridDim.x) * kTile + r_in_tile);
             }
             // ---- E_k, k = 1 .. S-1: g = D * relu'(h of stage k-1) -> TMEM A + G tile
@@ -1237,11 +1257,13 @@ k_tc_bwd_tma(const __grid_constant__ TmaDesc tm_h, const __grid_constant__ TmaDe
 #pragma unroll
                 for (int c = 0; c < 8; ++c) hv[c] = *reinterpret_cast<const int4*>(hrow + sw_off((uint32_t)r_in_tile, (uint32_t)c, 128));
                 const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
+                uint32_t acc2[2][32];
+                tmem_ld32(d_t, acc2[0]);
+                tmem_ld32(d_t + 32, acc2[1]);
+                tc_wait_ld();
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    uint32_t acc[32];
-                    tmem_ld32(d_t + h * 32, acc);
-                    tc_wait_ld();
+                    const uint32_t (&acc)[32] = acc2[h];
                     uint32_t p[16];
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
@@ -1258,7 +1280,7 @@ k_tc_bwd_tma(const __grid_constant__ TmaDesc tm_h, const __grid_constant__ TmaDe
                 tc_wait_st();
                 fence_proxy_async_smem();
                 tc_fence_before();
-                mbar_arrive(&a_ready[s]);
+                warp_arrive(&a_ready[s], lane);
             }
             // ---- E_S: dx
             mbar_wait(&d_full[s], (tl * S + (uint32_t)(S - 1)) & 1u);
@@ -1330,6 +1352,16 @@ k_tc_bwd_tma(const __grid_constant__ TmaDesc tm_h, const __grid_constant__ TmaDe
     if (warp == 0) tmem_dealloc(tmem0, kCols);
 }
 
+#ifdef ENERF_TC_TRACE
+}  // namespace tcm
+}  // namespace enerf
+extern "C" int enerf_debug_set_trace(unsigned long long* buf) {
+    cudaMemcpyToSymbol(enerf::tcm::g_trace, &buf, sizeof(buf));
+    return 0;
+}
+namespace enerf {
+namespace tcm {
+#endif
 static int g_bwd_tma = -1;    // -1: read ENERF_TC_BWD_TMA (default on); 0: k_tc_bwd; 1: k_tc_bwd_tma
 static int g_bwd_slots = 0;   // 0: read ENERF_TC_BWD_SLOTS (default 3)
 static int g_bwd_ring = 0;    // 0: read ENERF_TC_BWD_RING (default 2)
@@ -1406,7 +1438,7 @@ static int launch_bwd_tma(const __half* grad, const __half* x, const __half* W, 
 //   a_ready[s] / d_full[s] advance 2*NH+3 phases per tile (one per MMA stage; a_ready's last one = "accumulator read,
 //   slot free for the next tile").
 // ================================================================================================
-template <int NSLOTS, int NH, int PRO>
+template <int NSLOTS, int NH, int PRO, bool GD>
 __global__ void __launch_bounds__(32 + NSLOTS * 128, 1)
 k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ grad, const __half* __restrict__ W, __half* __restrict__ grad_inputs,
             float* __restrict__ dW, uint32_t n_tiles, uint32_t B, ProArgs pro) {
@@ -1414,7 +1446,10 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
     constexpr int S = NH + 2;                              // backward stages per tile
     constexpr int T = 2 * NH + 3;                          // MMA stages per tile (NH+1 forward, S backward)
     constexpr uint32_t kXBytes = kTile * in_dim * 2;
-    constexpr uint32_t kSlotBytes = 2 * kXBytes + (NH + 1) * kGBytes + kGBytes;     // x ring, h_0..h_NH, G
+    // GD: two G tiles per slot.  The dgrad of a stage is then committed on its own, so the next epilogue (which writes the other
+    // G tile) overlaps the stage's eight weight-gradient MMAs instead of waiting for them.
+    constexpr int NG = GD ? 2 : 1;
+    constexpr uint32_t kSlotBytes = 2 * kXBytes + (NH + 1) * kGBytes + NG * kGBytes;     // x ring, h_0..h_NH, G tile(s)
     extern __shared__ uint8_t smem_dyn[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     uint8_t* w0s = smem + (size_t)NSLOTS * kSlotBytes;     // [in_dim/8][64][16 B]   (forward layout)
@@ -1428,7 +1463,7 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
     // per-slot regions: [x0 | x1 | h_0 .. h_NH | G]
     auto slot_x = [&](int s, uint32_t b) { return smem + (size_t)s * kSlotBytes + (size_t)b * kXBytes; };
     auto slot_h = [&](int s, int L) { return smem + (size_t)s * kSlotBytes + 2 * kXBytes + (size_t)L * kGBytes; };
-    auto slot_g = [&](int s) { return smem + (size_t)s * kSlotBytes + 2 * kXBytes + (size_t)(NH + 1) * kGBytes; };
+    auto slot_g = [&](int s, int k) { return smem + (size_t)s * kSlotBytes + 2 * kXBytes + (size_t)(NH + 1 + (GD ? (k & 1) : 0)) * kGBytes; };
 
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -1439,7 +1474,7 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
     stage_matrix(wls, W + kW * in_dim + NH * kW * kW, 16, kW, tid, nthreads);
     if (tid == 0) {
         for (int s = 0; s < NSLOTS; ++s) {
-            mbar_init(&a_ready[s], 128);
+            mbar_init(&a_ready[s], 4);      // one arrival per epilogue warp
             mbar_init(&d_full[s], 1);
             mbar_init(&x_full[2 * s], 1);
             mbar_init(&x_full[2 * s + 1], 1);
@@ -1461,6 +1496,7 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
 
     if (warp == 0) {
         // ===================== MMA / TMA issuer: warp-uniform control flow, one elected lane issues =====================
+        ENERF_TRACE_DECL(0);
         const uint32_t tm = __shfl_sync(0xffffffffu, tmem0, 0);
         const uint32_t sm_b = smem_u32(smem), w0b = smem_u32(w0s), whb = smem_u32(whs), wlb = smem_u32(wls);
         uint32_t nt[NSLOTS];
@@ -1491,18 +1527,19 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
                     const uint32_t slot_b = sm_b + (uint32_t)s * kSlotBytes;
                     const uint32_t xb = slot_b + (tl & 1u) * kXBytes;
                     const uint32_t h0b = slot_b + 2 * kXBytes;           // h_L at h0b + L*kGBytes
-                    const uint32_t g_s = h0b + (uint32_t)(NH + 1) * kGBytes;
                     if (t == 0) {
                         // ---- F_0: h_0 pre-activation = x . W_0^T
                         if (tl > 0) mbar_wait(&a_ready[s], (tb - 1u) & 1u);              // the previous tile's dx accumulator has been read
                         mbar_wait(&x_full[2 * s + (tl & 1u)], (tl >> 1) & 1u);
                         tc_fence_after();
                         if (elect_one()) {
+                            if (s == 0) ENERF_TRACE(1000 + t);
                             if (tl + 1 < nt[s]) issue_x(s, tl + 1);                     // the other input buffer belonged to the finished tile tl-1
 #pragma unroll
                             for (int k = 0; k < in_dim / 16; ++k)
                                 mma_ss(d_t, smem_desc_sw(xb + k * 32, 64), smem_desc(w0b + k * 2 * (kW * 16), kW * 16, 128), idF, k > 0);
                             tc_commit(&d_full[s]);
+                            if (s == 0) ENERF_TRACE(2000 + t);
                         }
                         __syncwarp();
                     } else if (t <= NH) {
@@ -1510,21 +1547,27 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
                         mbar_wait(&a_ready[s], (tb + (uint32_t)(t - 1)) & 1u);
                         tc_fence_after();
                         if (elect_one()) {
+                            if (s == 0) ENERF_TRACE(1000 + t);
                             const uint32_t ab = h0b + (uint32_t)(t - 1) * kGBytes, wb = whb + (uint32_t)(t - 1) * 8192u;
 #pragma unroll
                             for (int k = 0; k < 4; ++k) mma_ss(d_t, smem_desc_sw(ab + k * 32, 128), smem_desc(wb + k * 2 * (kW * 16), kW * 16, 128), idF, k > 0);
                             tc_commit(&d_full[s]);
+                            if (s == 0) ENERF_TRACE(2000 + t);
                         }
                         __syncwarp();
                     } else {
                         // ---- B_k: backward stage k (see k_tc_bwd_tma); its activation tile is h_{NH-k}, or x for the last stage
                         const int k = t - (NH + 1);
+                        const uint32_t g_s = h0b + (uint32_t)(NH + 1 + (GD ? (k & 1) : 0)) * kGBytes;
+                        constexpr bool kSplit = GD;                      // commit the dgrad before the wgrad (all but the tile's last stage)
                         mbar_wait(&a_ready[s], (tb + (uint32_t)(t - 1)) & 1u);
                         tc_fence_after();
                         const bool acc = !(tl == 0 && s == 0);           // the very first issue on an accumulator overwrites it
                         if (elect_one()) {
+                            if (s == 0) ENERF_TRACE(1000 + t);
                             if (k == 0) {
                                 mma_ts(d_t, a_t, smem_desc(wlb, 128, 16 * 16), idD64, false);
+                                if (kSplit) tc_commit(&d_full[s]);
                                 const uint32_t h_s = h0b + (uint32_t)NH * kGBytes;
 #pragma unroll
                                 for (int ks = 0; ks < 8; ++ks)
@@ -1533,6 +1576,7 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
                                 const uint32_t wj = whb + (uint32_t)(NH - k) * 8192u;
 #pragma unroll
                                 for (int ks = 0; ks < 4; ++ks) mma_ts(d_t, a_t + ks * 8, smem_desc(wj + ks * 256, 128, 64 * 16), idD64, ks > 0);
+                                if (kSplit) tc_commit(&d_full[s]);
                                 const uint32_t h_s = h0b + (uint32_t)(NH - k) * kGBytes;
 #pragma unroll
                                 for (int ks = 0; ks < 8; ++ks)
@@ -1545,7 +1589,9 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
                                 for (int ks = 0; ks < 8; ++ks)
                                     mma_ss(tm + kAcc0, smem_desc(g_s + ks * 256, 128, 2048), smem_desc_sw(xb + ks * 16 * 64, 64), idW0, acc || ks > 0);
                             }
-                            tc_commit(&d_full[s]);
+                            // the last stage always commits after its wgrad: everything of the tile (G, x, h tiles) is then free
+                            if (!kSplit || k == S - 1) tc_commit(&d_full[s]);
+                            if (s == 0) ENERF_TRACE(2000 + t);
                         }
                         __syncwarp();
                     }
@@ -1561,7 +1607,7 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
         const int r_in_tile = q * 32 + lane;
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
         const uint32_t d_t = tmem0 + lane_sel + s * kSlotCols, a_t = d_t + 64;
-        uint8_t* g_tile = slot_g(s);
+        ENERF_TRACE_DECL(1);
 
         int4 pv0 = make_int4(0, 0, 0, 0), pv1 = make_int4(0, 0, 0, 0);
         float pf[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -1597,17 +1643,20 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
             for (int L = 0; L <= NH; ++L) {
                 mbar_wait(&d_full[s], (tb + (uint32_t)L) & 1u);
                 tc_fence_after();
+                if (s == 0 && r_in_tile == 0) ENERF_TRACE(3000 + L);
                 uint8_t* hb = slot_h(s, L);
+                uint32_t acc2[2][32];
+                tmem_ld32(d_t, acc2[0]);
+                tmem_ld32(d_t + 32, acc2[1]);
+                tc_wait_ld();
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    uint32_t acc[32];
-                    tmem_ld32(d_t + h * 32, acc);
-                    tc_wait_ld();
+                    const uint32_t (&acc)[32] = acc2[h];
 #pragma unroll
                     for (int v = 0; v < 4; ++v) {
                         uint32_t p[4];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) p[e] = pack2(relu(__uint_as_float(acc[8 * v + 2 * e])), relu(__uint_as_float(acc[8 * v + 2 * e + 1])));
+                        for (int e = 0; e < 4; ++e) p[e] = pack2_relu(__uint_as_float(acc[8 * v + 2 * e]), __uint_as_float(acc[8 * v + 2 * e + 1]));
                         *reinterpret_cast<int4*>(hb + sw_off((uint32_t)r_in_tile, (uint32_t)(h * 4 + v), 128)) = make_int4((int)p[0], (int)p[1], (int)p[2], (int)p[3]);
                     }
                 }
@@ -1639,13 +1688,16 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
                     const uint32_t r8[8] = {(uint32_t)v0.x, (uint32_t)v0.y, (uint32_t)v0.z, (uint32_t)v0.w,
                                             (uint32_t)v1.x, (uint32_t)v1.y, (uint32_t)v1.z, (uint32_t)v1.w};
                     tmem_st8(a_t, r8);
+                    uint8_t* g_tile = slot_g(s, 0);
                     *reinterpret_cast<int4*>(g_tile + 0 * 2048 + r_in_tile * 16) = v0;
                     *reinterpret_cast<int4*>(g_tile + 1 * 2048 + r_in_tile * 16) = v1;
                     tc_wait_st();
                 }
+                if (s == 0 && r_in_tile == 0) ENERF_TRACE(4000 + L);
                 fence_proxy_async_smem();
                 tc_fence_before();
-                mbar_arrive(&a_ready[s]);
+                warp_arrive(&a_ready[s], lane);
+                if (s == 0 && r_in_tile == 0) ENERF_TRACE(5000 + L);
                 if (L == NH && j + NSLOTS < my_tiles) fetch(((size_t)blockIdx.x + (size_t)(j + NSLOTS) * gridDim.x) * kTile + r_in_tile);
             }
             // ---- E_k, k = 1 .. S-1: g = D * relu'(h_{NH-(k-1)}) -> TMEM A + G tile
@@ -1653,16 +1705,20 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
             for (int k = 1; k < S; ++k) {
                 mbar_wait(&d_full[s], (tb + (uint32_t)(NH + k)) & 1u);
                 tc_fence_after();
+                if (s == 0 && r_in_tile == 0) ENERF_TRACE(3000 + NH + k);
                 const uint8_t* hrow = slot_h(s, NH - (k - 1));
+                uint8_t* g_tile = slot_g(s, k);
                 int4 hv[8];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) hv[c] = *reinterpret_cast<const int4*>(hrow + sw_off((uint32_t)r_in_tile, (uint32_t)c, 128));
                 const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
+                uint32_t acc2[2][32];
+                tmem_ld32(d_t, acc2[0]);
+                tmem_ld32(d_t + 32, acc2[1]);
+                tc_wait_ld();
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    uint32_t acc[32];
-                    tmem_ld32(d_t + h * 32, acc);
-                    tc_wait_ld();
+                    const uint32_t (&acc)[32] = acc2[h];
                     uint32_t p[16];
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
@@ -1676,21 +1732,24 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
                         *reinterpret_cast<int4*>(g_tile + (h * 4 + v) * 2048 + r_in_tile * 16) =
                             make_int4((int)p[4 * v], (int)p[4 * v + 1], (int)p[4 * v + 2], (int)p[4 * v + 3]);
                 }
+                if (s == 0 && r_in_tile == 0) ENERF_TRACE(4000 + NH + k);
                 tc_wait_st();
                 fence_proxy_async_smem();
                 tc_fence_before();
-                mbar_arrive(&a_ready[s]);
+                warp_arrive(&a_ready[s], lane);
+                if (s == 0 && r_in_tile == 0) ENERF_TRACE(5000 + NH + k);
             }
             // ---- E_S: dx
             mbar_wait(&d_full[s], (tb + (uint32_t)(T - 1)) & 1u);
             tc_fence_after();
+            if (s == 0 && r_in_tile == 0) ENERF_TRACE(3000 + T);
             {
                 uint32_t acc0[16], acc1[16];
                 tmem_ld16(d_t, acc0);
                 tmem_ld16(d_t + 16, acc1);
                 tc_wait_ld();
                 tc_fence_before();
-                mbar_arrive(&a_ready[s]);                  // accumulator read: the slot can start its next tile
+                warp_arrive(&a_ready[s], lane);                  // accumulator read: the slot can start its next tile
                 if (grad_inputs) {
                     uint32_t p[16];
 #pragma unroll
@@ -1755,21 +1814,21 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
     if (warp == 0) tmem_dealloc(tmem0, kCols);
 }
 
-template <int NSLOTS, int NH, int PRO>
+template <int NSLOTS, int NH, int PRO, bool GD>
 static int launch_bwd_rc_n(const TmaDesc& tx, const __half* grad, const __half* W, __half* grad_inputs, float* dW, uint32_t B, ProArgs pro,
                            cudaStream_t st, const char* name) {
-    constexpr size_t kSlot = 2 * (size_t)kTile * 32 * 2 + (size_t)(NH + 2) * kGBytes;
+    constexpr size_t kSlot = 2 * (size_t)kTile * 32 * 2 + (size_t)(NH + 2 + (GD ? 1 : 0)) * kGBytes;
     size_t smem = 1024 + NSLOTS * kSlot + 32 * 128 + (size_t)NH * 8192 + 2048 + (4 * NSLOTS + 1) * 8 + 16;
     if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: it allocates all 512 TMEM columns
     if (smem > 227 * 1024) return 1;
     static bool configured = false;
     if (!configured) {
-        ENERF_CUDA(cudaFuncSetAttribute(k_tc_bwd_rc<NSLOTS, NH, PRO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
+        ENERF_CUDA(cudaFuncSetAttribute(k_tc_bwd_rc<NSLOTS, NH, PRO, GD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
         configured = true;
     }
     const uint32_t n_tiles = B / kTile;
     const uint32_t grid = n_tiles < (uint32_t)kNumSM ? n_tiles : (uint32_t)kNumSM;
-    k_tc_bwd_rc<NSLOTS, NH, PRO><<<grid, 32 + NSLOTS * 128, smem, st>>>(tx, grad, W, grad_inputs, dW, n_tiles, B, pro);
+    k_tc_bwd_rc<NSLOTS, NH, PRO, GD><<<grid, 32 + NSLOTS * 128, smem, st>>>(tx, grad, W, grad_inputs, dW, n_tiles, B, pro);
     ENERF_CHECK_LAUNCH(name);
     return 0;
 }
@@ -1781,8 +1840,17 @@ static int launch_bwd_rc(const __half* grad, const __half* x, const __half* W, _
     if (in_dim != 32 || (n_hidden_mm != 1 && n_hidden_mm != 2) || (uint64_t)B >= (1ull << 31)) return 1;
     TmaDesc tx;
     if (!make_tmap_rows(&tx, x, B, 32, kTile)) return 1;
-    if (n_hidden_mm == 1) return launch_bwd_rc_n<3, 1, PRO>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
-    return launch_bwd_rc_n<2, 2, PRO>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
+    static int mode = -1;      // ENERF_TC_RC_MODE: bit 0 = double G tile + early dgrad commit for 3-layer nets, bit 1 = same with 2 slots for 2-layer nets
+    if (mode < 0) {
+        const char* e = getenv("ENERF_TC_RC_MODE");
+        mode = e ? atoi(e) : 1;
+    }
+    if (n_hidden_mm == 1) {
+        if (mode & 2) return launch_bwd_rc_n<2, 1, PRO, true>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
+        return launch_bwd_rc_n<3, 1, PRO, false>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
+    }
+    if (mode & 1) return launch_bwd_rc_n<2, 2, PRO, true>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
+    return launch_bwd_rc_n<2, 2, PRO, false>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
 }
 
 int tc_backward(const __half* grad, const __half* x, const __half* W, const __half* fwd_buf, __half* bwd_buf, __half* grad_inputs, float* dW,

@@ -124,6 +124,9 @@ def main():
                 if path == 0:   # what training runs: no backward_buffer (activation gradients stay on the SM; TMA operand loads)
                     med, mn = timeit(lambda: FB.ffmlp_backward(g, x, w, fb, S, 32, 16, 64, nl, 0, 6, True, None, gi, gw), args.iters, flush)
                     res[tag + "_bwd_nobuf"] = {"ms": med, "min_ms": mn, "TFLOPs": 2 * flops_f / med / 1e9, "frac": 2 * flops_f / med / 1e9 / 1387.0}
+                    # no forward_buffer either: hidden activations recomputed per tile (what the fused field trains with)
+                    med, mn = timeit(lambda: FB.ffmlp_backward(g, x, w, None, S, 32, 16, 64, nl, 0, 6, True, None, gi, gw), args.iters, flush)
+                    res[tag + "_bwd_recompute"] = {"ms": med, "min_ms": mn, "TFLOPs": 2 * flops_f / med / 1e9, "frac": 2 * flops_f / med / 1e9 / 1387.0}
             _lib.call("enerf_ffmlp_set_path", 0)
 
     if want("composite"):
