@@ -1438,11 +1438,15 @@ static int launch_bwd_tma(const __half* grad, const __half* x, const __half* W, 
 //   a_ready[s] / d_full[s] advance 2*NH+3 phases per tile (one per MMA stage; a_ready's last one = "accumulator read,
 //   slot free for the next tile").
 // ================================================================================================
-template <int NSLOTS, int NH, int PRO, bool GD>
-__global__ void __launch_bounds__(32 + NSLOTS * 128, 1)
+template <int NSLOTS, int NH, int PRO, bool GD, int CH>
+__global__ void __launch_bounds__(32 + NSLOTS * 128 * CH, 1)
 k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ grad, const __half* __restrict__ W, __half* __restrict__ grad_inputs,
             float* __restrict__ dW, uint32_t n_tiles, uint32_t B, ProArgs pro) {
+    // CH = warps per TMEM lane quarter of a slot (1 or 2): with 2, a row's 64 accumulator columns are split between two
+    // threads (warps w and w+4 share the quarter w % 4), which halves the serial epilogue work per stage.
+    static_assert(CH == 1 || CH == 2, "CH");
     constexpr int in_dim = 32;
+    constexpr int CW = 64 / CH;                            // accumulator columns per epilogue thread
     constexpr int S = NH + 2;                              // backward stages per tile
     constexpr int T = 2 * NH + 3;                          // MMA stages per tile (NH+1 forward, S backward)
     constexpr uint32_t kXBytes = kTile * in_dim * 2;
@@ -1474,7 +1478,7 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
     stage_matrix(wls, W + kW * in_dim + NH * kW * kW, 16, kW, tid, nthreads);
     if (tid == 0) {
         for (int s = 0; s < NSLOTS; ++s) {
-            mbar_init(&a_ready[s], 4);      // one arrival per epilogue warp
+            mbar_init(&a_ready[s], 4 * CH);      // one arrival per epilogue warp
             mbar_init(&d_full[s], 1);
             mbar_init(&x_full[2 * s], 1);
             mbar_init(&x_full[2 * s + 1], 1);
@@ -1601,9 +1605,11 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
         if (elect_one()) tc_commit(flush_bar);
         __syncwarp();
     } else {
-        // ===================== epilogue warps (4 per slot) =====================
-        const int s = (warp - 1) >> 2;
-        const int q = warp & 3;
+        // ===================== epilogue warps (4*CH per slot) =====================
+        const int ew = warp - 1;
+        const int s = ew / (4 * CH);
+        const int q = warp & 3;                            // TMEM lane quarter this warp may access
+        const int hf = (ew % (4 * CH)) >> 2;               // which CW-column part of the row this thread owns
         const int r_in_tile = q * 32 + lane;
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
         const uint32_t d_t = tmem0 + lane_sel + s * kSlotCols, a_t = d_t + 64;
@@ -1631,7 +1637,7 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
                 pv1 = __ldg(src + 1);
             }
         };
-        if ((uint32_t)s < my_tiles) fetch(((size_t)blockIdx.x + (size_t)s * gridDim.x) * kTile + r_in_tile);
+        if (hf == 0 && (uint32_t)s < my_tiles) fetch(((size_t)blockIdx.x + (size_t)s * gridDim.x) * kTile + r_in_tile);
 
         uint32_t tl = 0;
         for (uint32_t j = s; j < my_tiles; j += NSLOTS, ++tl) {
@@ -1645,22 +1651,21 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
                 tc_fence_after();
                 if (s == 0 && r_in_tile == 0) ENERF_TRACE(3000 + L);
                 uint8_t* hb = slot_h(s, L);
-                uint32_t acc2[2][32];
-                tmem_ld32(d_t, acc2[0]);
-                tmem_ld32(d_t + 32, acc2[1]);
-                tc_wait_ld();
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const uint32_t (&acc)[32] = acc2[h];
+                for (int h = 0; h < CW / 32; ++h) {
+                    uint32_t acc[32];
+                    tmem_ld32(d_t + hf * CW + h * 32, acc);
+                    tc_wait_ld();
 #pragma unroll
                     for (int v = 0; v < 4; ++v) {
                         uint32_t p[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e) p[e] = pack2_relu(__uint_as_float(acc[8 * v + 2 * e]), __uint_as_float(acc[8 * v + 2 * e + 1]));
-                        *reinterpret_cast<int4*>(hb + sw_off((uint32_t)r_in_tile, (uint32_t)(h * 4 + v), 128)) = make_int4((int)p[0], (int)p[1], (int)p[2], (int)p[3]);
+                        *reinterpret_cast<int4*>(hb + sw_off((uint32_t)r_in_tile, (uint32_t)(hf * (CW / 8) + h * 4 + v), 128)) =
+                            make_int4((int)p[0], (int)p[1], (int)p[2], (int)p[3]);
                     }
                 }
-                if (L == NH) {
+                if (L == NH && hf == 0) {
                     // dy -> TMEM A + dy tile (G buffer): E_0 of the backward
                     int4 v0, v1;
                     if (PRO == 0) {
@@ -1698,7 +1703,7 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
                 tc_fence_before();
                 warp_arrive(&a_ready[s], lane);
                 if (s == 0 && r_in_tile == 0) ENERF_TRACE(5000 + L);
-                if (L == NH && j + NSLOTS < my_tiles) fetch(((size_t)blockIdx.x + (size_t)(j + NSLOTS) * gridDim.x) * kTile + r_in_tile);
+                if (L == NH && hf == 0 && j + NSLOTS < my_tiles) fetch(((size_t)blockIdx.x + (size_t)(j + NSLOTS) * gridDim.x) * kTile + r_in_tile);
             }
             // ---- E_k, k = 1 .. S-1: g = D * relu'(h_{NH-(k-1)}) -> TMEM A + G tile
 #pragma unroll
@@ -1708,17 +1713,15 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
                 if (s == 0 && r_in_tile == 0) ENERF_TRACE(3000 + NH + k);
                 const uint8_t* hrow = slot_h(s, NH - (k - 1));
                 uint8_t* g_tile = slot_g(s, k);
-                int4 hv[8];
+                int4 hv[CW / 8];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) hv[c] = *reinterpret_cast<const int4*>(hrow + sw_off((uint32_t)r_in_tile, (uint32_t)c, 128));
+                for (int c = 0; c < CW / 8; ++c) hv[c] = *reinterpret_cast<const int4*>(hrow + sw_off((uint32_t)r_in_tile, (uint32_t)(hf * (CW / 8) + c), 128));
                 const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
-                uint32_t acc2[2][32];
-                tmem_ld32(d_t, acc2[0]);
-                tmem_ld32(d_t + 32, acc2[1]);
-                tc_wait_ld();
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const uint32_t (&acc)[32] = acc2[h];
+                for (int h = 0; h < CW / 32; ++h) {
+                    uint32_t acc[32];
+                    tmem_ld32(d_t + hf * CW + h * 32, acc);
+                    tc_wait_ld();
                     uint32_t p[16];
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
@@ -1726,10 +1729,10 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
                         const unsigned m = __hgt2_mask(*reinterpret_cast<const __half2*>(&hw), zero2);
                         p[e] = pack2(__uint_as_float(acc[2 * e]), __uint_as_float(acc[2 * e + 1])) & m;
                     }
-                    tmem_st16(a_t + h * 16, p);
+                    tmem_st16(a_t + hf * (CW / 2) + h * 16, p);
 #pragma unroll
                     for (int v = 0; v < 4; ++v)
-                        *reinterpret_cast<int4*>(g_tile + (h * 4 + v) * 2048 + r_in_tile * 16) =
+                        *reinterpret_cast<int4*>(g_tile + (hf * (CW / 8) + h * 4 + v) * 2048 + r_in_tile * 16) =
                             make_int4((int)p[4 * v], (int)p[4 * v + 1], (int)p[4 * v + 2], (int)p[4 * v + 3]);
                 }
                 if (s == 0 && r_in_tile == 0) ENERF_TRACE(4000 + NH + k);
@@ -1744,28 +1747,40 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
             tc_fence_after();
             if (s == 0 && r_in_tile == 0) ENERF_TRACE(3000 + T);
             {
-                uint32_t acc0[16], acc1[16];
-                tmem_ld16(d_t, acc0);
-                tmem_ld16(d_t + 16, acc1);
-                tc_wait_ld();
+                // dx: 32 columns; with CH == 2 each thread of the row takes 16 of them
+                constexpr int DXW = 32 / CH;
+                uint32_t acc[DXW];
+                if (CH == 1) {
+                    uint32_t a0[16], a1[16];
+                    tmem_ld16(d_t, a0);
+                    tmem_ld16(d_t + 16, a1);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) { acc[e % DXW] = a0[e]; }
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) { acc[(16 + e) % DXW] = a1[e]; }
+                } else {
+                    uint32_t a0[16];
+                    tmem_ld16(d_t + hf * 16, a0);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) acc[e % DXW] = a0[e];
+                }
                 tc_fence_before();
                 warp_arrive(&a_ready[s], lane);                  // accumulator read: the slot can start its next tile
                 if (grad_inputs) {
-                    uint32_t p[16];
+                    uint32_t p[DXW / 2];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        p[e] = pack2(__uint_as_float(acc0[2 * e]), __uint_as_float(acc0[2 * e + 1]));
-                        p[8 + e] = pack2(__uint_as_float(acc1[2 * e]), __uint_as_float(acc1[2 * e + 1]));
-                    }
-                    int4* dst = reinterpret_cast<int4*>(grad_inputs + row * in_dim);
+                    for (int e = 0; e < DXW / 2; ++e) p[e] = pack2(__uint_as_float(acc[2 * e]), __uint_as_float(acc[2 * e + 1]));
+                    int4* dst = reinterpret_cast<int4*>(grad_inputs + row * in_dim + hf * DXW);
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) dst[v] = make_int4((int)p[4 * v], (int)p[4 * v + 1], (int)p[4 * v + 2], (int)p[4 * v + 3]);
+                    for (int v = 0; v < DXW / 8; ++v) dst[v] = make_int4((int)p[4 * v], (int)p[4 * v + 1], (int)p[4 * v + 2], (int)p[4 * v + 3]);
                 }
             }
         }
 
         // ---- flush the weight-gradient accumulators (slot 0's four warps; M = 64 -> lanes 0..15 of each quarter)
-        if (s == 0 && my_tiles > 0) {
+        if (s == 0 && hf == 0 && my_tiles > 0) {
             mbar_wait(flush_bar, 0);
             tc_fence_after();
             const int m = q * 16 + lane;
@@ -1814,7 +1829,7 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
     if (warp == 0) tmem_dealloc(tmem0, kCols);
 }
 
-template <int NSLOTS, int NH, int PRO, bool GD>
+template <int NSLOTS, int NH, int PRO, bool GD, int CH>
 static int launch_bwd_rc_n(const TmaDesc& tx, const __half* grad, const __half* W, __half* grad_inputs, float* dW, uint32_t B, ProArgs pro,
                            cudaStream_t st, const char* name) {
     constexpr size_t kSlot = 2 * (size_t)kTile * 32 * 2 + (size_t)(NH + 2 + (GD ? 1 : 0)) * kGBytes;
@@ -1823,12 +1838,12 @@ static int launch_bwd_rc_n(const TmaDesc& tx, const __half* grad, const __half* 
     if (smem > 227 * 1024) return 1;
     static bool configured = false;
     if (!configured) {
-        ENERF_CUDA(cudaFuncSetAttribute(k_tc_bwd_rc<NSLOTS, NH, PRO, GD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
+        ENERF_CUDA(cudaFuncSetAttribute(k_tc_bwd_rc<NSLOTS, NH, PRO, GD, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
         configured = true;
     }
     const uint32_t n_tiles = B / kTile;
     const uint32_t grid = n_tiles < (uint32_t)kNumSM ? n_tiles : (uint32_t)kNumSM;
-    k_tc_bwd_rc<NSLOTS, NH, PRO, GD><<<grid, 32 + NSLOTS * 128, smem, st>>>(tx, grad, W, grad_inputs, dW, n_tiles, B, pro);
+    k_tc_bwd_rc<NSLOTS, NH, PRO, GD, CH><<<grid, 32 + NSLOTS * 128 * CH, smem, st>>>(tx, grad, W, grad_inputs, dW, n_tiles, B, pro);
     ENERF_CHECK_LAUNCH(name);
     return 0;
 }
@@ -1840,17 +1855,22 @@ static int launch_bwd_rc(const __half* grad, const __half* x, const __half* W, _
     if (in_dim != 32 || (n_hidden_mm != 1 && n_hidden_mm != 2) || (uint64_t)B >= (1ull << 31)) return 1;
     TmaDesc tx;
     if (!make_tmap_rows(&tx, x, B, 32, kTile)) return 1;
-    static int mode = -1;      // ENERF_TC_RC_MODE: bit 0 = double G tile + early dgrad commit for 3-layer nets, bit 1 = same with 2 slots for 2-layer nets
+    // Measured on B200 (3.29 M samples): 2-layer nets 0.255 ms with 3 slots x 4 epilogue warps (0.28 with 2 x 8); 3-layer nets 0.355 ms
+    // with 2 slots x 8 epilogue warps (0.386 with 2 x 4; a third slot does not fit in shared memory).  ENERF_TC_RC_MODE overrides for
+    // experiments: 1 = one thread per row everywhere, 2 = second G tile + early dgrad commit, 3 = two threads per row everywhere.
+    static int mode = -1;
     if (mode < 0) {
         const char* e = getenv("ENERF_TC_RC_MODE");
-        mode = e ? atoi(e) : 1;
+        mode = e ? atoi(e) : 0;
     }
     if (n_hidden_mm == 1) {
-        if (mode & 2) return launch_bwd_rc_n<2, 1, PRO, true>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
-        return launch_bwd_rc_n<3, 1, PRO, false>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
+        if (mode == 3) return launch_bwd_rc_n<2, 1, PRO, false, 2>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
+        if (mode == 2) return launch_bwd_rc_n<2, 1, PRO, true, 1>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
+        return launch_bwd_rc_n<3, 1, PRO, false, 1>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
     }
-    if (mode & 1) return launch_bwd_rc_n<2, 2, PRO, true>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
-    return launch_bwd_rc_n<2, 2, PRO, false>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
+    if (mode == 1) return launch_bwd_rc_n<2, 2, PRO, false, 1>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
+    if (mode == 2) return launch_bwd_rc_n<2, 2, PRO, true, 1>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
+    return launch_bwd_rc_n<2, 2, PRO, false, 2>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
 }
 
 int tc_backward(const __half* grad, const __half* x, const __half* W, const __half* fwd_buf, __half* bwd_buf, __half* grad_inputs, float* dW,
