@@ -1,0 +1,135 @@
+"""The steps on either side of the volume-rendering path, fused — host-side mirrors of the
+reference functions they replace, same names, argument meaning and return values:
+
+  get_rays(poses, intrinsics, H, W, N=-1, error_map=None)      nerf/utils.py:110-169
+  get_event_rays(xs, ys, c2w_before, c2w_at, intrinsics)       nerf/utils.py:185-216
+  event_loss(image1, image2, pols, ...)                        nerf/utils.py:494-528 (the body of train_step_events between
+                                                               the two renders and `loss = loss_evs`)
+
+`*_with_near_far` variants additionally return the near/far of raymarching.near_far_from_aabb computed in the same kernel.
+No CPU fallback: CUDA tensors only.
+"""
+import torch
+from torch.autograd import Function
+
+from . import _lib
+from ._lib import need_cuda, ptr, stream
+
+
+def _intr(intrinsics):
+    fx, fy, cx, cy = (float(v) for v in intrinsics)
+    return fx, fy, cx, cy
+
+
+def get_rays_with_near_far(poses, intrinsics, H, W, N=-1, error_map=None, aabb=None, min_near=0.2):
+    need_cuda(poses)
+    dev = poses.device
+    B = poses.shape[0]
+    fx, fy, cx, cy = _intr(intrinsics)
+    results = {}
+    inds = None
+    if N > 0:
+        N = min(N, H * W)
+        if error_map is None:
+            inds1 = torch.randint(0, H * W, size=[N], device=dev)        # may duplicate (utils.py:137)
+            results['inds'] = inds1.expand([B, N])
+            inds = inds1
+        else:
+            raise NotImplementedError("error_map sampling produces per-pose indices; use the reference's sampler and pass them via `inds`")
+    n = N if N > 0 else H * W
+    P = poses.detach().float().contiguous()
+    rays_o = torch.empty(B, n, 3, dtype=torch.float32, device=dev)
+    rays_d = torch.empty(B, n, 3, dtype=torch.float32, device=dev)
+    nears = fars = None
+    a = None
+    if aabb is not None:
+        a = aabb.detach().float().contiguous()
+        nears = torch.empty(B, n, dtype=torch.float32, device=dev)
+        fars = torch.empty(B, n, dtype=torch.float32, device=dev)
+    _lib.call("enerf_get_rays", ptr(P), fx, fy, cx, cy, H, W, ptr(inds), B, n, ptr(a), float(min_near), ptr(rays_o), ptr(rays_d), ptr(nears),
+              ptr(fars), stream())
+    results['rays_o'] = rays_o
+    results['rays_d'] = rays_d
+    if aabb is not None:
+        results['nears'], results['fars'] = nears, fars
+    return results
+
+
+def get_rays(poses, intrinsics, H, W, N=-1, error_map=None):
+    return get_rays_with_near_far(poses, intrinsics, H, W, N, error_map)
+
+
+def get_event_rays_with_near_far(xs, ys, c2w_before, c2w_at, intrinsics, aabb=None, min_near=0.2):
+    need_cuda(xs, ys, c2w_before, c2w_at)
+    dev = xs.device
+    fx, fy, cx, cy = _intr(intrinsics)
+    lead = c2w_before.shape[:-2]                                 # (B, Nevs) in the reference, B == 1
+    n = xs.numel()
+    if c2w_before.numel() != n * 12:
+        raise RuntimeError("get_event_rays: one [3,4] pose per event expected")
+    x = xs.detach().float().contiguous().view(-1)
+    y = ys.detach().float().contiguous().view(-1)
+    pb = c2w_before.detach().float().contiguous().view(-1, 3, 4)
+    pa = c2w_at.detach().float().contiguous().view(-1, 3, 4)
+    o1, d1, o2, d2 = (torch.empty(n, 3, dtype=torch.float32, device=dev) for _ in range(4))
+    nf1 = nf2 = a = None
+    if aabb is not None:
+        a = aabb.detach().float().contiguous()
+        nf1 = torch.empty(2, n, dtype=torch.float32, device=dev)
+        nf2 = torch.empty(2, n, dtype=torch.float32, device=dev)
+    _lib.call("enerf_event_rays", ptr(x), ptr(y), ptr(pb), ptr(pa), fx, fy, cx, cy, n, ptr(a), float(min_near), ptr(o1), ptr(d1), ptr(o2), ptr(d2),
+              ptr(nf1), ptr(nf2), stream())
+    out = {"rays_evs_o1": o1.view(*lead, 3), "rays_evs_d1": d1.view(*lead, 3), "rays_evs_o2": o2.view(*lead, 3), "rays_evs_d2": d2.view(*lead, 3)}
+    if aabb is not None:
+        out.update(nears1=nf1[0].view(*lead), fars1=nf1[1].view(*lead), nears2=nf2[0].view(*lead), fars2=nf2[1].view(*lead))
+    return out
+
+
+def get_event_rays(xs, ys, c2w_before, c2w_at, intrinsics):
+    return get_event_rays_with_near_far(xs, ys, c2w_before, c2w_at, intrinsics)
+
+
+class _EventLoss(Function):
+    @staticmethod
+    def forward(ctx, img1, img2, pols, use_luma, linlog, log_thres, c_thres, weight):
+        need_cuda(img1, img2, pols)
+        C = img1.shape[-1]
+        a = img1.detach().float().contiguous().view(-1, C)
+        b = img2.detach().float().contiguous().view(-1, C)
+        p = pols.detach().float().contiguous().view(-1)
+        N = a.shape[0]
+        if b.shape != a.shape or p.shape[0] != N:
+            raise RuntimeError("event_loss: image1, image2 [.., N, C] and pols [.., N] must agree")
+        Cp = 1 if use_luma else C
+        dev = a.device
+        delta = torch.empty(N, Cp, dtype=torch.float32, device=dev)
+        acc = torch.empty(16, dtype=torch.float32, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        _lib.call("enerf_event_loss_forward", ptr(a), ptr(b), ptr(p), N, C, int(use_luma), int(linlog), float(log_thres), float(c_thres), float(weight),
+                  ptr(delta), ptr(acc), ptr(loss), stream())
+        ctx.save_for_backward(a, b, p, delta, acc)
+        ctx.meta = (N, C, int(use_luma), int(linlog), float(log_thres), float(c_thres), float(weight), img1.shape, img2.shape)
+        ctx.mark_non_differentiable(delta)
+        return loss.view(()), delta
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_delta):
+        a, b, p, delta, acc = ctx.saved_tensors
+        N, C, use_luma, linlog, log_thres, c_thres, weight, s1, s2 = ctx.meta
+        g = g_loss.detach().float().contiguous().view(1)
+        g1 = torch.empty_like(a)
+        g2 = torch.empty_like(b)
+        _lib.call("enerf_event_loss_backward", ptr(a), ptr(b), ptr(p), ptr(delta), ptr(acc), ptr(g), N, C, use_luma, linlog, log_thres, c_thres, weight,
+                  ptr(g1), ptr(g2), stream())
+        return g1.view(s1), g2.view(s2), None, None, None, None, None, None
+
+
+def event_loss(image1, image2, pols, use_luma=False, linlog=True, C_thres=-1, event_only=True, log_thres=20.0):
+    """loss_evs and delta_linlog of nerf/utils.py:494-528 for the renders `image1`, `image2` [B,N,C] of the two poses of each
+    event pair and the accumulated polarities `pols` [B,N] (B == 1).  Returns (loss, delta_linlog [B,N,C'])."""
+    if C_thres != -1:
+        weight = 1.0
+    else:
+        weight = 20.0 * (1.0 if event_only else 20.0)      # utils.py:522-525
+    loss, delta = _EventLoss.apply(image1, image2, pols, bool(use_luma), bool(linlog), float(log_thres), float(C_thres), weight)
+    return loss, delta.view(*image1.shape[:-1], delta.shape[-1])

@@ -229,6 +229,37 @@ int enerf_composite_uniform_backward(const float* grad_weights, const float* gra
                                      uint32_t N, uint32_t T, float density_scale,
                                      float* grad_sigmas, void* stream);
 
+/* ------------------------------------------ next rows of the path ---- */
+/* N2 — ray generation on the device, fused with near_far_from_aabb.
+ * nerf/utils.py:110-169 get_rays for given pixels: poses [B,4,4] cam2world (row-major), pixel n of every pose is
+ * inds[n] (flat index j*W+i; NULL = pixel n), direction = normalize(((i-cx)/fx, (j-cy)/fy, 1)) rotated by pose[:3,:3],
+ * origin = pose[:3,3].  rays_o, rays_d: [B,N,3].  aabb (6 floats, device) may be NULL; otherwise nears/fars [B,N] get the
+ * slab test of raymarching.h:7 with `min_near`. */
+int enerf_get_rays(const float* poses, float fx, float fy, float cx, float cy, uint32_t H, uint32_t W,
+                   const int64_t* inds, uint32_t B, uint32_t N, const float* aabb, float min_near,
+                   float* rays_o, float* rays_d, float* nears, float* fars, void* stream);
+/* nerf/utils.py:185-216 get_event_rays: pixel (xs[n], ys[n]) seen from c2w_before[n] and c2w_at[n] ([N,3,4] row-major).
+ * near_far1 / near_far2: [2,N] = nears then fars of the two ray sets (NULL or aabb == NULL: not computed). */
+int enerf_event_rays(const float* xs, const float* ys, const float* c2w_before, const float* c2w_at, float fx,
+                     float fy, float cx, float cy, uint32_t N, const float* aabb, float min_near,
+                     float* rays_o1, float* rays_d1, float* rays_o2, float* rays_d2, float* near_far1,
+                     float* near_far2, void* stream);
+/* N1 — the event-loss tail after compositing, nerf/utils.py:494-528 (+ utils/event_utils.py:23-66 rgb_to_luma, lin_log).
+ * img1, img2: [N,C] rendered intensities of the two poses of each event pair (fp32); pols: [N] accumulated polarity.
+ * use_luma: BT.601 luma of 3 channels first (esim coefficients); linlog: lin_log(255*x, 20), else log(max(255*x, log_thres));
+ * c_thres != -1: loss = weight * mean((delta - pols*c_thres)^2); c_thres == -1: normalised loss
+ * weight * mean((delta/(||delta||+1e-9) - pols/(||pols||+1e-9))^2), norms over the N rays per channel.
+ * delta [N,C'] (C' = 1 with luma, else C) and acc [16] are outputs the backward call needs; loss: 1 float.
+ * (The reference's non-linlog luma branch uses pred_luma1 for both renders, utils.py:504-505 — an obvious slip that makes
+ * the loss constant; both renders are used here.) */
+int enerf_event_loss_forward(const float* img1, const float* img2, const float* pols, uint32_t N, uint32_t C,
+                             int use_luma, int linlog, float log_thres, float c_thres, float weight,
+                             float* delta, float* acc, float* loss, void* stream);
+int enerf_event_loss_backward(const float* img1, const float* img2, const float* pols, const float* delta,
+                              const float* acc, const float* grad_loss, uint32_t N, uint32_t C, int use_luma,
+                              int linlog, float log_thres, float c_thres, float weight, float* grad_img1,
+                              float* grad_img2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

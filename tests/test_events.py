@@ -1,0 +1,121 @@
+"""The next rows of the path: device ray generation and the fused event-loss tail.
+CPU: the numpy oracle reproduces the golden vectors the reference's own Python code produced (tests/golden/events.npz).
+GPU: the kernels reproduce the same vectors (forward, gradients, fused near/far)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import events_oracle as eo
+from oracle import oracle
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "events.npz"))
+HAS_GPU = torch.cuda.is_available()
+
+
+def _cases():
+    return [(int(a), int(b), float(c), int(d)) for a, b, c, d in G["el_cases"]]
+
+
+def _tag(use_luma, linlog, C_thres, event_only):
+    return f"el_{use_luma}{linlog}{int(C_thres != -1)}{event_only}"
+
+
+# ------------------------------------------------------------------ CPU: oracle pinned on the reference's outputs
+def test_oracle_get_rays_reproduces_reference():
+    H, W = (int(v) for v in G["gr_hw"])
+    o, d = eo.get_rays(G["gr_poses"], G["gr_intr"], H, W)
+    assert np.array_equal(o, G["gr_o_all"]) and np.allclose(d, G["gr_d_all"], atol=2e-7)
+    o, d = eo.get_rays(G["gr_poses"], G["gr_intr"], H, W, G["gr_inds"])
+    assert np.array_equal(o, G["gr_o_sel"]) and np.allclose(d, G["gr_d_sel"], atol=2e-7)
+
+
+def test_oracle_get_event_rays_reproduces_reference():
+    r = eo.get_event_rays(G["er_xs"], G["er_ys"], G["er_pb"], G["er_pa"], G["er_intr"])
+    for k in ("o1", "d1", "o2", "d2"):
+        assert np.allclose(r["rays_evs_" + k], G["er_" + k], atol=2e-7), k
+
+
+def test_oracle_event_loss_reproduces_reference():
+    for use_luma, linlog, C_thres, event_only in _cases():
+        tag = _tag(use_luma, linlog, C_thres, event_only)
+        loss, delta = eo.event_loss(G["el_img1"], G["el_img2"], G["el_pols"], use_luma, linlog, C_thres, event_only)
+        assert np.allclose(delta, G[tag + "_delta"], atol=2e-6), tag
+        assert abs(loss - float(G[tag + "_loss"])) <= 2e-5 * abs(float(G[tag + "_loss"])) + 1e-9, (tag, loss, float(G[tag + "_loss"]))
+
+
+# ------------------------------------------------------------------ GPU: kernels vs the same vectors
+@pytest.mark.gpu
+def test_gpu_get_rays_and_fused_near_far():
+    from enerf_b200 import events
+    dev = "cuda"
+    H, W = (int(v) for v in G["gr_hw"])
+    poses = torch.from_numpy(G["gr_poses"]).to(dev)
+    r = events.get_rays(poses, G["gr_intr"], H, W, -1)
+    assert torch.equal(r["rays_o"].cpu(), torch.from_numpy(G["gr_o_all"]))
+    assert np.allclose(r["rays_d"].cpu().numpy(), G["gr_d_all"], atol=3e-7)
+    # chosen pixels + the slab test in the same kernel vs the stand-alone near_far kernel / oracle
+    aabb = torch.tensor([-1.0, -1, -1, 1, 1, 1], device=dev)
+    from enerf_b200 import _lib
+    from enerf_b200._lib import ptr, stream
+    inds = torch.from_numpy(G["gr_inds"]).to(dev)
+    B, N = 3, inds.numel()
+    ro, rd = torch.empty(B, N, 3, device=dev), torch.empty(B, N, 3, device=dev)
+    nears, fars = torch.empty(B, N, device=dev), torch.empty(B, N, device=dev)
+    fx, fy, cx, cy = (float(v) for v in G["gr_intr"])
+    _lib.call("enerf_get_rays", ptr(poses.contiguous()), fx, fy, cx, cy, H, W, ptr(inds), B, N, ptr(aabb), 0.2, ptr(ro), ptr(rd), ptr(nears), ptr(fars), stream())
+    assert np.allclose(rd.cpu().numpy(), G["gr_d_sel"], atol=3e-7) and torch.equal(ro.cpu(), torch.from_numpy(G["gr_o_sel"]))
+    wn, wf = oracle.near_far_from_aabb(ro.cpu().numpy().reshape(-1, 3), rd.cpu().numpy().reshape(-1, 3), aabb.cpu().numpy(), 0.2)
+    assert np.array_equal(nears.cpu().numpy().reshape(-1), wn) and np.array_equal(fars.cpu().numpy().reshape(-1), wf)
+    # sampled variant returns indices in range and consistent rays
+    torch.manual_seed(0)
+    r = events.get_rays(poses, G["gr_intr"], H, W, 100)
+    o2, d2 = eo.get_rays(G["gr_poses"], G["gr_intr"], H, W, r["inds"][0].cpu().numpy())
+    assert r["inds"].shape == (3, 100) and np.allclose(r["rays_d"].cpu().numpy(), d2, atol=3e-7)
+
+
+@pytest.mark.gpu
+def test_gpu_get_event_rays():
+    from enerf_b200 import events
+    dev = "cuda"
+    t = lambda k: torch.from_numpy(G[k]).to(dev)          # noqa: E731
+    aabb = torch.tensor([-2.0, -2, -2, 2, 2, 2], device=dev)
+    r = events.get_event_rays_with_near_far(t("er_xs"), t("er_ys"), t("er_pb"), t("er_pa"), G["er_intr"], aabb=aabb, min_near=0.2)
+    for k in ("o1", "d1", "o2", "d2"):
+        got = r["rays_evs_" + k].cpu().numpy()
+        assert got.shape == G["er_" + k].shape and np.allclose(got, G["er_" + k], atol=3e-7), k
+    for v in ("1", "2"):
+        wn, wf = oracle.near_far_from_aabb(r["rays_evs_o" + v].cpu().numpy().reshape(-1, 3), r["rays_evs_d" + v].cpu().numpy().reshape(-1, 3),
+                                           aabb.cpu().numpy(), 0.2)
+        assert np.array_equal(r["nears" + v].cpu().numpy().reshape(-1), wn) and np.array_equal(r["fars" + v].cpu().numpy().reshape(-1), wf)
+    plain = events.get_event_rays(t("er_xs"), t("er_ys"), t("er_pb"), t("er_pa"), G["er_intr"])
+    assert set(plain) == {"rays_evs_o1", "rays_evs_d1", "rays_evs_o2", "rays_evs_d2"}
+
+
+@pytest.mark.gpu
+def test_gpu_event_loss_forward_backward_matches_reference():
+    from enerf_b200 import events
+    dev = "cuda"
+    for use_luma, linlog, C_thres, event_only in _cases():
+        tag = _tag(use_luma, linlog, C_thres, event_only)
+        a = torch.from_numpy(G["el_img1"]).to(dev).requires_grad_(True)
+        b = torch.from_numpy(G["el_img2"]).to(dev).requires_grad_(True)
+        p = torch.from_numpy(G["el_pols"]).to(dev)
+        loss, delta = events.event_loss(a, b, p, use_luma=use_luma, linlog=linlog, C_thres=C_thres, event_only=event_only)
+        want = float(G[tag + "_loss"])
+        assert abs(float(loss) - want) <= 2e-4 * abs(want) + 1e-8, (tag, float(loss), want)
+        assert np.allclose(delta.cpu().numpy(), G[tag + "_delta"], atol=5e-6), tag
+        (loss * 3.0).backward()
+        for got, key in ((a.grad, "_g1"), (b.grad, "_g2")):
+            w = 3.0 * G[tag + key]
+            err = np.abs(got.cpu().numpy() - w).max()
+            assert err <= 2e-4 * np.abs(w).max() + 1e-9, (tag, key, err, np.abs(w).max())
+    # one-channel images (what every shipped config trains: out_dim_color = 1)
+    a1 = torch.from_numpy(G["el_img1"][..., :1].copy()).to(dev).requires_grad_(True)
+    b1 = torch.from_numpy(G["el_img2"][..., :1].copy()).to(dev).requires_grad_(True)
+    loss, delta = events.event_loss(a1, b1, torch.from_numpy(G["el_pols"]).to(dev), use_luma=False, linlog=True, C_thres=-1, event_only=True)
+    want, wdelta = eo.event_loss(G["el_img1"][..., :1], G["el_img2"][..., :1], G["el_pols"], 0, 1, -1, 1)
+    assert abs(float(loss) - want) <= 2e-4 * abs(want) and np.allclose(delta.cpu().numpy(), wdelta, atol=5e-6)
+    loss.backward()
+    assert torch.isfinite(a1.grad).all() and float(a1.grad.abs().sum()) > 0
