@@ -239,84 +239,73 @@ class NeRFRenderer(nn.Module):
         xyzs = 2 * coords.float() / (self.grid_size - 1) - 1
         return xyzs * (bound - half_grid_size), half_grid_size
 
-    @torch.no_grad()
-    def mark_untrained_grid(self, poses, intrinsic, S=64):
-        """Cells no training camera sees get density -1 forever (renderer.py:408-471)."""
-        if not self.cuda_ray:
-            return
-        if isinstance(poses, np.ndarray):
-            poses = torch.from_numpy(poses)
-        B = poses.shape[0]
-        fx, fy, cx, cy = intrinsic
+    def _grid_blocks(self, S):
+        """Cells of the 128^3 occupancy grid in S^3 blocks: yields (integer coords [n,3], Morton indices [n])."""
         dev = self.density_grid.device
         axis = torch.arange(self.grid_size, dtype=torch.int32, device=dev).split(S)
-        count = torch.zeros_like(self.density_grid)
-        poses = poses.to(dev)
         for xs in axis:
             for ys in axis:
                 for zs in axis:
-                    xx, yy, zz = custom_meshgrid(xs, ys, zs)
-                    coords = torch.stack([xx.reshape(-1), yy.reshape(-1), zz.reshape(-1)], dim=-1)
-                    indices = raymarching.morton3D(coords).long()
-                    for cas in range(self.cascade):
-                        world, half_grid_size = self._cell_centres(coords, cas)
-                        world = world.unsqueeze(0)
-                        for head in range(0, B, S):
-                            tail = min(head + S, B)
-                            cam = (world - poses[head:tail, :3, 3].unsqueeze(1)) @ poses[head:tail, :3, :3]
-                            seen = (cam[:, :, 2] > 0) \
-                                & (cam[:, :, 0].abs() < cx / fx * cam[:, :, 2] + half_grid_size * 2) \
-                                & (cam[:, :, 1].abs() < cy / fy * cam[:, :, 2] + half_grid_size * 2)
-                            count[cas, indices] += seen.sum(0).reshape(-1)
-        self.density_grid[count == 0] = -1
+                    coords = torch.stack([g.reshape(-1) for g in custom_meshgrid(xs, ys, zs)], dim=-1)
+                    yield coords, raymarching.morton3D(coords).long()
+
+    @torch.no_grad()
+    def mark_untrained_grid(self, poses, intrinsic, S=64):
+        """Cells that no training camera sees keep density -1 forever (renderer.py:408-471)."""
+        if not self.cuda_ray:
+            return
+        poses = torch.as_tensor(poses).to(self.density_grid.device)
+        fx, fy, cx, cy = intrinsic
+        seen_by = torch.zeros_like(self.density_grid)
+        for coords, indices in self._grid_blocks(S):
+            for cas in range(self.cascade):
+                world, half_cell = self._cell_centres(coords, cas)
+                for first in range(0, poses.shape[0], S):
+                    cams = poses[first:first + S]
+                    local = (world.unsqueeze(0) - cams[:, :3, 3].unsqueeze(1)) @ cams[:, :3, :3]       # world -> camera frame
+                    depth = local[..., 2]
+                    inside = (depth > 0) & (local[..., 0].abs() < cx / fx * depth + half_cell * 2) \
+                        & (local[..., 1].abs() < cy / fy * depth + half_cell * 2)
+                    seen_by[cas, indices] += inside.sum(0).to(seen_by.dtype)
+        self.density_grid[seen_by == 0] = -1
 
     @torch.no_grad()
     def update_extra_state(self, decay=0.95, S=128):
-        """EMA-max refresh of density_grid + bitfield + mean sample count (renderer.py:474-563)."""
+        """EMA-max refresh of density_grid, its bitfield and the mean sample count (renderer.py:474-563)."""
         if not self.cuda_ray:
             return
         dev = self.density_grid.device
-        tmp_grid = -torch.ones_like(self.density_grid)
+        fresh = torch.full_like(self.density_grid, -1.0)
 
-        def query(coords, cas):
-            cas_xyzs, half_grid_size = self._cell_centres(coords, cas)
-            cas_xyzs = cas_xyzs + (torch.rand_like(cas_xyzs) * 2 - 1) * half_grid_size
-            sigmas = self.density(cas_xyzs)['sigma'].reshape(-1).detach().float()
-            return sigmas * (self.density_scale * 0.003383)
+        def sample_density(coords, cas):
+            centres, half_cell = self._cell_centres(coords, cas)
+            jittered = centres + (torch.rand_like(centres) * 2 - 1) * half_cell
+            sigma = self.density(jittered)['sigma'].reshape(-1).detach().float()
+            return sigma * (self.density_scale * 0.003383)          # density * nominal step length (renderer.py:512)
 
-        if self.iter_density < 16:      # full pass
-            axis = torch.arange(self.grid_size, dtype=torch.int32, device=dev).split(S)
-            for xs in axis:
-                for ys in axis:
-                    for zs in axis:
-                        xx, yy, zz = custom_meshgrid(xs, ys, zs)
-                        coords = torch.stack([xx.reshape(-1), yy.reshape(-1), zz.reshape(-1)], dim=-1)
-                        indices = raymarching.morton3D(coords).long()
-                        for cas in range(self.cascade):
-                            tmp_grid[cas, indices] = query(coords, cas)
-        else:                            # partial pass: uniform cells + currently occupied cells
-            N = self.grid_size ** 3 // 4
+        if self.iter_density < 16:                                   # first 16 refreshes: every cell of every cascade
+            for coords, indices in self._grid_blocks(S):
+                for cas in range(self.cascade):
+                    fresh[cas, indices] = sample_density(coords, cas)
+        else:                                                        # afterwards: a quarter of the cells at random + as many occupied ones
+            n_pick = self.grid_size ** 3 // 4
             for cas in range(self.cascade):
-                coords = torch.randint(0, self.grid_size, (N, 3), device=dev)
-                indices = raymarching.morton3D(coords).long()
-                occ_indices = torch.nonzero(self.density_grid[cas] > 0).squeeze(-1)
-                pick = torch.randint(0, occ_indices.shape[0], [N], dtype=torch.long, device=dev)
-                occ_indices = occ_indices[pick]
-                occ_coords = raymarching.morton3D_invert(occ_indices)
-                indices = torch.cat([indices, occ_indices], dim=0)
-                coords = torch.cat([coords, occ_coords], dim=0)
-                tmp_grid[cas, indices] = query(coords, cas)
+                rand_coords = torch.randint(0, self.grid_size, (n_pick, 3), device=dev)
+                rand_idx = raymarching.morton3D(rand_coords).long()
+                occupied = torch.nonzero(self.density_grid[cas] > 0).squeeze(-1)
+                occ_idx = occupied[torch.randint(0, occupied.shape[0], [n_pick], dtype=torch.long, device=dev)]
+                occ_coords = raymarching.morton3D_invert(occ_idx)
+                fresh[cas, torch.cat([rand_idx, occ_idx])] = sample_density(torch.cat([rand_coords, occ_coords]), cas)
 
-        valid = (self.density_grid >= 0) & (tmp_grid >= 0)
-        self.density_grid[valid] = torch.maximum(self.density_grid[valid] * decay, tmp_grid[valid])
+        both = (self.density_grid >= 0) & (fresh >= 0)
+        self.density_grid[both] = torch.maximum(self.density_grid[both] * decay, fresh[both])
         self.mean_density = torch.mean(self.density_grid.clamp(min=0)).item()
         self.iter_density += 1
-        density_thresh = min(self.mean_density, self.density_thresh)
-        self.density_bitfield = raymarching.packbits(self.density_grid, density_thresh, self.density_bitfield)
+        self.density_bitfield = raymarching.packbits(self.density_grid, min(self.mean_density, self.density_thresh), self.density_bitfield)
 
-        total_step = min(16, self.local_step)
-        if total_step > 0:
-            self.mean_count = int(self.step_counter[:total_step, 0].sum().item() / total_step)
+        counted = min(16, self.local_step)
+        if counted > 0:
+            self.mean_count = int(self.step_counter[:counted, 0].sum().item() / counted)
         self.local_step = 0
 
     # ------------------------------------------------------------------ dispatcher
