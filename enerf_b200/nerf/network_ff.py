@@ -35,53 +35,47 @@ class NeRFNetwork(NeRFRenderer):
                                num_layers=self.num_layers_color)
 
     def _color_inputs(self, d, geo_feat):
-        d = self.encoder_dir(d)
+        """[SH(d) (16) | geo_feat (15) | 0] — the 32-wide colour-net input of network_ff.py:64-67"""
+        sh = self.encoder_dir(d)
         if self.disable_view_direction:
-            d = d * 0
-        pad = torch.zeros_like(geo_feat[..., :1])
-        return torch.cat([d, geo_feat, pad], dim=-1)
+            sh = sh * 0
+        return torch.cat([sh, geo_feat, geo_feat.new_zeros(*geo_feat.shape[:-1], 1)], dim=-1)
+
+    def _sigma_head(self, x):
+        h = self.sigma_net(self.encoder(x, bound=self.bound))
+        return trunc_exp(h[..., 0]), h[..., 1:]
 
     def forward(self, x, d):
-        # x [N,3] in [-bound,bound], d [N,3] unit -> sigma [N] fp32, rgb [N,C]
-        if self.fuse_field and torch.is_autocast_enabled('cuda') and not self.disable_view_direction:
+        """x [N,3] in [-bound, bound], d [N,3] unit  ->  sigma [N] fp32, rgb [N, out_dim_color]"""
+        fusable = self.fuse_field and not self.disable_view_direction and torch.is_autocast_enabled('cuda')
+        if fusable:
             feat = self.encoder(x, bound=self.bound)
             if field.eligible(feat, d, self.hidden_dim, self.hidden_dim_color, self.in_dim, self.in_dim_color, self.geo_feat_dim,
                               getattr(self.encoder_dir, 'degree', -1), self.out_dim_color, self.sigma_net.activation):
                 return field.fused_field(feat, d, self.sigma_net.weights, self.color_net.weights, self.num_layers, self.num_layers_color,
                                          self.out_dim_color, self.training and torch.is_grad_enabled())
             h = self.sigma_net(feat)
+            sigma, geo_feat = trunc_exp(h[..., 0]), h[..., 1:]
         else:
-            h = self.sigma_net(self.encoder(x, bound=self.bound))
-        sigma = trunc_exp(h[..., 0])
-        geo_feat = h[..., 1:]
-        rgb = torch.sigmoid(self.color_net(self._color_inputs(d, geo_feat)))
-        return sigma, rgb
+            sigma, geo_feat = self._sigma_head(x)
+        return sigma, torch.sigmoid(self.color_net(self._color_inputs(d, geo_feat)))
 
     def density(self, x):
-        h = self.sigma_net(self.encoder(x, bound=self.bound))
-        return {'sigma': trunc_exp(h[..., 0]), 'geo_feat': h[..., 1:]}
+        sigma, geo_feat = self._sigma_head(x)
+        return {'sigma': sigma, 'geo_feat': geo_feat}
 
     def color(self, x, d, mask=None, geo_feat=None, **kwargs):
-        # masked colour query (network_ff.py:92-133): rows outside `mask` stay zero
-        if mask is not None:
-            rgbs = torch.zeros(mask.shape[0], self.out_dim_color, dtype=x.dtype, device=x.device)
-            if not mask.any():
-                return rgbs
-            d, geo_feat = d[mask], geo_feat[mask]
-        h = torch.sigmoid(self.color_net(self._color_inputs(d, geo_feat)))
-        if mask is not None:
-            rgbs[mask] = h.to(rgbs.dtype)
-            return rgbs
-        return h
+        """Colour query for the rows selected by `mask` (all rows without one); unselected rows stay zero (network_ff.py:92-133)."""
+        if mask is None:
+            return torch.sigmoid(self.color_net(self._color_inputs(d, geo_feat)))
+        rgbs = torch.zeros(mask.shape[0], self.out_dim_color, dtype=x.dtype, device=x.device)
+        if mask.any():
+            picked = torch.sigmoid(self.color_net(self._color_inputs(d[mask], geo_feat[mask])))
+            rgbs[mask] = picked.to(rgbs.dtype)
+        return rgbs
 
     def get_params(self, lr):
-        params = [
-            {'params': self.encoder.parameters(), 'lr': lr},
-            {'params': self.sigma_net.parameters(), 'lr': lr},
-            {'params': self.encoder_dir.parameters(), 'lr': lr},
-            {'params': self.color_net.parameters(), 'lr': lr},
-        ]
+        groups = [self.encoder, self.sigma_net, self.encoder_dir, self.color_net]
         if self.bg_radius > 0:
-            params.append({'params': self.encoder_bg.parameters(), 'lr': lr})
-            params.append({'params': self.bg_net.parameters(), 'lr': lr})
-        return params
+            groups += [self.encoder_bg, self.bg_net]
+        return [{'params': m.parameters(), 'lr': lr} for m in groups]
