@@ -29,9 +29,10 @@ sys.path.insert(0, ROOT)
 
 METRIC, UNIT = "train_rays_per_sec", "rays/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this workload (bytes)
-NCU_TRAFFIC_SRC = "profiles/r1_04_ncu_full_step_kernels.md (3.29 M samples/launch)"
-NCU_TRAFFIC = {"grid_encode_backward": 0.292428e9 + 0.008309e9, "grid_encode_forward": 0.062685e9 + 0.166211e9,
-               "march_rays_train": 0.000848e9 + 0.049901e9}
+NCU_TRAFFIC_SRC = "profiles/r1_22_ncu_full_step_kernels.md (3.29 M samples/launch)"
+NCU_TRAFFIC = {"grid_encode_backward": 292.386816e6 + 7.179008e6, "grid_encode_forward": 62.409472e6 + 167.536640e6,
+               "march_rays_train": 0.890112e6 + 46.206976e6, "field_color_backward": 236.773888e6 + 166.257664e6,
+               "field_sigma_backward": 447.215616e6 + 179.539712e6}
 RAYS = 4096
 BOUND = 3
 
@@ -46,6 +47,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"], help="replay the step from a CUDA graph (auto: fall back to eager launches if capture fails)")
     ap.add_argument("--cpu-rays", type=int, default=256, help="rays per CPU-baseline step (bounded sample)")
+    ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"], help="Adam step: this repo's fused kernel or torch.optim.Adam(fused=True)")
     ap.add_argument("--no-render", action="store_true", help="skip the full-frame inference measurement (the `render` object of the line)")
     return ap.parse_args()
 
@@ -232,7 +234,13 @@ def our_arm(args):
     model.density_bitfield.copy_(torch.from_numpy(synthetic.packbits_np(grid)))
     opt_kwargs = dict(num_steps=512, upsample_steps=0, max_ray_batch=5096, dt_gamma=0, out_dim_color=1)
 
-    optimizer = torch.optim.Adam(model.get_params(5e-3), betas=(0.9, 0.99), eps=1e-15, fused=True, capturable=True)
+    # E-NeRF's optimizer (main_nerf.py:211-214: Adam, betas (0.9, 0.99), eps 1e-15): this repo's fused step (enerf_b200/optim.py,
+    # same update rule, parity-tested against torch's) or torch's own fused Adam with --optimizer torch
+    if args.optimizer == "fused":
+        from enerf_b200.optim import FusedAdam
+        optimizer = FusedAdam(model.get_params(5e-3), betas=(0.9, 0.99), eps=1e-15)
+    else:
+        optimizer = torch.optim.Adam(model.get_params(5e-3), betas=(0.9, 0.99), eps=1e-15, fused=True, capturable=True)
     scaler = torch.amp.GradScaler("cuda", enabled=True)
     reducer = parallel.GradientAllReduce(list(model.parameters()), average=True)
 
@@ -397,7 +405,7 @@ def our_arm(args):
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": workload_config(n_rays, {"samples_per_step_per_gpu": S, "parallelism": f"dp{world} (ray-sharded, NCCL grad allreduce)", "launch": "cuda-graph replay" if graphed is not None else "eager",
+            "config": workload_config(n_rays, {"samples_per_step_per_gpu": S, "parallelism": f"dp{world} (ray-sharded, NCCL grad allreduce)", "launch": "cuda-graph replay" if graphed is not None else "eager", "optimizer": "enerf_b200.optim.FusedAdam" if args.optimizer == "fused" else "torch.optim.Adam(fused)",
                                                "l2": "per-step working set (samples x ~1.7 KB of activations + 52 MB grad table) is >> 126 MB L2; no explicit flush"}),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "kernels": kernels,
             "cpu_baseline": cpu_baseline, "render": render, "final_loss": float(loss_host), "host_enqueue_ms_per_step": host_enqueue_ms}

@@ -1,0 +1,74 @@
+// Fused Adam step — the optimizer E-NeRF runs after every backward of the path:
+// `torch.optim.Adam(model.get_params(lr), betas=(0.9, 0.99), eps=1e-15)` (main_nerf.py:211-214) over the 13 M-entry hash
+// table and the two flat MLP weight vectors, under a GradScaler.  One pass per tensor: 16-byte loads of p, g, m, v, the
+// update in registers (same operation order as torch's FusedAdamMathFunctor), 16-byte stores of p, m, v; the gradient is
+// un-scaled on the fly (grad_scale) and the whole step is skipped on the device when the scaler found an inf/nan
+// (found_inf), so nothing here synchronises with the host and the step can live inside a CUDA graph.
+// Purely HBM-bound: 28 bytes per parameter.
+#include "common.cuh"
+
+namespace enerf {
+
+struct AdamArgs {
+    float lr, beta1, beta2, eps, weight_decay;
+};
+
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, const AdamArgs& a, float inv_scale, float step_size, float bc2_sqrt) {
+    g *= inv_scale;
+    if (a.weight_decay != 0.f) g = __fmaf_rn(a.weight_decay, p, g);
+    m = m + (1.0f - a.beta1) * (g - m);                           // lerp(exp_avg, grad, 1 - beta1)
+    v = a.beta2 * v + (1.0f - a.beta2) * g * g;
+    const float denom = sqrtf(v) / bc2_sqrt + a.eps;
+    p -= step_size * m / denom;
+}
+
+__global__ void __launch_bounds__(256)
+k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, uint64_t n,
+       const float* __restrict__ step, AdamArgs a, const float* __restrict__ grad_scale, const float* __restrict__ found_inf) {
+    if (found_inf && *found_inf != 0.f) return;                  // the scaler skips this step
+    const float t = *step;                                        // already incremented by the caller
+    const float inv_scale = grad_scale ? 1.0f / *grad_scale : 1.0f;
+    const float bc1 = 1.0f - powf(a.beta1, t), bc2 = 1.0f - powf(a.beta2, t);
+    const float step_size = a.lr / bc1, bc2_sqrt = sqrtf(bc2);
+    const uint64_t n4 = n >> 2;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 P = reinterpret_cast<float4*>(p)[i], M = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i];
+        const float4 G = __ldg(reinterpret_cast<const float4*>(g) + i);
+        adam_one(P.x, G.x, M.x, V.x, a, inv_scale, step_size, bc2_sqrt);
+        adam_one(P.y, G.y, M.y, V.y, a, inv_scale, step_size, bc2_sqrt);
+        adam_one(P.z, G.z, M.z, V.z, a, inv_scale, step_size, bc2_sqrt);
+        adam_one(P.w, G.w, M.w, V.w, a, inv_scale, step_size, bc2_sqrt);
+        reinterpret_cast<float4*>(p)[i] = P;
+        reinterpret_cast<float4*>(m)[i] = M;
+        reinterpret_cast<float4*>(v)[i] = V;
+    }
+    // tail (n not a multiple of 4)
+    const uint64_t tail0 = n4 << 2;
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid < n - tail0) {
+        const uint64_t i = tail0 + gid;
+        adam_one(p[i], g[i], m[i], v[i], a, inv_scale, step_size, bc2_sqrt);
+    }
+}
+
+}  // namespace enerf
+
+using namespace enerf;
+
+extern "C" int enerf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, uint64_t n, const float* step, float lr,
+                               float beta1, float beta2, float eps, float weight_decay, const float* grad_scale, const float* found_inf,
+                               void* stream) {
+    if (n == 0) return 0;
+    ENERF_REQUIRE(step != nullptr, "adam_step", "step must be a device pointer to the (already incremented) step count");
+    ENERF_REQUIRE(((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(exp_avg) |
+                    reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15u) == 0, "adam_step", "tensors must be 16-byte aligned");
+    const AdamArgs a = {lr, beta1, beta2, eps, weight_decay};
+    const uint64_t n4 = n >> 2;
+    uint64_t blocks = (n4 + 255) / 256;
+    if (blocks > (uint64_t)kNumSM * 16) blocks = (uint64_t)kNumSM * 16;
+    if (blocks == 0) blocks = 1;
+    k_adam<<<(uint32_t)blocks, 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, step, a, grad_scale, found_inf);
+    ENERF_CHECK_LAUNCH("adam_step");
+    return 0;
+}

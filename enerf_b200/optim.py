@@ -1,0 +1,52 @@
+"""`FusedAdam` — drop-in for the optimizer E-NeRF builds in main_nerf.py:211-214,
+`torch.optim.Adam(model.get_params(lr), betas=(0.9, 0.99), eps=1e-15)`.
+
+Same update rule and state names (`step`, `exp_avg`, `exp_avg_sq`) as torch's Adam, one kernel per parameter tensor
+(28 bytes of HBM traffic per parameter), device-side step counters, and the GradScaler protocol of torch's fused optimizers
+(`_step_supports_amp_scaling`: `GradScaler.step` hands over `grad_scale` / `found_inf`, the kernel un-scales on the fly and
+skips the step on overflow), so a whole training iteration stays capturable in a CUDA graph.  CUDA fp32 parameters only.
+"""
+import torch
+
+from . import _lib
+from ._lib import ptr, stream
+
+
+class FusedAdam(torch.optim.Optimizer):
+    _step_supports_amp_scaling = True
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        if lr < 0 or eps < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1) or weight_decay < 0:
+            raise ValueError("FusedAdam: invalid hyper-parameter")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        if closure is not None:
+            raise RuntimeError("FusedAdam does not take a closure")
+        grad_scale = getattr(self, "grad_scale", None)
+        found_inf = getattr(self, "found_inf", None)
+        for group in self.param_groups:
+            b1, b2 = group["betas"]
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                    raise RuntimeError("FusedAdam: contiguous CUDA fp32 parameters only (there is no CPU path)")
+                g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                if g.dtype != torch.float32:
+                    g = g.float()
+                st = self.state[p]
+                if not st:
+                    st["step"] = torch.zeros((), dtype=torch.float32, device=p.device)
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                # device-side counter: advances only when the step is not skipped (as torch's capturable Adam does)
+                if found_inf is not None:
+                    st["step"] += 1.0 - found_inf.to(st["step"].device).reshape(())
+                else:
+                    st["step"] += 1.0
+                _lib.call("enerf_adam_step", ptr(p), ptr(g), ptr(st["exp_avg"]), ptr(st["exp_avg_sq"]), p.numel(), ptr(st["step"]),
+                          float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
+                          ptr(grad_scale), ptr(found_inf), stream())
+        return None

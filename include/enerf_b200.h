@@ -259,6 +259,13 @@ int enerf_event_loss_backward(const float* img1, const float* img2, const float*
                               const float* acc, const float* grad_loss, uint32_t N, uint32_t C, int use_luma,
                               int linlog, float log_thres, float c_thres, float weight, float* grad_img1,
                               float* grad_img2, void* stream);
+/* N4 — the optimizer step that follows every backward of the path: torch.optim.Adam as configured by main_nerf.py:211-214
+ * (amsgrad off, maximize off), fused into one pass per tensor.  `step`: device pointer to the step count of this parameter,
+ * ALREADY incremented for this step; grad_scale / found_inf: the GradScaler's device scalars (NULL = 1 / 0): gradients are
+ * divided by *grad_scale on the fly and the call is a no-op when *found_inf != 0.  fp32 tensors, 16-byte aligned. */
+int enerf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, uint64_t n, const float* step,
+                    float lr, float beta1, float beta2, float eps, float weight_decay, const float* grad_scale,
+                    const float* found_inf, void* stream);
 
 #ifdef __cplusplus
 }

@@ -119,3 +119,35 @@ def test_gpu_event_loss_forward_backward_matches_reference():
     assert abs(float(loss) - want) <= 2e-4 * abs(want) and np.allclose(delta.cpu().numpy(), wdelta, atol=5e-6)
     loss.backward()
     assert torch.isfinite(a1.grad).all() and float(a1.grad.abs().sum()) > 0
+
+
+@pytest.mark.gpu
+def test_gpu_fused_adam_matches_torch_adam_with_grad_scaler():
+    """N4: FusedAdam vs torch.optim.Adam (E-NeRF's hyper-parameters) over 20 steps, driven through a GradScaler, including a
+    step with an overflowing gradient that both must skip."""
+    from enerf_b200.optim import FusedAdam
+    dev = "cuda"
+    torch.manual_seed(0)
+    shapes = [(100003, 2), (7168,), (5,)]
+    ref_p = [torch.nn.Parameter(torch.randn(s, device=dev) * 0.1) for s in shapes]
+    our_p = [torch.nn.Parameter(p.detach().clone()) for p in ref_p]
+    kw = dict(lr=5e-3, betas=(0.9, 0.99), eps=1e-15)
+    ref_opt = torch.optim.Adam(ref_p, fused=True, capturable=True, **kw)
+    our_opt = FusedAdam(our_p, **kw)
+    ref_sc, our_sc = torch.amp.GradScaler("cuda", init_scale=1024.0), torch.amp.GradScaler("cuda", init_scale=1024.0)
+    for it in range(20):
+        grads = [torch.randn(s, device=dev) * (10.0 ** ((it % 5) - 3)) for s in shapes]
+        if it == 7:
+            grads[1][3] = float("inf")
+        for ps, opt, sc in ((ref_p, ref_opt, ref_sc), (our_p, our_opt, our_sc)):
+            scale = sc.scale(torch.ones((), device=dev))            # also initialises the scaler lazily, as scale(loss) does
+            for p, g in zip(ps, grads):
+                p.grad = g * scale
+            sc.step(opt)
+            sc.update()
+    assert ref_sc.get_scale() == our_sc.get_scale() == 512.0          # one skipped step halved the scale
+    for a, b in zip(ref_p, our_p):
+        assert torch.isfinite(b).all()
+        err = float((a - b).abs().max())
+        assert err <= 2e-6 * float(a.abs().max()) + 1e-8, err
+    assert float(our_opt.state[our_p[0]]["step"]) == float(ref_opt.state[ref_p[0]]["step"]) == 19.0
