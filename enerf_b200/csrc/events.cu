@@ -292,3 +292,45 @@ int enerf_event_loss_backward(const float* img1, const float* img2, const float*
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------- N3: event-pair sampler
+// nerf/provider.py:1364-1405 (`EventNeRFDataset.collate`, accumulate_evs branch) draws, for each of the M pairs of a step, a start
+// event, moves it one back if it is the last event of its pixel, draws an end event among its successors at the same pixel and
+// sums the polarities in between — a Python loop with one GPU slice + .sum() per pair.  Here the events of a frame stay resident
+// ([E,4] = x, y, t, polarity, grouped by pixel as the provider lays them out), the polarity sums come from an exclusive prefix sum
+// (double: exact for +-1 polarities at any E), and one thread per pair turns two uniform variates into (start, end, sum_pol) and —
+// given the per-event poses [E,3,4] — directly into the two rays of the pair (the get_event_rays kernel above).
+namespace enerf {
+
+__global__ void k_sample_event_pairs(const float* __restrict__ events, const double* __restrict__ pol_prefix, const int32_t* __restrict__ num_succ,
+                                     const uint8_t* __restrict__ no_succ, uint32_t E, uint32_t M, int32_t acc_max, const float* __restrict__ u_start,
+                                     const float* __restrict__ u_end, int64_t* __restrict__ eidx, int64_t* __restrict__ eidx_end,
+                                     float* __restrict__ pols, float* __restrict__ xs, float* __restrict__ ys) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= M) return;
+    // start ~ U{0..E-1} (np.random.randint(0, E)); a pixel's last event has no successor: take its predecessor (provider.py:1369-1371)
+    uint32_t s = min((uint32_t)(__ldg(u_start + t) * (float)E), E - 1);
+    if (no_succ[s]) s -= 1;
+    int32_t n = num_succ[s];
+    if (acc_max > 0) n = min(n, acc_max + 1);                       // provider.py:1378-1379
+    // end ~ U{s+1 .. s+n} (np.random.randint(s+1, s+1+n))
+    const uint32_t e = s + 1 + min((uint32_t)(__ldg(u_end + t) * (float)n), (uint32_t)(n - 1));
+    eidx[t] = s;
+    eidx_end[t] = e;
+    pols[t] = (float)(pol_prefix[e + 1] - pol_prefix[s + 1]);       // sum of events[s+1 .. e, 3]
+    xs[t] = __ldg(events + (size_t)s * 4);
+    ys[t] = __ldg(events + (size_t)s * 4 + 1);
+}
+
+}  // namespace enerf
+
+extern "C" int enerf_sample_event_pairs(const float* events, const double* pol_prefix, const int32_t* num_successors, const uint8_t* no_successor,
+                                        uint32_t E, uint32_t M, int32_t acc_max_num_evs, const float* u_start, const float* u_end, int64_t* eidx,
+                                        int64_t* eidx_end, float* pols, float* xs, float* ys, void* stream) {
+    if (M == 0) return 0;
+    ENERF_REQUIRE(E >= 2, "sample_event_pairs", "a frame needs at least two events");
+    enerf::k_sample_event_pairs<<<enerf::ceil_div(M, 256u), 256, 0, enerf::as_stream(stream)>>>(events, pol_prefix, num_successors, no_successor, E, M,
+                                                                                       acc_max_num_evs, u_start, u_end, eidx, eidx_end, pols, xs, ys);
+    ENERF_CHECK_LAUNCH("sample_event_pairs");
+    return 0;
+}

@@ -133,3 +133,45 @@ def event_loss(image1, image2, pols, use_luma=False, linlog=True, C_thres=-1, ev
         weight = 20.0 * (1.0 if event_only else 20.0)      # utils.py:522-525
     loss, delta = _EventLoss.apply(image1, image2, pols, bool(use_luma), bool(linlog), float(log_thres), float(C_thres), weight)
     return loss, delta.view(*image1.shape[:-1], delta.shape[-1])
+
+
+class EventPairSampler:
+    """Device-resident replacement for the per-pair Python loop of `EventNeRFDataset.collate` (nerf/provider.py:1364-1405,
+    accumulate_evs branch) for ONE event frame: keeps the frame's events, their polarity prefix sum, the successor counts and the
+    "last event of its pixel" mask on the GPU and draws M pairs per call with one kernel.
+
+        sampler = EventPairSampler(events_fidx, num_successor_evs_fidx, idx_no_successor_fidx, acc_max_num_evs, poses_evs_fidx)
+        batch = sampler.sample(M, intrinsics_evs)      # -> xs, ys, pols [1,M], eidx, eidx_end, rays_evs_o1/d1/o2/d2 [1,M,3]
+
+    The pairs follow the reference's distribution (uniform start event, predecessor if it has no successor, uniform end event among
+    the at most acc_max_num_evs+1 successors); the random variates come from torch's CUDA generator instead of NumPy's global one.
+    """
+
+    def __init__(self, events, num_successor_evs, idx_no_successor, acc_max_num_evs=0, poses_evs=None, device="cuda"):
+        self.events = torch.as_tensor(events, dtype=torch.float32).to(device).contiguous()
+        E = self.events.shape[0]
+        self.E = E
+        pol = self.events[:, 3].double()
+        self.pol_prefix = torch.cat([torch.zeros(1, dtype=torch.float64, device=device), torch.cumsum(pol, 0)]).contiguous()
+        self.num_succ = torch.as_tensor(num_successor_evs).to(device=device, dtype=torch.int32).contiguous()
+        mask = torch.zeros(E, dtype=torch.uint8, device=device)
+        mask[torch.as_tensor(idx_no_successor).to(device=device, dtype=torch.long)] = 1
+        self.no_succ = mask
+        self.acc_max = int(acc_max_num_evs or 0)
+        self.poses_evs = None if poses_evs is None else torch.as_tensor(poses_evs, dtype=torch.float32).to(device).contiguous()
+
+    def sample(self, M, intrinsics_evs=None, u_start=None, u_end=None, aabb=None, min_near=0.2):
+        dev = self.events.device
+        u_start = torch.rand(M, device=dev) if u_start is None else u_start.to(dev).float().contiguous()
+        u_end = torch.rand(M, device=dev) if u_end is None else u_end.to(dev).float().contiguous()
+        eidx = torch.empty(M, dtype=torch.int64, device=dev)
+        eidx_end = torch.empty(M, dtype=torch.int64, device=dev)
+        pols, xs, ys = (torch.empty(M, dtype=torch.float32, device=dev) for _ in range(3))
+        _lib.call("enerf_sample_event_pairs", ptr(self.events), ptr(self.pol_prefix), ptr(self.num_succ), ptr(self.no_succ), self.E, M, self.acc_max,
+                  ptr(u_start), ptr(u_end), ptr(eidx), ptr(eidx_end), ptr(pols), ptr(xs), ptr(ys), stream())
+        out = {"eidx": eidx, "eidx_end": eidx_end, "pols": pols.unsqueeze(0), "xs": xs.unsqueeze(0), "ys": ys.unsqueeze(0)}
+        if self.poses_evs is not None and intrinsics_evs is not None:
+            p1 = self.poses_evs[eidx].unsqueeze(0)          # (1, M, 3, 4), provider.py:1417-1418
+            p2 = self.poses_evs[eidx_end].unsqueeze(0)
+            out.update(get_event_rays_with_near_far(out["xs"], out["ys"], p1, p2, intrinsics_evs, aabb=aabb, min_near=min_near))
+        return out

@@ -266,6 +266,15 @@ int enerf_event_loss_backward(const float* img1, const float* img2, const float*
 int enerf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, uint64_t n, const float* step,
                     float lr, float beta1, float beta2, float eps, float weight_decay, const float* grad_scale,
                     const float* found_inf, void* stream);
+/* N3 — event-pair sampler, nerf/provider.py:1364-1405 (collate, accumulate_evs branch).  events [E,4] fp32 = (x, y, t, polarity),
+ * grouped by pixel as the provider stores them; pol_prefix [E+1] double = exclusive prefix sum of the polarity column;
+ * num_successors [E] (provider.py:1181-1187), no_successor [E] = 1 for the last event of a pixel (:1177-1178); u_start, u_end [M]
+ * uniform variates in [0,1) supplied by the caller (start = floor(u_start*E), end = start+1+floor(u_end*n)).  Outputs: event ids of
+ * the pair, the accumulated polarity between them and the pixel of the start event. */
+int enerf_sample_event_pairs(const float* events, const double* pol_prefix, const int32_t* num_successors,
+                             const uint8_t* no_successor, uint32_t E, uint32_t M, int32_t acc_max_num_evs,
+                             const float* u_start, const float* u_end, int64_t* eidx, int64_t* eidx_end, float* pols,
+                             float* xs, float* ys, void* stream);
 
 #ifdef __cplusplus
 }

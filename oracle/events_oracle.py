@@ -66,3 +66,21 @@ def event_loss(img1, img2, pols, use_luma, linlog, C_thres, event_only, log_thre
     dn = d64 / (np.linalg.norm(d64, axis=-2, keepdims=True) + 1e-9)
     pn = gt / (np.linalg.norm(gt, axis=-2, keepdims=True) + 1e-9)
     return float(w * np.mean((dn - pn) ** 2)), delta
+
+
+def sample_event_pairs(events, num_succ, idx_no_successor, acc_max, u_start, u_end):
+    """nerf/provider.py:1364-1405 (accumulate_evs branch) with the integer draws derived from uniform variates the way the
+    device sampler does (fp32: start = floor(u*E), end = start+1+floor(u*n)).  -> eidx, eidx_end, pols, xs, ys"""
+    E = events.shape[0]
+    no_succ = set(int(i) for i in idx_no_successor)
+    eidx = np.minimum((u_start.astype(F) * F(E)).astype(np.int64), E - 1)
+    eidx = np.asarray([i - 1 if int(i) in no_succ else i for i in eidx])
+    ends, pols = [], []
+    for k, s in enumerate(eidx):
+        n = int(num_succ[s])
+        if acc_max:
+            n = min(n, acc_max + 1)
+        e = s + 1 + min(int(F(u_end[k]) * F(n)), n - 1)
+        pols.append(events[s + 1:e + 1, 3].sum())
+        ends.append(e)
+    return eidx, np.asarray(ends), np.asarray(pols, F), events[eidx, 0], events[eidx, 1]

@@ -151,3 +151,42 @@ def test_gpu_fused_adam_matches_torch_adam_with_grad_scaler():
         err = float((a - b).abs().max())
         assert err <= 2e-6 * float(a.abs().max()) + 1e-8, err
     assert float(our_opt.state[our_p[0]]["step"]) == float(ref_opt.state[ref_p[0]]["step"]) == 19.0
+
+
+# ------------------------------------------------------------------ N3: event-pair sampler
+S = np.load(os.path.join(os.path.dirname(__file__), "golden", "sampler.npz"))
+
+
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_oracle_event_pair_sampler_reproduces_reference_collate(case):
+    ev = S[case + "_events"]
+    eidx, eend, pols, xs, ys = eo.sample_event_pairs(ev, S[case + "_num_succ"], S[case + "_no_succ"], int(S[case + "_acc_max"]),
+                                                     S[case + "_u_start"], S[case + "_u_end"])
+    assert np.array_equal(pols, S[case + "_pols"][0])
+    assert np.all(eend > eidx) and np.all(ev[eidx, 0] == ev[eend, 0]) and np.all(ev[eidx, 1] == ev[eend, 1])      # same pixel, later event
+    r = eo.get_event_rays(xs, ys, S[case + "_poses_evs"][eidx][None], S[case + "_poses_evs"][eend][None], S[case + "_intr"])
+    for k in ("o1", "d1", "o2", "d2"):
+        assert np.allclose(r["rays_evs_" + k], S[case + "_" + k], atol=2e-7), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_gpu_event_pair_sampler_matches_reference_collate(case):
+    from enerf_b200 import events
+    dev = "cuda"
+    sampler = events.EventPairSampler(S[case + "_events"], S[case + "_num_succ"], S[case + "_no_succ"], int(S[case + "_acc_max"]),
+                                      S[case + "_poses_evs"], device=dev)
+    out = sampler.sample(len(S[case + "_u_start"]), S[case + "_intr"], u_start=torch.from_numpy(S[case + "_u_start"]),
+                         u_end=torch.from_numpy(S[case + "_u_end"]))
+    assert torch.equal(out["pols"].cpu(), torch.from_numpy(S[case + "_pols"]))
+    for k in ("o1", "d1", "o2", "d2"):
+        assert np.allclose(out["rays_evs_" + k].cpu().numpy(), S[case + "_" + k], atol=3e-7), k
+    # free-running draws: valid pairs, right distribution support
+    out = sampler.sample(4096)
+    ev = S[case + "_events"]
+    s, e = out["eidx"].cpu().numpy(), out["eidx_end"].cpu().numpy()
+    assert np.all(e > s) and np.all(ev[s, 0] == ev[e, 0]) and np.all(ev[s, 1] == ev[e, 1])
+    acc_max = int(S[case + "_acc_max"])
+    if acc_max:
+        assert (e - s).max() <= acc_max + 1
+    assert np.array_equal(out["pols"].cpu().numpy()[0], np.array([ev[a + 1:b + 1, 3].sum() for a, b in zip(s, e)], np.float32))
