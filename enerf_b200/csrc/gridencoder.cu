@@ -16,6 +16,7 @@
 //     grid.py:70) and scatters with vector reductions (red.global.add.v2.f32 / .noftz.f16x2).
 #include "common.cuh"
 #include <math.h>
+#include <stdlib.h>
 #include <type_traits>
 
 namespace enerf {
@@ -835,9 +836,19 @@ static int launch_fwd(const float* inputs, const T* emb, const int32_t* offsets,
         const uint32_t n_groups = ceil_div(B, 32u);
         const uint32_t row_words = (L * kWpl) | 1u;
         const size_t smem = (out_layout == 1) ? (size_t)8 * 32 * row_words * 4 : 0;
-        const uint32_t ctas = min(ceil_div(n_groups, 8u), (uint32_t)kNumSM * 6u);
-        if (out_layout == 1) k_grid_fwd_w<T, (kWpl >= 1 ? C : 2), true><<<ctas, 256, smem, st>>>(inputs, emb, offsets, outputs, B, L, S, H, gridtype, n_groups, row_words);
-        else k_grid_fwd_w<T, (kWpl >= 1 ? C : 2), false><<<ctas, 256, 0, st>>>(inputs, emb, offsets, outputs, B, L, S, H, gridtype, n_groups, row_words);
+        // persistent grid = exactly the CTAs that are resident at once (a partial second wave would idle most SMs at the end).
+        // (Forcing 6 CTAs/SM with __launch_bounds__(256, 6) — 40 registers, 28 bytes of spills — measured slower: 0.418 vs 0.397 ms.)
+        constexpr int CCc = (kWpl >= 1 ? C : 2);
+        auto launch = [&](auto kern) -> int {
+            int per_sm = 0;
+            ENERF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem), "grid_encode_forward");
+            if (per_sm < 1) per_sm = 1;
+            const uint32_t ctas = min(ceil_div(n_groups, 8u), (uint32_t)kNumSM * (uint32_t)per_sm);
+            kern<<<ctas, 256, smem, st>>>(inputs, emb, offsets, outputs, B, L, S, H, gridtype, n_groups, row_words);
+            return 0;
+        };
+        const int rc = (out_layout == 1) ? launch(k_grid_fwd_w<T, CCc, true>) : launch(k_grid_fwd_w<T, CCc, false>);
+        if (rc) return rc;
         ENERF_CHECK_LAUNCH("grid_encode_forward");
         return 0;
     }
