@@ -175,6 +175,28 @@ __device__ __forceinline__ bool probe(const Ray& r, const MarchCfg& c, const uin
     return occ;
 }
 
+// Candidate `lane` of a batch that starts at tb when the step is the constant c: the value of `lane` sequential fp32 additions
+// t <- t + c (the reference's loop, raymarching.cu:387,397), bit for bit.
+// While t stays inside one binade every t is a multiple of u = ulp(t), so RN(t + c) = t + c' with the same c' = RN_u(c) at every
+// step (a tie c mod u == u/2 settles on one increment after its first step) and the sequence is the arithmetic progression
+// tb + k*c', exactly representable.  That case is detected (two equal successive increments, same exponent at both ends of the
+// batch) and evaluated with one fma; otherwise the 31 dependent additions are done literally.
+__device__ __forceinline__ float const_step_candidate(float tb, float c, unsigned lane) {
+    const float t1 = tb + c;
+    const float d1 = t1 - tb;                          // exact: t1 and tb are within a factor of two
+    const float d2 = (t1 + c) - t1;
+    const float t_end = __fmaf_rn(32.0f, d1, tb);      // one step past the batch
+    const bool same_binade = (__float_as_uint(tb) >> 23) == (__float_as_uint(t_end) >> 23);
+    if (d1 == d2 && same_binade && tb >= c && c > 0.0f) return __fmaf_rn((float)lane, d1, tb);   // tb >= c > 0: the subtractions above are exact
+    float t = tb;
+#pragma unroll
+    for (int j = 0; j < 31; ++j) {
+        const float tn = t + c;
+        t = ((unsigned)j < lane) ? tn : t;
+    }
+    return t;
+}
+
 // Marches one ray with one warp.  Emits at most `limit` samples, starting at t0; returns the
 // number emitted (warp-uniform).  With WRITE, sample i of this ray goes to row i of
 // xyzs/dirs/deltas (already offset to the ray's range).
@@ -204,12 +226,7 @@ __device__ uint32_t march_warp(const Ray& r, const MarchCfg& c, const uint8_t* _
         // bit-identical to the sequential loop's.
         float t = tb;
         if (c.dt_gamma == 0.0f) {
-            const float cstep = clampf(0.0f, c.dt_min, c.dt_max);
-#pragma unroll
-            for (int j = 0; j < 31; ++j) {
-                const float tn = t + cstep;
-                t = ((unsigned)j < lane) ? tn : t;
-            }
+            t = const_step_candidate(tb, clampf(0.0f, c.dt_min, c.dt_max), lane);
         } else {
             for (int j = 0; j < 31; ++j) {
                 const float tn = t + step_of(t, c);
@@ -310,12 +327,7 @@ __device__ void replay_warp(const Ray& r, const MarchCfg& c, float t0, const Bat
         const unsigned emit = log->emit[b];
         float t = tb;
         if (c.dt_gamma == 0.0f) {
-            const float cstep = clampf(0.0f, c.dt_min, c.dt_max);
-#pragma unroll
-            for (int j = 0; j < 31; ++j) {
-                const float tn = t + cstep;
-                t = ((unsigned)j < lane) ? tn : t;
-            }
+            t = const_step_candidate(tb, clampf(0.0f, c.dt_min, c.dt_max), lane);
         } else {
             for (int j = 0; j < 31; ++j) {
                 const float tn = t + step_of(t, c);
