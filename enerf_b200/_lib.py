@@ -47,7 +47,7 @@ _SIGS = {
     "enerf_field_sigma_backward": [_p, _p, _p, _p, _p, _p, _u32, _u32, _p, _p, _p],
     "enerf_composite_uniform_forward": [_p, _p, _p, _p, _u32, _u32, _f32, _p, _p, _p, _p],
     "enerf_composite_uniform_backward": [_p, _p, _p, _p, _p, _p, _p, _u32, _u32, _f32, _p, _p],
-    "enerf_get_rays": [_p, _f32, _f32, _f32, _f32, _u32, _u32, _p, _u32, _u32, _p, _f32, _p, _p, _p, _p, _p],
+    "enerf_get_rays": [_p, _f32, _f32, _f32, _f32, _u32, _u32, _p, _u32, _u32, _u32, _p, _f32, _p, _p, _p, _p, _p],
     "enerf_event_rays": [_p, _p, _p, _p, _f32, _f32, _f32, _f32, _u32, _p, _f32, _p, _p, _p, _p, _p, _p, _p],
     "enerf_event_loss_forward": [_p, _p, _p, _u32, _u32, _int, _int, _f32, _f32, _f32, _p, _p, _p, _p],
     "enerf_event_loss_backward": [_p, _p, _p, _p, _p, _p, _u32, _u32, _int, _int, _f32, _f32, _f32, _p, _p, _p],

@@ -47,12 +47,12 @@ __device__ __forceinline__ void slab(const float (&o)[3], const float (&d)[3], c
 
 // one thread per ray; poses [B,4,4]; pixel index inds[n] (or n itself) -> (i = idx % W, j = idx / W)
 __global__ void k_get_rays(const float* __restrict__ poses, float fx, float fy, float cx, float cy, uint32_t W, const int64_t* __restrict__ inds,
-                           uint32_t B, uint32_t N, const float* __restrict__ aabb, float min_near, float* __restrict__ rays_o,
+                           uint32_t inds_per_pose, uint32_t B, uint32_t N, const float* __restrict__ aabb, float min_near, float* __restrict__ rays_o,
                            float* __restrict__ rays_d, float* __restrict__ nears, float* __restrict__ fars) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= B * N) return;
     const uint32_t b = t / N, n = t - b * N;
-    const int64_t idx = inds ? inds[n] : (int64_t)n;
+    const int64_t idx = inds ? inds[inds_per_pose ? (size_t)b * N + n : n] : (int64_t)n;
     const float px = (float)(idx % W), py = (float)(idx / W);
     float dc[3], d[3], o[3];
     pixel_dir(px, py, fx, fy, cx, cy, dc);
@@ -239,13 +239,14 @@ using namespace enerf;
 
 extern "C" {
 
-int enerf_get_rays(const float* poses, float fx, float fy, float cx, float cy, uint32_t H, uint32_t W, const int64_t* inds, uint32_t B, uint32_t N,
+int enerf_get_rays(const float* poses, float fx, float fy, float cx, float cy, uint32_t H, uint32_t W, const int64_t* inds, uint32_t inds_per_pose,
+                   uint32_t B, uint32_t N,
                    const float* aabb, float min_near, float* rays_o, float* rays_d, float* nears, float* fars, void* stream) {
     (void)H;
     if ((uint64_t)B * N == 0) return 0;
     ENERF_REQUIRE(!aabb || (nears && fars), "get_rays", "nears/fars must be given with aabb");
     const uint32_t total = B * N;
-    k_get_rays<<<ceil_div(total, 256u), 256, 0, as_stream(stream)>>>(poses, fx, fy, cx, cy, W, inds, B, N, aabb, min_near, rays_o, rays_d, nears, fars);
+    k_get_rays<<<ceil_div(total, 256u), 256, 0, as_stream(stream)>>>(poses, fx, fy, cx, cy, W, inds, inds_per_pose, B, N, aabb, min_near, rays_o, rays_d, nears, fars);
     ENERF_CHECK_LAUNCH("get_rays");
     return 0;
 }

@@ -27,15 +27,22 @@ def get_rays_with_near_far(poses, intrinsics, H, W, N=-1, error_map=None, aabb=N
     B = poses.shape[0]
     fx, fy, cx, cy = _intr(intrinsics)
     results = {}
-    inds = None
+    inds, per_pose = None, 0
     if N > 0:
         N = min(N, H * W)
         if error_map is None:
-            inds1 = torch.randint(0, H * W, size=[N], device=dev)        # may duplicate (utils.py:137)
-            results['inds'] = inds1.expand([B, N])
-            inds = inds1
+            inds = torch.randint(0, H * W, size=[N], device=dev)          # may duplicate (utils.py:137); shared by all poses
+            results['inds'] = inds.expand([B, N])
         else:
-            raise NotImplementedError("error_map sampling produces per-pose indices; use the reference's sampler and pass them via `inds`")
+            # importance sampling on the 128x128 error map, then a random pixel inside the chosen cell (utils.py:140-150)
+            inds_coarse = torch.multinomial(error_map.to(dev), N, replacement=False)         # [B, N] in [0, 128*128)
+            cell_x, cell_y = inds_coarse // 128, inds_coarse % 128
+            sx, sy = H / 128, W / 128
+            px = (cell_x * sx + torch.rand(B, N, device=dev) * sx).long().clamp(max=H - 1)
+            py = (cell_y * sy + torch.rand(B, N, device=dev) * sy).long().clamp(max=W - 1)
+            inds, per_pose = (px * W + py).contiguous(), 1
+            results['inds_coarse'] = inds_coarse
+            results['inds'] = inds
     n = N if N > 0 else H * W
     P = poses.detach().float().contiguous()
     rays_o = torch.empty(B, n, 3, dtype=torch.float32, device=dev)
@@ -46,7 +53,7 @@ def get_rays_with_near_far(poses, intrinsics, H, W, N=-1, error_map=None, aabb=N
         a = aabb.detach().float().contiguous()
         nears = torch.empty(B, n, dtype=torch.float32, device=dev)
         fars = torch.empty(B, n, dtype=torch.float32, device=dev)
-    _lib.call("enerf_get_rays", ptr(P), fx, fy, cx, cy, H, W, ptr(inds), B, n, ptr(a), float(min_near), ptr(rays_o), ptr(rays_d), ptr(nears),
+    _lib.call("enerf_get_rays", ptr(P), fx, fy, cx, cy, H, W, ptr(inds), per_pose, B, n, ptr(a), float(min_near), ptr(rays_o), ptr(rays_d), ptr(nears),
               ptr(fars), stream())
     results['rays_o'] = rays_o
     results['rays_d'] = rays_d

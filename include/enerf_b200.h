@@ -232,11 +232,12 @@ int enerf_composite_uniform_backward(const float* grad_weights, const float* gra
 /* ------------------------------------------ next rows of the path ---- */
 /* N2 — ray generation on the device, fused with near_far_from_aabb.
  * nerf/utils.py:110-169 get_rays for given pixels: poses [B,4,4] cam2world (row-major), pixel n of every pose is
- * inds[n] (flat index j*W+i; NULL = pixel n), direction = normalize(((i-cx)/fx, (j-cy)/fy, 1)) rotated by pose[:3,:3],
+ * inds[n] (flat index j*W+i; NULL = pixel n; inds_per_pose != 0: inds is [B,N], one set per pose), direction = normalize(((i-cx)/fx, (j-cy)/fy, 1)) rotated by pose[:3,:3],
  * origin = pose[:3,3].  rays_o, rays_d: [B,N,3].  aabb (6 floats, device) may be NULL; otherwise nears/fars [B,N] get the
  * slab test of raymarching.h:7 with `min_near`. */
 int enerf_get_rays(const float* poses, float fx, float fy, float cx, float cy, uint32_t H, uint32_t W,
-                   const int64_t* inds, uint32_t B, uint32_t N, const float* aabb, float min_near,
+                   const int64_t* inds, uint32_t inds_per_pose, uint32_t B, uint32_t N, const float* aabb,
+                   float min_near,
                    float* rays_o, float* rays_d, float* nears, float* fars, void* stream);
 /* nerf/utils.py:185-216 get_event_rays: pixel (xs[n], ys[n]) seen from c2w_before[n] and c2w_at[n] ([N,3,4] row-major).
  * near_far1 / near_far2: [2,N] = nears then fars of the two ray sets (NULL or aabb == NULL: not computed). */

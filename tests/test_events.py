@@ -64,7 +64,7 @@ def test_gpu_get_rays_and_fused_near_far():
     ro, rd = torch.empty(B, N, 3, device=dev), torch.empty(B, N, 3, device=dev)
     nears, fars = torch.empty(B, N, device=dev), torch.empty(B, N, device=dev)
     fx, fy, cx, cy = (float(v) for v in G["gr_intr"])
-    _lib.call("enerf_get_rays", ptr(poses.contiguous()), fx, fy, cx, cy, H, W, ptr(inds), B, N, ptr(aabb), 0.2, ptr(ro), ptr(rd), ptr(nears), ptr(fars), stream())
+    _lib.call("enerf_get_rays", ptr(poses.contiguous()), fx, fy, cx, cy, H, W, ptr(inds), 0, B, N, ptr(aabb), 0.2, ptr(ro), ptr(rd), ptr(nears), ptr(fars), stream())
     assert np.allclose(rd.cpu().numpy(), G["gr_d_sel"], atol=3e-7) and torch.equal(ro.cpu(), torch.from_numpy(G["gr_o_sel"]))
     wn, wf = oracle.near_far_from_aabb(ro.cpu().numpy().reshape(-1, 3), rd.cpu().numpy().reshape(-1, 3), aabb.cpu().numpy(), 0.2)
     assert np.array_equal(nears.cpu().numpy().reshape(-1), wn) and np.array_equal(fars.cpu().numpy().reshape(-1), wf)
@@ -73,6 +73,13 @@ def test_gpu_get_rays_and_fused_near_far():
     r = events.get_rays(poses, G["gr_intr"], H, W, 100)
     o2, d2 = eo.get_rays(G["gr_poses"], G["gr_intr"], H, W, r["inds"][0].cpu().numpy())
     assert r["inds"].shape == (3, 100) and np.allclose(r["rays_d"].cpu().numpy(), d2, atol=3e-7)
+    # error-map importance sampling: per-pose pixel sets
+    emap = torch.rand(3, 128 * 128, device=dev)
+    r = events.get_rays(poses, G["gr_intr"], H, W, 64, error_map=emap)
+    assert r["inds"].shape == (3, 64) and r["inds_coarse"].shape == (3, 64) and int(r["inds"].max()) < H * W
+    for b in range(3):
+        _, db = eo.get_rays(G["gr_poses"][b:b + 1], G["gr_intr"], H, W, r["inds"][b].cpu().numpy())
+        assert np.allclose(r["rays_d"][b].cpu().numpy(), db[0], atol=3e-7)
 
 
 @pytest.mark.gpu
