@@ -1438,7 +1438,7 @@ static int launch_bwd_tma(const __half* grad, const __half* x, const __half* W, 
 //   a_ready[s] / d_full[s] advance 2*NH+3 phases per tile (one per MMA stage; a_ready's last one = "accumulator read,
 //   slot free for the next tile").
 // ================================================================================================
-template <int NSLOTS, int NH, int PRO, bool GD, int CH>
+template <int NSLOTS, int NH, int PRO, bool GD, int CH, bool XA>
 __global__ void __launch_bounds__(32 + NSLOTS * 128 * CH, 1)
 k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ grad, const __half* __restrict__ W, __half* __restrict__ grad_inputs,
             float* __restrict__ dW, uint32_t n_tiles, uint32_t B, ProArgs pro) {
@@ -1453,7 +1453,11 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
     // GD: two G tiles per slot.  The dgrad of a stage is then committed on its own, so the next epilogue (which writes the other
     // G tile) overlaps the stage's eight weight-gradient MMAs instead of waiting for them.
     constexpr int NG = GD ? 2 : 1;
-    constexpr uint32_t kSlotBytes = 2 * kXBytes + (NH + 1) * kGBytes + NG * kGBytes;     // x ring, h_0..h_NH, G tile(s)
+    // XA: no buffers of its own for the input tile.  It is loaded twice per tile (8 KB, the second time from L2): into the h_0 buffer
+    // for F_0 (h_0 overwrites it afterwards) and, once h_NH is dead (after B_0 and the mask read of E_1), into the h_NH buffer for
+    // the last stage's weight gradient.  16 KB less per slot -> one more tile in flight per SM.
+    constexpr uint32_t kXRing = XA ? 0u : 2u * kXBytes;
+    constexpr uint32_t kSlotBytes = kXRing + (NH + 1) * kGBytes + NG * kGBytes;     // [x ring], h_0..h_NH, G tile(s)
     extern __shared__ uint8_t smem_dyn[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     uint8_t* w0s = smem + (size_t)NSLOTS * kSlotBytes;     // [in_dim/8][64][16 B]   (forward layout)
@@ -1465,9 +1469,8 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
     uint64_t* flush_bar = x_full + 2 * NSLOTS;
     uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(flush_bar + 1);
     // per-slot regions: [x0 | x1 | h_0 .. h_NH | G]
-    auto slot_x = [&](int s, uint32_t b) { return smem + (size_t)s * kSlotBytes + (size_t)b * kXBytes; };
-    auto slot_h = [&](int s, int L) { return smem + (size_t)s * kSlotBytes + 2 * kXBytes + (size_t)L * kGBytes; };
-    auto slot_g = [&](int s, int k) { return smem + (size_t)s * kSlotBytes + 2 * kXBytes + (size_t)(NH + 1 + (GD ? (k & 1) : 0)) * kGBytes; };
+    auto slot_h = [&](int s, int L) { return smem + (size_t)s * kSlotBytes + kXRing + (size_t)L * kGBytes; };
+    auto slot_g = [&](int s, int k) { return smem + (size_t)s * kSlotBytes + kXRing + (size_t)(NH + 1 + (GD ? (k & 1) : 0)) * kGBytes; };
 
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -1506,15 +1509,17 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
         uint32_t nt[NSLOTS];
 #pragma unroll
         for (int s = 0; s < NSLOTS; ++s) nt[s] = (my_tiles > (uint32_t)s) ? (my_tiles - s + NSLOTS - 1) / NSLOTS : 0;
-        auto issue_x = [&](int s, uint32_t tl) {               // elected lane only
+        // input tile of the slot's tl-th tile -> (ring buffer tl & 1) or, with XA, the h_0 buffer (which = 0) / the h_NH buffer (which = 1)
+        auto issue_x = [&](int s, uint32_t tl, uint32_t which) {               // elected lane only
             const uint32_t tile = blockIdx.x + ((uint32_t)s + tl * NSLOTS) * gridDim.x;
-            uint64_t* bar = &x_full[2 * s + (tl & 1u)];
+            uint64_t* bar = &x_full[2 * s + which];
+            const uint32_t dst = sm_b + (uint32_t)s * kSlotBytes + (XA ? (which ? (uint32_t)NH * kGBytes : 0u) : which * kXBytes);
             mbar_arrive_expect_tx(bar, kXBytes);
-            tma_load_2d(sm_b + (uint32_t)s * kSlotBytes + (tl & 1u) * kXBytes, &tm_x, 0, (int32_t)(tile * kTile), bar);
+            tma_load_2d(dst, &tm_x, 0, (int32_t)(tile * kTile), bar);
         };
 #pragma unroll
         for (int s = 0; s < NSLOTS; ++s) {
-            if (nt[s] > 0 && elect_one()) issue_x(s, 0);
+            if (nt[s] > 0 && elect_one()) issue_x(s, 0, 0);
             __syncwarp();
         }
         constexpr uint32_t idF = idesc_f16(kTile, 64, false, false);
@@ -1529,19 +1534,22 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
                     const uint32_t tb = tl * T;                          // phase index of this tile's first stage
                     const uint32_t d_t = tm + s * kSlotCols, a_t = d_t + 64;
                     const uint32_t slot_b = sm_b + (uint32_t)s * kSlotBytes;
-                    const uint32_t xb = slot_b + (tl & 1u) * kXBytes;
-                    const uint32_t h0b = slot_b + 2 * kXBytes;           // h_L at h0b + L*kGBytes
+                    const uint32_t h0b = slot_b + kXRing;                // h_L at h0b + L*kGBytes
+                    // where F_0 / the last stage find the input tile, and which barrier + parity announces it
+                    const uint32_t xb_f = XA ? h0b : slot_b + (tl & 1u) * kXBytes;
+                    const uint32_t xb_b = XA ? h0b + (uint32_t)NH * kGBytes : xb_f;
+                    const uint32_t xw_f = XA ? 0u : (tl & 1u), xp_f = XA ? (tl & 1u) : ((tl >> 1) & 1u);
                     if (t == 0) {
                         // ---- F_0: h_0 pre-activation = x . W_0^T
                         if (tl > 0) mbar_wait(&a_ready[s], (tb - 1u) & 1u);              // the previous tile's dx accumulator has been read
-                        mbar_wait(&x_full[2 * s + (tl & 1u)], (tl >> 1) & 1u);
+                        mbar_wait(&x_full[2 * s + xw_f], xp_f);
                         tc_fence_after();
                         if (elect_one()) {
                             if (s == 0) ENERF_TRACE(1000 + t);
-                            if (tl + 1 < nt[s]) issue_x(s, tl + 1);                     // the other input buffer belonged to the finished tile tl-1
+                            if (!XA && tl + 1 < nt[s]) issue_x(s, tl + 1, (tl + 1) & 1u);       // the other ring buffer belonged to the finished tile tl-1
 #pragma unroll
                             for (int k = 0; k < in_dim / 16; ++k)
-                                mma_ss(d_t, smem_desc_sw(xb + k * 32, 64), smem_desc(w0b + k * 2 * (kW * 16), kW * 16, 128), idF, k > 0);
+                                mma_ss(d_t, smem_desc_sw(xb_f + k * 32, 64), smem_desc(w0b + k * 2 * (kW * 16), kW * 16, 128), idF, k > 0);
                             tc_commit(&d_full[s]);
                             if (s == 0) ENERF_TRACE(2000 + t);
                         }
@@ -1565,10 +1573,13 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
                         const uint32_t g_s = h0b + (uint32_t)(NH + 1 + (GD ? (k & 1) : 0)) * kGBytes;
                         constexpr bool kSplit = GD;                      // commit the dgrad before the wgrad (all but the tile's last stage)
                         mbar_wait(&a_ready[s], (tb + (uint32_t)(t - 1)) & 1u);
+                        if (XA && k == S - 1) mbar_wait(&x_full[2 * s + 1], tl & 1u);      // the re-loaded input tile (in the h_NH buffer)
                         tc_fence_after();
                         const bool acc = !(tl == 0 && s == 0);           // the very first issue on an accumulator overwrites it
                         if (elect_one()) {
                             if (s == 0) ENERF_TRACE(1000 + t);
+                            if (XA && k == 1) issue_x(s, tl, 1);                              // E_1 has read its mask from h_NH and B_0 is complete: h_NH is dead
+                            if (XA && k == S - 1 && tl + 1 < nt[s]) issue_x(s, tl + 1, 0);    // E_{S-1} has read h_0 and B_NH is complete: h_0 is dead
                             if (k == 0) {
                                 mma_ts(d_t, a_t, smem_desc(wlb, 128, 16 * 16), idD64, false);
                                 if (kSplit) tc_commit(&d_full[s]);
@@ -1591,7 +1602,7 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
                                 for (int ks = 0; ks < 4; ++ks) mma_ts(d_t, a_t + ks * 8, smem_desc(w0b + ks * 256, 128, 64 * 16), idDx, ks > 0);
 #pragma unroll
                                 for (int ks = 0; ks < 8; ++ks)
-                                    mma_ss(tm + kAcc0, smem_desc(g_s + ks * 256, 128, 2048), smem_desc_sw(xb + ks * 16 * 64, 64), idW0, acc || ks > 0);
+                                    mma_ss(tm + kAcc0, smem_desc(g_s + ks * 256, 128, 2048), smem_desc_sw(xb_b + ks * 16 * 64, 64), idW0, acc || ks > 0);
                             }
                             // the last stage always commits after its wgrad: everything of the tile (G, x, h tiles) is then free
                             if (!kSplit || k == S - 1) tc_commit(&d_full[s]);
@@ -1829,21 +1840,21 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
     if (warp == 0) tmem_dealloc(tmem0, kCols);
 }
 
-template <int NSLOTS, int NH, int PRO, bool GD, int CH>
+template <int NSLOTS, int NH, int PRO, bool GD, int CH, bool XA>
 static int launch_bwd_rc_n(const TmaDesc& tx, const __half* grad, const __half* W, __half* grad_inputs, float* dW, uint32_t B, ProArgs pro,
                            cudaStream_t st, const char* name) {
-    constexpr size_t kSlot = 2 * (size_t)kTile * 32 * 2 + (size_t)(NH + 2 + (GD ? 1 : 0)) * kGBytes;
+    constexpr size_t kSlot = (XA ? 0 : 2 * (size_t)kTile * 32 * 2) + (size_t)(NH + 2 + (GD ? 1 : 0)) * kGBytes;
     size_t smem = 1024 + NSLOTS * kSlot + 32 * 128 + (size_t)NH * 8192 + 2048 + (4 * NSLOTS + 1) * 8 + 16;
     if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: it allocates all 512 TMEM columns
     if (smem > 227 * 1024) return 1;
     static bool configured = false;
     if (!configured) {
-        ENERF_CUDA(cudaFuncSetAttribute(k_tc_bwd_rc<NSLOTS, NH, PRO, GD, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
+        ENERF_CUDA(cudaFuncSetAttribute(k_tc_bwd_rc<NSLOTS, NH, PRO, GD, CH, XA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
         configured = true;
     }
     const uint32_t n_tiles = B / kTile;
     const uint32_t grid = n_tiles < (uint32_t)kNumSM ? n_tiles : (uint32_t)kNumSM;
-    k_tc_bwd_rc<NSLOTS, NH, PRO, GD, CH><<<grid, 32 + NSLOTS * 128 * CH, smem, st>>>(tx, grad, W, grad_inputs, dW, n_tiles, B, pro);
+    k_tc_bwd_rc<NSLOTS, NH, PRO, GD, CH, XA><<<grid, 32 + NSLOTS * 128 * CH, smem, st>>>(tx, grad, W, grad_inputs, dW, n_tiles, B, pro);
     ENERF_CHECK_LAUNCH(name);
     return 0;
 }
@@ -1855,22 +1866,25 @@ static int launch_bwd_rc(const __half* grad, const __half* x, const __half* W, _
     if (in_dim != 32 || (n_hidden_mm != 1 && n_hidden_mm != 2) || (uint64_t)B >= (1ull << 31)) return 1;
     TmaDesc tx;
     if (!make_tmap_rows(&tx, x, B, 32, kTile)) return 1;
-    // Measured on B200 (3.29 M samples): 2-layer nets 0.255 ms with 3 slots x 4 epilogue warps (0.28 with 2 x 8); 3-layer nets 0.355 ms
-    // with 2 slots x 8 epilogue warps (0.386 with 2 x 4; a third slot does not fit in shared memory).  ENERF_TC_RC_MODE overrides for
-    // experiments: 1 = one thread per row everywhere, 2 = second G tile + early dgrad commit, 3 = two threads per row everywhere.
+    // Measured on B200 (3.29 M samples).  2-layer nets: 0.255 ms with 3 slots x 4 epilogue warps (0.28 with 2 x 8; 0.33 with 4 slots and
+    // the input tile aliased: 96 registers, spills).  3-layer nets: 0.343 ms with 3 slots, input tile aliased onto dead activation
+    // buffers (XA); 0.355 with 2 slots x 8 epilogue warps; 0.386 with 2 x 4.  ENERF_TC_RC_MODE overrides for experiments: 1 = 2/3 slots,
+    // one thread per row, own input buffers; 2 = second G tile + early dgrad commit; 3 = two threads per row; 4 = XA everywhere.
     static int mode = -1;
     if (mode < 0) {
         const char* e = getenv("ENERF_TC_RC_MODE");
         mode = e ? atoi(e) : 0;
     }
     if (n_hidden_mm == 1) {
-        if (mode == 3) return launch_bwd_rc_n<2, 1, PRO, false, 2>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
-        if (mode == 2) return launch_bwd_rc_n<2, 1, PRO, true, 1>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
-        return launch_bwd_rc_n<3, 1, PRO, false, 1>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
+        if (mode == 4) return launch_bwd_rc_n<4, 1, PRO, false, 1, true>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
+        if (mode == 3) return launch_bwd_rc_n<2, 1, PRO, false, 2, false>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
+        if (mode == 2) return launch_bwd_rc_n<2, 1, PRO, true, 1, false>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
+        return launch_bwd_rc_n<3, 1, PRO, false, 1, false>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
     }
-    if (mode == 1) return launch_bwd_rc_n<2, 2, PRO, false, 1>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
-    if (mode == 2) return launch_bwd_rc_n<2, 2, PRO, true, 1>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
-    return launch_bwd_rc_n<2, 2, PRO, false, 2>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
+    if (mode == 1) return launch_bwd_rc_n<2, 2, PRO, false, 1, false>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
+    if (mode == 2) return launch_bwd_rc_n<2, 2, PRO, true, 1, false>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
+    if (mode == 3) return launch_bwd_rc_n<2, 2, PRO, false, 2, false>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
+    return launch_bwd_rc_n<3, 2, PRO, false, 1, true>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
 }
 
 int tc_backward(const __half* grad, const __half* x, const __half* W, const __half* fwd_buf, __half* bwd_buf, __half* grad_inputs, float* dW,
