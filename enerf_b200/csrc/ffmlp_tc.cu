@@ -1429,22 +1429,25 @@ static int launch_bwd_tma(const __half* grad, const __half* x, const __half* W, 
 // forward writes [num_layers, B, 64] fp16 of forward_buffer and the backward reads it back (2.2 + 2.8 GB per step on
 // the bench workload), while re-running the hidden layers of a tile costs a few hundred tensor-core cycles.  This
 // kernel takes only the network input and dL/dy:
-//   F_0 .. F_NH : h_L = relu(h_{L-1} . W_L^T)  — SS MMAs; the epilogue writes h_L (fp16) into a shared-memory tile in the
-//                 128-byte swizzle, which serves three readers without another copy: the next forward MMA (K-major A
-//                 operand), the weight-gradient MMA (MN-major operand) and the ReLU mask of the backward epilogue.
+//   F_0 .. F_NH : h_L = relu(h_{L-1} . W_L^T); the epilogue writes h_L (fp16) to TMEM (A operand of the next forward MMA) and into a
+//                 shared-memory tile in the 128-byte swizzle, which the weight-gradient MMA reads as its MN-major operand and the
+//                 backward epilogue as the ReLU mask.
 //   B_0 .. B_S-1: exactly the stages of k_tc_bwd_tma (dgrad with A in TMEM, wgrad into TMEM accumulators).
 // The recomputed activations are bit-identical to what the training forward would have stored (same MMAs, same K
 // order, same rounding point), so the gradients match the stored-activation path.  Input width 32.
 //   a_ready[s] / d_full[s] advance 2*NH+3 phases per tile (one per MMA stage; a_ready's last one = "accumulator read,
 //   slot free for the next tile").
 // ================================================================================================
-template <int NSLOTS, int NH, int PRO, bool GD, int CH, bool XA>
-__global__ void __launch_bounds__(32 + NSLOTS * 128 * CH, 1)
+template <int NSLOTS, int NH, int PRO, bool GD, int CH, bool XA, int NI>
+__global__ void __launch_bounds__(32 * NI + NSLOTS * 128 * CH, 1)
 k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ grad, const __half* __restrict__ W, __half* __restrict__ grad_inputs,
             float* __restrict__ dW, uint32_t n_tiles, uint32_t B, ProArgs pro) {
     // CH = warps per TMEM lane quarter of a slot (1 or 2): with 2, a row's 64 accumulator columns are split between two
     // threads (warps w and w+4 share the quarter w % 4), which halves the serial epilogue work per stage.
     static_assert(CH == 1 || CH == 2, "CH");
+    // NI = issuing warps: with 2, warp 0 issues the forward (recompute) stages and warp 1 the backward stages — they never share an
+    // accumulator, and each consumes its own "A ready" barrier (a_ready[2s] / a_ready[2s+1]) phase by phase.
+    static_assert(NI == 1 || NI == 2, "NI");
     constexpr int in_dim = 32;
     constexpr int CW = 64 / CH;                            // accumulator columns per epilogue thread
     constexpr int S = NH + 2;                              // backward stages per tile
@@ -1464,7 +1467,7 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
     uint8_t* whs = w0s + in_dim * 128;                     // NH x [8][64][16 B]
     uint8_t* wls = whs + NH * 8192;                        // [8][16][16 B]
     uint64_t* a_ready = reinterpret_cast<uint64_t*>(wls + 2048);
-    uint64_t* d_full = a_ready + NSLOTS;
+    uint64_t* d_full = a_ready + 2 * NSLOTS;           // a_ready: [NSLOTS][2] = (forward issuer's, backward issuer's)
     uint64_t* x_full = d_full + NSLOTS;                    // [NSLOTS][2]
     uint64_t* flush_bar = x_full + 2 * NSLOTS;
     uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(flush_bar + 1);
@@ -1481,7 +1484,8 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
     stage_matrix(wls, W + kW * in_dim + NH * kW * kW, 16, kW, tid, nthreads);
     if (tid == 0) {
         for (int s = 0; s < NSLOTS; ++s) {
-            mbar_init(&a_ready[s], 4 * CH);      // one arrival per epilogue warp
+            mbar_init(&a_ready[2 * s], 4 * CH);      // one arrival per epilogue warp
+            mbar_init(&a_ready[2 * s + 1], 4 * CH);
             mbar_init(&d_full[s], 1);
             mbar_init(&x_full[2 * s], 1);
             mbar_init(&x_full[2 * s + 1], 1);
@@ -1501,9 +1505,10 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
     constexpr uint32_t kAccLast = NSLOTS * kSlotCols, kAccHid = kAccLast + 16, kAcc0 = kAccHid + NH * 64;
     static_assert(kAcc0 + in_dim <= 512, "TMEM budget");
 
-    if (warp == 0) {
-        // ===================== MMA / TMA issuer: warp-uniform control flow, one elected lane issues =====================
+    if (warp < NI) {
+        // ===================== MMA / TMA issuer(s): warp-uniform control flow, one elected lane issues =====================
         ENERF_TRACE_DECL(0);
+        const bool do_f = (NI == 1) || warp == 0, do_b = (NI == 1) || warp == 1;
         const uint32_t tm = __shfl_sync(0xffffffffu, tmem0, 0);
         const uint32_t sm_b = smem_u32(smem), w0b = smem_u32(w0s), whb = smem_u32(whs), wlb = smem_u32(wls);
         uint32_t nt[NSLOTS];
@@ -1519,7 +1524,7 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
         };
 #pragma unroll
         for (int s = 0; s < NSLOTS; ++s) {
-            if (nt[s] > 0 && elect_one()) issue_x(s, 0, 0);
+            if (do_f && nt[s] > 0 && elect_one()) issue_x(s, 0, 0);
             __syncwarp();
         }
         constexpr uint32_t idF = idesc_f16(kTile, 64, false, false);
@@ -1531,7 +1536,8 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
 #pragma unroll
                 for (int s = 0; s < NSLOTS; ++s) {
                     if (tl >= nt[s]) continue;
-                    const uint32_t tb = tl * T;                          // phase index of this tile's first stage
+                    if ((t <= NH) ? !do_f : !do_b) continue;
+                    const uint32_t fb = tl * (NH + 1), bb = tl * S;      // first phase of this tile on the forward / backward "A ready" barrier
                     const uint32_t d_t = tm + s * kSlotCols, a_t = d_t + 64;
                     const uint32_t slot_b = sm_b + (uint32_t)s * kSlotBytes;
                     const uint32_t h0b = slot_b + kXRing;                // h_L at h0b + L*kGBytes
@@ -1541,7 +1547,7 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
                     const uint32_t xw_f = XA ? 0u : (tl & 1u), xp_f = XA ? (tl & 1u) : ((tl >> 1) & 1u);
                     if (t == 0) {
                         // ---- F_0: h_0 pre-activation = x . W_0^T
-                        if (tl > 0) mbar_wait(&a_ready[s], (tb - 1u) & 1u);              // the previous tile's dx accumulator has been read
+                        if (tl > 0) mbar_wait(&a_ready[2 * s], (fb - 1u) & 1u);          // the previous tile's dx accumulator has been read
                         mbar_wait(&x_full[2 * s + xw_f], xp_f);
                         tc_fence_after();
                         if (elect_one()) {
@@ -1556,13 +1562,15 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
                         __syncwarp();
                     } else if (t <= NH) {
                         // ---- F_t: h_t pre-activation = h_{t-1} . W_t^T   (A = the swizzled activation tile, K-major)
-                        mbar_wait(&a_ready[s], (tb + (uint32_t)(t - 1)) & 1u);
+                        mbar_wait(&a_ready[2 * s], (fb + (uint32_t)(t - 1)) & 1u);
                         tc_fence_after();
                         if (elect_one()) {
                             if (s == 0) ENERF_TRACE(1000 + t);
-                            const uint32_t ab = h0b + (uint32_t)(t - 1) * kGBytes, wb = whb + (uint32_t)(t - 1) * 8192u;
+                            // A = h_{t-1} from TMEM (the epilogue stored it there as well): the shared-memory pipe, which bounds this
+                            // kernel (ncu: 37 % LSU + 39 % tensor-core operand wavefronts), is spared 16 KB of operand reads per stage
+                            const uint32_t wb = whb + (uint32_t)(t - 1) * 8192u;
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) mma_ss(d_t, smem_desc_sw(ab + k * 32, 128), smem_desc(wb + k * 2 * (kW * 16), kW * 16, 128), idF, k > 0);
+                            for (int k = 0; k < 4; ++k) mma_ts(d_t, a_t + k * 8, smem_desc(wb + k * 2 * (kW * 16), kW * 16, 128), idF, k > 0);
                             tc_commit(&d_full[s]);
                             if (s == 0) ENERF_TRACE(2000 + t);
                         }
@@ -1572,7 +1580,7 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
                         const int k = t - (NH + 1);
                         const uint32_t g_s = h0b + (uint32_t)(NH + 1 + (GD ? (k & 1) : 0)) * kGBytes;
                         constexpr bool kSplit = GD;                      // commit the dgrad before the wgrad (all but the tile's last stage)
-                        mbar_wait(&a_ready[s], (tb + (uint32_t)(t - 1)) & 1u);
+                        mbar_wait(&a_ready[2 * s + 1], (bb + (uint32_t)k) & 1u);
                         if (XA && k == S - 1) mbar_wait(&x_full[2 * s + 1], tl & 1u);      // the re-loaded input tile (in the h_NH buffer)
                         tc_fence_after();
                         const bool acc = !(tl == 0 && s == 0);           // the very first issue on an accumulator overwrites it
@@ -1613,11 +1621,11 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
                 }
             }
         }
-        if (elect_one()) tc_commit(flush_bar);
+        if (do_b && elect_one()) tc_commit(flush_bar);
         __syncwarp();
     } else {
         // ===================== epilogue warps (4*CH per slot) =====================
-        const int ew = warp - 1;
+        const int ew = warp - NI;
         const int s = ew / (4 * CH);
         const int q = warp & 3;                            // TMEM lane quarter this warp may access
         const int hf = (ew % (4 * CH)) >> 2;               // which CW-column part of the row this thread owns
@@ -1667,15 +1675,16 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
                     uint32_t acc[32];
                     tmem_ld32(d_t + hf * CW + h * 32, acc);
                     tc_wait_ld();
+                    uint32_t p[16];
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) {
-                        uint32_t p[4];
+                    for (int e = 0; e < 16; ++e) p[e] = pack2_relu(__uint_as_float(acc[2 * e]), __uint_as_float(acc[2 * e + 1]));
+                    if (L < NH) tmem_st16(a_t + hf * (CW / 2) + h * 16, p);       // A operand of the next forward stage
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) p[e] = pack2_relu(__uint_as_float(acc[8 * v + 2 * e]), __uint_as_float(acc[8 * v + 2 * e + 1]));
+                    for (int v = 0; v < 4; ++v)
                         *reinterpret_cast<int4*>(hb + sw_off((uint32_t)r_in_tile, (uint32_t)(hf * (CW / 8) + h * 4 + v), 128)) =
-                            make_int4((int)p[0], (int)p[1], (int)p[2], (int)p[3]);
-                    }
+                            make_int4((int)p[4 * v], (int)p[4 * v + 1], (int)p[4 * v + 2], (int)p[4 * v + 3]);
                 }
+                if (L < NH) tc_wait_st();
                 if (L == NH && hf == 0) {
                     // dy -> TMEM A + dy tile (G buffer): E_0 of the backward
                     int4 v0, v1;
@@ -1712,7 +1721,7 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
                 if (s == 0 && r_in_tile == 0) ENERF_TRACE(4000 + L);
                 fence_proxy_async_smem();
                 tc_fence_before();
-                warp_arrive(&a_ready[s], lane);
+                warp_arrive(&a_ready[2 * s + (L == NH ? 1 : 0)], lane);      // the next stage is forward (L < NH) or the first backward stage
                 if (s == 0 && r_in_tile == 0) ENERF_TRACE(5000 + L);
                 if (L == NH && hf == 0 && j + NSLOTS < my_tiles) fetch(((size_t)blockIdx.x + (size_t)(j + NSLOTS) * gridDim.x) * kTile + r_in_tile);
             }
@@ -1750,7 +1759,7 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
                 tc_wait_st();
                 fence_proxy_async_smem();
                 tc_fence_before();
-                warp_arrive(&a_ready[s], lane);
+                warp_arrive(&a_ready[2 * s + 1], lane);
                 if (s == 0 && r_in_tile == 0) ENERF_TRACE(5000 + NH + k);
             }
             // ---- E_S: dx
@@ -1778,7 +1787,7 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
                     for (int e = 0; e < 16; ++e) acc[e % DXW] = a0[e];
                 }
                 tc_fence_before();
-                warp_arrive(&a_ready[s], lane);                  // accumulator read: the slot can start its next tile
+                warp_arrive(&a_ready[2 * s], lane);              // accumulator read: the slot can start its next tile
                 if (grad_inputs) {
                     uint32_t p[DXW / 2];
 #pragma unroll
@@ -1840,21 +1849,21 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
     if (warp == 0) tmem_dealloc(tmem0, kCols);
 }
 
-template <int NSLOTS, int NH, int PRO, bool GD, int CH, bool XA>
+template <int NSLOTS, int NH, int PRO, bool GD, int CH, bool XA, int NI = 1>
 static int launch_bwd_rc_n(const TmaDesc& tx, const __half* grad, const __half* W, __half* grad_inputs, float* dW, uint32_t B, ProArgs pro,
                            cudaStream_t st, const char* name) {
     constexpr size_t kSlot = (XA ? 0 : 2 * (size_t)kTile * 32 * 2) + (size_t)(NH + 2 + (GD ? 1 : 0)) * kGBytes;
-    size_t smem = 1024 + NSLOTS * kSlot + 32 * 128 + (size_t)NH * 8192 + 2048 + (4 * NSLOTS + 1) * 8 + 16;
+    size_t smem = 1024 + NSLOTS * kSlot + 32 * 128 + (size_t)NH * 8192 + 2048 + (5 * NSLOTS + 1) * 8 + 16;
     if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: it allocates all 512 TMEM columns
     if (smem > 227 * 1024) return 1;
     static bool configured = false;
     if (!configured) {
-        ENERF_CUDA(cudaFuncSetAttribute(k_tc_bwd_rc<NSLOTS, NH, PRO, GD, CH, XA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
+        ENERF_CUDA(cudaFuncSetAttribute(k_tc_bwd_rc<NSLOTS, NH, PRO, GD, CH, XA, NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
         configured = true;
     }
     const uint32_t n_tiles = B / kTile;
     const uint32_t grid = n_tiles < (uint32_t)kNumSM ? n_tiles : (uint32_t)kNumSM;
-    k_tc_bwd_rc<NSLOTS, NH, PRO, GD, CH, XA><<<grid, 32 + NSLOTS * 128 * CH, smem, st>>>(tx, grad, W, grad_inputs, dW, n_tiles, B, pro);
+    k_tc_bwd_rc<NSLOTS, NH, PRO, GD, CH, XA, NI><<<grid, 32 * NI + NSLOTS * 128 * CH, smem, st>>>(tx, grad, W, grad_inputs, dW, n_tiles, B, pro);
     ENERF_CHECK_LAUNCH(name);
     return 0;
 }
@@ -1874,6 +1883,10 @@ static int launch_bwd_rc(const __half* grad, const __half* x, const __half* W, _
     if (mode < 0) {
         const char* e = getenv("ENERF_TC_RC_MODE");
         mode = e ? atoi(e) : 0;
+    }
+    if (mode == 5) {       // two issuing warps
+        if (n_hidden_mm == 1) return launch_bwd_rc_n<3, 1, PRO, false, 1, false, 2>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
+        return launch_bwd_rc_n<3, 2, PRO, false, 1, true, 2>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
     }
     if (n_hidden_mm == 1) {
         if (mode == 4) return launch_bwd_rc_n<4, 1, PRO, false, 1, true>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
