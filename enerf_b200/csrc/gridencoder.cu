@@ -870,11 +870,24 @@ template <typename T, typename G, int D, int C>
 static int launch_bwd(const T* grad, const float* inputs, const int32_t* offsets, G* gg, uint32_t B, uint32_t L, float S, uint32_t H,
                       bool cg, const T* dy_dx, T* grad_inputs, uint32_t gridtype, int out_layout, cudaStream_t st) {
     if (g_bwd_walk && L <= 32 && (32 % L) == 0) {
-        constexpr int SEG = 32;
-        const uint64_t threads = (uint64_t)ceil_div(B, (uint32_t)SEG) * L;
-        const dim3 grid((uint32_t)ceil_div(threads, (uint64_t)256));
-        if (out_layout == 1) k_grid_bwd_walk<T, G, D, C, true, SEG><<<grid, 256, 0, st>>>(grad, inputs, offsets, gg, B, L, S, H, gridtype);
-        else k_grid_bwd_walk<T, G, D, C, false, SEG><<<grid, 256, 0, st>>>(grad, inputs, offsets, gg, B, L, S, H, gridtype);
+        // samples per thread-run: every run boundary costs one extra flush (8 reductions) per level, longer runs mean fewer threads
+        static int seg = 0;
+        if (seg == 0) {
+            const char* e = getenv("ENERF_GRID_BWD_SEG");
+            seg = e ? atoi(e) : 64;                 // measured (3.29 M samples): 16: 0.768, 32: 0.707, 64: 0.696, 128: 0.715 ms
+            if (seg != 16 && seg != 32 && seg != 64 && seg != 128) seg = 64;
+        }
+        auto go = [&](auto seg_tag) {
+            constexpr int SEG = decltype(seg_tag)::value;
+            const uint64_t threads = (uint64_t)ceil_div(B, (uint32_t)SEG) * L;
+            const dim3 grid((uint32_t)ceil_div(threads, (uint64_t)256));
+            if (out_layout == 1) k_grid_bwd_walk<T, G, D, C, true, SEG><<<grid, 256, 0, st>>>(grad, inputs, offsets, gg, B, L, S, H, gridtype);
+            else k_grid_bwd_walk<T, G, D, C, false, SEG><<<grid, 256, 0, st>>>(grad, inputs, offsets, gg, B, L, S, H, gridtype);
+        };
+        if (seg == 16) go(std::integral_constant<int, 16>{});
+        else if (seg == 64) go(std::integral_constant<int, 64>{});
+        else if (seg == 128) go(std::integral_constant<int, 128>{});
+        else go(std::integral_constant<int, 32>{});
     } else {
         const dim3 block(32, min(L, 16u));
         const dim3 grid(ceil_div(B, (uint32_t)kSamplesPerCta));
