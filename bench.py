@@ -29,10 +29,10 @@ sys.path.insert(0, ROOT)
 
 METRIC, UNIT = "train_rays_per_sec", "rays/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this workload (bytes)
-NCU_TRAFFIC_SRC = "profiles/r1_25_ncu_full_step_kernels.md (3.29 M samples/launch)"
-NCU_TRAFFIC = {"grid_encode_backward": 292.386816e6 + 7.179008e6, "grid_encode_forward": 62.409472e6 + 167.536640e6,
-               "march_rays_train": 0.890112e6 + 46.206976e6, "field_color_backward": 236.773888e6 + 166.257664e6,
-               "field_sigma_backward": 447.215616e6 + 179.539712e6}
+NCU_TRAFFIC_SRC = "profiles/r1_29_ncu_full_step_kernels_final.md (3.29 M samples/launch)"
+NCU_TRAFFIC = {"grid_encode_backward": 292.092160e6 + 6.025984e6, "grid_encode_forward": 62.590976e6 + 166.863104e6,
+               "march_rays_train": 0.846336e6 + 47.198976e6, "field_color_backward": 236.899840e6 + 167.285248e6,
+               "field_sigma_backward": 447.282432e6 + 179.736064e6}
 RAYS = 4096
 BOUND = 3
 
