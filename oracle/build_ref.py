@@ -37,33 +37,49 @@ SPECS = {
 }
 
 
+def _build_one(name):
+    """Compile one reference module in this process (torch's JIT recipe, in-tree build directory)."""
+    os.environ["TORCH_CUDA_ARCH_LIST"] = "10.0a"
+    os.environ.setdefault("MAX_JOBS", "2")
+    from torch.utils.cpp_extension import load
+    spec = SPECS[name]
+    bdir = os.path.join(OUT, name)
+    os.makedirs(bdir, exist_ok=True)
+    src = os.path.join(REF, spec["dir"], "src")
+    load(name=name, extra_cflags=CXX, extra_cuda_cflags=NVCC + spec.get("nvcc", []),
+         extra_include_paths=[os.path.join(REF, spec["dir"], p) for p in spec.get("inc", [])],
+         sources=[os.path.join(src, f) for f in spec["srcs"]],
+         build_directory=bdir, is_python_module=False, verbose=False)
+
+
 def build(names=None):
+    """Build the missing modules, one child process each, all at once: every module is a single
+    long nvcc translation unit (2.5-5.5 min), so the four in parallel cost what `_ffmlp` costs alone."""
     if not os.path.isdir(REF):
         print(f"[build_ref] {REF} not present: skipping (prebuilt oracle/_ref is used if it exists)")
         return False
-    os.environ["TORCH_CUDA_ARCH_LIST"] = "10.0a"
-    os.environ.setdefault("MAX_JOBS", "4")
-    from torch.utils.cpp_extension import load
-    ok = True
+    import subprocess
+    todo = []
     for name in (names or list(SPECS)):
-        spec = SPECS[name]
-        bdir = os.path.join(OUT, name)
-        os.makedirs(bdir, exist_ok=True)
-        if os.path.exists(os.path.join(bdir, name + ".so")):
+        if os.path.exists(os.path.join(OUT, name, name + ".so")):
             print(f"[build_ref] {name}: already built")
-            continue
-        src = os.path.join(REF, spec["dir"], "src")
-        try:
-            load(name=name, extra_cflags=CXX, extra_cuda_cflags=NVCC + spec.get("nvcc", []),
-                 extra_include_paths=[os.path.join(REF, spec["dir"], p) for p in spec.get("inc", [])],
-                 sources=[os.path.join(src, f) for f in spec["srcs"]],
-                 build_directory=bdir, is_python_module=False, verbose=False)
-            print(f"[build_ref] {name}: built -> {bdir}/{name}.so")
-        except Exception as e:  # noqa: BLE001
+        else:
+            todo.append(name)
+    procs = [(n, subprocess.Popen([sys.executable, os.path.abspath(__file__), "--one", n],
+                                  stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)) for n in todo]
+    ok = True
+    for n, p in procs:
+        out, _ = p.communicate()
+        if p.returncode == 0:
+            print(f"[build_ref] {n}: built -> {OUT}/{n}/{n}.so")
+        else:
             ok = False
-            print(f"[build_ref] {name}: FAILED: {e}")
+            print(f"[build_ref] {n}: FAILED:\n{out[-2000:]}")
     return ok
 
 
 if __name__ == "__main__":
+    if len(sys.argv) == 3 and sys.argv[1] == "--one":
+        _build_one(sys.argv[2])
+        sys.exit(0)
     sys.exit(0 if build(sys.argv[1:] or None) else 1)
