@@ -35,6 +35,7 @@ _SIGS = {
     "enerf_grid_encode_forward": [_p, _p, _p, _p, _u32, _u32, _u32, _u32, _f32, _u32, _int, _p, _u32, _int, _int, _p],
     "enerf_grid_encode_backward": [_p, _p, _p, _p, _p, _u32, _u32, _u32, _u32, _f32, _u32, _int, _p, _p, _u32, _int, _int, _int, _p],
     "enerf_grid_set_backward_mode": [_int],
+    "enerf_grid_set_backward_block": [_int],
     "enerf_grid_set_forward_mode": [_int],
     "enerf_sh_encode_forward": [_p, _p, _u32, _u32, _u32, _int, _p, _int, _p],
     "enerf_sh_encode_backward": [_p, _p, _u32, _u32, _u32, _p, _p, _int, _p],
@@ -54,6 +55,7 @@ _SIGS = {
     "enerf_sample_event_pairs": [_p, _p, _p, _p, _u32, _u32, _int, _p, _p, _p, _p, _p, _p, _p, _p],
     "enerf_adam_step": [_p, _p, _p, _p, _u64, _p, _f32, _f32, _f32, _f32, _f32, _p, _p, _p],
     "enerf_ffmlp_set_path": [_int],
+    "enerf_ffmlp_set_max_ctas": [_int],
     "enerf_ffmlp_uses_tcgen05": [_u32, _u32, _u32, _u32, _u32],
     "enerf_allocate_splitk": [_u64],
     "enerf_free_splitk": [],

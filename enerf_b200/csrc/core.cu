@@ -22,7 +22,7 @@ void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxe
 extern "C" {
 
 const char* enerf_last_error(void) { return enerf::g_err; }
-int enerf_abi_version(void) { return 2; }   // 2: recomputation (NULL forward_buffer), events / sampler / Adam entry points
+int enerf_abi_version(void) { return 3; }   // 2: recomputation (NULL forward_buffer), events / sampler / Adam; 3: CTA cap + scatter CTA size
 uint64_t enerf_launch_count(void) { return enerf::g_launches.load(std::memory_order_relaxed); }
 
 }

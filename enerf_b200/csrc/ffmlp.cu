@@ -360,6 +360,7 @@ int tc_backward_rgb(const float* g_rgb, const float* rgb, int n_ch, const __half
                     uint32_t B, int n_hidden_mm, cudaStream_t st);
 void tc_set_bwd_tma(int on);
 void tc_set_fwd_tma(int on);
+void tc_set_max_ctas(int n);
 int tc_backward_sigma(const float* g_sigma, const float* sigma, const __half* dcin, const __half* feat, const __half* W, const __half* fwd_buf,
                       __half* dfeat, float* dW, uint32_t B, int n_hidden_mm, cudaStream_t st);
 }
@@ -516,6 +517,12 @@ int enerf_ffmlp_set_path(int path) {
     g_mlp_path = (path == 1) ? 1 : 0;
     tcm::tc_set_bwd_tma(path != 2);
     tcm::tc_set_fwd_tma(path != 2);
+    return 0;
+}
+
+int enerf_ffmlp_set_max_ctas(int n) {
+    ENERF_REQUIRE(n >= 0 && n <= kNumSM, "ffmlp_set_max_ctas", "n must be in [0, 148] (0 = one CTA per SM)");
+    tcm::tc_set_max_ctas(n);
     return 0;
 }
 

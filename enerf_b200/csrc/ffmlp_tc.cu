@@ -562,6 +562,12 @@ k_tc_fwd_tma(const __grid_constant__ TmaDesc tm_x, const __grid_constant__ TmaDe
     if (warp == 0) tmem_dealloc(tmem0, kCols);
 }
 
+// Persistent grids: one CTA per SM, optionally capped (enerf_ffmlp_set_max_ctas) so that a kernel with a different bottleneck
+// (the hash-grid scatter, bound by L2 reductions) can run on the remaining SMs from another stream at the same time.
+static int g_max_ctas = kNumSM;
+void tc_set_max_ctas(int n) { g_max_ctas = (n <= 0 || n > kNumSM) ? kNumSM : n; }
+static inline uint32_t tc_grid(uint32_t n_tiles) { return n_tiles < (uint32_t)g_max_ctas ? n_tiles : (uint32_t)g_max_ctas; }
+
 static int g_fwd_tma = -1;    // -1: read ENERF_TC_FWD_TMA (default on); 0: k_tc_fwd; 1: k_tc_fwd_tma when applicable
 void tc_set_fwd_tma(int on) { g_fwd_tma = on ? 1 : 0; }
 
@@ -578,7 +584,7 @@ static int launch_fwd_tma_n(const TmaDesc& tx, const TmaDesc& tfb, const TmaDesc
         configured = true;
     }
     const uint32_t n_tiles = B / kTile;
-    const uint32_t grid = n_tiles < (uint32_t)kNumSM ? n_tiles : (uint32_t)kNumSM;
+    const uint32_t grid = tc_grid(n_tiles);
     k_tc_fwd_tma<NSLOTS, NH, IN_DIM, HEAD, TRAIN><<<grid, 32 + NSLOTS * 128, smem, st>>>(tx, tfb, tcin, W, out, n_tiles, B, head);
     ENERF_CHECK_LAUNCH(name);
     return 0;
@@ -629,7 +635,7 @@ static int launch_fwd(const __half* in, const __half* W, uint32_t B, int n_hidde
         configured = smem;
     }
     const uint32_t n_tiles = B / kTile;
-    const uint32_t grid = n_tiles < (uint32_t)kNumSM ? n_tiles : (uint32_t)kNumSM;
+    const uint32_t grid = tc_grid(n_tiles);
     k_tc_fwd<NSLOTS, IN_DIM, HEAD><<<grid, 32 + NSLOTS * 128, smem, st>>>(in, W, fwd_buf, out, n_tiles, B, n_hidden_mm, head);
     ENERF_CHECK_LAUNCH(name);
     return 0;
@@ -1003,7 +1009,7 @@ static int launch_bwd(const __half* grad, const __half* x, const __half* W, cons
         configured = smem;
     }
     const uint32_t n_tiles = B / kTile;
-    const uint32_t grid = n_tiles < (uint32_t)kNumSM ? n_tiles : (uint32_t)kNumSM;
+    const uint32_t grid = tc_grid(n_tiles);
     k_tc_bwd<NSLOTS, PRO><<<grid, 32 + NSLOTS * 128, smem, st>>>(grad, x, W, fwd_buf, bwd_buf, grad_inputs, dW, n_tiles, B, in_dim, n_hidden_mm, pro);
     ENERF_CHECK_LAUNCH(name);
     return 0;
@@ -1382,7 +1388,7 @@ static int launch_bwd_tma_n(const TmaDesc& th, const TmaDesc& tx, const __half* 
             configured = true;
         }
         const uint32_t n_tiles = B / kTile;
-        const uint32_t grid = n_tiles < (uint32_t)kNumSM ? n_tiles : (uint32_t)kNumSM;
+        const uint32_t grid = tc_grid(n_tiles);
         k_tc_bwd_tma<NSLOTS, RING, NH, PRO, IN_DIM><<<grid, 32 + NSLOTS * 128, smem, st>>>(th, tx, grad, W, grad_inputs, dW, n_tiles, B, pro);
         ENERF_CHECK_LAUNCH(name);
         return 0;
@@ -1862,7 +1868,7 @@ static int launch_bwd_rc_n(const TmaDesc& tx, const __half* grad, const __half* 
         configured = true;
     }
     const uint32_t n_tiles = B / kTile;
-    const uint32_t grid = n_tiles < (uint32_t)kNumSM ? n_tiles : (uint32_t)kNumSM;
+    const uint32_t grid = tc_grid(n_tiles);
     k_tc_bwd_rc<NSLOTS, NH, PRO, GD, CH, XA, NI><<<grid, 32 * NI + NSLOTS * 128 * CH, smem, st>>>(tx, grad, W, grad_inputs, dW, n_tiles, B, pro);
     ENERF_CHECK_LAUNCH(name);
     return 0;

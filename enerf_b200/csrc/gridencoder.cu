@@ -24,6 +24,7 @@ namespace enerf {
 static constexpr unsigned kFull = 0xffffffffu;
 static constexpr int kSamplesPerCta = 32;
 static int g_fwd_fast = 1;   // D = 3 without input gradients: 1 = k_grid_fwd_w (warp walks the levels), 2 = k_grid_fwd3; 0 = always the generic kernel
+static int g_bwd_block = 256;  // threads per CTA of the walking scatter (enerf_grid_set_backward_block)
 static int g_bwd_walk = 1;   // 1: walking scatter (register aggregation along rays), 0: one reduction per corner
 
 // ---- element-type helpers: the accumulator is rounded to T after every corner -----------
@@ -880,9 +881,10 @@ static int launch_bwd(const T* grad, const float* inputs, const int32_t* offsets
         auto go = [&](auto seg_tag) {
             constexpr int SEG = decltype(seg_tag)::value;
             const uint64_t threads = (uint64_t)ceil_div(B, (uint32_t)SEG) * L;
-            const dim3 grid((uint32_t)ceil_div(threads, (uint64_t)256));
-            if (out_layout == 1) k_grid_bwd_walk<T, G, D, C, true, SEG><<<grid, 256, 0, st>>>(grad, inputs, offsets, gg, B, L, S, H, gridtype);
-            else k_grid_bwd_walk<T, G, D, C, false, SEG><<<grid, 256, 0, st>>>(grad, inputs, offsets, gg, B, L, S, H, gridtype);
+            const uint32_t block = (uint32_t)g_bwd_block;
+            const dim3 grid((uint32_t)ceil_div(threads, (uint64_t)block));
+            if (out_layout == 1) k_grid_bwd_walk<T, G, D, C, true, SEG><<<grid, block, 0, st>>>(grad, inputs, offsets, gg, B, L, S, H, gridtype);
+            else k_grid_bwd_walk<T, G, D, C, false, SEG><<<grid, block, 0, st>>>(grad, inputs, offsets, gg, B, L, S, H, gridtype);
         };
         if (seg == 16) go(std::integral_constant<int, 16>{});
         else if (seg == 64) go(std::integral_constant<int, 64>{});
@@ -935,6 +937,13 @@ extern "C" {
 int enerf_grid_set_forward_mode(int mode) {
     ENERF_REQUIRE(mode >= 0 && mode <= 2, "grid_set_forward_mode", "mode must be 0 (generic kernel), 1 (warp-walks-levels D=3 kernel) or 2 (per-level D=3 kernel)");
     g_fwd_fast = mode;
+    return 0;
+}
+
+int enerf_grid_set_backward_block(int threads) {
+    ENERF_REQUIRE(threads == 64 || threads == 128 || threads == 192 || threads == 256, "grid_set_backward_block",
+                  "threads must be 64, 128, 192 or 256");
+    g_bwd_block = threads;
     return 0;
 }
 

@@ -49,11 +49,18 @@ class NeRFNetwork(NeRFRenderer):
         """x [N,3] in [-bound, bound], d [N,3] unit  ->  sigma [N] fp32, rgb [N, out_dim_color]"""
         fusable = self.fuse_field and not self.disable_view_direction and torch.is_autocast_enabled('cuda')
         if fusable:
+            shapes = (self.hidden_dim, self.hidden_dim_color, self.in_dim, self.in_dim_color, self.geo_feat_dim,
+                      getattr(self.encoder_dir, 'degree', -1), self.out_dim_color, self.sigma_net.activation)
+            training = self.training and torch.is_grad_enabled()
+            if (field.PIPELINE and training and field.shapes_eligible(*shapes) and field.encoder_eligible(self.encoder, x)
+                    and d.shape[0] == x.shape[0]):
+                # encoder + field as one autograd node: its backward overlaps the hash-grid scatter with the MLP backward
+                return field.encoded_field((x + self.bound) / (2 * self.bound), d, self.encoder, self.sigma_net.weights, self.color_net.weights,
+                                           self.num_layers, self.num_layers_color, self.out_dim_color, True)
             feat = self.encoder(x, bound=self.bound)
-            if field.eligible(feat, d, self.hidden_dim, self.hidden_dim_color, self.in_dim, self.in_dim_color, self.geo_feat_dim,
-                              getattr(self.encoder_dir, 'degree', -1), self.out_dim_color, self.sigma_net.activation):
+            if field.eligible(feat, d, *shapes):
                 return field.fused_field(feat, d, self.sigma_net.weights, self.color_net.weights, self.num_layers, self.num_layers_color,
-                                         self.out_dim_color, self.training and torch.is_grad_enabled())
+                                         self.out_dim_color, training)
             h = self.sigma_net(feat)
             sigma, geo_feat = trunc_exp(h[..., 0]), h[..., 1:]
         else:

@@ -125,6 +125,9 @@ int enerf_grid_encode_backward(const void* grad, const float* inputs, const void
  * 32 consecutive samples of one level and aggregates in registers while they stay in one cell;
  * 0 = one reduction per corner per sample (the reference's strategy).  Same sums either way. */
 int enerf_grid_set_backward_mode(int mode);
+/* Threads per CTA of the walking scatter: 64, 128, 192 or 256 (default).  Smaller CTAs fit next to a
+ * resident tcgen05 MLP CTA (53 K registers) when the two kernels run concurrently on two streams. */
+int enerf_grid_set_backward_block(int threads);
 /* Forward kernel selector (tests), D = 3 without input gradients: 1 (default) = a warp walks all levels of its
  * 32 samples (persistent CTAs), 2 = one warp per (32 samples, level), 0 = always the generic kernel.
  * Bit-identical outputs. */
@@ -181,6 +184,10 @@ int enerf_allocate_splitk(uint64_t size);
  * otherwise; 1 = always the generic mma.sync kernels; 2 = tcgen05 kernels with per-thread operand loads
  * instead of TMA (used by the parity tests to cross-check the families). */
 int enerf_ffmlp_set_path(int path);
+/* Cap on the persistent grid of the tcgen05 kernels (no reference counterpart): n CTAs instead of one
+ * per SM (148); 0 restores the default.  Used by the pipelined backward (enerf_b200/field.py), which
+ * leaves SMs to the hash-grid scatter running on a second stream. */
+int enerf_ffmlp_set_max_ctas(int n);
 /* 1 when forward/inference/backward of this shape run on the tcgen05 kernels (backward_buffer may
  * then be NULL), else 0.  Not a compute call: usable without a GPU. */
 int enerf_ffmlp_uses_tcgen05(uint32_t input_dim, uint32_t hidden_dim, uint32_t num_layers, uint32_t activation,
