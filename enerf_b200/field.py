@@ -88,7 +88,10 @@ def fused_field(feat, dirs, w_sigma, w_color, nl_sigma, nl_color, n_ch, training
 # a capped number of SMs while the scatter of chunk k runs on a second stream on the rest.  Same kernels, same sums (fp32
 # reductions in a different order); CUDA-graph capturable (fork / join through events).
 #
-# ENERF_PIPELINE=1 turns it on (default off until measured on more shapes); ENERF_PIPELINE_CHUNKS / _MLP_CTAS / _SCATTER_BLOCK.
+# Measured on B200 (profiles/r1_30_overlap_probe_two_streams.json, 3.29 M samples): SLOWER than back to back in every setting
+# (1.32 ms -> 1.46 / 1.66 / 1.84 ms with 2 / 4 / 8 chunks; capping the MLP grid makes it worse) — both kernels need all SMs, and an
+# MLP CTA cannot be placed until the scatter CTAs on its SM have drained.  Kept as a tested experiment: ENERF_PIPELINE=1 turns it
+# on (default off); ENERF_PIPELINE_CHUNKS / _MLP_CTAS / _SCATTER_BLOCK.
 PIPELINE = os.environ.get("ENERF_PIPELINE", "0") == "1"
 PIPELINE_CHUNKS = int(os.environ.get("ENERF_PIPELINE_CHUNKS", "4"))
 PIPELINE_MLP_CTAS = int(os.environ.get("ENERF_PIPELINE_MLP_CTAS", "120"))
