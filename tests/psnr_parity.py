@@ -8,8 +8,8 @@ Two trainings from identical initial parameters on identical ray batches:
 then both render the 8 training poses; reports PSNR vs the analytic target for each, their difference (the north star asks
 for <= 0.1 dB) and the PSNR between the two renderings.
 
-  python tools/psnr_parity.py [--steps 200] [--num-steps 128] [--rays 256] [--res 64]
-Used by tests/test_gpu_renderer.py::test_psnr_parity_tiny_scene (test infrastructure: it imports oracle/).
+  python tests/psnr_parity.py [--steps 200] [--num-steps 128] [--rays 256] [--res 64]
+Test infrastructure (it imports oracle/): used by tests/test_gpu_renderer.py::test_psnr_parity_tiny_scene.
 """
 import argparse
 import json

@@ -329,9 +329,7 @@ def test_pipelined_backward_matches_sequential(graph):
 def test_psnr_parity_tiny_scene():
     """BASELINE configs[0]: train the CPU port of the reference's pure-PyTorch renderer and this repo's GPU stack from the same
     initial parameters on the same ray batches; rendered PSNR must agree within the north star's 0.1 dB."""
-    import sys
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
-    import psnr_parity
+    from tests import psnr_parity
     r = psnr_parity.run(steps=60, num_steps=96, rays=256, res=48)
     assert r["psnr_ours_db"] > 12.0 and r["psnr_reference_db"] > 12.0, r          # both actually learned the scene
     assert r["abs_diff_db"] <= 0.1, r
