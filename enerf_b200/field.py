@@ -95,7 +95,7 @@ def fused_field(feat, dirs, w_sigma, w_color, nl_sigma, nl_color, n_ch, training
 PIPELINE = os.environ.get("ENERF_PIPELINE", "0") == "1"
 PIPELINE_CHUNKS = int(os.environ.get("ENERF_PIPELINE_CHUNKS", "4"))
 PIPELINE_MLP_CTAS = int(os.environ.get("ENERF_PIPELINE_MLP_CTAS", "120"))
-PIPELINE_SCATTER_BLOCK = int(os.environ.get("ENERF_PIPELINE_SCATTER_BLOCK", "256"))
+PIPELINE_SCATTER_BLOCK = int(os.environ.get("ENERF_PIPELINE_SCATTER_BLOCK", "0"))
 _side_streams = {}
 
 
@@ -152,7 +152,7 @@ def pipelined_backward(g_sigma, g_rgb, sigma, rgb, cin, feat, x, table, offsets,
                                         False, dummy, dummy, gridtype, 1)
     finally:
         _lib.call("enerf_ffmlp_set_max_ctas", 0)
-        _lib.call("enerf_grid_set_backward_block", 256)
+        _lib.call("enerf_grid_set_backward_block", 0)
     join = torch.cuda.Event()
     join.record(side)
     main.wait_event(join)

@@ -125,7 +125,7 @@ int enerf_grid_encode_backward(const void* grad, const float* inputs, const void
  * 32 consecutive samples of one level and aggregates in registers while they stay in one cell;
  * 0 = one reduction per corner per sample (the reference's strategy).  Same sums either way. */
 int enerf_grid_set_backward_mode(int mode);
-/* Threads per CTA of the walking scatter: 64, 128, 192 or 256 (default).  Smaller CTAs fit next to a
+/* Threads per CTA of the walking scatter: 64, 128 (default; 0 restores it), 192 or 256.  Smaller CTAs fit next to a
  * resident tcgen05 MLP CTA (53 K registers) when the two kernels run concurrently on two streams. */
 int enerf_grid_set_backward_block(int threads);
 /* Forward kernel selector (tests), D = 3 without input gradients: 1 (default) = a warp walks all levels of its
