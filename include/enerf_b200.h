@@ -129,8 +129,9 @@ int enerf_grid_set_backward_mode(int mode);
  * resident tcgen05 MLP CTA (53 K registers) when the two kernels run concurrently on two streams. */
 int enerf_grid_set_backward_block(int threads);
 /* Forward kernel selector (tests), D = 3 without input gradients: 1 (default) = a warp walks all levels of its
- * 32 samples (persistent CTAs), 2 = one warp per (32 samples, level), 0 = always the generic kernel.
- * Bit-identical outputs. */
+ * 32 samples (persistent CTAs), 2 = one warp per (32 samples, level), 0 = always the generic kernel,
+ * 3 = mode 1 with the two x-neighbour corners fetched by one 8-byte load where they share an aligned
+ * block (fp16 tables with 2 features; experimental, not yet measured).  Bit-identical outputs. */
 int enerf_grid_set_forward_mode(int mode);
 
 /* -------------------------------------------------------------------- shencoder ---- */

@@ -7,6 +7,8 @@ in arbitrary order -> compared with the exact (float64) sum, 1e-4 relative to th
 gradient for fp32 accumulation, 2e-2 for the reference-style fp16 atomics.  SH: fp32 within
 2e-6 of the closed forms; fp16 outputs within 1 fp16 ulp of the fp32 value (the reference
 evaluates in fp16 and is up to ~4 ulp away from it)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -90,6 +92,9 @@ def test_grid_forward_hoisted_kernel_is_bit_identical_to_generic(dtype):
     """The two hot-path kernels — k_grid_fwd_w (mode 1: a warp walks all levels of its 32 samples) and k_grid_fwd3 (mode 2: one warp per
     (32 samples, level)) — vs the generic k_grid_fwd (mode 0), and all vs the reference build when it is available."""
     from enerf_b200 import _lib
+    # mode 3 (mode 1 with paired 8-byte loads) was written after the round's GPU budget was spent: not the default, and checked
+    # here only on request until it has had its first run on a GPU (ENERF_TEST_EXPERIMENTAL=1)
+    MODES = (1, 2, 3) if os.environ.get("ENERF_TEST_EXPERIMENTAL", "0") == "1" else (1, 2)
     R = ref_mod("_gridencoder")
     rng = np.random.default_rng(12)
     for bound, C, L, gridtype, log2T in [(3, 2, 16, 0, 19), (1, 2, 16, 0, 19), (2, 2, 16, 1, 19), (1, 4, 8, 0, 14), (2, 1, 16, 0, 12), (1, 8, 4, 1, 9)]:
@@ -101,14 +106,14 @@ def test_grid_forward_hoisted_kernel_is_bit_identical_to_generic(dtype):
         B = len(x)
         outs = {}
         try:
-            for mode in (1, 2, 0):
+            for mode in MODES + (0,):
                 _lib.call("enerf_grid_set_forward_mode", mode)
                 for layout in (0, 1):
                     o, _ = _fwd(x, emb, offsets, pls, layout, gridtype=gridtype)
                     outs[(mode, layout)] = o
         finally:
             _lib.call("enerf_grid_set_forward_mode", 1)
-        for mode in (1, 2):
+        for mode in MODES:
             assert torch.equal(outs[(mode, 0)], outs[(0, 0)]), (mode, bound, C, L, gridtype)
             assert torch.equal(outs[(mode, 1)], outs[(0, 1)]), (mode, bound, C, L, gridtype)
         assert torch.equal(outs[(1, 1)].view(B, L, C).permute(1, 0, 2), outs[(1, 0)])
