@@ -9,7 +9,7 @@ CUDA stream, so code written against the reference extensions runs unchanged.
 import torch
 
 from . import _lib
-from ._lib import check, dtype_code, need_cuda, ptr, stream
+from ._lib import dtype_code, need_cuda, ptr, stream
 
 
 def _contig(name, *ts):

@@ -18,7 +18,6 @@ Differences (results identical up to fp reassociation):
 """
 import math
 
-import numpy as np
 import torch
 import torch.nn as nn
 

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from enerf_b200 import _lib, synthetic  # noqa: E402
+from enerf_b200 import synthetic  # noqa: E402
 from enerf_b200 import raymarching as rm  # noqa: E402
 from enerf_b200.backends import ffmlp_backend as FB, gridencoder_backend as GB, raymarching_backend as RB  # noqa: E402
 from enerf_b200.gridencoder import GridEncoder  # noqa: E402

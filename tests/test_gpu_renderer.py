@@ -2,7 +2,6 @@
 kernels vs (a) the CPU port of the reference's pure-PyTorch renderer with identical weights and
 (b) a stage-by-stage oracle composition of the cuda_ray path.  fp32 paths: 1e-4; fp16 autocast
 paths: 5e-3 (one fp16 ulp at the magnitude of the MLP activations)."""
-import os
 
 import numpy as np
 import pytest
