@@ -46,14 +46,14 @@ _SIGS = {
     "enerf_field_color_forward": [_p, _p, _u32, _u32, _u32, _p, _p, _p],
     "enerf_field_color_backward": [_p, _p, _u32, _p, _p, _p, _u32, _u32, _p, _p, _p],
     "enerf_field_sigma_backward": [_p, _p, _p, _p, _p, _p, _u32, _u32, _p, _p, _p],
-    "enerf_composite_uniform_forward": [_p, _p, _p, _p, _u32, _u32, _f32, _p, _p, _p, _p],
-    "enerf_composite_uniform_backward": [_p, _p, _p, _p, _p, _p, _p, _u32, _u32, _f32, _p, _p],
+    "enerf_composite_uniform_forward": [_p, _p, _p, _p, _u32, _u32, _u32, _f32, _p, _p, _p, _p],
+    "enerf_composite_uniform_backward": [_p, _p, _p, _p, _p, _p, _p, _u32, _u32, _u32, _f32, _p, _p],
     "enerf_get_rays": [_p, _f32, _f32, _f32, _f32, _u32, _u32, _p, _u32, _u32, _u32, _p, _f32, _p, _p, _p, _p, _p],
     "enerf_event_rays": [_p, _p, _p, _p, _f32, _f32, _f32, _f32, _u32, _p, _f32, _p, _p, _p, _p, _p, _p, _p],
     "enerf_event_loss_forward": [_p, _p, _p, _u32, _u32, _int, _int, _f32, _f32, _f32, _p, _p, _p, _p],
     "enerf_event_loss_backward": [_p, _p, _p, _p, _p, _p, _u32, _u32, _int, _int, _f32, _f32, _f32, _p, _p, _p],
     "enerf_sample_event_pairs": [_p, _p, _p, _p, _u32, _u32, _int, _p, _p, _p, _p, _p, _p, _p, _p],
-    "enerf_adam_step": [_p, _p, _p, _p, _u64, _p, _f32, _f32, _f32, _f32, _f32, _p, _p, _p],
+    "enerf_adam_step": [_p, _p, _p, _p, _u64, _p, _f32, _f32, _f32, _f32, _f32, _p, _p, _p, _p],
     "enerf_ffmlp_set_path": [_int],
     "enerf_ffmlp_set_max_ctas": [_int],
     "enerf_ffmlp_uses_tcgen05": [_u32, _u32, _u32, _u32, _u32],

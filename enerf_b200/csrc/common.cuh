@@ -47,7 +47,8 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 template <typename T>
 __host__ __device__ inline T ceil_div(T a, T b) { return (a + b - 1) / b; }
 
-constexpr int kNumSM = 148;  // B200
+// SMs of the current device (148 on B200), queried once per device through cudaDeviceGetAttribute: persistent grids are sized from it
+int num_sms();
 
 // ---- device helpers -----------------------------------------------------------------------
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }

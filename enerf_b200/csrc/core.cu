@@ -17,12 +17,26 @@ void set_error(const char* fmt, ...) {
 
 void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+int num_sms() {
+    static std::atomic<int> cached[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    int n = cached[dev].load(std::memory_order_relaxed);
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev].store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
+
 }  // namespace enerf
 
 extern "C" {
 
 const char* enerf_last_error(void) { return enerf::g_err; }
-int enerf_abi_version(void) { return 3; }   // 2: recomputation (NULL forward_buffer), events / sampler / Adam; 3: CTA cap + scatter CTA size
+// 2: recomputation (NULL forward_buffer), events / sampler / Adam; 3: CTA cap + scatter CTA size; 4: fp16 shadow in adam_step,
+// T_dist in composite_uniform_*
+int enerf_abi_version(void) { return 4; }
 uint64_t enerf_launch_count(void) { return enerf::g_launches.load(std::memory_order_relaxed); }
 
 }

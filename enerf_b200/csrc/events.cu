@@ -311,11 +311,11 @@ __global__ void k_sample_event_pairs(const float* __restrict__ events, const dou
     if (t >= M) return;
     // start ~ U{0..E-1} (np.random.randint(0, E)); a pixel's last event has no successor: take its predecessor (provider.py:1369-1371)
     uint32_t s = min((uint32_t)(__ldg(u_start + t) * (float)E), E - 1);
-    if (no_succ[s]) s -= 1;
-    int32_t n = num_succ[s];
+    if (no_succ[s] && s > 0) s -= 1;                                // (layout validated on the host: EventPairSampler.__init__)
+    int32_t n = max(num_succ[s], 1);
     if (acc_max > 0) n = min(n, acc_max + 1);                       // provider.py:1378-1379
     // end ~ U{s+1 .. s+n} (np.random.randint(s+1, s+1+n))
-    const uint32_t e = s + 1 + min((uint32_t)(__ldg(u_end + t) * (float)n), (uint32_t)(n - 1));
+    const uint32_t e = min(s + 1 + min((uint32_t)(__ldg(u_end + t) * (float)n), (uint32_t)(n - 1)), E - 1);
     eidx[t] = s;
     eidx_end[t] = e;
     pols[t] = (float)(pol_prefix[e + 1] - pol_prefix[s + 1]);       // sum of events[s+1 .. e, 3]

@@ -293,7 +293,7 @@ static int run_fwd(const __half* in, const __half* W, uint32_t B, int in_dim, in
         configured = smem;
     }
     const uint32_t n_tiles = B / Shape<WIDTH>::ROWS;
-    const uint32_t grid = n_tiles < (uint32_t)(kNumSM * 4) ? n_tiles : (uint32_t)(kNumSM * 4);
+    const uint32_t grid = n_tiles < (uint32_t)(num_sms() * 4) ? n_tiles : (uint32_t)(num_sms() * 4);
     k_mlp_fwd<WIDTH><<<grid, kWarps * 32, smem, st>>>(in, W, fwd_buf, out, B, in_dim, nhm, act, out_act);
     ENERF_CHECK_LAUNCH(name);
     return 0;
@@ -310,7 +310,7 @@ static int run_bwd(const __half* grad, const __half* W, const __half* fwd_buf, _
         configured = smem;
     }
     const uint32_t n_tiles = B / Shape<WIDTH>::ROWS;
-    const uint32_t grid = n_tiles < (uint32_t)(kNumSM * 2) ? n_tiles : (uint32_t)(kNumSM * 2);
+    const uint32_t grid = n_tiles < (uint32_t)(num_sms() * 2) ? n_tiles : (uint32_t)(num_sms() * 2);
     k_mlp_bwd<WIDTH><<<grid, kWarps * 32, smem, st>>>(grad, W, fwd_buf, bwd_buf, grad_inputs, B, in_dim, nhm, act);
     ENERF_CHECK_LAUNCH("ffmlp_backward");
     return 0;
@@ -318,7 +318,7 @@ static int run_bwd(const __half* grad, const __half* W, const __half* fwd_buf, _
 
 static int run_wgrad(const __half* dY, int ldY, const __half* X, int ldX, float* dW, uint32_t B, int M, int N, cudaStream_t st) {
     const dim3 grid_mn(1, ceil_div(M, 64), ceil_div(N, 64));
-    uint32_t ks = (uint32_t)(2 * kNumSM) / (grid_mn.y * grid_mn.z);
+    uint32_t ks = (uint32_t)(2 * num_sms()) / (grid_mn.y * grid_mn.z);
     const uint32_t n_blocks = B / kWgRows;
     if (ks > n_blocks) ks = n_blocks;
     if (ks < 1) ks = 1;
@@ -521,7 +521,7 @@ int enerf_ffmlp_set_path(int path) {
 }
 
 int enerf_ffmlp_set_max_ctas(int n) {
-    ENERF_REQUIRE(n >= 0 && n <= kNumSM, "ffmlp_set_max_ctas", "n must be in [0, 148] (0 = one CTA per SM)");
+    ENERF_REQUIRE(n >= 0 && n <= num_sms(), "ffmlp_set_max_ctas", "n must be in [0, SM count] (0 = one CTA per SM)");
     tcm::tc_set_max_ctas(n);
     return 0;
 }

@@ -564,9 +564,12 @@ k_tc_fwd_tma(const __grid_constant__ TmaDesc tm_x, const __grid_constant__ TmaDe
 
 // Persistent grids: one CTA per SM, optionally capped (enerf_ffmlp_set_max_ctas) so that a kernel with a different bottleneck
 // (the hash-grid scatter, bound by L2 reductions) can run on the remaining SMs from another stream at the same time.
-static int g_max_ctas = kNumSM;
-void tc_set_max_ctas(int n) { g_max_ctas = (n <= 0 || n > kNumSM) ? kNumSM : n; }
-static inline uint32_t tc_grid(uint32_t n_tiles) { return n_tiles < (uint32_t)g_max_ctas ? n_tiles : (uint32_t)g_max_ctas; }
+static int g_max_ctas = 0;    // 0 = one CTA per SM
+void tc_set_max_ctas(int n) { g_max_ctas = (n <= 0 || n > num_sms()) ? 0 : n; }
+static inline uint32_t tc_grid(uint32_t n_tiles) {
+    const uint32_t cap = (uint32_t)(g_max_ctas > 0 ? g_max_ctas : num_sms());
+    return n_tiles < cap ? n_tiles : cap;
+}
 
 static int g_fwd_tma = -1;    // -1: read ENERF_TC_FWD_TMA (default on); 0: k_tc_fwd; 1: k_tc_fwd_tma when applicable
 void tc_set_fwd_tma(int on) { g_fwd_tma = on ? 1 : 0; }

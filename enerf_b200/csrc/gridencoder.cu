@@ -16,15 +16,13 @@
 //     grid.py:70) and scatters with vector reductions (red.global.add.v2.f32 / .noftz.f16x2).
 #include "common.cuh"
 #include <math.h>
-#include <stdlib.h>
 #include <type_traits>
 
 namespace enerf {
 
 static constexpr unsigned kFull = 0xffffffffu;
 static constexpr int kSamplesPerCta = 32;
-static int g_fwd_fast = 1;   // D = 3 without input gradients: 1 = k_grid_fwd_w (warp walks the levels), 3 = the same with paired 8-byte loads,
-                             // 2 = k_grid_fwd3; 0 = always the generic kernel
+static int g_fwd_fast = 1;   // D = 3 without input gradients: 1 = k_grid_fwd_w (warp walks the levels), 2 = k_grid_fwd3; 0 = always the generic kernel
 constexpr int kBwdBlockDefault = 128;   // measured (3.29 M samples): 256: 0.685, 192: 0.688, 128: 0.675, 64: 0.673 ms
 static int g_bwd_block = kBwdBlockDefault;  // threads per CTA of the walking scatter (enerf_grid_set_backward_block)
 static int g_bwd_walk = 1;   // 1: walking scatter (register aggregation along rays), 0: one reduction per corner
@@ -423,11 +421,7 @@ template <typename T, int C>
 struct LevelWork {
     float wxy[4], wz[2];
     T v[8][C];
-    // PAIR (fp16 table, 2 features): the two x-neighbour corners of a (y, z) pair sit in one aligned 8-byte block whenever their
-    // entry indices differ only in bit 0 — always for an even x on a hashed power-of-two level ((x ^ h) and ((x + 1) ^ h)), for an
-    // even index on a dense level — so one 8-byte load fetches both and the second 4-byte load is issued only by the other lanes:
-    // 6 instead of 8 sector accesses per (sample, level) on average.  Same values, same blend.
-    template <int MODE, bool PAIR = false>
+    template <int MODE>
     __device__ __forceinline__ void fetch(const LevelTabW& lt, const T* __restrict__ grid, const float (&x)[3]) {
         const T* __restrict__ tab = grid + (size_t)lt.offset * C;
         float fr[3];
@@ -441,22 +435,7 @@ struct LevelWork {
         }
         uint32_t e[8];
         corner_index<C, MODE>(lt, pg, e);
-        if (PAIR && MODE != 2 && C == 2 && sizeof(T) == 2) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t e0 = e[2 * k], e1 = e[2 * k + 1];                 // element offsets = entry index * 2
-                const bool odd = (e0 & 2u) != 0u;
-                const uint2 pr = __ldg(reinterpret_cast<const uint2*>(tab + (e0 & ~2u)));
-                const uint32_t w0 = odd ? pr.y : pr.x;
-                uint32_t w1 = odd ? pr.x : pr.y;
-                if ((e0 ^ e1) != 2u) w1 = __ldg(reinterpret_cast<const uint32_t*>(tab + e1));
-                const __half2 h0 = *reinterpret_cast<const __half2*>(&w0), h1 = *reinterpret_cast<const __half2*>(&w1);
-                v[2 * k][0] = *reinterpret_cast<const T*>(&h0.x);
-                v[2 * k][C - 1] = *reinterpret_cast<const T*>(&h0.y);
-                v[2 * k + 1][0] = *reinterpret_cast<const T*>(&h1.x);
-                v[2 * k + 1][C - 1] = *reinterpret_cast<const T*>(&h1.y);
-            }
-        } else if (C == 2 && sizeof(T) == 2) {
+        if (C == 2 && sizeof(T) == 2) {
 #pragma unroll
             for (int idx = 0; idx < 8; ++idx) {
                 const __half2 h2 = __ldg(reinterpret_cast<const __half2*>(tab + e[idx]));
@@ -501,7 +480,7 @@ struct LevelWork {
     }
 };
 
-template <typename T, int C, bool BLC, bool PAIR = false>
+template <typename T, int C, bool BLC>
 __global__ void __launch_bounds__(256)
 k_grid_fwd_w(const float* __restrict__ inputs, const T* __restrict__ grid, const int32_t* __restrict__ offsets,
              T* __restrict__ outputs, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype, uint32_t n_groups,
@@ -577,8 +556,8 @@ k_grid_fwd_w(const float* __restrict__ inputs, const T* __restrict__ grid, const
             uint32_t level = lo;
             for (; level + 1 < hi; level += 2) {
                 LevelWork<T, C> wa, wb;
-                wa.template fetch<MODE, PAIR>(ltab[level], grid, x);
-                wb.template fetch<MODE, PAIR>(ltab[level + 1], grid, x);
+                wa.template fetch<MODE>(ltab[level], grid, x);
+                wb.template fetch<MODE>(ltab[level + 1], grid, x);
                 uint32_t oa[WPL], ob[WPL];
                 wa.blend(oa, oob);
                 wb.blend(ob, oob);
@@ -587,7 +566,7 @@ k_grid_fwd_w(const float* __restrict__ inputs, const T* __restrict__ grid, const
             }
             if (level < hi) {
                 LevelWork<T, C> wa;
-                wa.template fetch<MODE, PAIR>(ltab[level], grid, x);
+                wa.template fetch<MODE>(ltab[level], grid, x);
                 uint32_t oa[WPL];
                 wa.blend(oa, oob);
                 emit(level, oa);
@@ -853,7 +832,7 @@ static int launch_fwd(const float* inputs, const T* emb, const int32_t* offsets,
     const dim3 grid(ceil_div(B, (uint32_t)kSamplesPerCta));
     const bool fast = (D == 3) && !cg && g_fwd_fast;
     constexpr int kWpl = (C * (int)sizeof(T)) / 4;
-    if (fast && (g_fwd_fast == 1 || g_fwd_fast == 3) && kWpl >= 1 && L * kWpl <= 64) {
+    if (fast && g_fwd_fast == 1 && kWpl >= 1 && L * kWpl <= 64) {
         // v2: warp walks all levels of its 32 samples (persistent CTAs of 8 warps)
         const uint32_t n_groups = ceil_div(B, 32u);
         const uint32_t row_words = (L * kWpl) | 1u;
@@ -865,14 +844,13 @@ static int launch_fwd(const float* inputs, const T* emb, const int32_t* offsets,
             int per_sm = 0;
             ENERF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem), "grid_encode_forward");
             if (per_sm < 1) per_sm = 1;
-            const uint32_t ctas = min(ceil_div(n_groups, 8u), (uint32_t)kNumSM * (uint32_t)per_sm);
+            const uint32_t ctas = min(ceil_div(n_groups, 8u), (uint32_t)num_sms() * (uint32_t)per_sm);
             kern<<<ctas, 256, smem, st>>>(inputs, emb, offsets, outputs, B, L, S, H, gridtype, n_groups, row_words);
             return 0;
         };
-        constexpr bool kCanPair = (CCc == 2 && sizeof(T) == 2);
-        int rc;
-        if (kCanPair && g_fwd_fast == 3) rc = (out_layout == 1) ? launch(k_grid_fwd_w<T, CCc, true, kCanPair>) : launch(k_grid_fwd_w<T, CCc, false, kCanPair>);
-        else rc = (out_layout == 1) ? launch(k_grid_fwd_w<T, CCc, true>) : launch(k_grid_fwd_w<T, CCc, false>);
+        // (A variant fetching the two x-neighbour corners with one 8-byte load where they share an aligned block — 6 instead of 8
+        // sector accesses per sample-level — was bit-identical but slower on B200, 0.465 vs 0.399 ms: removed, profiles/r2_01.)
+        const int rc = (out_layout == 1) ? launch(k_grid_fwd_w<T, CCc, true>) : launch(k_grid_fwd_w<T, CCc, false>);
         if (rc) return rc;
         ENERF_CHECK_LAUNCH("grid_encode_forward");
         return 0;
@@ -896,24 +874,15 @@ static int launch_bwd(const T* grad, const float* inputs, const int32_t* offsets
                       bool cg, const T* dy_dx, T* grad_inputs, uint32_t gridtype, int out_layout, cudaStream_t st) {
     if (g_bwd_walk && L <= 32 && (32 % L) == 0) {
         // samples per thread-run: every run boundary costs one extra flush (8 reductions) per level, longer runs mean fewer threads
-        static int seg = 0;
-        if (seg == 0) {
-            const char* e = getenv("ENERF_GRID_BWD_SEG");
-            seg = e ? atoi(e) : 64;                 // measured (3.29 M samples): 16: 0.768, 32: 0.707, 64: 0.696, 128: 0.715 ms
-            if (seg != 16 && seg != 32 && seg != 64 && seg != 128) seg = 64;
-        }
-        auto go = [&](auto seg_tag) {
-            constexpr int SEG = decltype(seg_tag)::value;
+        // (measured, 3.29 M samples: 16: 0.768, 32: 0.707, 64: 0.696, 128: 0.715 ms)
+        {
+            constexpr int SEG = 64;
             const uint64_t threads = (uint64_t)ceil_div(B, (uint32_t)SEG) * L;
             const uint32_t block = (uint32_t)g_bwd_block;
             const dim3 grid((uint32_t)ceil_div(threads, (uint64_t)block));
             if (out_layout == 1) k_grid_bwd_walk<T, G, D, C, true, SEG><<<grid, block, 0, st>>>(grad, inputs, offsets, gg, B, L, S, H, gridtype);
             else k_grid_bwd_walk<T, G, D, C, false, SEG><<<grid, block, 0, st>>>(grad, inputs, offsets, gg, B, L, S, H, gridtype);
-        };
-        if (seg == 16) go(std::integral_constant<int, 16>{});
-        else if (seg == 64) go(std::integral_constant<int, 64>{});
-        else if (seg == 128) go(std::integral_constant<int, 128>{});
-        else go(std::integral_constant<int, 32>{});
+        }
     } else {
         const dim3 block(32, min(L, 16u));
         const dim3 grid(ceil_div(B, (uint32_t)kSamplesPerCta));
@@ -959,8 +928,8 @@ using namespace enerf;
 extern "C" {
 
 int enerf_grid_set_forward_mode(int mode) {
-    ENERF_REQUIRE(mode >= 0 && mode <= 3, "grid_set_forward_mode",
-                  "mode must be 0 (generic kernel), 1 (warp-walks-levels D=3 kernel), 2 (per-level D=3 kernel) or 3 (mode 1 with paired 8-byte loads)");
+    ENERF_REQUIRE(mode >= 0 && mode <= 2, "grid_set_forward_mode",
+                  "mode must be 0 (generic kernel), 1 (warp-walks-levels D=3 kernel) or 2 (per-level D=3 kernel)");
     g_fwd_fast = mode;
     return 0;
 }

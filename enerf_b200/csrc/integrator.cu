@@ -48,13 +48,13 @@ __device__ __forceinline__ RayStep load_step(const float* __restrict__ sig, cons
 
 __global__ void __launch_bounds__(256)
 k_uniform_fwd(const float* __restrict__ sigmas, const float* __restrict__ z_vals, const float* __restrict__ nears,
-              const float* __restrict__ fars, uint32_t N, uint32_t T, float density_scale, float* __restrict__ weights,
+              const float* __restrict__ fars, uint32_t N, uint32_t T, uint32_t T_dist, float density_scale, float* __restrict__ weights,
               float* __restrict__ weights_sum, float* __restrict__ depth) {
     const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (n >= N) return;
     const unsigned lane = lane_id();
     const float near = nears[n], far = fars[n];
-    const float sample_dist = (far - near) / (float)T;
+    const float sample_dist = (far - near) / (float)T_dist;
     const float* sig = sigmas + (size_t)n * T;
     const float* zv = z_vals + (size_t)n * T;
     float* wout = weights + (size_t)n * T;
@@ -91,12 +91,12 @@ k_uniform_fwd(const float* __restrict__ sigmas, const float* __restrict__ z_vals
 __global__ void __launch_bounds__(256)
 k_uniform_bwd(const float* __restrict__ grad_weights, const float* __restrict__ grad_ws, const float* __restrict__ grad_depth,
               const float* __restrict__ sigmas, const float* __restrict__ z_vals, const float* __restrict__ nears,
-              const float* __restrict__ fars, uint32_t N, uint32_t T, float density_scale, float* __restrict__ grad_sigmas) {
+              const float* __restrict__ fars, uint32_t N, uint32_t T, uint32_t T_dist, float density_scale, float* __restrict__ grad_sigmas) {
     const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (n >= N) return;
     const unsigned lane = lane_id();
     const float near = nears[n], far = fars[n];
-    const float sample_dist = (far - near) / (float)T;
+    const float sample_dist = (far - near) / (float)T_dist;
     const float* sig = sigmas + (size_t)n * T;
     const float* zv = z_vals + (size_t)n * T;
     const float* gw = grad_weights ? grad_weights + (size_t)n * T : nullptr;
@@ -163,19 +163,22 @@ using namespace enerf;
 extern "C" {
 
 int enerf_composite_uniform_forward(const float* sigmas, const float* z_vals, const float* nears, const float* fars, uint32_t N,
-                                    uint32_t T, float density_scale, float* weights, float* weights_sum, float* depth, void* stream) {
+                                    uint32_t T, uint32_t T_dist, float density_scale, float* weights, float* weights_sum, float* depth,
+                                    void* stream) {
     if (N == 0 || T == 0) return 0;
-    k_uniform_fwd<<<ceil_div(N, 8u), 256, 0, as_stream(stream)>>>(sigmas, z_vals, nears, fars, N, T, density_scale, weights, weights_sum, depth);
+    if (T_dist == 0) T_dist = T;
+    k_uniform_fwd<<<ceil_div(N, 8u), 256, 0, as_stream(stream)>>>(sigmas, z_vals, nears, fars, N, T, T_dist, density_scale, weights, weights_sum, depth);
     ENERF_CHECK_LAUNCH("composite_uniform_forward");
     return 0;
 }
 
 int enerf_composite_uniform_backward(const float* grad_weights, const float* grad_weights_sum, const float* grad_depth,
                                      const float* sigmas, const float* z_vals, const float* nears, const float* fars, uint32_t N,
-                                     uint32_t T, float density_scale, float* grad_sigmas, void* stream) {
+                                     uint32_t T, uint32_t T_dist, float density_scale, float* grad_sigmas, void* stream) {
     if (N == 0 || T == 0) return 0;
+    if (T_dist == 0) T_dist = T;
     k_uniform_bwd<<<ceil_div(N, 8u), 256, 0, as_stream(stream)>>>(grad_weights, grad_weights_sum, grad_depth, sigmas, z_vals, nears, fars,
-                                                                 N, T, density_scale, grad_sigmas);
+                                                                 N, T, T_dist, density_scale, grad_sigmas);
     ENERF_CHECK_LAUNCH("composite_uniform_backward");
     return 0;
 }

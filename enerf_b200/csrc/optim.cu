@@ -4,7 +4,8 @@
 // update in registers (same operation order as torch's FusedAdamMathFunctor), 16-byte stores of p, m, v; the gradient is
 // un-scaled on the fly (grad_scale) and the whole step is skipped on the device when the scaler found an inf/nan
 // (found_inf), so nothing here synchronises with the host and the step can live inside a CUDA graph.
-// Purely HBM-bound: 28 bytes per parameter.
+// Purely HBM-bound: 28 bytes per parameter (+2 when the caller keeps an fp16 shadow of the parameter: the hash-grid kernels read
+// the table in fp16 under autocast, and writing that copy here replaces a separate 52 MB -> 26 MB cast per step).
 #include "common.cuh"
 
 namespace enerf {
@@ -24,8 +25,9 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 
 __global__ void __launch_bounds__(256)
 k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, uint64_t n,
-       const float* __restrict__ step, AdamArgs a, const float* __restrict__ grad_scale, const float* __restrict__ found_inf) {
-    if (found_inf && *found_inf != 0.f) return;                  // the scaler skips this step
+       const float* __restrict__ step, AdamArgs a, const float* __restrict__ grad_scale, const float* __restrict__ found_inf,
+       __half* __restrict__ shadow) {
+    if (found_inf && *found_inf != 0.f) return;                  // the scaler skips this step (the fp16 shadow stays valid: p is unchanged)
     const float t = *step;                                        // already incremented by the caller
     const float inv_scale = grad_scale ? 1.0f / *grad_scale : 1.0f;
     const float bc1 = 1.0f - powf(a.beta1, t), bc2 = 1.0f - powf(a.beta2, t);
@@ -42,6 +44,10 @@ k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m
         reinterpret_cast<float4*>(p)[i] = P;
         reinterpret_cast<float4*>(m)[i] = M;
         reinterpret_cast<float4*>(v)[i] = V;
+        if (shadow) {                                             // fp16 copy of the updated parameter (what the hash-grid kernels read)
+            const __half2 lo = __floats2half2_rn(P.x, P.y), hi = __floats2half2_rn(P.z, P.w);
+            reinterpret_cast<uint2*>(shadow)[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+        }
     }
     // tail (n not a multiple of 4)
     const uint64_t tail0 = n4 << 2;
@@ -49,6 +55,7 @@ k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m
     if (gid < n - tail0) {
         const uint64_t i = tail0 + gid;
         adam_one(p[i], g[i], m[i], v[i], a, inv_scale, step_size, bc2_sqrt);
+        if (shadow) shadow[i] = __float2half_rn(p[i]);
     }
 }
 
@@ -58,17 +65,19 @@ using namespace enerf;
 
 extern "C" int enerf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, uint64_t n, const float* step, float lr,
                                float beta1, float beta2, float eps, float weight_decay, const float* grad_scale, const float* found_inf,
-                               void* stream) {
+                               uint16_t* half_shadow, void* stream) {
     if (n == 0) return 0;
     ENERF_REQUIRE(step != nullptr, "adam_step", "step must be a device pointer to the (already incremented) step count");
     ENERF_REQUIRE(((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(exp_avg) |
                     reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15u) == 0, "adam_step", "tensors must be 16-byte aligned");
+    ENERF_REQUIRE((reinterpret_cast<uintptr_t>(half_shadow) & 7u) == 0, "adam_step", "half_shadow must be 8-byte aligned");
     const AdamArgs a = {lr, beta1, beta2, eps, weight_decay};
     const uint64_t n4 = n >> 2;
     uint64_t blocks = (n4 + 255) / 256;
-    if (blocks > (uint64_t)kNumSM * 16) blocks = (uint64_t)kNumSM * 16;
+    if (blocks > (uint64_t)num_sms() * 16) blocks = (uint64_t)num_sms() * 16;
     if (blocks == 0) blocks = 1;
-    k_adam<<<(uint32_t)blocks, 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, step, a, grad_scale, found_inf);
+    k_adam<<<(uint32_t)blocks, 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, step, a, grad_scale, found_inf,
+                                                                reinterpret_cast<__half*>(half_shadow));
     ENERF_CHECK_LAUNCH("adam_step");
     return 0;
 }

@@ -164,6 +164,23 @@ class EventPairSampler:
         mask = torch.zeros(E, dtype=torch.uint8, device=device)
         mask[torch.as_tensor(idx_no_successor).to(device=device, dtype=torch.long)] = 1
         self.no_succ = mask
+        # The kernel steps back one event where a pixel's last event was drawn and then draws among `num_successor` followers.
+        # The reference's provider guarantees the layout that makes this safe (pixels with a single event are dropped,
+        # provider.py:1164); arbitrary arrays are checked here, once, instead of reading out of bounds on the device.
+        if E < 2:
+            raise ValueError("EventPairSampler: a frame needs at least two events")
+        if self.num_succ.shape[0] != E:
+            raise ValueError("EventPairSampler: num_successor_evs must have one entry per event")
+        if bool(mask[0]):
+            raise ValueError("EventPairSampler: event 0 is marked as having no successor (it has no predecessor to fall back to)")
+        has_succ = mask == 0
+        idx = torch.arange(E, device=device)
+        if bool(((self.num_succ < 1) & has_succ).any()):
+            raise ValueError("EventPairSampler: an event that is not the last of its pixel must have num_successor_evs >= 1")
+        if bool(((idx + self.num_succ.long() >= E) & has_succ).any()):
+            raise ValueError("EventPairSampler: num_successor_evs points past the end of the frame")
+        if bool((mask[1:].bool() & mask[:-1].bool()).any()):
+            raise ValueError("EventPairSampler: two consecutive events without successor (a pixel with a single event)")
         self.acc_max = int(acc_max_num_evs or 0)
         self.poses_evs = None if poses_evs is None else torch.as_tensor(poses_evs, dtype=torch.float32).to(device).contiguous()
 

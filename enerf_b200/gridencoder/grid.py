@@ -10,7 +10,10 @@ initialisation (:133-135), `desired_resolution` overriding `per_level_scale` (:9
 Different underneath (B200-first):
   * the kernels read and write the [B, L*C] row layout directly, so the permute copy after the forward (grid.py:52) and the
     permute + contiguous before the backward (:70) do not exist;
-  * the fp16 copy of the table is cached per parameter version instead of being re-cast (25-50 MB) on every call;
+  * the fp16 copy of the table lives next to the parameter (`param._enerf_half`) instead of being re-cast (25-50 MB) on every
+    call: `enerf_b200.optim.FusedAdam` rewrites it inside the Adam kernel (its raw-pointer update does not touch the
+    parameter's version counter), every other writer (torch optimizers, `copy_`, `load_state_dict`, EMA swaps) bumps the
+    version and triggers a re-cast on the next forward;
   * embedding gradients are accumulated in fp32 and handed back in the parameter's dtype — the reference accumulates with
     fp16 atomics when the table is fp16 (gridencoder.cu:296-302); `ENERF_GRID_GRAD_FP16=1` reproduces that.
 """
@@ -25,16 +28,28 @@ from .backend import _backend
 
 _gridtype_to_id = {'hash': 0, 'tiled': 1}
 _ROW_LAYOUT = 1                      # out_layout of the C ABI: [B, L*C]
-_fp16_tables = {}                    # (data_ptr, numel, device) -> (parameter version, half copy)
+
+
+def half_shadow(param, create=False):
+    """The fp16 shadow slot `[tensor, version it mirrors]` of an fp32 table parameter, or None.  One slot per Parameter object
+    (two encoders never evict each other; a freed-and-reallocated parameter cannot alias it)."""
+    slot = getattr(param, "_enerf_half", None)
+    if slot is not None and (slot[0].shape != param.shape or slot[0].device != param.device):
+        slot = None                                        # the parameter moved (model.to(...)) or was resized
+    if slot is None and create:
+        slot = [torch.empty(param.shape, dtype=torch.half, device=param.device), -1]
+        param._enerf_half = slot
+    return slot
 
 
 def _half_table(param):
-    key = (param.data_ptr(), param.numel(), param.device)
-    cached = _fp16_tables.get(key)
-    if cached is None or cached[0] != param._version:
-        _fp16_tables.clear()         # a handful of encoders at most: never let stale 25 MB copies pile up
-        cached = _fp16_tables[key] = (param._version, param.detach().half())
-    return cached[1]
+    """fp16 view of the table for the kernels.  Valid while the parameter's version counter is the one the shadow was cast at;
+    `FusedAdam` keeps it current without bumping the version (its kernel writes parameter and shadow in one pass)."""
+    slot = half_shadow(param, create=True)
+    if slot[1] != param._version:
+        slot[0].copy_(param.detach())                      # in place: pointers captured in a CUDA graph stay valid
+        slot[1] = param._version
+    return slot[0]
 
 
 class _grid_encode(torch.autograd.Function):

@@ -122,7 +122,7 @@ class NeRFRenderer(nn.Module):
 
         if upsample_steps > 0:
             with torch.no_grad():
-                w0, _, _ = raymarching.composite_uniform(density_outputs['sigma'].squeeze(-1), z_vals, nears, fars, self.density_scale)
+                w0, _, _ = raymarching.composite_uniform(density_outputs['sigma'].squeeze(-1), z_vals, nears, fars, self.density_scale, num_steps)
                 deltas = z_vals[..., 1:] - z_vals[..., :-1]
                 z_mid = z_vals[..., :-1] + 0.5 * deltas
                 new_z = sample_pdf(z_mid, w0[:, 1:-1], upsample_steps, det=not self.training).detach()
@@ -139,7 +139,8 @@ class NeRFRenderer(nn.Module):
                 density_outputs[k] = torch.gather(both, dim=1, index=z_index.unsqueeze(-1).expand_as(both))
 
         # fused: deltas, alphas, transmittance scan, weights, weights_sum, depth
-        weights, weights_sum, depth = raymarching.composite_uniform(density_outputs['sigma'].squeeze(-1), z_vals, nears, fars, self.density_scale)
+        weights, weights_sum, depth = raymarching.composite_uniform(density_outputs['sigma'].squeeze(-1), z_vals, nears, fars, self.density_scale,
+                                                                    num_steps)
         mask = weights > 1e-4
 
         dirs = rays_d.view(-1, 1, 3).expand_as(xyzs)

@@ -5,6 +5,11 @@ Same update rule and state names (`step`, `exp_avg`, `exp_avg_sq`) as torch's Ad
 (28 bytes of HBM traffic per parameter), device-side step counters, and the GradScaler protocol of torch's fused optimizers
 (`_step_supports_amp_scaling`: `GradScaler.step` hands over `grad_scale` / `found_inf`, the kernel un-scales on the fly and
 skips the step on overflow), so a whole training iteration stays capturable in a CUDA graph.  CUDA fp32 parameters only.
+
+The update goes through the parameter's raw device pointer, so its autograd version counter does not move.  Consumers that
+cache derived data per version must be told another way: for a hash-grid table with an fp16 shadow
+(`enerf_b200.gridencoder.grid.half_shadow`) the kernel writes the shadow in the same pass, so the next forward reads the updated
+table without the 52 MB -> 26 MB cast of gridencoder/grid.py:38-39.
 """
 import torch
 
@@ -46,7 +51,10 @@ class FusedAdam(torch.optim.Optimizer):
                     st["step"] += 1.0 - found_inf.to(st["step"].device).reshape(())
                 else:
                     st["step"] += 1.0
+                shadow = getattr(p, "_enerf_half", None)
+                if shadow is not None and (shadow[0].shape != p.shape or shadow[0].device != p.device):
+                    shadow = None
                 _lib.call("enerf_adam_step", ptr(p), ptr(g), ptr(st["exp_avg"]), ptr(st["exp_avg_sq"]), p.numel(), ptr(st["step"]),
                           float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
-                          ptr(grad_scale), ptr(found_inf), stream())
+                          ptr(grad_scale), ptr(found_inf), ptr(shadow[0]) if shadow is not None else None, stream())
         return None

@@ -230,12 +230,14 @@ compact_rays = _compact_rays.apply
 # ---------------------------------------------------------------------------- fused run() integrator
 class _composite_uniform(Function):
     """Fixed-step integrator of NeRFRenderer.run (nerf/renderer.py:230-255) as one kernel:
-    (sigmas [N,T], z_vals [N,T], nears [N], fars [N], density_scale) -> weights [N,T],
-    weights_sum [N], depth [N].  Differentiable in sigmas.  No reference ABI (extension)."""
+    (sigmas [N,T], z_vals [N,T], nears [N], fars [N], density_scale, num_steps) -> weights [N,T],
+    weights_sum [N], depth [N].  Differentiable in sigmas.  No reference ABI (extension).
+    `num_steps` = the COARSE step count that defines the last sample's delta, (far-near)/num_steps
+    (renderer.py:177,231 keep it after PDF upsampling has made the rows longer); 0 = T."""
 
     @staticmethod
     @_fwd32
-    def forward(ctx, sigmas, z_vals, nears, fars, density_scale=1.0):
+    def forward(ctx, sigmas, z_vals, nears, fars, density_scale=1.0, num_steps=0):
         from .. import _lib
         sigmas, z_vals = sigmas.contiguous(), z_vals.contiguous()
         nears, fars = nears.contiguous().view(-1), fars.contiguous().view(-1)
@@ -245,10 +247,10 @@ class _composite_uniform(Function):
         weights_sum = torch.empty(N, dtype=sigmas.dtype, device=sigmas.device)
         depth = torch.empty(N, dtype=sigmas.dtype, device=sigmas.device)
         _lib.call("enerf_composite_uniform_forward", _lib.ptr(sigmas), _lib.ptr(z_vals), _lib.ptr(nears), _lib.ptr(fars), N, T,
-                                                              float(density_scale), _lib.ptr(weights), _lib.ptr(weights_sum),
+                                                              int(num_steps), float(density_scale), _lib.ptr(weights), _lib.ptr(weights_sum),
                                                               _lib.ptr(depth), _lib.stream())
         ctx.save_for_backward(sigmas, z_vals, nears, fars)
-        ctx.density_scale = float(density_scale)
+        ctx.density_scale, ctx.num_steps = float(density_scale), int(num_steps)
         return weights, weights_sum, depth
 
     @staticmethod
@@ -262,9 +264,9 @@ class _composite_uniform(Function):
         gd = None if grad_depth is None else grad_depth.contiguous().float()
         grad_sigmas = torch.empty_like(sigmas)
         _lib.call("enerf_composite_uniform_backward", _lib.ptr(gw), _lib.ptr(gs), _lib.ptr(gd), _lib.ptr(sigmas), _lib.ptr(z_vals),
-                                                               _lib.ptr(nears), _lib.ptr(fars), N, T, ctx.density_scale,
+                                                               _lib.ptr(nears), _lib.ptr(fars), N, T, ctx.num_steps, ctx.density_scale,
                                                                _lib.ptr(grad_sigmas), _lib.stream())
-        return grad_sigmas, None, None, None, None
+        return grad_sigmas, None, None, None, None, None
 
 
 composite_uniform = _composite_uniform.apply

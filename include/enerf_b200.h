@@ -129,9 +129,8 @@ int enerf_grid_set_backward_mode(int mode);
  * resident tcgen05 MLP CTA (53 K registers) when the two kernels run concurrently on two streams. */
 int enerf_grid_set_backward_block(int threads);
 /* Forward kernel selector (tests), D = 3 without input gradients: 1 (default) = a warp walks all levels of its
- * 32 samples (persistent CTAs), 2 = one warp per (32 samples, level), 0 = always the generic kernel,
- * 3 = mode 1 with the two x-neighbour corners fetched by one 8-byte load where they share an aligned
- * block (fp16 tables with 2 features; experimental, not yet measured).  Bit-identical outputs. */
+ * 32 samples (persistent CTAs), 2 = one warp per (32 samples, level), 0 = always the generic kernel.
+ * Bit-identical outputs. */
 int enerf_grid_set_forward_mode(int mode);
 
 /* -------------------------------------------------------------------- shencoder ---- */
@@ -221,20 +220,23 @@ int enerf_field_sigma_backward(const float* grad_sigma, const float* sigma, cons
 
 /* Fixed-step integrator of NeRFRenderer.run (nerf/renderer.py:230-255), which the reference
  * evaluates as ~25 ATen kernels over [N,T] temporaries.  One warp per ray:
- *   delta_i = z_{i+1}-z_i, last = (far-near)/T           (renderer.py:230-231)
+ *   delta_i = z_{i+1}-z_i, last = (far-near)/T_dist      (renderer.py:177,230-231; T_dist = the COARSE step
+ *             count `num_steps`, which the reference keeps for the last delta even when upsampling has made
+ *             the rows T = num_steps + upsample_steps long; 0 = T)
  *   alpha_i = 1-exp(-delta_i*density_scale*sigma_i)      (renderer.py:232)
  *   w_i = alpha_i * prod_{j<i}(1-alpha_j+1e-15)          (renderer.py:233-234)
  *   weights_sum = sum w, depth = sum w*clamp((z-near)/(far-near),0,1)   (renderer.py:248-252)
  * sigmas, z_vals, weights: [N,T]; nears, fars, weights_sum, depth: [N]. */
 int enerf_composite_uniform_forward(const float* sigmas, const float* z_vals, const float* nears,
-                                    const float* fars, uint32_t N, uint32_t T, float density_scale,
-                                    float* weights, float* weights_sum, float* depth, void* stream);
+                                    const float* fars, uint32_t N, uint32_t T, uint32_t T_dist,
+                                    float density_scale, float* weights, float* weights_sum,
+                                    float* depth, void* stream);
 /* d(loss)/d(sigmas) given d(loss)/d(weights) [N,T], d/d(weights_sum) [N], d/d(depth) [N]
  * (each may be NULL = zero). */
 int enerf_composite_uniform_backward(const float* grad_weights, const float* grad_weights_sum,
                                      const float* grad_depth, const float* sigmas,
                                      const float* z_vals, const float* nears, const float* fars,
-                                     uint32_t N, uint32_t T, float density_scale,
+                                     uint32_t N, uint32_t T, uint32_t T_dist, float density_scale,
                                      float* grad_sigmas, void* stream);
 
 /* ------------------------------------------ next rows of the path ---- */
@@ -271,10 +273,12 @@ int enerf_event_loss_backward(const float* img1, const float* img2, const float*
 /* N4 — the optimizer step that follows every backward of the path: torch.optim.Adam as configured by main_nerf.py:211-214
  * (amsgrad off, maximize off), fused into one pass per tensor.  `step`: device pointer to the step count of this parameter,
  * ALREADY incremented for this step; grad_scale / found_inf: the GradScaler's device scalars (NULL = 1 / 0): gradients are
- * divided by *grad_scale on the fly and the call is a no-op when *found_inf != 0.  fp32 tensors, 16-byte aligned. */
+ * divided by *grad_scale on the fly and the call is a no-op when *found_inf != 0.  fp32 tensors, 16-byte aligned.
+ * half_shadow (may be NULL): fp16 [n] copy of the UPDATED parameter written in the same pass — gridencoder/grid.py:38-39
+ * re-casts the whole table to half on every forward under autocast; with the shadow that 52 MB -> 26 MB pass disappears. */
 int enerf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, uint64_t n, const float* step,
                     float lr, float beta1, float beta2, float eps, float weight_decay, const float* grad_scale,
-                    const float* found_inf, void* stream);
+                    const float* found_inf, uint16_t* half_shadow, void* stream);
 /* N3 — event-pair sampler, nerf/provider.py:1364-1405 (collate, accumulate_evs branch).  events [E,4] fp32 = (x, y, t, polarity),
  * grouped by pixel as the provider stores them; pol_prefix [E+1] double = exclusive prefix sum of the polarity column;
  * num_successors [E] (provider.py:1181-1187), no_successor [E] = 1 for the last event of a pixel (:1177-1178); u_start, u_end [M]

@@ -92,9 +92,7 @@ def test_grid_forward_hoisted_kernel_is_bit_identical_to_generic(dtype):
     """The two hot-path kernels — k_grid_fwd_w (mode 1: a warp walks all levels of its 32 samples) and k_grid_fwd3 (mode 2: one warp per
     (32 samples, level)) — vs the generic k_grid_fwd (mode 0), and all vs the reference build when it is available."""
     from enerf_b200 import _lib
-    # mode 3 (mode 1 with paired 8-byte loads) was written after the round's GPU budget was spent: not the default, and checked
-    # here only on request until it has had its first run on a GPU (ENERF_TEST_EXPERIMENTAL=1)
-    MODES = (1, 2, 3) if os.environ.get("ENERF_TEST_EXPERIMENTAL", "0") == "1" else (1, 2)
+    MODES = (1, 2)
     R = ref_mod("_gridencoder")
     rng = np.random.default_rng(12)
     for bound, C, L, gridtype, log2T in [(3, 2, 16, 0, 19), (1, 2, 16, 0, 19), (2, 2, 16, 1, 19), (1, 4, 8, 0, 14), (2, 1, 16, 0, 12), (1, 8, 4, 1, 9)]:

@@ -81,15 +81,6 @@ def main():
             med, mn = timeit(lambda: GB.grid_encode_forward(x01, emb, enc.offsets, out, S, 3, 2, 16, Sx, 16, False, dummy, 0, 1), args.iters, flush)
             nbytes = (12 + 16 * 8 * 2 * emb.element_size() + 32 * emb.element_size()) * S
             res[f"grid_fwd_{str(dt)[6:]}"] = {"ms": med, "min_ms": mn, "GBps": nbytes / med / 1e6, "frac": nbytes / med / 1e6 / peak}
-            if dt == torch.float16:        # experimental variant: x-neighbour corners fetched by one 8-byte load where they share a block
-                ref_out = out.clone()
-                _lib.call("enerf_grid_set_forward_mode", 3)
-                try:
-                    med, mn = timeit(lambda: GB.grid_encode_forward(x01, emb, enc.offsets, out, S, 3, 2, 16, Sx, 16, False, dummy, 0, 1), args.iters, flush)
-                    res["grid_fwd_float16_paired_loads"] = {"ms": med, "min_ms": mn, "frac": nbytes / med / 1e6 / peak,
-                                                            "bit_identical_to_default": bool(torch.equal(out, ref_out))}
-                finally:
-                    _lib.call("enerf_grid_set_forward_mode", 1)
             grad = torch.randn(S, 32, device=dev).to(dt)
             for gdt in ((torch.float32, torch.float16) if dt == torch.float16 else (torch.float32,)):
                 for mode in (1, 0):
