@@ -46,6 +46,20 @@ _SIGS = {
     "enerf_field_color_forward": [_p, _p, _u32, _u32, _u32, _p, _p, _p],
     "enerf_field_color_backward": [_p, _p, _u32, _p, _p, _p, _u32, _u32, _p, _p, _p],
     "enerf_field_sigma_backward": [_p, _p, _p, _p, _p, _p, _u32, _u32, _p, _p, _p],
+    "enerf_field_density_forward": [_p, _p, _u32, _u32, _p, _p, _p],
+    "enerf_field_density_backward": [_p, _p, _p, _p, _p, _u32, _u32, _p, _p, _p],
+    "enerf_field_color_inputs": [_p, _u32, _p, _p, _u32, _u32, _f32, _p, _p],
+    "enerf_field_color_inputs_backward": [_p, _p, _u32, _p, _p],
+    "enerf_compact_greater": [_p, _f32, _u32, _p, _p, _p, _p],
+    "enerf_compact_mask": [_p, _u32, _p, _p, _p, _p],
+    "enerf_gather_rows": [_p, _p, _u32, _u32, _u32, _p, _p],
+    "enerf_scatter_rows": [_p, _p, _u32, _u32, _p, _p],
+    "enerf_weighted_sum_forward": [_p, _p, _u32, _u32, _u32, _p, _p],
+    "enerf_weighted_sum_backward": [_p, _p, _p, _u32, _u32, _u32, _p, _p, _p],
+    "enerf_occ_points_full": [_p, _u32, _u32, _f32, _p, _u64, _p],
+    "enerf_occ_points_partial": [_p, _p, _u32, _u32, _u32, _f32, _p, _p, _p, _p, _p, _u64, _p],
+    "enerf_occ_update": [_p, _p, _p, _u32, _u32, _u32, _f32, _f32, _f32, _p, _p, _p, _p, _p],
+    "enerf_mark_untrained_grid": [_p, _p, _u32, _f32, _f32, _f32, _f32, _u32, _u32, _f32, _p],
     "enerf_composite_uniform_forward": [_p, _p, _p, _p, _u32, _u32, _u32, _f32, _p, _p, _p, _p],
     "enerf_composite_uniform_backward": [_p, _p, _p, _p, _p, _p, _p, _u32, _u32, _u32, _f32, _p, _p],
     "enerf_get_rays": [_p, _f32, _f32, _f32, _f32, _u32, _u32, _p, _u32, _u32, _u32, _p, _f32, _p, _p, _p, _p, _p],

@@ -358,16 +358,21 @@ int tc_forward_sigma_head(const __half* feat, const __half* W, uint32_t B, int n
 int tc_forward_rgb_head(const __half* cin, const __half* W, uint32_t B, int n_hidden_mm, __half* fwd_buf, float* rgb, int n_ch, cudaStream_t st);
 int tc_backward_rgb(const float* g_rgb, const float* rgb, int n_ch, const __half* cin, const __half* W, const __half* fwd_buf, __half* dcin, float* dW,
                     uint32_t B, int n_hidden_mm, cudaStream_t st);
-void tc_set_bwd_tma(int on);
-void tc_set_fwd_tma(int on);
 void tc_set_max_ctas(int n);
+int tc_forward_density(const __half* feat, const __half* W, uint32_t B, int n_hidden_mm, float* sigma, __half* h, cudaStream_t st);
+int tc_backward_density(const float* g_sigma, const float* sigma, const __half* g_h, const __half* feat, const __half* W, __half* dfeat, float* dW,
+                        uint32_t B, int n_hidden_mm, cudaStream_t st);
+int tc_color_inputs(const float* dirs, uint32_t dir_div, const __half* h, const int32_t* idx, uint32_t n, uint32_t n_pad, float sh_scale, __half* cin,
+                    cudaStream_t st);
+int tc_color_inputs_backward(const __half* dcin, const int32_t* idx, uint32_t n, __half* g_h, cudaStream_t st);
 int tc_backward_sigma(const float* g_sigma, const float* sigma, const __half* dcin, const __half* feat, const __half* W, const __half* fwd_buf,
                       __half* dfeat, float* dW, uint32_t B, int n_hidden_mm, cudaStream_t st);
 }
 static int g_mlp_path = 0;   // 0: tcgen05 kernels when eligible, 1: always the generic mma.sync kernels
+// the tcgen05 kernels cover E-NeRF's own networks: 32 inputs, 64 wide, ReLU, 2 or 3 layers (3 or 4 matmuls)
 static bool tc_eligible(uint32_t input_dim, uint32_t hidden_dim, uint32_t num_layers, uint32_t activation, uint32_t output_activation) {
-    return g_mlp_path == 0 && hidden_dim == 64 && input_dim <= 64 && activation == ENERF_ACT_RELU && output_activation == ENERF_ACT_NONE &&
-           num_layers <= 8;
+    return g_mlp_path == 0 && hidden_dim == 64 && input_dim == 32 && activation == ENERF_ACT_RELU && output_activation == ENERF_ACT_NONE &&
+           num_layers >= 2 && num_layers <= 3;
 }
 }  // namespace enerf
 
@@ -414,7 +419,7 @@ int enerf_ffmlp_backward(const uint16_t* grad, const uint16_t* inputs, const uin
     if (int rc = check_dims("ffmlp_backward", B, input_dim, output_dim, hidden_dim, num_layers)) return rc;
     ENERF_REQUIRE(grad_weights_dtype == ENERF_F32 || grad_weights_dtype == ENERF_F16, "ffmlp_backward", "bad grad_weights_dtype");
     ENERF_REQUIRE(scratch != nullptr, "ffmlp_backward", "scratch must not be NULL");
-    const bool use_tc = tc_eligible(input_dim, hidden_dim, num_layers, activation, ENERF_ACT_NONE) && num_layers <= 4;
+    const bool use_tc = tc_eligible(input_dim, hidden_dim, num_layers, activation, ENERF_ACT_NONE);
     ENERF_REQUIRE(use_tc || backward_buffer != nullptr, "ffmlp_backward", "the mma.sync path needs backward_buffer");
     ENERF_REQUIRE(use_tc || forward_buffer != nullptr, "ffmlp_backward", "the mma.sync path needs forward_buffer (recomputation exists on the tcgen05 path only)");
     cudaStream_t st = as_stream(stream);
@@ -464,7 +469,7 @@ int enerf_ffmlp_backward(const uint16_t* grad, const uint16_t* inputs, const uin
 // ---- fused E-NeRF field heads (64-wide ReLU networks, 32 inputs) on the tcgen05 kernels ------------------
 static int field_check(const char* name, uint32_t B, uint32_t num_layers) {
     ENERF_REQUIRE(B % 128 == 0, name, "batch size must be a multiple of 128");
-    ENERF_REQUIRE(num_layers >= 2 && num_layers <= 4, name, "num_layers must be in [2,4]");
+    ENERF_REQUIRE(num_layers >= 2 && num_layers <= 3, name, "num_layers must be 2 or 3");
     return 0;
 }
 
@@ -508,15 +513,44 @@ int enerf_field_sigma_backward(const float* grad_sigma, const float* sigma, cons
                                   (const __half*)forward_buffer, (__half*)grad_feat, grad_weights, B, (int)num_layers - 1, as_stream(stream));
 }
 
+// ---- torch-topology field (nerf/network.py): density head and masked colour inputs -------------------------------
+int enerf_field_density_forward(const uint16_t* feat, const uint16_t* weights, uint32_t B, uint32_t num_layers, float* sigma, uint16_t* h,
+                                void* stream) {
+    ENERF_REQUIRE(B % 128 == 0, "field_density_forward", "batch size must be a multiple of 128");
+    ENERF_REQUIRE(num_layers >= 1 && num_layers <= 2, "field_density_forward", "num_layers must be 1 (nerf/network.py) or 2 (nerf/network_ff.py)");
+    ENERF_REQUIRE(sigma != nullptr, "field_density_forward", "sigma must not be NULL");
+    if (B == 0) return 0;
+    return tcm::tc_forward_density((const __half*)feat, (const __half*)weights, B, (int)num_layers - 1, sigma, (__half*)h, as_stream(stream));
+}
+
+int enerf_field_density_backward(const float* grad_sigma, const float* sigma, const uint16_t* grad_h, const uint16_t* feat, const uint16_t* weights,
+                                 uint32_t B, uint32_t num_layers, uint16_t* grad_feat, float* grad_weights, void* stream) {
+    ENERF_REQUIRE(B % 128 == 0, "field_density_backward", "batch size must be a multiple of 128");
+    ENERF_REQUIRE(num_layers >= 1 && num_layers <= 2, "field_density_backward", "num_layers must be 1 or 2");
+    const size_t n_w = (size_t)64 * (32 + (size_t)64 * (num_layers - 1) + 16);
+    ENERF_CUDA(cudaMemsetAsync(grad_weights, 0, n_w * sizeof(float), as_stream(stream)), "field_density_backward");
+    if (B == 0) return 0;
+    return tcm::tc_backward_density(grad_sigma, sigma, (const __half*)grad_h, (const __half*)feat, (const __half*)weights, (__half*)grad_feat,
+                                    grad_weights, B, (int)num_layers - 1, as_stream(stream));
+}
+
+int enerf_field_color_inputs(const float* dirs, uint32_t dir_div, const uint16_t* h, const int32_t* idx, uint32_t n, uint32_t n_pad, float sh_scale,
+                             uint16_t* cin, void* stream) {
+    ENERF_REQUIRE(dir_div >= 1 && n_pad >= n && n_pad % 128 == 0, "field_color_inputs", "dir_div >= 1, n_pad >= n, n_pad a multiple of 128");
+    return tcm::tc_color_inputs(dirs, dir_div, (const __half*)h, idx, n, n_pad, sh_scale, (__half*)cin, as_stream(stream));
+}
+
+int enerf_field_color_inputs_backward(const uint16_t* grad_cin, const int32_t* idx, uint32_t n, uint16_t* grad_h, void* stream) {
+    return tcm::tc_color_inputs_backward((const __half*)grad_cin, idx, n, (__half*)grad_h, as_stream(stream));
+}
+
 int enerf_ffmlp_uses_tcgen05(uint32_t input_dim, uint32_t hidden_dim, uint32_t num_layers, uint32_t activation, uint32_t output_activation) {
-    return (tc_eligible(input_dim, hidden_dim, num_layers, activation, output_activation) && num_layers <= 4) ? 1 : 0;
+    return tc_eligible(input_dim, hidden_dim, num_layers, activation, output_activation) ? 1 : 0;
 }
 
 int enerf_ffmlp_set_path(int path) {
-    ENERF_REQUIRE(path >= 0 && path <= 2, "ffmlp_set_path", "path must be 0 (auto), 1 (generic mma.sync kernels) or 2 (tcgen05 without TMA operand loads)");
-    g_mlp_path = (path == 1) ? 1 : 0;
-    tcm::tc_set_bwd_tma(path != 2);
-    tcm::tc_set_fwd_tma(path != 2);
+    ENERF_REQUIRE(path == 0 || path == 1, "ffmlp_set_path", "path must be 0 (auto) or 1 (generic mma.sync kernels)");
+    g_mlp_path = path;
     return 0;
 }
 

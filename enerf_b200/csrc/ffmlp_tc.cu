@@ -1,21 +1,17 @@
 // Fully-fused 64-wide MLP on the 5th-generation tensor cores (tcgen05) with TMEM-resident
-// activations — the path E-NeRF's networks (sigma-net 32-64-64-16, colour-net 32-64-64-64-16)
-// take.  Other shapes use the mma.sync kernels in ffmlp.cu.
+// activations — the path E-NeRF's networks take: FFMLP sigma-net 32-64-64-16 and colour-net
+// 32-64-64-64-16 (nerf/network_ff.py:31-49) and the torch-topology nets 32-64-16 and
+// 31(+1)-64-64-C (nerf/network.py:40-77).  Other shapes use the mma.sync kernels in ffmlp.cu.
 //
-// Forward / inference (k_tc_fwd)
-//   CTA = 1 MMA warp + NSLOTS x 4 epilogue warps, persistent over 128-sample tiles; NSLOTS tiles
-//   are in flight per CTA so the tensor pipe works on one tile while the epilogue warps of the
-//   other(s) run.  Per tile:
-//     epilogue warps: global row (fp16) -> registers -> tcgen05.st -> A operand in TMEM
-//     MMA thread    : tcgen05.mma  D[128 x 64] (TMEM, fp32) = A[TMEM] x W_k^T [smem, K-major]
-//     epilogue warps: tcgen05.ld D -> ReLU -> fp16 pack -> tcgen05.st (next layer's A, never
-//                     leaves the SM) [+ 128-B row store to forward_buffer when training]
-//     ... last layer N = 16 -> fp16 row store of the 16 outputs.
-//   Weights are staged once per CTA in shared memory in the no-swizzle canonical layout
-//   (tc_common.cuh); hand-offs use mbarriers (128 arrivals: "A ready"; tcgen05.commit: "D full").
+// All kernels: CTA = 1 issuing warp + NSLOTS x 4 epilogue warps, persistent over 128-sample
+// tiles; NSLOTS tiles are in flight per CTA so the tensor pipe works on one tile while the
+// epilogue warps of the others run.  Operand tiles arrive by TMA (cp.async.bulk.tensor) in the
+// hardware swizzle; weights are staged once per CTA in shared memory in the no-swizzle canonical
+// layout (tc_common.cuh); accumulators are fp32 in TMEM; between layers the activation goes
+// tcgen05.ld -> ReLU -> fp16 -> tcgen05.st and never leaves the SM; hand-offs use mbarriers
+// (one arrival per epilogue warp: "A ready"; tcgen05.commit: "D full").
 #include "tc_common.cuh"
 #include <cuda.h>
-#include <stdlib.h>
 
 namespace enerf {
 namespace tcm {
@@ -94,6 +90,8 @@ __device__ __forceinline__ void stage_matrix(uint8_t* dst, const __half* __restr
 //   HEAD 1 (sigma-net): h = fp16(y); sigma = exp(h[0]) (fp32, `trunc_exp`); the colour-net input row
 //           [SH_4(dir) (16) | h[1:16] (15) | 0] is written directly (no SH kernel, no cat, no zeros_like)
 //   HEAD 2 (colour-net): rgb[c] = sigmoid(fp16(y[c])) for c < n_ch, written as fp32 [B, n_ch]
+//   HEAD 3 (density only): sigma = exp(fp16(y[0])) and nothing else — the occupancy-grid refresh (nerf/renderer.py:510)
+//   HEAD 4 (density + features, nerf/network.py:134-151): sigma as above plus the 16 raw outputs h (fp16 rows; geo_feat = h[1:16])
 struct HeadArgs {
     const float* dirs;   // [B,3] fp32                    (HEAD 1)
     float* sigma;        // [B] fp32                      (HEAD 1)
@@ -124,215 +122,8 @@ __device__ __forceinline__ void sh_deg4(float x, float y, float z, float (&o)[16
 }
 __device__ __forceinline__ float f16_round(float v) { return __half2float(__float2half_rn(v)); }
 
-template <int NSLOTS, int IN_DIM, int HEAD>
-__global__ void __launch_bounds__(32 + NSLOTS * 128, 1)
-k_tc_fwd(const __half* __restrict__ in, const __half* __restrict__ W, __half* __restrict__ fwd_buf, __half* __restrict__ out,
-         uint32_t n_tiles, uint32_t B, int n_hidden_mm, HeadArgs head) {
-    constexpr int in_dim = IN_DIM;
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* w0s = smem;                                  // [in_dim/8][64][16 B]
-    uint8_t* whs = w0s + in_dim * 128;                    // n_hidden_mm x [8][64][16 B]
-    uint8_t* wls = whs + n_hidden_mm * 8192;              // [8][16][16 B]
-    uint8_t* stage_base = wls + 2048;                     // 4 KB per epilogue warp (row <-> coalesced transposition)
-    uint64_t* a_ready = reinterpret_cast<uint64_t*>(stage_base + (size_t)NSLOTS * 4 * 4096);
-    uint64_t* d_full = a_ready + NSLOTS;
-    uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(d_full + NSLOTS);
-
-    const int tid = threadIdx.x, nthreads = blockDim.x;
-    const int warp = tid >> 5, lane = tid & 31;
-    constexpr uint32_t kCols = (NSLOTS * kSlotCols <= 256) ? 256 : 512;
-
-    stage_matrix(w0s, W, kW, in_dim, tid, nthreads);
-    for (int j = 0; j < n_hidden_mm; ++j) stage_matrix(whs + j * 8192, W + kW * in_dim + j * kW * kW, kW, kW, tid, nthreads);
-    stage_matrix(wls, W + kW * in_dim + n_hidden_mm * kW * kW, 16, kW, tid, nthreads);
-    if (tid == 0) {
-        for (int s = 0; s < NSLOTS; ++s) {
-            mbar_init(&a_ready[s], 128);
-            mbar_init(&d_full[s], 1);
-        }
-        mbar_fence_init();
-    }
-    if (warp == 0) tmem_alloc(tmem_base_ptr, kCols);
-    fence_proxy_async_smem();      // weights written with st.shared are read by the tensor core
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem0 = *tmem_base_ptr;
-
-    const int S = n_hidden_mm + 2;                                     // matmuls per network
-    const uint32_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-
-    if (warp == 0) {
-        // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
-        {
-            // Serve whichever slot has its A operand ready (no fixed slot order: a slow epilogue must not
-            // stall the other tiles in flight).
-            uint32_t pa[NSLOTS], stage[NSLOTS], left[NSLOTS];
-            uint32_t remaining = 0;
-#pragma unroll
-            for (int s = 0; s < NSLOTS; ++s) {
-                pa[s] = 0;
-                stage[s] = 0;
-                left[s] = (my_tiles > (uint32_t)s) ? (my_tiles - s + NSLOTS - 1) / NSLOTS : 0;   // tiles this slot will process
-                remaining += left[s] * S;
-            }
-            const uint32_t tm = __shfl_sync(0xffffffffu, tmem0, 0);
-            const uint32_t idesc64 = idesc_f16(kTile, 64, false, false), idesc16 = idesc_f16(kTile, 16, false, false);
-            const uint32_t w0b = smem_u32(w0s), whb = smem_u32(whs), wlb = smem_u32(wls);
-            while (remaining > 0) {
-#pragma unroll
-                for (int s = 0; s < NSLOTS; ++s) {
-                    if (left[s] == 0) continue;
-                    if (!__all_sync(0xffffffffu, mbar_test(&a_ready[s], pa[s]))) continue;
-                    pa[s] ^= 1;
-                    tc_fence_after();
-                    const int i = (int)stage[s];
-                    const bool last = (i == S - 1);
-                    const uint32_t d_t = tm + s * kSlotCols, a_t = d_t + 64;
-                    if (elect_one()) {
-                        if (i == 0) {
-#pragma unroll
-                            for (int k = 0; k < in_dim / 16; ++k) mma_ts(d_t, a_t + k * 8, smem_desc(w0b + k * 2 * (kW * 16), kW * 16, 128), idesc64, k > 0);
-                        } else if (!last) {
-                            const uint32_t wb = whb + (uint32_t)(i - 1) * 8192u;
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) mma_ts(d_t, a_t + k * 8, smem_desc(wb + k * 2 * (kW * 16), kW * 16, 128), idesc64, k > 0);
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) mma_ts(d_t, a_t + k * 8, smem_desc(wlb + k * 2 * (16 * 16), 16 * 16, 128), idesc16, k > 0);
-                        }
-                        tc_commit(&d_full[s]);
-                    }
-                    __syncwarp();
-                    --remaining;
-                    if (++stage[s] == (uint32_t)S) {
-                        stage[s] = 0;
-                        --left[s];
-                    }
-                }
-            }
-        }
-    } else {
-        // ===================== epilogue warps =====================
-        // Every global access of a warp is a fully coalesced 512-byte request: the warp's 32 rows are
-        // moved between "coalesced" and "row per lane" form through a swizzled, warp-private staging tile.
-        const int s = (warp - 1) >> 2;                 // slot
-        const int q = warp & 3;                        // TMEM quarter this warp may access
-        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-        const uint32_t d_t = tmem0 + lane_sel + s * kSlotCols, a_t = d_t + 64;
-        uint8_t* stg = stage_base + (size_t)(warp - 1) * 4096;
-        constexpr int NVI = IN_DIM / 8;                // 16-byte chunks per input row
-        constexpr bool kCoalIn = (NVI == 2 || NVI == 4 || NVI == 8);
-        uint32_t pd = 0;
-        // the input rows of the NEXT tile are fetched while the current tile's layers run
-        int4 xco[NVI];
-        auto fetch_input = [&](uint32_t jj) {
-            const size_t wrow0 = ((size_t)blockIdx.x + (size_t)jj * gridDim.x) * kTile + q * 32;     // first row of this warp
-            if (kCoalIn) {
-                const int4* g = reinterpret_cast<const int4*>(in + wrow0 * in_dim);
-#pragma unroll
-                for (int i = 0; i < NVI; ++i) xco[i] = __ldg(g + i * 32 + lane);
-            } else {
-                const int4* g = reinterpret_cast<const int4*>(in + (wrow0 + lane) * in_dim);
-#pragma unroll
-                for (int c = 0; c < NVI; ++c) xco[c] = __ldg(g + c);
-            }
-        };
-        if ((uint32_t)s < my_tiles) fetch_input(s);
-        for (uint32_t j = s; j < my_tiles; j += NSLOTS) {
-            const size_t tile = (size_t)blockIdx.x + (size_t)j * gridDim.x;
-            const size_t wrow0 = tile * kTile + q * 32;
-            const size_t row = wrow0 + lane;
-            // ---- input row -> TMEM A
-            {
-                int4 xin[NVI];
-                if (kCoalIn) {
-                    if constexpr (kCoalIn) coalesced_to_rows<NVI>(xco, xin, stg, lane);
-                } else {
-#pragma unroll
-                    for (int c = 0; c < NVI; ++c) xin[c] = xco[c];
-                }
-#pragma unroll
-                for (int c = 0; c < IN_DIM / 16; ++c) {            // 16 halves = 8 TMEM columns per step
-                    const int4 v0 = xin[2 * c], v1 = xin[2 * c + 1];
-                    const uint32_t r[8] = {(uint32_t)v0.x, (uint32_t)v0.y, (uint32_t)v0.z, (uint32_t)v0.w,
-                                           (uint32_t)v1.x, (uint32_t)v1.y, (uint32_t)v1.z, (uint32_t)v1.w};
-                    tmem_st8(a_t + c * 8, r);
-                }
-                tc_wait_st();
-                tc_fence_before();
-                mbar_arrive(&a_ready[s]);
-                if (j + NSLOTS < my_tiles) fetch_input(j + NSLOTS);
-            }
-            for (int i = 0; i < S; ++i) {
-                mbar_wait(&d_full[s], pd);
-                pd ^= 1;
-                tc_fence_after();
-                if (i < S - 1) {
-                    int4 hrow[8];                                  // this lane's 64 fp16 activations
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        uint32_t acc[32];
-                        tmem_ld32(d_t + h * 32, acc);
-                        tc_wait_ld();
-                        uint32_t p[16];
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) p[e] = pack2(relu(__uint_as_float(acc[2 * e])), relu(__uint_as_float(acc[2 * e + 1])));
-                        tmem_st16(a_t + h * 16, p);
-#pragma unroll
-                        for (int v = 0; v < 4; ++v) hrow[h * 4 + v] = make_int4((int)p[4 * v], (int)p[4 * v + 1], (int)p[4 * v + 2], (int)p[4 * v + 3]);
-                    }
-                    tc_wait_st();
-                    tc_fence_before();
-                    mbar_arrive(&a_ready[s]);
-                    // the forward_buffer rows leave after the hand-off, off the critical path of the next MMA
-                    if (fwd_buf) store_rows<8>(reinterpret_cast<int4*>(fwd_buf + ((size_t)i * B + wrow0) * kW), hrow, stg, lane);
-                } else {
-                    uint32_t acc[16];
-                    tmem_ld16(d_t, acc);
-                    tc_wait_ld();
-                    if (HEAD == 0) {
-                        int4 orow[2];
-                        orow[0] = make_int4((int)pack2(__uint_as_float(acc[0]), __uint_as_float(acc[1])), (int)pack2(__uint_as_float(acc[2]), __uint_as_float(acc[3])),
-                                            (int)pack2(__uint_as_float(acc[4]), __uint_as_float(acc[5])), (int)pack2(__uint_as_float(acc[6]), __uint_as_float(acc[7])));
-                        orow[1] = make_int4((int)pack2(__uint_as_float(acc[8]), __uint_as_float(acc[9])), (int)pack2(__uint_as_float(acc[10]), __uint_as_float(acc[11])),
-                                            (int)pack2(__uint_as_float(acc[12]), __uint_as_float(acc[13])), (int)pack2(__uint_as_float(acc[14]), __uint_as_float(acc[15])));
-                        store_rows<2>(reinterpret_cast<int4*>(out + wrow0 * 16), orow, stg, lane);
-                    } else if (HEAD == 1) {
-                        head.sigma[row] = expf(f16_round(__uint_as_float(acc[0])));
-                        // directions reach the SH encoder as fp16 under autocast (sphere_harmonics.py:16)
-                        const float dx = f16_round(head.dirs[row * 3]), dy = f16_round(head.dirs[row * 3 + 1]), dz = f16_round(head.dirs[row * 3 + 2]);
-                        float sh[16];
-                        sh_deg4(dx, dy, dz, sh);
-                        uint32_t p[16];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) p[e] = pack2(sh[2 * e], sh[2 * e + 1]);
-#pragma unroll
-                        for (int e = 0; e < 7; ++e) p[8 + e] = pack2(__uint_as_float(acc[1 + 2 * e]), __uint_as_float(acc[2 + 2 * e]));
-                        p[15] = pack2(__uint_as_float(acc[15]), 0.0f);
-                        int4 crow[4];
-#pragma unroll
-                        for (int v = 0; v < 4; ++v) crow[v] = make_int4((int)p[4 * v], (int)p[4 * v + 1], (int)p[4 * v + 2], (int)p[4 * v + 3]);
-                        store_rows<4>(reinterpret_cast<int4*>(head.cin + wrow0 * 32), crow, stg, lane);
-                    } else {
-                        for (int c = 0; c < head.n_ch; ++c) {
-                            const float y = f16_round(__uint_as_float(acc[c]));
-                            head.rgb[row * head.n_ch + c] = f16_round(1.0f / (1.0f + expf(-y)));
-                        }
-                    }
-                    tc_fence_before();
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem0, kCols);
-}
-
 // ================================================================================================
-// Forward / inference, TMA variant (k_tc_fwd_tma): the E-NeRF shapes (32 or 64 inputs, 1 or 2 hidden-to-hidden
-// matmuls).  Differences to k_tc_fwd:
+// Forward / inference (k_tc_fwd_tma): 32 or 64 inputs, 0, 1 or 2 hidden-to-hidden matmuls.
 //   * the [128 x in_dim] input tile arrives by cp.async.bulk.tensor (two-deep ring per slot) in the TMA swizzle and
 //     is the layer-0 A operand straight from shared memory (K-major swizzled descriptor) — no per-thread loads,
 //     no row transposition, no tcgen05.st for the inputs;
@@ -515,7 +306,8 @@ k_tc_fwd_tma(const __grid_constant__ TmaDesc tm_x, const __grid_constant__ TmaDe
                     tc_wait_ld();
                     tc_fence_before();
                     warp_arrive(&a_ready[s], lane);              // accumulator read: the slot can start its next tile
-                    if (HEAD == 0) {
+                    if (HEAD == 3 || HEAD == 4) head.sigma[row] = expf(f16_round(__uint_as_float(acc[0])));
+                    if (HEAD == 0 || HEAD == 4) {
                         // 32-byte output rows: two 16-byte stores per lane (consecutive lanes -> consecutive rows)
                         int4* o = reinterpret_cast<int4*>(out + row * 16);
                         o[0] = make_int4((int)pack2(__uint_as_float(acc[0]), __uint_as_float(acc[1])), (int)pack2(__uint_as_float(acc[2]), __uint_as_float(acc[3])),
@@ -546,7 +338,7 @@ k_tc_fwd_tma(const __grid_constant__ TmaDesc tm_x, const __grid_constant__ TmaDe
                             tma_store_2d(&tm_cin, smem_u32(cb), 0, (int32_t)((uint32_t)tile * kTile));
                             tma_store_commit();
                         }
-                    } else {
+                    } else if (HEAD == 2) {
                         for (int c = 0; c < head.n_ch; ++c) {
                             const float y = f16_round(__uint_as_float(acc[c]));
                             head.rgb[row * head.n_ch + c] = f16_round(1.0f / (1.0f + expf(-y)));
@@ -571,16 +363,13 @@ static inline uint32_t tc_grid(uint32_t n_tiles) {
     return n_tiles < cap ? n_tiles : cap;
 }
 
-static int g_fwd_tma = -1;    // -1: read ENERF_TC_FWD_TMA (default on); 0: k_tc_fwd; 1: k_tc_fwd_tma when applicable
-void tc_set_fwd_tma(int on) { g_fwd_tma = on ? 1 : 0; }
-
 template <int NSLOTS, int NH, int IN_DIM, int HEAD, bool TRAIN>
 static int launch_fwd_tma_n(const TmaDesc& tx, const TmaDesc& tfb, const TmaDesc& tcin, const __half* W, __half* out, uint32_t B, HeadArgs head,
                             cudaStream_t st, const char* name) {
     size_t smem = 1024 + (size_t)NSLOTS * 2 * kTile * IN_DIM * 2 + (TRAIN ? (size_t)NSLOTS * 2 * kGBytes : 0) + (HEAD == 1 ? (size_t)NSLOTS * kTile * 64 : 0) +
                   (size_t)IN_DIM * 128 + (size_t)NH * 8192 + 2048 + 4 * NSLOTS * 8 + 16;
     if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM (TMEM)
-    if (smem > 227 * 1024) return 1;
+    if (smem > 227 * 1024) { set_error("%s: shared-memory budget exceeded", name); return -2; }
     static bool configured = false;
     if (!configured) {
         ENERF_CUDA(cudaFuncSetAttribute(k_tc_fwd_tma<NSLOTS, NH, IN_DIM, HEAD, TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
@@ -593,84 +382,68 @@ static int launch_fwd_tma_n(const TmaDesc& tx, const TmaDesc& tfb, const TmaDesc
     return 0;
 }
 
-// returns 1 when the TMA kernel is not applicable (the caller then launches k_tc_fwd)
-template <int IN_DIM, int HEAD>
-static int launch_fwd_tma(const __half* in, const __half* W, uint32_t B, int n_hidden_mm, __half* fwd_buf, __half* out, HeadArgs head, cudaStream_t st,
-                          const char* name) {
-    if (g_fwd_tma < 0) {
-        const char* e = getenv("ENERF_TC_FWD_TMA");
-        g_fwd_tma = (e && e[0] == '0') ? 0 : 1;
-    }
-    if (!g_fwd_tma || (n_hidden_mm != 1 && n_hidden_mm != 2) || (uint64_t)(n_hidden_mm + 1) * B >= (1ull << 31)) return 1;
-    if (HEAD == 0 && (reinterpret_cast<uintptr_t>(out) & 15u)) return 1;
-    TmaDesc tx, tfb, tcin;
-    if (!make_tmap_rows(&tx, in, B, IN_DIM, kTile)) return 1;
-    tfb = tx;
-    tcin = tx;
-    if (fwd_buf && !make_tmap_rows(&tfb, fwd_buf, (uint64_t)(n_hidden_mm + 1) * B, 64, kTile)) return 1;
-    if (HEAD == 1 && !make_tmap_rows(&tcin, head.cin, B, 32, kTile)) return 1;
-    if (fwd_buf) {
-        if (n_hidden_mm == 1) return launch_fwd_tma_n<3, 1, IN_DIM, HEAD, true>(tx, tfb, tcin, W, out, B, head, st, name);
-        return launch_fwd_tma_n<3, 2, IN_DIM, HEAD, true>(tx, tfb, tcin, W, out, B, head, st, name);
-    }
-    if (n_hidden_mm == 1) return launch_fwd_tma_n<4, 1, IN_DIM, HEAD, false>(tx, tfb, tcin, W, out, B, head, st, name);
-    return launch_fwd_tma_n<4, 2, IN_DIM, HEAD, false>(tx, tfb, tcin, W, out, B, head, st, name);
-}
-
-static size_t fwd_smem_bytes(int in_dim, int n_hidden_mm, int nslots) {
-    return (size_t)in_dim * 128 + (size_t)n_hidden_mm * 8192 + 2048 + (size_t)nslots * 4 * 4096 + (size_t)nslots * 16 + 16;
-}
-
-template <int IN_DIM, int HEAD>
+// n_hidden_mm = hidden-to-hidden matmuls (0, 1 or 2); fwd_buf != NULL stores every hidden activation (the reference's training contract)
+template <int HEAD>
 static int launch_fwd(const __half* in, const __half* W, uint32_t B, int n_hidden_mm, __half* fwd_buf, __half* out, HeadArgs head, cudaStream_t st,
                       const char* name) {
-    if constexpr (IN_DIM == 32 || IN_DIM == 64) {
-        const int rc = launch_fwd_tma<IN_DIM, HEAD>(in, W, B, n_hidden_mm, fwd_buf, out, head, st, name);
-        if (rc != 1) return rc;
+    constexpr int IN_DIM = 32;
+    if (n_hidden_mm < 0 || n_hidden_mm > 2 || (uint64_t)(n_hidden_mm + 1) * B >= (1ull << 31)) {
+        set_error("%s: the tcgen05 path takes 1 to 3 layers and fewer than 2^31 activation rows", name);
+        return -2;
     }
-    constexpr int NSLOTS = 4;
-    size_t smem = fwd_smem_bytes(IN_DIM, n_hidden_mm, NSLOTS);
-    if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: it allocates all 512 TMEM columns
-    if (smem > 200 * 1024) { set_error("%s: network too deep for the tcgen05 path", name); return -2; }
-    static size_t configured = 0;
-    if (smem > configured) {
-        ENERF_CUDA(cudaFuncSetAttribute(k_tc_fwd<NSLOTS, IN_DIM, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
-        configured = smem;
+    TmaDesc tx, tfb, tcin;
+    if (!make_tmap_rows(&tx, in, B, IN_DIM, kTile)) { set_error("%s: inputs must be 16-byte aligned (TMA)", name); return -2; }
+    if ((HEAD == 0 || HEAD == 4) && (reinterpret_cast<uintptr_t>(out) & 15u)) { set_error("%s: outputs must be 16-byte aligned", name); return -2; }
+    tfb = tx;
+    tcin = tx;
+    if (fwd_buf && !make_tmap_rows(&tfb, fwd_buf, (uint64_t)(n_hidden_mm + 1) * B, 64, kTile)) { set_error("%s: bad forward_buffer", name); return -2; }
+    if (HEAD == 1 && !make_tmap_rows(&tcin, head.cin, B, 32, kTile)) { set_error("%s: bad colour-input buffer", name); return -2; }
+    if (fwd_buf) {
+        if constexpr (HEAD <= 2) {
+            if (n_hidden_mm == 1) return launch_fwd_tma_n<3, 1, IN_DIM, HEAD, true>(tx, tfb, tcin, W, out, B, head, st, name);
+            if (n_hidden_mm == 2) return launch_fwd_tma_n<3, 2, IN_DIM, HEAD, true>(tx, tfb, tcin, W, out, B, head, st, name);
+        }
+        set_error("%s: forward_buffer is stored for 2- and 3-layer networks only", name);
+        return -2;
     }
-    const uint32_t n_tiles = B / kTile;
-    const uint32_t grid = tc_grid(n_tiles);
-    k_tc_fwd<NSLOTS, IN_DIM, HEAD><<<grid, 32 + NSLOTS * 128, smem, st>>>(in, W, fwd_buf, out, n_tiles, B, n_hidden_mm, head);
-    ENERF_CHECK_LAUNCH(name);
-    return 0;
+    if (n_hidden_mm == 0) {
+        if constexpr (HEAD == 0 || HEAD == 3 || HEAD == 4) return launch_fwd_tma_n<4, 0, IN_DIM, HEAD, false>(tx, tfb, tcin, W, out, B, head, st, name);
+        set_error("%s: a 1-layer network has no fused colour head", name);
+        return -2;
+    }
+    if (n_hidden_mm == 1) return launch_fwd_tma_n<4, 1, IN_DIM, HEAD, false>(tx, tfb, tcin, W, out, B, head, st, name);
+    if constexpr (HEAD <= 2) return launch_fwd_tma_n<4, 2, IN_DIM, HEAD, false>(tx, tfb, tcin, W, out, B, head, st, name);
+    set_error("%s: density heads take 1- and 2-layer networks", name);
+    return -2;
 }
 
 int tc_forward(const __half* in, const __half* W, uint32_t B, int in_dim, int n_hidden_mm, __half* fwd_buf, __half* out, cudaStream_t st,
                const char* name) {
     HeadArgs none = {nullptr, nullptr, nullptr, nullptr, 0};
-    switch (in_dim) {
-        case 16: return launch_fwd<16, 0>(in, W, B, n_hidden_mm, fwd_buf, out, none, st, name);
-        case 32: return launch_fwd<32, 0>(in, W, B, n_hidden_mm, fwd_buf, out, none, st, name);
-        case 48: return launch_fwd<48, 0>(in, W, B, n_hidden_mm, fwd_buf, out, none, st, name);
-        case 64: return launch_fwd<64, 0>(in, W, B, n_hidden_mm, fwd_buf, out, none, st, name);
-    }
-    set_error("%s: input_dim must be 16, 32, 48 or 64 on the tcgen05 path", name);
-    return -2;
+    if (in_dim != 32) { set_error("%s: input_dim must be 32 on the tcgen05 path", name); return -2; }
+    return launch_fwd<0>(in, W, B, n_hidden_mm, fwd_buf, out, none, st, name);
 }
 
 // sigma-net with fused exp / SH / colour-input head (input_dim 32)
 int tc_forward_sigma_head(const __half* feat, const __half* W, uint32_t B, int n_hidden_mm, __half* fwd_buf, const float* dirs, float* sigma,
                           __half* cin, cudaStream_t st) {
     HeadArgs h = {dirs, sigma, cin, nullptr, 0};
-    return launch_fwd<32, 1>(feat, W, B, n_hidden_mm, fwd_buf, nullptr, h, st, "field_sigma_forward");
+    return launch_fwd<1>(feat, W, B, n_hidden_mm, fwd_buf, nullptr, h, st, "field_sigma_forward");
 }
 // colour-net with fused sigmoid head (input_dim 32)
 int tc_forward_rgb_head(const __half* cin, const __half* W, uint32_t B, int n_hidden_mm, __half* fwd_buf, float* rgb, int n_ch, cudaStream_t st) {
     HeadArgs h = {nullptr, nullptr, nullptr, rgb, n_ch};
-    return launch_fwd<32, 2>(cin, W, B, n_hidden_mm, fwd_buf, nullptr, h, st, "field_color_forward");
+    return launch_fwd<2>(cin, W, B, n_hidden_mm, fwd_buf, nullptr, h, st, "field_color_forward");
+}
+// density head: sigma (+ the 16 raw outputs when h != NULL) of a 1- or 2-layer sigma-net
+int tc_forward_density(const __half* feat, const __half* W, uint32_t B, int n_hidden_mm, float* sigma, __half* h, cudaStream_t st) {
+    HeadArgs a = {nullptr, sigma, nullptr, nullptr, 0};
+    if (h) return launch_fwd<4>(feat, W, B, n_hidden_mm, nullptr, h, a, st, "field_density_forward");
+    return launch_fwd<3>(feat, W, B, n_hidden_mm, nullptr, nullptr, a, st, "field_density_forward");
 }
 
 // ================================================================================================
-// Backward (k_tc_bwd): activation gradients AND weight gradients in one persistent kernel.
+// Backward: activation gradients AND weight gradients in one persistent kernel.
 //
 //   g_n   = (dy  . W_last) * relu'(h_n)              dgrad: A = dy/g in TMEM (K-major), B = the forward
 //   g_i-1 = (g_i . W_i)    * relu'(h_i-1)            weight tile read MN-major (same smem bytes)
@@ -683,7 +456,7 @@ int tc_forward_rgb_head(const __half* cin, const __half* W, uint32_t B, int n_hi
 //                                                     life and are reduced once with red.global.add.
 //   Activation gradients never touch HBM unless the caller asks for backward_buffer.
 //
-// Stage k (k = 0 .. n_hidden_mm+1) of a tile: epilogue E_k prepares operands, MMA thread issues
+// Stage k (k = 0 .. NH+1) of a tile: epilogue E_k prepares operands, the issuing warp launches
 // dgrad_k + wgrad_k, tcgen05.commit -> E_k+1 ... (see the schedule in DESIGN.md).
 // ================================================================================================
 
@@ -696,6 +469,8 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 //   PRO 1 (colour-net): dy[c] = fp16(g_rgb[c]) * rgb[c] * (1 - rgb[c]) for c < n_ch (sigmoid'), 0 otherwise
 //   PRO 2 (sigma-net) : dy[0] = g_sigma * exp(clamp(h0, -15, 15)) (trunc_exp', activation.py:15-18; h0 = log sigma),
 //                       dy[1:16] = dL/d(colour-net input)[16:31] (the geo_feat columns)
+//   PRO 3 (density head, nerf/network.py:134-151): dy[0] = g_sigma * exp(clamp(h0, -15, 15)) + grad[0], dy[1:16] = grad[1:16]
+//                       (grad [B,16] fp16 = dL/dh as autograd delivers it for the geo_feat slice; may be NULL = zero)
 struct ProArgs {
     const float* g_rgb;     // [B,n_ch]  (PRO 1)
     const float* rgb;       // [B,n_ch]  (PRO 1)
@@ -705,326 +480,11 @@ struct ProArgs {
     const __half* dcin;     // [B,32]    (PRO 2)
 };
 
-template <int NSLOTS, int PRO>
-__global__ void __launch_bounds__(32 + NSLOTS * 128, 1)
-k_tc_bwd(const __half* __restrict__ grad, const __half* __restrict__ x, const __half* __restrict__ W, const __half* __restrict__ fwd_buf,
-         __half* __restrict__ bwd_buf, __half* __restrict__ grad_inputs, float* __restrict__ dW, uint32_t n_tiles, uint32_t B, int in_dim,
-         int n_hidden_mm, ProArgs pro) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* w0s = smem;                                  // [in_dim/8][64][16 B]   (forward layout)
-    uint8_t* whs = w0s + in_dim * 128;                    // n_hidden_mm x [8][64][16 B]
-    uint8_t* wls = whs + n_hidden_mm * 8192;              // [8][16][16 B]
-    uint8_t* tiles = wls + 2048;                          // per slot: G tile, H tile
-    uint64_t* a_ready = reinterpret_cast<uint64_t*>(tiles + (size_t)NSLOTS * 2 * kGBytes);
-    uint64_t* d_full = a_ready + NSLOTS;
-    uint64_t* flush_bar = d_full + NSLOTS;
-    uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(flush_bar + 1);
-
-    const int tid = threadIdx.x, nthreads = blockDim.x;
-    const int warp = tid >> 5, lane = tid & 31;
-    constexpr uint32_t kCols = 512;
-
-    stage_matrix(w0s, W, kW, in_dim, tid, nthreads);
-    for (int j = 0; j < n_hidden_mm; ++j) stage_matrix(whs + j * 8192, W + kW * in_dim + j * kW * kW, kW, kW, tid, nthreads);
-    stage_matrix(wls, W + kW * in_dim + n_hidden_mm * kW * kW, 16, kW, tid, nthreads);
-    if (tid == 0) {
-        for (int s = 0; s < NSLOTS; ++s) {
-            mbar_init(&a_ready[s], 128);
-            mbar_init(&d_full[s], 1);
-        }
-        mbar_init(flush_bar, 1);
-        mbar_fence_init();
-    }
-    if (warp == 0) tmem_alloc(tmem_base_ptr, kCols);
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem0 = *tmem_base_ptr;
-
-    const int S = n_hidden_mm + 2;
-    const uint32_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    // weight-gradient accumulators (TMEM columns): [dW_last^T : 16][dW_hidden j : 64 each][dW_0 : in_dim]
-    const uint32_t acc_last = tmem0 + NSLOTS * kSlotCols;
-    const uint32_t acc_hid = acc_last + 16;
-    const uint32_t acc_0 = acc_hid + n_hidden_mm * 64;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            uint32_t pa[NSLOTS], stage[NSLOTS], left[NSLOTS];
-            uint32_t remaining = 0, started = 0;   // bit k of `started`: stage k's wgrad accumulator has been written once
-#pragma unroll
-            for (int s = 0; s < NSLOTS; ++s) {
-                pa[s] = 0;
-                stage[s] = 0;
-                left[s] = (my_tiles > (uint32_t)s) ? (my_tiles - s + NSLOTS - 1) / NSLOTS : 0;
-                remaining += left[s] * S;
-            }
-            while (remaining > 0) {
-#pragma unroll
-                for (int s = 0; s < NSLOTS; ++s) {
-                    if (left[s] == 0 || !mbar_test(&a_ready[s], pa[s])) continue;
-                    pa[s] ^= 1;
-                    tc_fence_after();
-                    const int k = (int)stage[s];
-                    const uint32_t d_t = tmem0 + s * kSlotCols, a_t = d_t + 64;
-                    const uint32_t g_s = smem_u32(tiles + (size_t)s * 2 * kGBytes), h_s = g_s + kGBytes;
-                    const bool acc = (started >> k) & 1u;
-                    started |= 1u << k;
-                    if (k == 0) {
-                        // dgrad through the output layer: D[128x64] = dy[128x16] . W_last[16x64]
-                        mma_ts(d_t, a_t, smem_desc(smem_u32(wls), 128, 16 * 16), idesc_f16(kTile, 64, false, true), false);
-                        // dW_last^T[64x16] += h_n^T[64x128] . dy[128x16]   (A = H tile, B = dy tile in the G buffer)
-                        for (int ks = 0; ks < 8; ++ks)
-                            mma_ss(acc_last, smem_desc(h_s + ks * 256, 128, 2048), smem_desc(g_s + ks * 256, 128, 2048),
-                                   idesc_f16(64, 16, true, true), acc || ks > 0);
-                    } else if (k <= n_hidden_mm) {
-                        const int jm = n_hidden_mm - k;      // hidden matmul index
-                        const uint32_t wj = smem_u32(whs + jm * 8192);
-                        for (int ks = 0; ks < 4; ++ks)
-                            mma_ts(d_t, a_t + ks * 8, smem_desc(wj + ks * 256, 128, 64 * 16), idesc_f16(kTile, 64, false, true), ks > 0);
-                        for (int ks = 0; ks < 8; ++ks)
-                            mma_ss(acc_hid + jm * 64, smem_desc(g_s + ks * 256, 128, 2048), smem_desc(h_s + ks * 256, 128, 2048),
-                                   idesc_f16(64, 64, true, true), acc || ks > 0);
-                    } else {
-                        if (grad_inputs)
-                            for (int ks = 0; ks < 4; ++ks)
-                                mma_ts(d_t, a_t + ks * 8, smem_desc(smem_u32(w0s) + ks * 256, 128, 64 * 16),
-                                       idesc_f16(kTile, (uint32_t)in_dim, false, true), ks > 0);
-                        for (int ks = 0; ks < 8; ++ks)
-                            mma_ss(acc_0, smem_desc(g_s + ks * 256, 128, 2048), smem_desc(h_s + ks * 256, 128, 2048),
-                                   idesc_f16(64, (uint32_t)in_dim, true, true), acc || ks > 0);
-                    }
-                    tc_commit(&d_full[s]);
-                    --remaining;
-                    if (++stage[s] == (uint32_t)S) {
-                        stage[s] = 0;
-                        --left[s];
-                    }
-                }
-            }
-            tc_commit(flush_bar);
-        }
-    } else {
-        const int s = (warp - 1) >> 2;
-        const int q = warp & 3;
-        const int r_in_tile = q * 32 + lane;
-        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-        const uint32_t d_t = tmem0 + lane_sel + s * kSlotCols, a_t = d_t + 64;
-        uint8_t* g_tile = tiles + (size_t)s * 2 * kGBytes;
-        uint8_t* h_tile = g_tile + kGBytes;
-        uint32_t pd = 0;
-        uint32_t hreg[32];       // this row's forward activation (64 fp16) used as ReLU mask by the next epilogue
-        // Global rows needed by the NEXT epilogue stage are requested before waiting for the tensor core, so
-        // their HBM latency overlaps the MMAs: `pre` = h_n row of the tile about to start, `nxt` = next stage's row.
-        int4 pre[8];
-        if ((uint32_t)s < my_tiles) {
-            const size_t row0 = ((size_t)blockIdx.x + (size_t)s * gridDim.x) * kTile + r_in_tile;
-            const int4* hs0 = reinterpret_cast<const int4*>(fwd_buf + ((size_t)n_hidden_mm * B + row0) * kW);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) pre[c] = __ldg(hs0 + c);
-        }
-
-        for (uint32_t j = s; j < my_tiles; j += NSLOTS) {
-            const size_t tile = (size_t)blockIdx.x + (size_t)j * gridDim.x;
-            const size_t row = tile * kTile + r_in_tile;
-            // ---- E_0: dy -> TMEM A + dy tile (G buffer); h_n -> registers + H tile
-            {
-                int4 v0, v1;
-                if (PRO == 0) {
-                    const int4* src = reinterpret_cast<const int4*>(grad + row * 16);
-                    v0 = __ldg(src);
-                    v1 = __ldg(src + 1);
-                } else if (PRO == 1) {
-                    float dyv[4] = {0.f, 0.f, 0.f, 0.f};
-                    for (int c = 0; c < pro.n_ch; ++c) {
-                        const float y = pro.rgb[row * pro.n_ch + c];
-                        dyv[c] = f16_round(pro.g_rgb[row * pro.n_ch + c]) * (1.0f - y) * y;
-                    }
-                    v0 = make_int4((int)pack2(dyv[0], dyv[1]), (int)pack2(dyv[2], dyv[3]), 0, 0);
-                    v1 = make_int4(0, 0, 0, 0);
-                } else {
-                    const float sg = fminf(fmaxf(pro.sigma[row], 3.0590232050182579e-07f), 3269017.3724721107f);   // exp(-15), exp(15)
-                    const __half d0 = __float2half_rn(pro.g_sigma[row] * sg);
-                    // dcin columns 16..30 -> dy columns 1..15 (shift by one fp16)
-                    const int4* src = reinterpret_cast<const int4*>(pro.dcin + row * 32 + 16);
-                    const int4 a = __ldg(src), b = __ldg(src + 1);
-                    const uint32_t w[8] = {(uint32_t)a.x, (uint32_t)a.y, (uint32_t)a.z, (uint32_t)a.w, (uint32_t)b.x, (uint32_t)b.y, (uint32_t)b.z, (uint32_t)b.w};
-                    uint32_t o[8];
-                    o[0] = (uint32_t)__half_as_ushort(d0) | (w[0] << 16);
-#pragma unroll
-                    for (int e = 1; e < 8; ++e) o[e] = (w[e - 1] >> 16) | (w[e] << 16);
-                    v0 = make_int4((int)o[0], (int)o[1], (int)o[2], (int)o[3]);
-                    v1 = make_int4((int)o[4], (int)o[5], (int)o[6], (int)o[7]);
-                }
-                const uint32_t r8[8] = {(uint32_t)v0.x, (uint32_t)v0.y, (uint32_t)v0.z, (uint32_t)v0.w,
-                                        (uint32_t)v1.x, (uint32_t)v1.y, (uint32_t)v1.z, (uint32_t)v1.w};
-                tmem_st8(a_t, r8);
-                *reinterpret_cast<int4*>(g_tile + 0 * 2048 + r_in_tile * 16) = v0;
-                *reinterpret_cast<int4*>(g_tile + 1 * 2048 + r_in_tile * 16) = v1;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const int4 v = pre[c];
-                    hreg[4 * c] = (uint32_t)v.x; hreg[4 * c + 1] = (uint32_t)v.y; hreg[4 * c + 2] = (uint32_t)v.z; hreg[4 * c + 3] = (uint32_t)v.w;
-                    *reinterpret_cast<int4*>(h_tile + c * 2048 + r_in_tile * 16) = v;
-                }
-                tc_wait_st();
-                fence_proxy_async_smem();
-                tc_fence_before();
-                mbar_arrive(&a_ready[s]);
-            }
-            // ---- E_k, k = 1 .. S-1: g = D * relu'(h) -> TMEM A + G tile; next activation (or x) -> H tile
-            for (int k = 1; k < S; ++k) {
-                int4 nxt[8];
-                if (k < S - 1) {
-                    const int4* hs = reinterpret_cast<const int4*>(fwd_buf + ((size_t)(n_hidden_mm - k) * B + row) * kW);
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) nxt[c] = __ldg(hs + c);
-                } else {
-                    const int4* xs = reinterpret_cast<const int4*>(x + row * in_dim);
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) nxt[c] = (c < in_dim / 8) ? __ldg(xs + c) : make_int4(0, 0, 0, 0);
-                }
-                mbar_wait(&d_full[s], pd);
-                pd ^= 1;
-                tc_fence_after();
-                __half* bb = bwd_buf ? bwd_buf + ((size_t)(k - 1) * B + row) * kW : nullptr;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    uint32_t acc[32];
-                    tmem_ld32(d_t + h * 32, acc);
-                    tc_wait_ld();
-                    uint32_t p[16];
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        const __half2 hv = *reinterpret_cast<const __half2*>(&hreg[h * 16 + e]);
-                        const float g0 = (__low2float(hv) > 0.f) ? __uint_as_float(acc[2 * e]) : 0.f;
-                        const float g1 = (__high2float(hv) > 0.f) ? __uint_as_float(acc[2 * e + 1]) : 0.f;
-                        p[e] = pack2(g0, g1);
-                    }
-                    tmem_st16(a_t + h * 16, p);
-#pragma unroll
-                    for (int v = 0; v < 4; ++v) {
-                        const int4 val = make_int4((int)p[4 * v], (int)p[4 * v + 1], (int)p[4 * v + 2], (int)p[4 * v + 3]);
-                        *reinterpret_cast<int4*>(g_tile + (h * 4 + v) * 2048 + r_in_tile * 16) = val;
-                        if (bb) reinterpret_cast<int4*>(bb)[h * 4 + v] = val;
-                    }
-                }
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const int4 v = nxt[c];
-                    hreg[4 * c] = (uint32_t)v.x; hreg[4 * c + 1] = (uint32_t)v.y; hreg[4 * c + 2] = (uint32_t)v.z; hreg[4 * c + 3] = (uint32_t)v.w;
-                    if (k < S - 1 || c < in_dim / 8) *reinterpret_cast<int4*>(h_tile + c * 2048 + r_in_tile * 16) = v;
-                }
-                tc_wait_st();
-                fence_proxy_async_smem();
-                tc_fence_before();
-                mbar_arrive(&a_ready[s]);
-            }
-            // ---- E_S: dx
-            if (j + NSLOTS < my_tiles) {
-                const size_t nrow = ((size_t)blockIdx.x + (size_t)(j + NSLOTS) * gridDim.x) * kTile + r_in_tile;
-                const int4* hs0 = reinterpret_cast<const int4*>(fwd_buf + ((size_t)n_hidden_mm * B + nrow) * kW);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) pre[c] = __ldg(hs0 + c);
-            }
-            mbar_wait(&d_full[s], pd);
-            pd ^= 1;
-            tc_fence_after();
-            if (grad_inputs) {
-                for (int c = 0; c < in_dim / 16; ++c) {
-                    uint32_t acc[16];
-                    tmem_ld16(d_t + c * 16, acc);
-                    tc_wait_ld();
-                    uint32_t p[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) p[e] = pack2(__uint_as_float(acc[2 * e]), __uint_as_float(acc[2 * e + 1]));
-                    int4* dst = reinterpret_cast<int4*>(grad_inputs + row * in_dim + c * 16);
-                    dst[0] = make_int4((int)p[0], (int)p[1], (int)p[2], (int)p[3]);
-                    dst[1] = make_int4((int)p[4], (int)p[5], (int)p[6], (int)p[7]);
-                }
-            }
-            tc_fence_before();
-        }
-
-        // ---- flush the weight-gradient accumulators (slot 0's four warps; M = 64 -> lanes 0..15 of each quarter)
-        if (s == 0 && my_tiles > 0) {
-            mbar_wait(flush_bar, 0);
-            tc_fence_after();
-            const int m = q * 16 + lane;                  // row of the 64-row accumulator held by lanes < 16
-            const uint32_t base = lane_sel;
-            float* dW0 = dW;
-            float* dWh = dW + kW * in_dim;
-            float* dWl = dWh + (size_t)n_hidden_mm * kW * kW;
-            {   // dW_last^T [hidden m][out n] -> dW_last[n][m]
-                uint32_t acc[16];
-                tmem_ld16(acc_last + base, acc);
-                tc_wait_ld();
-                if (lane < 16)
-#pragma unroll
-                    for (int nn = 0; nn < 16; ++nn) atomicAdd(dWl + nn * kW + m, __uint_as_float(acc[nn]));
-            }
-            for (int jj = 0; jj < n_hidden_mm; ++jj)
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t acc[16];
-                    tmem_ld16(acc_hid + jj * 64 + c * 16 + base, acc);
-                    tc_wait_ld();
-                    if (lane < 16) {
-                        float* dst = dWh + (size_t)jj * kW * kW + (size_t)m * kW + c * 16;
-#pragma unroll
-                        for (int v = 0; v < 4; ++v)
-                            red_add_v4(dst + 4 * v, __uint_as_float(acc[4 * v]), __uint_as_float(acc[4 * v + 1]), __uint_as_float(acc[4 * v + 2]),
-                                       __uint_as_float(acc[4 * v + 3]));
-                    }
-                }
-            for (int c = 0; c < in_dim / 16; ++c) {
-                uint32_t acc[16];
-                tmem_ld16(acc_0 + c * 16 + base, acc);
-                tc_wait_ld();
-                if (lane < 16) {
-                    float* dst = dW0 + (size_t)m * in_dim + c * 16;
-#pragma unroll
-                    for (int v = 0; v < 4; ++v)
-                        red_add_v4(dst + 4 * v, __uint_as_float(acc[4 * v]), __uint_as_float(acc[4 * v + 1]), __uint_as_float(acc[4 * v + 2]),
-                                   __uint_as_float(acc[4 * v + 3]));
-                }
-            }
-            tc_fence_before();
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem0, kCols);
-}
-
-template <int PRO>
-static int launch_bwd(const __half* grad, const __half* x, const __half* W, const __half* fwd_buf, __half* bwd_buf, __half* grad_inputs, float* dW,
-                      uint32_t B, int in_dim, int n_hidden_mm, ProArgs pro, cudaStream_t st, const char* name) {
-    constexpr int NSLOTS = 2;
-    // TMEM: NSLOTS*96 + 16 + 64*n_hidden_mm + in_dim columns
-    if (NSLOTS * kSlotCols + 16 + 64 * n_hidden_mm + in_dim > 512) { set_error("%s: network too deep for the tcgen05 path", name); return -2; }
-    size_t smem = (size_t)in_dim * 128 + (size_t)n_hidden_mm * 8192 + 2048 + (size_t)NSLOTS * 2 * kGBytes + (2 * NSLOTS + 1) * 8 + 16;
-    if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: it allocates all 512 TMEM columns
-    if (smem > 220 * 1024) { set_error("%s: network too deep for the tcgen05 path", name); return -2; }
-    static size_t configured = 0;
-    if (smem > configured) {
-        ENERF_CUDA(cudaFuncSetAttribute(k_tc_bwd<NSLOTS, PRO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
-        configured = smem;
-    }
-    const uint32_t n_tiles = B / kTile;
-    const uint32_t grid = tc_grid(n_tiles);
-    k_tc_bwd<NSLOTS, PRO><<<grid, 32 + NSLOTS * 128, smem, st>>>(grad, x, W, fwd_buf, bwd_buf, grad_inputs, dW, n_tiles, B, in_dim, n_hidden_mm, pro);
-    ENERF_CHECK_LAUNCH(name);
-    return 0;
-}
-
-
 // ================================================================================================
-// Backward, TMA variant (k_tc_bwd_tma).  Same mathematics and the same TMEM plan as k_tc_bwd; what
-// changes is how the stored forward activations reach the SM.  k_tc_bwd has every epilogue thread
-// read its own 128-byte row (8 strided 16-byte loads per stage: 32 L1 wavefronts per request, the LSU
-// data pipe sat at 75-80 % in ncu) and copy it into the canonical operand tile.  Here the MMA thread
-// issues ONE cp.async.bulk.tensor per stage: the [128 x 64] fp16 tile of forward_buffer (or the
+// Backward from stored activations (k_tc_bwd_tma; the reference's contract: forward_buffer in).  The first version of this
+// kernel had every epilogue thread read its own 128-byte activation row (8 strided 16-byte loads per stage: 32 L1 wavefronts
+// per request, the LSU data pipe sat at 75-80 % in ncu) and copy it into a canonical operand tile.  Here the issuing warp
+// launches ONE cp.async.bulk.tensor per stage: the [128 x 64] fp16 tile of forward_buffer (or the
 // [128 x in_dim] input tile for the last stage) lands in shared memory in the 128-byte (64-byte)
 // TMA swizzle, which tcgen05.mma reads directly as the MN-major wgrad operand; a RING-deep ring per
 // slot keeps the loads of the next RING-1 stages in flight while stage i computes.  Epilogue threads only read their row's
@@ -1038,7 +498,8 @@ static int launch_bwd(const __half* grad, const __half* x, const __half* W, cons
 template <int NSLOTS, int RING, int NH, int PRO, int IN_DIM>
 __global__ void __launch_bounds__(32 + NSLOTS * 128, 1)
 k_tc_bwd_tma(const __grid_constant__ TmaDesc tm_h, const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ grad,
-             const __half* __restrict__ W, __half* __restrict__ grad_inputs, float* __restrict__ dW, uint32_t n_tiles, uint32_t B, ProArgs pro) {
+             const __half* __restrict__ W, __half* __restrict__ bwd_buf, __half* __restrict__ grad_inputs, float* __restrict__ dW, uint32_t n_tiles,
+             uint32_t B, ProArgs pro) {
     // NH = hidden-to-hidden matmuls (compile time): every stage of a tile is unrolled, so descriptors, ring buffers and
     // accumulator columns are constants relative to a handful of uniform registers and the issuing warp spends a few
     // instructions per MMA (with run-time stage dispatch it needed ~300 instructions per stage and was the bottleneck).
@@ -1203,12 +664,20 @@ k_tc_bwd_tma(const __grid_constant__ TmaDesc tm_h, const __grid_constant__ TmaDe
                         pf[c] = __ldg(pro.rgb + row * pro.n_ch + c);
                         pf[4 + c] = __ldg(pro.g_rgb + row * pro.n_ch + c);
                     }
-            } else {
+            } else if (PRO == 2) {
                 pf[0] = __ldg(pro.sigma + row);
                 pf[1] = __ldg(pro.g_sigma + row);
                 const int4* src = reinterpret_cast<const int4*>(pro.dcin + row * 32 + 16);
                 pv0 = __ldg(src);
                 pv1 = __ldg(src + 1);
+            } else {
+                pf[0] = __ldg(pro.sigma + row);
+                pf[1] = pro.g_sigma ? __ldg(pro.g_sigma + row) : 0.f;
+                if (grad) {
+                    const int4* src = reinterpret_cast<const int4*>(grad + row * 16);
+                    pv0 = __ldg(src);
+                    pv1 = __ldg(src + 1);
+                }
             }
         };
         if ((uint32_t)s < my_tiles) fetch(((size_t)blockIdx.x + (size_t)s * gridDim.x) * kTile + r_in_tile);
@@ -1282,9 +751,12 @@ k_tc_bwd_tma(const __grid_constant__ TmaDesc tm_h, const __grid_constant__ TmaDe
                     }
                     tmem_st16(a_t + h * 16, p);
 #pragma unroll
-                    for (int v = 0; v < 4; ++v)
-                        *reinterpret_cast<int4*>(g_tile + (h * 4 + v) * 2048 + r_in_tile * 16) =
-                            make_int4((int)p[4 * v], (int)p[4 * v + 1], (int)p[4 * v + 2], (int)p[4 * v + 3]);
+                    for (int v = 0; v < 4; ++v) {
+                        const int4 val = make_int4((int)p[4 * v], (int)p[4 * v + 1], (int)p[4 * v + 2], (int)p[4 * v + 3]);
+                        *reinterpret_cast<int4*>(g_tile + (h * 4 + v) * 2048 + r_in_tile * 16) = val;
+                        // the reference's `backward_buffer` [num_layers, B, 64] (ffmlp.cu:742-748): written only when a caller asks for it
+                        if (bwd_buf) reinterpret_cast<int4*>(bwd_buf + ((size_t)(k - 1) * B + row) * kW)[h * 4 + v] = val;
+                    }
                 }
                 tc_wait_st();
                 fence_proxy_async_smem();
@@ -1371,66 +843,41 @@ extern "C" int enerf_debug_set_trace(unsigned long long* buf) {
 namespace enerf {
 namespace tcm {
 #endif
-static int g_bwd_tma = -1;    // -1: read ENERF_TC_BWD_TMA (default on); 0: k_tc_bwd; 1: k_tc_bwd_tma
-static int g_bwd_slots = 0;   // 0: read ENERF_TC_BWD_SLOTS (default 3)
-static int g_bwd_ring = 0;    // 0: read ENERF_TC_BWD_RING (default 2)
-void tc_set_bwd_tma(int on) { g_bwd_tma = on ? 1 : 0; }
-
 template <int NSLOTS, int RING, int NH, int PRO, int IN_DIM>
-static int launch_bwd_tma_n(const TmaDesc& th, const TmaDesc& tx, const __half* grad, const __half* W, __half* grad_inputs, float* dW, uint32_t B,
-                            ProArgs pro, cudaStream_t st, const char* name) {
-    if constexpr ((NH + 2) % RING != 0 || NSLOTS * kSlotCols + 16 + 64 * NH + IN_DIM > 512) {
-        return 1;
-    } else {
-        size_t smem = 1024 + (size_t)NSLOTS * (RING + 1) * kGBytes + (size_t)IN_DIM * 128 + (size_t)NH * 8192 + 2048 + ((2 + RING) * NSLOTS + 1) * 8 + 16;
-        if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: it allocates all 512 TMEM columns
-        if (smem > 227 * 1024) return 1;
-        static bool configured = false;
-        if (!configured) {
-            ENERF_CUDA(cudaFuncSetAttribute(k_tc_bwd_tma<NSLOTS, RING, NH, PRO, IN_DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
-            configured = true;
-        }
-        const uint32_t n_tiles = B / kTile;
-        const uint32_t grid = tc_grid(n_tiles);
-        k_tc_bwd_tma<NSLOTS, RING, NH, PRO, IN_DIM><<<grid, 32 + NSLOTS * 128, smem, st>>>(th, tx, grad, W, grad_inputs, dW, n_tiles, B, pro);
-        ENERF_CHECK_LAUNCH(name);
-        return 0;
+static int launch_bwd_tma_n(const TmaDesc& th, const TmaDesc& tx, const __half* grad, const __half* W, __half* bwd_buf, __half* grad_inputs, float* dW,
+                            uint32_t B, ProArgs pro, cudaStream_t st, const char* name) {
+    static_assert((NH + 2) % RING == 0 && NSLOTS * kSlotCols + 16 + 64 * NH + IN_DIM <= 512, "ring / TMEM budget");
+    size_t smem = 1024 + (size_t)NSLOTS * (RING + 1) * kGBytes + (size_t)IN_DIM * 128 + (size_t)NH * 8192 + 2048 + ((2 + RING) * NSLOTS + 1) * 8 + 16;
+    if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: it allocates all 512 TMEM columns
+    if (smem > 227 * 1024) { set_error("%s: shared-memory budget exceeded", name); return -2; }
+    static bool configured = false;
+    if (!configured) {
+        ENERF_CUDA(cudaFuncSetAttribute(k_tc_bwd_tma<NSLOTS, RING, NH, PRO, IN_DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
+        configured = true;
     }
+    const uint32_t n_tiles = B / kTile;
+    const uint32_t grid = tc_grid(n_tiles);
+    k_tc_bwd_tma<NSLOTS, RING, NH, PRO, IN_DIM><<<grid, 32 + NSLOTS * 128, smem, st>>>(th, tx, grad, W, bwd_buf, grad_inputs, dW, n_tiles, B, pro);
+    ENERF_CHECK_LAUNCH(name);
+    return 0;
 }
 
-// returns 1 when the TMA kernel is not applicable (caller falls back to k_tc_bwd), 0 on success, <0 / CUDA error otherwise
+// backward from stored activations: 3 tiles in flight; 3 stages per tile -> activation ring of 3, 4 stages -> ring of 2
+// (measured, 3.29 M samples: 2 slots 0.25 / 0.34 ms, 3 slots 0.22 / 0.30 ms for the 2- / 3-layer net)
 template <int PRO>
-static int launch_bwd_tma(const __half* grad, const __half* x, const __half* W, const __half* fwd_buf, __half* grad_inputs, float* dW, uint32_t B,
-                          int in_dim, int n_hidden_mm, ProArgs pro, cudaStream_t st, const char* name) {
-    if (g_bwd_tma < 0) {
-        const char* e = getenv("ENERF_TC_BWD_TMA");
-        g_bwd_tma = (e && e[0] == '0') ? 0 : 1;
+static int launch_bwd_tma(const __half* grad, const __half* x, const __half* W, const __half* fwd_buf, __half* bwd_buf, __half* grad_inputs, float* dW,
+                          uint32_t B, int in_dim, int n_hidden_mm, ProArgs pro, cudaStream_t st, const char* name) {
+    if (in_dim != 32 || (n_hidden_mm != 1 && n_hidden_mm != 2) || (uint64_t)(n_hidden_mm + 1) * B >= (1ull << 31)) {
+        set_error("%s: the tcgen05 path takes 32 inputs, 2 or 3 layers and fewer than 2^31 activation rows", name);
+        return -2;
     }
-    if (g_bwd_slots == 0) {
-        const char* e = getenv("ENERF_TC_BWD_SLOTS");
-        g_bwd_slots = e ? atoi(e) : 3;
-        if (g_bwd_slots < 2 || g_bwd_slots > 4) g_bwd_slots = 3;
-        e = getenv("ENERF_TC_BWD_RING");
-        g_bwd_ring = e ? atoi(e) : 0;       // 0 = automatic: 3 for three-stage networks, 2 for four-stage networks
-    }
-    if (!g_bwd_tma || in_dim != 32 || (n_hidden_mm != 1 && n_hidden_mm != 2) || (uint64_t)(n_hidden_mm + 1) * B >= (1ull << 31)) return 1;
     TmaDesc th, tx;
-    if (!make_tmap_rows(&th, fwd_buf, (uint64_t)(n_hidden_mm + 1) * B, 64, kTile) || !make_tmap_rows(&tx, x, B, (uint32_t)in_dim, kTile)) return 1;
-    const int slots = g_bwd_slots;
-    if (n_hidden_mm == 1) {           // 3 stages per tile: ring of 3
-#define ENERF_BWD_TMA_CASE(NS) \
-    if (slots == NS) return launch_bwd_tma_n<NS, 3, 1, PRO, 32>(th, tx, grad, W, grad_inputs, dW, B, pro, st, name);
-        ENERF_BWD_TMA_CASE(2) ENERF_BWD_TMA_CASE(3) ENERF_BWD_TMA_CASE(4)
-#undef ENERF_BWD_TMA_CASE
-    } else {                          // 4 stages per tile: ring of 2 (or 4 with ENERF_TC_BWD_RING=4)
-        if (g_bwd_ring == 4) {
-            if (slots == 2) return launch_bwd_tma_n<2, 4, 2, PRO, 32>(th, tx, grad, W, grad_inputs, dW, B, pro, st, name);
-            return 1;
-        }
-        if (slots == 2) return launch_bwd_tma_n<2, 2, 2, PRO, 32>(th, tx, grad, W, grad_inputs, dW, B, pro, st, name);
-        return launch_bwd_tma_n<3, 2, 2, PRO, 32>(th, tx, grad, W, grad_inputs, dW, B, pro, st, name);
+    if (!make_tmap_rows(&th, fwd_buf, (uint64_t)(n_hidden_mm + 1) * B, 64, kTile) || !make_tmap_rows(&tx, x, B, (uint32_t)in_dim, kTile)) {
+        set_error("%s: inputs / forward_buffer must be 16-byte aligned (TMA)", name);
+        return -2;
     }
-    return 1;
+    if (n_hidden_mm == 1) return launch_bwd_tma_n<3, 3, 1, PRO, 32>(th, tx, grad, W, bwd_buf, grad_inputs, dW, B, pro, st, name);
+    return launch_bwd_tma_n<3, 2, 2, PRO, 32>(th, tx, grad, W, bwd_buf, grad_inputs, dW, B, pro, st, name);
 }
 
 // ================================================================================================
@@ -1657,12 +1104,20 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
                         pf[c] = __ldg(pro.rgb + row * pro.n_ch + c);
                         pf[4 + c] = __ldg(pro.g_rgb + row * pro.n_ch + c);
                     }
-            } else {
+            } else if (PRO == 2) {
                 pf[0] = __ldg(pro.sigma + row);
                 pf[1] = __ldg(pro.g_sigma + row);
                 const int4* src = reinterpret_cast<const int4*>(pro.dcin + row * 32 + 16);
                 pv0 = __ldg(src);
                 pv1 = __ldg(src + 1);
+            } else {
+                pf[0] = __ldg(pro.sigma + row);
+                pf[1] = pro.g_sigma ? __ldg(pro.g_sigma + row) : 0.f;
+                if (grad) {
+                    const int4* src = reinterpret_cast<const int4*>(grad + row * 16);
+                    pv0 = __ldg(src);
+                    pv1 = __ldg(src + 1);
+                }
             }
         };
         if (hf == 0 && (uint32_t)s < my_tiles) fetch(((size_t)blockIdx.x + (size_t)s * gridDim.x) * kTile + r_in_tile);
@@ -1707,7 +1162,7 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
                             if (c < pro.n_ch) dyv[c] = f16_round(pf[4 + c]) * (1.0f - pf[c]) * pf[c];
                         v0 = make_int4((int)pack2(dyv[0], dyv[1]), (int)pack2(dyv[2], dyv[3]), 0, 0);
                         v1 = make_int4(0, 0, 0, 0);
-                    } else {
+                    } else if (PRO == 2) {
                         const float sg = fminf(fmaxf(pf[0], 3.0590232050182579e-07f), 3269017.3724721107f);   // exp(-15), exp(15)
                         const __half d0 = __float2half_rn(pf[1] * sg);
                         const uint32_t w[8] = {(uint32_t)pv0.x, (uint32_t)pv0.y, (uint32_t)pv0.z, (uint32_t)pv0.w,
@@ -1718,6 +1173,13 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
                         for (int e = 1; e < 8; ++e) o[e] = (w[e - 1] >> 16) | (w[e] << 16);
                         v0 = make_int4((int)o[0], (int)o[1], (int)o[2], (int)o[3]);
                         v1 = make_int4((int)o[4], (int)o[5], (int)o[6], (int)o[7]);
+                    } else {
+                        // density head: column 0 carries trunc_exp' (activation.py:15-18) on top of whatever arrived for h[0]
+                        const float sg = fminf(fmaxf(pf[0], 3.0590232050182579e-07f), 3269017.3724721107f);   // exp(-15), exp(15)
+                        const float g0 = __half2float(__ushort_as_half((unsigned short)((uint32_t)pv0.x & 0xffffu)));
+                        const __half d0 = __float2half_rn(pf[1] * sg + g0);
+                        v0 = make_int4((int)(((uint32_t)pv0.x & 0xffff0000u) | (uint32_t)__half_as_ushort(d0)), pv0.y, pv0.z, pv0.w);
+                        v1 = pv1;
                     }
                     const uint32_t r8[8] = {(uint32_t)v0.x, (uint32_t)v0.y, (uint32_t)v0.z, (uint32_t)v0.w,
                                             (uint32_t)v1.x, (uint32_t)v1.y, (uint32_t)v1.z, (uint32_t)v1.w};
@@ -1858,13 +1320,16 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
     if (warp == 0) tmem_dealloc(tmem0, kCols);
 }
 
-template <int NSLOTS, int NH, int PRO, bool GD, int CH, bool XA, int NI = 1>
+template <int NSLOTS, int NH, int PRO, bool XA>
 static int launch_bwd_rc_n(const TmaDesc& tx, const __half* grad, const __half* W, __half* grad_inputs, float* dW, uint32_t B, ProArgs pro,
                            cudaStream_t st, const char* name) {
+    constexpr bool GD = false;      // second G tile + early dgrad commit: measured +-0 %
+    constexpr int CH = 1;           // two epilogue threads per row: +8 % with 2 tiles in flight, nothing with 3
+    constexpr int NI = 1;           // second issuing warp: +-0 %
     constexpr size_t kSlot = (XA ? 0 : 2 * (size_t)kTile * 32 * 2) + (size_t)(NH + 2 + (GD ? 1 : 0)) * kGBytes;
     size_t smem = 1024 + NSLOTS * kSlot + 32 * 128 + (size_t)NH * 8192 + 2048 + (5 * NSLOTS + 1) * 8 + 16;
     if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: it allocates all 512 TMEM columns
-    if (smem > 227 * 1024) return 1;
+    if (smem > 227 * 1024) { set_error("%s: shared-memory budget exceeded", name); return -2; }
     static bool configured = false;
     if (!configured) {
         ENERF_CUDA(cudaFuncSetAttribute(k_tc_bwd_rc<NSLOTS, NH, PRO, GD, CH, XA, NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
@@ -1877,79 +1342,115 @@ static int launch_bwd_rc_n(const TmaDesc& tx, const __half* grad, const __half* 
     return 0;
 }
 
-// backward from the network input alone (hidden activations recomputed per tile); 1 = not applicable
+// backward from the network input alone (hidden activations recomputed per tile).
+// Measured on B200 (3.29 M samples).  2-layer nets: 0.255 ms with 3 slots x 4 epilogue warps (0.28 with 2 x 8; 0.33 with 4 slots and
+// the input tile aliased: 96 registers, spills).  3-layer nets: 0.343 ms with 3 slots, input tile aliased onto dead activation
+// buffers (XA); 0.355 with 2 slots x 8 epilogue warps; 0.386 with 2 x 4.  1-layer nets (torch topology sigma-net): 3 slots.
 template <int PRO>
 static int launch_bwd_rc(const __half* grad, const __half* x, const __half* W, __half* grad_inputs, float* dW, uint32_t B, int in_dim, int n_hidden_mm,
                          ProArgs pro, cudaStream_t st, const char* name) {
-    if (in_dim != 32 || (n_hidden_mm != 1 && n_hidden_mm != 2) || (uint64_t)B >= (1ull << 31)) return 1;
+    if (in_dim != 32 || n_hidden_mm < 0 || n_hidden_mm > 2 || (uint64_t)B >= (1ull << 31)) {
+        set_error("%s: recomputation (NULL forward_buffer) takes 32 inputs and 1 to 3 layers", name);
+        return -2;
+    }
     TmaDesc tx;
-    if (!make_tmap_rows(&tx, x, B, 32, kTile)) return 1;
-    // Measured on B200 (3.29 M samples).  2-layer nets: 0.255 ms with 3 slots x 4 epilogue warps (0.28 with 2 x 8; 0.33 with 4 slots and
-    // the input tile aliased: 96 registers, spills).  3-layer nets: 0.343 ms with 3 slots, input tile aliased onto dead activation
-    // buffers (XA); 0.355 with 2 slots x 8 epilogue warps; 0.386 with 2 x 4.  ENERF_TC_RC_MODE overrides for experiments: 1 = 2/3 slots,
-    // one thread per row, own input buffers; 2 = second G tile + early dgrad commit; 3 = two threads per row; 4 = XA everywhere.
-    static int mode = -1;
-    if (mode < 0) {
-        const char* e = getenv("ENERF_TC_RC_MODE");
-        mode = e ? atoi(e) : 0;
+    if (!make_tmap_rows(&tx, x, B, 32, kTile)) { set_error("%s: inputs must be 16-byte aligned (TMA)", name); return -2; }
+    if (n_hidden_mm == 0) {
+        if constexpr (PRO == 0 || PRO == 3) return launch_bwd_rc_n<3, 0, PRO, false>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
+        set_error("%s: a 1-layer network has no fused field prologue", name);
+        return -2;
     }
-    if (mode == 5) {       // two issuing warps
-        if (n_hidden_mm == 1) return launch_bwd_rc_n<3, 1, PRO, false, 1, false, 2>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
-        return launch_bwd_rc_n<3, 2, PRO, false, 1, true, 2>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
-    }
-    if (n_hidden_mm == 1) {
-        if (mode == 4) return launch_bwd_rc_n<4, 1, PRO, false, 1, true>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
-        if (mode == 3) return launch_bwd_rc_n<2, 1, PRO, false, 2, false>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
-        if (mode == 2) return launch_bwd_rc_n<2, 1, PRO, true, 1, false>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
-        return launch_bwd_rc_n<3, 1, PRO, false, 1, false>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
-    }
-    if (mode == 1) return launch_bwd_rc_n<2, 2, PRO, false, 1, false>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
-    if (mode == 2) return launch_bwd_rc_n<2, 2, PRO, true, 1, false>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
-    if (mode == 3) return launch_bwd_rc_n<2, 2, PRO, false, 2, false>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
-    return launch_bwd_rc_n<3, 2, PRO, false, 1, true>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
+    if (n_hidden_mm == 1) return launch_bwd_rc_n<3, 1, PRO, false>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
+    if constexpr (PRO != 3) return launch_bwd_rc_n<3, 2, PRO, true>(tx, grad, W, grad_inputs, dW, B, pro, st, name);
+    set_error("%s: density heads take 1- and 2-layer networks", name);
+    return -2;
 }
 
 int tc_backward(const __half* grad, const __half* x, const __half* W, const __half* fwd_buf, __half* bwd_buf, __half* grad_inputs, float* dW,
                 uint32_t B, int in_dim, int n_hidden_mm, cudaStream_t st) {
     ProArgs none = {nullptr, nullptr, 0, nullptr, nullptr, nullptr};
-    if (!fwd_buf) {
-        const int rc = launch_bwd_rc<0>(grad, x, W, grad_inputs, dW, B, in_dim, n_hidden_mm, none, st, "ffmlp_backward");
-        if (rc == 1) set_error("ffmlp_backward: forward_buffer may only be NULL (recomputation) for 32 inputs and 2 or 3 layers on the tcgen05 path");
-        return rc == 1 ? -2 : rc;
-    }
-    if (!bwd_buf) {
-        const int rc = launch_bwd_tma<0>(grad, x, W, fwd_buf, grad_inputs, dW, B, in_dim, n_hidden_mm, none, st, "ffmlp_backward");
-        if (rc != 1) return rc;
-    }
-    return launch_bwd<0>(grad, x, W, fwd_buf, bwd_buf, grad_inputs, dW, B, in_dim, n_hidden_mm, none, st, "ffmlp_backward");
+    if (!fwd_buf) return launch_bwd_rc<0>(grad, x, W, grad_inputs, dW, B, in_dim, n_hidden_mm, none, st, "ffmlp_backward");
+    return launch_bwd_tma<0>(grad, x, W, fwd_buf, bwd_buf, grad_inputs, dW, B, in_dim, n_hidden_mm, none, st, "ffmlp_backward");
 }
 int tc_backward_rgb(const float* g_rgb, const float* rgb, int n_ch, const __half* cin, const __half* W, const __half* fwd_buf, __half* dcin, float* dW,
                     uint32_t B, int n_hidden_mm, cudaStream_t st) {
     ProArgs p = {g_rgb, rgb, n_ch, nullptr, nullptr, nullptr};
-    if (!fwd_buf) {
-        const int rc = launch_bwd_rc<1>(nullptr, cin, W, dcin, dW, B, 32, n_hidden_mm, p, st, "field_color_backward");
-        if (rc == 1) set_error("field_color_backward: recomputation needs 2 or 3 layers");
-        return rc == 1 ? -2 : rc;
-    }
-    {
-        const int rc = launch_bwd_tma<1>(nullptr, cin, W, fwd_buf, dcin, dW, B, 32, n_hidden_mm, p, st, "field_color_backward");
-        if (rc != 1) return rc;
-    }
-    return launch_bwd<1>(nullptr, cin, W, fwd_buf, nullptr, dcin, dW, B, 32, n_hidden_mm, p, st, "field_color_backward");
+    if (!fwd_buf) return launch_bwd_rc<1>(nullptr, cin, W, dcin, dW, B, 32, n_hidden_mm, p, st, "field_color_backward");
+    return launch_bwd_tma<1>(nullptr, cin, W, fwd_buf, nullptr, dcin, dW, B, 32, n_hidden_mm, p, st, "field_color_backward");
 }
 int tc_backward_sigma(const float* g_sigma, const float* sigma, const __half* dcin, const __half* feat, const __half* W, const __half* fwd_buf,
                       __half* dfeat, float* dW, uint32_t B, int n_hidden_mm, cudaStream_t st) {
     ProArgs p = {nullptr, nullptr, 0, g_sigma, sigma, dcin};
-    if (!fwd_buf) {
-        const int rc = launch_bwd_rc<2>(nullptr, feat, W, dfeat, dW, B, 32, n_hidden_mm, p, st, "field_sigma_backward");
-        if (rc == 1) set_error("field_sigma_backward: recomputation needs 2 or 3 layers");
-        return rc == 1 ? -2 : rc;
+    if (!fwd_buf) return launch_bwd_rc<2>(nullptr, feat, W, dfeat, dW, B, 32, n_hidden_mm, p, st, "field_sigma_backward");
+    return launch_bwd_tma<2>(nullptr, feat, W, fwd_buf, nullptr, dfeat, dW, B, 32, n_hidden_mm, p, st, "field_sigma_backward");
+}
+// density head (always recomputing): g_sigma [B] (may be NULL) and g_h [B,16] fp16 (may be NULL) -> dfeat, dW
+int tc_backward_density(const float* g_sigma, const float* sigma, const __half* g_h, const __half* feat, const __half* W, __half* dfeat, float* dW,
+                        uint32_t B, int n_hidden_mm, cudaStream_t st) {
+    ProArgs p = {nullptr, nullptr, 0, g_sigma, sigma, nullptr};
+    return launch_bwd_rc<3>(g_h, feat, W, dfeat, dW, B, 32, n_hidden_mm, p, st, "field_density_backward");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Colour-net input rows of the torch-topology field (nerf/network.py:171-199): for the samples selected by the `weights > 1e-4`
+// mask, row i = [SH_4(fp16(dir of sample idx[i])) * sh_scale (16) | h[idx[i], 1:16] (15) | 0] — the masked gather `d[mask]`,
+// `geo_feat[mask]`, the SH encoder, `torch.cat` and the 31 -> 32 padding in one pass.  A ray's direction is shared by its
+// `dir_div` consecutive samples (dirs [B / dir_div, 3]); rows n .. n_pad-1 are zero (tile padding).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_color_inputs(const float* __restrict__ dirs, uint32_t dir_div, const __half* __restrict__ h, const int32_t* __restrict__ idx, uint32_t n, uint32_t n_pad,
+               float sh_scale, __half* __restrict__ cin) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    int4* o = reinterpret_cast<int4*>(cin + (size_t)i * 32);
+    if (i >= n) {
+        o[0] = o[1] = o[2] = o[3] = make_int4(0, 0, 0, 0);
+        return;
     }
-    {
-        const int rc = launch_bwd_tma<2>(nullptr, feat, W, fwd_buf, dfeat, dW, B, 32, n_hidden_mm, p, st, "field_sigma_backward");
-        if (rc != 1) return rc;
-    }
-    return launch_bwd<2>(nullptr, feat, W, fwd_buf, nullptr, dfeat, dW, B, 32, n_hidden_mm, p, st, "field_sigma_backward");
+    const uint32_t j = (uint32_t)idx[i];
+    const float* d = dirs + (size_t)(j / dir_div) * 3;
+    float sh[16];
+    sh_deg4(f16_round(__ldg(d)), f16_round(__ldg(d + 1)), f16_round(__ldg(d + 2)), sh);
+    const int4 a = __ldg(reinterpret_cast<const int4*>(h + (size_t)j * 16)), b = __ldg(reinterpret_cast<const int4*>(h + (size_t)j * 16) + 1);
+    const uint32_t w[8] = {(uint32_t)a.x, (uint32_t)a.y, (uint32_t)a.z, (uint32_t)a.w, (uint32_t)b.x, (uint32_t)b.y, (uint32_t)b.z, (uint32_t)b.w};
+    uint32_t p[16];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) p[e] = pack2(sh[2 * e] * sh_scale, sh[2 * e + 1] * sh_scale);
+#pragma unroll
+    for (int e = 0; e < 7; ++e) p[8 + e] = (w[e] >> 16) | (w[e + 1] << 16);      // h[1+2e], h[2+2e]
+    p[15] = w[7] >> 16;                                                          // h[15], 0
+#pragma unroll
+    for (int v = 0; v < 4; ++v) o[v] = make_int4((int)p[4 * v], (int)p[4 * v + 1], (int)p[4 * v + 2], (int)p[4 * v + 3]);
+}
+// backward of the above w.r.t. h: g_h[idx[i], 1:16] = dcin[i, 16:31], g_h[idx[i], 0] = 0 (g_h zero-initialised by the caller)
+__global__ void __launch_bounds__(256)
+k_color_inputs_bwd(const __half* __restrict__ dcin, const int32_t* __restrict__ idx, uint32_t n, __half* __restrict__ g_h) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int4* src = reinterpret_cast<const int4*>(dcin + (size_t)i * 32 + 16);
+    const int4 a = __ldg(src), b = __ldg(src + 1);
+    const uint32_t w[8] = {(uint32_t)a.x, (uint32_t)a.y, (uint32_t)a.z, (uint32_t)a.w, (uint32_t)b.x, (uint32_t)b.y, (uint32_t)b.z, (uint32_t)b.w};
+    uint32_t o[8];
+    o[0] = w[0] << 16;
+#pragma unroll
+    for (int e = 1; e < 8; ++e) o[e] = (w[e - 1] >> 16) | (w[e] << 16);
+    int4* dst = reinterpret_cast<int4*>(g_h + (size_t)idx[i] * 16);
+    dst[0] = make_int4((int)o[0], (int)o[1], (int)o[2], (int)o[3]);
+    dst[1] = make_int4((int)o[4], (int)o[5], (int)o[6], (int)o[7]);
+}
+
+int tc_color_inputs(const float* dirs, uint32_t dir_div, const __half* h, const int32_t* idx, uint32_t n, uint32_t n_pad, float sh_scale, __half* cin,
+                    cudaStream_t st) {
+    if (n_pad == 0) return 0;
+    k_color_inputs<<<ceil_div(n_pad, 256u), 256, 0, st>>>(dirs, dir_div, h, idx, n, n_pad, sh_scale, cin);
+    ENERF_CHECK_LAUNCH("field_color_inputs");
+    return 0;
+}
+int tc_color_inputs_backward(const __half* dcin, const int32_t* idx, uint32_t n, __half* g_h, cudaStream_t st) {
+    if (n == 0) return 0;
+    k_color_inputs_bwd<<<ceil_div(n, 256u), 256, 0, st>>>(dcin, idx, n, g_h);
+    ENERF_CHECK_LAUNCH("field_color_inputs_backward");
+    return 0;
 }
 
 }  // namespace tcm

@@ -7,9 +7,6 @@ traffic and ~20 small kernels per step.
 `fused_field(feat, dirs, w_sigma, w_color, nl_sigma, nl_color, n_ch, training)` ->
 (sigma [S] fp32, rgb [S,n_ch] fp32).  Differentiable in feat, w_sigma, w_color.
 """
-import os
-
-import numpy as np
 import torch
 from torch.autograd import Function
 
@@ -80,125 +77,105 @@ def fused_field(feat, dirs, w_sigma, w_color, nl_sigma, nl_color, n_ch, training
 
 
 # --------------------------------------------------------------------------------------------
-# Encoder + field as ONE autograd node with a pipelined backward.
-#
-# The two halves of the backward have different bottlenecks: the MLP backward kernels are bound by the SM's shared-memory /
-# tensor pipes (persistent, one CTA per SM), the hash-grid scatter by L2 reduction throughput (it needs few SMs).  Run back to
-# back they cost their sum.  Here the samples are cut into chunks; the MLP backward of chunk k+1 runs on the current stream on
-# a capped number of SMs while the scatter of chunk k runs on a second stream on the rest.  Same kernels, same sums (fp32
-# reductions in a different order); CUDA-graph capturable (fork / join through events).
-#
-# Measured on B200 (profiles/r1_30_overlap_probe_two_streams.json, 3.29 M samples): SLOWER than back to back in every setting
-# (1.32 ms -> 1.46 / 1.66 / 1.84 ms with 2 / 4 / 8 chunks; capping the MLP grid makes it worse) — both kernels need all SMs, and an
-# MLP CTA cannot be placed until the scatter CTAs on its SM have drained.  Kept as a tested experiment: ENERF_PIPELINE=1 turns it
-# on (default off); ENERF_PIPELINE_CHUNKS / _MLP_CTAS / _SCATTER_BLOCK.
-PIPELINE = os.environ.get("ENERF_PIPELINE", "0") == "1"
-PIPELINE_CHUNKS = int(os.environ.get("ENERF_PIPELINE_CHUNKS", "4"))
-PIPELINE_MLP_CTAS = int(os.environ.get("ENERF_PIPELINE_MLP_CTAS", "120"))
-PIPELINE_SCATTER_BLOCK = int(os.environ.get("ENERF_PIPELINE_SCATTER_BLOCK", "0"))
-_side_streams = {}
+# The torch-topology field of nerf/network.py:104-199 — what every shipped E-NeRF config runs (ff = False): sigma-net
+# Linear(32,64)-ReLU-Linear(64,16), colour-net Linear(31,64)-ReLU-Linear(64,64)-ReLU-Linear(64,C) on the `weights > 1e-4` samples.
+# Same tcgen05 kernels as the FFMLP path (one hidden-to-hidden matmul fewer per net); the weights are the nn.Linear matrices
+# concatenated in FFMLP order, the colour-net's first matrix padded with a zero 32nd column (its input row is [SH | geo_feat | 0])
+# and its last one with zero rows up to 16.
+def torch_topology_eligible(hidden_dim, num_layers, num_layers_color, in_dim, in_dim_dir, geo_feat_dim, sh_degree, n_ch):
+    return (hidden_dim == 64 and num_layers == 2 and num_layers_color == 3 and in_dim == 32 and in_dim_dir == 16 and geo_feat_dim == 15
+            and sh_degree == 4 and 1 <= n_ch <= 4)
 
 
-def _side_stream(dev):
-    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
-    if key not in _side_streams:
-        _side_streams[key] = torch.cuda.Stream(device=key)
-    return _side_streams[key]
+def flat_sigma_weights(layers):
+    """[Linear(32,64), Linear(64,16)] -> flat [64*32 + 16*64]"""
+    return torch.cat([l.weight.reshape(-1) for l in layers])
 
 
-def encoder_eligible(encoder, x):
-    """hash / tiled grid with D = 3, 16 levels x 2 features (the 32-wide sigma-net input), no input gradients"""
-    return (type(encoder).__name__ == "GridEncoder" and encoder.input_dim == 3 and encoder.level_dim == 2 and encoder.num_levels == 16
-            and x.is_cuda and x.shape[-1] == 3 and not x.requires_grad and x.numel() // 3 % 128 == 0 and x.numel() > 0)
+def flat_color_weights(layers):
+    """[Linear(31,64), Linear(64,64), Linear(64,C)] -> flat [64*32 + 64*64 + 16*64] (zero column / zero rows added)"""
+    w0, w1, w2 = (l.weight for l in layers)
+    w0 = torch.nn.functional.pad(w0, (0, 32 - w0.shape[1]))
+    w2 = torch.nn.functional.pad(w2, (0, 0, 0, 16 - w2.shape[0]))
+    return torch.cat([w0.reshape(-1), w1.reshape(-1), w2.reshape(-1)])
 
 
-def pipelined_backward(g_sigma, g_rgb, sigma, rgb, cin, feat, x, table, offsets, geometry, gridtype, ws, wc, nl_sigma, nl_color, n_ch,
-                       acc_dtype=torch.float32, chunks=None, mlp_ctas=None, scatter_block=None):
-    """colour-net bwd -> sigma-net bwd -> hash-grid scatter over `chunks` sample ranges, the scatter of a range on a second stream
-    while the MLP kernels work on the next one.  Returns (d_table [entries, C] acc_dtype, gw_sigma fp32, gw_color fp32)."""
-    from .backends import gridencoder_backend as GB
-    chunks = PIPELINE_CHUNKS if chunks is None else chunks
-    mlp_ctas = PIPELINE_MLP_CTAS if mlp_ctas is None else mlp_ctas
-    scatter_block = PIPELINE_SCATTER_BLOCK if scatter_block is None else scatter_block
-    S, dev = feat.shape[0], feat.device
-    _, dim, width, levels, log2_scale, base_resolution = geometry
-    step = -(-(S // 128) // max(1, chunks)) * 128
-    n_used = -(-S // step)
-    main, side = torch.cuda.current_stream(dev), _side_stream(dev)
-    d_table = torch.zeros(table.shape, dtype=acc_dtype, device=dev)
-    dcin = torch.empty(S, 32, dtype=torch.float16, device=dev)
-    dfeat = torch.empty(S, 32, dtype=torch.float16, device=dev)
-    gw_c = torch.empty(n_used, wc.numel(), dtype=torch.float32, device=dev)
-    gw_s = torch.empty(n_used, ws.numel(), dtype=torch.float32, device=dev)
-    dummy = table.new_zeros(1)
-    fork = torch.cuda.Event()
-    fork.record(main)
-    side.wait_event(fork)
-    _lib.call("enerf_ffmlp_set_max_ctas", mlp_ctas)
-    _lib.call("enerf_grid_set_backward_block", scatter_block)
-    try:
-        for k in range(n_used):
-            lo, hi = k * step, min(S, (k + 1) * step)
-            n = hi - lo
-            _lib.call("enerf_field_color_backward", ptr(g_rgb[lo:hi]), ptr(rgb[lo:hi]), n_ch, ptr(cin[lo:hi]), ptr(wc), None, n, nl_color,
-                      ptr(dcin[lo:hi]), ptr(gw_c[k]), stream())
-            _lib.call("enerf_field_sigma_backward", ptr(g_sigma[lo:hi]), ptr(sigma[lo:hi]), ptr(dcin[lo:hi]), ptr(feat[lo:hi]), ptr(ws), None, n,
-                      nl_sigma, ptr(dfeat[lo:hi]), ptr(gw_s[k]), stream())
-            ready = torch.cuda.Event()
-            ready.record(main)
-            side.wait_event(ready)
-            with torch.cuda.stream(side):
-                GB.grid_encode_backward(dfeat[lo:hi], x[lo:hi], table, offsets, d_table, n, dim, width, levels, log2_scale, base_resolution,
-                                        False, dummy, dummy, gridtype, 1)
-    finally:
-        _lib.call("enerf_ffmlp_set_max_ctas", 0)
-        _lib.call("enerf_grid_set_backward_block", 0)
-    join = torch.cuda.Event()
-    join.record(side)
-    main.wait_event(join)
-    return d_table, gw_s.sum(0), gw_c.sum(0)
-
-
-class _EncodedField(Function):
-    """hash-grid gather + fused field (forward identical to `grid_encode` followed by `fused_field`); backward pipelined."""
+class _Density(Function):
+    """feat [B,32] fp16, flat sigma-net weights -> sigma [B] fp32 (= trunc_exp(h[0])), h [B,16] fp16 (geo_feat = h[:,1:])."""
 
     @staticmethod
-    def forward(ctx, x, dirs, embeddings, offsets, per_level_scale, base_resolution, gridtype, w_sigma, w_color, nl_sigma, nl_color, n_ch,
-                training):
-        from .backends import gridencoder_backend as GB
-        from .gridencoder.grid import _half_table
-        x = x.contiguous().float()
-        S, dev = x.shape[0], x.device
-        table = (embeddings.detach() if embeddings.dtype == torch.half else _half_table(embeddings)).contiguous()
-        levels, width = offsets.shape[0] - 1, embeddings.shape[1]
-        geometry = (S, 3, width, levels, np.log2(per_level_scale), base_resolution)
-        feat = table.new_empty(S, levels * width)
-        GB.grid_encode_forward(x, table, offsets, feat, *geometry, False, table.new_empty(1), gridtype, 1)
-        dirs = dirs.contiguous().float()
-        ws, wc = w_sigma.detach().half().contiguous(), w_color.detach().half().contiguous()
-        sigma = torch.empty(S, dtype=torch.float32, device=dev)
-        cin = torch.empty(S, 32, dtype=torch.float16, device=dev)
-        rgb = torch.empty(S, n_ch, dtype=torch.float32, device=dev)
-        _lib.call("enerf_field_sigma_forward", ptr(feat), ptr(ws), ptr(dirs), S, nl_sigma, None, ptr(sigma), ptr(cin), stream())
-        _lib.call("enerf_field_color_forward", ptr(cin), ptr(wc), S, nl_color, n_ch, None, ptr(rgb), stream())
-        if training:
-            ctx.save_for_backward(x, table, offsets, feat, ws, wc, sigma, cin, rgb)
-            ctx.meta = (geometry, gridtype, nl_sigma, nl_color, n_ch, embeddings.dtype, w_sigma.dtype, w_color.dtype)
-        return sigma, rgb
+    def forward(ctx, feat, w_sigma, num_layers):
+        B = feat.shape[0]
+        feat = feat.contiguous()
+        ws = w_sigma.detach().half().contiguous()
+        sigma = torch.empty(B, dtype=torch.float32, device=feat.device)
+        h = torch.empty(B, 16, dtype=torch.float16, device=feat.device)
+        _lib.call("enerf_field_density_forward", ptr(feat), ptr(ws), B, num_layers, ptr(sigma), ptr(h), stream())
+        ctx.save_for_backward(feat, ws, sigma)
+        ctx.meta = (num_layers, w_sigma.dtype)
+        return sigma, h
 
     @staticmethod
-    def backward(ctx, g_sigma, g_rgb):
-        x, table, offsets, feat, ws, wc, sigma, cin, rgb = ctx.saved_tensors
-        geometry, gridtype, nl_sigma, nl_color, n_ch, dt_e, dt_s, dt_c = ctx.meta
-        g_sigma = torch.zeros_like(sigma) if g_sigma is None else g_sigma.contiguous().float()
-        g_rgb = torch.zeros_like(rgb) if g_rgb is None else g_rgb.contiguous().float()
-        acc_dtype = table.dtype if os.environ.get('ENERF_GRID_GRAD_FP16', '0') == '1' else torch.float32
-        d_table, gw_s, gw_c = pipelined_backward(g_sigma, g_rgb, sigma, rgb, cin, feat, x, table, offsets, geometry, gridtype, ws, wc,
-                                                 nl_sigma, nl_color, n_ch, acc_dtype)
-        return (None, None, d_table.to(dt_e), None, None, None, None, gw_s.to(dt_s), gw_c.to(dt_c), None, None, None, None)
+    def backward(ctx, g_sigma, g_h):
+        feat, ws, sigma = ctx.saved_tensors
+        num_layers, dt = ctx.meta
+        B = feat.shape[0]
+        g_sigma = None if g_sigma is None else g_sigma.contiguous().float()
+        g_h = None if g_h is None else g_h.contiguous().half()
+        dfeat = torch.empty_like(feat)
+        gw = torch.empty(ws.numel(), dtype=torch.float32, device=feat.device)
+        _lib.call("enerf_field_density_backward", ptr(g_sigma), ptr(sigma), ptr(g_h), ptr(feat), ptr(ws), B, num_layers, ptr(dfeat), ptr(gw), stream())
+        return dfeat, gw.to(dt), None
 
 
-def encoded_field(x_unit, dirs, encoder, w_sigma, w_color, nl_sigma, nl_color, n_ch, training):
-    """x_unit [S,3] in [0,1] -> (sigma [S] fp32, rgb [S,n_ch] fp32); differentiable in the table and both weight vectors."""
-    return _EncodedField.apply(x_unit, dirs, encoder.embeddings, encoder.offsets, encoder.per_level_scale, encoder.base_resolution,
-                               encoder.gridtype_id, w_sigma, w_color, nl_sigma, nl_color, n_ch, training)
+def density_head(feat, w_sigma, num_layers=1):
+    return _Density.apply(feat, w_sigma, num_layers)
+
+
+def density_only(feat, w_sigma, num_layers):
+    """sigma [B] fp32 alone (no gradient): the occupancy-grid refresh"""
+    B = feat.shape[0]
+    sigma = torch.empty(B, dtype=torch.float32, device=feat.device)
+    _lib.call("enerf_field_density_forward", ptr(feat.contiguous()), ptr(w_sigma.detach().half().contiguous()), B, num_layers, ptr(sigma), None, stream())
+    return sigma
+
+
+class _MaskedColor(Function):
+    """h [B,16] fp16, dirs [B/dir_div,3] fp32, idx [n] int32 (selected samples, increasing), flat colour-net weights ->
+    rgbs [B,n_ch] fp32 with sigmoid(colour-net) on the selected rows and zeros elsewhere (network.py:171-199)."""
+
+    @staticmethod
+    def forward(ctx, h, dirs, dir_div, idx, w_color, n_ch, sh_scale):
+        B, n = h.shape[0], idx.shape[0]
+        dev = h.device
+        n_pad = -(-n // 128) * 128
+        h = h.contiguous()
+        wc = w_color.detach().half().contiguous()
+        cin = torch.empty(n_pad, 32, dtype=torch.float16, device=dev)
+        _lib.call("enerf_field_color_inputs", ptr(dirs), dir_div, ptr(h), ptr(idx), n, n_pad, float(sh_scale), ptr(cin), stream())
+        rgb_c = torch.empty(n_pad, n_ch, dtype=torch.float32, device=dev)
+        _lib.call("enerf_field_color_forward", ptr(cin), ptr(wc), n_pad, 2, n_ch, None, ptr(rgb_c), stream())
+        rgbs = torch.zeros(B, n_ch, dtype=torch.float32, device=dev)
+        _lib.call("enerf_scatter_rows", ptr(rgb_c), ptr(idx), n, 4 * n_ch, ptr(rgbs), stream())
+        ctx.save_for_backward(cin, wc, rgb_c, idx)
+        ctx.meta = (B, n, n_pad, n_ch, w_color.dtype)
+        return rgbs
+
+    @staticmethod
+    def backward(ctx, g_rgbs):
+        cin, wc, rgb_c, idx = ctx.saved_tensors
+        B, n, n_pad, n_ch, dt = ctx.meta
+        dev = cin.device
+        g_rgbs = g_rgbs.contiguous().float()
+        g_c = torch.empty(n_pad, n_ch, dtype=torch.float32, device=dev)
+        _lib.call("enerf_gather_rows", ptr(g_rgbs), ptr(idx), n, n_pad, 4 * n_ch, ptr(g_c), stream())
+        dcin = torch.empty(n_pad, 32, dtype=torch.float16, device=dev)
+        gw = torch.empty(wc.numel(), dtype=torch.float32, device=dev)
+        _lib.call("enerf_field_color_backward", ptr(g_c), ptr(rgb_c), n_ch, ptr(cin), ptr(wc), None, n_pad, 2, ptr(dcin), ptr(gw), stream())
+        g_h = torch.zeros(B, 16, dtype=torch.float16, device=dev)
+        _lib.call("enerf_field_color_inputs_backward", ptr(dcin), ptr(idx), n, ptr(g_h), stream())
+        return g_h, None, None, None, gw.to(dt), None, None
+
+
+def masked_color(h, dirs, dir_div, idx, w_color, n_ch, sh_scale=1.0):
+    return _MaskedColor.apply(h, dirs.contiguous().float(), int(dir_div), idx, w_color, int(n_ch), float(sh_scale))

@@ -52,11 +52,6 @@ class NeRFNetwork(NeRFRenderer):
             shapes = (self.hidden_dim, self.hidden_dim_color, self.in_dim, self.in_dim_color, self.geo_feat_dim,
                       getattr(self.encoder_dir, 'degree', -1), self.out_dim_color, self.sigma_net.activation)
             training = self.training and torch.is_grad_enabled()
-            if (field.PIPELINE and training and field.shapes_eligible(*shapes) and field.encoder_eligible(self.encoder, x)
-                    and d.shape[0] == x.shape[0]):
-                # encoder + field as one autograd node: its backward overlaps the hash-grid scatter with the MLP backward
-                return field.encoded_field((x + self.bound) / (2 * self.bound), d, self.encoder, self.sigma_net.weights, self.color_net.weights,
-                                           self.num_layers, self.num_layers_color, self.out_dim_color, True)
             feat = self.encoder(x, bound=self.bound)
             if field.eligible(feat, d, *shapes):
                 return field.fused_field(feat, d, self.sigma_net.weights, self.color_net.weights, self.num_layers, self.num_layers_color,
@@ -70,6 +65,16 @@ class NeRFNetwork(NeRFRenderer):
     def density(self, x):
         sigma, geo_feat = self._sigma_head(x)
         return {'sigma': sigma, 'geo_feat': geo_feat}
+
+    def _grid_density(self, xyzs):
+        """density alone for the occupancy-grid refresh: gather + sigma-net with the exp head, nothing else written (the generic
+        path would store forward_buffer — 1.6 GB for the 6.3 M cells of a bound-3 grid — because the module is in training mode)"""
+        if (torch.is_autocast_enabled('cuda') and xyzs.is_cuda and xyzs.shape[0] % 128 == 0 and self.hidden_dim == 64 and self.in_dim == 32
+                and self.num_layers == 2 and self.geo_feat_dim == 15 and self.sigma_net.activation == 0):
+            feat = self.encoder(xyzs, bound=self.bound)
+            if feat.dtype == torch.float16:
+                return field.density_only(feat, self.sigma_net.weights, 2)
+        return super()._grid_density(xyzs)
 
     def color(self, x, d, mask=None, geo_feat=None, **kwargs):
         """Colour query for the rows selected by `mask` (all rows without one); unselected rows stay zero (network_ff.py:92-133)."""

@@ -146,9 +146,14 @@ class NeRFRenderer(nn.Module):
         dirs = rays_d.view(-1, 1, 3).expand_as(xyzs)
         for k, v in density_outputs.items():
             density_outputs[k] = v.view(-1, v.shape[-1])
-        rgbs = self.color(xyzs.reshape(-1, 3), dirs.reshape(-1, 3), mask=mask.reshape(-1), **density_outputs)
+        # a field that says so gets the per-ray directions as the broadcast [N,T,3] view (stride 0 over T) instead of a materialised copy
+        flat_dirs = dirs if getattr(self, 'accepts_ray_dirs', False) else dirs.reshape(-1, 3)
+        rgbs = self.color(xyzs.reshape(-1, 3), flat_dirs, mask=mask.reshape(-1), **density_outputs)
         rgbs = rgbs.view(N, -1, n_ch)
-        image = torch.sum(weights.unsqueeze(-1) * rgbs, dim=-2)
+        if rgbs.is_cuda and 1 <= n_ch <= 4:
+            image = raymarching.weighted_sum(weights, rgbs)                 # sum_t w * rgb, one warp per ray
+        else:
+            image = torch.sum(weights.unsqueeze(-1) * rgbs, dim=-2)
 
         if self.bg_radius > 0:
             polar = raymarching.polar_from_ray(rays_o, rays_d, self.bg_radius)
@@ -232,76 +237,107 @@ class NeRFRenderer(nn.Module):
         return {'depth': depth.view(*prefix), 'image': image.view(*prefix, image.shape[-1])}
 
     # ------------------------------------------------------------------ occupancy-grid maintenance
-    def _cell_centres(self, coords, cas):
-        """world position of density-grid cells `coords` int [n,3] in cascade `cas` (renderer.py:499-506)"""
-        bound = min(2 ** cas, self.bound)
-        half_grid_size = bound / self.grid_size
-        xyzs = 2 * coords.float() / (self.grid_size - 1) - 1
-        return xyzs * (bound - half_grid_size), half_grid_size
+    # renderer.py:408-563 as a handful of kernels (csrc/occupancy.cu), no host synchronisation besides `mean_count`
+    @property
+    def mean_density(self):
+        """mean of clamp(density_grid, 0) after the last refresh (renderer.py:550).  Kept on the device by `update_extra_state`
+        (the threshold min(mean, density_thresh) is taken there); reading the attribute fetches it."""
+        dev_val = self.__dict__.get('_mean_density_dev')
+        if dev_val is not None:
+            self.__dict__['_mean_density'] = float(dev_val.item())
+            self.__dict__['_mean_density_dev'] = None
+        return self.__dict__.get('_mean_density', 0)
 
-    def _grid_blocks(self, S):
-        """Cells of the 128^3 occupancy grid in S^3 blocks: yields (integer coords [n,3], Morton indices [n])."""
+    @mean_density.setter
+    def mean_density(self, value):
+        self.__dict__['_mean_density'] = value
+        self.__dict__['_mean_density_dev'] = None
+
+    def _occ_scratch(self):
         dev = self.density_grid.device
-        axis = torch.arange(self.grid_size, dtype=torch.int32, device=dev).split(S)
-        for xs in axis:
-            for ys in axis:
-                for zs in axis:
-                    coords = torch.stack([g.reshape(-1) for g in custom_meshgrid(xs, ys, zs)], dim=-1)
-                    yield coords, raymarching.morton3D(coords).long()
+        sc = self.__dict__.get('_occ_sc')
+        cells = self.grid_size ** 3
+        if sc is None or sc['owner'].device != dev or sc['owner'].numel() != self.cascade * cells:
+            sc = {
+                'owner': torch.full((self.cascade * cells,), -1, dtype=torch.int32, device=dev),
+                'sum': torch.zeros(1, dtype=torch.float64, device=dev),
+                'mean': torch.zeros(1, dtype=torch.float32, device=dev),
+                'occ_list': torch.empty(self.cascade, cells, dtype=torch.int32, device=dev),
+                'occ_count': torch.zeros(self.cascade, dtype=torch.int32, device=dev),
+                'blocks': torch.empty(-(-cells // 4096) + 1, dtype=torch.int32, device=dev),
+            }
+            self.__dict__['_occ_sc'] = sc
+        return sc
+
+    def _grid_density(self, xyzs):
+        """sigma [n] fp32 at world positions xyzs [n,3] for the occupancy refresh; subclasses override it with a density-only kernel"""
+        return self.density(xyzs)['sigma'].reshape(-1).detach().float()
 
     @torch.no_grad()
     def mark_untrained_grid(self, poses, intrinsic, S=64):
-        """Cells that no training camera sees keep density -1 forever (renderer.py:408-471)."""
+        """Cells that no training camera sees keep density -1 forever (renderer.py:408-471): one kernel, a thread per cell."""
         if not self.cuda_ray:
             return
-        poses = torch.as_tensor(poses).to(self.density_grid.device)
-        fx, fy, cx, cy = intrinsic
-        seen_by = torch.zeros_like(self.density_grid)
-        for coords, indices in self._grid_blocks(S):
-            for cas in range(self.cascade):
-                world, half_cell = self._cell_centres(coords, cas)
-                for first in range(0, poses.shape[0], S):
-                    cams = poses[first:first + S]
-                    local = (world.unsqueeze(0) - cams[:, :3, 3].unsqueeze(1)) @ cams[:, :3, :3]       # world -> camera frame
-                    depth = local[..., 2]
-                    inside = (depth > 0) & (local[..., 0].abs() < cx / fx * depth + half_cell * 2) \
-                        & (local[..., 1].abs() < cy / fy * depth + half_cell * 2)
-                    seen_by[cas, indices] += inside.sum(0).to(seen_by.dtype)
-        self.density_grid[seen_by == 0] = -1
+        from .. import _lib
+        dev = self.density_grid.device
+        _lib.need_cuda(self.density_grid)
+        poses = torch.as_tensor(poses).to(device=dev, dtype=torch.float32).contiguous()
+        if poses.dim() != 3 or poses.shape[1:] != (4, 4):
+            raise RuntimeError("mark_untrained_grid: poses must be [B, 4, 4] camera-to-world matrices")
+        fx, fy, cx, cy = (float(v) for v in intrinsic)
+        _lib.call("enerf_mark_untrained_grid", _lib.ptr(self.density_grid), _lib.ptr(poses), poses.shape[0], fx, fy, cx, cy, self.cascade,
+                  self.grid_size, float(self.bound), _lib.stream())
 
     @torch.no_grad()
-    def update_extra_state(self, decay=0.95, S=128):
-        """EMA-max refresh of density_grid, its bitfield and the mean sample count (renderer.py:474-563)."""
+    def update_extra_state(self, decay=0.95, S=128, _draws=None):
+        """EMA-max refresh of density_grid, its bitfield and the mean sample count (renderer.py:474-563).
+
+        First 16 calls: every cell of every cascade; afterwards a quarter of the cells at random plus as many drawn from the
+        occupied ones.  Query positions are generated on the device in grid order, the density comes from `_grid_density`, the
+        EMA / mean / threshold / bitfield from one update + one packing kernel.  `_draws` (tests): dict with the uniform variates
+        `noise` [n,3] and, for the partial branch, `rand_coords` [C,n_pick,3] / `rand_occ` [C,n_pick] that replace the in-kernel RNG."""
         if not self.cuda_ray:
             return
+        from .. import _lib
+        ptr = _lib.ptr
         dev = self.density_grid.device
-        fresh = torch.full_like(self.density_grid, -1.0)
+        _lib.need_cuda(self.density_grid)
+        C, H = self.cascade, self.grid_size
+        cells = H ** 3
+        sc = self._occ_scratch()
+        draws = _draws or {}
+        noise = draws.get('noise')
+        noise = None if noise is None else noise.to(device=dev, dtype=torch.float32).contiguous()
+        # the jitter seed comes from torch's CPU generator: no device sync, reproducible under torch.manual_seed, and identical on every
+        # rank of a data-parallel job that seeded identically (replicated grids stay bit-identical without a broadcast)
+        seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+        scale = float(self.density_scale * 0.003383)          # density * nominal step length (renderer.py:512)
+        if self.density_bitfield.device != dev:
+            self.density_bitfield = self.density_bitfield.to(dev)
 
-        def sample_density(coords, cas):
-            centres, half_cell = self._cell_centres(coords, cas)
-            jittered = centres + (torch.rand_like(centres) * 2 - 1) * half_cell
-            sigma = self.density(jittered)['sigma'].reshape(-1).detach().float()
-            return sigma * (self.density_scale * 0.003383)          # density * nominal step length (renderer.py:512)
-
-        if self.iter_density < 16:                                   # first 16 refreshes: every cell of every cascade
-            for coords, indices in self._grid_blocks(S):
-                for cas in range(self.cascade):
-                    fresh[cas, indices] = sample_density(coords, cas)
-        else:                                                        # afterwards: a quarter of the cells at random + as many occupied ones
-            n_pick = self.grid_size ** 3 // 4
-            for cas in range(self.cascade):
-                rand_coords = torch.randint(0, self.grid_size, (n_pick, 3), device=dev)
-                rand_idx = raymarching.morton3D(rand_coords).long()
-                occupied = torch.nonzero(self.density_grid[cas] > 0).squeeze(-1)
-                occ_idx = occupied[torch.randint(0, occupied.shape[0], [n_pick], dtype=torch.long, device=dev)]
-                occ_coords = raymarching.morton3D_invert(occ_idx)
-                fresh[cas, torch.cat([rand_idx, occ_idx])] = sample_density(torch.cat([rand_coords, occ_coords]), cas)
-
-        both = (self.density_grid >= 0) & (fresh >= 0)
-        self.density_grid[both] = torch.maximum(self.density_grid[both] * decay, fresh[both])
-        self.mean_density = torch.mean(self.density_grid.clamp(min=0)).item()
+        if self.iter_density < 16:
+            xyzs = torch.empty(C * cells, 3, dtype=torch.float32, device=dev)
+            _lib.call("enerf_occ_points_full", ptr(xyzs), C, H, float(self.bound), ptr(noise), seed, _lib.stream())
+            sigmas = self._grid_density(xyzs).contiguous()
+            _lib.call("enerf_occ_update", ptr(self.density_grid), ptr(sigmas), None, 0, C, H, float(decay), scale, float(self.density_thresh),
+                      ptr(sc['owner']), ptr(sc['sum']), ptr(self.density_bitfield), ptr(sc['mean']), _lib.stream())
+        else:
+            n_pick = cells // 4
+            for cas in range(C):
+                _lib.call("enerf_compact_greater", ptr(self.density_grid[cas]), 0.0, cells, ptr(sc['occ_list'][cas]), ptr(sc['occ_count'][cas:]),
+                          ptr(sc['blocks']), _lib.stream())
+            rc, ro = draws.get('rand_coords'), draws.get('rand_occ')
+            rc = None if rc is None else rc.to(device=dev, dtype=torch.int32).contiguous()
+            ro = None if ro is None else ro.to(device=dev, dtype=torch.int32).contiguous()
+            xyzs = torch.empty(C * 2 * n_pick, 3, dtype=torch.float32, device=dev)
+            indices = torch.empty(C * 2 * n_pick, dtype=torch.int32, device=dev)
+            _lib.call("enerf_occ_points_partial", ptr(xyzs), ptr(indices), n_pick, C, H, float(self.bound), ptr(sc['occ_list']),
+                      ptr(sc['occ_count']), ptr(rc), ptr(ro), ptr(noise), seed, _lib.stream())
+            sigmas = self._grid_density(xyzs).contiguous()
+            _lib.call("enerf_occ_update", ptr(self.density_grid), ptr(sigmas), ptr(indices), 2 * n_pick, C, H, float(decay), scale,
+                      float(self.density_thresh), ptr(sc['owner']), ptr(sc['sum']), ptr(self.density_bitfield), ptr(sc['mean']), _lib.stream())
+        self.__dict__['_mean_density_dev'] = sc['mean'].clone()
         self.iter_density += 1
-        self.density_bitfield = raymarching.packbits(self.density_grid, min(self.mean_density, self.density_thresh), self.density_bitfield)
 
         counted = min(16, self.local_step)
         if counted > 0:

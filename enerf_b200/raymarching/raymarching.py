@@ -270,3 +270,53 @@ class _composite_uniform(Function):
 
 
 composite_uniform = _composite_uniform.apply
+
+
+# ---------------------------------------------------------------------------- run(): image = sum_t w * rgb
+class _weighted_sum(Function):
+    """image [N,C] = sum_t weights [N,T] * rgbs [N,T,C] (renderer.py:255), one warp per ray; differentiable in both."""
+
+    @staticmethod
+    @_fwd32
+    def forward(ctx, weights, rgbs):
+        from .. import _lib
+        weights, rgbs = weights.contiguous(), rgbs.contiguous()
+        _lib.need_cuda(weights, rgbs)
+        N, T = weights.shape
+        n_ch = rgbs.shape[-1]
+        image = torch.empty(N, n_ch, dtype=torch.float32, device=weights.device)
+        _lib.call("enerf_weighted_sum_forward", _lib.ptr(weights), _lib.ptr(rgbs), N, T, n_ch, _lib.ptr(image), _lib.stream())
+        ctx.save_for_backward(weights, rgbs)
+        return image
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, grad_image):
+        from .. import _lib
+        weights, rgbs = ctx.saved_tensors
+        N, T = weights.shape
+        n_ch = rgbs.shape[-1]
+        g = grad_image.contiguous().float()
+        gw = torch.empty_like(weights) if ctx.needs_input_grad[0] else None
+        gr = torch.empty_like(rgbs) if ctx.needs_input_grad[1] else None
+        _lib.call("enerf_weighted_sum_backward", _lib.ptr(g), _lib.ptr(weights), _lib.ptr(rgbs), N, T, n_ch, _lib.ptr(gw), _lib.ptr(gr), _lib.stream())
+        return gw, gr
+
+
+weighted_sum = _weighted_sum.apply
+
+
+def compact_mask(mask):
+    """Indices (int32, increasing) of the True entries of a flat bool tensor and their count — `torch.nonzero(mask)` as three small
+    kernels; the count is read back once (the reference's `x[mask]` synchronises the same way, network.py:180-183)."""
+    from .. import _lib
+    mask = mask.contiguous().view(-1)
+    _lib.need_cuda(mask)
+    n = mask.shape[0]
+    dev = mask.device
+    idx = torch.empty(n, dtype=torch.int32, device=dev)
+    count = torch.empty(1, dtype=torch.int32, device=dev)
+    blocks = torch.empty(-(-n // 4096) + 1, dtype=torch.int32, device=dev)
+    _lib.call("enerf_compact_mask", _lib.ptr(mask.view(torch.uint8)), n, _lib.ptr(idx), _lib.ptr(count), _lib.ptr(blocks), _lib.stream())
+    k = int(count.item())
+    return idx[:k], k

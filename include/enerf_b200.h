@@ -163,7 +163,7 @@ int enerf_ffmlp_inference(const uint16_t* inputs, const uint16_t* weights, uint3
                           uint32_t num_layers, uint32_t activation, uint32_t output_activation,
                           uint16_t* inference_buffer, uint16_t* outputs, void* stream);
 /* ffmlp.h:11 ffmlp_backward; ffmlp.cu:742-894.  backward_buffer [num_layers,B,hidden] may be
- * NULL (the activation gradients then never leave the SM).  forward_buffer may be NULL for 32-input,
+ * NULL on the tcgen05 path (the activation gradients then never leave the SM; when given it is filled as the reference does).  forward_buffer may be NULL for 32-input,
  * 64-wide ReLU networks with 2 or 3 layers: the kernel then recomputes the hidden activations of each
  * 128-sample tile from `inputs` (bit-identical to the stored ones) instead of reading them from HBM.  grad_weights: fp16 when
  * grad_weights_dtype == ENERF_F16 (reference), fp32 flat buffer when ENERF_F32; it is
@@ -180,9 +180,9 @@ int enerf_ffmlp_backward(const uint16_t* grad, const uint16_t* inputs, const uin
  * are fused into the backward kernel here, so these only validate their argument. */
 int enerf_allocate_splitk(uint64_t size);
 /* Kernel-family selector (no reference counterpart): 0 = automatic — the tcgen05/TMEM kernels for
- * 64-wide ReLU networks with input_dim <= 64 (backward operands staged by TMA), the mma.sync kernels
- * otherwise; 1 = always the generic mma.sync kernels; 2 = tcgen05 kernels with per-thread operand loads
- * instead of TMA (used by the parity tests to cross-check the families). */
+ * E-NeRF's own shapes (32 inputs, 64 wide, ReLU, 2 or 3 layers; operands staged by TMA), the mma.sync
+ * kernels otherwise; 1 = always the generic mma.sync kernels (used by the parity tests to cross-check
+ * the two families). */
 int enerf_ffmlp_set_path(int path);
 /* Cap on the persistent grid of the tcgen05 kernels (no reference counterpart): n CTAs instead of one
  * per SM (148); 0 restores the default.  Used by the pipelined backward (enerf_b200/field.py), which
@@ -217,6 +217,63 @@ int enerf_field_sigma_backward(const float* grad_sigma, const float* sigma, cons
                                uint32_t B, uint32_t num_layers, uint16_t* grad_feat, float* grad_weights,
                                void* stream);
 
+
+/* The torch-topology field of nerf/network.py:104-199 (what every shipped E-NeRF config runs: sigma-net Linear(32,64)-ReLU-
+ * Linear(64,16), colour-net Linear(31,64)-ReLU-Linear(64,64)-ReLU-Linear(64,C), no bias) on the same tcgen05 kernels.
+ * Weights are the nn.Linear matrices ([out,in] row-major) concatenated in FFMLP order, the colour-net's first matrix padded with a
+ * zero 32nd column and its last one with zero rows up to 16.
+ *   density forward : h = fp16(sigma_net(feat)) [B,16]; sigma = exp(h[0]) (trunc_exp); geo_feat = h[1:16].  num_layers = 1 for
+ *                     nerf/network.py (2 matmuls), 2 for the FFMLP sigma-net (used by the occupancy-grid refresh).  h may be NULL.
+ *   density backward: dL/dh[0] += grad_sigma * exp(clamp(h0, -15, 15)) (activation.py:15-18); hidden activations are recomputed per
+ *                     tile; grad_sigma / grad_h may be NULL (= zero); grad_weights fp32, overwritten.
+ *   colour inputs   : rows of the samples idx[0..n) (the `weights > 1e-4` mask of renderer.py:236, compacted): [SH_4(fp16(dir)) *
+ *                     sh_scale | h[idx,1:16] | 0], dirs [B/dir_div,3] (one direction per dir_div consecutive samples), rows n..n_pad
+ *                     zero; then enerf_field_color_forward / _backward with num_layers = 2 run the colour-net on the compact batch.
+ *   colour inputs backward: grad_h[idx[i],1:16] = grad_cin[i,16:31] (grad_h [B,16] zero-initialised by the caller). */
+int enerf_field_density_forward(const uint16_t* feat, const uint16_t* weights, uint32_t B, uint32_t num_layers, float* sigma,
+                                uint16_t* h, void* stream);
+int enerf_field_density_backward(const float* grad_sigma, const float* sigma, const uint16_t* grad_h, const uint16_t* feat,
+                                 const uint16_t* weights, uint32_t B, uint32_t num_layers, uint16_t* grad_feat,
+                                 float* grad_weights, void* stream);
+int enerf_field_color_inputs(const float* dirs, uint32_t dir_div, const uint16_t* h, const int32_t* idx, uint32_t n,
+                             uint32_t n_pad, float sh_scale, uint16_t* cin, void* stream);
+int enerf_field_color_inputs_backward(const uint16_t* grad_cin, const int32_t* idx, uint32_t n, uint16_t* grad_h, void* stream);
+/* Order-preserving compaction: indices[0..count) = { i < n : values[i] > thresh } in increasing order, count[0] = how many —
+ * `torch.nonzero(values > thresh)` (renderer.py:236-242 mask, :523 occupied cells) without the host round trip.
+ * scratch: int32 [ceil(n/4096)].  indices may be NULL (count only). */
+int enerf_compact_greater(const float* values, float thresh, uint32_t n, int32_t* indices, int32_t* count, int32_t* scratch,
+                          void* stream);
+/* the same for a byte mask (a torch.bool tensor): { i : mask[i] != 0 } */
+int enerf_compact_mask(const uint8_t* mask, uint32_t n, int32_t* indices, int32_t* count, int32_t* scratch, void* stream);
+/* dst[i] = src[idx[i]] for i < n, zero rows for n <= i < n_pad / dst[idx[i]] = src[i]; rows of row_bytes (multiple of 4). */
+int enerf_gather_rows(const void* src, const int32_t* idx, uint32_t n, uint32_t n_pad, uint32_t row_bytes, void* dst, void* stream);
+int enerf_scatter_rows(const void* src, const int32_t* idx, uint32_t n, uint32_t row_bytes, void* dst, void* stream);
+/* image[n,c] = sum_t weights[n,t] * rgbs[n,t,c] (renderer.py:255) and its backward (grad_weights / grad_rgbs may be NULL). */
+int enerf_weighted_sum_forward(const float* weights, const float* rgbs, uint32_t N, uint32_t T, uint32_t n_ch, float* image,
+                               void* stream);
+int enerf_weighted_sum_backward(const float* grad_image, const float* weights, const float* rgbs, uint32_t N, uint32_t T,
+                                uint32_t n_ch, float* grad_weights, float* grad_rgbs, void* stream);
+
+/* Occupancy-grid maintenance, nerf/renderer.py:408-563, without host synchronisation.
+ *   occ_points_full   : jittered query position of EVERY cell, sample t = cascade*H^3 + Morton index (renderer.py:485-515).
+ *   occ_points_partial: per cascade n_pick uniformly random cells + n_pick cells drawn from the occupied ones (renderer.py:517-545);
+ *                       occ_list [C,H^3] / occ_count [C] from enerf_compact_greater(density_grid[c], 0); indices [C*2*n_pick] out.
+ *                       noise ([n,3] uniform variates), rand_coords [C,n_pick,3], rand_occ [C,n_pick]: scripted draws for the parity
+ *                       tests; NULL = in-kernel PCG32 streams keyed by (seed, sample).
+ *   occ_update        : grid = max(grid*decay, sigma*scale) where both >= 0 (renderer.py:548-549), duplicates resolved "last sample
+ *                       wins"; mean of clamp(grid,0) -> *mean_density; bitfield = grid > min(mean, density_thresh) (renderer.py:550-555).
+ *                       indices == NULL: full refresh (sigmas [C*H^3] in cell order).  owner: int32 [C*H^3] scratch holding -1 (left so);
+ *                       sum: double scratch.
+ *   mark_untrained_grid: density -1 for cells outside every camera frustum, poses [B,4,4] cam-to-world (renderer.py:408-471). */
+int enerf_occ_points_full(float* xyzs, uint32_t C, uint32_t H, float bound, const float* noise, uint64_t seed, void* stream);
+int enerf_occ_points_partial(float* xyzs, int32_t* indices, uint32_t n_pick, uint32_t C, uint32_t H, float bound,
+                             const int32_t* occ_list, const int32_t* occ_count, const int32_t* rand_coords,
+                             const int32_t* rand_occ, const float* noise, uint64_t seed, void* stream);
+int enerf_occ_update(float* density_grid, const float* sigmas, const int32_t* indices, uint32_t per_cascade, uint32_t C,
+                     uint32_t H, float decay, float scale, float density_thresh, int32_t* owner, double* sum,
+                     uint8_t* bitfield, float* mean_density, void* stream);
+int enerf_mark_untrained_grid(float* density_grid, const float* poses, uint32_t B, float fx, float fy, float cx, float cy,
+                              uint32_t C, uint32_t H, float bound, void* stream);
 
 /* Fixed-step integrator of NeRFRenderer.run (nerf/renderer.py:230-255), which the reference
  * evaluates as ~25 ATen kernels over [N,T] temporaries.  One warp per ray:

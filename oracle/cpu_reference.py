@@ -68,6 +68,27 @@ def sh_encode_torch(d):
         1.4453057213202769 * z * (x2 - y2), 0.59004358992664352 * x * (-x2 + 3.0 * y2)], dim=-1)
 
 
+def sample_pdf_cpu(bins, weights, n_samples, det=False):
+    """inverse-CDF sampling of new z values, nerf/renderer.py:12-46.  bins [B,T-1], weights [B,T-2] -> [B,n_samples]"""
+    weights = weights + 1e-5
+    pdf = weights / torch.sum(weights, -1, keepdim=True)
+    cdf = torch.cumsum(pdf, -1)
+    cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], -1)
+    if det:
+        u = torch.linspace(0.5 / n_samples, 1.0 - 0.5 / n_samples, steps=n_samples).expand(list(cdf.shape[:-1]) + [n_samples])
+    else:
+        u = torch.rand(list(cdf.shape[:-1]) + [n_samples])
+    u = u.contiguous()
+    inds = torch.searchsorted(cdf, u, right=True)
+    below = (inds - 1).clamp(min=0)
+    above = inds.clamp(max=cdf.shape[-1] - 1)
+    c0, c1 = torch.gather(cdf, -1, below), torch.gather(cdf, -1, above)
+    b0, b1 = torch.gather(bins, -1, below), torch.gather(bins, -1, above)
+    denom = c1 - c0
+    denom = torch.where(denom < 1e-5, torch.ones_like(denom), denom)
+    return b0 + (u - c0) / denom * (b1 - b0)
+
+
 class NeRFNetworkCPU(nn.Module):
     """nerf/network.py:10-132 (sigma-net 32->64->16, colour-net 31->64->64->C, no bias) +
     NeRFRenderer.run (nerf/renderer.py:150-278), fp32, CPU."""
@@ -103,7 +124,14 @@ class NeRFNetworkCPU(nn.Module):
         rgbs[mask] = torch.sigmoid(self._mlp(self.color_net, h))
         return rgbs
 
-    def render(self, rays_o, rays_d, num_steps=512, bg_color=1, perturb=False):
+    def _weights(self, sigma, z_vals, sample_dist):
+        """renderer.py:230-234 (and :203-208): the last delta is (far-near)/num_steps even when the rows have been upsampled"""
+        deltas = torch.cat([z_vals[..., 1:] - z_vals[..., :-1], sample_dist * torch.ones_like(z_vals[..., :1])], dim=-1)
+        alphas = 1 - torch.exp(-deltas * self.density_scale * sigma)
+        alphas_shifted = torch.cat([torch.ones_like(alphas[..., :1]), 1 - alphas + 1e-15], dim=-1)
+        return alphas * torch.cumprod(alphas_shifted, dim=-1)[..., :-1], deltas
+
+    def render(self, rays_o, rays_d, num_steps=512, bg_color=1, perturb=False, upsample_steps=0):
         rays_o, rays_d = rays_o.reshape(-1, 3), rays_d.reshape(-1, 3)
         N = rays_o.shape[0]
         nears, fars = oracle.near_far_from_aabb(rays_o.numpy(), rays_d.numpy(), self.aabb.numpy(), self.min_near)
@@ -115,14 +143,26 @@ class NeRFNetworkCPU(nn.Module):
         xyzs = rays_o.unsqueeze(-2) + rays_d.unsqueeze(-2) * z_vals.unsqueeze(-1)
         xyzs = torch.min(torch.max(xyzs, self.aabb[:3]), self.aabb[3:])
         sigma, geo_feat = self.density(xyzs.reshape(-1, 3))
-        sigma = sigma.view(N, num_steps)
-        deltas = torch.cat([z_vals[..., 1:] - z_vals[..., :-1], sample_dist * torch.ones_like(z_vals[..., :1])], dim=-1)
-        alphas = 1 - torch.exp(-deltas * self.density_scale * sigma)
-        alphas_shifted = torch.cat([torch.ones_like(alphas[..., :1]), 1 - alphas + 1e-15], dim=-1)
-        weights = alphas * torch.cumprod(alphas_shifted, dim=-1)[..., :-1]
+        sigma, geo_feat = sigma.view(N, num_steps), geo_feat.view(N, num_steps, -1)
+        if upsample_steps > 0:                                   # renderer.py:196-228
+            with torch.no_grad():
+                w0, deltas = self._weights(sigma, z_vals, sample_dist)
+                z_mid = z_vals[..., :-1] + 0.5 * deltas[..., :-1]
+                new_z = sample_pdf_cpu(z_mid, w0[:, 1:-1], upsample_steps, det=not self.training).detach()
+                new_xyzs = rays_o.unsqueeze(-2) + rays_d.unsqueeze(-2) * new_z.unsqueeze(-1)
+                new_xyzs = torch.min(torch.max(new_xyzs, self.aabb[:3]), self.aabb[3:])
+            new_sigma, new_geo = self.density(new_xyzs.reshape(-1, 3))
+            z_vals, z_index = torch.sort(torch.cat([z_vals, new_z], dim=1), dim=1)
+            xyzs = torch.cat([xyzs, new_xyzs], dim=1)
+            xyzs = torch.gather(xyzs, dim=1, index=z_index.unsqueeze(-1).expand_as(xyzs))
+            sigma = torch.gather(torch.cat([sigma, new_sigma.view(N, upsample_steps)], dim=1), dim=1, index=z_index)
+            geo_feat = torch.cat([geo_feat, new_geo.view(N, upsample_steps, -1)], dim=1)
+            geo_feat = torch.gather(geo_feat, dim=1, index=z_index.unsqueeze(-1).expand_as(geo_feat))
+        weights, _ = self._weights(sigma, z_vals, sample_dist)
         mask = weights > 1e-4
         dirs = rays_d.view(-1, 1, 3).expand_as(xyzs)
-        rgbs = self.color(dirs.reshape(-1, 3), geo_feat, mask.reshape(-1)).view(N, num_steps, self.out_dim_color)
+        geo_feat = geo_feat.reshape(-1, geo_feat.shape[-1])
+        rgbs = self.color(dirs.reshape(-1, 3), geo_feat, mask.reshape(-1)).view(N, -1, self.out_dim_color)
         weights_sum = weights.sum(dim=-1)
         depth = torch.sum(weights * ((z_vals - nears) / (fars - nears)).clamp(0, 1), dim=-1)
         image = torch.sum(weights.unsqueeze(-1) * rgbs, dim=-2) + (1 - weights_sum).unsqueeze(-1) * bg_color

@@ -97,7 +97,7 @@ def test_vs_reference_build(nl):
     _close(n(ggw), n(rgw).astype(np.float64), 5e-2, "grad_weights vs reference")
 
 
-@pytest.mark.parametrize("I,nl", [(32, 2), (32, 3), (64, 2), (16, 4), (48, 2)])
+@pytest.mark.parametrize("I,nl", [(32, 2), (32, 3)])
 def test_tcgen05_and_mma_sync_paths_agree(I, nl):
     """The two kernel families (tcgen05/TMEM for 64-wide ReLU nets, generic mma.sync) against the
     oracle and against each other.  Run under a watchdog: a wrong mbarrier phase would hang."""
@@ -128,9 +128,8 @@ def test_tcgen05_and_mma_sync_paths_agree(I, nl):
     tfb, tg = t(fb_all), t(g)
     nobuf = {}
     try:
-        # path 0 = tcgen05 with TMA-staged operands (taken when no backward_buffer is asked for), 2 = tcgen05 with per-thread
-        # operand loads, 1 = mma.sync
-        for path in (0, 2, 1):
+        # path 0 = tcgen05 (TMA-staged operands; backward_buffer filled only when asked for), 1 = mma.sync
+        for path in (0, 1):
             _lib.call("enerf_ffmlp_set_path", path)
             for with_bb in ((True, False) if path != 1 else (True,)):
                 bbuf = torch.zeros(nl, B, W, device=DEV, dtype=torch.half) if with_bb else None
@@ -173,8 +172,6 @@ def test_tcgen05_and_mma_sync_paths_agree(I, nl):
             _close(n(gwt2), gw, 1e-3, f"grad_weights (no dx) path {path}")
     finally:
         _lib.call("enerf_ffmlp_set_path", 0)
-    # the two tcgen05 backward kernels issue the same MMAs on the same tiles: activation gradients are bit-identical
-    assert torch.equal(nobuf[0][0], nobuf[2][0]), "grad_inputs: TMA-staged vs per-thread operand loads"
     d_out = (outs[0][0].float() - outs[1][0].float()).abs().max().item()
     d_fb = (outs[0][1].float() - outs[1][1].float()).abs().max().item()
     assert d_out <= 4e-3 * float(outs[1][0].float().abs().max()) + 1e-3, d_out

@@ -266,65 +266,6 @@ def test_fused_field_matches_module_chain(n_ch):
         assert float((got - want).abs().max()) <= 1e-4 * float(want.abs().max()) + 1e-12
 
 
-@pytest.mark.parametrize("graph", [False, True], ids=["eager", "cuda-graph"])
-def test_pipelined_backward_matches_sequential(graph):
-    """enerf_b200.field.encoded_field (one autograd node; the scatter of sample chunk k on a second stream while the MLP backward
-    works on chunk k+1 with a capped grid) vs the default encoder -> fused_field chain: identical outputs (same kernels), gradients
-    equal up to the order of the fp32 reductions (1e-4 of the largest entry).  Chunkings include ragged ones and more chunks than
-    tiles; the CUDA-graph variant checks that the two-stream fork / join is capturable and replays to the same result."""
-    from enerf_b200 import field
-    bound = 2
-    torch.manual_seed(5)
-    model = FFNet(bound=bound, cuda_ray=True, out_dim_color=1).to(DEV).train()
-    with torch.no_grad():
-        model.encoder.embeddings.uniform_(-0.5, 0.5)
-    S = 128 * 301
-    x = ((torch.rand(S, 3, device=DEV) * 2 - 1) * bound).sort(dim=0).values          # sorted: long same-cell runs on coarse levels
-    d = torch.randn(S, 3, device=DEV)
-    d = d / d.norm(dim=-1, keepdim=True)
-    gs = torch.randn(S, device=DEV) * 0.1
-    gr = torch.randn(S, 1, device=DEV)
-    params = (model.encoder.embeddings, model.sigma_net.weights, model.color_net.weights)
-
-    def run():
-        for p_ in params:
-            p_.grad = None
-        with torch.autocast("cuda", dtype=torch.float16):
-            sigma, rgb = model(x, d)
-        ((sigma * gs).sum() + (rgb.float() * gr).sum()).backward()
-        return (sigma.detach().clone(), rgb.detach().clone()) + tuple(p_.grad.clone() for p_ in params)
-
-    want = run()
-    saved = (field.PIPELINE, field.PIPELINE_CHUNKS, field.PIPELINE_MLP_CTAS, field.PIPELINE_SCATTER_BLOCK)
-    try:
-        field.PIPELINE = True
-        for chunks, ctas, block in ((1, 0, 256), (4, 120, 256), (3, 100, 128), (7, 64, 192), (512, 148, 64)):
-            field.PIPELINE_CHUNKS, field.PIPELINE_MLP_CTAS, field.PIPELINE_SCATTER_BLOCK = chunks, ctas, block
-            if graph:
-                side = torch.cuda.Stream()
-                side.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(side):
-                    run()                                   # warm-up outside the capture (lazy initialisations)
-                torch.cuda.current_stream().wait_stream(side)
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    got = run()
-                for t_ in got:
-                    t_.zero_()
-                g.replay()
-                torch.cuda.synchronize()
-            else:
-                got = run()
-            assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1]), (chunks, ctas, block)
-            for a, b, name in zip(got[2:], want[2:], ("embeddings", "sigma_net", "color_net")):
-                assert float((a - b).abs().max()) <= 1e-4 * float(b.abs().max()) + 1e-12, (name, chunks, ctas, block)
-    finally:
-        field.PIPELINE, field.PIPELINE_CHUNKS, field.PIPELINE_MLP_CTAS, field.PIPELINE_SCATTER_BLOCK = saved
-    # the global launch settings are restored after every pipelined backward
-    again = run()
-    assert torch.equal(again[0], want[0]) and float((again[2] - want[2]).abs().max()) <= 1e-4 * float(want[2].abs().max())
-
-
 def test_psnr_parity_tiny_scene():
     """BASELINE configs[0]: train the CPU port of the reference's pure-PyTorch renderer and this repo's GPU stack from the same
     initial parameters on the same ray batches; rendered PSNR must agree within the north star's 0.1 dB."""

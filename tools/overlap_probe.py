@@ -5,7 +5,7 @@ The scatter is bound by L2 reductions and the gather by L1/LSU sectors, the tcge
 tensor pipes (backward) and HBM (sigma forward): different bottlenecks, so chunk k of one can run next to chunk k+1 of the
 other.  This probe times, on the bench workload's marched samples,
 
-  bwd: colour-net bwd -> sigma-net bwd -> scatter        sequential vs `enerf_b200.field.pipelined_backward`
+  bwd: colour-net bwd -> sigma-net bwd -> scatter        sequential vs `tools/pipelined_backward.py`
   fwd: gather -> sigma-net fwd -> colour-net fwd         sequential vs the same pipeline in the other direction
 
 for a few (chunks, MLP CTA cap, scatter CTA size) settings and checks that the results agree.
@@ -19,7 +19,8 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from enerf_b200 import _lib, field, synthetic  # noqa: E402
+from enerf_b200 import _lib, synthetic  # noqa: E402
+from tools import pipelined_backward as pipelined  # noqa: E402
 from enerf_b200 import raymarching as rm  # noqa: E402
 from enerf_b200._lib import ptr, stream  # noqa: E402
 from enerf_b200.backends import gridencoder_backend as GB  # noqa: E402
@@ -75,7 +76,7 @@ def main():
     cin = torch.empty(S, 32, dtype=torch.half, device=dev)
     rgb = torch.empty(S, n_ch, device=dev)
     dummy = table.new_empty(1)
-    side = field._side_stream(dev)
+    side = pipelined._side_stream(dev)
 
     def gather(lo, hi):
         GB.grid_encode_forward(x[lo:hi], table, offsets, feat[lo:hi], hi - lo, 3, 2, 16, geometry[4], geometry[5], False, dummy, 0, 1)
@@ -155,7 +156,7 @@ def main():
     res["scatter_ms"] = timeit(scatter, args.iters)
 
     def bwd_pipe(chunks, cap, block):
-        return field.pipelined_backward(g_sigma, g_rgb, sigma, rgb, cin, feat, x, table, offsets, geometry, 0, ws, wc, nl_s, nl_c, n_ch,
+        return pipelined.pipelined_backward(g_sigma, g_rgb, sigma, rgb, cin, feat, x, table, offsets, geometry, 0, ws, wc, nl_s, nl_c, n_ch,
                                         torch.float32, chunks, cap, block)
 
     for chunks, cap, block in [(1, 148, 256), (2, 148, 256), (4, 148, 256), (4, 148, 128), (4, 132, 256), (4, 120, 256), (4, 104, 256), (4, 88, 256),
