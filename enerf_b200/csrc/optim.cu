@@ -26,10 +26,11 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 __global__ void __launch_bounds__(256)
 k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, uint64_t n,
        const float* __restrict__ step, AdamArgs a, const float* __restrict__ grad_scale, const float* __restrict__ found_inf,
-       __half* __restrict__ shadow) {
+       float grad_mul, __half* __restrict__ shadow) {
     if (found_inf && *found_inf != 0.f) return;                  // the scaler skips this step (the fp16 shadow stays valid: p is unchanged)
     const float t = *step;                                        // already incremented by the caller
-    const float inv_scale = grad_scale ? 1.0f / *grad_scale : 1.0f;
+    // gradients arrive multiplied by the GradScaler's scale and, after a sum-reduction over N ranks, by N: both are undone here
+    const float inv_scale = (grad_scale ? 1.0f / *grad_scale : 1.0f) * grad_mul;
     const float bc1 = 1.0f - powf(a.beta1, t), bc2 = 1.0f - powf(a.beta2, t);
     const float step_size = a.lr / bc1, bc2_sqrt = sqrtf(bc2);
     const uint64_t n4 = n >> 2;
@@ -65,7 +66,7 @@ using namespace enerf;
 
 extern "C" int enerf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, uint64_t n, const float* step, float lr,
                                float beta1, float beta2, float eps, float weight_decay, const float* grad_scale, const float* found_inf,
-                               uint16_t* half_shadow, void* stream) {
+                               float grad_mul, uint16_t* half_shadow, void* stream) {
     if (n == 0) return 0;
     ENERF_REQUIRE(step != nullptr, "adam_step", "step must be a device pointer to the (already incremented) step count");
     ENERF_REQUIRE(((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(exp_avg) |
@@ -76,7 +77,7 @@ extern "C" int enerf_adam_step(float* param, const float* grad, float* exp_avg, 
     uint64_t blocks = (n4 + 255) / 256;
     if (blocks > (uint64_t)num_sms() * 16) blocks = (uint64_t)num_sms() * 16;
     if (blocks == 0) blocks = 1;
-    k_adam<<<(uint32_t)blocks, 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, step, a, grad_scale, found_inf,
+    k_adam<<<(uint32_t)blocks, 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, step, a, grad_scale, found_inf, grad_mul,
                                                                 reinterpret_cast<__half*>(half_shadow));
     ENERF_CHECK_LAUNCH("adam_step");
     return 0;

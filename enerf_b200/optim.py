@@ -38,14 +38,25 @@ class FusedAdam(torch.optim.Optimizer):
                     continue
                 if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
                     raise RuntimeError("FusedAdam: contiguous CUDA fp32 parameters only (there is no CPU path)")
-                g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
-                if g.dtype != torch.float32:
-                    g = g.float()
+                # data-parallel sharding (enerf_b200.parallel.ShardedExchange): this rank owns elements [lo, hi) of the flattened
+                # parameter, `grad` is the sum over ranks of that slice and `mul` = 1/world undoes the sum
+                shard = getattr(p, "_enerf_shard", None)
+                if shard is not None:
+                    lo, hi, g, mul = shard
+                    pv = p.view(-1)[lo:hi]
+                else:
+                    lo, hi, mul = 0, p.numel(), 1.0
+                    pv = p
+                    g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                    if g.dtype != torch.float32:
+                        g = g.float()
                 st = self.state[p]
                 if not st:
                     st["step"] = torch.zeros((), dtype=torch.float32, device=p.device)
-                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg"] = torch.zeros_like(pv, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(pv, memory_format=torch.preserve_format)
+                if st["exp_avg"].numel() != hi - lo:
+                    raise RuntimeError("FusedAdam: the shard of a parameter changed after its state was created")
                 # device-side counter: advances only when the step is not skipped (as torch's capturable Adam does)
                 if found_inf is not None:
                     st["step"] += 1.0 - found_inf.to(st["step"].device).reshape(())
@@ -54,7 +65,8 @@ class FusedAdam(torch.optim.Optimizer):
                 shadow = getattr(p, "_enerf_half", None)
                 if shadow is not None and (shadow[0].shape != p.shape or shadow[0].device != p.device):
                     shadow = None
-                _lib.call("enerf_adam_step", ptr(p), ptr(g), ptr(st["exp_avg"]), ptr(st["exp_avg_sq"]), p.numel(), ptr(st["step"]),
+                sh_ptr = ptr(shadow[0].view(-1)[lo:hi]) if shadow is not None else None
+                _lib.call("enerf_adam_step", ptr(pv), ptr(g), ptr(st["exp_avg"]), ptr(st["exp_avg_sq"]), hi - lo, ptr(st["step"]),
                           float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
-                          ptr(grad_scale), ptr(found_inf), ptr(shadow[0]) if shadow is not None else None, stream())
+                          ptr(grad_scale), ptr(found_inf), float(mul), sh_ptr, stream())
         return None

@@ -1,11 +1,22 @@
 """Ray-sharded data parallelism.
 
 Rays are independent, the model (<= 50 MiB) is replicated, so the only exchange step of a
-training iteration is one sum-allreduce of the gradients: the hash-grid gradient table
-(13.0 M fp32 = 52 MB) reduced in place, and the two flat MLP gradient vectors (18 432 floats)
-coalesced into one small bucket that is launched first.  Inference shards image rows and
-all-gathers the result.  Backend-agnostic (`nccl` on GPUs, `gloo` in the CPU tests); the
-reference itself is single-process (its DDP hooks are unreachable, nerf/utils.py:351-353).
+training iteration is the gradient exchange.  Two implementations with one interface
+(`begin_step()`, `before_step(scaler)`, `after_step()`):
+
+  AllReduceExchange   sum-allreduce of every gradient (the hash-grid gradient table, 13.0 M fp32 =
+                      52 MB, in place; the MLP gradient vectors coalesced into one small bucket
+                      launched first), every rank then runs the full optimizer step.
+  ShardedExchange     reduce-scatter of the table gradient -> each rank runs Adam on its 1/N slice
+                      (FusedAdam, which also writes that slice of the fp16 table) -> all-gather of the
+                      fp16 table (what the kernels read under autocast): 45 + 23 MB on the wire instead
+                      of 91 MB at N = 8, 1/N of the Adam work, no 1/N scaling pass (folded into the Adam
+                      kernel).  The fp32 master copy of a rank is current for its own slice only;
+                      `gather_master()` completes it (checkpoints, fp32 evaluation).
+
+Inference shards image rows and all-gathers the result.  Backend-agnostic (`nccl` on GPUs, `gloo`
+in the CPU tests); the reference itself is single-process (its DDP hooks are unreachable,
+nerf/utils.py:351-353).
 """
 import torch
 import torch.distributed as dist
@@ -89,6 +100,122 @@ class GradientAllReduce:
             if scale != 1.0:
                 for p in ps:
                     p.grad.mul_(scale)
+
+
+class AllReduceExchange:
+    """every gradient sum-allreduced and averaged; the optimizer step is replicated"""
+    name = "allreduce"
+
+    def __init__(self, model, optimizer=None, big=1 << 20):
+        self.reducer = GradientAllReduce(list(model.parameters()), average=True, big=big)
+
+    def begin_step(self):
+        pass
+
+    def before_step(self, scaler=None):
+        self.reducer.reduce()
+
+    def after_step(self):
+        pass
+
+    def gather_master(self):
+        pass
+
+
+def _reduce_scatter_sum(out, full):
+    """out <- this rank's slice of the sum over ranks of `full` (gloo has no reduce-scatter: all-reduce a copy and slice)"""
+    if dist.get_backend() == "gloo":
+        tmp = full.clone()
+        dist.all_reduce(tmp, op=dist.ReduceOp.SUM)
+        n = out.numel()
+        out.copy_(tmp.view(-1)[dist.get_rank() * n:(dist.get_rank() + 1) * n])
+    else:
+        dist.reduce_scatter_tensor(out, full, op=dist.ReduceOp.SUM)
+
+
+def _all_gather_inplace(full, lo, hi):
+    """every rank contributes full[lo:hi] (its slice, equal sizes); afterwards `full` is complete everywhere"""
+    if dist.get_backend() == "gloo":
+        parts = [torch.empty(hi - lo, dtype=full.dtype) for _ in range(dist.get_world_size())]
+        dist.all_gather(parts, full[lo:hi].clone())
+        full.copy_(torch.cat(parts))
+    else:
+        dist.all_gather_into_tensor(full, full[lo:hi])
+
+
+class ShardedExchange:
+    """reduce-scatter of the big gradients, optimizer step on the local slice, all-gather of the updated (fp16) table.
+
+    Requires an optimizer that honours `param._enerf_shard = (lo, hi, reduced_grad_slice, 1/world)` — `enerf_b200.optim.FusedAdam`.
+    GradScaler: its inf check runs on every rank's LOCAL gradients, so a non-finite value seen by one rank is made visible to all
+    (one 4-byte all-reduce; the local gradient's first element is overwritten with NaN where any rank overflowed) — all ranks skip
+    the same steps and keep the same scale."""
+    name = "reduce-scatter + sharded Adam + fp16 all-gather"
+
+    def __init__(self, model, optimizer=None, big=1 << 20):
+        self.rank, self.world = world()
+        params = [p for p in model.parameters() if p.requires_grad]
+        self.big = [p for p in params if p.numel() >= big and p.numel() % (4 * max(self.world, 1)) == 0] if self.world > 1 else []
+        ids = {id(p) for p in self.big}
+        self.small = GradientAllReduce([p for p in params if id(p) not in ids], average=True, big=1 << 62)
+        self._slices = {}
+        if self.world > 1 and optimizer is not None and not getattr(optimizer, "_step_supports_amp_scaling", False):
+            raise RuntimeError("ShardedExchange needs an optimizer that understands sharded parameters (enerf_b200.optim.FusedAdam)")
+
+    def _slice(self, p):
+        n = p.numel() // self.world
+        return self.rank * n, (self.rank + 1) * n
+
+    def begin_step(self):
+        pass
+
+    def before_step(self, scaler=None):
+        if self.world == 1:
+            return
+        pending = self.small.reduce(async_op=True)
+        flag = None
+        for p in self.big:
+            if p.grad is None:
+                continue
+            lo, hi = self._slice(p)
+            g = p.grad.contiguous().view(-1)
+            key = id(p)
+            if key not in self._slices or self._slices[key].numel() != hi - lo or self._slices[key].device != g.device:
+                self._slices[key] = torch.empty(hi - lo, dtype=g.dtype, device=g.device)
+            shard = self._slices[key]
+            _reduce_scatter_sum(shard, g)
+            bad = (~torch.isfinite(shard)).any().to(torch.float32).reshape(1)
+            flag = bad if flag is None else torch.maximum(flag, bad)
+            p._enerf_shard = (lo, hi, shard, 1.0 / self.world)
+        self.small.finish(pending)
+        if flag is not None:
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            poison = torch.where(flag > 0, torch.full_like(flag, float("nan")), torch.zeros_like(flag))
+            for p in self.big:
+                if p.grad is not None:
+                    p.grad.view(-1)[:1].add_(poison)          # 0 normally; NaN everywhere if any rank overflowed anywhere
+
+    def after_step(self):
+        if self.world == 1:
+            return
+        for p in self.big:
+            if getattr(p, "_enerf_shard", None) is None:
+                continue
+            lo, hi = self._slice(p)
+            slot = getattr(p, "_enerf_half", None)
+            if slot is not None and slot[0].shape == p.shape and slot[0].device == p.device:
+                _all_gather_inplace(slot[0].view(-1), lo, hi)          # the fp16 table the kernels read
+            else:
+                _all_gather_inplace(p.data.view(-1), lo, hi)
+
+    @torch.no_grad()
+    def gather_master(self):
+        """complete the fp32 parameters on every rank (each rank keeps only its own slice current during training)"""
+        if self.world == 1:
+            return
+        for p in self.big:
+            lo, hi = self._slice(p)
+            _all_gather_inplace(p.data.view(-1), lo, hi)
 
 
 def all_gather_rows(local, n_total):

@@ -88,3 +88,31 @@ def ball_density_grid(bound, cascade, H=128, radius_frac=0.5):
 def packbits_np(grid, thresh=0.01):
     bits = (grid.reshape(-1, 8) > thresh).astype(np.uint8)
     return (bits << np.arange(8, dtype=np.uint8)).sum(-1).astype(np.uint8)
+
+
+EVENT_H, EVENT_W = 260, 346          # DAVIS-346 sensor, as the mocapDesk2 recordings (TUM-VIE) are undistorted to
+
+
+def event_frame(bound=2, n_pixels=60000, seed=0):
+    """One synthetic event frame laid out as `EventNeRFDataset` stores it (nerf/provider.py:1148-1202): events [E,4] = (x, y, t,
+    polarity) grouped by pixel with >= 2 events per pixel, the per-event successor counts, the indices of every pixel's last event,
+    and per-event camera poses [E,3,4] = a look-at pose jittered by 0.2 degrees / 1 mm (BASELINE configs[2] / SURVEY.md §8d C3)."""
+    rng = np.random.default_rng(seed)
+    counts = rng.integers(2, 12, n_pixels)
+    pix = rng.choice(EVENT_H * EVENT_W, n_pixels, replace=False)
+    xs = np.repeat(pix % EVENT_W, counts).astype(np.float32)
+    ys = np.repeat(pix // EVENT_W, counts).astype(np.float32)
+    E = int(counts.sum())
+    ts = rng.random(E).astype(np.float32)
+    pol = rng.choice([-1.0, 1.0], E).astype(np.float32)
+    ev = np.stack([xs, ys, ts, pol], 1)
+    cum = np.cumsum(counts)
+    num_succ = (np.repeat(cum, counts) - np.arange(E) - 1).astype(np.int64)
+    base = look_at_poses(1, 0.6 * bound, seed=3)[0]
+    ang = np.radians(0.2) * rng.normal(size=(E, 3)).astype(np.float32)
+    K = np.zeros((E, 3, 3), np.float32)
+    K[:, 0, 1], K[:, 0, 2], K[:, 1, 0], K[:, 1, 2], K[:, 2, 0], K[:, 2, 1] = -ang[:, 2], ang[:, 1], ang[:, 2], -ang[:, 0], -ang[:, 1], ang[:, 0]
+    R = (np.eye(3, dtype=np.float32)[None] + K) @ (base[:3, :3] * np.array([1, -1, -1], np.float32))       # OpenCV-style camera axes
+    t = base[:3, 3][None] + 1e-3 * rng.normal(size=(E, 3)).astype(np.float32)
+    poses = np.concatenate([R, t[:, :, None]], -1).astype(np.float32)
+    return ev, num_succ, cum - 1, poses

@@ -1,8 +1,5 @@
 #!/usr/bin/env python
-"""Kernel times of the reference's OWN CUDA extensions (oracle/_ref, built for sm_100a by oracle/build_ref.py) next to this
-repo's kernels, on the bench workload's marched samples, same B200, same process.  TEST INFRASTRUCTURE (it loads oracle/_ref);
-not a test, not on the product path.  The reference kernels launch on the legacy default stream, which is torch's default
-stream, so torch events bracket them correctly.
+"""CLI around oracle/gpu_bar.py: kernel times of the reference's own CUDA build next to this repo's kernels.
 
   python tests/bench_vs_reference_build.py [--rays 4096] [--iters 5] [--out gpurun_out/x.json]
 Every row is printed as soon as it is measured; a failing row does not stop the rest."""
@@ -11,161 +8,14 @@ import json
 import os
 import sys
 
-import numpy as np
-import torch
-
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from enerf_b200 import synthetic  # noqa: E402
-from enerf_b200 import raymarching as rm  # noqa: E402
-from enerf_b200.backends import ffmlp_backend as FB, gridencoder_backend as GB, raymarching_backend as RB  # noqa: E402
-from enerf_b200.gridencoder import GridEncoder  # noqa: E402
-from oracle import ref  # noqa: E402
+from oracle import gpu_bar  # noqa: E402
 
-
-def timeit(fn, iters):
-    for _ in range(2):
-        fn()
-    torch.cuda.synchronize()
-    ts = []
-    for _ in range(iters):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        fn()
-        b.record()
-        torch.cuda.synchronize()
-        ts.append(a.elapsed_time(b))
-    return round(float(np.median(ts)), 4)
-
-
-def main():
+if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--rays", type=int, default=4096)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--bound", type=int, default=3)
     ap.add_argument("--out", default="")
-    args = ap.parse_args()
-    dev = torch.device("cuda", 0)
-    bound = args.bound
-    cascade = 1 + int(np.ceil(np.log2(bound)))
-    bits = torch.from_numpy(synthetic.packbits_np(synthetic.ball_density_grid(bound, cascade))).to(dev)
-    o, d = synthetic.random_rays(args.rays, bound, seed=100)
-    o, d = torch.from_numpy(o).to(dev), torch.from_numpy(d).to(dev)
-    aabb = torch.tensor([-bound] * 3 + [bound] * 3, dtype=torch.float32, device=dev)
-    nears, fars = rm.near_far_from_aabb(o, d, aabb, 0.2)
-    counter = torch.zeros(2, dtype=torch.int32, device=dev)
-    xyzs, dirs, deltas, rays = rm.march_rays_train(o, d, float(bound), bits, cascade, 128, nears, fars, counter, -1, True, 128, False, 0, 1024)
-    S = xyzs.shape[0] // 128 * 128
-    N = args.rays
-    rows = []
-    res = {"samples": S, "rays": N, "unit": "ms (median of %d, CUDA events)" % args.iters, "rows": rows}
-
-    def row(name, ours, theirs, note=""):
-        r = {"kernel": name}
-        for key, fn in (("ours_ms", ours), ("reference_build_ms", theirs)):
-            if fn is None:
-                continue
-            try:
-                r[key] = timeit(fn, args.iters)
-            except Exception as e:  # noqa: BLE001
-                r[key + "_error"] = f"{type(e).__name__}: {e}"[:300]
-                torch.cuda.synchronize()
-        if "ours_ms" in r and "reference_build_ms" in r:
-            r["speedup"] = round(r["reference_build_ms"] / r["ours_ms"], 2)
-        if note:
-            r["note"] = note
-        rows.append(r)
-        print(json.dumps(r), flush=True)
-        if args.out:
-            with open(args.out, "w") as f:
-                json.dump(res, f, indent=1)
-
-    # ---------------- marcher (K5)
-    R = ref.load("_raymarching")
-    M = xyzs.shape[0]
-    bx, bd, bdl = torch.zeros(M, 3, device=dev), torch.zeros(M, 3, device=dev), torch.zeros(M, 2, device=dev)
-    br = torch.empty(N, 3, dtype=torch.int32, device=dev)
-
-    def march_ours():
-        counter.zero_()
-        RB.march_rays_train(o, d, bits, float(bound), 0.0, 1024, N, cascade, 128, M, nears, fars, bx, bd, bdl, br, counter, 1)
-
-    def march_ref():
-        counter.zero_()
-        R.march_rays_train(o, d, bits, float(bound), 0.0, 1024, N, cascade, 128, M, nears, fars, bx, bd, bdl, br, counter, 1)
-
-    row("march_rays_train", march_ours, march_ref if R else None)
-
-    # ---------------- compositing (K6/K7), 3 channels as in the reference
-    sig = torch.rand(M, device=dev) * 20
-    rgb3 = torch.rand(M, 3, device=dev)
-    ws, dp, im = torch.empty(N, device=dev), torch.empty(N, device=dev), torch.empty(N, 3, device=dev)
-    g1, g3 = torch.randn(N, device=dev), torch.randn(N, 3, device=dev)
-    gs, gr = torch.zeros(M, device=dev), torch.zeros(M, 3, device=dev)
-    row("composite_rays_train_forward", lambda: RB.composite_rays_train_forward(sig, rgb3, deltas, rays, M, N, ws, dp, im),
-        (lambda: R.composite_rays_train_forward(sig, rgb3, deltas, rays, M, N, ws, dp, im)) if R else None)
-    row("composite_rays_train_backward", lambda: RB.composite_rays_train_backward(g1, g3, sig, rgb3, deltas, rays, ws, im, M, N, gs, gr),
-        (lambda: R.composite_rays_train_backward(g1, g3, sig, rgb3, deltas, rays, ws, im, M, N, gs, gr)) if R else None)
-    del sig, rgb3, gs, gr, bx, bd, bdl
-
-    # ---------------- hash grid (K11/K12), fp16 table as under autocast
-    R = ref.load("_gridencoder")
-    enc = GridEncoder(desired_resolution=2048 * bound).to(dev)
-    table = (torch.rand_like(enc.embeddings) - 0.5).half().contiguous()
-    offsets = enc.offsets
-    x = ((xyzs[:S] + bound) / (2 * bound)).contiguous()
-    log2s, H = float(np.log2(enc.per_level_scale)), enc.base_resolution
-    out_blc = torch.empty(S, 32, dtype=torch.half, device=dev)
-    out_lbc = torch.empty(16, S, 2, dtype=torch.half, device=dev)
-    dummy = torch.empty(1, dtype=torch.half, device=dev)
-    row("grid_encode_forward (fp16 table)", lambda: GB.grid_encode_forward(x, table, offsets, out_blc, S, 3, 2, 16, log2s, H, False, dummy, 0, 1),
-        (lambda: R.grid_encode_forward(x, table, offsets, out_lbc, S, 3, 2, 16, log2s, H, False, dummy, 0)) if R else None,
-        "reference writes [L,B,C]; its wrapper then copies to [B,L*C] (grid.py:52), not included")
-    grad_blc = (torch.randn(S, 32, device=dev) * 1e-2).half()
-    grad_lbc = grad_blc.view(S, 16, 2).permute(1, 0, 2).contiguous()
-    gt32 = torch.empty(table.shape, dtype=torch.float32, device=dev)
-    gt16 = torch.empty(table.shape, dtype=torch.half, device=dev)
-
-    def scatter_ours():
-        gt32.zero_()
-        GB.grid_encode_backward(grad_blc, x, table, offsets, gt32, S, 3, 2, 16, log2s, H, False, dummy, dummy, 0, 1)
-
-    def scatter_ref():
-        gt16.zero_()
-        R.grid_encode_backward(grad_lbc, x, table, offsets, gt16, S, 3, 2, 16, log2s, H, False, dummy, dummy, 0)
-
-    row("grid_encode_backward (fp16 table)", scatter_ours, scatter_ref if R else None,
-        "incl. zero-fill of the gradient table; reference: fp16 atomics into an fp16 table, and its wrapper first copies grad to [L,B,C] "
-        "(grid.py:70), not included; ours: fp32 accumulation")
-    del out_lbc, grad_lbc, gt16, gt32, grad_blc
-
-    # ---------------- fully-fused MLP (K16-K19): sigma-net (2 layers) and colour-net (3 layers), 32 -> 64 -> ... -> 16
-    R = ref.load("_ffmlp")
-    xin = out_blc
-    for nl, name in ((2, "sigma-net 32-64-64-16"), (3, "colour-net 32-64-64-64-16")):
-        w = ((torch.rand(64 * (32 + 64 * (nl - 1) + 16), device=dev) * 2 - 1) * (3 / 64) ** 0.5).half()
-        out = torch.empty(S, 16, dtype=torch.half, device=dev)
-        fb = torch.empty(nl, S, 64, dtype=torch.half, device=dev)
-        ib = torch.empty(S, 64, dtype=torch.half, device=dev)
-        g = (torch.randn(S, 16, device=dev) * 0.1).half()
-        bb = torch.empty(nl, S, 64, dtype=torch.half, device=dev)
-        gi = torch.empty(S, 32, dtype=torch.half, device=dev)
-        gw16 = torch.empty(w.numel(), dtype=torch.half, device=dev)
-        gw32 = torch.empty(w.numel(), dtype=torch.float32, device=dev)
-        if R:
-            R.allocate_splitk(nl + 1)
-        row(f"ffmlp_inference {name}", lambda: FB.ffmlp_inference(xin, w, S, 32, 16, 64, nl, 0, 6, None, out),
-            (lambda: R.ffmlp_inference(xin, w, S, 32, 16, 64, nl, 0, 6, ib, out)) if R else None)
-        row(f"ffmlp_forward (training, stores forward_buffer) {name}", lambda: FB.ffmlp_forward(xin, w, S, 32, 16, 64, nl, 0, 6, fb, out),
-            (lambda: R.ffmlp_forward(xin, w, S, 32, 16, 64, nl, 0, 6, fb, out)) if R else None)
-        FB.ffmlp_forward(xin, w, S, 32, 16, 64, nl, 0, 6, fb, out)
-        row(f"ffmlp_backward (from forward_buffer) {name}", lambda: FB.ffmlp_backward(g, xin, w, fb, S, 32, 16, 64, nl, 0, 6, True, None, gi, gw32),
-            (lambda: R.ffmlp_backward(g, xin, w, fb, S, 32, 16, 64, nl, 0, 6, True, bb, gi, gw16)) if R else None,
-            "reference: dgrad kernel + (nl+1) CUTLASS split-K weight-gradient GEMMs on side streams, fp16 accumulation")
-        row(f"ffmlp_backward (recomputing, no forward_buffer: the training path) {name}",
-            lambda: FB.ffmlp_backward(g, xin, w, None, S, 32, 16, 64, nl, 0, 6, True, None, gi, gw32), None)
-        del out, fb, ib, g, bb, gi
-    print(json.dumps(res))
-
-
-if __name__ == "__main__":
-    main()
+    a = ap.parse_args()
+    print(json.dumps(gpu_bar.measure(a.rays, a.iters, a.bound, a.out, verbose=True)))

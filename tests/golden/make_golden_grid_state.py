@@ -24,6 +24,9 @@ BOUND, H = 2, 128
 
 
 def main():
+    # one thread: `tmp_grid[cas, indices] = sigmas` (renderer.py:545) has duplicate indices in the partial branch, and torch's CPU index_put
+    # only resolves them deterministically ("the last one wins") when it runs sequentially
+    torch.set_num_threads(1)
     ns = ref_python.load()
     r = ns.NeRFRenderer(bound=BOUND, cuda_ray=True, density_scale=1, min_near=0.2, density_thresh=0.01, bg_radius=-1)
     C, cells = r.cascade, H ** 3

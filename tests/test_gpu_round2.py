@@ -58,7 +58,7 @@ def test_fused_adam_keeps_fp16_table_current(graphed):
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
         after = enc(x, bound=1)
     assert not torch.equal(before, after), "the encoder does not see its own updates"
-    assert losses[-1] < 0.8 * losses[1], losses
+    assert min(losses[1:]) < 0.5 * losses[0], losses
     # a writer that goes through torch (version bump) invalidates the shadow: the next forward re-casts
     with torch.no_grad():
         enc.embeddings.copy_(torch.zeros_like(enc.embeddings))
@@ -98,8 +98,8 @@ def test_composite_uniform_last_delta_after_upsampling():
     nears = torch.rand(N, generator=g).double() + 0.2
     fars = nears + 1 + torch.rand(N, generator=g).double() * 3
     z = torch.sort(nears[:, None] + (fars - nears)[:, None] * torch.rand(N, T0 + Tu, generator=g).double(), dim=1).values
-    sig = (torch.rand(N, T0 + Tu, generator=g) * 20).double()
-    sig[:, -1] = 40.0                                           # make the last sample matter
+    sig = (torch.rand(N, T0 + Tu, generator=g) * 0.3).double()  # nearly transparent up to the last sample ...
+    sig[:, -1] = 40.0                                           # ... so that its delta decides a visible weight
     sig_ref = sig.clone().requires_grad_(True)
     w, ws, depth = _weights_reference(sig_ref, z, nears, fars, 1.0, T0)
     gw = torch.randn(N, T0 + Tu, generator=g).double()

@@ -83,3 +83,65 @@ def test_two_rank_gradient_allreduce_matches_single_process():
         assert p.exitcode == 0
     got = dict(out.get(timeout=10) for _ in range(2))
     assert got == {"grads": True, "gather": True}
+
+
+def _sharded_worker(rank, world_size, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        torch.manual_seed(0)
+        big = torch.nn.Parameter(torch.randn(1 << 20, 2) * 0.01)           # stands in for the hash table (same values on every rank)
+        small = torch.nn.Parameter(torch.randn(7))
+        model = torch.nn.ParameterList([big, small])
+
+        class _SliceSGD:                                                    # an optimizer that honours `_enerf_shard` like FusedAdam does
+            _step_supports_amp_scaling = True
+
+            def step(self):
+                lo, hi, g, mul = big._enerf_shard
+                big.data.view(-1)[lo:hi] -= 0.5 * mul * g
+                small.data -= 0.5 * small.grad
+
+        ex = parallel.ShardedExchange(model, _SliceSGD())
+        assert len(ex.big) == 1 and ex.name.startswith("reduce-scatter")
+        g_local = torch.full_like(big, float(rank + 1))
+        g_local.view(-1)[5] = 10.0 * (rank + 1)
+        big.grad, small.grad = g_local.clone(), torch.full((7,), float(rank))
+        before = big.detach().clone()
+        ex.before_step()
+        lo, hi, shard, mul = big._enerf_shard
+        want_sum = sum(r + 1 for r in range(world_size))
+        ok = (hi - lo) * world_size == big.numel() and abs(mul - 1.0 / world_size) < 1e-12
+        ok &= bool(torch.all(shard[(1 if rank == 0 else 0):6 if rank == 0 else None] == want_sum)) if rank != 0 else bool(shard[5] == 10.0 * want_sum and shard[0] == want_sum)
+        ok &= bool(torch.allclose(small.grad, torch.full((7,), sum(range(world_size)) / world_size)))
+        ok &= bool(torch.isfinite(big.grad).all())                         # nothing overflowed: the local gradient is not poisoned
+        _SliceSGD().step()
+        ex.after_step()                                                    # no fp16 shadow here: the fp32 slices are gathered
+        expect = before - 0.5 * (want_sum / world_size)
+        expect.view(-1)[5] = before.view(-1)[5] - 0.5 * 10.0 * want_sum / world_size
+        ok &= bool(torch.allclose(big.detach(), expect, atol=1e-6))
+        # overflow on ONE rank is seen by all
+        big.grad = torch.ones_like(big)
+        if rank == world_size - 1:
+            big.grad.view(-1)[-3] = float("inf")
+        small.grad = torch.zeros(7)
+        ex.before_step()
+        ok &= bool(torch.isnan(big.grad.view(-1)[0]))
+        ex.gather_master()
+        out.put((f"rank{rank}", bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_sharded_exchange():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    got = dict(out.get(timeout=10) for _ in range(2))
+    assert got == {"rank0": True, "rank1": True}

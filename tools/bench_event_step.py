@@ -22,32 +22,7 @@ from enerf_b200.nerf.network_ff import NeRFNetwork  # noqa: E402
 from enerf_b200.optim import FusedAdam  # noqa: E402
 
 BOUND = 2
-H_EV, W_EV = 260, 346
-
-
-def synthetic_event_frame(n_pixels=60000, seed=0):
-    rng = np.random.default_rng(seed)
-    counts = rng.integers(2, 12, n_pixels)
-    pix = rng.choice(H_EV * W_EV, n_pixels, replace=False)
-    xs = np.repeat(pix % W_EV, counts).astype(np.float32)
-    ys = np.repeat(pix // W_EV, counts).astype(np.float32)
-    E = int(counts.sum())
-    ts = rng.random(E).astype(np.float32)
-    pol = rng.choice([-1.0, 1.0], E).astype(np.float32)
-    ev = np.stack([xs, ys, ts, pol], 1)
-    cum = np.cumsum(counts)
-    start = np.repeat(cum - counts, counts)
-    num_succ = (np.repeat(cum, counts) - np.arange(E) - 1).astype(np.int64)
-    del start
-    base = synthetic.look_at_poses(1, 0.6 * BOUND, seed=3)[0]
-    # per-event pose: small rotation about a random axis (sigma 0.2 deg) and translation (sigma 1 mm)
-    ang = np.radians(0.2) * rng.normal(size=(E, 3)).astype(np.float32)
-    K = np.zeros((E, 3, 3), np.float32)
-    K[:, 0, 1], K[:, 0, 2], K[:, 1, 0], K[:, 1, 2], K[:, 2, 0], K[:, 2, 1] = -ang[:, 2], ang[:, 1], ang[:, 2], -ang[:, 0], -ang[:, 1], ang[:, 0]
-    R = (np.eye(3, dtype=np.float32)[None] + K) @ (base[:3, :3] * np.array([1, -1, -1], np.float32))       # OpenCV-style camera axes
-    t = base[:3, 3][None] + 1e-3 * rng.normal(size=(E, 3)).astype(np.float32)
-    poses = np.concatenate([R, t[:, :, None]], -1).astype(np.float32)
-    return ev, num_succ, cum - 1, poses
+H_EV, W_EV = synthetic.EVENT_H, synthetic.EVENT_W
 
 
 def main():
@@ -64,7 +39,7 @@ def main():
     grid = synthetic.ball_density_grid(BOUND, model.cascade)
     model.density_grid.copy_(torch.from_numpy(grid))
     model.density_bitfield.copy_(torch.from_numpy(synthetic.packbits_np(grid)))
-    ev, num_succ, no_succ, poses = synthetic_event_frame()
+    ev, num_succ, no_succ, poses = synthetic.event_frame(bound=BOUND)
     sampler = events.EventPairSampler(ev, num_succ, no_succ, acc_max_num_evs=8, poses_evs=poses, device=dev)
     focal = H_EV / (2 * np.tan(np.radians(50.0) / 2))
     intr = (focal, focal, W_EV / 2, H_EV / 2)
