@@ -230,6 +230,7 @@ class TrainLoop:
         self.bits_saved = model.density_bitfield.clone()
 
         def step(o, d, tg):
+            exchange.begin_step()
             with torch.autocast("cuda", dtype=torch.float16):
                 out = model.render(o.unsqueeze(0), d.unsqueeze(0), staged=False, bg_color=self.bg, perturb=True, **self.kw)
             loss = F.mse_loss(out["image"].reshape(-1, 1).float(), tg)
@@ -597,8 +598,6 @@ def our_arm(args):
     dev = torch.device("cuda", D.local_rank)
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL's version banner goes to stdout; this script prints exactly one line there
         dist.init_process_group("nccl", device_id=dev)
     n_rays, K = args.rays, max(1, args.steps)
     W = max(3, args.warmup)                         # the timing rules ask for >= 3 warm-up steps

@@ -23,8 +23,23 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
     p -= step_size * m / denom;
 }
 
+// gradient element i as fp32: G = float (the usual case) or __half (gradients that crossed the wire in fp16, see parallel.py)
+template <typename G>
+__device__ __forceinline__ float4 load_grad4(const G* __restrict__ g, uint64_t i4);
+template <>
+__device__ __forceinline__ float4 load_grad4<float>(const float* __restrict__ g, uint64_t i4) { return __ldg(reinterpret_cast<const float4*>(g) + i4); }
+template <>
+__device__ __forceinline__ float4 load_grad4<__half>(const __half* __restrict__ g, uint64_t i4) {
+    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(g) + i4);
+    const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ float grad_as_float(float g) { return g; }
+__device__ __forceinline__ float grad_as_float(__half g) { return __half2float(g); }
+
+template <typename G>
 __global__ void __launch_bounds__(256)
-k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, uint64_t n,
+k_adam(float* __restrict__ p, const G* __restrict__ g, float* __restrict__ m, float* __restrict__ v, uint64_t n,
        const float* __restrict__ step, AdamArgs a, const float* __restrict__ grad_scale, const float* __restrict__ found_inf,
        float grad_mul, __half* __restrict__ shadow) {
     if (found_inf && *found_inf != 0.f) return;                  // the scaler skips this step (the fp16 shadow stays valid: p is unchanged)
@@ -37,11 +52,11 @@ k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
         float4 P = reinterpret_cast<float4*>(p)[i], M = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i];
-        const float4 G = __ldg(reinterpret_cast<const float4*>(g) + i);
-        adam_one(P.x, G.x, M.x, V.x, a, inv_scale, step_size, bc2_sqrt);
-        adam_one(P.y, G.y, M.y, V.y, a, inv_scale, step_size, bc2_sqrt);
-        adam_one(P.z, G.z, M.z, V.z, a, inv_scale, step_size, bc2_sqrt);
-        adam_one(P.w, G.w, M.w, V.w, a, inv_scale, step_size, bc2_sqrt);
+        const float4 Gv = load_grad4<G>(g, i);
+        adam_one(P.x, Gv.x, M.x, V.x, a, inv_scale, step_size, bc2_sqrt);
+        adam_one(P.y, Gv.y, M.y, V.y, a, inv_scale, step_size, bc2_sqrt);
+        adam_one(P.z, Gv.z, M.z, V.z, a, inv_scale, step_size, bc2_sqrt);
+        adam_one(P.w, Gv.w, M.w, V.w, a, inv_scale, step_size, bc2_sqrt);
         reinterpret_cast<float4*>(p)[i] = P;
         reinterpret_cast<float4*>(m)[i] = M;
         reinterpret_cast<float4*>(v)[i] = V;
@@ -55,7 +70,7 @@ k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m
     const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid < n - tail0) {
         const uint64_t i = tail0 + gid;
-        adam_one(p[i], g[i], m[i], v[i], a, inv_scale, step_size, bc2_sqrt);
+        adam_one(p[i], grad_as_float(g[i]), m[i], v[i], a, inv_scale, step_size, bc2_sqrt);
         if (shadow) shadow[i] = __float2half_rn(p[i]);
     }
 }
@@ -64,12 +79,13 @@ k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m
 
 using namespace enerf;
 
-extern "C" int enerf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, uint64_t n, const float* step, float lr,
+extern "C" int enerf_adam_step(float* param, const void* grad, int grad_dtype, float* exp_avg, float* exp_avg_sq, uint64_t n, const float* step, float lr,
                                float beta1, float beta2, float eps, float weight_decay, const float* grad_scale, const float* found_inf,
                                float grad_mul, uint16_t* half_shadow, void* stream) {
     if (n == 0) return 0;
     ENERF_REQUIRE(step != nullptr, "adam_step", "step must be a device pointer to the (already incremented) step count");
-    ENERF_REQUIRE(((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(exp_avg) |
+    ENERF_REQUIRE(grad_dtype == ENERF_F32 || grad_dtype == ENERF_F16, "adam_step", "grad_dtype must be ENERF_F32 or ENERF_F16");
+    ENERF_REQUIRE(((reinterpret_cast<uintptr_t>(param) | (reinterpret_cast<uintptr_t>(grad) << (grad_dtype == ENERF_F16 ? 1 : 0)) | reinterpret_cast<uintptr_t>(exp_avg) |
                     reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15u) == 0, "adam_step", "tensors must be 16-byte aligned");
     ENERF_REQUIRE((reinterpret_cast<uintptr_t>(half_shadow) & 7u) == 0, "adam_step", "half_shadow must be 8-byte aligned");
     const AdamArgs a = {lr, beta1, beta2, eps, weight_decay};
@@ -77,8 +93,12 @@ extern "C" int enerf_adam_step(float* param, const float* grad, float* exp_avg, 
     uint64_t blocks = (n4 + 255) / 256;
     if (blocks > (uint64_t)num_sms() * 16) blocks = (uint64_t)num_sms() * 16;
     if (blocks == 0) blocks = 1;
-    k_adam<<<(uint32_t)blocks, 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, step, a, grad_scale, found_inf, grad_mul,
-                                                                reinterpret_cast<__half*>(half_shadow));
+    if (grad_dtype == ENERF_F16)
+        k_adam<__half><<<(uint32_t)blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<float*>(param), reinterpret_cast<const __half*>(grad), exp_avg, exp_avg_sq, n,
+                                                                        step, a, grad_scale, found_inf, grad_mul, reinterpret_cast<__half*>(half_shadow));
+    else
+        k_adam<float><<<(uint32_t)blocks, 256, 0, as_stream(stream)>>>(param, reinterpret_cast<const float*>(grad), exp_avg, exp_avg_sq, n, step, a, grad_scale,
+                                                                       found_inf, grad_mul, reinterpret_cast<__half*>(half_shadow));
     ENERF_CHECK_LAUNCH("adam_step");
     return 0;
 }

@@ -46,6 +46,9 @@ def _half_table(param):
     """fp16 view of the table for the kernels.  Valid while the parameter's version counter is the one the shadow was cast at;
     `FusedAdam` keeps it current without bumping the version (its kernel writes parameter and shadow in one pass)."""
     slot = half_shadow(param, create=True)
+    wait = getattr(param, "_enerf_wait", None)
+    if wait is not None:
+        wait(param)                                        # data-parallel: slices of the table may still be in flight (parallel.ShardedExchange)
     if slot[1] != param._version:
         slot[0].copy_(param.detach())                      # in place: pointers captured in a CUDA graph stay valid
         slot[1] = param._version

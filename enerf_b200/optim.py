@@ -66,7 +66,9 @@ class FusedAdam(torch.optim.Optimizer):
                 if shadow is not None and (shadow[0].shape != p.shape or shadow[0].device != p.device):
                     shadow = None
                 sh_ptr = ptr(shadow[0].view(-1)[lo:hi]) if shadow is not None else None
-                _lib.call("enerf_adam_step", ptr(pv), ptr(g), ptr(st["exp_avg"]), ptr(st["exp_avg_sq"]), hi - lo, ptr(st["step"]),
+                if g.dtype not in (torch.float32, torch.float16) or g.numel() != hi - lo:
+                    raise RuntimeError("FusedAdam: gradient (slice) must be fp32 or fp16 and match the parameter (slice)")
+                _lib.call("enerf_adam_step", ptr(pv), ptr(g), _lib.dtype_code(g), ptr(st["exp_avg"]), ptr(st["exp_avg_sq"]), hi - lo, ptr(st["step"]),
                           float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
                           ptr(grad_scale), ptr(found_inf), float(mul), sh_ptr, stream())
         return None

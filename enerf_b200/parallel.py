@@ -146,28 +146,76 @@ def _all_gather_inplace(full, lo, hi):
 class ShardedExchange:
     """reduce-scatter of the big gradients, optimizer step on the local slice, all-gather of the updated (fp16) table.
 
+    Per step, for the hash table (13.0 M parameters, N ranks):
+      before_step  gradient cast fp32 -> fp16 (the wire format; the reference itself accumulates these gradients in fp16,
+                   gridencoder.cu:296-302), reduce-scatter (26 MB * (N-1)/N per rank instead of the 52 MB * 2(N-1)/N of an fp32
+                   all-reduce), non-finite check of the reduced slice;
+      optimizer    FusedAdam on the rank's 1/N slice: un-scales (GradScaler) and divides by N in the kernel, writes the fp32
+                   master slice and the fp16 table slice;
+      begin_step   (of the NEXT step) all-gather of the fp16 table on a side stream, overlapped with ray set-up and the
+                   occupancy-grid march, which do not read the table; the first hash-grid kernel waits for it.
     Requires an optimizer that honours `param._enerf_shard = (lo, hi, reduced_grad_slice, 1/world)` — `enerf_b200.optim.FusedAdam`.
-    GradScaler: its inf check runs on every rank's LOCAL gradients, so a non-finite value seen by one rank is made visible to all
-    (one 4-byte all-reduce; the local gradient's first element is overwritten with NaN where any rank overflowed) — all ranks skip
-    the same steps and keep the same scale."""
-    name = "reduce-scatter + sharded Adam + fp16 all-gather"
+    GradScaler: its inf check runs on every rank's LOCAL gradients, so a non-finite value in the reduced slice of any rank (an
+    overflow anywhere, incl. in the fp16 cast) is made visible to all: one 4-byte all-reduce, after which the local gradient's first
+    element is NaN on every rank — all ranks skip the same steps and keep the same scale.
+    The fp32 master copy of a rank is current for its own slice only; `gather_master()` completes it (checkpoints, EMA, fp32 eval)."""
+    name = "fp16 reduce-scatter + sharded Adam + fp16 all-gather (overlapped with the next march)"
 
-    def __init__(self, model, optimizer=None, big=1 << 20):
+    def __init__(self, model, optimizer=None, big=1 << 20, wire_dtype=torch.float16):
         self.rank, self.world = world()
+        self.wire_dtype = wire_dtype
         params = [p for p in model.parameters() if p.requires_grad]
-        self.big = [p for p in params if p.numel() >= big and p.numel() % (4 * max(self.world, 1)) == 0] if self.world > 1 else []
+        self.big = [p for p in params if p.numel() >= big and p.numel() % (8 * max(self.world, 1)) == 0] if self.world > 1 else []
         ids = {id(p) for p in self.big}
         self.small = GradientAllReduce([p for p in params if id(p) not in ids], average=True, big=1 << 62)
-        self._slices = {}
+        self._slices, self._wire = {}, {}
+        self._dirty = False            # table slices written by the optimizer, not yet gathered
+        self._event = None             # completion of the last gather (side stream)
+        self._side = None
         if self.world > 1 and optimizer is not None and not getattr(optimizer, "_step_supports_amp_scaling", False):
             raise RuntimeError("ShardedExchange needs an optimizer that understands sharded parameters (enerf_b200.optim.FusedAdam)")
+        for p in self.big:
+            p._enerf_wait = self._wait_table          # consulted by gridencoder.grid._half_table before the table is read
 
     def _slice(self, p):
         n = p.numel() // self.world
         return self.rank * n, (self.rank + 1) * n
 
+    def _gather_tables(self):
+        for p in self.big:
+            lo, hi = self._slice(p)
+            slot = getattr(p, "_enerf_half", None)
+            if slot is not None and slot[0].shape == p.shape and slot[0].device == p.device:
+                _all_gather_inplace(slot[0].view(-1), lo, hi)          # the fp16 table the kernels read
+            else:
+                _all_gather_inplace(p.data.view(-1), lo, hi)
+
     def begin_step(self):
-        pass
+        """start gathering the table slices the previous optimizer step wrote; returns immediately"""
+        if self.world == 1 or not self._dirty:
+            return
+        self._dirty = False
+        if self.big and self.big[0].is_cuda:
+            main = torch.cuda.current_stream()
+            if self._side is None:
+                self._side = torch.cuda.Stream()
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                self._gather_tables()
+                self._event = torch.cuda.Event()
+                self._event.record(self._side)
+        else:
+            self._gather_tables()
+
+    def _wait_table(self, p=None):
+        """the table is about to be read on the current stream"""
+        if self.world == 1:
+            return
+        if self._dirty:
+            self.begin_step()
+        if self._event is not None:
+            torch.cuda.current_stream().wait_event(self._event)
+            self._event = None
 
     def before_step(self, scaler=None):
         if self.world == 1:
@@ -181,8 +229,12 @@ class ShardedExchange:
             g = p.grad.contiguous().view(-1)
             key = id(p)
             if key not in self._slices or self._slices[key].numel() != hi - lo or self._slices[key].device != g.device:
-                self._slices[key] = torch.empty(hi - lo, dtype=g.dtype, device=g.device)
+                self._slices[key] = torch.empty(hi - lo, dtype=self.wire_dtype, device=g.device)
+                self._wire[key] = torch.empty(g.numel(), dtype=self.wire_dtype, device=g.device) if self.wire_dtype != g.dtype else None
             shard = self._slices[key]
+            if self._wire[key] is not None:
+                self._wire[key].copy_(g)
+                g = self._wire[key]
             _reduce_scatter_sum(shard, g)
             bad = (~torch.isfinite(shard)).any().to(torch.float32).reshape(1)
             flag = bad if flag is None else torch.maximum(flag, bad)
@@ -196,23 +248,15 @@ class ShardedExchange:
                     p.grad.view(-1)[:1].add_(poison)          # 0 normally; NaN everywhere if any rank overflowed anywhere
 
     def after_step(self):
-        if self.world == 1:
-            return
-        for p in self.big:
-            if getattr(p, "_enerf_shard", None) is None:
-                continue
-            lo, hi = self._slice(p)
-            slot = getattr(p, "_enerf_half", None)
-            if slot is not None and slot[0].shape == p.shape and slot[0].device == p.device:
-                _all_gather_inplace(slot[0].view(-1), lo, hi)          # the fp16 table the kernels read
-            else:
-                _all_gather_inplace(p.data.view(-1), lo, hi)
+        if self.world > 1 and self.big:
+            self._dirty = True
 
     @torch.no_grad()
     def gather_master(self):
-        """complete the fp32 parameters on every rank (each rank keeps only its own slice current during training)"""
+        """complete the fp32 parameters (and the fp16 table) on every rank"""
         if self.world == 1:
             return
+        self._wait_table()
         for p in self.big:
             lo, hi = self._slice(p)
             _all_gather_inplace(p.data.view(-1), lo, hi)

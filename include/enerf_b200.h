@@ -331,10 +331,11 @@ int enerf_event_loss_backward(const float* img1, const float* img2, const float*
  * (amsgrad off, maximize off), fused into one pass per tensor.  `step`: device pointer to the step count of this parameter,
  * ALREADY incremented for this step; grad_scale / found_inf: the GradScaler's device scalars (NULL = 1 / 0): gradients are
  * divided by *grad_scale and multiplied by grad_mul on the fly (grad_mul = 1/N after a sum-reduction over N ranks, else 1) and the
- * call is a no-op when *found_inf != 0.  fp32 tensors, 16-byte aligned.
+ * call is a no-op when *found_inf != 0.  fp32 tensors, 16-byte aligned; grad is fp32 or (grad_dtype == ENERF_F16, 8-byte aligned) fp16 —
+ * gradients that crossed the NVLink wire in half precision (enerf_b200/parallel.py).
  * half_shadow (may be NULL): fp16 [n] copy of the UPDATED parameter written in the same pass — gridencoder/grid.py:38-39
  * re-casts the whole table to half on every forward under autocast; with the shadow that 52 MB -> 26 MB pass disappears. */
-int enerf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, uint64_t n, const float* step,
+int enerf_adam_step(float* param, const void* grad, int grad_dtype, float* exp_avg, float* exp_avg_sq, uint64_t n, const float* step,
                     float lr, float beta1, float beta2, float eps, float weight_decay, const float* grad_scale,
                     const float* found_inf, float grad_mul, uint16_t* half_shadow, void* stream);
 /* N3 — event-pair sampler, nerf/provider.py:1364-1405 (collate, accumulate_evs branch).  events [E,4] fp32 = (x, y, t, polarity),

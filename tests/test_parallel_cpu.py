@@ -99,11 +99,11 @@ def _sharded_worker(rank, world_size, port, out):
 
             def step(self):
                 lo, hi, g, mul = big._enerf_shard
-                big.data.view(-1)[lo:hi] -= 0.5 * mul * g
+                big.data.view(-1)[lo:hi] -= 0.5 * mul * g.float()
                 small.data -= 0.5 * small.grad
 
         ex = parallel.ShardedExchange(model, _SliceSGD())
-        assert len(ex.big) == 1 and ex.name.startswith("reduce-scatter")
+        assert len(ex.big) == 1 and "reduce-scatter" in ex.name
         g_local = torch.full_like(big, float(rank + 1))
         g_local.view(-1)[5] = 10.0 * (rank + 1)
         big.grad, small.grad = g_local.clone(), torch.full((7,), float(rank))
@@ -115,8 +115,10 @@ def _sharded_worker(rank, world_size, port, out):
         ok &= bool(torch.all(shard[(1 if rank == 0 else 0):6 if rank == 0 else None] == want_sum)) if rank != 0 else bool(shard[5] == 10.0 * want_sum and shard[0] == want_sum)
         ok &= bool(torch.allclose(small.grad, torch.full((7,), sum(range(world_size)) / world_size)))
         ok &= bool(torch.isfinite(big.grad).all())                         # nothing overflowed: the local gradient is not poisoned
+        assert shard.dtype == torch.float16                                # the wire format
         _SliceSGD().step()
-        ex.after_step()                                                    # no fp16 shadow here: the fp32 slices are gathered
+        ex.after_step()
+        ex.begin_step()                                                    # deferred gather (no fp16 shadow here: the fp32 slices travel)
         expect = before - 0.5 * (want_sum / world_size)
         expect.view(-1)[5] = before.view(-1)[5] - 0.5 * 10.0 * want_sum / world_size
         ok &= bool(torch.allclose(big.detach(), expect, atol=1e-6))
