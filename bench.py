@@ -60,7 +60,8 @@ def parse():
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"], help="Adam step: this repo's fused kernel or torch.optim.Adam(fused=True)")
     ap.add_argument("--skip", default="", help="comma-separated extra objects to skip: strong_scaling,event_step,run_variant,render,gpu_bar,extra_state")
     ap.add_argument("--no-render", action="store_true", help="same as --skip render")
-    ap.add_argument("--exchange", default="sharded", choices=["sharded", "allreduce"], help="gradient exchange at N > 1 (enerf_b200/parallel.py)")
+    ap.add_argument("--exchange", default="sharded", choices=["sharded", "allreduce", "none"],
+                    help="gradient exchange at N > 1 (enerf_b200/parallel.py); none = no exchange at all (diagnosis only: the ranks diverge)")
     return ap.parse_args()
 
 
@@ -604,7 +605,7 @@ def our_arm(args):
     skip = set(x for x in args.skip.split(",") if x)
     if args.no_render:
         skip.add("render")
-    exchange_cls = parallel.ShardedExchange if args.exchange == "sharded" else parallel.AllReduceExchange
+    exchange_cls = {"sharded": parallel.ShardedExchange, "allreduce": parallel.AllReduceExchange, "none": parallel.NoExchange}[args.exchange]
 
     peaks = {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0, "src": "fallback (B200_PROFILING.md)"}
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")

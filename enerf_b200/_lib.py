@@ -68,6 +68,7 @@ _SIGS = {
     "enerf_event_loss_backward": [_p, _p, _p, _p, _p, _p, _u32, _u32, _int, _int, _f32, _f32, _f32, _p, _p, _p],
     "enerf_sample_event_pairs": [_p, _p, _p, _p, _u32, _u32, _int, _p, _p, _p, _p, _p, _p, _p, _p],
     "enerf_adam_step": [_p, _p, _int, _p, _p, _u64, _p, _f32, _f32, _f32, _f32, _f32, _p, _p, _f32, _p, _p],
+    "enerf_grad_to_half": [_p, _p, _u64, _f32, _p, _p],
     "enerf_ffmlp_set_path": [_int],
     "enerf_ffmlp_set_max_ctas": [_int],
     "enerf_ffmlp_uses_tcgen05": [_u32, _u32, _u32, _u32, _u32],

@@ -75,9 +75,43 @@ k_adam(float* __restrict__ p, const G* __restrict__ g, float* __restrict__ m, fl
     }
 }
 
+// fp32 -> fp16 copy of a gradient for the wire (parallel.ShardedExchange) that also raises *flag (float, set to 1) when a value is
+// non-finite or exceeds `limit` in magnitude (limit = 65504 / world: the sum over the ranks then cannot overflow fp16 either)
+__global__ void __launch_bounds__(256)
+k_grad_to_half(const float* __restrict__ g, __half* __restrict__ out, uint64_t n, float limit, float* __restrict__ flag) {
+    const uint64_t n4 = n >> 2;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    bool bad = false;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(g) + i);
+        bad |= !(fabsf(v.x) <= limit) | !(fabsf(v.y) <= limit) | !(fabsf(v.z) <= limit) | !(fabsf(v.w) <= limit);      // NaN compares false
+        const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+        reinterpret_cast<uint2*>(out)[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+    }
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid < n - (n4 << 2)) {
+        const float v = g[(n4 << 2) + gid];
+        bad |= !(fabsf(v) <= limit);
+        out[(n4 << 2) + gid] = __float2half_rn(v);
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31u) == 0) *flag = 1.0f;
+}
+
 }  // namespace enerf
 
 using namespace enerf;
+
+extern "C" int enerf_grad_to_half(const float* grad, uint16_t* out, uint64_t n, float limit, float* flag, void* stream) {
+    if (n == 0) return 0;
+    ENERF_REQUIRE(flag != nullptr, "grad_to_half", "flag must not be NULL");
+    ENERF_REQUIRE(((reinterpret_cast<uintptr_t>(grad) & 15u) | (reinterpret_cast<uintptr_t>(out) & 7u)) == 0, "grad_to_half", "grad must be 16-byte, out 8-byte aligned");
+    uint64_t blocks = ((n >> 2) + 255) / 256;
+    if (blocks > (uint64_t)num_sms() * 16) blocks = (uint64_t)num_sms() * 16;
+    if (blocks == 0) blocks = 1;
+    k_grad_to_half<<<(uint32_t)blocks, 256, 0, as_stream(stream)>>>(grad, reinterpret_cast<__half*>(out), n, limit, flag);
+    ENERF_CHECK_LAUNCH("grad_to_half");
+    return 0;
+}
 
 extern "C" int enerf_adam_step(float* param, const void* grad, int grad_dtype, float* exp_avg, float* exp_avg_sq, uint64_t n, const float* step, float lr,
                                float beta1, float beta2, float eps, float weight_decay, const float* grad_scale, const float* found_inf,

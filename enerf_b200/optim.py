@@ -19,6 +19,7 @@ from ._lib import ptr, stream
 
 class FusedAdam(torch.optim.Optimizer):
     _step_supports_amp_scaling = True
+    honours_enerf_shard = True        # parallel.ShardedExchange: `param._enerf_shard = (lo, hi, summed gradient slice, 1/world)`
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         if lr < 0 or eps < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1) or weight_decay < 0:

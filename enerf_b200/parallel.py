@@ -102,18 +102,47 @@ class GradientAllReduce:
                     p.grad.mul_(scale)
 
 
-class AllReduceExchange:
-    """every gradient sum-allreduced and averaged; the optimizer step is replicated"""
-    name = "allreduce"
+class NoExchange:
+    """no communication (single GPU, or diagnosis of what the exchange costs)"""
+    name = "none"
 
-    def __init__(self, model, optimizer=None, big=1 << 20):
-        self.reducer = GradientAllReduce(list(model.parameters()), average=True, big=big)
+    def __init__(self, model=None, optimizer=None, big=1 << 20):
+        pass
 
     def begin_step(self):
         pass
 
     def before_step(self, scaler=None):
+        pass
+
+    def after_step(self):
+        pass
+
+    def gather_master(self):
+        pass
+
+
+class AllReduceExchange:
+    """every gradient sum-allreduced (fp32); the optimizer step is replicated.  With FusedAdam the 1/N of the average is applied
+    inside the Adam kernel instead of by a separate pass over the 52 MB table gradient."""
+    name = "allreduce"
+
+    def __init__(self, model, optimizer=None, big=1 << 20):
+        self._fused = optimizer is not None and getattr(optimizer, "honours_enerf_shard", False)
+        self.reducer = GradientAllReduce(list(model.parameters()), average=not self._fused, big=big)
+
+    def begin_step(self):
+        pass
+
+    def before_step(self, scaler=None):
+        rank, world_size = world()
+        if world_size == 1:
+            return
         self.reducer.reduce()
+        if self._fused:
+            for p in self.reducer.params:
+                if p.grad is not None and p.grad.is_contiguous():
+                    p._enerf_shard = (0, p.numel(), p.grad.view(-1), 1.0 / world_size)
 
     def after_step(self):
         pass
@@ -172,7 +201,8 @@ class ShardedExchange:
         self._dirty = False            # table slices written by the optimizer, not yet gathered
         self._event = None             # completion of the last gather (side stream)
         self._side = None
-        if self.world > 1 and optimizer is not None and not getattr(optimizer, "_step_supports_amp_scaling", False):
+        self._fused = optimizer is not None and getattr(optimizer, "honours_enerf_shard", False)
+        if self.world > 1 and self.big and not self._fused:
             raise RuntimeError("ShardedExchange needs an optimizer that understands sharded parameters (enerf_b200.optim.FusedAdam)")
         for p in self.big:
             p._enerf_wait = self._wait_table          # consulted by gridencoder.grid._half_table before the table is read
@@ -217,35 +247,65 @@ class ShardedExchange:
             torch.cuda.current_stream().wait_event(self._event)
             self._event = None
 
+    def _to_wire(self, g, wire, flag):
+        """wire <- fp16(g); flag[0] = 1 if a value is non-finite or too large for the fp16 sum over the ranks"""
+        limit = 65504.0 / self.world
+        if g.is_cuda:
+            from . import _lib
+            _lib.call("enerf_grad_to_half", _lib.ptr(g), _lib.ptr(wire), g.numel(), limit, _lib.ptr(flag), _lib.stream())
+        else:                                                # gloo tests
+            wire.copy_(g)
+            flag.copy_(torch.maximum(flag, (~(g.abs() <= limit)).any().to(flag.dtype).reshape(1)))
+
     def before_step(self, scaler=None):
+        """Collectives per step: ONE all-reduce of [small gradients | overflow flag] (74 KB) and one reduce-scatter per table.
+        Nothing is scaled here: the sums carry a factor N that the optimizer kernel removes (`_enerf_shard[3]`)."""
         if self.world == 1:
             return
-        pending = self.small.reduce(async_op=True)
-        flag = None
-        for p in self.big:
-            if p.grad is None:
-                continue
-            lo, hi = self._slice(p)
+        small = [p for p in self.small.params if p.grad is not None]
+        big = [p for p in self.big if p.grad is not None]
+        if not small and not big:
+            return
+        dev = (small + big)[0].grad.device
+        flag = torch.zeros(1, dtype=torch.float32, device=dev)
+        wires = []
+        for p in big:
             g = p.grad.contiguous().view(-1)
             key = id(p)
+            lo, hi = self._slice(p)
             if key not in self._slices or self._slices[key].numel() != hi - lo or self._slices[key].device != g.device:
                 self._slices[key] = torch.empty(hi - lo, dtype=self.wire_dtype, device=g.device)
                 self._wire[key] = torch.empty(g.numel(), dtype=self.wire_dtype, device=g.device) if self.wire_dtype != g.dtype else None
-            shard = self._slices[key]
             if self._wire[key] is not None:
-                self._wire[key].copy_(g)
+                self._to_wire(g, self._wire[key], flag)
                 g = self._wire[key]
+            wires.append(g)
+        # small gradients and the overflow flag travel together
+        bucket = torch.cat([p.grad.reshape(-1).float() for p in small] + [flag])
+        work = dist.all_reduce(bucket, op=dist.ReduceOp.SUM, async_op=True)
+        for p, g in zip(big, wires):
+            lo, hi = self._slice(p)
+            shard = self._slices[id(p)]
             _reduce_scatter_sum(shard, g)
-            bad = (~torch.isfinite(shard)).any().to(torch.float32).reshape(1)
-            flag = bad if flag is None else torch.maximum(flag, bad)
             p._enerf_shard = (lo, hi, shard, 1.0 / self.world)
-        self.small.finish(pending)
-        if flag is not None:
-            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
-            poison = torch.where(flag > 0, torch.full_like(flag, float("nan")), torch.zeros_like(flag))
-            for p in self.big:
-                if p.grad is not None:
-                    p.grad.view(-1)[:1].add_(poison)          # 0 normally; NaN everywhere if any rank overflowed anywhere
+        work.wait()
+        o = 0
+        for p in small:
+            k = p.grad.numel()
+            view = bucket[o:o + k]
+            if self._folds(p, view):
+                p._enerf_shard = (0, k, view, 1.0 / self.world)      # the summed gradient, 1/N applied inside the Adam kernel
+            else:
+                p.grad.copy_((view / self.world).view_as(p.grad))
+            o += k
+        # a non-finite / too-large value on ANY rank -> NaN in the first element of every rank's local gradient: the GradScaler of every
+        # rank then finds an inf, skips the step and backs off
+        poison = torch.where(bucket[-1:] > 0, torch.full_like(flag, float("nan")), torch.zeros_like(flag))
+        for p in (big or small)[:1]:
+            p.grad.view(-1)[:1].add_(poison.to(p.grad.dtype))
+
+    def _folds(self, p, view):
+        return self._fused and p.is_cuda and view.data_ptr() % 16 == 0
 
     def after_step(self):
         if self.world > 1 and self.big:

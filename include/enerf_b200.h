@@ -338,6 +338,10 @@ int enerf_event_loss_backward(const float* img1, const float* img2, const float*
 int enerf_adam_step(float* param, const void* grad, int grad_dtype, float* exp_avg, float* exp_avg_sq, uint64_t n, const float* step,
                     float lr, float beta1, float beta2, float eps, float weight_decay, const float* grad_scale,
                     const float* found_inf, float grad_mul, uint16_t* half_shadow, void* stream);
+/* Wire format of the data-parallel gradient exchange (enerf_b200/parallel.py; no reference counterpart — the reference is single-GPU):
+ * out = fp16(grad); *flag (device float, zeroed by the caller) is set to 1 when an element is non-finite or larger than `limit` in
+ * magnitude (limit = 65504 / world: the fp16 sum over the ranks then cannot overflow either). */
+int enerf_grad_to_half(const float* grad, uint16_t* out, uint64_t n, float limit, float* flag, void* stream);
 /* N3 — event-pair sampler, nerf/provider.py:1364-1405 (collate, accumulate_evs branch).  events [E,4] fp32 = (x, y, t, polarity),
  * grouped by pixel as the provider stores them; pol_prefix [E+1] double = exclusive prefix sum of the polarity column;
  * num_successors [E] (provider.py:1181-1187), no_successor [E] = 1 for the last event of a pixel (:1177-1178); u_start, u_end [M]

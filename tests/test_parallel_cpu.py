@@ -95,7 +95,7 @@ def _sharded_worker(rank, world_size, port, out):
         model = torch.nn.ParameterList([big, small])
 
         class _SliceSGD:                                                    # an optimizer that honours `_enerf_shard` like FusedAdam does
-            _step_supports_amp_scaling = True
+            honours_enerf_shard = True
 
             def step(self):
                 lo, hi, g, mul = big._enerf_shard
