@@ -1,0 +1,205 @@
+"""The reference's hot path chained on the reference's OWN CUDA kernels (TEST INFRASTRUCTURE, GPU box).
+
+`RefStack` is nerf/network_ff.py:51-73 (hash grid -> FFMLP sigma-net -> trunc_exp -> SH ⊕ geo_feat ⊕ 0 -> FFMLP colour-net ->
+sigmoid) driven by the training branch of nerf/renderer.py:281-342 (near/far -> march_rays_train -> field -> composite_rays_train),
+with every kernel taken from oracle/_ref — the four unmodified extensions of /root/reference built for sm_100a by
+oracle/build_ref.py.  The reference's `--ff` network cannot be constructed at HEAD and its Python wrappers are
+not on the GPU box, so the thin autograd wrappers are restated here, each citing the wrapper it follows; the arithmetic that
+matters (every CUDA kernel, incl. fp16 accumulation in the MLP and fp16 atomics in the hash-grid backward) is the reference's.
+Host-side bookkeeping (density-grid refresh, buffers) comes from this repo's mirror `NeRFRenderer`, whose refresh is pinned
+bit-for-bit to the reference's Python by tests/test_gpu_occupancy.py.
+
+Used by tests/hotpath_parity.py (training-level PSNR parity of the tcgen05 stack) and tests/test_gpu_hotpath_parity.py; never by
+the product.
+"""
+import numpy as np
+import torch
+from torch.autograd import Function
+
+from enerf_b200.gridencoder import GridEncoder
+from enerf_b200.nerf.renderer import NeRFRenderer
+from . import ref
+
+
+def available():
+    return all(ref.available(n) for n in ref.NAMES)
+
+
+class _RefGrid(Function):
+    """gridencoder/grid.py:19-88: fp16 table under autocast, outputs [L,B,C] permuted to [B,L*C], fp16 atomics in the backward"""
+
+    @staticmethod
+    def forward(ctx, inputs, embeddings, offsets, per_level_scale, base_resolution):
+        R = ref.load("_gridencoder")
+        inputs = inputs.contiguous()
+        table = embeddings.half().contiguous()                 # grid.py:38-39 (re-cast on every call)
+        B, D = inputs.shape
+        L, C = offsets.shape[0] - 1, table.shape[1]
+        S = float(np.log2(per_level_scale))
+        out = torch.empty(L, B, C, device=inputs.device, dtype=table.dtype)
+        dummy = torch.empty(1, device=inputs.device, dtype=table.dtype)
+        R.grid_encode_forward(inputs, table, offsets, out, B, D, C, L, S, base_resolution, False, dummy, 0)
+        ctx.save_for_backward(inputs, table, offsets)
+        ctx.dims = (B, D, C, L, S, base_resolution)
+        return out.permute(1, 0, 2).reshape(B, L * C)          # grid.py:52
+
+    @staticmethod
+    def backward(ctx, grad):
+        R = ref.load("_gridencoder")
+        inputs, table, offsets = ctx.saved_tensors
+        B, D, C, L, S, H = ctx.dims
+        grad = grad.view(B, L, C).permute(1, 0, 2).contiguous().to(table.dtype)      # grid.py:70
+        gt = torch.zeros_like(table)                                                  # grid.py:72
+        dummy = torch.empty(1, device=grad.device, dtype=table.dtype)
+        R.grid_encode_backward(grad, inputs, table, offsets, gt, B, D, C, L, S, H, False, dummy, dummy, 0)
+        return None, gt.float(), None, None, None
+
+
+class _RefSH(Function):
+    """shencoder/sphere_harmonics.py:14-58 (inputs cast to half under autocast, no input gradient on this path)"""
+
+    @staticmethod
+    def forward(ctx, dirs, degree):
+        R = ref.load("_shencoder")
+        x = dirs.half().contiguous()
+        B = x.shape[0]
+        out = torch.empty(B, degree ** 2, dtype=x.dtype, device=x.device)
+        dummy = torch.empty(1, dtype=x.dtype, device=x.device)
+        R.sh_encode_forward(x, out, B, 3, degree, False, dummy)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return None, None
+
+
+class _RefFFMLP(Function):
+    """ffmlp/ffmlp.py:15-86: fp16 in/out, forward_buffer stored, backward = fused dgrad kernel + split-K CUTLASS weight gradients"""
+
+    @staticmethod
+    def forward(ctx, x, weights, in_dim, num_layers, calc_grad_inputs):
+        R = ref.load("_ffmlp")
+        x = x.half().contiguous()
+        w = weights.half().contiguous()
+        B = x.shape[0]
+        out = torch.empty(B, 16, dtype=torch.half, device=x.device)
+        fb = torch.empty(num_layers, B, 64, dtype=torch.half, device=x.device)
+        R.ffmlp_forward(x, w, B, in_dim, 16, 64, num_layers, 0, 6, fb, out)
+        ctx.save_for_backward(x, w, fb)
+        ctx.dims = (B, in_dim, num_layers, calc_grad_inputs)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        R = ref.load("_ffmlp")
+        x, w, fb = ctx.saved_tensors
+        B, in_dim, nl, want_dx = ctx.dims
+        g = g.half().contiguous()
+        bb = torch.zeros(nl, B, 64, dtype=torch.half, device=g.device)               # ffmlp.py:67-73
+        gi = torch.zeros(B, in_dim, dtype=torch.half, device=g.device)
+        gw = torch.zeros_like(w)
+        R.ffmlp_backward(g, x, w, fb, B, in_dim, 16, 64, nl, 0, 6, want_dx, bb, gi, gw)
+        return (gi if want_dx else None), gw.float(), None, None, None
+
+
+class _RefTruncExp(Function):
+    """activation.py:5-18"""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.float()
+        ctx.save_for_backward(x)
+        return torch.exp(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, = ctx.saved_tensors
+        return g * torch.exp(x.clamp(-15, 15))
+
+
+class _RefComposite(Function):
+    """raymarching/raymarching.py:233-286 (3 colour channels, hard-wired in the reference kernels)"""
+
+    @staticmethod
+    def forward(ctx, sigmas, rgbs, deltas, rays):
+        R = ref.load("_raymarching")
+        sigmas, rgbs = sigmas.float().contiguous(), rgbs.float().contiguous()
+        M, N = sigmas.shape[0], rays.shape[0]
+        ws, dp, im = (torch.empty(N, device=sigmas.device), torch.empty(N, device=sigmas.device), torch.empty(N, 3, device=sigmas.device))
+        R.composite_rays_train_forward(sigmas, rgbs, deltas, rays, M, N, ws, dp, im)
+        ctx.save_for_backward(sigmas, rgbs, deltas, rays, ws, im)
+        ctx.dims = (M, N)
+        return ws, dp, im
+
+    @staticmethod
+    def backward(ctx, g_ws, g_dp, g_im):
+        R = ref.load("_raymarching")
+        sigmas, rgbs, deltas, rays, ws, im = ctx.saved_tensors
+        M, N = ctx.dims
+        gs, gr = torch.zeros_like(sigmas), torch.zeros_like(rgbs)
+        R.composite_rays_train_backward(g_ws.contiguous(), g_im.contiguous(), sigmas, rgbs, deltas, rays, ws, im, M, N, gs, gr)
+        return gs, gr, None, None
+
+
+def _pad128(x):
+    tail = -x.shape[0] % 128
+    return x if tail == 0 else torch.cat([x, x.new_zeros(tail, x.shape[1])])
+
+
+class RefStack(NeRFRenderer):
+    """parameters: `encoder.embeddings`, `w_sigma` (32-64-64-16), `w_color` (32-64-64-64-16): the layouts of GridEncoder / FFMLP"""
+
+    def __init__(self, bound=1, density_scale=1, min_near=0.2, density_thresh=0.01):
+        super().__init__(bound, cuda_ray=True, density_scale=density_scale, min_near=min_near, density_thresh=density_thresh, bg_radius=-1)
+        self.encoder = GridEncoder(desired_resolution=2048 * bound)
+        self.w_sigma = torch.nn.Parameter(torch.zeros(64 * (32 + 64 + 16)))
+        self.w_color = torch.nn.Parameter(torch.zeros(64 * (32 + 64 * 2 + 16)))
+        ref.load("_ffmlp").allocate_splitk(4)
+
+    def _h(self, x):
+        e = self.encoder
+        feat = _RefGrid.apply((x + self.bound) / (2 * self.bound), e.embeddings, e.offsets, e.per_level_scale, e.base_resolution)
+        n = feat.shape[0]
+        return _RefFFMLP.apply(_pad128(feat), self.w_sigma, 32, 2, False)[:n]
+
+    def density(self, x):
+        h = self._h(x)
+        return {'sigma': _RefTruncExp.apply(h[:, 0]), 'geo_feat': h[:, 1:]}
+
+    def forward(self, x, d):
+        """network_ff.py:51-73"""
+        h = self._h(x)
+        sigma = _RefTruncExp.apply(h[:, 0])
+        sh = _RefSH.apply(d, 4)
+        cin = torch.cat([sh, h[:, 1:], torch.zeros_like(h[:, :1])], dim=-1)
+        n = cin.shape[0]
+        y = _RefFFMLP.apply(_pad128(cin), self.w_color, 32, 3, True)[:n]
+        return sigma, torch.sigmoid(y[:, :3])
+
+    def render_train(self, rays_o, rays_d, bg_color=1, perturb=True, force_all_rays=False, max_steps=1024):
+        """training branch of NeRFRenderer.run_cuda (renderer.py:281-342) on the reference kernels"""
+        R = ref.load("_raymarching")
+        rays_o, rays_d = rays_o.contiguous().view(-1, 3), rays_d.contiguous().view(-1, 3)
+        N, dev = rays_o.shape[0], rays_o.device
+        nears, fars = torch.empty(N, device=dev), torch.empty(N, device=dev)
+        R.near_far_from_aabb(rays_o, rays_d, self.aabb_train, N, self.min_near, nears, fars)
+        counter = self.step_counter[self.local_step % 16]
+        counter.zero_()
+        self.local_step += 1
+        exact = force_all_rays or self.mean_count <= 0                       # raymarching.py:195-203
+        M = N * max_steps if exact else self.mean_count + (128 - self.mean_count % 128)
+        xyzs, dirs, deltas = torch.zeros(M, 3, device=dev), torch.zeros(M, 3, device=dev), torch.zeros(M, 2, device=dev)
+        rays = torch.empty(N, 3, dtype=torch.int32, device=dev)
+        R.march_rays_train(rays_o, rays_d, self.density_bitfield, float(self.bound), 0.0, max_steps, N, self.cascade, self.grid_size, M, nears, fars,
+                           xyzs, dirs, deltas, rays, counter, 1 if perturb else 0)
+        if exact:                                                            # raymarching.py:218-226
+            m = int(counter[0].item())
+            m = m + (128 - m % 128)
+            xyzs, dirs, deltas = xyzs[:m], dirs[:m], deltas[:m]
+        with torch.autocast("cuda", dtype=torch.float16):
+            sigmas, rgbs = self(xyzs, dirs)
+        sigmas = self.density_scale * sigmas
+        ws, depth, image = _RefComposite.apply(sigmas, rgbs, deltas, rays)
+        image = image + (1 - ws).unsqueeze(-1) * bg_color
+        depth = torch.clamp(depth - nears, min=0) / (fars - nears)
+        return {'image': image, 'depth': depth}

@@ -1,0 +1,156 @@
+#!/usr/bin/env python
+"""Training-level parity of the benchmarked hot path against the reference's OWN CUDA kernels (north star: "rendered PSNR within
+0.1 dB of the reference").
+
+Two trainings of the tiny synthetic scene (8 poses, 64x64 RGB, analytic shaded ball) from identical initial parameters, on identical
+ray batches, fp16 autocast + GradScaler, occupancy grid refreshed every 16 steps (nerf/utils.py:945-947), `max_steps` 1024:
+  reference : oracle/ref_chain.RefStack — nerf/network_ff.py + the training branch of NeRFRenderer.run_cuda chained on the reference's
+              unmodified extensions built for sm_100a (oracle/_ref): wmma/CUTLASS MLP with fp16 accumulation, fp16-atomic hash-grid
+              backward, thread-per-ray marcher and compositor; torch.optim.Adam
+  ours      : enerf_b200.nerf.network_ff.NeRFNetwork — warp-per-ray marcher, gather, tcgen05 fused field (recomputing backward),
+              walking scatter, FusedAdam
+Both parameter sets are then rendered with the same inference renderer (this repo's, eval mode) on the 8 training poses: PSNR vs the
+analytic target, their difference, and the PSNR between the two renderings.  `gradient_check()` compares the composed gradient of
+one training step (same bitfield, same samples) between the two stacks.
+
+  python tests/hotpath_parity.py [--steps 200] [--rays 1024] [--out profiles/x.json]
+Test infrastructure (imports oracle/): used by tests/test_gpu_hotpath_parity.py."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tests.psnr_parity import psnr, scene  # noqa: E402
+
+
+def _models(bound, dev, seed=0):
+    from enerf_b200.nerf.network_ff import NeRFNetwork
+    from oracle import ref_chain
+    torch.manual_seed(seed)
+    ours = NeRFNetwork(encoding="hashgrid", bound=bound, cuda_ray=True, density_scale=1, min_near=0.2, density_thresh=0.01, bg_radius=-1,
+                       out_dim_color=3).to(dev).train()
+    theirs = ref_chain.RefStack(bound=bound).to(dev).train()
+    with torch.no_grad():
+        theirs.encoder.embeddings.copy_(ours.encoder.embeddings)
+        theirs.w_sigma.copy_(ours.sigma_net.weights)
+        theirs.w_color.copy_(ours.color_net.weights)
+    return ours, theirs
+
+
+def _rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def gradient_check(n_rays=1024, bound=1, seed=0):
+    """one training step on identical samples (the occupancy bitfield of `ours` is given to both; the two marchers are bit-identical):
+    image / depth and the gradient of every parameter, tcgen05 stack vs reference kernels"""
+    dev = torch.device("cuda", 0)
+    ours, theirs = _models(bound, dev, seed)
+    with torch.no_grad():
+        ours.encoder.embeddings.uniform_(-0.5, 0.5)                # non-degenerate densities
+        theirs.encoder.embeddings.copy_(ours.encoder.embeddings)
+    torch.manual_seed(1)
+    with torch.autocast("cuda", dtype=torch.float16):
+        ours.update_extra_state()
+    theirs.density_grid.copy_(ours.density_grid)
+    theirs.density_bitfield.copy_(ours.density_bitfield)
+    o, d, rgb = scene(res=64, bound=bound)
+    idx = np.random.default_rng(seed).integers(0, len(o), size=n_rays)
+    go, gd, gt = (torch.from_numpy(a[idx]).to(dev) for a in (o, d, rgb))
+    scale = 1024.0                                                 # GradScaler's role: fp16 gradients out of the subnormal range
+    with torch.autocast("cuda", dtype=torch.float16):
+        out_o = ours.render(go[None], gd[None], staged=False, bg_color=1, perturb=True, force_all_rays=True, out_dim_color=3)
+    (F.mse_loss(out_o["image"].reshape(-1, 3).float(), gt) * scale).backward()
+    out_t = theirs.render_train(go, gd, bg_color=1, perturb=True, force_all_rays=True)
+    (F.mse_loss(out_t["image"].float(), gt) * scale).backward()
+    samples = (int(ours.step_counter[0, 0]), int(theirs.step_counter[0, 0]))
+    res = {"samples_ours": samples[0], "samples_reference": samples[1],
+           "image_max_abs_diff": float((out_o["image"].reshape(-1, 3).float() - out_t["image"].float()).abs().max()),
+           "depth_max_abs_diff": float((out_o["depth"].reshape(-1) - out_t["depth"]).abs().max()),
+           "grad_embeddings_rel_l2": _rel(ours.encoder.embeddings.grad, theirs.encoder.embeddings.grad),
+           "grad_sigma_net_rel_l2": _rel(ours.sigma_net.weights.grad, theirs.w_sigma.grad),
+           "grad_color_net_rel_l2": _rel(ours.color_net.weights.grad, theirs.w_color.grad),
+           "grad_embeddings_norm": float(theirs.encoder.embeddings.grad.norm())}
+    return res
+
+
+def run(steps=200, n_rays=1024, bound=1, lr=5e-3, seed=0, verbose=False):
+    from enerf_b200.optim import FusedAdam
+    dev = torch.device("cuda", 0)
+    ours, theirs = _models(bound, dev, seed)
+    o, d, rgb = scene(res=64, bound=bound)
+    go, gd, gt = (torch.from_numpy(a).to(dev) for a in (o, d, rgb))
+    opt_o = FusedAdam(ours.get_params(lr), betas=(0.9, 0.99), eps=1e-15)
+    opt_t = torch.optim.Adam(theirs.parameters(), lr=lr, betas=(0.9, 0.99), eps=1e-15)
+    sc_o, sc_t = torch.amp.GradScaler("cuda"), torch.amp.GradScaler("cuda")
+    rng = np.random.default_rng(seed)
+    log = []
+    for it in range(steps):
+        if it % 16 == 0:                                           # nerf/utils.py:945-947; same jitter seed for both refreshes
+            for m in (ours, theirs):
+                torch.manual_seed(1000 + it)
+                with torch.autocast("cuda", dtype=torch.float16):
+                    m.update_extra_state()
+        idx = torch.from_numpy(rng.integers(0, len(o), size=n_rays)).to(dev)
+        with torch.autocast("cuda", dtype=torch.float16):
+            out_o = ours.render(go[idx][None], gd[idx][None], staged=False, bg_color=1, perturb=True, out_dim_color=3)
+        loss_o = F.mse_loss(out_o["image"].reshape(-1, 3).float(), gt[idx])
+        opt_o.zero_grad(set_to_none=True)
+        sc_o.scale(loss_o).backward()
+        sc_o.step(opt_o)
+        sc_o.update()
+        out_t = theirs.render_train(go[idx], gd[idx], bg_color=1, perturb=True)
+        loss_t = F.mse_loss(out_t["image"].float(), gt[idx])
+        opt_t.zero_grad(set_to_none=True)
+        sc_t.scale(loss_t).backward()
+        sc_t.step(opt_t)
+        sc_t.update()
+        if it % 25 == 0 or it == steps - 1:
+            log.append((it, float(loss_o), float(loss_t)))
+            if verbose:
+                print(f"step {it:4d}  loss ours {float(loss_o):.6f}  reference kernels {float(loss_t):.6f}  samples {int(ours.step_counter[(ours.local_step - 1) % 16, 0])} / "
+                      f"{int(theirs.step_counter[(theirs.local_step - 1) % 16, 0])}", flush=True)
+    # render both parameter sets with the same inference renderer
+    images = {}
+    ours.eval()
+    state_ours = {k: v.detach().clone() for k, v in (("emb", ours.encoder.embeddings), ("ws", ours.sigma_net.weights), ("wc", ours.color_net.weights),
+                                                    ("grid", ours.density_grid), ("bits", ours.density_bitfield))}
+    state_ref = {"emb": theirs.encoder.embeddings.detach(), "ws": theirs.w_sigma.detach(), "wc": theirs.w_color.detach(), "grid": theirs.density_grid,
+                 "bits": theirs.density_bitfield}
+    for name, st in (("ours", state_ours), ("reference", state_ref)):
+        with torch.no_grad():
+            ours.encoder.embeddings.copy_(st["emb"])
+            ours.sigma_net.weights.copy_(st["ws"])
+            ours.color_net.weights.copy_(st["wc"])
+            ours.density_grid.copy_(st["grid"])
+            ours.density_bitfield.copy_(st["bits"])
+            parts = []
+            for s in range(0, len(o), 8192):
+                with torch.autocast("cuda", dtype=torch.float16):
+                    parts.append(ours.render(go[s:s + 8192][None], gd[s:s + 8192][None], staged=False, bg_color=1, perturb=False,
+                                             out_dim_color=3)["image"].reshape(-1, 3).float().cpu().numpy())
+            images[name] = np.concatenate(parts)
+    p_o, p_t = psnr(images["ours"], rgb), psnr(images["reference"], rgb)
+    return {"psnr_ours_db": p_o, "psnr_reference_kernels_db": p_t, "abs_diff_db": abs(p_o - p_t), "psnr_between_db": psnr(images["ours"], images["reference"]),
+            "final_loss_ours": log[-1][1], "final_loss_reference_kernels": log[-1][2], "loss_log": log, "steps": steps, "rays_per_batch": n_rays,
+            "config": "tiny synthetic scene (8 poses, 64x64 RGB), ff + cuda_ray, fp16 autocast + GradScaler, max_steps 1024, perturb on, "
+                      "update_extra_state every 16 steps; reference side = the reference's own CUDA build (oracle/_ref) chained as network_ff.py + run_cuda"}
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--rays", type=int, default=1024)
+    ap.add_argument("--out", default="")
+    a = ap.parse_args()
+    res = {"gradient_check": gradient_check(), "training": run(a.steps, a.rays, verbose=True)}
+    print(json.dumps(res))
+    if a.out:
+        with open(a.out, "w") as f:
+            json.dump(res, f, indent=1)

@@ -30,6 +30,7 @@ def train(exchange_cls, steps, rank, dev, graph=False, poison_at=-1):
     grid = synthetic.ball_density_grid(BOUND, model.cascade)
     model.density_grid.copy_(torch.from_numpy(grid))
     model.density_bitfield.copy_(torch.from_numpy(synthetic.packbits_np(grid)))
+    init = model.encoder.embeddings.detach().clone()
     opt = FusedAdam(model.get_params(5e-3), betas=(0.9, 0.99), eps=1e-15)
     scaler = torch.amp.GradScaler("cuda", init_scale=1024.0)
     ex = exchange_cls(model, opt)
@@ -68,7 +69,7 @@ def train(exchange_cls, steps, rank, dev, graph=False, poison_at=-1):
     with torch.autocast("cuda", dtype=torch.float16), torch.no_grad():
         model.encoder(o[:128], bound=BOUND)                 # makes sure the fp16 table is complete
     table16 = half_shadow(model.encoder.embeddings)[0].detach().float().clone()
-    return dict(table=model.encoder.embeddings.detach().clone(), table16=table16, ws=model.sigma_net.weights.detach().clone(),
+    return dict(init=init, table=model.encoder.embeddings.detach().clone(), table16=table16, ws=model.sigma_net.weights.detach().clone(),
                 wc=model.color_net.weights.detach().clone(), scales=scales)
 
 
@@ -81,12 +82,15 @@ def main():
     for graph in (False, True):
         a = train(parallel.AllReduceExchange, 6, rank, dev, graph)
         b = train(parallel.ShardedExchange, 6, rank, dev, graph)
-        torch.manual_seed(0)
-        init = torch.empty_like(a["table"]).uniform_(-0.2, 0.2)          # the table both runs started from
-        upd = float((a["table"] - init).abs().max())
+        assert torch.equal(a["init"], b["init"])
+        upd = float((a["table"] - a["init"]).abs().max())
         tag = "graph" if graph else "eager"
-        out[tag] = {"max_update": upd, "table_diff_rel": float((a["table"] - b["table"]).abs().max()) / upd,
-                    "table16_diff_rel": float((a["table16"] - b["table16"]).abs().max()) / upd,
+        moved = (a["table"] - a["init"]).abs() > 0
+        # Adam (eps 1e-15) turns any non-zero gradient into a full-size step, so entries whose gradient is within fp16 rounding of zero
+        # may move differently with the fp16 wire; what must agree is the bulk: relative L2 distance of the UPDATES
+        da, db = (a["table"] - a["init"]).double(), (b["table"] - a["init"]).double()
+        out[tag] = {"max_update": upd, "entries_moved": int(moved.sum()), "update_rel_l2": float((da - db).norm() / da.norm()),
+                    "table_diff_max_over_max_update": float((a["table"] - b["table"]).abs().max()) / upd,
                     "sigma_w_diff": float((a["ws"] - b["ws"]).abs().max()), "color_w_diff": float((a["wc"] - b["wc"]).abs().max())}
         ref = b["table16"].clone()
         dist.broadcast(ref, 0)
