@@ -15,10 +15,8 @@ Different underneath (B200-first):
     parameter's version counter), every other writer (torch optimizers, `copy_`, `load_state_dict`, EMA swaps) bumps the
     version and triggers a re-cast on the next forward;
   * embedding gradients are accumulated in fp32 and handed back in the parameter's dtype — the reference accumulates with
-    fp16 atomics when the table is fp16 (gridencoder.cu:296-302); `ENERF_GRID_GRAD_FP16=1` reproduces that.
+    fp16 atomics when the table is fp16 (gridencoder.cu:296-302); `set_grad_accumulation('fp16')` reproduces that (parity experiments).
 """
-import os
-
 import numpy as np
 import torch
 from torch import nn
@@ -28,6 +26,17 @@ from .backend import _backend
 
 _gridtype_to_id = {'hash': 0, 'tiled': 1}
 _ROW_LAYOUT = 1                      # out_layout of the C ABI: [B, L*C]
+_grad_accumulation = "fp32"
+
+
+def set_grad_accumulation(mode):
+    """'fp32' (default): embedding gradients are accumulated in fp32 reductions; 'fp16': in the table's dtype with fp16 atomics, as
+    the reference does under autocast (gridencoder.cu:296-302) — lossy, kept to reproduce the reference's numerics in parity runs."""
+    global _grad_accumulation
+    if mode not in ("fp32", "fp16"):
+        raise ValueError("grad accumulation must be 'fp32' or 'fp16'")
+    _grad_accumulation = mode
+
 
 
 def half_shadow(param, create=False):
@@ -81,7 +90,7 @@ class _grid_encode(torch.autograd.Function):
     def backward(ctx, d_feats):
         x, table, offsets, jac = ctx.saved_tensors
         d_feats = d_feats.contiguous().to(table.dtype)                 # [B, L*C], read in place by the scatter kernel
-        acc_dtype = table.dtype if os.environ.get('ENERF_GRID_GRAD_FP16', '0') == '1' else torch.float32
+        acc_dtype = table.dtype if _grad_accumulation == 'fp16' else torch.float32
         d_table = torch.zeros(table.shape, dtype=acc_dtype, device=table.device)
         d_x = torch.zeros_like(x, dtype=table.dtype) if ctx.want_dx else table.new_zeros(1)
         _backend.grid_encode_backward(d_feats, x, table, offsets, d_table, *ctx.geometry, ctx.want_dx, jac, d_x, ctx.gridtype, _ROW_LAYOUT)

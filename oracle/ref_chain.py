@@ -160,7 +160,7 @@ class RefStack(NeRFRenderer):
         e = self.encoder
         feat = _RefGrid.apply((x + self.bound) / (2 * self.bound), e.embeddings, e.offsets, e.per_level_scale, e.base_resolution)
         n = feat.shape[0]
-        return _RefFFMLP.apply(_pad128(feat), self.w_sigma, 32, 2, False)[:n]
+        return _RefFFMLP.apply(_pad128(feat), self.w_sigma, 32, 2, feat.requires_grad)[:n]       # ffmlp.py:161: calc_grad_inputs = inputs.requires_grad
 
     def density(self, x):
         h = self._h(x)
@@ -173,7 +173,7 @@ class RefStack(NeRFRenderer):
         sh = _RefSH.apply(d, 4)
         cin = torch.cat([sh, h[:, 1:], torch.zeros_like(h[:, :1])], dim=-1)
         n = cin.shape[0]
-        y = _RefFFMLP.apply(_pad128(cin), self.w_color, 32, 3, True)[:n]
+        y = _RefFFMLP.apply(_pad128(cin), self.w_color, 32, 3, cin.requires_grad)[:n]
         return sigma, torch.sigmoid(y[:, :3])
 
     def render_train(self, rays_o, rays_d, bg_color=1, perturb=True, force_all_rays=False, max_steps=1024):

@@ -80,7 +80,19 @@ def gradient_check(n_rays=1024, bound=1, seed=0):
     return res
 
 
-def run(steps=200, n_rays=1024, bound=1, lr=5e-3, seed=0, verbose=False):
+def run(steps=600, n_rays=1024, bound=1, lr=5e-3, seed=0, verbose=False, eval_last=5, eval_every=10, grad_accumulation="fp32"):
+    """grad_accumulation: 'fp32' = this repo's default; 'fp16' = embedding gradients accumulated with fp16 atomics like the reference
+    (gridencoder.cu:296-302), which shows how much of a PSNR difference is the reference's lossy accumulation and not the kernels"""
+    from enerf_b200.gridencoder import grid as grid_mod
+    from enerf_b200.optim import FusedAdam
+    grid_mod.set_grad_accumulation(grad_accumulation)
+    try:
+        return _run(steps, n_rays, bound, lr, seed, verbose, eval_last, eval_every, grad_accumulation)
+    finally:
+        grid_mod.set_grad_accumulation("fp32")
+
+
+def _run(steps, n_rays, bound, lr, seed, verbose, eval_last, eval_every, grad_accumulation):
     from enerf_b200.optim import FusedAdam
     dev = torch.device("cuda", 0)
     ours, theirs = _models(bound, dev, seed)
@@ -89,8 +101,37 @@ def run(steps=200, n_rays=1024, bound=1, lr=5e-3, seed=0, verbose=False):
     opt_o = FusedAdam(ours.get_params(lr), betas=(0.9, 0.99), eps=1e-15)
     opt_t = torch.optim.Adam(theirs.parameters(), lr=lr, betas=(0.9, 0.99), eps=1e-15)
     sc_o, sc_t = torch.amp.GradScaler("cuda"), torch.amp.GradScaler("cuda")
+    # the reference's schedule: lr * 0.1 ** (step / iters) (main_nerf.py:212)
+    sch_o = torch.optim.lr_scheduler.LambdaLR(opt_o, lambda it: 0.1 ** min(it / steps, 1))
+    sch_t = torch.optim.lr_scheduler.LambdaLR(opt_t, lambda it: 0.1 ** min(it / steps, 1))
     rng = np.random.default_rng(seed)
-    log = []
+    log, evals = [], []
+
+    def evaluate():
+        """PSNR of both parameter sets on the 8 training poses through the SAME inference renderer (this repo's, eval mode)"""
+        was = ours.training
+        ours.eval()
+        keep = {k: v.detach().clone() for k, v in (("emb", ours.encoder.embeddings), ("ws", ours.sigma_net.weights), ("wc", ours.color_net.weights),
+                                                 ("grid", ours.density_grid), ("bits", ours.density_bitfield))}
+        other = {"emb": theirs.encoder.embeddings.detach(), "ws": theirs.w_sigma.detach(), "wc": theirs.w_color.detach(), "grid": theirs.density_grid,
+                 "bits": theirs.density_bitfield}
+        images = {}
+        for name, st in (("reference", other), ("ours", keep)):          # `ours` last: its own state is back in place afterwards
+            with torch.no_grad():
+                ours.encoder.embeddings.copy_(st["emb"])
+                ours.sigma_net.weights.copy_(st["ws"])
+                ours.color_net.weights.copy_(st["wc"])
+                ours.density_grid.copy_(st["grid"])
+                ours.density_bitfield.copy_(st["bits"])
+                parts = []
+                for s0 in range(0, len(o), 8192):
+                    with torch.autocast("cuda", dtype=torch.float16):
+                        parts.append(ours.render(go[s0:s0 + 8192][None], gd[s0:s0 + 8192][None], staged=False, bg_color=1, perturb=False,
+                                                 out_dim_color=3)["image"].reshape(-1, 3).float().cpu().numpy())
+                images[name] = np.concatenate(parts)
+        ours.train(was)
+        return psnr(images["ours"], rgb), psnr(images["reference"], rgb), psnr(images["ours"], images["reference"])
+
     for it in range(steps):
         if it % 16 == 0:                                           # nerf/utils.py:945-947; same jitter seed for both refreshes
             for m in (ours, theirs):
@@ -105,51 +146,50 @@ def run(steps=200, n_rays=1024, bound=1, lr=5e-3, seed=0, verbose=False):
         sc_o.scale(loss_o).backward()
         sc_o.step(opt_o)
         sc_o.update()
+        sch_o.step()
         out_t = theirs.render_train(go[idx], gd[idx], bg_color=1, perturb=True)
         loss_t = F.mse_loss(out_t["image"].float(), gt[idx])
         opt_t.zero_grad(set_to_none=True)
         sc_t.scale(loss_t).backward()
         sc_t.step(opt_t)
         sc_t.update()
+        sch_t.step()
+        if it >= steps - eval_last * eval_every and (steps - 1 - it) % eval_every == 0:
+            evals.append((it,) + evaluate())
         if it % 25 == 0 or it == steps - 1:
             log.append((it, float(loss_o), float(loss_t)))
             if verbose:
                 print(f"step {it:4d}  loss ours {float(loss_o):.6f}  reference kernels {float(loss_t):.6f}  samples {int(ours.step_counter[(ours.local_step - 1) % 16, 0])} / "
                       f"{int(theirs.step_counter[(theirs.local_step - 1) % 16, 0])}", flush=True)
-    # render both parameter sets with the same inference renderer
-    images = {}
-    ours.eval()
-    state_ours = {k: v.detach().clone() for k, v in (("emb", ours.encoder.embeddings), ("ws", ours.sigma_net.weights), ("wc", ours.color_net.weights),
-                                                    ("grid", ours.density_grid), ("bits", ours.density_bitfield))}
-    state_ref = {"emb": theirs.encoder.embeddings.detach(), "ws": theirs.w_sigma.detach(), "wc": theirs.w_color.detach(), "grid": theirs.density_grid,
-                 "bits": theirs.density_bitfield}
-    for name, st in (("ours", state_ours), ("reference", state_ref)):
-        with torch.no_grad():
-            ours.encoder.embeddings.copy_(st["emb"])
-            ours.sigma_net.weights.copy_(st["ws"])
-            ours.color_net.weights.copy_(st["wc"])
-            ours.density_grid.copy_(st["grid"])
-            ours.density_bitfield.copy_(st["bits"])
-            parts = []
-            for s in range(0, len(o), 8192):
-                with torch.autocast("cuda", dtype=torch.float16):
-                    parts.append(ours.render(go[s:s + 8192][None], gd[s:s + 8192][None], staged=False, bg_color=1, perturb=False,
-                                             out_dim_color=3)["image"].reshape(-1, 3).float().cpu().numpy())
-            images[name] = np.concatenate(parts)
-    p_o, p_t = psnr(images["ours"], rgb), psnr(images["reference"], rgb)
-    return {"psnr_ours_db": p_o, "psnr_reference_kernels_db": p_t, "abs_diff_db": abs(p_o - p_t), "psnr_between_db": psnr(images["ours"], images["reference"]),
-            "final_loss_ours": log[-1][1], "final_loss_reference_kernels": log[-1][2], "loss_log": log, "steps": steps, "rays_per_batch": n_rays,
+    # both trainings are chaotic (different rounding -> diverging trajectories): the PSNR of a single checkpoint wobbles by more than the
+    # 0.1 dB the north star asks for, so the last `eval_last` checkpoints (every `eval_every` steps) are averaged
+    p_o, p_t = float(np.mean([e[1] for e in evals])), float(np.mean([e[2] for e in evals]))
+    return {"psnr_ours_db": p_o, "psnr_reference_kernels_db": p_t, "abs_diff_db": abs(p_o - p_t), "psnr_between_db": float(np.mean([e[3] for e in evals])),
+            "checkpoints": [{"step": e[0], "psnr_ours_db": e[1], "psnr_reference_kernels_db": e[2], "psnr_between_db": e[3]} for e in evals],
+            "psnr_std_over_checkpoints_db": [float(np.std([e[1] for e in evals])), float(np.std([e[2] for e in evals]))],
+            "grad_accumulation_ours": grad_accumulation, "final_loss_ours": log[-1][1], "final_loss_reference_kernels": log[-1][2], "loss_log": log, "steps": steps, "rays_per_batch": n_rays,
             "config": "tiny synthetic scene (8 poses, 64x64 RGB), ff + cuda_ray, fp16 autocast + GradScaler, max_steps 1024, perturb on, "
-                      "update_extra_state every 16 steps; reference side = the reference's own CUDA build (oracle/_ref) chained as network_ff.py + run_cuda"}
+                      "update_extra_state every 16 steps, lr 5e-3 * 0.1^(step/steps) (main_nerf.py:212); reference side = the reference's own CUDA build (oracle/_ref) chained as network_ff.py + run_cuda"}
 
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=600)
     ap.add_argument("--rays", type=int, default=1024)
     ap.add_argument("--out", default="")
+    ap.add_argument("--seeds", type=int, default=1, help="independent repetitions (different initial parameters and ray batches)")
     a = ap.parse_args()
     res = {"gradient_check": gradient_check(), "training": run(a.steps, a.rays, verbose=True)}
+    if a.seeds > 1:
+        # both trainings are chaotic and (atomics) not even reproducible run to run: the comparison is between MEANS over repetitions
+        runs = [res["training"]] + [run(a.steps, a.rays, seed=s, verbose=False) for s in range(1, a.seeds)]
+        po, pt = np.array([r["psnr_ours_db"] for r in runs]), np.array([r["psnr_reference_kernels_db"] for r in runs])
+        res["repetitions"] = {"seeds": a.seeds, "steps": a.steps, "psnr_ours_db": po.tolist(), "psnr_reference_kernels_db": pt.tolist(),
+                              "mean_ours_db": float(po.mean()), "mean_reference_kernels_db": float(pt.mean()),
+                              "mean_diff_db": float((po - pt).mean()), "stderr_of_mean_diff_db": float((po - pt).std(ddof=1) / np.sqrt(a.seeds)),
+                              "std_ours_db": float(po.std(ddof=1)), "std_reference_kernels_db": float(pt.std(ddof=1))}
+        print("repetitions", res["repetitions"])
+        res["training_fp16_grad_accumulation"] = run(a.steps, a.rays, verbose=False, grad_accumulation="fp16")
     print(json.dumps(res))
     if a.out:
         with open(a.out, "w") as f:

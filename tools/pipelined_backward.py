@@ -123,7 +123,7 @@ class _EncodedField(Function):
         geometry, gridtype, nl_sigma, nl_color, n_ch, dt_e, dt_s, dt_c = ctx.meta
         g_sigma = torch.zeros_like(sigma) if g_sigma is None else g_sigma.contiguous().float()
         g_rgb = torch.zeros_like(rgb) if g_rgb is None else g_rgb.contiguous().float()
-        acc_dtype = table.dtype if os.environ.get('ENERF_GRID_GRAD_FP16', '0') == '1' else torch.float32
+        acc_dtype = torch.float32
         d_table, gw_s, gw_c = pipelined_backward(g_sigma, g_rgb, sigma, rgb, cin, feat, x, table, offsets, geometry, gridtype, ws, wc,
                                                  nl_sigma, nl_color, n_ch, acc_dtype)
         return (None, None, d_table.to(dt_e), None, None, None, None, gw_s.to(dt_s), gw_c.to(dt_c), None, None, None, None)
