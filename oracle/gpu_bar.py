@@ -156,4 +156,56 @@ def measure(n_rays=4096, iters=5, bound=3, out_path="", verbose=False):
     both = [r for r in rows if "ours_ms" in r and "reference_build_ms" in r and "stores forward_buffer" not in r["kernel"] and "inference" not in r["kernel"]]
     res["training_step_kernels_ms"] = {"ours": round(sum(r["ours_ms"] for r in both), 4), "reference_build": round(sum(r["reference_build_ms"] for r in both), 4),
                                        "rows": [r["kernel"] for r in both]}
+    try:
+        res["full_step"] = full_step(n_rays, bound, iters)
+    except Exception as e:  # noqa: BLE001
+        res["full_step"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     return res
+
+
+def full_step(n_rays=4096, bound=3, iters=3):
+    """One whole training step (fwd + bwd + GradScaler + torch Adam, fp16 autocast, 3 colour channels) of the reference's hot path —
+    nerf/network_ff.py + NeRFRenderer.run_cuda chained by oracle/ref_chain.RefStack — (a) on the reference's own CUDA build and
+    (b) with the same unfused wrappers on this repo's kernels (INTEGRATION.md level 2: only `_backend` swapped).  ms per step, median."""
+    from . import ref_chain
+    dev = torch.device("cuda", torch.cuda.current_device())
+    o, d = synthetic.random_rays(n_rays, bound, seed=100)
+    o, d = torch.from_numpy(o).to(dev), torch.from_numpy(d).to(dev)
+    target = torch.rand(n_rays, 3, device=dev)
+    out = {"rays": n_rays, "unit": "ms per training step (eager launches, median of %d)" % iters}
+    for which in ("reference", "ours"):
+        ref_chain.use_backends(which)
+        try:
+            torch.manual_seed(0)
+            m = ref_chain.RefStack(bound=bound).to(dev).train()
+            with torch.no_grad():
+                m.encoder.embeddings.uniform_(-1e-4, 1e-4)
+                m.w_sigma.uniform_(-(3 / 64) ** 0.5, (3 / 64) ** 0.5)
+                m.w_color.uniform_(-(3 / 64) ** 0.5, (3 / 64) ** 0.5)
+            grid = synthetic.ball_density_grid(bound, m.cascade)
+            m.density_grid.copy_(torch.from_numpy(grid))
+            m.density_bitfield.copy_(torch.from_numpy(synthetic.packbits_np(grid)))
+            opt = torch.optim.Adam(m.parameters(), lr=5e-3, betas=(0.9, 0.99), eps=1e-15)
+            scaler = torch.amp.GradScaler("cuda")
+
+            def step():
+                res = m.render_train(o, d, bg_color=1, perturb=True)
+                loss = ((res["image"].float() - target) ** 2).mean()
+                opt.zero_grad(set_to_none=True)
+                scaler.scale(loss).backward()
+                scaler.step(opt)
+                scaler.update()
+
+            step()                                         # exact sizing (mean_count = 0), then fixed buffers like the trainer
+            m.mean_count = int(m.step_counter[0, 0].item())
+            key = "reference_build_ms" if which == "reference" else "reference_wrappers_on_this_repos_kernels_ms"
+            out[key] = timeit(step, iters)
+            out["samples_per_step"] = m.mean_count
+            del m, opt
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001
+            out[which + "_error"] = f"{type(e).__name__}: {e}"[:300]
+            torch.cuda.synchronize()
+        finally:
+            ref_chain.use_backends("reference")
+    return out

@@ -25,12 +25,33 @@ def available():
     return all(ref.available(n) for n in ref.NAMES)
 
 
+# which extension modules the wrappers below call: the reference's own build (default) or this repo's pybind-compatible backends
+# (enerf_b200/backends.py, the same 20 positional signatures) — the latter is "drop-in level 2" of INTEGRATION.md: the reference's
+# unfused Python wrappers kept, only `_backend` swapped
+_provider = "reference"
+
+
+def use_backends(which):
+    global _provider
+    if which not in ("reference", "ours"):
+        raise ValueError(which)
+    _provider = which
+
+
+def _ext(name):
+    if _provider == "reference":
+        return ref.load(name)
+    from enerf_b200 import backends
+    return {"_raymarching": backends.raymarching_backend, "_gridencoder": backends.gridencoder_backend, "_shencoder": backends.shencoder_backend,
+            "_ffmlp": backends.ffmlp_backend}[name]
+
+
 class _RefGrid(Function):
     """gridencoder/grid.py:19-88: fp16 table under autocast, outputs [L,B,C] permuted to [B,L*C], fp16 atomics in the backward"""
 
     @staticmethod
     def forward(ctx, inputs, embeddings, offsets, per_level_scale, base_resolution):
-        R = ref.load("_gridencoder")
+        R = _ext("_gridencoder")
         inputs = inputs.contiguous()
         table = embeddings.half().contiguous()                 # grid.py:38-39 (re-cast on every call)
         B, D = inputs.shape
@@ -45,7 +66,7 @@ class _RefGrid(Function):
 
     @staticmethod
     def backward(ctx, grad):
-        R = ref.load("_gridencoder")
+        R = _ext("_gridencoder")
         inputs, table, offsets = ctx.saved_tensors
         B, D, C, L, S, H = ctx.dims
         grad = grad.view(B, L, C).permute(1, 0, 2).contiguous().to(table.dtype)      # grid.py:70
@@ -60,7 +81,7 @@ class _RefSH(Function):
 
     @staticmethod
     def forward(ctx, dirs, degree):
-        R = ref.load("_shencoder")
+        R = _ext("_shencoder")
         x = dirs.half().contiguous()
         B = x.shape[0]
         out = torch.empty(B, degree ** 2, dtype=x.dtype, device=x.device)
@@ -78,7 +99,7 @@ class _RefFFMLP(Function):
 
     @staticmethod
     def forward(ctx, x, weights, in_dim, num_layers, calc_grad_inputs):
-        R = ref.load("_ffmlp")
+        R = _ext("_ffmlp")
         x = x.half().contiguous()
         w = weights.half().contiguous()
         B = x.shape[0]
@@ -91,7 +112,7 @@ class _RefFFMLP(Function):
 
     @staticmethod
     def backward(ctx, g):
-        R = ref.load("_ffmlp")
+        R = _ext("_ffmlp")
         x, w, fb = ctx.saved_tensors
         B, in_dim, nl, want_dx = ctx.dims
         g = g.half().contiguous()
@@ -122,7 +143,7 @@ class _RefComposite(Function):
 
     @staticmethod
     def forward(ctx, sigmas, rgbs, deltas, rays):
-        R = ref.load("_raymarching")
+        R = _ext("_raymarching")
         sigmas, rgbs = sigmas.float().contiguous(), rgbs.float().contiguous()
         M, N = sigmas.shape[0], rays.shape[0]
         ws, dp, im = (torch.empty(N, device=sigmas.device), torch.empty(N, device=sigmas.device), torch.empty(N, 3, device=sigmas.device))
@@ -133,7 +154,7 @@ class _RefComposite(Function):
 
     @staticmethod
     def backward(ctx, g_ws, g_dp, g_im):
-        R = ref.load("_raymarching")
+        R = _ext("_raymarching")
         sigmas, rgbs, deltas, rays, ws, im = ctx.saved_tensors
         M, N = ctx.dims
         gs, gr = torch.zeros_like(sigmas), torch.zeros_like(rgbs)
@@ -154,7 +175,7 @@ class RefStack(NeRFRenderer):
         self.encoder = GridEncoder(desired_resolution=2048 * bound)
         self.w_sigma = torch.nn.Parameter(torch.zeros(64 * (32 + 64 + 16)))
         self.w_color = torch.nn.Parameter(torch.zeros(64 * (32 + 64 * 2 + 16)))
-        ref.load("_ffmlp").allocate_splitk(4)
+        _ext("_ffmlp").allocate_splitk(4)
 
     def _h(self, x):
         e = self.encoder
@@ -178,7 +199,7 @@ class RefStack(NeRFRenderer):
 
     def render_train(self, rays_o, rays_d, bg_color=1, perturb=True, force_all_rays=False, max_steps=1024):
         """training branch of NeRFRenderer.run_cuda (renderer.py:281-342) on the reference kernels"""
-        R = ref.load("_raymarching")
+        R = _ext("_raymarching")
         rays_o, rays_d = rays_o.contiguous().view(-1, 3), rays_d.contiguous().view(-1, 3)
         N, dev = rays_o.shape[0], rays_o.device
         nears, fars = torch.empty(N, device=dev), torch.empty(N, device=dev)
