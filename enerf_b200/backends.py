@@ -69,24 +69,27 @@ class _Raymarching:
                                                              ptr(grad_rgbs), stream())
 
     @staticmethod
-    def march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid, nears, fars, xyzs, dirs, deltas, perturb):
-        need_cuda(rays_alive, rays_t, rays_o, rays_d, grid, nears, fars, xyzs, dirs, deltas)
-        _lib.call("enerf_march_rays", n_alive, n_step, ptr(rays_alive), ptr(rays_t), ptr(rays_o), ptr(rays_d), bound, dt_gamma,
-                                          max_steps, C, H, ptr(grid), ptr(nears), ptr(fars), ptr(xyzs), ptr(dirs), ptr(deltas),
-                                          int(perturb), stream())
+    def march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid, nears, fars, xyzs, dirs, deltas, perturb,
+                   n_alive_dev=None):
+        """`n_alive_dev` (extension, also on the two functions below): int32 device scalar with the true number of alive rays; `n_alive`
+        is then an upper bound and the host does not have to read the count back before launching"""
+        need_cuda(rays_alive, rays_t, rays_o, rays_d, grid, nears, fars, xyzs, dirs, deltas, n_alive_dev)
+        _lib.call("enerf_march_rays_dev", n_alive, n_step, ptr(rays_alive), ptr(rays_t), ptr(rays_o), ptr(rays_d), bound, dt_gamma,
+                                              max_steps, C, H, ptr(grid), ptr(nears), ptr(fars), ptr(xyzs), ptr(dirs), ptr(deltas),
+                                              int(perturb), ptr(n_alive_dev), stream())
 
     @staticmethod
-    def composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image):
-        need_cuda(rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image)
+    def composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image, n_alive_dev=None):
+        need_cuda(rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image, n_alive_dev)
         n_ch = rgbs.shape[-1] if rgbs.dim() > 1 else 1
-        _lib.call("enerf_composite_rays", n_alive, n_step, ptr(rays_alive), ptr(rays_t), ptr(sigmas), ptr(rgbs), ptr(deltas), n_ch,
-                                              ptr(weights_sum), ptr(depth), ptr(image), stream())
+        _lib.call("enerf_composite_rays_dev", n_alive, n_step, ptr(rays_alive), ptr(rays_t), ptr(sigmas), ptr(rgbs), ptr(deltas), n_ch,
+                                                  ptr(weights_sum), ptr(depth), ptr(image), ptr(n_alive_dev), stream())
 
     @staticmethod
-    def compact_rays(n_alive, rays_alive, rays_alive_old, rays_t, rays_t_old, alive_counter):
-        need_cuda(rays_alive, rays_alive_old, rays_t, rays_t_old, alive_counter)
-        _lib.call("enerf_compact_rays", n_alive, ptr(rays_alive), ptr(rays_alive_old), ptr(rays_t), ptr(rays_t_old),
-                                            ptr(alive_counter), stream())
+    def compact_rays(n_alive, rays_alive, rays_alive_old, rays_t, rays_t_old, alive_counter, n_alive_dev=None):
+        need_cuda(rays_alive, rays_alive_old, rays_t, rays_t_old, alive_counter, n_alive_dev)
+        _lib.call("enerf_compact_rays_dev", n_alive, ptr(rays_alive), ptr(rays_alive_old), ptr(rays_t), ptr(rays_t_old),
+                                                ptr(alive_counter), ptr(n_alive_dev), stream())
 
 
 class _GridEncoder:

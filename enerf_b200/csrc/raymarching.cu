@@ -405,15 +405,25 @@ k_march_rays_train(const float* __restrict__ rays_o, const float* __restrict__ r
     else march_warp<true>(r, c, grid, t0, far, num_steps, px, pd, pl);     // more emitting batches than the log holds: re-march
 }
 
+// The inference loop of NeRFRenderer.run_cuda (renderer.py:364-391) reads the number of alive rays back to the host after every
+// compaction.  Here the kernels also accept that count as a DEVICE pointer: `n_alive` is then only an upper bound (rays never come
+// back to life, so any earlier count is one) and slots at or beyond *n_alive_dev are skipped — the host can keep enqueueing rounds
+// and synchronise only every few rounds.
+__device__ __forceinline__ uint32_t alive_count(uint32_t n_alive, const int32_t* __restrict__ n_alive_dev) {
+    if (!n_alive_dev) return n_alive;
+    const int32_t v = *n_alive_dev;
+    return v < 0 ? 0u : min(n_alive, (uint32_t)v);
+}
+
 // raymarching.cu:700-804.  One warp per alive ray, at most n_step samples from rays_t.
 __global__ void __launch_bounds__(256)
 k_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* __restrict__ rays_alive,
              const float* __restrict__ rays_t, const float* __restrict__ rays_o,
              const float* __restrict__ rays_d, MarchCfg c, const uint8_t* __restrict__ grid,
              const float* __restrict__ nears, const float* __restrict__ fars, float* __restrict__ xyzs,
-             float* __restrict__ dirs, float* __restrict__ deltas, uint32_t perturb) {
+             float* __restrict__ dirs, float* __restrict__ deltas, uint32_t perturb, const int32_t* __restrict__ n_alive_dev) {
     const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (n >= n_alive) return;
+    if (n >= alive_count(n_alive, n_alive_dev)) return;
     const uint32_t index = (uint32_t)rays_alive[n];
     float t = rays_t[n];
     const Ray r = load_ray(rays_o, rays_d, index);
@@ -593,9 +603,9 @@ __global__ void k_composite_rays(uint32_t n_alive, uint32_t n_step, const int32_
                                  float* __restrict__ rays_t, const float* __restrict__ sigmas,
                                  const float* __restrict__ rgbs, const float* __restrict__ deltas,
                                  float* __restrict__ weights_sum, float* __restrict__ depth,
-                                 float* __restrict__ image) {
+                                 float* __restrict__ image, const int32_t* __restrict__ n_alive_dev) {
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= n_alive) return;
+    if (n >= alive_count(n_alive, n_alive_dev)) return;
     const uint32_t index = (uint32_t)rays_alive[n];
     float t = rays_t[n];
     sigmas += (size_t)n * n_step;
@@ -630,19 +640,101 @@ __global__ void k_composite_rays(uint32_t n_alive, uint32_t n_step, const int32_
     for (int ch = 0; ch < NCH; ++ch) image[index * NCH + ch] = c[ch];
 }
 
+// The same in-place accumulation with one WARP per ray, for rounds of many steps (the mirror's inference loop marches up to 2^23
+// samples per round, i.e. n_step in the tens or hundreds): the ray's n_step consecutive samples are read 32 at a time, fully coalesced;
+// T_i = (1 - ws) * prod_{j<i} (1 - alpha_j) comes from a multiplicative shuffle scan (mathematically the reference's running
+// `T = 1 - weight_sum`, raymarching.cu:872), t_i from an additive scan of deltas[:,1]; the two stopping rules become ballots:
+//   * a sample with delta == 0 is not consumed and ends the ray's round (padding written by march_rays);
+//   * a sample that sees T < 1e-5 IS consumed and then ends the ray (raymarching.cu:884) -> rays_t = -1.
+template <int NCH>
+__global__ void __launch_bounds__(256)
+k_composite_rays_warp(uint32_t n_alive, uint32_t n_step, const int32_t* __restrict__ rays_alive, float* __restrict__ rays_t,
+                      const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ deltas,
+                      float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image,
+                      const int32_t* __restrict__ n_alive_dev) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (n >= alive_count(n_alive, n_alive_dev)) return;
+    const unsigned lane = lane_id();
+    const uint32_t index = (uint32_t)rays_alive[n];
+    float t = rays_t[n];
+    sigmas += (size_t)n * n_step;
+    rgbs += (size_t)n * n_step * NCH;
+    deltas += (size_t)n * n_step * 2;
+    float T = 1.0f - weights_sum[index];           // transmittance in front of the first sample of this round
+    float acc_ws = 0.f, acc_d = 0.f, acc_c[NCH];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) acc_c[ch] = 0.f;
+    bool ended = false;
+    for (uint32_t base = 0; base < n_step && !ended; base += 32) {
+        const uint32_t i = base + lane;
+        const bool in = i < n_step;
+        float d0 = 0.f, d1 = 0.f, sg = 0.f;
+        if (in) {
+            const float2 dd = *reinterpret_cast<const float2*>(deltas + (size_t)i * 2);
+            d0 = dd.x;
+            d1 = dd.y;
+            sg = sigmas[i];
+        }
+        const bool real = in && d0 != 0.f;
+        const float alpha = real ? 1.0f - __expf(-sg * d0) : 0.f;
+        const float incl = scan_mul_incl(1.0f - alpha, lane);
+        float excl = __shfl_up_sync(kFull, incl, 1);
+        if (lane == 0) excl = 1.0f;
+        const float Ti = T * excl;                                   // transmittance seen by sample i
+        const float ti = t + scan_add_incl(real ? d1 : 0.f, lane);   // t after consuming sample i
+        // first sample that is padding (not consumed) / first consumed sample that saw T < 1e-5
+        const unsigned m_pad = __ballot_sync(kFull, !real);
+        const unsigned m_small = __ballot_sync(kFull, real && Ti < 1e-5f);
+        const uint32_t first_pad = m_pad ? (uint32_t)(__ffs(m_pad) - 1) : 32u;
+        const uint32_t first_small = m_small ? (uint32_t)(__ffs(m_small) - 1) : 32u;
+        const uint32_t consumed = min(first_pad, first_small + 1u);  // lanes [0, consumed) contribute
+        if (lane < consumed) {
+            const float w = alpha * Ti;
+            acc_ws += w;
+            acc_d += w * ti;
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) acc_c[ch] += w * rgbs[(size_t)i * NCH + ch];
+        }
+        const bool stop_small = first_small < 32u && first_small + 1u == consumed;      // the transmittance rule fired (no padding before it)
+        const bool stop_pad = first_pad < 32u && consumed == first_pad;                 // padding, or the end of the round's n_step samples
+        if (stop_small || stop_pad) {
+            ended = true;
+            if (consumed > 0) t = __shfl_sync(kFull, ti, consumed - 1);
+            // `step < n_step` in the reference <=> the ray stopped before using up every sample of the round: it is finished
+            if (stop_small || base + consumed < n_step) t = -1.0f;
+        } else {
+            t = __shfl_sync(kFull, ti, 31);
+            T *= __shfl_sync(kFull, incl, 31);
+        }
+    }
+    acc_ws = warp_sum(acc_ws);
+    acc_d = warp_sum(acc_d);
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) acc_c[ch] = warp_sum(acc_c[ch]);
+    if (lane == 0) {
+        rays_t[n] = t;
+        weights_sum[index] += acc_ws;
+        depth[index] += acc_d;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) image[index * NCH + ch] += acc_c[ch];
+    }
+}
+
 // raymarching.cu:912-930 with one atomic per warp (ballot-aggregated).
 __global__ void k_compact_rays(uint32_t n_alive, int32_t* __restrict__ rays_alive,
                                const int32_t* __restrict__ rays_alive_old, float* __restrict__ rays_t,
-                               const float* __restrict__ rays_t_old, int32_t* __restrict__ alive_counter) {
+                               const float* __restrict__ rays_t_old, int32_t* __restrict__ alive_counter,
+                               const int32_t* __restrict__ n_alive_dev) {
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = lane_id();
+    const uint32_t n_old = alive_count(n_alive, n_alive_dev);
     float t = -1.f;
     int32_t id = 0;
-    if (n < n_alive) {
+    if (n < n_old) {
         t = rays_t_old[n];
         id = rays_alive_old[n];
     }
-    const bool keep = (n < n_alive) && (t >= 0);
+    const bool keep = (n < n_old) && (t >= 0);
     const unsigned m = __ballot_sync(kFull, keep);
     if (!m) return;
     int base = 0;
@@ -759,37 +851,59 @@ int enerf_composite_rays_train_backward(const float* grad_weights_sum, const flo
     return 0;
 }
 
-int enerf_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
-                     const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps,
-                     uint32_t C, uint32_t H, const uint8_t* grid, const float* nears, const float* fars, float* xyzs,
-                     float* dirs, float* deltas, uint32_t perturb, void* stream) {
+int enerf_march_rays_dev(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
+                         const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps,
+                         uint32_t C, uint32_t H, const uint8_t* grid, const float* nears, const float* fars, float* xyzs,
+                         float* dirs, float* deltas, uint32_t perturb, const int32_t* n_alive_dev, void* stream) {
     if (n_alive == 0 || n_step == 0) return 0;
     ENERF_REQUIRE(C >= 1 && C <= 16 && H >= 2 && H <= 1024 && max_steps > 0, "march_rays", "bad C/H/max_steps");
     const MarchCfg c = make_cfg(bound, dt_gamma, max_steps, C, H);
     k_march_rays<<<ceil_div(n_alive, 8u), 256, 0, as_stream(stream)>>>(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, c,
-                                                                     grid, nears, fars, xyzs, dirs, deltas, perturb);
+                                                                     grid, nears, fars, xyzs, dirs, deltas, perturb, n_alive_dev);
     ENERF_CHECK_LAUNCH("march_rays");
     return 0;
 }
+int enerf_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
+                     const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps,
+                     uint32_t C, uint32_t H, const uint8_t* grid, const float* nears, const float* fars, float* xyzs,
+                     float* dirs, float* deltas, uint32_t perturb, void* stream) {
+    return enerf_march_rays_dev(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid, nears, fars, xyzs, dirs,
+                                deltas, perturb, nullptr, stream);
+}
 
-int enerf_composite_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, float* rays_t,
-                         const float* sigmas, const float* rgbs, const float* deltas, uint32_t n_ch,
-                         float* weights_sum, float* depth, float* image, void* stream) {
+int enerf_composite_rays_dev(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, float* rays_t,
+                             const float* sigmas, const float* rgbs, const float* deltas, uint32_t n_ch,
+                             float* weights_sum, float* depth, float* image, const int32_t* n_alive_dev, void* stream) {
     if (n_alive == 0) return 0;
-    ENERF_NCH_SWITCH(n_ch, "composite_rays",
-                     (k_composite_rays<NCH><<<ceil_div(n_alive, 128u), 128, 0, as_stream(stream)>>>(
-                         n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image)));
+    if (n_step > 8) {      // many steps per round: one warp per ray (coalesced, scans); the reference's n_step <= 8: one thread per ray
+        ENERF_NCH_SWITCH(n_ch, "composite_rays",
+                         (k_composite_rays_warp<NCH><<<ceil_div(n_alive, 8u), 256, 0, as_stream(stream)>>>(
+                             n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image, n_alive_dev)));
+    } else {
+        ENERF_NCH_SWITCH(n_ch, "composite_rays",
+                         (k_composite_rays<NCH><<<ceil_div(n_alive, 128u), 128, 0, as_stream(stream)>>>(
+                             n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image, n_alive_dev)));
+    }
     ENERF_CHECK_LAUNCH("composite_rays");
     return 0;
 }
+int enerf_composite_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, float* rays_t,
+                         const float* sigmas, const float* rgbs, const float* deltas, uint32_t n_ch,
+                         float* weights_sum, float* depth, float* image, void* stream) {
+    return enerf_composite_rays_dev(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, n_ch, weights_sum, depth, image, nullptr, stream);
+}
 
-int enerf_compact_rays(uint32_t n_alive, int32_t* rays_alive, const int32_t* rays_alive_old, float* rays_t,
-                       const float* rays_t_old, int32_t* alive_counter, void* stream) {
+int enerf_compact_rays_dev(uint32_t n_alive, int32_t* rays_alive, const int32_t* rays_alive_old, float* rays_t,
+                           const float* rays_t_old, int32_t* alive_counter, const int32_t* n_alive_dev, void* stream) {
     if (n_alive == 0) return 0;
     k_compact_rays<<<ceil_div(n_alive, 256u), 256, 0, as_stream(stream)>>>(n_alive, rays_alive, rays_alive_old, rays_t,
-                                                                          rays_t_old, alive_counter);
+                                                                          rays_t_old, alive_counter, n_alive_dev);
     ENERF_CHECK_LAUNCH("compact_rays");
     return 0;
+}
+int enerf_compact_rays(uint32_t n_alive, int32_t* rays_alive, const int32_t* rays_alive_old, float* rays_t,
+                       const float* rays_t_old, int32_t* alive_counter, void* stream) {
+    return enerf_compact_rays_dev(n_alive, rays_alive, rays_alive_old, rays_t, rays_t_old, alive_counter, nullptr, stream);
 }
 
 }  // extern "C"

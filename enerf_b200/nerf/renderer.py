@@ -11,7 +11,8 @@ Differences (results identical up to fp reassociation):
   * any number of colour channels 1..4 works in `run_cuda` (the reference is hard-wired to 3,
     renderer.py:341,354,400, while every E-NeRF config trains 1 channel);
   * the inference loop of `run_cuda` marches more steps per round (`inference_batch_samples`, default 2^23 samples per round;
-    0 restores the reference's `n_step <= 8`): same per-ray samples, same image, ~10x fewer host round trips;
+    0 restores the reference's `n_step <= 8`) — same per-ray samples and image with perturb off — and keeps the alive-ray count
+    on the device, reading it back every `inference_sync_every` rounds instead of after every compaction;
   * `render(staged=True)` takes the channel count from `self.out_dim_color` when the subclass
     defines it, else from `kwargs['out_dim_color']`, else 3 (the reference requires the attribute,
     renderer.py:581, and only nerf/network.py sets it).
@@ -73,8 +74,10 @@ class NeRFRenderer(nn.Module):
             self.register_buffer('step_counter', torch.zeros(16, 2, dtype=torch.int32))
             self.mean_count = 0
             self.local_step = 0
-        # samples per inference round (0 = exactly the reference's n_step policy); see run_cuda
+        # samples per inference round (0 = exactly the reference's n_step policy) and rounds between host reads of the alive count
+        # (1 = after every compaction, as the reference does); see run_cuda
         self.inference_batch_samples = 1 << 23
+        self.inference_sync_every = 4
 
     def forward(self, x, d):
         raise NotImplementedError()
@@ -194,41 +197,52 @@ class NeRFRenderer(nn.Module):
             weights_sum = torch.zeros(N, dtype=torch.float32, device=device)
             depth = torch.zeros(N, dtype=torch.float32, device=device)
             image = None
-            n_alive = N
-            alive_counter = torch.zeros([1], dtype=torch.int32, device=device)
-            rays_alive = torch.zeros(2, n_alive, dtype=torch.int32, device=device)
-            rays_t = torch.zeros(2, n_alive, dtype=torch.float32, device=device)
-            step, i = 0, 0
-            self.last_render_stats = {'samples': 0, 'iterations': 0}    # bookkeeping for bench.py (not in the reference)
+            rays_alive = torch.zeros(2, N, dtype=torch.int32, device=device)
+            rays_t = torch.zeros(2, N, dtype=torch.float32, device=device)
+            # The alive count lives on the device: counters[i % 2] = rays left after the compaction of round i.  The kernels take it as a
+            # pointer and `n_bound` (the last count the host has seen — an upper bound, rays never come back) only sizes the launches and
+            # buffers, so the host reads the counter every `inference_sync_every` rounds instead of after every compaction (renderer.py:374).
+            counters = torch.zeros(2, dtype=torch.int32, device=device)
+            count_dev = None
+            n_bound = N
+            shaded = torch.zeros(1, dtype=torch.int64, device=device)
+            step, i, since_sync, syncs = 0, 0, 0, 0
             while step < 1024:   # hard-coded in the reference as well (renderer.py:364)
                 if step == 0:
-                    torch.arange(n_alive, out=rays_alive[0])
+                    torch.arange(N, out=rays_alive[0])
                     rays_t[0] = nears
                 else:
-                    alive_counter.zero_()
-                    raymarching.compact_rays(n_alive, rays_alive[i % 2], rays_alive[(i + 1) % 2], rays_t[i % 2], rays_t[(i + 1) % 2], alive_counter)
-                    n_alive = alive_counter.item()
-                if n_alive <= 0:
+                    cur = counters[i % 2:i % 2 + 1]
+                    cur.zero_()
+                    raymarching.compact_rays(n_bound, rays_alive[i % 2], rays_alive[(i + 1) % 2], rays_t[i % 2], rays_t[(i + 1) % 2], cur, count_dev)
+                    count_dev = cur
+                    since_sync += 1
+                    if since_sync >= max(1, self.inference_sync_every):
+                        n_bound = min(n_bound, int(cur.item()))
+                        since_sync, syncs = 0, syncs + 1
+                if n_bound <= 0:
                     break
-                n_step = max(min(N // n_alive, 8), 1)          # the reference's policy (renderer.py:378)
+                n_step = max(min(N // n_bound, 8), 1)          # the reference's policy (renderer.py:378)
                 if self.inference_batch_samples > 0:
-                    # B200: march more steps per round while the batch stays below `inference_batch_samples`; the per-ray sample
-                    # sequence and compositing order do not depend on how the steps are grouped into rounds, so the image is the
-                    # same — only the number of Python rounds (each with a host sync on n_alive) drops from ~1000 to ~100.
-                    n_step = max(n_step, min(self.inference_batch_samples // n_alive, 1024 - step))
-                xyzs, dirs, deltas = raymarching.march_rays(n_alive, n_step, rays_alive[i % 2], rays_t[i % 2], rays_o, rays_d, self.bound,
+                    # B200: march more steps per round while the batch stays below `inference_batch_samples`.  With perturb off the per-ray
+                    # sample sequence and compositing order do not depend on how the steps are grouped into rounds, so the image is the same
+                    # (with perturb on, march_rays re-applies the jitter at the start of every round — raymarching.cu:742-745 —, so fewer
+                    # rounds draw fewer jitters: statistically equivalent, not sample-identical); the number of rounds drops from ~1000 to ~100.
+                    n_step = max(n_step, min(self.inference_batch_samples // n_bound, 1024 - step))
+                xyzs, dirs, deltas = raymarching.march_rays(n_bound, n_step, rays_alive[i % 2], rays_t[i % 2], rays_o, rays_d, self.bound,
                                                             self.density_bitfield, self.cascade, self.grid_size, nears, fars, 128, perturb,
-                                                            dt_gamma, max_steps)
+                                                            dt_gamma, max_steps, count_dev)
                 sigmas, rgbs = self(xyzs, dirs)
                 sigmas = self.density_scale * sigmas
                 if image is None:
                     n_ch = rgbs.shape[-1]
                     image = torch.zeros(N, n_ch, dtype=torch.float32, device=device)
-                raymarching.composite_rays(n_alive, n_step, rays_alive[i % 2], rays_t[i % 2], sigmas, rgbs, deltas, weights_sum, depth, image)
-                self.last_render_stats['samples'] += n_alive * n_step
-                self.last_render_stats['iterations'] += 1
+                raymarching.composite_rays(n_bound, n_step, rays_alive[i % 2], rays_t[i % 2], sigmas, rgbs, deltas, weights_sum, depth, image, count_dev)
+                shaded += (count_dev.long() if count_dev is not None else N) * n_step
                 step += n_step
                 i += 1
+            # bookkeeping for bench.py (not in the reference): samples actually shaded (alive rays x steps), rounds, host reads of the counter
+            self.last_render_stats = {'samples': int(shaded.item()), 'iterations': i, 'host_syncs': syncs}
             if image is None:
                 image = torch.zeros(N, kwargs.get("out_dim_color", getattr(self, "out_dim_color", 3)), dtype=torch.float32, device=device)
 

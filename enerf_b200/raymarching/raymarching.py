@@ -187,8 +187,9 @@ class _march_rays(Function):
     @staticmethod
     @_fwd32
     def forward(ctx, n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, density_bitfield, C, H, near, far, align=-1,
-                perturb=False, dt_gamma=0, max_steps=1024):
-        """March each alive ray up to n_step samples from rays_t; slots without a sample stay zero."""
+                perturb=False, dt_gamma=0, max_steps=1024, n_alive_dev=None):
+        """March each alive ray up to n_step samples from rays_t; slots without a sample stay zero.  `n_alive_dev` (extension): int32
+        device scalar holding the true alive count, `n_alive` then being an upper bound."""
         rays_o, rays_d = _rays(rays_o), _rays(rays_d)
         M = _pad_up(n_alive * n_step, align)
         dev = rays_o.device
@@ -196,7 +197,7 @@ class _march_rays(Function):
         dirs = torch.zeros(M, 3, dtype=torch.float32, device=dev)
         deltas = torch.zeros(M, 2, dtype=torch.float32, device=dev)
         _backend.march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, density_bitfield,
-                            near, far, xyzs, dirs, deltas, perturb)
+                            near, far, xyzs, dirs, deltas, perturb, n_alive_dev)
         return xyzs, dirs, deltas
 
 
@@ -206,9 +207,10 @@ march_rays = _march_rays.apply
 class _composite_rays(Function):
     @staticmethod
     @_fwd32
-    def forward(ctx, n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image):
+    def forward(ctx, n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image, n_alive_dev=None):
         """In-place accumulation into weights_sum/depth/image; rays_t <- -1 for terminated rays."""
-        _backend.composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas.contiguous(), rgbs.contiguous(), deltas, weights_sum, depth, image)
+        _backend.composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas.contiguous(), rgbs.contiguous(), deltas, weights_sum, depth, image,
+                                n_alive_dev)
         return tuple()
 
 
@@ -218,9 +220,9 @@ composite_rays = _composite_rays.apply
 class _compact_rays(Function):
     @staticmethod
     @_fwd32
-    def forward(ctx, n_alive, rays_alive, rays_alive_old, rays_t, rays_t_old, alive_counter):
+    def forward(ctx, n_alive, rays_alive, rays_alive_old, rays_t, rays_t_old, alive_counter, n_alive_dev=None):
         """Keep rays with rays_t_old >= 0; alive_counter[0] += number kept."""
-        _backend.compact_rays(n_alive, rays_alive, rays_alive_old, rays_t, rays_t_old, alive_counter)
+        _backend.compact_rays(n_alive, rays_alive, rays_alive_old, rays_t, rays_t_old, alive_counter, n_alive_dev)
         return tuple()
 
 

@@ -99,6 +99,20 @@ int enerf_compact_rays(uint32_t n_alive, int32_t* rays_alive, const int32_t* ray
                        float* rays_t, const float* rays_t_old, int32_t* alive_counter,
                        void* stream);
 
+/* The three inference-loop primitives with the alive count on the DEVICE (no reference counterpart): `n_alive` is then only an upper
+ * bound (any earlier count: rays never come back to life) and slots at or beyond *n_alive_dev are skipped, so NeRFRenderer.run_cuda's
+ * loop (renderer.py:364-391) need not read the counter back after every compaction (renderer.py:374).  n_alive_dev == NULL: as above.
+ * composite_rays with n_step > 8 runs one warp per ray (coalesced loads, shuffle scans) instead of the reference's thread per ray. */
+int enerf_march_rays_dev(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t, const float* rays_o,
+                         const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
+                         const uint8_t* grid, const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
+                         uint32_t perturb, const int32_t* n_alive_dev, void* stream);
+int enerf_composite_rays_dev(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, float* rays_t, const float* sigmas,
+                             const float* rgbs, const float* deltas, uint32_t n_ch, float* weights_sum, float* depth,
+                             float* image, const int32_t* n_alive_dev, void* stream);
+int enerf_compact_rays_dev(uint32_t n_alive, int32_t* rays_alive, const int32_t* rays_alive_old, float* rays_t,
+                           const float* rays_t_old, int32_t* alive_counter, const int32_t* n_alive_dev, void* stream);
+
 /* ------------------------------------------------------------------ gridencoder ---- */
 /* gridencoder/src/gridencoder.h:12-13, gridencoder/src/gridencoder.cu.
  * dtype = element type of embeddings/outputs/dy_dx/grad (ENERF_F32 | ENERF_F16); inputs are

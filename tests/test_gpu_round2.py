@@ -115,3 +115,73 @@ def test_composite_uniform_last_delta_after_upsampling():
     assert np.allclose(n(s_gpu.grad), ref_g, atol=2e-5 * max(1.0, np.abs(ref_g).max()), rtol=2e-3)
     W_old, _, _ = rm.composite_uniform(s_gpu.detach(), *args)    # num_steps = 0 -> (far-near)/T
     assert float((W_old[:, -1] - W[:, -1]).abs().max()) > 1e-3
+
+
+@pytest.mark.parametrize("n_step", [9, 32, 33, 100, 257])
+def test_warp_per_ray_inference_compositor_matches_oracle(n_step):
+    """composite_rays with n_step > 8 runs one warp per ray (the mirror's inference loop marches tens to hundreds of steps
+    per round, for which the thread-per-ray kernel reads strided).  Same results as the sequential oracle (raymarching.cu:842-899),
+    including both stopping rules (padding with delta == 0, transmittance < 1e-5), the rays_t = -1 marking and a device-side alive count
+    smaller than the launch bound."""
+    from oracle import oracle
+    from tests.gpu_common import scene, t
+    bound = 2
+    sc = scene(600, bound, seed=7)
+    N, n_alive = 600, 450
+    rng = np.random.default_rng(n_step)
+    alive_np = rng.permutation(N)[:n_alive].astype(np.int32)
+    t_np = sc["nears"][alive_np].copy()
+    wx, wd, wdl = oracle.march_rays(n_alive, n_step, alive_np, t_np, sc["o"], sc["d"], bound, sc["bits"], sc["cascade"], 128, sc["nears"], sc["fars"], perturb=0)
+    m = n_alive * n_step
+    # densities: a third of the rays nearly transparent, a third terminating by the transmittance rule, a third mixed
+    kind = rng.integers(0, 3, n_alive)
+    sig = (rng.uniform(0, 1, (n_alive, n_step)) * np.array([0.5, 3000.0, 150.0])[kind][:, None]).astype(np.float32).reshape(-1)
+    rgb = rng.random((m, 3)).astype(np.float32)
+    ws0, d0, im0 = rng.random(N).astype(np.float32) * 0.3, rng.random(N).astype(np.float32), rng.random((N, 3)).astype(np.float32)
+    wt, wws, wdp, wim = oracle.composite_rays(n_alive, n_step, alive_np, t_np, sig, rgb, wdl, ws0, d0, im0)
+    assert (wt < 0).any() and (wt >= 0).any()
+    for bound_n, dev_count in ((n_alive, None), (N, n_alive)):
+        gt, gws_, gdp, gim = torch.zeros(N, device=DEV), t(ws0), t(d0), t(im0)
+        gt[:n_alive] = t(t_np)
+        alive_pad = torch.zeros(N, dtype=torch.int32, device=DEV)
+        alive_pad[:n_alive] = t(alive_np)
+        pad = bound_n * n_step - m
+        sig_g = torch.cat([t(sig), torch.zeros(pad, device=DEV)])
+        rgb_g = torch.cat([t(rgb), torch.zeros(pad, 3, device=DEV)])
+        dl_g = torch.cat([t(wdl), torch.zeros(pad, 2, device=DEV)])
+        cnt = None if dev_count is None else torch.tensor([dev_count], dtype=torch.int32, device=DEV)
+        rm.composite_rays(bound_n, n_step, alive_pad, gt, sig_g, rgb_g, dl_g, gws_, gdp, gim, cnt)
+        got_t = n(gt)[:n_alive]
+        assert np.array_equal(got_t < 0, wt < 0)
+        assert np.allclose(got_t, wt, atol=1e-5) and np.allclose(n(gws_), wws, atol=2e-6) and np.allclose(n(gdp), wdp, atol=2e-5)
+        assert np.allclose(n(gim), wim, atol=2e-6)
+
+
+def test_inference_loop_without_per_round_sync_renders_the_same_image():
+    """run_cuda inference: reference policy (n_step <= 8, counter read after every compaction) vs large rounds with the alive count kept
+    on the device and read every 4 rounds — same image and depth (perturb off), far fewer host reads."""
+    from enerf_b200 import synthetic
+    from enerf_b200.nerf.network_ff import NeRFNetwork
+    from tests.gpu_common import t
+    bound = 2
+    torch.manual_seed(0)
+    model = NeRFNetwork(bound=bound, cuda_ray=True, out_dim_color=3).to(DEV).eval()
+    with torch.no_grad():
+        model.encoder.embeddings.uniform_(-2.0, 2.0)           # dense enough for rays to terminate at different depths
+    grid = synthetic.ball_density_grid(bound, model.cascade)
+    model.density_grid.copy_(t(grid))
+    model.density_bitfield.copy_(t(synthetic.packbits_np(grid)))
+    o, d = synthetic.random_rays(3000, bound, seed=4)
+    res = {}
+    for name, batch, every in (("reference_policy", 0, 1), ("large_rounds", 1 << 17, 1), ("device_count", 1 << 17, 4)):
+        model.inference_batch_samples, model.inference_sync_every = batch, every
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            out = model.render(t(o)[None], t(d)[None], staged=False, bg_color=1, perturb=False, out_dim_color=3)
+        res[name] = (out["image"][0].float(), out["depth"][0].float(), dict(model.last_render_stats))
+    a = res["reference_policy"]
+    for name in ("large_rounds", "device_count"):
+        b = res[name]
+        assert float((a[0] - b[0]).abs().max()) <= 2e-3 and float((a[1] - b[1]).abs().max()) <= 2e-3, name
+        assert b[2]["samples"] == a[2]["samples"], (a[2], b[2])
+    assert res["device_count"][2]["host_syncs"] * 3 <= res["large_rounds"][2]["host_syncs"]
+    assert res["large_rounds"][2]["iterations"] * 4 <= a[2]["iterations"]
