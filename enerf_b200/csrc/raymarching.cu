@@ -875,7 +875,9 @@ int enerf_composite_rays_dev(uint32_t n_alive, uint32_t n_step, const int32_t* r
                              const float* sigmas, const float* rgbs, const float* deltas, uint32_t n_ch,
                              float* weights_sum, float* depth, float* image, const int32_t* n_alive_dev, void* stream) {
     if (n_alive == 0) return 0;
-    if (n_step > 8) {      // many steps per round: one warp per ray (coalesced, scans); the reference's n_step <= 8: one thread per ray
+    // many steps per round: one warp per ray (coalesced, scans); few (the reference's n_step <= 8, and up to a warp's width, where most
+    // lanes of a warp-per-ray kernel would idle: measured 138 vs 126 ms per 800x800 frame at n_step = 13): one thread per ray
+    if (n_step >= 32) {
         ENERF_NCH_SWITCH(n_ch, "composite_rays",
                          (k_composite_rays_warp<NCH><<<ceil_div(n_alive, 8u), 256, 0, as_stream(stream)>>>(
                              n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image, n_alive_dev)));

@@ -102,7 +102,7 @@ int enerf_compact_rays(uint32_t n_alive, int32_t* rays_alive, const int32_t* ray
 /* The three inference-loop primitives with the alive count on the DEVICE (no reference counterpart): `n_alive` is then only an upper
  * bound (any earlier count: rays never come back to life) and slots at or beyond *n_alive_dev are skipped, so NeRFRenderer.run_cuda's
  * loop (renderer.py:364-391) need not read the counter back after every compaction (renderer.py:374).  n_alive_dev == NULL: as above.
- * composite_rays with n_step > 8 runs one warp per ray (coalesced loads, shuffle scans) instead of the reference's thread per ray. */
+ * composite_rays with n_step >= 32 runs one warp per ray (coalesced loads, shuffle scans) instead of the reference's thread per ray. */
 int enerf_march_rays_dev(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t, const float* rays_o,
                          const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
                          const uint8_t* grid, const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,

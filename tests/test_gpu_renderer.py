@@ -173,7 +173,8 @@ def test_run_cuda_inference_matches_training_composite():
         model.inference_batch_samples = 1 << 23
         e = model.render(t(o)[None], t(d)[None], bg_color=1, perturb=False, out_dim_color=1)
         rounds_big = model.last_render_stats["iterations"]
-    assert torch.equal(c["image"], e["image"]) and torch.equal(c["depth"], e["depth"])
+    # (rounds of 32+ steps are composited by the warp-per-ray kernel: same sums in a different order)
+    assert torch.allclose(c["image"], e["image"], atol=1e-5) and torch.allclose(c["depth"], e["depth"], atol=1e-4)
     assert rounds_big < rounds_ref
 
 
