@@ -474,7 +474,8 @@ def event_step_bench(args, dev, K):
 def run_variant_bench(args, dev, K, peaks):
     """What every shipped E-NeRF config executes (cuda_ray = False, ff = False, configs/*/*.txt:23-30): NeRFRenderer.run with 512 fixed
     steps per ray through the nerf/network.py topology — here on the tcgen05 kernels (enerf_b200/nerf/network.py), fp16 autocast,
-    4096 rays -> 2.10 M samples per step, fwd + bwd + GradScaler + Adam.  Eager launches (the colour mask makes shapes dynamic)."""
+    4096 rays -> 2.10 M samples per step, fwd + bwd + GradScaler + Adam.  The colour mask's row count stays on the device (every kernel of
+    the compacted colour batch reads it there), so the step has no host synchronisation and replays from a CUDA graph."""
     import torch
     import torch.nn.functional as F
     from enerf_b200 import _lib
@@ -501,6 +502,20 @@ def run_variant_bench(args, dev, K, peaks):
         scaler.update()
         return loss
 
+    eager, graphed = step, None
+    for i in range(3):
+        step(*batches[i % 2])
+    if args.graph in ("on", "auto"):      # no host synchronisation inside the step (the colour mask's count stays on the device): capturable
+        try:
+            from enerf_b200.graphs import GraphedStep
+            graphed = GraphedStep(eager, list(batches[0]), warmup=2)
+            step = graphed
+        except Exception as e:  # noqa: BLE001
+            if args.graph == "on":
+                raise
+            print(f"[bench] run_variant: graph capture failed ({type(e).__name__}: {e})", file=sys.stderr)
+            torch.cuda.synchronize()
+            step = eager
     for i in range(3):
         step(*batches[i % 2])
     torch.cuda.synchronize()
@@ -514,7 +529,7 @@ def run_variant_bench(args, dev, K, peaks):
     P = min(K, 5)
     _lib.profile_start()
     for i in range(P):
-        step(*batches[i % 2])
+        eager(*batches[i % 2])
     prof = _lib.profile_stop()
     S = n_rays * T
     work = {"enerf_grid_encode_forward": ("hbm", 588.0 * S), "enerf_grid_encode_backward": ("hbm", 1100.0 * S),
@@ -530,11 +545,14 @@ def run_variant_bench(args, dev, K, peaks):
         kernels[name.replace("enerf_", "")] = e
     out = {"workload": "shipped-config path (configs/*/*.txt: cuda_ray = False, ff = False): NeRFRenderer.run, 512 fixed steps/ray, nerf/network.py "
                        "topology (sigma-net 32-64-16, colour-net 31-64-64-1 on the weights > 1e-4 samples) on tcgen05, hashgrid bound 3, fp16 autocast; "
-                       "4096 rays, full train step (fwd+bwd+GradScaler+Adam), eager launches",
+                       "4096 rays, full train step (fwd+bwd+GradScaler+Adam)",
+           "launch": "cuda-graph replay" if graphed is not None else "eager",
            "rays": n_rays, "steps_per_ray": T, "samples_per_step": S, "steps": K, "ms_per_step": ms, "rays_per_s": n_rays / (ms * 1e-3),
            "msamples_per_s": S / (ms * 1e-3) / 1e6, "kernels": kernels, "kernels_sum_ms": sum(v["ms_per_step"] for v in kernels.values()),
            "mlp": "tcgen05 (enerf_field_density_* / enerf_field_color_*)" if "field_density_forward" in kernels else "nn.Linear (cuBLAS) fallback",
            "loss_finite": bool(torch.isfinite(loss))}
+    if graphed is not None:
+        graphed.graph = None
     del model, optimizer
     torch.cuda.empty_cache()
     return out

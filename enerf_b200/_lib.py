@@ -46,17 +46,17 @@ _SIGS = {
     "enerf_ffmlp_inference": [_p, _p, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _p, _p, _p],
     "enerf_ffmlp_backward": [_p, _p, _p, _p, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _int, _p, _p, _p, _int, _p, _p],
     "enerf_field_sigma_forward": [_p, _p, _p, _u32, _u32, _p, _p, _p, _p],
-    "enerf_field_color_forward": [_p, _p, _u32, _u32, _u32, _p, _p, _p],
-    "enerf_field_color_backward": [_p, _p, _u32, _p, _p, _p, _u32, _u32, _p, _p, _p],
+    "enerf_field_color_forward": [_p, _p, _u32, _u32, _u32, _p, _p, _p, _p],
+    "enerf_field_color_backward": [_p, _p, _u32, _p, _p, _p, _u32, _u32, _p, _p, _p, _p],
     "enerf_field_sigma_backward": [_p, _p, _p, _p, _p, _p, _u32, _u32, _p, _p, _p],
     "enerf_field_density_forward": [_p, _p, _u32, _u32, _p, _p, _p],
     "enerf_field_density_backward": [_p, _p, _p, _p, _p, _u32, _u32, _p, _p, _p],
-    "enerf_field_color_inputs": [_p, _u32, _p, _p, _u32, _u32, _f32, _p, _p],
-    "enerf_field_color_inputs_backward": [_p, _p, _u32, _p, _p],
+    "enerf_field_color_inputs": [_p, _u32, _p, _p, _u32, _u32, _f32, _p, _p, _p],
+    "enerf_field_color_inputs_backward": [_p, _p, _u32, _p, _p, _p],
     "enerf_compact_greater": [_p, _f32, _u32, _p, _p, _p, _p],
     "enerf_compact_mask": [_p, _u32, _p, _p, _p, _p],
-    "enerf_gather_rows": [_p, _p, _u32, _u32, _u32, _p, _p],
-    "enerf_scatter_rows": [_p, _p, _u32, _u32, _p, _p],
+    "enerf_gather_rows": [_p, _p, _u32, _u32, _u32, _p, _p, _p],
+    "enerf_scatter_rows": [_p, _p, _u32, _u32, _p, _p, _p],
     "enerf_weighted_sum_forward": [_p, _p, _u32, _u32, _u32, _p, _p],
     "enerf_weighted_sum_backward": [_p, _p, _p, _u32, _u32, _u32, _p, _p, _p],
     "enerf_occ_points_full": [_p, _u32, _u32, _f32, _p, _u64, _p],

@@ -355,16 +355,17 @@ int tc_backward(const __half* grad, const __half* x, const __half* W, const __ha
                 uint32_t B, int in_dim, int n_hidden_mm, cudaStream_t st);
 int tc_forward_sigma_head(const __half* feat, const __half* W, uint32_t B, int n_hidden_mm, __half* fwd_buf, const float* dirs, float* sigma,
                           __half* cin, cudaStream_t st);
-int tc_forward_rgb_head(const __half* cin, const __half* W, uint32_t B, int n_hidden_mm, __half* fwd_buf, float* rgb, int n_ch, cudaStream_t st);
+int tc_forward_rgb_head(const __half* cin, const __half* W, uint32_t B, int n_hidden_mm, __half* fwd_buf, float* rgb, int n_ch, const int32_t* n_rows_dev,
+                        cudaStream_t st);
 int tc_backward_rgb(const float* g_rgb, const float* rgb, int n_ch, const __half* cin, const __half* W, const __half* fwd_buf, __half* dcin, float* dW,
-                    uint32_t B, int n_hidden_mm, cudaStream_t st);
+                    uint32_t B, int n_hidden_mm, const int32_t* n_rows_dev, cudaStream_t st);
 void tc_set_max_ctas(int n);
 int tc_forward_density(const __half* feat, const __half* W, uint32_t B, int n_hidden_mm, float* sigma, __half* h, cudaStream_t st);
 int tc_backward_density(const float* g_sigma, const float* sigma, const __half* g_h, const __half* feat, const __half* W, __half* dfeat, float* dW,
                         uint32_t B, int n_hidden_mm, cudaStream_t st);
 int tc_color_inputs(const float* dirs, uint32_t dir_div, const __half* h, const int32_t* idx, uint32_t n, uint32_t n_pad, float sh_scale, __half* cin,
-                    cudaStream_t st);
-int tc_color_inputs_backward(const __half* dcin, const int32_t* idx, uint32_t n, __half* g_h, cudaStream_t st);
+                    const int32_t* n_dev, cudaStream_t st);
+int tc_color_inputs_backward(const __half* dcin, const int32_t* idx, uint32_t n, __half* g_h, const int32_t* n_dev, cudaStream_t st);
 int tc_backward_sigma(const float* g_sigma, const float* sigma, const __half* dcin, const __half* feat, const __half* W, const __half* fwd_buf,
                       __half* dfeat, float* dW, uint32_t B, int n_hidden_mm, cudaStream_t st);
 }
@@ -482,24 +483,24 @@ int enerf_field_sigma_forward(const uint16_t* feat, const uint16_t* weights, con
 }
 
 int enerf_field_color_forward(const uint16_t* cin, const uint16_t* weights, uint32_t B, uint32_t num_layers, uint32_t n_ch,
-                              uint16_t* forward_buffer, float* rgb, void* stream) {
+                              uint16_t* forward_buffer, float* rgb, const int32_t* n_rows_dev, void* stream) {
     if (int rc = field_check("field_color_forward", B, num_layers)) return rc;
     ENERF_REQUIRE(n_ch >= 1 && n_ch <= 4, "field_color_forward", "n_ch must be in [1,4]");
     if (B == 0) return 0;
     return tcm::tc_forward_rgb_head((const __half*)cin, (const __half*)weights, B, (int)num_layers - 1, (__half*)forward_buffer, rgb, (int)n_ch,
-                                    as_stream(stream));
+                                    n_rows_dev, as_stream(stream));
 }
 
 int enerf_field_color_backward(const float* grad_rgb, const float* rgb, uint32_t n_ch, const uint16_t* cin, const uint16_t* weights,
                                const uint16_t* forward_buffer, uint32_t B, uint32_t num_layers, uint16_t* grad_cin, float* grad_weights,
-                               void* stream) {
+                               const int32_t* n_rows_dev, void* stream) {
     if (int rc = field_check("field_color_backward", B, num_layers)) return rc;
     ENERF_REQUIRE(n_ch >= 1 && n_ch <= 4, "field_color_backward", "n_ch must be in [1,4]");
     const size_t n_w = (size_t)64 * (32 + (size_t)64 * (num_layers - 1) + 16);
     ENERF_CUDA(cudaMemsetAsync(grad_weights, 0, n_w * sizeof(float), as_stream(stream)), "field_color_backward");
     if (B == 0) return 0;
     return tcm::tc_backward_rgb(grad_rgb, rgb, (int)n_ch, (const __half*)cin, (const __half*)weights, (const __half*)forward_buffer,
-                                (__half*)grad_cin, grad_weights, B, (int)num_layers - 1, as_stream(stream));
+                                (__half*)grad_cin, grad_weights, B, (int)num_layers - 1, n_rows_dev, as_stream(stream));
 }
 
 int enerf_field_sigma_backward(const float* grad_sigma, const float* sigma, const uint16_t* grad_cin, const uint16_t* feat,
@@ -535,13 +536,13 @@ int enerf_field_density_backward(const float* grad_sigma, const float* sigma, co
 }
 
 int enerf_field_color_inputs(const float* dirs, uint32_t dir_div, const uint16_t* h, const int32_t* idx, uint32_t n, uint32_t n_pad, float sh_scale,
-                             uint16_t* cin, void* stream) {
+                             uint16_t* cin, const int32_t* n_dev, void* stream) {
     ENERF_REQUIRE(dir_div >= 1 && n_pad >= n && n_pad % 128 == 0, "field_color_inputs", "dir_div >= 1, n_pad >= n, n_pad a multiple of 128");
-    return tcm::tc_color_inputs(dirs, dir_div, (const __half*)h, idx, n, n_pad, sh_scale, (__half*)cin, as_stream(stream));
+    return tcm::tc_color_inputs(dirs, dir_div, (const __half*)h, idx, n, n_pad, sh_scale, (__half*)cin, n_dev, as_stream(stream));
 }
 
-int enerf_field_color_inputs_backward(const uint16_t* grad_cin, const int32_t* idx, uint32_t n, uint16_t* grad_h, void* stream) {
-    return tcm::tc_color_inputs_backward((const __half*)grad_cin, idx, n, (__half*)grad_h, as_stream(stream));
+int enerf_field_color_inputs_backward(const uint16_t* grad_cin, const int32_t* idx, uint32_t n, uint16_t* grad_h, const int32_t* n_dev, void* stream) {
+    return tcm::tc_color_inputs_backward((const __half*)grad_cin, idx, n, (__half*)grad_h, n_dev, as_stream(stream));
 }
 
 int enerf_ffmlp_uses_tcgen05(uint32_t input_dim, uint32_t hidden_dim, uint32_t num_layers, uint32_t activation, uint32_t output_activation) {

@@ -98,7 +98,15 @@ struct HeadArgs {
     __half* cin;         // [B,32] fp16                   (HEAD 1)
     float* rgb;          // [B,n_ch] fp32                 (HEAD 2)
     int n_ch;
+    const int32_t* n_rows_dev;   // optional: the number of valid rows lives on the device (B is then the capacity); tiles beyond it are skipped
 };
+
+// the tile count a kernel really processes when the row count is only known on the device (compacted batches, see field.py)
+__device__ __forceinline__ uint32_t effective_tiles(uint32_t n_tiles, const int32_t* __restrict__ n_rows_dev) {
+    if (!n_rows_dev) return n_tiles;
+    const int32_t v = *n_rows_dev;
+    return v <= 0 ? 0u : min(n_tiles, ((uint32_t)v + (uint32_t)kTile - 1u) / (uint32_t)kTile);
+}
 
 // real spherical harmonics up to l = 3 of (x,y,z) — the basis of shencoder.cu:51-69, fp32
 __device__ __forceinline__ void sh_deg4(float x, float y, float z, float (&o)[16]) {
@@ -180,6 +188,7 @@ k_tc_fwd_tma(const __grid_constant__ TmaDesc tm_x, const __grid_constant__ TmaDe
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem0 = *tmem_base_ptr;
+    n_tiles = effective_tiles(n_tiles, head.n_rows_dev);
     const uint32_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     if (warp == 0) {
@@ -431,8 +440,9 @@ int tc_forward_sigma_head(const __half* feat, const __half* W, uint32_t B, int n
     return launch_fwd<1>(feat, W, B, n_hidden_mm, fwd_buf, nullptr, h, st, "field_sigma_forward");
 }
 // colour-net with fused sigmoid head (input_dim 32)
-int tc_forward_rgb_head(const __half* cin, const __half* W, uint32_t B, int n_hidden_mm, __half* fwd_buf, float* rgb, int n_ch, cudaStream_t st) {
-    HeadArgs h = {nullptr, nullptr, nullptr, rgb, n_ch};
+int tc_forward_rgb_head(const __half* cin, const __half* W, uint32_t B, int n_hidden_mm, __half* fwd_buf, float* rgb, int n_ch, const int32_t* n_rows_dev,
+                        cudaStream_t st) {
+    HeadArgs h = {nullptr, nullptr, nullptr, rgb, n_ch, n_rows_dev};
     return launch_fwd<2>(cin, W, B, n_hidden_mm, fwd_buf, nullptr, h, st, "field_color_forward");
 }
 // density head: sigma (+ the 16 raw outputs when h != NULL) of a 1- or 2-layer sigma-net
@@ -478,6 +488,7 @@ struct ProArgs {
     const float* g_sigma;   // [B]       (PRO 2)
     const float* sigma;     // [B]       (PRO 2)
     const __half* dcin;     // [B,32]    (PRO 2)
+    const int32_t* n_rows_dev;   // optional device-side row count (see HeadArgs)
 };
 
 // ================================================================================================
@@ -545,6 +556,7 @@ k_tc_bwd_tma(const __grid_constant__ TmaDesc tm_h, const __grid_constant__ TmaDe
     tc_fence_after();
     const uint32_t tmem0 = *tmem_base_ptr;
 
+    n_tiles = effective_tiles(n_tiles, pro.n_rows_dev);
     const uint32_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     // TMEM columns: [slot s: D 64 | A 32] x NSLOTS, then the weight-gradient accumulators [dW_last^T : 16][dW_hidden j : 64 each][dW_0 : in_dim]
     constexpr uint32_t kAccLast = NSLOTS * kSlotCols, kAccHid = kAccLast + 16, kAcc0 = kAccHid + NH * 64;
@@ -957,6 +969,7 @@ k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ gra
     tc_fence_after();
     const uint32_t tmem0 = *tmem_base_ptr;
 
+    n_tiles = effective_tiles(n_tiles, pro.n_rows_dev);
     const uint32_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     constexpr uint32_t kAccLast = NSLOTS * kSlotCols, kAccHid = kAccLast + 16, kAcc0 = kAccHid + NH * 64;
     static_assert(kAcc0 + in_dim <= 512, "TMEM budget");
@@ -1373,8 +1386,8 @@ int tc_backward(const __half* grad, const __half* x, const __half* W, const __ha
     return launch_bwd_tma<0>(grad, x, W, fwd_buf, bwd_buf, grad_inputs, dW, B, in_dim, n_hidden_mm, none, st, "ffmlp_backward");
 }
 int tc_backward_rgb(const float* g_rgb, const float* rgb, int n_ch, const __half* cin, const __half* W, const __half* fwd_buf, __half* dcin, float* dW,
-                    uint32_t B, int n_hidden_mm, cudaStream_t st) {
-    ProArgs p = {g_rgb, rgb, n_ch, nullptr, nullptr, nullptr};
+                    uint32_t B, int n_hidden_mm, const int32_t* n_rows_dev, cudaStream_t st) {
+    ProArgs p = {g_rgb, rgb, n_ch, nullptr, nullptr, nullptr, n_rows_dev};
     if (!fwd_buf) return launch_bwd_rc<1>(nullptr, cin, W, dcin, dW, B, 32, n_hidden_mm, p, st, "field_color_backward");
     return launch_bwd_tma<1>(nullptr, cin, W, fwd_buf, nullptr, dcin, dW, B, 32, n_hidden_mm, p, st, "field_color_backward");
 }
@@ -1399,8 +1412,12 @@ int tc_backward_density(const float* g_sigma, const float* sigma, const __half* 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_color_inputs(const float* __restrict__ dirs, uint32_t dir_div, const __half* __restrict__ h, const int32_t* __restrict__ idx, uint32_t n, uint32_t n_pad,
-               float sh_scale, __half* __restrict__ cin) {
+               float sh_scale, __half* __restrict__ cin, const int32_t* __restrict__ n_dev) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_dev) {                                   // row count on the device: n = capacity; rows up to the next tile boundary are zero-filled
+        n = min(n, (uint32_t)max(*n_dev, 0));
+        n_pad = min(n_pad, (n + (uint32_t)kTile - 1u) / (uint32_t)kTile * (uint32_t)kTile);
+    }
     if (i >= n_pad) return;
     int4* o = reinterpret_cast<int4*>(cin + (size_t)i * 32);
     if (i >= n) {
@@ -1424,8 +1441,10 @@ k_color_inputs(const float* __restrict__ dirs, uint32_t dir_div, const __half* _
 }
 // backward of the above w.r.t. h: g_h[idx[i], 1:16] = dcin[i, 16:31], g_h[idx[i], 0] = 0 (g_h zero-initialised by the caller)
 __global__ void __launch_bounds__(256)
-k_color_inputs_bwd(const __half* __restrict__ dcin, const int32_t* __restrict__ idx, uint32_t n, __half* __restrict__ g_h) {
+k_color_inputs_bwd(const __half* __restrict__ dcin, const int32_t* __restrict__ idx, uint32_t n, __half* __restrict__ g_h,
+                   const int32_t* __restrict__ n_dev) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_dev) n = min(n, (uint32_t)max(*n_dev, 0));
     if (i >= n) return;
     const int4* src = reinterpret_cast<const int4*>(dcin + (size_t)i * 32 + 16);
     const int4 a = __ldg(src), b = __ldg(src + 1);
@@ -1440,15 +1459,15 @@ k_color_inputs_bwd(const __half* __restrict__ dcin, const int32_t* __restrict__ 
 }
 
 int tc_color_inputs(const float* dirs, uint32_t dir_div, const __half* h, const int32_t* idx, uint32_t n, uint32_t n_pad, float sh_scale, __half* cin,
-                    cudaStream_t st) {
+                    const int32_t* n_dev, cudaStream_t st) {
     if (n_pad == 0) return 0;
-    k_color_inputs<<<ceil_div(n_pad, 256u), 256, 0, st>>>(dirs, dir_div, h, idx, n, n_pad, sh_scale, cin);
+    k_color_inputs<<<ceil_div(n_pad, 256u), 256, 0, st>>>(dirs, dir_div, h, idx, n, n_pad, sh_scale, cin, n_dev);
     ENERF_CHECK_LAUNCH("field_color_inputs");
     return 0;
 }
-int tc_color_inputs_backward(const __half* dcin, const int32_t* idx, uint32_t n, __half* g_h, cudaStream_t st) {
+int tc_color_inputs_backward(const __half* dcin, const int32_t* idx, uint32_t n, __half* g_h, const int32_t* n_dev, cudaStream_t st) {
     if (n == 0) return 0;
-    k_color_inputs_bwd<<<ceil_div(n, 256u), 256, 0, st>>>(dcin, idx, n, g_h);
+    k_color_inputs_bwd<<<ceil_div(n, 256u), 256, 0, st>>>(dcin, idx, n, g_h, n_dev);
     ENERF_CHECK_LAUNCH("field_color_inputs_backward");
     return 0;
 }

@@ -336,16 +336,22 @@ k_mark_untrained(float* __restrict__ grid, const float* __restrict__ poses, uint
 // dst[i] = src[idx[i]] for i < n, zero rows for n <= i < n_pad
 __global__ void __launch_bounds__(256)
 k_gather_rows(const uint32_t* __restrict__ src, const int32_t* __restrict__ idx, uint32_t n, uint32_t n_pad, uint32_t wpr,
-              uint32_t* __restrict__ dst) {
+              uint32_t* __restrict__ dst, const int32_t* __restrict__ n_dev) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_dev) {                                   // row count on the device: n = capacity, zero rows up to the next multiple of 128
+        n = min(n, (uint32_t)max(*n_dev, 0));
+        n_pad = min(n_pad, (n + 127u) / 128u * 128u);
+    }
     if (t >= (uint64_t)n_pad * wpr) return;
     const uint32_t i = (uint32_t)(t / wpr), w = (uint32_t)(t - (uint64_t)i * wpr);
     dst[t] = (i < n) ? src[(size_t)idx[i] * wpr + w] : 0u;
 }
 // dst[idx[i]] = src[i] for i < n (dst pre-initialised by the caller)
 __global__ void __launch_bounds__(256)
-k_scatter_rows(const uint32_t* __restrict__ src, const int32_t* __restrict__ idx, uint32_t n, uint32_t wpr, uint32_t* __restrict__ dst) {
+k_scatter_rows(const uint32_t* __restrict__ src, const int32_t* __restrict__ idx, uint32_t n, uint32_t wpr, uint32_t* __restrict__ dst,
+               const int32_t* __restrict__ n_dev) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_dev) n = min(n, (uint32_t)max(*n_dev, 0));
     if (t >= (uint64_t)n * wpr) return;
     const uint32_t i = (uint32_t)(t / wpr), w = (uint32_t)(t - (uint64_t)i * wpr);
     dst[(size_t)idx[i] * wpr + w] = src[t];
@@ -484,22 +490,22 @@ int enerf_mark_untrained_grid(float* density_grid, const float* poses, uint32_t 
     return 0;
 }
 
-int enerf_gather_rows(const void* src, const int32_t* idx, uint32_t n, uint32_t n_pad, uint32_t row_bytes, void* dst, void* stream) {
+int enerf_gather_rows(const void* src, const int32_t* idx, uint32_t n, uint32_t n_pad, uint32_t row_bytes, void* dst, const int32_t* n_dev, void* stream) {
     ENERF_REQUIRE(row_bytes % 4 == 0 && row_bytes > 0 && n_pad >= n, "gather_rows", "row_bytes must be a positive multiple of 4, n_pad >= n");
     if (n_pad == 0) return 0;
     const uint32_t wpr = row_bytes / 4;
     const uint64_t total = (uint64_t)n_pad * wpr;
-    k_gather_rows<<<(uint32_t)ceil_div(total, (uint64_t)256), 256, 0, as_stream(stream)>>>((const uint32_t*)src, idx, n, n_pad, wpr, (uint32_t*)dst);
+    k_gather_rows<<<(uint32_t)ceil_div(total, (uint64_t)256), 256, 0, as_stream(stream)>>>((const uint32_t*)src, idx, n, n_pad, wpr, (uint32_t*)dst, n_dev);
     ENERF_CHECK_LAUNCH("gather_rows");
     return 0;
 }
 
-int enerf_scatter_rows(const void* src, const int32_t* idx, uint32_t n, uint32_t row_bytes, void* dst, void* stream) {
+int enerf_scatter_rows(const void* src, const int32_t* idx, uint32_t n, uint32_t row_bytes, void* dst, const int32_t* n_dev, void* stream) {
     ENERF_REQUIRE(row_bytes % 4 == 0 && row_bytes > 0, "scatter_rows", "row_bytes must be a positive multiple of 4");
     if (n == 0) return 0;
     const uint32_t wpr = row_bytes / 4;
     const uint64_t total = (uint64_t)n * wpr;
-    k_scatter_rows<<<(uint32_t)ceil_div(total, (uint64_t)256), 256, 0, as_stream(stream)>>>((const uint32_t*)src, idx, n, wpr, (uint32_t*)dst);
+    k_scatter_rows<<<(uint32_t)ceil_div(total, (uint64_t)256), 256, 0, as_stream(stream)>>>((const uint32_t*)src, idx, n, wpr, (uint32_t*)dst, n_dev);
     ENERF_CHECK_LAUNCH("scatter_rows");
     return 0;
 }

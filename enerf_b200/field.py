@@ -45,7 +45,7 @@ class _FusedField(Function):
         fb_s = torch.empty(nl_sigma, S, 64, dtype=torch.float16, device=dev) if store else None
         fb_c = torch.empty(nl_color, S, 64, dtype=torch.float16, device=dev) if store else None
         _lib.call("enerf_field_sigma_forward", ptr(feat), ptr(ws), ptr(dirs), S, nl_sigma, ptr(fb_s), ptr(sigma), ptr(cin), stream())
-        _lib.call("enerf_field_color_forward", ptr(cin), ptr(wc), S, nl_color, n_ch, ptr(fb_c), ptr(rgb), stream())
+        _lib.call("enerf_field_color_forward", ptr(cin), ptr(wc), S, nl_color, n_ch, ptr(fb_c), ptr(rgb), None, stream())
         if training:
             saved = [feat, ws, wc, sigma, cin, rgb] + ([fb_s, fb_c] if store else [])
             ctx.save_for_backward(*saved)
@@ -66,7 +66,7 @@ class _FusedField(Function):
         dfeat = torch.empty(S, 32, dtype=torch.float16, device=dev)
         gw_c = torch.empty(wc.numel(), dtype=torch.float32, device=dev)
         gw_s = torch.empty(ws.numel(), dtype=torch.float32, device=dev)
-        _lib.call("enerf_field_color_backward", ptr(g_rgb), ptr(rgb), n_ch, ptr(cin), ptr(wc), ptr(fb_c), S, nl_color, ptr(dcin), ptr(gw_c), stream())
+        _lib.call("enerf_field_color_backward", ptr(g_rgb), ptr(rgb), n_ch, ptr(cin), ptr(wc), ptr(fb_c), S, nl_color, ptr(dcin), ptr(gw_c), None, stream())
         _lib.call("enerf_field_sigma_backward", ptr(g_sigma), ptr(sigma), ptr(dcin), ptr(feat), ptr(ws), ptr(fb_s), S, nl_sigma, ptr(dfeat),
                   ptr(gw_s), stream())
         return dfeat, None, gw_s.to(dt_s), gw_c.to(dt_c), None, None, None, None
@@ -141,41 +141,44 @@ def density_only(feat, w_sigma, num_layers):
 
 
 class _MaskedColor(Function):
-    """h [B,16] fp16, dirs [B/dir_div,3] fp32, idx [n] int32 (selected samples, increasing), flat colour-net weights ->
-    rgbs [B,n_ch] fp32 with sigmoid(colour-net) on the selected rows and zeros elsewhere (network.py:171-199)."""
+    """h [B,16] fp16, dirs [B/dir_div,3] fp32, idx [cap] int32 (selected samples, increasing; the first `count` entries are valid), flat
+    colour-net weights -> rgbs [B,n_ch] fp32 with sigmoid(colour-net) on the selected rows and zeros elsewhere (network.py:171-199).
+    `count`: int32 device scalar (from `raymarching.compact_mask`) or None (= all of idx).  The count never travels to the host: every
+    kernel reads it from the device and skips the tiles / rows beyond it, so the whole render stays capturable in a CUDA graph."""
 
     @staticmethod
-    def forward(ctx, h, dirs, dir_div, idx, w_color, n_ch, sh_scale):
-        B, n = h.shape[0], idx.shape[0]
+    def forward(ctx, h, dirs, dir_div, idx, count, w_color, n_ch, sh_scale):
+        B, cap = h.shape[0], idx.shape[0]
         dev = h.device
-        n_pad = -(-n // 128) * 128
+        cap_pad = -(-cap // 128) * 128
         h = h.contiguous()
         wc = w_color.detach().half().contiguous()
-        cin = torch.empty(n_pad, 32, dtype=torch.float16, device=dev)
-        _lib.call("enerf_field_color_inputs", ptr(dirs), dir_div, ptr(h), ptr(idx), n, n_pad, float(sh_scale), ptr(cin), stream())
-        rgb_c = torch.empty(n_pad, n_ch, dtype=torch.float32, device=dev)
-        _lib.call("enerf_field_color_forward", ptr(cin), ptr(wc), n_pad, 2, n_ch, None, ptr(rgb_c), stream())
+        cin = torch.empty(cap_pad, 32, dtype=torch.float16, device=dev)
+        _lib.call("enerf_field_color_inputs", ptr(dirs), dir_div, ptr(h), ptr(idx), cap, cap_pad, float(sh_scale), ptr(cin), ptr(count), stream())
+        rgb_c = torch.empty(cap_pad, n_ch, dtype=torch.float32, device=dev)
+        _lib.call("enerf_field_color_forward", ptr(cin), ptr(wc), cap_pad, 2, n_ch, None, ptr(rgb_c), ptr(count), stream())
         rgbs = torch.zeros(B, n_ch, dtype=torch.float32, device=dev)
-        _lib.call("enerf_scatter_rows", ptr(rgb_c), ptr(idx), n, 4 * n_ch, ptr(rgbs), stream())
-        ctx.save_for_backward(cin, wc, rgb_c, idx)
-        ctx.meta = (B, n, n_pad, n_ch, w_color.dtype)
+        _lib.call("enerf_scatter_rows", ptr(rgb_c), ptr(idx), cap, 4 * n_ch, ptr(rgbs), ptr(count), stream())
+        ctx.save_for_backward(cin, wc, rgb_c, idx, count if count is not None else idx.new_empty(0))
+        ctx.meta = (B, cap, cap_pad, n_ch, w_color.dtype, count is not None)
         return rgbs
 
     @staticmethod
     def backward(ctx, g_rgbs):
-        cin, wc, rgb_c, idx = ctx.saved_tensors
-        B, n, n_pad, n_ch, dt = ctx.meta
+        cin, wc, rgb_c, idx, count = ctx.saved_tensors
+        B, cap, cap_pad, n_ch, dt, has_count = ctx.meta
+        count = count if has_count else None
         dev = cin.device
         g_rgbs = g_rgbs.contiguous().float()
-        g_c = torch.empty(n_pad, n_ch, dtype=torch.float32, device=dev)
-        _lib.call("enerf_gather_rows", ptr(g_rgbs), ptr(idx), n, n_pad, 4 * n_ch, ptr(g_c), stream())
-        dcin = torch.empty(n_pad, 32, dtype=torch.float16, device=dev)
+        g_c = torch.empty(cap_pad, n_ch, dtype=torch.float32, device=dev)
+        _lib.call("enerf_gather_rows", ptr(g_rgbs), ptr(idx), cap, cap_pad, 4 * n_ch, ptr(g_c), ptr(count), stream())
+        dcin = torch.empty(cap_pad, 32, dtype=torch.float16, device=dev)
         gw = torch.empty(wc.numel(), dtype=torch.float32, device=dev)
-        _lib.call("enerf_field_color_backward", ptr(g_c), ptr(rgb_c), n_ch, ptr(cin), ptr(wc), None, n_pad, 2, ptr(dcin), ptr(gw), stream())
+        _lib.call("enerf_field_color_backward", ptr(g_c), ptr(rgb_c), n_ch, ptr(cin), ptr(wc), None, cap_pad, 2, ptr(dcin), ptr(gw), ptr(count), stream())
         g_h = torch.zeros(B, 16, dtype=torch.float16, device=dev)
-        _lib.call("enerf_field_color_inputs_backward", ptr(dcin), ptr(idx), n, ptr(g_h), stream())
-        return g_h, None, None, None, gw.to(dt), None, None
+        _lib.call("enerf_field_color_inputs_backward", ptr(dcin), ptr(idx), cap, ptr(g_h), ptr(count), stream())
+        return g_h, None, None, None, None, gw.to(dt), None, None
 
 
-def masked_color(h, dirs, dir_div, idx, w_color, n_ch, sh_scale=1.0):
-    return _MaskedColor.apply(h, dirs.contiguous().float(), int(dir_div), idx, w_color, int(n_ch), float(sh_scale))
+def masked_color(h, dirs, dir_div, idx, count, w_color, n_ch, sh_scale=1.0):
+    return _MaskedColor.apply(h, dirs.contiguous().float(), int(dir_div), idx, count, w_color, int(n_ch), float(sh_scale))

@@ -114,12 +114,10 @@ class NeRFNetwork(NeRFRenderer):
             else:
                 dirs, dir_div = d.reshape(-1, 3), 1
             if mask is None:
-                idx = torch.arange(B, dtype=torch.int32, device=x.device)
+                idx, count = torch.arange(B, dtype=torch.int32, device=x.device), None
             else:
-                idx, n = raymarching.compact_mask(mask)
-                if n == 0:
-                    return torch.zeros(B, self.out_dim_color, dtype=x.dtype, device=x.device)
-            rgbs = field.masked_color(h, dirs, dir_div, idx, field.flat_color_weights(self.color_net), self.out_dim_color,
+                idx, count = raymarching.compact_mask(mask)         # the count stays on the device (no sync, graph-capturable)
+            rgbs = field.masked_color(h, dirs, dir_div, idx, count, field.flat_color_weights(self.color_net), self.out_dim_color,
                                       0.0 if self.disable_view_direction else 1.0)
             return rgbs.to(x.dtype)
         d = d.reshape(-1, 3)

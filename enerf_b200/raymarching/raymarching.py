@@ -310,7 +310,8 @@ weighted_sum = _weighted_sum.apply
 
 def compact_mask(mask):
     """Indices (int32, increasing) of the True entries of a flat bool tensor and their count — `torch.nonzero(mask)` as three small
-    kernels; the count is read back once (the reference's `x[mask]` synchronises the same way, network.py:180-183)."""
+    kernels WITHOUT the host round trip: returns (idx [n] — the first `count` entries are valid —, count int32 [1] on the device).
+    Consumers (field.masked_color) read the count from the device (the reference's `x[mask]` synchronises, network.py:180-183)."""
     from .. import _lib
     mask = mask.contiguous().view(-1)
     _lib.need_cuda(mask)
@@ -320,5 +321,4 @@ def compact_mask(mask):
     count = torch.empty(1, dtype=torch.int32, device=dev)
     blocks = torch.empty(-(-n // 4096) + 1, dtype=torch.int32, device=dev)
     _lib.call("enerf_compact_mask", _lib.ptr(mask.view(torch.uint8)), n, _lib.ptr(idx), _lib.ptr(count), _lib.ptr(blocks), _lib.stream())
-    k = int(count.item())
-    return idx[:k], k
+    return idx, count

@@ -217,15 +217,18 @@ int enerf_free_splitk(void);
  *   backward       : the prologues apply sigmoid' / trunc_exp' and pick the geo_feat columns.
  * forward_buffer [num_layers,B,64] may be NULL in the forward calls (inference, or training with
  * recomputation) and in the backward calls (the hidden activations are then recomputed per tile from
- * cin / feat; same gradients, no forward_buffer traffic).  grad_weights: fp32, overwritten. */
+ * cin / feat; same gradients, no forward_buffer traffic).  grad_weights: fp32, overwritten.
+ * n_rows_dev (colour-net calls; may be NULL): int32 device scalar with the number of valid rows when only the device knows it (the
+ * compacted `weights > 1e-4` batch of NeRFRenderer.run); B is then the capacity and 128-row tiles beyond the count are skipped. */
 int enerf_field_sigma_forward(const uint16_t* feat, const uint16_t* weights, const float* dirs, uint32_t B,
                               uint32_t num_layers, uint16_t* forward_buffer, float* sigma, uint16_t* cin,
                               void* stream);
 int enerf_field_color_forward(const uint16_t* cin, const uint16_t* weights, uint32_t B, uint32_t num_layers,
-                              uint32_t n_ch, uint16_t* forward_buffer, float* rgb, void* stream);
+                              uint32_t n_ch, uint16_t* forward_buffer, float* rgb, const int32_t* n_rows_dev, void* stream);
 int enerf_field_color_backward(const float* grad_rgb, const float* rgb, uint32_t n_ch, const uint16_t* cin,
                                const uint16_t* weights, const uint16_t* forward_buffer, uint32_t B,
-                               uint32_t num_layers, uint16_t* grad_cin, float* grad_weights, void* stream);
+                               uint32_t num_layers, uint16_t* grad_cin, float* grad_weights, const int32_t* n_rows_dev,
+                               void* stream);
 int enerf_field_sigma_backward(const float* grad_sigma, const float* sigma, const uint16_t* grad_cin,
                                const uint16_t* feat, const uint16_t* weights, const uint16_t* forward_buffer,
                                uint32_t B, uint32_t num_layers, uint16_t* grad_feat, float* grad_weights,
@@ -243,15 +246,18 @@ int enerf_field_sigma_backward(const float* grad_sigma, const float* sigma, cons
  *   colour inputs   : rows of the samples idx[0..n) (the `weights > 1e-4` mask of renderer.py:236, compacted): [SH_4(fp16(dir)) *
  *                     sh_scale | h[idx,1:16] | 0], dirs [B/dir_div,3] (one direction per dir_div consecutive samples), rows n..n_pad
  *                     zero; then enerf_field_color_forward / _backward with num_layers = 2 run the colour-net on the compact batch.
- *   colour inputs backward: grad_h[idx[i],1:16] = grad_cin[i,16:31] (grad_h [B,16] zero-initialised by the caller). */
+ *   colour inputs backward: grad_h[idx[i],1:16] = grad_cin[i,16:31] (grad_h [B,16] zero-initialised by the caller).
+ *   n_dev (here and in gather_rows / scatter_rows; may be NULL): the count from enerf_compact_mask, still on the device — n / n_pad
+ *   are then capacities, rows [count, next multiple of 128) are zero-filled and nothing beyond is touched: no host round trip. */
 int enerf_field_density_forward(const uint16_t* feat, const uint16_t* weights, uint32_t B, uint32_t num_layers, float* sigma,
                                 uint16_t* h, void* stream);
 int enerf_field_density_backward(const float* grad_sigma, const float* sigma, const uint16_t* grad_h, const uint16_t* feat,
                                  const uint16_t* weights, uint32_t B, uint32_t num_layers, uint16_t* grad_feat,
                                  float* grad_weights, void* stream);
 int enerf_field_color_inputs(const float* dirs, uint32_t dir_div, const uint16_t* h, const int32_t* idx, uint32_t n,
-                             uint32_t n_pad, float sh_scale, uint16_t* cin, void* stream);
-int enerf_field_color_inputs_backward(const uint16_t* grad_cin, const int32_t* idx, uint32_t n, uint16_t* grad_h, void* stream);
+                             uint32_t n_pad, float sh_scale, uint16_t* cin, const int32_t* n_dev, void* stream);
+int enerf_field_color_inputs_backward(const uint16_t* grad_cin, const int32_t* idx, uint32_t n, uint16_t* grad_h,
+                                      const int32_t* n_dev, void* stream);
 /* Order-preserving compaction: indices[0..count) = { i < n : values[i] > thresh } in increasing order, count[0] = how many —
  * `torch.nonzero(values > thresh)` (renderer.py:236-242 mask, :523 occupied cells) without the host round trip.
  * scratch: int32 [ceil(n/4096)].  indices may be NULL (count only). */
@@ -260,8 +266,10 @@ int enerf_compact_greater(const float* values, float thresh, uint32_t n, int32_t
 /* the same for a byte mask (a torch.bool tensor): { i : mask[i] != 0 } */
 int enerf_compact_mask(const uint8_t* mask, uint32_t n, int32_t* indices, int32_t* count, int32_t* scratch, void* stream);
 /* dst[i] = src[idx[i]] for i < n, zero rows for n <= i < n_pad / dst[idx[i]] = src[i]; rows of row_bytes (multiple of 4). */
-int enerf_gather_rows(const void* src, const int32_t* idx, uint32_t n, uint32_t n_pad, uint32_t row_bytes, void* dst, void* stream);
-int enerf_scatter_rows(const void* src, const int32_t* idx, uint32_t n, uint32_t row_bytes, void* dst, void* stream);
+int enerf_gather_rows(const void* src, const int32_t* idx, uint32_t n, uint32_t n_pad, uint32_t row_bytes, void* dst,
+                      const int32_t* n_dev, void* stream);
+int enerf_scatter_rows(const void* src, const int32_t* idx, uint32_t n, uint32_t row_bytes, void* dst, const int32_t* n_dev,
+                       void* stream);
 /* image[n,c] = sum_t weights[n,t] * rgbs[n,t,c] (renderer.py:255) and its backward (grad_weights / grad_rgbs may be NULL). */
 int enerf_weighted_sum_forward(const float* weights, const float* rgbs, uint32_t N, uint32_t T, uint32_t n_ch, float* image,
                                void* stream);

@@ -147,10 +147,15 @@ def test_weighted_sum_and_row_moves():
     src = torch.randn(1000, 32, device=DEV).half()
     idx = torch.randperm(1000, device=DEV)[:333].sort().values.int()
     dst = torch.full((384, 32), 9.0, device=DEV, dtype=torch.half)
-    _lib.call("enerf_gather_rows", _lib.ptr(src), _lib.ptr(idx), 333, 384, 64, _lib.ptr(dst), _lib.stream())
+    _lib.call("enerf_gather_rows", _lib.ptr(src), _lib.ptr(idx), 333, 384, 64, _lib.ptr(dst), None, _lib.stream())
     assert torch.equal(dst[:333], src[idx.long()]) and float(dst[333:].abs().max()) == 0
     back = torch.zeros(1000, 32, device=DEV, dtype=torch.half)
-    _lib.call("enerf_scatter_rows", _lib.ptr(dst), _lib.ptr(idx), 333, 64, _lib.ptr(back), _lib.stream())
+    _lib.call("enerf_scatter_rows", _lib.ptr(dst), _lib.ptr(idx), 333, 64, _lib.ptr(back), None, _lib.stream())
+    # the same with the row count on the device and capacities on the host side
+    cnt = torch.tensor([200], dtype=torch.int32, device=DEV)
+    dst2 = torch.full((384, 32), 9.0, device=DEV, dtype=torch.half)
+    _lib.call("enerf_gather_rows", _lib.ptr(src), _lib.ptr(idx), 333, 384, 64, _lib.ptr(dst2), _lib.ptr(cnt), _lib.stream())
+    assert torch.equal(dst2[:200], src[idx.long()][:200]) and float(dst2[200:256].abs().max()) == 0 and float(dst2[256:].float().min()) == 9.0
     assert torch.equal(back[idx.long()], src[idx.long()])
     rest = torch.ones(1000, dtype=torch.bool, device=DEV)
     rest[idx.long()] = False

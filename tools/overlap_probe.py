@@ -83,7 +83,7 @@ def main():
 
     def mlp_fwd(lo, hi):
         _lib.call("enerf_field_sigma_forward", ptr(feat[lo:hi]), ptr(ws), ptr(dirs[lo:hi]), hi - lo, nl_s, None, ptr(sigma[lo:hi]), ptr(cin[lo:hi]), stream())
-        _lib.call("enerf_field_color_forward", ptr(cin[lo:hi]), ptr(wc), hi - lo, nl_c, n_ch, None, ptr(rgb[lo:hi]), stream())
+        _lib.call("enerf_field_color_forward", ptr(cin[lo:hi]), ptr(wc), hi - lo, nl_c, n_ch, None, ptr(rgb[lo:hi]), None, stream())
 
     def fwd_seq():
         gather(0, S)
@@ -137,7 +137,7 @@ def main():
     d_table = torch.empty(table.shape, dtype=torch.float32, device=dev)
 
     def mlp_bwd():
-        _lib.call("enerf_field_color_backward", ptr(g_rgb), ptr(rgb), n_ch, ptr(cin), ptr(wc), None, S, nl_c, ptr(dcin), ptr(gw_c), stream())
+        _lib.call("enerf_field_color_backward", ptr(g_rgb), ptr(rgb), n_ch, ptr(cin), ptr(wc), None, S, nl_c, ptr(dcin), ptr(gw_c), None, stream())
         _lib.call("enerf_field_sigma_backward", ptr(g_sigma), ptr(sigma), ptr(dcin), ptr(feat), ptr(ws), None, S, nl_s, ptr(dfeat), ptr(gw_s), stream())
 
     def scatter():

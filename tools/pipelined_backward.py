@@ -72,7 +72,7 @@ def pipelined_backward(g_sigma, g_rgb, sigma, rgb, cin, feat, x, table, offsets,
             lo, hi = k * step, min(S, (k + 1) * step)
             n = hi - lo
             _lib.call("enerf_field_color_backward", ptr(g_rgb[lo:hi]), ptr(rgb[lo:hi]), n_ch, ptr(cin[lo:hi]), ptr(wc), None, n, nl_color,
-                      ptr(dcin[lo:hi]), ptr(gw_c[k]), stream())
+                      ptr(dcin[lo:hi]), ptr(gw_c[k]), None, stream())
             _lib.call("enerf_field_sigma_backward", ptr(g_sigma[lo:hi]), ptr(sigma[lo:hi]), ptr(dcin[lo:hi]), ptr(feat[lo:hi]), ptr(ws), None, n,
                       nl_sigma, ptr(dfeat[lo:hi]), ptr(gw_s[k]), stream())
             ready = torch.cuda.Event()
@@ -111,7 +111,7 @@ class _EncodedField(Function):
         cin = torch.empty(S, 32, dtype=torch.float16, device=dev)
         rgb = torch.empty(S, n_ch, dtype=torch.float32, device=dev)
         _lib.call("enerf_field_sigma_forward", ptr(feat), ptr(ws), ptr(dirs), S, nl_sigma, None, ptr(sigma), ptr(cin), stream())
-        _lib.call("enerf_field_color_forward", ptr(cin), ptr(wc), S, nl_color, n_ch, None, ptr(rgb), stream())
+        _lib.call("enerf_field_color_forward", ptr(cin), ptr(wc), S, nl_color, n_ch, None, ptr(rgb), None, stream())
         if training:
             ctx.save_for_backward(x, table, offsets, feat, ws, wc, sigma, cin, rgb)
             ctx.meta = (geometry, gridtype, nl_sigma, nl_color, n_ch, embeddings.dtype, w_sigma.dtype, w_color.dtype)
