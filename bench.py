@@ -60,6 +60,7 @@ def parse():
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"], help="Adam step: this repo's fused kernel or torch.optim.Adam(fused=True)")
     ap.add_argument("--skip", default="", help="comma-separated extra objects to skip: strong_scaling,event_step,run_variant,render,gpu_bar,extra_state")
     ap.add_argument("--no-render", action="store_true", help="same as --skip render")
+    ap.add_argument("--only", default="", help="profiling aid: run ONE of event_step / run_variant alone and print its object (no headline line)")
     ap.add_argument("--exchange", default="sharded", choices=["sharded", "allreduce", "none"],
                     help="gradient exchange at N > 1 (enerf_b200/parallel.py); none = no exchange at all (diagnosis only: the ranks diverge)")
     return ap.parse_args()
@@ -631,6 +632,12 @@ def our_arm(args):
         with open(pk) as f:
             m = json.load(f)
         peaks = {"hbm_gbs": m["hbm_gbs"], "bf16_tflops_sustained": m.get("bf16_tflops_sustained", m["bf16_tflops"]), "src": "MEASURED_PEAKS.json"}
+
+    if args.only:                                   # profiling aid (ncu captures of one object's kernels); not the contract line
+        K1 = max(3, min(K, 10))
+        obj = {"event_step": lambda: event_step_bench(args, dev, K1), "run_variant": lambda: run_variant_bench(args, dev, K1, peaks)}[args.only]()
+        print(json.dumps({"only": args.only, args.only: obj}), flush=True)
+        return
 
     # ---------------- headline: configs[1], 4096 rays per GPU
     torch.manual_seed(0)
