@@ -37,10 +37,11 @@ sys.path.insert(0, ROOT)
 
 METRIC, UNIT = "train_rays_per_sec", "rays/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this workload (bytes)
-NCU_TRAFFIC_SRC = "profiles/r1_29_ncu_full_step_kernels_final.md (3.29 M samples/launch)"
-NCU_TRAFFIC = {"grid_encode_backward": 292.092160e6 + 6.025984e6, "grid_encode_forward": 62.590976e6 + 166.863104e6,
-               "march_rays_train": 0.846336e6 + 47.198976e6, "field_color_backward": 236.899840e6 + 167.285248e6,
-               "field_sigma_backward": 447.282432e6 + 179.736064e6}
+NCU_TRAFFIC_SRC = "profiles/r2_18_ncu_full_step_kernels.md (3.29 M samples/launch)"
+NCU_TRAFFIC = {"grid_encode_backward": 292.509440e6 + 5.846272e6, "grid_encode_forward": 62.280448e6 + 168.950016e6,
+               "march_rays_train": 0.846336e6 + 47.198976e6, "field_color_backward": 237.653248e6 + 166.174976e6,
+               "field_sigma_backward": 448.646144e6 + 182.492672e6, "field_sigma_forward": 250.628608e6 + 181.403392e6,
+               "field_color_forward": 211.133440e6 + 12.515328e6}
 RAYS = 4096
 BOUND = 3
 N_BATCHES = 8            # distinct ray batches cycled through the timed region

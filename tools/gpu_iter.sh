@@ -1,24 +1,19 @@
 #!/bin/bash
-# Short GPU iteration: targeted tests + per-kernel timings (+ optional env sweeps).  gpurun -- 'bash tools/gpu_iter.sh tag'
+# Short GPU iteration: targeted tests + per-kernel timings + one bench line.  gpurun -- 'bash tools/gpu_iter.sh tag'
 tag=${1:-it}
 out=gpurun_out
 mkdir -p $out
 timeout 600 python -m pytest tests -m gpu -x -q -k "${TESTS:-ffmlp or field or grid or golden or renderer}" > $out/${tag}_pytest.log 2>&1
 echo "pytest exit $?"; tail -15 $out/${tag}_pytest.log
-for cfg in ${SLOTS:-3:2}; do
-  slots=${cfg%%:*}; ring=${cfg##*:}; [ "$ring" = "$cfg" ] && ring=2
-  export ENERF_TC_BWD_RING=$ring
-  ENERF_TC_BWD_SLOTS=$slots timeout 300 python tools/bench_kernels.py --iters 10 --only ${ONLY:-mlp,grid} > $out/${tag}_kernels_s${slots}.json 2> $out/${tag}_kernels_s${slots}.err
-  echo "bench_kernels slots=$slots ring=$ring exit $?"; tail -3 $out/${tag}_kernels_s${slots}.err
-  python - <<PY
+timeout 300 python tools/bench_kernels.py --iters 10 --only ${ONLY:-mlp,grid} > $out/${tag}_kernels.json 2> $out/${tag}_kernels.err
+echo "bench_kernels exit $?"; tail -3 $out/${tag}_kernels.err
+python - <<PY
 import json
-d=json.load(open("$out/${tag}_kernels_s${slots}.json"))
+d=json.load(open("$out/${tag}_kernels.json"))
 for k,v in d.items():
-    if isinstance(v,dict) and (('tc' in k and '${BRIEF:-}' in k) or 'grid_fwd' in k or 'walk' in k): print(f"{k:45s} {v['ms']:.3f} ms  frac={v.get('frac')}")
+    if isinstance(v,dict) and 'ms' in v: print(f"{k:45s} {v['ms']:.3f} ms  frac={v.get('frac')}")
 PY
-done
-unset ENERF_TC_BWD_RING
-timeout 600 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > $out/${tag}_bench.json 2> $out/${tag}_bench.err
+timeout 600 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --skip ${SKIP:-gpu_bar} > $out/${tag}_bench.json 2> $out/${tag}_bench.err
 echo "bench exit $?"; tail -3 $out/${tag}_bench.err
 python - <<PY
 import json
