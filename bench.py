@@ -61,6 +61,7 @@ def parse():
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"], help="Adam step: this repo's fused kernel or torch.optim.Adam(fused=True)")
     ap.add_argument("--skip", default="", help="comma-separated extra objects to skip: strong_scaling,event_step,run_variant,render,gpu_bar,extra_state")
     ap.add_argument("--no-render", action="store_true", help="same as --skip render")
+    ap.add_argument("--nvtx", action="store_true", help="NVTX range around every C-ABI call (profiling; named after the entry point)")
     ap.add_argument("--only", default="", help="profiling aid: run ONE of event_step / run_variant alone and print its object (no headline line)")
     ap.add_argument("--exchange", default="sharded", choices=["sharded", "allreduce", "none"],
                     help="gradient exchange at N > 1 (enerf_b200/parallel.py); none = no exchange at all (diagnosis only: the ranks diverge)")
@@ -613,6 +614,8 @@ def our_arm(args):
 
     D = Dist()
     world, rank = D.world, D.rank
+    if args.nvtx:
+        _lib.enable_nvtx(True)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(D.local_rank)

@@ -129,9 +129,30 @@ def profile_stop():
     return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (rec or {}).items()}
 
 
+_nvtx = False
+
+
+def enable_nvtx(on=True):
+    """Wrap every C-ABI call in an NVTX range named after the entry point (`enerf_grid_encode_forward`, ...), so that profiler
+    timelines and `ncu --nvtx --nvtx-include` filters can address the stages of the path by name.  Off by default (a push/pop pair
+    costs ~1 us of host time per call)."""
+    global _nvtx
+    _nvtx = bool(on)
+
+
 def call(name, *args):
     """Invoke a C-ABI entry point and raise on failure."""
     fn = getattr(lib(), name)
+    if _nvtx:
+        torch.cuda.nvtx.range_push(name)
+        try:
+            return _call(fn, name, args)
+        finally:
+            torch.cuda.nvtx.range_pop()
+    return _call(fn, name, args)
+
+
+def _call(fn, name, args):
     if _prof is None:
         check(fn(*args))
         return
