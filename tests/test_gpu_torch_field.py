@@ -175,3 +175,26 @@ def test_grid_density_paths_agree():
             a = m._grid_density(x)
             b = m.density(x)['sigma'].float()
         assert a.dtype == torch.float32 and float((a - b).abs().max()) <= 2e-3 * float(b.abs().max())
+
+
+@pytest.mark.parametrize("n_rays,T", [(100, 33), (1, 7), (257, 128)])
+def test_run_on_tensor_cores_ragged_sizes(n_rays, T):
+    """sample counts that are not a multiple of the 128-row MLP tile (padding inside density(), capacity padding in the colour batch)"""
+    torch.manual_seed(7)
+    model = NeRFNetwork(bound=1, out_dim_color=1).to(DEV).train()
+    with torch.no_grad():
+        model.encoder.embeddings.uniform_(-0.5, 0.5)
+    o, d = synthetic.random_rays(n_rays, 1, seed=3)
+    res = {}
+    for tc in (True, False):
+        model.use_tensor_cores = tc
+        for p_ in model.parameters():
+            p_.grad = None
+        with torch.autocast("cuda", dtype=torch.float16):
+            out = model.render(t(o)[None], t(d)[None], staged=False, num_steps=T, upsample_steps=0, bg_color=1, perturb=False, out_dim_color=1)
+        (out["image"].float().sum() * 256.0).backward()
+        res[tc] = (out["image"][0].detach().float(), [p_.grad.clone() for p_ in model.parameters()])
+    assert res[True][0].shape == (n_rays, 1)
+    assert float((res[True][0] - res[False][0]).abs().max()) <= 5e-3
+    for a, b in zip(res[True][1], res[False][1]):
+        assert torch.isfinite(a).all() and _rel(a, b) < 5e-2, _rel(a, b)
