@@ -96,7 +96,11 @@ class NeRFNetwork(NeRFRenderer):
         return super()._grid_density(xyzs)
 
     def forward(self, x, d):
+        """sigma [B] fp32, rgb [B, C] for every sample (network.py:104-132) — the field `run_cuda` queries when a config sets
+        `cuda_ray` without `ff`"""
         out = self.density(x)
+        if 'h' in out:                                   # tensor-core path: the colour-net on all rows (no mask)
+            return out['sigma'], self.color(x, d, mask=None, **out)
         h = torch.cat([self._dir_features(d), out['geo_feat']], dim=-1)
         return out['sigma'], torch.sigmoid(_run_mlp(self.color_net, h))
 

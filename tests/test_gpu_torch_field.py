@@ -198,3 +198,30 @@ def test_run_on_tensor_cores_ragged_sizes(n_rays, T):
     assert float((res[True][0] - res[False][0]).abs().max()) <= 5e-3
     for a, b in zip(res[True][1], res[False][1]):
         assert torch.isfinite(a).all() and _rel(a, b) < 5e-2, _rel(a, b)
+
+
+@pytest.mark.parametrize("n_ch", [1, 3])
+def test_forward_all_samples_matches_linear_formulation(n_ch):
+    """`forward(x, d)` (what run_cuda calls for `cuda_ray` without `ff`): colour-net on every row, ragged row count"""
+    torch.manual_seed(11)
+    model = NeRFNetwork(bound=1, out_dim_color=n_ch).to(DEV).train()
+    with torch.no_grad():
+        model.encoder.embeddings.uniform_(-0.5, 0.5)
+    B = 128 * 9 + 37
+    x = torch.rand(B, 3, device=DEV) * 2 - 1
+    d = torch.randn(B, 3, device=DEV)
+    d = d / d.norm(dim=-1, keepdim=True)
+    gs, gr = torch.randn(B, device=DEV), torch.randn(B, n_ch, device=DEV)
+    res = {}
+    for tc in (True, False):
+        model.use_tensor_cores = tc
+        for p_ in model.parameters():
+            p_.grad = None
+        with torch.autocast("cuda", dtype=torch.float16):
+            sigma, rgb = model(x, d)
+        ((sigma.float() * gs).sum() + (rgb.float() * gr).sum()).backward()
+        res[tc] = (sigma.detach().float(), rgb.detach().float(), [p_.grad.clone() for p_ in model.parameters()])
+    assert res[True][1].shape == (B, n_ch)
+    assert _rel(res[True][0], res[False][0]) < 3e-3 and float((res[True][1] - res[False][1]).abs().max()) <= 3e-3
+    for a, b in zip(res[True][2], res[False][2]):
+        assert _rel(a, b) < 3e-2, _rel(a, b)
