@@ -278,11 +278,14 @@ k_tc_fwd_tma(const __grid_constant__ TmaDesc tm_x, const __grid_constant__ TmaDe
                 tc_fence_after();
                 if (L < S - 1) {
                     uint8_t* sb = stg + ((size_t)s * 2 + (n_store & 1u)) * kGBytes;
+                    // both halves of the accumulator row are requested before the first is used (one TMEM round trip instead of two)
+                    uint32_t acc2[2][32];
+                    tmem_ld32(d_t, acc2[0]);
+                    tmem_ld32(d_t + 32, acc2[1]);
+                    tc_wait_ld();
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        uint32_t acc[32];
-                        tmem_ld32(d_t + h * 32, acc);
-                        tc_wait_ld();
+                        const uint32_t (&acc)[32] = acc2[h];
                         uint32_t p[16];
 #pragma unroll
                         for (int e = 0; e < 16; ++e) p[e] = pack2_relu(__uint_as_float(acc[2 * e]), __uint_as_float(acc[2 * e + 1]));
@@ -392,6 +395,9 @@ static int launch_fwd_tma_n(const TmaDesc& tx, const TmaDesc& tfb, const TmaDesc
 }
 
 // n_hidden_mm = hidden-to-hidden matmuls (0, 1 or 2); fwd_buf != NULL stores every hidden activation (the reference's training contract)
+#ifndef ENERF_FWD_SLOTS
+#define ENERF_FWD_SLOTS 5       // tiles in flight per CTA of the forward without forward_buffer (3: 0.097 / 0.099 ms, 4: 0.088 / 0.096, 5: 0.084 / 0.092; 6 x 96 columns exceed TMEM)
+#endif
 template <int HEAD>
 static int launch_fwd(const __half* in, const __half* W, uint32_t B, int n_hidden_mm, __half* fwd_buf, __half* out, HeadArgs head, cudaStream_t st,
                       const char* name) {
@@ -416,12 +422,12 @@ static int launch_fwd(const __half* in, const __half* W, uint32_t B, int n_hidde
         return -2;
     }
     if (n_hidden_mm == 0) {
-        if constexpr (HEAD == 0 || HEAD == 3 || HEAD == 4) return launch_fwd_tma_n<4, 0, IN_DIM, HEAD, false>(tx, tfb, tcin, W, out, B, head, st, name);
+        if constexpr (HEAD == 0 || HEAD == 3 || HEAD == 4) return launch_fwd_tma_n<ENERF_FWD_SLOTS, 0, IN_DIM, HEAD, false>(tx, tfb, tcin, W, out, B, head, st, name);
         set_error("%s: a 1-layer network has no fused colour head", name);
         return -2;
     }
-    if (n_hidden_mm == 1) return launch_fwd_tma_n<4, 1, IN_DIM, HEAD, false>(tx, tfb, tcin, W, out, B, head, st, name);
-    if constexpr (HEAD <= 2) return launch_fwd_tma_n<4, 2, IN_DIM, HEAD, false>(tx, tfb, tcin, W, out, B, head, st, name);
+    if (n_hidden_mm == 1) return launch_fwd_tma_n<ENERF_FWD_SLOTS, 1, IN_DIM, HEAD, false>(tx, tfb, tcin, W, out, B, head, st, name);
+    if constexpr (HEAD <= 2) return launch_fwd_tma_n<ENERF_FWD_SLOTS, 2, IN_DIM, HEAD, false>(tx, tfb, tcin, W, out, B, head, st, name);
     set_error("%s: density heads take 1- and 2-layer networks", name);
     return -2;
 }
@@ -906,6 +912,8 @@ static int launch_bwd_tma(const __half* grad, const __half* x, const __half* W, 
 //   a_ready[s] / d_full[s] advance 2*NH+3 phases per tile (one per MMA stage; a_ready's last one = "accumulator read,
 //   slot free for the next tile").
 // ================================================================================================
+// 128 registers per thread is the hardware limit for 13 warps (a scheduler partition owns 16 K registers and hosts four of them);
+// requesting both 32-column halves of an accumulator row before using the first costs 16 more and spills (0.36 / 0.33 vs 0.34 / 0.29 ms)
 template <int NSLOTS, int NH, int PRO, bool GD, int CH, bool XA, int NI>
 __global__ void __launch_bounds__(32 * NI + NSLOTS * 128 * CH, 1)
 k_tc_bwd_rc(const __grid_constant__ TmaDesc tm_x, const __half* __restrict__ grad, const __half* __restrict__ W, __half* __restrict__ grad_inputs,
