@@ -172,13 +172,82 @@ def _run(steps, n_rays, bound, lr, seed, verbose, eval_last, eval_every, grad_ac
                       "update_extra_state every 16 steps, lr 5e-3 * 0.1^(step/steps) (main_nerf.py:212); reference side = the reference's own CUDA build (oracle/_ref) chained as network_ff.py + run_cuda"}
 
 
+def train_single(kind, steps=1500, n_rays=1024, bound=1, lr=5e-3, seed=0, eval_last=5, eval_every=10):
+    """one training of ONE stack ('ours' or 'reference'), same protocol as run(); returns the PSNR (mean of the last checkpoints) on the
+    8 training poses.  Two calls with the same arguments differ only by what is not reproducible in the stack itself (the order of the
+    marcher's atomic reservations and of the gradient atomics): `run_to_run_noise` uses that as the floor of any PSNR comparison."""
+    from enerf_b200.optim import FusedAdam
+    dev = torch.device("cuda", 0)
+    ours, theirs = _models(bound, dev, seed)
+    o, d, rgb = scene(res=64, bound=bound)
+    go, gd, gt = (torch.from_numpy(a).to(dev) for a in (o, d, rgb))
+    model = ours if kind == "ours" else theirs
+    opt = FusedAdam(ours.get_params(lr), betas=(0.9, 0.99), eps=1e-15) if kind == "ours" else torch.optim.Adam(theirs.parameters(), lr=lr, betas=(0.9, 0.99),
+                                                                                                            eps=1e-15)
+    scaler = torch.amp.GradScaler("cuda")
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda it: 0.1 ** min(it / steps, 1))
+    rng = np.random.default_rng(seed)
+    vals = []
+    for it in range(steps):
+        if it % 16 == 0:
+            torch.manual_seed(1000 + it)
+            with torch.autocast("cuda", dtype=torch.float16):
+                model.update_extra_state()
+        idx = torch.from_numpy(rng.integers(0, len(o), size=n_rays)).to(dev)
+        if kind == "ours":
+            with torch.autocast("cuda", dtype=torch.float16):
+                img = ours.render(go[idx][None], gd[idx][None], staged=False, bg_color=1, perturb=True, out_dim_color=3)["image"].reshape(-1, 3)
+        else:
+            img = theirs.render_train(go[idx], gd[idx], bg_color=1, perturb=True)["image"]
+        loss = F.mse_loss(img.float(), gt[idx])
+        opt.zero_grad(set_to_none=True)
+        scaler.scale(loss).backward()
+        scaler.step(opt)
+        scaler.update()
+        sched.step()
+        if it >= steps - eval_last * eval_every and (steps - 1 - it) % eval_every == 0:
+            if kind == "reference":                                  # render the reference's parameters with this repo's inference renderer
+                with torch.no_grad():
+                    ours.encoder.embeddings.copy_(theirs.encoder.embeddings)
+                    ours.sigma_net.weights.copy_(theirs.w_sigma)
+                    ours.color_net.weights.copy_(theirs.w_color)
+                    ours.density_grid.copy_(theirs.density_grid)
+                    ours.density_bitfield.copy_(theirs.density_bitfield)
+            ours.eval()
+            parts = []
+            with torch.no_grad():
+                for s0 in range(0, len(o), 8192):
+                    with torch.autocast("cuda", dtype=torch.float16):
+                        parts.append(ours.render(go[s0:s0 + 8192][None], gd[s0:s0 + 8192][None], staged=False, bg_color=1, perturb=False,
+                                                 out_dim_color=3)["image"].reshape(-1, 3).float().cpu().numpy())
+            ours.train()
+            vals.append(psnr(np.concatenate(parts), rgb))
+    return float(np.mean(vals))
+
+
+def run_to_run_noise(kind, pairs=4, steps=1500, n_rays=1024):
+    """PSNR of `pairs` x 2 trainings of the same stack from the same seed: |a - b| is pure run-to-run noise"""
+    a = np.array([[train_single(kind, steps, n_rays, seed=s) for _ in range(2)] for s in range(pairs)])
+    diff = a[:, 0] - a[:, 1]
+    return {"stack": kind, "pairs": pairs, "steps": steps, "psnr_db": a.tolist(), "abs_diff_db": np.abs(diff).tolist(),
+            "rms_diff_db": float(np.sqrt((diff ** 2).mean())), "max_abs_diff_db": float(np.abs(diff).max())}
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=600)
     ap.add_argument("--rays", type=int, default=1024)
     ap.add_argument("--out", default="")
     ap.add_argument("--seeds", type=int, default=1, help="independent repetitions (different initial parameters and ray batches)")
+    ap.add_argument("--noise", type=int, default=0, help="only measure run-to-run noise: this many same-seed pairs of each stack")
     a = ap.parse_args()
+    if a.noise > 0:
+        res = {"run_to_run_noise": [run_to_run_noise("ours", a.noise, a.steps, a.rays), run_to_run_noise("reference", a.noise, a.steps, a.rays)]}
+        print(json.dumps(res))
+        if a.out:
+            with open(a.out, "w") as f:
+                json.dump(res, f, indent=1)
+        sys.exit(0)
     res = {"gradient_check": gradient_check(), "training": run(a.steps, a.rays, verbose=True)}
     if a.seeds > 1:
         # both trainings are chaotic and (atomics) not even reproducible run to run: the comparison is between MEANS over repetitions
