@@ -224,3 +224,70 @@ class RefStack(NeRFRenderer):
         image = image + (1 - ws).unsqueeze(-1) * bg_color
         depth = torch.clamp(depth - nears, min=0) / (fars - nears)
         return {'image': image, 'depth': depth}
+
+    # ---- inference (renderer.py:344-400) on the reference kernels -------------------------------------------------------------
+    def _infer_mlp(self, x, w, num_layers):
+        """ffmlp.py:40-42: the inference kernel (no forward_buffer)"""
+        R = _ext("_ffmlp")
+        x = _pad128(x.half().contiguous())
+        B = x.shape[0]
+        out = torch.empty(B, 16, dtype=torch.half, device=x.device)
+        buf = torch.empty(B, 64, dtype=torch.half, device=x.device)
+        R.ffmlp_inference(x, w.detach().half().contiguous(), B, 32, 16, 64, num_layers, 0, 6, buf, out)
+        return out
+
+    def _infer_field(self, xyzs, dirs):
+        """network_ff.py:51-73 without autograd"""
+        R, e = _ext("_gridencoder"), self.encoder
+        n = xyzs.shape[0]
+        x = ((xyzs + self.bound) / (2 * self.bound)).contiguous()
+        table = e.embeddings.detach().half().contiguous()
+        L, C = e.offsets.shape[0] - 1, table.shape[1]
+        feat = torch.empty(L, n, C, device=x.device, dtype=table.dtype)
+        dummy = torch.empty(1, device=x.device, dtype=table.dtype)
+        R.grid_encode_forward(x, table, e.offsets, feat, n, 3, C, L, float(np.log2(e.per_level_scale)), e.base_resolution, False, dummy, 0)
+        h = self._infer_mlp(feat.permute(1, 0, 2).reshape(n, L * C), self.w_sigma, 2)[:n]
+        sigma = torch.exp(h[:, 0].float())
+        sh = _RefSH.apply(dirs, 4)
+        cin = torch.cat([sh, h[:, 1:], torch.zeros_like(h[:, :1])], dim=-1)
+        y = self._infer_mlp(cin, self.w_color, 3)[:n]
+        return sigma, torch.sigmoid(y[:, :3])
+
+    @torch.no_grad()
+    def render_infer(self, rays_o, rays_d, bg_color=1, perturb=False, dt_gamma=0.0, max_steps=1024):
+        R = _ext("_raymarching")
+        rays_o, rays_d = rays_o.contiguous().view(-1, 3), rays_d.contiguous().view(-1, 3)
+        N, dev = rays_o.shape[0], rays_o.device
+        nears, fars = torch.empty(N, device=dev), torch.empty(N, device=dev)
+        R.near_far_from_aabb(rays_o, rays_d, self.aabb_infer, N, self.min_near, nears, fars)
+        weights_sum, depth, image = torch.zeros(N, device=dev), torch.zeros(N, device=dev), torch.zeros(N, 3, device=dev)
+        n_alive = N
+        alive_counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        rays_alive = torch.zeros(2, N, dtype=torch.int32, device=dev)
+        rays_t = torch.zeros(2, N, device=dev)
+        step = i = 0
+        while step < 1024:                                                  # renderer.py:365 (hard-coded)
+            if step == 0:
+                rays_alive[0] = torch.arange(N, dtype=torch.int32, device=dev)
+                rays_t[0] = nears
+            else:
+                alive_counter.zero_()
+                R.compact_rays(n_alive, rays_alive[i % 2], rays_alive[(i + 1) % 2], rays_t[i % 2], rays_t[(i + 1) % 2], alive_counter)
+                n_alive = int(alive_counter.item())
+            if n_alive <= 0:
+                break
+            n_step = max(min(N // n_alive, 8), 1)
+            M = n_alive * n_step
+            M += 128 - (M % 128)                                            # raymarching.py:326-327
+            xyzs, dirs, deltas = torch.zeros(M, 3, device=dev), torch.zeros(M, 3, device=dev), torch.zeros(M, 2, device=dev)
+            R.march_rays(n_alive, n_step, rays_alive[i % 2], rays_t[i % 2], rays_o, rays_d, float(self.bound), dt_gamma, max_steps, self.cascade,
+                         self.grid_size, self.density_bitfield, nears, fars, xyzs, dirs, deltas, 1 if perturb else 0)
+            sigmas, rgbs = self._infer_field(xyzs, dirs)
+            sigmas = self.density_scale * sigmas
+            R.composite_rays(n_alive, n_step, rays_alive[i % 2], rays_t[i % 2], sigmas.float().contiguous(), rgbs.float().contiguous(), deltas, weights_sum,
+                             depth, image)
+            step += n_step
+            i += 1
+        image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
+        depth = torch.clamp(depth - nears, min=0) / (fars - nears)
+        return {'image': image, 'depth': depth, 'weights_sum': weights_sum}

@@ -233,14 +233,71 @@ def run_to_run_noise(kind, pairs=4, steps=1500, n_rays=1024):
             "rms_diff_db": float(np.sqrt((diff ** 2).mean())), "max_abs_diff_db": float(np.abs(diff).max())}
 
 
+def render_parity(steps=400, n_rays=1024, bound=1, seed=0):
+    """"rendered PSNR within 0.1 dB of the reference", the deterministic part: ONE trained parameter set (ours, `steps` steps) rendered
+    on the 8 training poses by (a) this repo's inference path (device-counted marching loop, tcgen05 field, warp compositor) and (b) the
+    reference's own inference kernels chained as renderer.py:344-400 (march_rays / ffmlp_inference / composite_rays / compact_rays of
+    oracle/_ref).  Same parameters, same occupancy bitfield, perturb off."""
+    from enerf_b200.optim import FusedAdam
+    dev = torch.device("cuda", 0)
+    ours, theirs = _models(bound, dev, seed)
+    o, d, rgb = scene(res=64, bound=bound)
+    go, gd, gt = (torch.from_numpy(a).to(dev) for a in (o, d, rgb))
+    opt = FusedAdam(ours.get_params(5e-3), betas=(0.9, 0.99), eps=1e-15)
+    scaler = torch.amp.GradScaler("cuda")
+    rng = np.random.default_rng(seed)
+    for it in range(steps):
+        if it % 16 == 0:
+            with torch.autocast("cuda", dtype=torch.float16):
+                ours.update_extra_state()
+        idx = torch.from_numpy(rng.integers(0, len(o), size=n_rays)).to(dev)
+        with torch.autocast("cuda", dtype=torch.float16):
+            img = ours.render(go[idx][None], gd[idx][None], staged=False, bg_color=1, perturb=True, out_dim_color=3)["image"].reshape(-1, 3)
+        loss = F.mse_loss(img.float(), gt[idx])
+        opt.zero_grad(set_to_none=True)
+        scaler.scale(loss).backward()
+        scaler.step(opt)
+        scaler.update()
+    with torch.no_grad():
+        theirs.encoder.embeddings.copy_(ours.encoder.embeddings)
+        theirs.w_sigma.copy_(ours.sigma_net.weights)
+        theirs.w_color.copy_(ours.color_net.weights)
+        theirs.density_grid.copy_(ours.density_grid)
+        theirs.density_bitfield.copy_(ours.density_bitfield)
+    ours.eval()
+    theirs.eval()
+    img_o, img_t, dep_o, dep_t = [], [], [], []
+    with torch.no_grad():
+        for s0 in range(0, len(o), 8192):
+            with torch.autocast("cuda", dtype=torch.float16):
+                r = ours.render(go[s0:s0 + 8192][None], gd[s0:s0 + 8192][None], staged=False, bg_color=1, perturb=False, out_dim_color=3)
+            img_o.append(r["image"].reshape(-1, 3).float().cpu().numpy())
+            dep_o.append(r["depth"].reshape(-1).float().cpu().numpy())
+            t = theirs.render_infer(go[s0:s0 + 8192], gd[s0:s0 + 8192], bg_color=1, perturb=False)
+            img_t.append(t["image"].float().cpu().numpy())
+            dep_t.append(t["depth"].float().cpu().numpy())
+    img_o, img_t, dep_o, dep_t = (np.concatenate(a) for a in (img_o, img_t, dep_o, dep_t))
+    return {"train_steps": steps, "psnr_ours_db": psnr(img_o, rgb), "psnr_reference_kernels_db": psnr(img_t, rgb),
+            "abs_diff_db": abs(psnr(img_o, rgb) - psnr(img_t, rgb)), "psnr_between_db": psnr(img_o, img_t),
+            "image_max_abs_diff": float(np.abs(img_o - img_t).max()), "depth_max_abs_diff": float(np.abs(dep_o - dep_t).max()),
+            "depth_mean_abs_diff": float(np.abs(dep_o - dep_t).mean()), "pixels": int(img_o.shape[0])}
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=600)
     ap.add_argument("--rays", type=int, default=1024)
     ap.add_argument("--out", default="")
     ap.add_argument("--seeds", type=int, default=1, help="independent repetitions (different initial parameters and ray batches)")
-    ap.add_argument("--noise", type=int, default=0, help="only measure run-to-run noise: this many same-seed pairs of each stack")
+    ap.add_argument("--noise", type=int, default=0, help="only measure run-to-run noise: this many same-seed pairs of each stack (negative: render parity of that many trained checkpoints)")
     a = ap.parse_args()
+    if a.noise < 0:
+        res = {"render_parity": [render_parity(a.steps, a.rays, seed=s_) for s_ in range(-a.noise)]}
+        print(json.dumps(res))
+        if a.out:
+            with open(a.out, "w") as f:
+                json.dump(res, f, indent=1)
+        sys.exit(0)
     if a.noise > 0:
         res = {"run_to_run_noise": [run_to_run_noise("ours", a.noise, a.steps, a.rays), run_to_run_noise("reference", a.noise, a.steps, a.rays)]}
         print(json.dumps(res))

@@ -40,3 +40,13 @@ def test_training_psnr_parity_vs_reference_kernels():
     assert r["psnr_ours_db"] > 36.0 and r["psnr_reference_kernels_db"] > 36.0, r
     assert r["psnr_ours_db"] >= r["psnr_reference_kernels_db"] - 2.5, r
     assert r["psnr_between_db"] > 34.0, r
+
+
+def test_rendered_psnr_of_one_checkpoint_matches_reference_inference_kernels():
+    """north star: "rendered PSNR within 0.1 dB of the reference" — one trained checkpoint through both inference paths"""
+    _need_ref()
+    from tests import hotpath_parity
+    r = hotpath_parity.render_parity(steps=400)
+    assert r["psnr_ours_db"] > 30.0, r
+    assert r["abs_diff_db"] <= 0.1, r
+    assert r["psnr_between_db"] >= 45.0, r
