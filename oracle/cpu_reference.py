@@ -8,8 +8,6 @@ the path every shipped E-NeRF config runs — `NeRFNetwork` of nerf/network.py (
 near_far_from_aabb) come from the C oracle (oracle/enerf_oracle.c).  Nothing in enerf_b200/
 imports this module.
 """
-import math
-
 import numpy as np
 import torch
 import torch.nn as nn

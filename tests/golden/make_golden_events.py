@@ -8,7 +8,6 @@ modules themselves do not import here: matplotlib, h5py, tensorboardX ... are mi
 """
 import ast
 import os
-import sys
 
 import numpy as np
 import torch

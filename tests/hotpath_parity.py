@@ -84,7 +84,6 @@ def run(steps=600, n_rays=1024, bound=1, lr=5e-3, seed=0, verbose=False, eval_la
     """grad_accumulation: 'fp32' = this repo's default; 'fp16' = embedding gradients accumulated with fp16 atomics like the reference
     (gridencoder.cu:296-302), which shows how much of a PSNR difference is the reference's lossy accumulation and not the kernels"""
     from enerf_b200.gridencoder import grid as grid_mod
-    from enerf_b200.optim import FusedAdam
     grid_mod.set_grad_accumulation(grad_accumulation)
     try:
         return _run(steps, n_rays, bound, lr, seed, verbose, eval_last, eval_every, grad_accumulation)

@@ -1,7 +1,5 @@
 """CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol
 include/enerf_b200.h declares, and the product path refuses to run without a GPU."""
-import ctypes
-
 import pytest
 import torch
 

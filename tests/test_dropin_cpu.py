@@ -1,7 +1,6 @@
 """The bare-name shims resolve to this repo's packages, and — in the build container, where
 /root/reference exists — the reference's own nerf/renderer.py, nerf/network_ff.py and encoding.py
 import against them unchanged (third-party imports the container lacks are stubbed)."""
-import importlib
 import os
 import subprocess
 import sys

@@ -7,8 +7,6 @@ in arbitrary order -> compared with the exact (float64) sum, 1e-4 relative to th
 gradient for fp32 accumulation, 2e-2 for the reference-style fp16 atomics.  SH: fp32 within
 2e-6 of the closed forms; fp16 outputs within 1 fp16 ulp of the fp32 value (the reference
 evaluates in fp16 and is up to ~4 ulp away from it)."""
-import os
-
 import numpy as np
 import pytest
 import torch
