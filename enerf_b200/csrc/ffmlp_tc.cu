@@ -434,7 +434,7 @@ static int launch_fwd(const __half* in, const __half* W, uint32_t B, int n_hidde
 
 int tc_forward(const __half* in, const __half* W, uint32_t B, int in_dim, int n_hidden_mm, __half* fwd_buf, __half* out, cudaStream_t st,
                const char* name) {
-    HeadArgs none = {nullptr, nullptr, nullptr, nullptr, 0};
+    HeadArgs none = {nullptr, nullptr, nullptr, nullptr, 0, nullptr};
     if (in_dim != 32) { set_error("%s: input_dim must be 32 on the tcgen05 path", name); return -2; }
     return launch_fwd<0>(in, W, B, n_hidden_mm, fwd_buf, out, none, st, name);
 }
@@ -442,7 +442,7 @@ int tc_forward(const __half* in, const __half* W, uint32_t B, int in_dim, int n_
 // sigma-net with fused exp / SH / colour-input head (input_dim 32)
 int tc_forward_sigma_head(const __half* feat, const __half* W, uint32_t B, int n_hidden_mm, __half* fwd_buf, const float* dirs, float* sigma,
                           __half* cin, cudaStream_t st) {
-    HeadArgs h = {dirs, sigma, cin, nullptr, 0};
+    HeadArgs h = {dirs, sigma, cin, nullptr, 0, nullptr};
     return launch_fwd<1>(feat, W, B, n_hidden_mm, fwd_buf, nullptr, h, st, "field_sigma_forward");
 }
 // colour-net with fused sigmoid head (input_dim 32)
@@ -453,7 +453,7 @@ int tc_forward_rgb_head(const __half* cin, const __half* W, uint32_t B, int n_hi
 }
 // density head: sigma (+ the 16 raw outputs when h != NULL) of a 1- or 2-layer sigma-net
 int tc_forward_density(const __half* feat, const __half* W, uint32_t B, int n_hidden_mm, float* sigma, __half* h, cudaStream_t st) {
-    HeadArgs a = {nullptr, sigma, nullptr, nullptr, 0};
+    HeadArgs a = {nullptr, sigma, nullptr, nullptr, 0, nullptr};
     if (h) return launch_fwd<4>(feat, W, B, n_hidden_mm, nullptr, h, a, st, "field_density_forward");
     return launch_fwd<3>(feat, W, B, n_hidden_mm, nullptr, nullptr, a, st, "field_density_forward");
 }
@@ -1389,7 +1389,7 @@ static int launch_bwd_rc(const __half* grad, const __half* x, const __half* W, _
 
 int tc_backward(const __half* grad, const __half* x, const __half* W, const __half* fwd_buf, __half* bwd_buf, __half* grad_inputs, float* dW,
                 uint32_t B, int in_dim, int n_hidden_mm, cudaStream_t st) {
-    ProArgs none = {nullptr, nullptr, 0, nullptr, nullptr, nullptr};
+    ProArgs none = {nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr};
     if (!fwd_buf) return launch_bwd_rc<0>(grad, x, W, grad_inputs, dW, B, in_dim, n_hidden_mm, none, st, "ffmlp_backward");
     return launch_bwd_tma<0>(grad, x, W, fwd_buf, bwd_buf, grad_inputs, dW, B, in_dim, n_hidden_mm, none, st, "ffmlp_backward");
 }
@@ -1401,14 +1401,14 @@ int tc_backward_rgb(const float* g_rgb, const float* rgb, int n_ch, const __half
 }
 int tc_backward_sigma(const float* g_sigma, const float* sigma, const __half* dcin, const __half* feat, const __half* W, const __half* fwd_buf,
                       __half* dfeat, float* dW, uint32_t B, int n_hidden_mm, cudaStream_t st) {
-    ProArgs p = {nullptr, nullptr, 0, g_sigma, sigma, dcin};
+    ProArgs p = {nullptr, nullptr, 0, g_sigma, sigma, dcin, nullptr};
     if (!fwd_buf) return launch_bwd_rc<2>(nullptr, feat, W, dfeat, dW, B, 32, n_hidden_mm, p, st, "field_sigma_backward");
     return launch_bwd_tma<2>(nullptr, feat, W, fwd_buf, nullptr, dfeat, dW, B, 32, n_hidden_mm, p, st, "field_sigma_backward");
 }
 // density head (always recomputing): g_sigma [B] (may be NULL) and g_h [B,16] fp16 (may be NULL) -> dfeat, dW
 int tc_backward_density(const float* g_sigma, const float* sigma, const __half* g_h, const __half* feat, const __half* W, __half* dfeat, float* dW,
                         uint32_t B, int n_hidden_mm, cudaStream_t st) {
-    ProArgs p = {nullptr, nullptr, 0, g_sigma, sigma, nullptr};
+    ProArgs p = {nullptr, nullptr, 0, g_sigma, sigma, nullptr, nullptr};
     return launch_bwd_rc<3>(g_h, feat, W, dfeat, dW, B, 32, n_hidden_mm, p, st, "field_density_backward");
 }
 

@@ -20,7 +20,6 @@
 
 namespace enerf {
 
-static constexpr unsigned kFull = 0xffffffffu;
 static constexpr int kSamplesPerCta = 32;
 static int g_fwd_fast = 1;   // D = 3 without input gradients: 1 = k_grid_fwd_w (warp walks the levels), 2 = k_grid_fwd3; 0 = always the generic kernel
 constexpr int kBwdBlockDefault = 128;   // measured (3.29 M samples): 256: 0.685, 192: 0.688, 128: 0.675, 64: 0.673 ms
