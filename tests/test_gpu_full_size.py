@@ -1,4 +1,5 @@
-"""GPU parity at BASELINE.json's full size (configs[1]: 4096 rays, bound 3 -> ~3.3 M samples).
+"""GPU parity at BASELINE.json's full sizes (configs[1]: 4096 rays, bound 3 -> ~3.3 M samples; configs[4]: 65 536 rays -> ~50 M samples;
+configs[3]: one 800 x 800 frame, 640 000 rays, through the inference loop).
 
 The oracle needs minutes at this size, so the kernels are checked through properties that do not
 depend on the size and tie the full-size launch to the small launches the oracle *does* verify
@@ -172,3 +173,89 @@ def test_mlp_rows_are_independent_of_the_launch_size(samples, nl):
     rel_w = float((gw - wr.grad).norm() / wr.grad.norm())
     rel_x = float((gin.float() - xr.grad).norm() / xr.grad.norm())
     assert rel_w < 2e-2 and rel_x < 2e-2, (rel_w, rel_x)
+
+
+# ---- BASELINE configs[4]: 65 536 rays per batch (spiral1-shaped, bound 3) ---------------------------------------------------------
+def _march(o, d, bits, nears, fars):
+    counter = torch.zeros(2, dtype=torch.int32, device=DEV)
+    xyzs, dirs, deltas, rays = rm.march_rays_train(o, d, float(BOUND), bits, 3, 128, nears, fars, counter, -1, True, 128, False, 0, 1024)
+    return xyzs, deltas, rays, counter
+
+
+def _synthetic_field(xyzs):
+    """a deterministic per-sample density / colour (so that a ray's samples carry the same values wherever the marcher put them)"""
+    sigma = (torch.sin(xyzs[:, 0] * 7.0) + torch.cos(xyzs[:, 1] * 5.0) + 2.1) * 3.0
+    rgb = torch.sigmoid(xyzs * 2.0)
+    return sigma.contiguous(), rgb.contiguous()
+
+
+def test_march_and_composite_65536_rays_match_4096_ray_launches():
+    """the marcher reserves sample ranges with atomics, so the LAYOUT of a 65 536-ray launch is not reproducible — but every ray's
+    sample count, samples and composited pixel must equal what the same ray gets in a 4096-ray launch (bit-exact: per-ray code paths
+    do not depend on the launch size), the ranges must tile [0, total) and the counter must equal their sum"""
+    N = 65536
+    sc = scene(N, BOUND, seed=21)
+    o, d, bits, nears, fars = (t(sc[k]) for k in ("o", "d", "bits", "nears", "fars"))
+    xyzs, deltas, rays, counter = _march(o, d, bits, nears, fars)
+    total = int(counter[0])
+    assert int(counter[1]) == N and total == int(rays[:, 2].sum()) and total > 30_000_000
+    order = torch.argsort(rays[:, 1])
+    off, cnt = rays[order, 1].long(), rays[order, 2].long()
+    assert int(off[0]) == 0 and bool((off[1:] == off[:-1] + cnt[:-1]).all())          # the ranges tile [0, total)
+    sigma, rgb = _synthetic_field(xyzs)
+    ws, depth, image = rm.composite_rays_train(sigma, rgb, deltas, rays)
+    assert bool(torch.isfinite(image).all()) and float(ws.max()) <= 1.0 + 1e-5 and float(ws.min()) >= 0.0
+    steps_full = torch.empty(N, dtype=torch.int64, device=DEV)
+    steps_full[rays[:, 0].long()] = rays[:, 2].long()
+    first = torch.empty(N, dtype=torch.int64, device=DEV)
+    first[rays[:, 0].long()] = rays[:, 1].long()
+    for c in (0, 7, 15):                                                             # three of the sixteen 4096-ray chunks
+        s = slice(c * 4096, (c + 1) * 4096)
+        xs, ds, rs, cn = _march(o[s].contiguous(), d[s].contiguous(), bits, nears[s].contiguous(), fars[s].contiguous())
+        # NB the training jitter is seeded by the ray's index IN ITS LAUNCH (raymarching.cu:349-352), so only chunk 0 shares it
+        sg, rg = _synthetic_field(xs)
+        w2, d2, im2 = rm.composite_rays_train(sg, rg, ds, rs)
+        if c == 0:
+            small = torch.empty(4096, dtype=torch.int64, device=DEV)
+            small[rs[:, 0].long()] = rs[:, 2].long()
+            assert torch.equal(small, steps_full[s])
+            assert torch.equal(im2, image[s]) and torch.equal(w2, ws[s]) and torch.equal(d2, depth[s])
+            # and the samples themselves, ray by ray
+            f2 = torch.empty(4096, dtype=torch.int64, device=DEV)
+            f2[rs[:, 0].long()] = rs[:, 1].long()
+            for ray in (0, 1, 2047, 4095):
+                n_ = int(small[ray])
+                a, b = int(first[ray]), int(f2[ray])
+                assert torch.equal(xyzs[a:a + n_], xs[b:b + n_]) and torch.equal(deltas[a:a + n_], ds[b:b + n_])
+        else:
+            assert int(cn[0]) == int(rs[:, 2].sum()) and bool(torch.isfinite(im2).all())
+
+
+# ---- BASELINE configs[3]: 800 x 800 full-frame inference -----------------------------------------------------------------------
+def test_full_frame_inference_equals_its_row_bands():
+    """640 000 rays through the device-counted marching loop in one call vs the same frame rendered as four bands of 200 rows (what
+    four GPUs would each render): the per-ray sample sequence does not depend on which rays share a launch; n_alive, n_step and the compaction
+    order all differ, and with them the points where a ray's transmittance is re-derived from its weight sum (raymarching.cu:842-899:
+    T = 1 - weights_sum at the start of every round), so the images agree to rounding (1e-5 of the [0, 1] range), not to the bit"""
+    from enerf_b200 import synthetic
+    from enerf_b200.nerf.network_ff import NeRFNetwork
+    torch.manual_seed(3)
+    model = NeRFNetwork(encoding="hashgrid", bound=BOUND, cuda_ray=True, out_dim_color=1).to(DEV).eval()
+    with torch.no_grad():
+        model.encoder.embeddings.uniform_(-0.5, 0.5)
+        grid = synthetic.ball_density_grid(BOUND, model.cascade)
+        model.density_grid.copy_(t(grid).view(model.cascade, -1))
+        model.density_bitfield.copy_(t(synthetic.packbits_np(grid)))
+    pose = synthetic.look_at_poses(1, 0.6 * BOUND, seed=5)[0]
+    o, d = synthetic.pinhole_rays(pose, 800, 800)
+    o, d = t(o), t(d)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        full = model.render(o[None], d[None], staged=False, bg_color=1, perturb=False, out_dim_color=1)
+        stats = dict(model.last_render_stats)
+        bands = [model.render(o[i:i + 160000][None], d[i:i + 160000][None], staged=False, bg_color=1, perturb=False, out_dim_color=1)
+                 for i in range(0, 640000, 160000)]
+    img = full["image"].reshape(-1)
+    assert img.shape[0] == 640000 and bool(torch.isfinite(img).all()) and stats["samples"] > 50_000_000, stats
+    assert float((img - torch.cat([b["image"].reshape(-1) for b in bands])).abs().max()) <= 1e-5
+    assert float((full["depth"].reshape(-1) - torch.cat([b["depth"].reshape(-1) for b in bands])).abs().max()) <= 1e-4
+    assert float(img.std()) > 1e-3 and float(img.min()) >= 0.0 and float(img.max()) <= 1.0 + 1e-5          # a picture, not a constant
