@@ -35,6 +35,9 @@ _SIGS = {
     "enerf_march_rays_dev": [_u32, _u32, _p, _p, _p, _p, _f32, _f32, _u32, _u32, _u32, _p, _p, _p, _p, _p, _p, _u32, _p, _p],
     "enerf_composite_rays_dev": [_u32, _u32, _p, _p, _p, _p, _p, _u32, _p, _p, _p, _p, _p],
     "enerf_compact_rays_dev": [_u32, _p, _p, _p, _p, _p, _p, _p],
+    "enerf_occupancy_bounds": [_p, _u32, _u32, _p, _p],
+    "enerf_march_rays_train_bounded": [_p, _p, _p, _f32, _f32, _u32, _u32, _u32, _u32, _u32, _p, _p, _p, _p, _p, _p, _p, _u32, _p, _p],
+    "enerf_march_rays_bounded": [_u32, _u32, _p, _p, _p, _p, _f32, _f32, _u32, _u32, _u32, _p, _p, _p, _p, _p, _p, _u32, _p, _p, _p],
     "enerf_grid_encode_forward": [_p, _p, _p, _p, _u32, _u32, _u32, _u32, _f32, _u32, _int, _p, _u32, _int, _int, _p],
     "enerf_grid_encode_backward": [_p, _p, _p, _p, _p, _u32, _u32, _u32, _u32, _f32, _u32, _int, _p, _p, _u32, _int, _int, _int, _p],
     "enerf_grid_set_backward_mode": [_int],

@@ -47,11 +47,24 @@ class _Raymarching:
         _lib.call("enerf_packbits", ptr(grid), N, density_thresh, ptr(bitfield), stream())
 
     @staticmethod
-    def march_rays_train(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, xyzs, dirs, deltas, rays, counter, perturb):
-        need_cuda(rays_o, rays_d, grid, nears, fars, xyzs, dirs, deltas, rays, counter)
-        _lib.call("enerf_march_rays_train", ptr(rays_o), ptr(rays_d), ptr(grid), bound, dt_gamma, max_steps, N, C, H, M,
-                                                ptr(nears), ptr(fars), ptr(xyzs), ptr(dirs), ptr(deltas), ptr(rays), ptr(counter),
-                                                int(perturb), stream())
+    def occupancy_bounds(grid, C, H):
+        """extension: int32 [C, 6] box around the occupied cells of each cascade level, or None when H is not a power of two >= 4"""
+        if H < 4 or H & (H - 1):
+            return None
+        need_cuda(grid)
+        bounds = torch.empty(C, 6, dtype=torch.int32, device=grid.device)
+        _lib.call("enerf_occupancy_bounds", ptr(grid), C, H, ptr(bounds), stream())
+        return bounds
+
+    @staticmethod
+    def march_rays_train(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, xyzs, dirs, deltas, rays, counter, perturb,
+                         occ_bounds=None):
+        """`occ_bounds` (extension): the result of occupancy_bounds() for this bitfield; the march then steps over the candidates outside
+        the occupied box without probing the grid — same samples, bit for bit"""
+        need_cuda(rays_o, rays_d, grid, nears, fars, xyzs, dirs, deltas, rays, counter, occ_bounds)
+        _lib.call("enerf_march_rays_train_bounded", ptr(rays_o), ptr(rays_d), ptr(grid), bound, dt_gamma, max_steps, N, C, H, M,
+                                                        ptr(nears), ptr(fars), ptr(xyzs), ptr(dirs), ptr(deltas), ptr(rays), ptr(counter),
+                                                        int(perturb), ptr(occ_bounds), stream())
 
     @staticmethod
     def composite_rays_train_forward(sigmas, rgbs, deltas, rays, M, N, weights_sum, depth, image):
@@ -70,13 +83,13 @@ class _Raymarching:
 
     @staticmethod
     def march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid, nears, fars, xyzs, dirs, deltas, perturb,
-                   n_alive_dev=None):
+                   n_alive_dev=None, occ_bounds=None):
         """`n_alive_dev` (extension, also on the two functions below): int32 device scalar with the true number of alive rays; `n_alive`
         is then an upper bound and the host does not have to read the count back before launching"""
-        need_cuda(rays_alive, rays_t, rays_o, rays_d, grid, nears, fars, xyzs, dirs, deltas, n_alive_dev)
-        _lib.call("enerf_march_rays_dev", n_alive, n_step, ptr(rays_alive), ptr(rays_t), ptr(rays_o), ptr(rays_d), bound, dt_gamma,
-                                              max_steps, C, H, ptr(grid), ptr(nears), ptr(fars), ptr(xyzs), ptr(dirs), ptr(deltas),
-                                              int(perturb), ptr(n_alive_dev), stream())
+        need_cuda(rays_alive, rays_t, rays_o, rays_d, grid, nears, fars, xyzs, dirs, deltas, n_alive_dev, occ_bounds)
+        _lib.call("enerf_march_rays_bounded", n_alive, n_step, ptr(rays_alive), ptr(rays_t), ptr(rays_o), ptr(rays_d), bound, dt_gamma,
+                                                  max_steps, C, H, ptr(grid), ptr(nears), ptr(fars), ptr(xyzs), ptr(dirs), ptr(deltas),
+                                                  int(perturb), ptr(n_alive_dev), ptr(occ_bounds), stream())
 
     @staticmethod
     def composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image, n_alive_dev=None):

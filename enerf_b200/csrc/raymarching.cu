@@ -197,6 +197,83 @@ __device__ __forceinline__ float const_step_candidate(float tb, float c, unsigne
     return t;
 }
 
+// Candidate 32 of a batch (= candidate 0 of the next one) without generating the 32 in between: what 32 sequential steps leave in t
+__device__ __forceinline__ float advance_batch(float tb, const MarchCfg& c) {
+    if (c.dt_gamma == 0.0f) {
+        const float s = clampf(0.0f, c.dt_min, c.dt_max);
+        const float t1 = tb + s;
+        const float d1 = t1 - tb;
+        const float d2 = (t1 + s) - t1;
+        const float t_end = __fmaf_rn(32.0f, d1, tb);
+        const bool same_binade = (__float_as_uint(tb) >> 23) == (__float_as_uint(t_end) >> 23);
+        if (d1 == d2 && same_binade && tb >= s && s > 0.0f) return t_end;      // see const_step_candidate
+        float t = tb;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) t += s;
+        return t;
+    }
+    float t = tb;
+    for (int j = 0; j < 32; ++j) t += step_of(t, c);
+    return t;
+}
+
+// The parameter interval in which a ray can meet an occupied cell at all: its intersection with the box around the occupied cells of
+// every cascade level (`occ_bounds`: int32 [C][6] = min x, y, z, max x, y, z in cells; enerf_occupancy_bounds).  The sequence of
+// candidate parameters t0, t0 + dt, ... does not depend on the occupancy (an empty voxel is left by repeated `t += dt`,
+// raymarching.cu:390-398), so candidates outside the interval can be stepped over without looking at the grid: the samples, their
+// order and every bit of them stay what the exhaustive march produces.  Without bounds: (-inf, +inf).
+struct TRange {
+    float lo, hi;
+};
+__device__ __forceinline__ TRange occupied_range(const Ray& r, const MarchCfg& c, const int32_t* __restrict__ occ_bounds) {
+    TRange o;
+    o.lo = -FLT_MAX;
+    o.hi = FLT_MAX;
+    if (!occ_bounds) return o;
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (uint32_t l = 0; l < c.C; ++l) {
+        const float mb = fminf((float)(1u << l), c.bound);
+        const float cell = 2.0f * mb / c.Hf;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const int mn = __ldg(occ_bounds + l * 6 + a), mx = __ldg(occ_bounds + l * 6 + 3 + a);
+            if (mx >= mn) {
+                lo[a] = fminf(lo[a], (float)mn * cell - mb);
+                hi[a] = fmaxf(hi[a], (float)(mx + 1) * cell - mb);
+            }
+        }
+    }
+    if (hi[0] < lo[0]) {          // nothing occupied anywhere
+        o.lo = FLT_MAX;
+        o.hi = -FLT_MAX;
+        return o;
+    }
+    // one cell of the finest level plus rounding of the cell index / the slab test: far more than either can be off by
+    const float margin = 2.0f * fminf(1.0f, c.bound) / c.Hf + 1e-3f * c.bound;
+    const float org[3] = {r.ox, r.oy, r.oz}, rd[3] = {r.rdx, r.rdy, r.rdz};
+    float t_in = -FLT_MAX, t_out = FLT_MAX;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float ta = (lo[a] - margin - org[a]) * rd[a], tb = (hi[a] + margin - org[a]) * rd[a];
+        // a NaN (origin on a slab plane of an axis-parallel ray) leaves the axis unconstrained: fminf / fmaxf return the other operand
+        t_in = fmaxf(t_in, fminf(ta, tb));
+        t_out = fminf(t_out, fmaxf(ta, tb));
+    }
+    const float slack = 1e-4f * (1.0f + fabsf(t_in) + fabsf(t_out));
+    o.lo = t_in - slack;
+    o.hi = t_out + slack;
+    if (!(o.lo <= o.hi)) {        // the ray misses the box (or a NaN crept in: then be exhaustive)
+        if (o.lo > o.hi) {
+            o.lo = FLT_MAX;
+            o.hi = -FLT_MAX;
+        } else {
+            o.lo = -FLT_MAX;
+            o.hi = FLT_MAX;
+        }
+    }
+    return o;
+}
+
 // Marches one ray with one warp.  Emits at most `limit` samples, starting at t0; returns the
 // number emitted (warp-uniform).  With WRITE, sample i of this ray goes to row i of
 // xyzs/dirs/deltas (already offset to the ray's range).
@@ -211,7 +288,7 @@ struct BatchLog {
 template <bool WRITE>
 __device__ uint32_t march_warp(const Ray& r, const MarchCfg& c, const uint8_t* __restrict__ grid,
                                float t0, float far, uint32_t limit, float* __restrict__ xyzs,
-                               float* __restrict__ dirs, float* __restrict__ deltas, BatchLog* log = nullptr,
+                               float* __restrict__ dirs, float* __restrict__ deltas, TRange occ, BatchLog* log = nullptr,
                                uint32_t* n_logged = nullptr) {
     const unsigned lane = lane_id();
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -222,6 +299,14 @@ __device__ uint32_t march_warp(const Ray& r, const MarchCfg& c, const uint8_t* _
     float last_t = t0;            // t after the previously emitted sample (raymarching.cu:425,462)
 
     while (tb < far && count < limit) {
+        if (tb > occ.hi) break;                   // no occupied cell from here on: nothing more to emit
+        if (tb < occ.lo) {                        // the whole batch may lie before the first occupied cell: step over it unprobed
+            const float te = advance_batch(tb, c);
+            if (te <= occ.lo) {
+                tb = te;
+                continue;
+            }
+        }
         // 32 consecutive candidates; lane i applies the step function i times so that its t is
         // bit-identical to the sequential loop's.
         float t = tb;
@@ -370,11 +455,12 @@ k_march_rays_train(const float* __restrict__ rays_o, const float* __restrict__ r
                    const uint8_t* __restrict__ grid, MarchCfg c, uint32_t max_steps, uint32_t N, uint32_t M,
                    const float* __restrict__ nears, const float* __restrict__ fars,
                    float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas,
-                   int32_t* __restrict__ rays, int32_t* __restrict__ counter, uint32_t perturb) {
+                   int32_t* __restrict__ rays, int32_t* __restrict__ counter, uint32_t perturb, const int32_t* __restrict__ occ_bounds) {
     const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (n >= N) return;
     const unsigned lane = lane_id();
     const Ray r = load_ray(rays_o, rays_d, n);
+    const TRange occ = occupied_range(r, c, occ_bounds);
     const float near = nears[n], far = fars[n];
     float t0 = near;
     if (perturb) {
@@ -384,7 +470,7 @@ k_march_rays_train(const float* __restrict__ rays_o, const float* __restrict__ r
     __shared__ BatchLog logs[8];
     BatchLog* log = &logs[threadIdx.x >> 5];
     uint32_t n_logged = 0;
-    const uint32_t num_steps = march_warp<false>(r, c, grid, t0, far, max_steps, nullptr, nullptr, nullptr, log, &n_logged);
+    const uint32_t num_steps = march_warp<false>(r, c, grid, t0, far, max_steps, nullptr, nullptr, nullptr, occ, log, &n_logged);
     __syncwarp();
 
     uint32_t point_index = 0;
@@ -402,7 +488,7 @@ k_march_rays_train(const float* __restrict__ rays_o, const float* __restrict__ r
     float* pd = dirs + (size_t)point_index * 3;
     float* pl = deltas + (size_t)point_index * 2;
     if (n_logged <= (uint32_t)kLogBatches) replay_warp(r, c, t0, log, n_logged, px, pd, pl);
-    else march_warp<true>(r, c, grid, t0, far, num_steps, px, pd, pl);     // more emitting batches than the log holds: re-march
+    else march_warp<true>(r, c, grid, t0, far, num_steps, px, pd, pl, occ);     // more emitting batches than the log holds: re-march
 }
 
 // The inference loop of NeRFRenderer.run_cuda (renderer.py:364-391) reads the number of alive rays back to the host after every
@@ -421,7 +507,8 @@ k_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* __restrict__ rays
              const float* __restrict__ rays_t, const float* __restrict__ rays_o,
              const float* __restrict__ rays_d, MarchCfg c, const uint8_t* __restrict__ grid,
              const float* __restrict__ nears, const float* __restrict__ fars, float* __restrict__ xyzs,
-             float* __restrict__ dirs, float* __restrict__ deltas, uint32_t perturb, const int32_t* __restrict__ n_alive_dev) {
+             float* __restrict__ dirs, float* __restrict__ deltas, uint32_t perturb, const int32_t* __restrict__ n_alive_dev,
+             const int32_t* __restrict__ occ_bounds) {
     const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (n >= alive_count(n_alive, n_alive_dev)) return;
     const uint32_t index = (uint32_t)rays_alive[n];
@@ -433,7 +520,71 @@ k_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* __restrict__ rays
         t = __fmaf_rn(c.dt_min, rng.next_float(), t);
     }
     const size_t base = (size_t)n * n_step;
-    march_warp<true>(r, c, grid, t, far, n_step, xyzs + base * 3, dirs + base * 3, deltas + base * 2);
+    march_warp<true>(r, c, grid, t, far, n_step, xyzs + base * 3, dirs + base * 3, deltas + base * 2, occupied_range(r, c, occ_bounds));
+}
+
+// Box around the occupied cells of each cascade level: one CTA per level scans the level's bits 128 at a time (128 consecutive Morton
+// codes = an aligned 8 x 4 x 4 block of cells, taken whole when any of its bits is set).  out: int32 [C][6] = min x, y, z, max x, y, z;
+// an empty level gets min = H, max = -1.
+__global__ void __launch_bounds__(1024)
+k_occupancy_bounds(const uint8_t* __restrict__ grid, uint32_t H, uint32_t words_per_level, int32_t* __restrict__ out) {
+    const uint32_t level = blockIdx.x;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(grid) + (size_t)level * words_per_level;
+    int mn[3] = {(int)H, (int)H, (int)H}, mx[3] = {-1, -1, -1};
+    // `span` consecutive Morton codes starting at a multiple of span = an aligned block of ex x ey x ez cells, taken whole
+    auto take = [&](uint32_t code, int ex, int ey, int ez) {
+        const int x = (int)compact3(code), y = (int)compact3(code >> 1), z = (int)compact3(code >> 2);
+        mn[0] = min(mn[0], x); mn[1] = min(mn[1], y); mn[2] = min(mn[2], z);
+        mx[0] = max(mx[0], x + ex - 1); mx[1] = max(mx[1], y + ey - 1); mx[2] = max(mx[2], z + ez - 1);
+    };
+    // one CTA reads a whole level (256 KB at H = 128): eight independent 16-byte loads in flight per thread (a plain loop is a chain of
+    // memory latencies: 46 us for three levels), and one decode per non-zero 16 bytes = 128 codes = an 8 x 4 x 4 block
+    const uint32_t n4 = (words_per_level % 4u == 0u) ? words_per_level / 4u : 0u;      // levels stay 16-byte aligned only then
+    const uint4* w4 = reinterpret_cast<const uint4*>(w);
+    for (uint32_t base = 0; base < n4; base += 8u * blockDim.x) {
+        uint4 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t i = base + (uint32_t)k * blockDim.x + threadIdx.x;
+            v[k] = i < n4 ? __ldg(w4 + i) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if ((v[k].x | v[k].y | v[k].z | v[k].w) != 0u) take((base + (uint32_t)k * blockDim.x + threadIdx.x) * 128u, 8, 4, 4);
+    }
+    for (uint32_t i = n4 * 4u + threadIdx.x; i < words_per_level; i += blockDim.x)
+        if (__ldg(w + i) != 0u) take(i * 32u, 4, 4, 2);
+    __shared__ int s_mn[3][32], s_mx[3][32];
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int k = 16; k > 0; k >>= 1) {
+            mn[a] = min(mn[a], __shfl_xor_sync(kFull, mn[a], k));
+            mx[a] = max(mx[a], __shfl_xor_sync(kFull, mx[a], k));
+        }
+        if (lane == 0) {
+            s_mn[a][warp] = mn[a];
+            s_mx[a][warp] = mx[a];
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const unsigned n_warps = blockDim.x >> 5;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            int v0 = lane < n_warps ? s_mn[a][lane] : (int)H, v1 = lane < n_warps ? s_mx[a][lane] : -1;
+#pragma unroll
+            for (int k = 16; k > 0; k >>= 1) {
+                v0 = min(v0, __shfl_xor_sync(kFull, v0, k));
+                v1 = max(v1, __shfl_xor_sync(kFull, v1, k));
+            }
+            if (lane == 0) {
+                out[level * 6 + a] = v0;
+                out[level * 6 + 3 + a] = min(v1, (int)H - 1);
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -805,17 +956,32 @@ int enerf_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t*
     return 0;
 }
 
-int enerf_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
-                           float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
-                           const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
-                           int32_t* rays, int32_t* counter, uint32_t perturb, void* stream) {
+int enerf_occupancy_bounds(const uint8_t* grid, uint32_t C, uint32_t H, int32_t* bounds, void* stream) {
+    ENERF_REQUIRE(C >= 1 && C <= 16 && H >= 4 && H <= 1024 && (H & (H - 1)) == 0, "occupancy_bounds", "C in [1,16], H a power of two in [4,1024]");
+    ENERF_REQUIRE(((uintptr_t)grid & 15u) == 0, "occupancy_bounds", "bitfield must be 16-byte aligned");
+    k_occupancy_bounds<<<C, 1024, 0, as_stream(stream)>>>(grid, H, H * H * H / 32u, bounds);
+    ENERF_CHECK_LAUNCH("occupancy_bounds");
+    return 0;
+}
+
+int enerf_march_rays_train_bounded(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
+                                   float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                                   const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
+                                   int32_t* rays, int32_t* counter, uint32_t perturb, const int32_t* occ_bounds, void* stream) {
     if (N == 0) return 0;
     ENERF_REQUIRE(C >= 1 && C <= 16 && H >= 2 && H <= 1024 && max_steps > 0, "march_rays_train", "bad C/H/max_steps");
     const MarchCfg c = make_cfg(bound, dt_gamma, max_steps, C, H);
     k_march_rays_train<<<ceil_div(N, 8u), 256, 0, as_stream(stream)>>>(rays_o, rays_d, grid, c, max_steps, N, M, nears, fars,
-                                                                      xyzs, dirs, deltas, rays, counter, perturb);
+                                                                      xyzs, dirs, deltas, rays, counter, perturb, occ_bounds);
     ENERF_CHECK_LAUNCH("march_rays_train");
     return 0;
+}
+int enerf_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
+                           float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                           const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
+                           int32_t* rays, int32_t* counter, uint32_t perturb, void* stream) {
+    return enerf_march_rays_train_bounded(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, xyzs, dirs, deltas, rays, counter,
+                                          perturb, nullptr, stream);
 }
 
 #define ENERF_NCH_SWITCH(n_ch, name, CALL)                                         \
@@ -851,17 +1017,24 @@ int enerf_composite_rays_train_backward(const float* grad_weights_sum, const flo
     return 0;
 }
 
-int enerf_march_rays_dev(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
-                         const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps,
-                         uint32_t C, uint32_t H, const uint8_t* grid, const float* nears, const float* fars, float* xyzs,
-                         float* dirs, float* deltas, uint32_t perturb, const int32_t* n_alive_dev, void* stream) {
+int enerf_march_rays_bounded(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
+                             const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps,
+                             uint32_t C, uint32_t H, const uint8_t* grid, const float* nears, const float* fars, float* xyzs,
+                             float* dirs, float* deltas, uint32_t perturb, const int32_t* n_alive_dev, const int32_t* occ_bounds, void* stream) {
     if (n_alive == 0 || n_step == 0) return 0;
     ENERF_REQUIRE(C >= 1 && C <= 16 && H >= 2 && H <= 1024 && max_steps > 0, "march_rays", "bad C/H/max_steps");
     const MarchCfg c = make_cfg(bound, dt_gamma, max_steps, C, H);
     k_march_rays<<<ceil_div(n_alive, 8u), 256, 0, as_stream(stream)>>>(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, c,
-                                                                     grid, nears, fars, xyzs, dirs, deltas, perturb, n_alive_dev);
+                                                                     grid, nears, fars, xyzs, dirs, deltas, perturb, n_alive_dev, occ_bounds);
     ENERF_CHECK_LAUNCH("march_rays");
     return 0;
+}
+int enerf_march_rays_dev(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
+                         const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps,
+                         uint32_t C, uint32_t H, const uint8_t* grid, const float* nears, const float* fars, float* xyzs,
+                         float* dirs, float* deltas, uint32_t perturb, const int32_t* n_alive_dev, void* stream) {
+    return enerf_march_rays_bounded(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid, nears, fars, xyzs,
+                                    dirs, deltas, perturb, n_alive_dev, nullptr, stream);
 }
 int enerf_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
                      const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps,

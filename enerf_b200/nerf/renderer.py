@@ -206,6 +206,7 @@ class NeRFRenderer(nn.Module):
             count_dev = None
             n_bound = N
             shaded = torch.zeros(1, dtype=torch.int64, device=device)
+            occ_bounds = raymarching.occupancy_bounds(self.density_bitfield, self.cascade, self.grid_size)      # once per frame
             step, i, since_sync, syncs = 0, 0, 0, 0
             while step < 1024:   # hard-coded in the reference as well (renderer.py:364)
                 if step == 0:
@@ -231,7 +232,7 @@ class NeRFRenderer(nn.Module):
                     n_step = max(n_step, min(self.inference_batch_samples // n_bound, 1024 - step))
                 xyzs, dirs, deltas = raymarching.march_rays(n_bound, n_step, rays_alive[i % 2], rays_t[i % 2], rays_o, rays_d, self.bound,
                                                             self.density_bitfield, self.cascade, self.grid_size, nears, fars, 128, perturb,
-                                                            dt_gamma, max_steps, count_dev)
+                                                            dt_gamma, max_steps, count_dev, occ_bounds)
                 sigmas, rgbs = self(xyzs, dirs)
                 sigmas = self.density_scale * sigmas
                 if image is None:

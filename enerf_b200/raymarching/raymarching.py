@@ -135,8 +135,10 @@ class _march_rays_train(Function):
         if step_counter is None:
             step_counter = torch.zeros(2, dtype=torch.int32, device=dev)
 
+        # the box around the occupied cells (one 5 us pass over the bitfield, recomputed on every call so that it can never be stale):
+        # the marcher steps over the candidates outside it without probing the grid
         _backend.march_rays_train(rays_o, rays_d, density_bitfield, bound, dt_gamma, max_steps, N, C, H, M, nears, fars,
-                                  xyzs, dirs, deltas, rays, step_counter, perturb)
+                                  xyzs, dirs, deltas, rays, step_counter, perturb, _backend.occupancy_bounds(density_bitfield, C, H))
 
         if exact:
             # first epochs only: size the outputs to the real sample count (one D2H read)
@@ -187,9 +189,10 @@ class _march_rays(Function):
     @staticmethod
     @_fwd32
     def forward(ctx, n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, density_bitfield, C, H, near, far, align=-1,
-                perturb=False, dt_gamma=0, max_steps=1024, n_alive_dev=None):
+                perturb=False, dt_gamma=0, max_steps=1024, n_alive_dev=None, occ_bounds=None):
         """March each alive ray up to n_step samples from rays_t; slots without a sample stay zero.  `n_alive_dev` (extension): int32
-        device scalar holding the true alive count, `n_alive` then being an upper bound."""
+        device scalar holding the true alive count, `n_alive` then being an upper bound.  `occ_bounds` (extension): `occupancy_bounds()` of
+        this bitfield — candidates outside the occupied box are stepped over unprobed (same samples)."""
         rays_o, rays_d = _rays(rays_o), _rays(rays_d)
         M = _pad_up(n_alive * n_step, align)
         dev = rays_o.device
@@ -197,11 +200,16 @@ class _march_rays(Function):
         dirs = torch.zeros(M, 3, dtype=torch.float32, device=dev)
         deltas = torch.zeros(M, 2, dtype=torch.float32, device=dev)
         _backend.march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, density_bitfield,
-                            near, far, xyzs, dirs, deltas, perturb, n_alive_dev)
+                            near, far, xyzs, dirs, deltas, perturb, n_alive_dev, occ_bounds)
         return xyzs, dirs, deltas
 
 
 march_rays = _march_rays.apply
+
+
+def occupancy_bounds(density_bitfield, C, H):
+    """int32 [C, 6] (min x, y, z, max x, y, z in cells) around the occupied cells of each cascade level; None if H is not a power of two"""
+    return _backend.occupancy_bounds(density_bitfield.contiguous(), C, H)
 
 
 class _composite_rays(Function):

@@ -112,6 +112,20 @@ int enerf_composite_rays_dev(uint32_t n_alive, uint32_t n_step, const int32_t* r
                              float* image, const int32_t* n_alive_dev, void* stream);
 int enerf_compact_rays_dev(uint32_t n_alive, int32_t* rays_alive, const int32_t* rays_alive_old, float* rays_t,
                            const float* rays_t_old, int32_t* alive_counter, const int32_t* n_alive_dev, void* stream);
+/* Marching bounded by the occupied region (no reference counterpart; the samples are those of raymarching.cu:313-480 / :700-813, bit for
+ * bit).  The candidate parameters t0, t0 + dt, ... of a ray do not depend on the occupancy (an empty voxel is left by repeated
+ * `t += dt`, raymarching.cu:390-398), so candidates outside the box around the occupied cells can be stepped over without a grid
+ * lookup and the march can stop behind it.  enerf_occupancy_bounds: bounds = int32 [C][6] (min x, y, z, max x, y, z in cells of each
+ * cascade level, rounded outwards to aligned 8 x 4 x 4 blocks; an empty level has min = H, max = -1); H a power of two >= 4.  occ_bounds == NULL: the exhaustive march. */
+int enerf_occupancy_bounds(const uint8_t* grid, uint32_t C, uint32_t H, int32_t* bounds, void* stream);
+int enerf_march_rays_train_bounded(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound, float dt_gamma,
+                                   uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float* nears,
+                                   const float* fars, float* xyzs, float* dirs, float* deltas, int32_t* rays, int32_t* counter,
+                                   uint32_t perturb, const int32_t* occ_bounds, void* stream);
+int enerf_march_rays_bounded(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t, const float* rays_o,
+                             const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
+                             const uint8_t* grid, const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
+                             uint32_t perturb, const int32_t* n_alive_dev, const int32_t* occ_bounds, void* stream);
 
 /* ------------------------------------------------------------------ gridencoder ---- */
 /* gridencoder/src/gridencoder.h:12-13, gridencoder/src/gridencoder.cu.
