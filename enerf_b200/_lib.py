@@ -66,6 +66,8 @@ _SIGS = {
     "enerf_occ_points_partial": [_p, _p, _u32, _u32, _u32, _f32, _p, _p, _p, _p, _p, _u64, _p],
     "enerf_occ_update": [_p, _p, _p, _u32, _u32, _u32, _f32, _f32, _f32, _p, _p, _p, _p, _p],
     "enerf_mark_untrained_grid": [_p, _p, _u32, _f32, _f32, _f32, _f32, _u32, _u32, _f32, _p],
+    "enerf_finish_rays_forward": [_p, _p, _p, _p, _p, _p, _int, _f32, _u32, _u32, _p, _p, _p],
+    "enerf_finish_rays_backward": [_p, _p, _p, _p, _p, _p, _int, _f32, _u32, _u32, _p, _p, _p],
     "enerf_composite_uniform_forward": [_p, _p, _p, _p, _u32, _u32, _u32, _f32, _p, _p, _p, _p],
     "enerf_composite_uniform_backward": [_p, _p, _p, _p, _p, _p, _p, _u32, _u32, _u32, _f32, _p, _p],
     "enerf_get_rays": [_p, _f32, _f32, _f32, _f32, _u32, _u32, _p, _u32, _u32, _u32, _p, _f32, _p, _p, _p, _p, _p],

@@ -156,11 +156,68 @@ k_uniform_bwd(const float* __restrict__ grad_weights, const float* __restrict__ 
     }
 }
 
+// The last two lines of NeRFRenderer.run_cuda (renderer.py:397-398) as one kernel each way instead of eight ATen launches:
+//   image += (1 - weights_sum) * bg_color;   depth = clamp(depth - nears, min=0) / (fars - nears)
+// evaluated with torch's operation order and roundings (no fused multiply-add), so the results are the ATen ones to the bit.
+// bg: NULL (scalar `bg_scalar`), or [n_ch] (bg_per_ray = 0), or [N, n_ch] (bg_per_ray = 1).
+__global__ void __launch_bounds__(256)
+k_finish_fwd(const float* __restrict__ weights_sum, const float* __restrict__ depth, const float* __restrict__ image,
+             const float* __restrict__ nears, const float* __restrict__ fars, const float* __restrict__ bg, int bg_per_ray, float bg_scalar,
+             uint32_t N, uint32_t n_ch, float* __restrict__ image_out, float* __restrict__ depth_out) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float rest = __fsub_rn(1.0f, weights_sum[n]);
+    for (uint32_t c = 0; c < n_ch; ++c) {
+        const float b = bg ? bg[(bg_per_ray ? (size_t)n * n_ch : 0) + c] : bg_scalar;
+        image_out[(size_t)n * n_ch + c] = __fadd_rn(image[(size_t)n * n_ch + c], __fmul_rn(rest, b));
+    }
+    const float near = nears[n];
+    float d = __fsub_rn(depth[n], near);
+    d = d < 0.0f ? 0.0f : d;                                  // keeps a NaN, like torch.clamp
+    depth_out[n] = __fdiv_rn(d, __fsub_rn(fars[n], near));
+}
+__global__ void __launch_bounds__(256)
+k_finish_bwd(const float* __restrict__ g_image, const float* __restrict__ g_depth, const float* __restrict__ depth,
+             const float* __restrict__ nears, const float* __restrict__ fars, const float* __restrict__ bg, int bg_per_ray, float bg_scalar,
+             uint32_t N, uint32_t n_ch, float* __restrict__ g_weights_sum, float* __restrict__ g_depth_in) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float acc = 0.0f;
+    if (g_image)
+        for (uint32_t c = 0; c < n_ch; ++c) {
+            const float b = bg ? bg[(bg_per_ray ? (size_t)n * n_ch : 0) + c] : bg_scalar;
+            acc = __fadd_rn(acc, __fmul_rn(g_image[(size_t)n * n_ch + c], b));
+        }
+    g_weights_sum[n] = -acc;
+    const float near = nears[n];
+    const float pass = __fsub_rn(depth[n], near) >= 0.0f ? 1.0f : 0.0f;
+    g_depth_in[n] = g_depth ? __fmul_rn(__fdiv_rn(g_depth[n], __fsub_rn(fars[n], near)), pass) : 0.0f;
+}
+
 }  // namespace enerf
 
 using namespace enerf;
 
 extern "C" {
+
+int enerf_finish_rays_forward(const float* weights_sum, const float* depth, const float* image, const float* nears, const float* fars,
+                              const float* bg, int bg_per_ray, float bg_scalar, uint32_t N, uint32_t n_ch, float* image_out, float* depth_out,
+                              void* stream) {
+    if (N == 0) return 0;
+    k_finish_fwd<<<ceil_div(N, 256u), 256, 0, as_stream(stream)>>>(weights_sum, depth, image, nears, fars, bg, bg_per_ray, bg_scalar, N, n_ch, image_out,
+                                                                  depth_out);
+    ENERF_CHECK_LAUNCH("finish_rays_forward");
+    return 0;
+}
+int enerf_finish_rays_backward(const float* g_image, const float* g_depth, const float* depth, const float* nears, const float* fars,
+                               const float* bg, int bg_per_ray, float bg_scalar, uint32_t N, uint32_t n_ch, float* g_weights_sum, float* g_depth_in,
+                               void* stream) {
+    if (N == 0) return 0;
+    k_finish_bwd<<<ceil_div(N, 256u), 256, 0, as_stream(stream)>>>(g_image, g_depth, depth, nears, fars, bg, bg_per_ray, bg_scalar, N, n_ch, g_weights_sum,
+                                                                  g_depth_in);
+    ENERF_CHECK_LAUNCH("finish_rays_backward");
+    return 0;
+}
 
 int enerf_composite_uniform_forward(const float* sigmas, const float* z_vals, const float* nears, const float* fars, uint32_t N,
                                     uint32_t T, uint32_t T_dist, float density_scale, float* weights, float* weights_sum, float* depth,

@@ -247,8 +247,7 @@ class NeRFRenderer(nn.Module):
             if image is None:
                 image = torch.zeros(N, kwargs.get("out_dim_color", getattr(self, "out_dim_color", 3)), dtype=torch.float32, device=device)
 
-        image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
-        depth = torch.clamp(depth - nears, min=0) / (fars - nears)
+        image, depth = raymarching.finish_rays(weights_sum, depth, image, nears, fars, bg_color)      # renderer.py:397-398
         return {'depth': depth.view(*prefix), 'image': image.view(*prefix, image.shape[-1])}
 
     # ------------------------------------------------------------------ occupancy-grid maintenance

@@ -12,6 +12,7 @@ import torch
 from torch.amp import custom_bwd, custom_fwd
 from torch.autograd import Function
 
+from .. import _lib
 from .backend import _backend
 
 _fwd32 = custom_fwd(device_type='cuda', cast_inputs=torch.float32)
@@ -111,6 +112,12 @@ def _pad_up(m, align):
     return m + (align - m % align) if align > 0 else m
 
 
+def _zero_samples(M, dev):
+    """zero-initialised xyzs [M,3], dirs [M,3], deltas [M,2] (raymarching.py:205-207) carved out of one allocation: one fill kernel, not three"""
+    buf = torch.zeros(M * 8, dtype=torch.float32, device=dev)
+    return buf[:3 * M].view(M, 3), buf[3 * M:6 * M].view(M, 3), buf[6 * M:].view(M, 2)
+
+
 # ---------------------------------------------------------------------------- train
 class _march_rays_train(Function):
     @staticmethod
@@ -128,9 +135,7 @@ class _march_rays_train(Function):
         exact = force_all_rays or mean_count <= 0
         M = N * max_steps if exact else _pad_up(mean_count, align)
 
-        xyzs = torch.zeros(M, 3, dtype=torch.float32, device=dev)
-        dirs = torch.zeros(M, 3, dtype=torch.float32, device=dev)
-        deltas = torch.zeros(M, 2, dtype=torch.float32, device=dev)
+        xyzs, dirs, deltas = _zero_samples(M, dev)
         rays = torch.empty(N, 3, dtype=torch.int32, device=dev)
         if step_counter is None:
             step_counter = torch.zeros(2, dtype=torch.int32, device=dev)
@@ -174,14 +179,71 @@ class _composite_rays_train(Function):
         # grad_depth is not propagated (raymarching.py:270)
         sigmas, rgbs, deltas, rays, weights_sum, image = ctx.saved_tensors
         M, N = ctx.dims
-        grad_sigmas = torch.zeros_like(sigmas)
-        grad_rgbs = torch.zeros_like(rgbs)
+        if rgbs.dim() == 2 and rgbs.dtype == sigmas.dtype:        # one zero fill for both gradients
+            buf = torch.zeros(M * (1 + rgbs.shape[1]), dtype=sigmas.dtype, device=sigmas.device)
+            grad_sigmas, grad_rgbs = buf[:M], buf[M:].view(M, rgbs.shape[1])
+        else:
+            grad_sigmas, grad_rgbs = torch.zeros_like(sigmas), torch.zeros_like(rgbs)
         _backend.composite_rays_train_backward(grad_weights_sum.contiguous(), grad_image.contiguous(), sigmas, rgbs, deltas, rays,
                                                weights_sum, image, M, N, grad_sigmas, grad_rgbs)
         return grad_sigmas, grad_rgbs, None, None
 
 
 composite_rays_train = _composite_rays_train.apply
+
+
+class _finish_rays(Function):
+    @staticmethod
+    @_fwd32
+    def forward(ctx, weights_sum, depth, image, nears, fars, bg, bg_scalar):
+        N, n_ch = image.shape
+        weights_sum, depth, image = weights_sum.contiguous(), depth.contiguous(), image.contiguous()
+        image_out, depth_out = torch.empty_like(image), torch.empty_like(depth)
+        per_ray = int(bg is not None and bg.dim() == 2)
+        _lib.call("enerf_finish_rays_forward", _lib.ptr(weights_sum), _lib.ptr(depth), _lib.ptr(image), _lib.ptr(nears), _lib.ptr(fars), _lib.ptr(bg),
+                  per_ray, float(bg_scalar), N, n_ch, _lib.ptr(image_out), _lib.ptr(depth_out), _lib.stream())
+        ctx.save_for_backward(depth, nears, fars, bg if bg is not None else depth.new_empty(0))
+        ctx.meta = (N, n_ch, per_ray, float(bg_scalar), bg is not None)
+        return image_out, depth_out
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, g_image, g_depth):
+        depth, nears, fars, bg = ctx.saved_tensors
+        N, n_ch, per_ray, bg_scalar, has_bg = ctx.meta
+        g_image = None if g_image is None else g_image.contiguous()
+        g_depth = None if g_depth is None else g_depth.contiguous()
+        g_ws, g_d = torch.empty_like(depth), torch.empty_like(depth)
+        _lib.call("enerf_finish_rays_backward", _lib.ptr(g_image), _lib.ptr(g_depth), _lib.ptr(depth), _lib.ptr(nears), _lib.ptr(fars),
+                  _lib.ptr(bg) if has_bg else None, per_ray, bg_scalar, N, n_ch, _lib.ptr(g_ws), _lib.ptr(g_d), _lib.stream())
+        return g_ws, g_d, g_image, None, None, None, None
+
+
+def finish_rays(weights_sum, depth, image, nears, fars, bg_color):
+    """The two lines that end NeRFRenderer.run_cuda (renderer.py:397-398):
+        image = image + (1 - weights_sum).unsqueeze(-1) * bg_color;  depth = clamp(depth - nears, min=0) / (fars - nears)
+    as one kernel each way (same operation order and roundings as the ATen expression).  A background that needs a gradient (the
+    `bg_radius > 0` model) or an unusual shape keeps the ATen expression."""
+    N, n_ch = image.shape
+    bg, scalar = None, 0.0
+    fused = image.is_cuda and image.dtype == torch.float32 and depth.dtype == torch.float32 and weights_sum.dtype == torch.float32
+    if isinstance(bg_color, (int, float)):
+        scalar = float(bg_color)
+    elif torch.is_tensor(bg_color) and not bg_color.requires_grad and bg_color.is_cuda and bg_color.numel() > 0:
+        b = bg_color.detach().float()
+        if b.dim() == 0:
+            bg = b.reshape(1).expand(n_ch).contiguous()
+        elif b.shape == (n_ch,) or b.shape == (N, n_ch):
+            bg = b.contiguous()
+        elif b.shape == (1, n_ch):
+            bg = b.reshape(n_ch).contiguous()
+        else:
+            fused = False
+    else:
+        fused = False
+    if not fused:
+        return image + (1 - weights_sum).unsqueeze(-1) * bg_color, torch.clamp(depth - nears, min=0) / (fars - nears)
+    return _finish_rays.apply(weights_sum, depth, image, nears, fars, bg, scalar)
 
 
 # ---------------------------------------------------------------------------- inference
@@ -196,9 +258,7 @@ class _march_rays(Function):
         rays_o, rays_d = _rays(rays_o), _rays(rays_d)
         M = _pad_up(n_alive * n_step, align)
         dev = rays_o.device
-        xyzs = torch.zeros(M, 3, dtype=torch.float32, device=dev)
-        dirs = torch.zeros(M, 3, dtype=torch.float32, device=dev)
-        deltas = torch.zeros(M, 2, dtype=torch.float32, device=dev)
+        xyzs, dirs, deltas = _zero_samples(M, dev)
         _backend.march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, density_bitfield,
                             near, far, xyzs, dirs, deltas, perturb, n_alive_dev, occ_bounds)
         return xyzs, dirs, deltas

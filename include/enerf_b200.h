@@ -332,6 +332,18 @@ int enerf_composite_uniform_backward(const float* grad_weights, const float* gra
                                      uint32_t N, uint32_t T, uint32_t T_dist, float density_scale,
                                      float* grad_sigmas, void* stream);
 
+/* nerf/renderer.py:397-398, the two lines after the compositing of run_cuda, one kernel each way (ATen: eight launches):
+ *   image_out = image + (1 - weights_sum) * bg_color;  depth_out = clamp(depth - nears, min=0) / (fars - nears)
+ * in torch's operation order and roundings.  bg: NULL (use bg_scalar), [n_ch] (bg_per_ray = 0) or [N, n_ch] (bg_per_ray = 1).
+ * backward: g_weights_sum = -sum_c g_image * bg, g_depth_in = g_depth / (fars - nears) where depth - nears >= 0 (g_image passes through;
+ * either incoming gradient may be NULL). */
+int enerf_finish_rays_forward(const float* weights_sum, const float* depth, const float* image, const float* nears, const float* fars,
+                              const float* bg, int bg_per_ray, float bg_scalar, uint32_t N, uint32_t n_ch, float* image_out,
+                              float* depth_out, void* stream);
+int enerf_finish_rays_backward(const float* g_image, const float* g_depth, const float* depth, const float* nears, const float* fars,
+                               const float* bg, int bg_per_ray, float bg_scalar, uint32_t N, uint32_t n_ch, float* g_weights_sum,
+                               float* g_depth_in, void* stream);
+
 /* ------------------------------------------ next rows of the path ---- */
 /* N2 — ray generation on the device, fused with near_far_from_aabb.
  * nerf/utils.py:110-169 get_rays for given pixels: poses [B,4,4] cam2world (row-major), pixel n of every pose is

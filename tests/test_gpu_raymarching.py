@@ -322,3 +322,34 @@ def test_bounded_march_emits_the_samples_of_the_exhaustive_march(case):
         outs.append(acc)
     for (xa, da), (xb, db) in zip(*outs):
         assert torch.equal(xa, xb) and torch.equal(da, db)
+
+
+@pytest.mark.parametrize("n_ch,bg_kind", [(1, "scalar"), (3, "scalar"), (3, "vector"), (3, "per_ray"), (4, "zero_dim")])
+def test_finish_rays_is_the_aten_expression(n_ch, bg_kind):
+    """renderer.py:397-398 as one kernel: forward bit-identical to the ATen expression, gradients to 1e-6"""
+    g = torch.Generator(device=DEV).manual_seed(3)
+    N = 5000
+    ws = torch.rand(N, device=DEV, generator=g).requires_grad_()
+    depth = (torch.rand(N, device=DEV, generator=g) * 3).requires_grad_()
+    image = torch.rand(N, n_ch, device=DEV, generator=g).requires_grad_()
+    nears = torch.rand(N, device=DEV, generator=g) + 0.2
+    fars = nears + torch.rand(N, device=DEV, generator=g) * 4 + 0.1
+    nears[:5] = fars[:5] = 3.4028234663852886e38                       # rays that miss the box: 0 / 0
+    bg = {"scalar": 1, "vector": torch.rand(n_ch, device=DEV, generator=g), "per_ray": torch.rand(N, n_ch, device=DEV, generator=g),
+          "zero_dim": torch.tensor(0.25, device=DEV)}[bg_kind]
+    gi, gd = torch.randn(N, n_ch, device=DEV, generator=g), torch.randn(N, device=DEV, generator=g)
+    gd[:5] = 0
+    outs = []
+    for fused in (True, False):
+        for v in (ws, depth, image):
+            v.grad = None
+        if fused:
+            im, dp = rm.finish_rays(ws, depth, image, nears, fars, bg)
+        else:
+            im, dp = image + (1 - ws).unsqueeze(-1) * bg, torch.clamp(depth - nears, min=0) / (fars - nears)
+        ((im * gi).sum() + (dp[5:] * gd[5:]).sum()).backward()
+        outs.append((im.detach(), dp.detach(), ws.grad.clone(), depth.grad.clone(), image.grad.clone()))
+    a, b = outs
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1][5:], b[1][5:]) and bool(torch.isnan(a[1][:5]).all()) and bool(torch.isnan(b[1][:5]).all())
+    assert float((a[2] - b[2]).abs().max()) <= 1e-5 and torch.equal(a[4], b[4])
+    assert float((a[3][5:] - b[3][5:]).abs().max()) <= 1e-6 * float(b[3][5:].abs().max())
