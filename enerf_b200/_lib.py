@@ -40,6 +40,8 @@ _SIGS = {
     "enerf_march_rays_bounded": [_u32, _u32, _p, _p, _p, _p, _f32, _f32, _u32, _u32, _u32, _p, _p, _p, _p, _p, _p, _u32, _p, _p, _p],
     "enerf_grid_encode_forward": [_p, _p, _p, _p, _u32, _u32, _u32, _u32, _f32, _u32, _int, _p, _u32, _int, _int, _p],
     "enerf_grid_encode_backward": [_p, _p, _p, _p, _p, _u32, _u32, _u32, _u32, _f32, _u32, _int, _p, _p, _u32, _int, _int, _int, _p],
+    "enerf_grid_encode_forward_xf": [_p, _f32, _f32, _p, _p, _p, _u32, _u32, _u32, _u32, _f32, _u32, _int, _p, _u32, _int, _int, _p],
+    "enerf_grid_encode_backward_xf": [_p, _p, _f32, _f32, _p, _p, _p, _u32, _u32, _u32, _u32, _f32, _u32, _int, _p, _p, _u32, _int, _int, _int, _p],
     "enerf_grid_set_backward_mode": [_int],
     "enerf_grid_set_backward_block": [_int],
     "enerf_grid_set_forward_mode": [_int],

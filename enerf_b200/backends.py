@@ -121,20 +121,25 @@ class _GridEncoder:
             raise RuntimeError("offsets must be an int tensor")
 
     @staticmethod
-    def grid_encode_forward(inputs, embeddings, offsets, outputs, B, D, C, L, S, H, calc_grad_inputs, dy_dx, gridtype, out_layout=0):
+    def grid_encode_forward(inputs, embeddings, offsets, outputs, B, D, C, L, S, H, calc_grad_inputs, dy_dx, gridtype, out_layout=0, in_add=0.0,
+                            in_mul=0.0):
+        """`in_add`, `in_mul` (extension): `inputs` are raw positions and the kernel applies x = (raw + in_add) * in_mul itself"""
         _GridEncoder._check(inputs, embeddings, offsets, outputs, dy_dx)
         _contig("outputs", outputs)
-        _lib.call("enerf_grid_encode_forward", ptr(inputs), ptr(embeddings), ptr(offsets), ptr(outputs), B, D, C, L, float(S), H,
-                                                   int(calc_grad_inputs), ptr(dy_dx), gridtype, dtype_code(embeddings), out_layout, stream())
+        _lib.call("enerf_grid_encode_forward_xf", ptr(inputs), float(in_add), float(in_mul), ptr(embeddings), ptr(offsets), ptr(outputs), B, D, C, L,
+                                                      float(S), H, int(calc_grad_inputs), ptr(dy_dx), gridtype, dtype_code(embeddings), out_layout,
+                                                      stream())
 
     @staticmethod
-    def grid_encode_backward(grad, inputs, embeddings, offsets, grad_embeddings, B, D, C, L, S, H, calc_grad_inputs, dy_dx, grad_inputs, gridtype, out_layout=0):
+    def grid_encode_backward(grad, inputs, embeddings, offsets, grad_embeddings, B, D, C, L, S, H, calc_grad_inputs, dy_dx, grad_inputs, gridtype, out_layout=0,
+                             in_add=0.0, in_mul=0.0):
         _GridEncoder._check(inputs, embeddings, offsets, grad, grad_embeddings, dy_dx, grad_inputs)
         _contig("grad", grad)
         _contig("grad_embeddings", grad_embeddings)
-        _lib.call("enerf_grid_encode_backward", ptr(grad), ptr(inputs), ptr(embeddings), ptr(offsets), ptr(grad_embeddings), B, D, C, L,
-                                                    float(S), H, int(calc_grad_inputs), ptr(dy_dx), ptr(grad_inputs), gridtype,
-                                                    dtype_code(grad), dtype_code(grad_embeddings), out_layout, stream())
+        _lib.call("enerf_grid_encode_backward_xf", ptr(grad), ptr(inputs), float(in_add), float(in_mul), ptr(embeddings), ptr(offsets),
+                                                       ptr(grad_embeddings), B, D, C, L, float(S), H, int(calc_grad_inputs), ptr(dy_dx),
+                                                       ptr(grad_inputs), gridtype, dtype_code(grad), dtype_code(grad_embeddings), out_layout,
+                                                       stream())
 
 
 class _SHEncoder:

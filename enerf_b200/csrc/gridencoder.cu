@@ -94,12 +94,21 @@ __device__ __forceinline__ uint32_t grid_index(const LevelGeom& g, const uint32_
     return index < g.hashmap_size ? index : index % g.hashmap_size;
 }
 
+// The positions of a launch: [B, D] fp32, either already in [0, 1] (mul == 0: the reference's contract) or raw world coordinates that
+// the kernel maps itself, x = (raw + add) * mul — GridEncoder.forward's `(inputs + bound) / (2 * bound)` (grid.py:144) with ATen's own
+// operation order and roundings (a division by a Python scalar is a multiplication by its fp32 reciprocal), which saves two
+// elementwise passes over the samples per call.
+struct Inputs {
+    const float* p;
+    float add, mul;
+};
 template <int D>
-__device__ __forceinline__ bool load_pos(const float* __restrict__ inputs, uint32_t b, float (&x)[D]) {
+__device__ __forceinline__ bool load_pos(const Inputs& inputs, uint32_t b, float (&x)[D]) {
     bool oob = false;
 #pragma unroll
     for (int d = 0; d < D; ++d) {
-        x[d] = __ldg(inputs + (size_t)b * D + d);
+        x[d] = __ldg(inputs.p + (size_t)b * D + d);
+        if (inputs.mul != 0.0f) x[d] = __fmul_rn(__fadd_rn(x[d], inputs.add), inputs.mul);
         oob |= (x[d] < 0.0f) || (x[d] > 1.0f);
     }
     return oob;
@@ -110,7 +119,7 @@ __device__ __forceinline__ bool load_pos(const float* __restrict__ inputs, uint3
 // ------------------------------------------------------------------------------------------
 template <typename T, int D, int C, bool BLC>
 __global__ void __launch_bounds__(512)
-k_grid_fwd(const float* __restrict__ inputs, const T* __restrict__ grid, const int32_t* __restrict__ offsets,
+k_grid_fwd(const Inputs inputs, const T* __restrict__ grid, const int32_t* __restrict__ offsets,
            T* __restrict__ outputs, uint32_t B, uint32_t L, float S, uint32_t H, bool calc_grad_inputs,
            T* __restrict__ dy_dx, uint32_t gridtype, uint32_t row_stride /* staging row, in T */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -248,7 +257,7 @@ struct LevelTab {
 
 template <typename T, int C, bool BLC>
 __global__ void __launch_bounds__(512)
-k_grid_fwd3(const float* __restrict__ inputs, const T* __restrict__ grid, const int32_t* __restrict__ offsets,
+k_grid_fwd3(const Inputs inputs, const T* __restrict__ grid, const int32_t* __restrict__ offsets,
             T* __restrict__ outputs, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype, uint32_t row_stride) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* stage = reinterpret_cast<T*>(smem_raw);
@@ -481,7 +490,7 @@ struct LevelWork {
 
 template <typename T, int C, bool BLC>
 __global__ void __launch_bounds__(256)
-k_grid_fwd_w(const float* __restrict__ inputs, const T* __restrict__ grid, const int32_t* __restrict__ offsets,
+k_grid_fwd_w(const Inputs inputs, const T* __restrict__ grid, const int32_t* __restrict__ offsets,
              T* __restrict__ outputs, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype, uint32_t n_groups,
              uint32_t row_words /* staging row stride in 32-bit words (odd) */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -611,7 +620,7 @@ __device__ __forceinline__ void red_add2(__half* addr, float a, float b) {
 // T = table / grad element type, G = gradient-table element type (T, or float for fp32 accumulation)
 template <typename T, typename G, int D, int C, bool BLC>
 __global__ void __launch_bounds__(512)
-k_grid_bwd(const T* __restrict__ grad, const float* __restrict__ inputs, const int32_t* __restrict__ offsets,
+k_grid_bwd(const T* __restrict__ grad, const Inputs inputs, const int32_t* __restrict__ offsets,
            G* __restrict__ grad_grid, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype) {
     const unsigned lane = threadIdx.x;
     const uint32_t b = blockIdx.x * kSamplesPerCta + lane;
@@ -667,7 +676,7 @@ k_grid_bwd(const T* __restrict__ grad, const float* __restrict__ inputs, const i
 // disappears.  Same sums as k_grid_bwd up to fp32 reassociation.
 template <typename T, typename G, int D, int C, bool BLC, int SEG>
 __global__ void __launch_bounds__(256)
-k_grid_bwd_walk(const T* __restrict__ grad, const float* __restrict__ inputs, const int32_t* __restrict__ offsets,
+k_grid_bwd_walk(const T* __restrict__ grad, const Inputs inputs, const int32_t* __restrict__ offsets,
                 G* __restrict__ grad_grid, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t level = t % L;
@@ -825,7 +834,7 @@ static inline uint32_t stage_row_stride(uint32_t L, uint32_t C, size_t elt) {
 }
 
 template <typename T, int D, int C>
-static int launch_fwd(const float* inputs, const T* emb, const int32_t* offsets, T* outputs, uint32_t B, uint32_t L, float S,
+static int launch_fwd(const Inputs inputs, const T* emb, const int32_t* offsets, T* outputs, uint32_t B, uint32_t L, float S,
                       uint32_t H, bool cg, T* dy_dx, uint32_t gridtype, int out_layout, cudaStream_t st) {
     const dim3 block(32, min(L, 16u));
     const dim3 grid(ceil_div(B, (uint32_t)kSamplesPerCta));
@@ -869,7 +878,7 @@ static int launch_fwd(const float* inputs, const T* emb, const int32_t* offsets,
 }
 
 template <typename T, typename G, int D, int C>
-static int launch_bwd(const T* grad, const float* inputs, const int32_t* offsets, G* gg, uint32_t B, uint32_t L, float S, uint32_t H,
+static int launch_bwd(const T* grad, const Inputs inputs, const int32_t* offsets, G* gg, uint32_t B, uint32_t L, float S, uint32_t H,
                       bool cg, const T* dy_dx, T* grad_inputs, uint32_t gridtype, int out_layout, cudaStream_t st) {
     if (g_bwd_walk && L <= 32 && (32 % L) == 0) {
         // samples per thread-run: every run boundary costs one extra flush (8 reductions) per level, longer runs mean fewer threads
@@ -946,10 +955,12 @@ int enerf_grid_set_backward_mode(int mode) {
     return 0;
 }
 
-int enerf_grid_encode_forward(const float* inputs, const void* embeddings, const int32_t* offsets, void* outputs,
-                              uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, int calc_grad_inputs,
-                              void* dy_dx, uint32_t gridtype, int dtype, int out_layout, void* stream) {
+int enerf_grid_encode_forward_xf(const float* raw_inputs, float in_add, float in_mul, const void* embeddings, const int32_t* offsets, void* outputs,
+                                 uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, int calc_grad_inputs,
+                                 void* dy_dx, uint32_t gridtype, int dtype, int out_layout, void* stream) {
     if (B == 0) return 0;
+    ENERF_REQUIRE(in_mul == 0.0f || !calc_grad_inputs, "grid_encode_forward", "dy_dx is defined for inputs in [0, 1] only");
+    const Inputs inputs = {raw_inputs, in_add, in_mul};
     ENERF_REQUIRE(dtype == ENERF_F32 || dtype == ENERF_F16, "grid_encode_forward", "dtype must be ENERF_F32 or ENERF_F16");
     ENERF_REQUIRE(out_layout == 0 || out_layout == 1, "grid_encode_forward", "out_layout must be 0 or 1");
     ENERF_REQUIRE(L >= 1 && L <= 64, "grid_encode_forward", "L must be in [1,64]");
@@ -967,12 +978,21 @@ int enerf_grid_encode_forward(const float* inputs, const void* embeddings, const
     return rc;
 }
 
-int enerf_grid_encode_backward(const void* grad, const float* inputs, const void* embeddings, const int32_t* offsets,
-                               void* grad_embeddings, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
-                               int calc_grad_inputs, const void* dy_dx, void* grad_inputs, uint32_t gridtype, int dtype,
-                               int grad_dtype, int out_layout, void* stream) {
+int enerf_grid_encode_forward(const float* inputs, const void* embeddings, const int32_t* offsets, void* outputs,
+                              uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, int calc_grad_inputs,
+                              void* dy_dx, uint32_t gridtype, int dtype, int out_layout, void* stream) {
+    return enerf_grid_encode_forward_xf(inputs, 0.0f, 0.0f, embeddings, offsets, outputs, B, D, C, L, S, H, calc_grad_inputs, dy_dx, gridtype, dtype,
+                                        out_layout, stream);
+}
+
+int enerf_grid_encode_backward_xf(const void* grad, const float* raw_inputs, float in_add, float in_mul, const void* embeddings, const int32_t* offsets,
+                                  void* grad_embeddings, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+                                  int calc_grad_inputs, const void* dy_dx, void* grad_inputs, uint32_t gridtype, int dtype,
+                                  int grad_dtype, int out_layout, void* stream) {
     (void)embeddings;
     if (B == 0) return 0;
+    ENERF_REQUIRE(in_mul == 0.0f || !calc_grad_inputs, "grid_encode_backward", "input gradients are defined for inputs in [0, 1] only");
+    const Inputs inputs = {raw_inputs, in_add, in_mul};
     ENERF_REQUIRE(dtype == ENERF_F32 || dtype == ENERF_F16, "grid_encode_backward", "dtype must be ENERF_F32 or ENERF_F16");
     ENERF_REQUIRE(grad_dtype == ENERF_F32 || grad_dtype == dtype, "grid_encode_backward", "grad_dtype must be ENERF_F32 or equal dtype");
     ENERF_REQUIRE(out_layout == 0 || out_layout == 1, "grid_encode_backward", "out_layout must be 0 or 1");
@@ -994,6 +1014,13 @@ int enerf_grid_encode_backward(const void* grad, const float* inputs, const void
                                                                cg, (const float*)dy_dx, (float*)grad_inputs, gridtype, out_layout, st)));
     }
     return rc;
+}
+int enerf_grid_encode_backward(const void* grad, const float* inputs, const void* embeddings, const int32_t* offsets,
+                               void* grad_embeddings, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+                               int calc_grad_inputs, const void* dy_dx, void* grad_inputs, uint32_t gridtype, int dtype,
+                               int grad_dtype, int out_layout, void* stream) {
+    return enerf_grid_encode_backward_xf(grad, inputs, 0.0f, 0.0f, embeddings, offsets, grad_embeddings, B, D, C, L, S, H, calc_grad_inputs, dy_dx,
+                                         grad_inputs, gridtype, dtype, grad_dtype, out_layout, stream);
 }
 
 }  // extern "C"

@@ -67,8 +67,9 @@ def _half_table(param):
 class _grid_encode(torch.autograd.Function):
     @staticmethod
     @custom_fwd(device_type='cuda')
-    def forward(ctx, inputs, embeddings, offsets, per_level_scale, base_resolution, calc_grad_inputs=False, gridtype=0):
-        """inputs [B, D] fp32 in [0, 1], embeddings [entries, C], offsets [L+1] int32  ->  [B, L*C]"""
+    def forward(ctx, inputs, embeddings, offsets, per_level_scale, base_resolution, calc_grad_inputs=False, gridtype=0, in_add=0.0, in_mul=0.0):
+        """inputs [B, D] fp32 in [0, 1] — or, with in_mul != 0, raw positions that the kernels map with x = (raw + in_add) * in_mul —,
+        embeddings [entries, C], offsets [L+1] int32  ->  [B, L*C]"""
         x = inputs.contiguous()
         n, dim = x.shape
         levels, width = offsets.shape[0] - 1, embeddings.shape[1]
@@ -80,8 +81,9 @@ class _grid_encode(torch.autograd.Function):
         feats = table.new_empty(n, levels * width)
         jac = table.new_empty(n, levels * dim * width) if calc_grad_inputs else table.new_empty(1)
         geometry = (n, dim, width, levels, log2_scale, base_resolution)
-        _backend.grid_encode_forward(x, table, offsets, feats, *geometry, calc_grad_inputs, jac, gridtype, _ROW_LAYOUT)
+        _backend.grid_encode_forward(x, table, offsets, feats, *geometry, calc_grad_inputs, jac, gridtype, _ROW_LAYOUT, in_add, in_mul)
         ctx.geometry, ctx.gridtype, ctx.want_dx, ctx.param_dtype = geometry, gridtype, calc_grad_inputs, embeddings.dtype
+        ctx.xf = (in_add, in_mul)
         ctx.save_for_backward(x, table, offsets, jac)
         return feats
 
@@ -93,8 +95,8 @@ class _grid_encode(torch.autograd.Function):
         acc_dtype = table.dtype if _grad_accumulation == 'fp16' else torch.float32
         d_table = torch.zeros(table.shape, dtype=acc_dtype, device=table.device)
         d_x = torch.zeros_like(x, dtype=table.dtype) if ctx.want_dx else table.new_zeros(1)
-        _backend.grid_encode_backward(d_feats, x, table, offsets, d_table, *ctx.geometry, ctx.want_dx, jac, d_x, ctx.gridtype, _ROW_LAYOUT)
-        return (d_x.to(x.dtype) if ctx.want_dx else None, d_table.to(ctx.param_dtype)) + (None,) * 5
+        _backend.grid_encode_backward(d_feats, x, table, offsets, d_table, *ctx.geometry, ctx.want_dx, jac, d_x, ctx.gridtype, _ROW_LAYOUT, *ctx.xf)
+        return (d_x.to(x.dtype) if ctx.want_dx else None, d_table.to(ctx.param_dtype)) + (None,) * 7
 
 
 grid_encode = _grid_encode.apply
@@ -137,6 +139,12 @@ class GridEncoder(nn.Module):
     def forward(self, inputs, bound=1):
         """inputs [..., input_dim] in [-bound, bound]  ->  [..., num_levels * level_dim]"""
         lead = inputs.shape[:-1]
+        if inputs.is_cuda and inputs.dtype == torch.float32 and not inputs.requires_grad and isinstance(bound, (int, float)):
+            # the kernels apply (inputs + bound) / (2 * bound) themselves, in ATen's arithmetic: x = (raw + bound) * fp32(1 / fp32(2 bound))
+            in_mul = float(np.float32(1.0) / np.float32(2 * bound))
+            feats = grid_encode(inputs.reshape(-1, self.input_dim), self.embeddings, self.offsets, self.per_level_scale, self.base_resolution,
+                                False, self.gridtype_id, float(bound), in_mul)
+            return feats.view(*lead, self.output_dim)
         unit = ((inputs + bound) / (2 * bound)).view(-1, self.input_dim)
         feats = grid_encode(unit, self.embeddings, self.offsets, self.per_level_scale, self.base_resolution, unit.requires_grad,
                             self.gridtype_id)

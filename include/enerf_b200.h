@@ -149,6 +149,17 @@ int enerf_grid_encode_backward(const void* grad, const float* inputs, const void
                                uint32_t gridtype, int dtype, int grad_dtype, int out_layout,
                                void* stream);
 
+/* The same two kernels fed with RAW positions: x = (raw + in_add) * in_mul is applied inside (in_mul == 0: none).  GridEncoder.forward's
+ * `(inputs + bound) / (2 * bound)` (gridencoder/grid.py:144) is in_add = bound, in_mul = fp32(1) / fp32(2 * bound) — ATen's operation order
+ * and roundings for that expression, so the features are the same bits — and costs two elementwise passes over the samples less.
+ * calc_grad_inputs must be 0 with a transform. */
+int enerf_grid_encode_forward_xf(const float* raw_inputs, float in_add, float in_mul, const void* embeddings, const int32_t* offsets,
+                                 void* outputs, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+                                 int calc_grad_inputs, void* dy_dx, uint32_t gridtype, int dtype, int out_layout, void* stream);
+int enerf_grid_encode_backward_xf(const void* grad, const float* raw_inputs, float in_add, float in_mul, const void* embeddings,
+                                  const int32_t* offsets, void* grad_embeddings, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S,
+                                  uint32_t H, int calc_grad_inputs, const void* dy_dx, void* grad_inputs, uint32_t gridtype, int dtype,
+                                  int grad_dtype, int out_layout, void* stream);
 /* Scatter strategy of grid_encode_backward (no reference counterpart): 1 (default) = a thread walks
  * 32 consecutive samples of one level and aggregates in registers while they stay in one cell;
  * 0 = one reduction per corner per sample (the reference's strategy).  Same sums either way. */

@@ -306,3 +306,33 @@ def test_sh_module_forward_backward():
     with torch.autocast("cuda", dtype=torch.float16):
         yh = enc(d.detach())
     assert yh.dtype == torch.float16 and torch.allclose(yh.float(), y.detach(), atol=2e-3)
+
+
+@pytest.mark.parametrize("bound", [1, 2, 3, 0.75])
+@pytest.mark.parametrize("autocast", [False, True])
+def test_grid_module_input_mapping_inside_the_kernels_is_bit_identical(bound, autocast):
+    """GridEncoder.forward hands raw positions to the kernels, which apply (x + bound) / (2 * bound) in ATen's arithmetic (a scalar
+    divisor is a multiplication by its fp32 reciprocal): features and table gradient equal, to the bit, those of the explicit
+    ATen expression followed by the [0, 1] kernels — including positions outside [-bound, bound] (zero features, no gradient)"""
+    torch.manual_seed(4)
+    enc = gridencoder.GridEncoder(desired_resolution=2048 * max(1, int(bound))).to(DEV)
+    with torch.no_grad():
+        enc.embeddings.uniform_(-0.5, 0.5)
+    g = torch.Generator(device=DEV).manual_seed(9)
+    x = (torch.rand(20011, 3, device=DEV, generator=g) * 2 - 1) * (bound * 1.02)          # 2 % outside
+    gout = torch.randn(20011, 32, device=DEV, generator=g)
+    res = []
+    for fused in (True, False):
+        enc.embeddings.grad = None
+        with torch.autocast("cuda", dtype=torch.float16, enabled=autocast):
+            if fused:
+                f = enc(x, bound=bound)
+            else:
+                unit = (x + bound) / (2 * bound)
+                f = gridencoder.grid.grid_encode(unit, enc.embeddings, enc.offsets, enc.per_level_scale, enc.base_resolution, False, enc.gridtype_id)
+        (f.float() * gout).sum().backward()
+        res.append((f.detach().clone(), enc.embeddings.grad.clone()))
+    assert torch.equal(res[0][0], res[1][0])
+    assert int((res[0][0].float().abs().sum(dim=1) == 0).sum()) > 100                     # the out-of-range rows
+    scale = float(res[1][1].abs().max())
+    assert float((res[0][1] - res[1][1]).abs().max()) <= 1e-5 * scale                     # same contributions, atomics in another order
