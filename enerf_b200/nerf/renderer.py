@@ -190,7 +190,8 @@ class NeRFRenderer(nn.Module):
                                                                     self.grid_size, nears, fars, counter, self.mean_count, perturb, 128,
                                                                     force_all_rays, dt_gamma, max_steps)
             sigmas, rgbs = self(xyzs, dirs)
-            sigmas = self.density_scale * sigmas
+            if self.density_scale != 1:                      # x * 1 is x: not worth a pass over the samples (renderer.py:309)
+                sigmas = self.density_scale * sigmas
             weights_sum, depth, image = raymarching.composite_rays_train(sigmas, rgbs, deltas, rays)
         else:
             n_ch = None
@@ -234,7 +235,8 @@ class NeRFRenderer(nn.Module):
                                                             self.density_bitfield, self.cascade, self.grid_size, nears, fars, 128, perturb,
                                                             dt_gamma, max_steps, count_dev, occ_bounds)
                 sigmas, rgbs = self(xyzs, dirs)
-                sigmas = self.density_scale * sigmas
+                if self.density_scale != 1:
+                    sigmas = self.density_scale * sigmas
                 if image is None:
                     n_ch = rgbs.shape[-1]
                     image = torch.zeros(N, n_ch, dtype=torch.float32, device=device)

@@ -32,8 +32,8 @@ class FusedAdam(torch.optim.Optimizer):
             raise RuntimeError("FusedAdam does not take a closure")
         grad_scale = getattr(self, "grad_scale", None)
         found_inf = getattr(self, "found_inf", None)
+        work = []
         for group in self.param_groups:
-            b1, b2 = group["betas"]
             for p in group["params"]:
                 if p.grad is None:
                     continue
@@ -58,18 +58,29 @@ class FusedAdam(torch.optim.Optimizer):
                     st["exp_avg_sq"] = torch.zeros_like(pv, memory_format=torch.preserve_format)
                 if st["exp_avg"].numel() != hi - lo:
                     raise RuntimeError("FusedAdam: the shard of a parameter changed after its state was created")
-                # device-side counter: advances only when the step is not skipped (as torch's capturable Adam does)
-                if found_inf is not None:
-                    st["step"] += 1.0 - found_inf.to(st["step"].device).reshape(())
-                else:
-                    st["step"] += 1.0
-                shadow = getattr(p, "_enerf_half", None)
-                if shadow is not None and (shadow[0].shape != p.shape or shadow[0].device != p.device):
-                    shadow = None
-                sh_ptr = ptr(shadow[0].view(-1)[lo:hi]) if shadow is not None else None
                 if g.dtype not in (torch.float32, torch.float16) or g.numel() != hi - lo:
                     raise RuntimeError("FusedAdam: gradient (slice) must be fp32 or fp16 and match the parameter (slice)")
-                _lib.call("enerf_adam_step", ptr(pv), ptr(g), _lib.dtype_code(g), ptr(st["exp_avg"]), ptr(st["exp_avg_sq"]), hi - lo, ptr(st["step"]),
-                          float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
-                          ptr(grad_scale), ptr(found_inf), float(mul), sh_ptr, stream())
+                work.append((group, p, pv, g, st, lo, hi, mul))
+        if not work:
+            return None
+        # device-side counters: they advance only when the step is not skipped (as torch's capturable Adam does); the increment is
+        # formed once per device, not once per parameter
+        incs = {}
+        for w in work:
+            step = w[4]["step"]
+            if found_inf is None:
+                step += 1.0
+                continue
+            if step.device not in incs:
+                incs[step.device] = 1.0 - found_inf.to(step.device).reshape(())
+            step += incs[step.device]
+        for group, p, pv, g, st, lo, hi, mul in work:
+            b1, b2 = group["betas"]
+            shadow = getattr(p, "_enerf_half", None)
+            if shadow is not None and (shadow[0].shape != p.shape or shadow[0].device != p.device):
+                shadow = None
+            sh_ptr = ptr(shadow[0].view(-1)[lo:hi]) if shadow is not None else None
+            _lib.call("enerf_adam_step", ptr(pv), ptr(g), _lib.dtype_code(g), ptr(st["exp_avg"]), ptr(st["exp_avg_sq"]), hi - lo, ptr(st["step"]),
+                      float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
+                      ptr(grad_scale), ptr(found_inf), float(mul), sh_ptr, stream())
         return None
