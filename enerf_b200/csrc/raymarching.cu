@@ -613,6 +613,30 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+static constexpr int kCompositeGroup = 4;       // 32-sample chunks fetched together (one group ahead of the one being composited)
+// one lane's sample of a 32-sample chunk (zeros beyond the ray's last sample)
+template <int NCH>
+struct CompositeChunk {
+    float sigma, d0, d1, c[NCH];
+};
+template <int NCH>
+__device__ __forceinline__ CompositeChunk<NCH> composite_fetch(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                                                               const float* __restrict__ deltas, uint32_t i, uint32_t num_steps) {
+    CompositeChunk<NCH> k;
+    k.sigma = k.d0 = k.d1 = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) k.c[ch] = 0.f;
+    if (i < num_steps) {
+        const float2 dl = *reinterpret_cast<const float2*>(deltas + (size_t)i * 2);
+        k.sigma = sigmas[i];
+        k.d0 = dl.x;
+        k.d1 = dl.y;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) k.c[ch] = rgbs[(size_t)i * NCH + ch];
+    }
+    return k;
+}
+
 // raymarching.cu:500-578.  Warp per ray.
 template <int NCH>
 __global__ void __launch_bounds__(256)
@@ -645,14 +669,15 @@ k_composite_train_fwd(const float* __restrict__ sigmas, const float* __restrict_
     for (int ch = 0; ch < NCH; ++ch) acc_c[ch] = 0.f;
     float acc_d = 0.f, acc_ws = 0.f;
 
-    for (uint32_t base = 0; base < num_steps; base += 32) {
+    // 4096 rays are 28 warps per SM, each a chain of ~25 dependent iterations: the loads of the next kCompositeGroup x 32 samples are
+    // in flight while the scans of the current group run, or every iteration waits for a round trip to memory
+    auto process = [&](const CompositeChunk<NCH>& cur, uint32_t base) {
         const uint32_t i = base + lane;
         const bool valid = i < num_steps;
         float alpha = 0.f, d1 = 0.f;
         if (valid) {
-            const float2 dl = *reinterpret_cast<const float2*>(deltas + (size_t)i * 2);
-            alpha = 1.0f - __expf(-sigmas[i] * dl.x);
-            d1 = dl.y;
+            alpha = 1.0f - __expf(-cur.sigma * cur.d0);
+            d1 = cur.d1;
         }
         const float incl = scan_mul_incl(1.0f - alpha, lane);
         float excl = __shfl_up_sync(kFull, incl, 1);
@@ -662,12 +687,27 @@ k_composite_train_fwd(const float* __restrict__ sigmas, const float* __restrict_
         const float t = t_carry + t_incl;
         if (valid) {
 #pragma unroll
-            for (int ch = 0; ch < NCH; ++ch) acc_c[ch] += w * rgbs[(size_t)i * NCH + ch];
+            for (int ch = 0; ch < NCH; ++ch) acc_c[ch] += w * cur.c[ch];
             acc_d += w * t;
             acc_ws += w;
         }
         T_carry *= __shfl_sync(kFull, incl, 31);
         t_carry += __shfl_sync(kFull, t_incl, 31);
+    };
+    CompositeChunk<NCH> cur[kCompositeGroup], nxt[kCompositeGroup];
+#pragma unroll
+    for (int k = 0; k < kCompositeGroup; ++k) cur[k] = composite_fetch<NCH>(sigmas, rgbs, deltas, 32u * k + lane, num_steps);
+    for (uint32_t gbase = 0; gbase < num_steps; gbase += 32u * kCompositeGroup) {
+        const uint32_t nbase = gbase + 32u * kCompositeGroup;
+        if (nbase < num_steps) {
+#pragma unroll
+            for (int k = 0; k < kCompositeGroup; ++k) nxt[k] = composite_fetch<NCH>(sigmas, rgbs, deltas, nbase + 32u * k + lane, num_steps);
+        }
+#pragma unroll
+        for (int k = 0; k < kCompositeGroup; ++k)
+            if (gbase + 32u * k < num_steps) process(cur[k], gbase + 32u * k);
+#pragma unroll
+        for (int k = 0; k < kCompositeGroup; ++k) cur[k] = nxt[k];
     }
     acc_d = warp_sum(acc_d);
     acc_ws = warp_sum(acc_ws);
@@ -714,7 +754,7 @@ k_composite_train_bwd(const float* __restrict__ grad_weights_sum, const float* _
     const float ws_final = weights_sum[index];
     float pre_ws = 0.f, T_carry = 1.0f;
 
-    for (uint32_t base = 0; base < num_steps; base += 32) {
+    auto process = [&](const CompositeChunk<NCH>& cur, uint32_t base) {
         const uint32_t i = base + lane;
         const bool valid = i < num_steps;
         float alpha = 0.f, d0 = 0.f;
@@ -722,10 +762,10 @@ k_composite_train_bwd(const float* __restrict__ grad_weights_sum, const float* _
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) c[ch] = 0.f;
         if (valid) {
-            d0 = deltas[(size_t)i * 2];
-            alpha = 1.0f - __expf(-sigmas[i] * d0);
+            d0 = cur.d0;
+            alpha = 1.0f - __expf(-cur.sigma * d0);
 #pragma unroll
-            for (int ch = 0; ch < NCH; ++ch) c[ch] = rgbs[(size_t)i * NCH + ch];
+            for (int ch = 0; ch < NCH; ++ch) c[ch] = cur.c[ch];
         }
         const float incl = scan_mul_incl(1.0f - alpha, lane);
         float excl = __shfl_up_sync(kFull, incl, 1);
@@ -745,6 +785,22 @@ k_composite_train_bwd(const float* __restrict__ grad_weights_sum, const float* _
         if (valid) grad_sigmas[i] = d0 * acc;
         pre_ws = __shfl_sync(kFull, ws_incl, 31);
         T_carry *= __shfl_sync(kFull, incl, 31);
+    };
+    // loads one group of chunks ahead, as in the forward kernel
+    CompositeChunk<NCH> cur[kCompositeGroup], nxt[kCompositeGroup];
+#pragma unroll
+    for (int k = 0; k < kCompositeGroup; ++k) cur[k] = composite_fetch<NCH>(sigmas, rgbs, deltas, 32u * k + lane, num_steps);
+    for (uint32_t gbase = 0; gbase < num_steps; gbase += 32u * kCompositeGroup) {
+        const uint32_t nbase = gbase + 32u * kCompositeGroup;
+        if (nbase < num_steps) {
+#pragma unroll
+            for (int k = 0; k < kCompositeGroup; ++k) nxt[k] = composite_fetch<NCH>(sigmas, rgbs, deltas, nbase + 32u * k + lane, num_steps);
+        }
+#pragma unroll
+        for (int k = 0; k < kCompositeGroup; ++k)
+            if (gbase + 32u * k < num_steps) process(cur[k], gbase + 32u * k);
+#pragma unroll
+        for (int k = 0; k < kCompositeGroup; ++k) cur[k] = nxt[k];
     }
 }
 
