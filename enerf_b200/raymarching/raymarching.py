@@ -231,12 +231,13 @@ def finish_rays(weights_sum, depth, image, nears, fars, bg_color):
         scalar = float(bg_color)
     elif torch.is_tensor(bg_color) and not bg_color.requires_grad and bg_color.is_cuda and bg_color.numel() > 0:
         b = bg_color.detach().float()
-        if b.dim() == 0:
+        # shapes that broadcast against [N, n_ch] the way the ATen expression does (the caller views the result as [..., n_ch] anyway)
+        if b.numel() == 1:
             bg = b.reshape(1).expand(n_ch).contiguous()
-        elif b.shape == (n_ch,) or b.shape == (N, n_ch):
-            bg = b.contiguous()
-        elif b.shape == (1, n_ch):
+        elif b.numel() == n_ch and b.shape[-1] == n_ch:
             bg = b.reshape(n_ch).contiguous()
+        elif b.numel() == N * n_ch and b.shape[-1] == n_ch and n_ch > 1 or b.shape == (N, n_ch):
+            bg = b.reshape(N, n_ch).contiguous()
         else:
             fused = False
     else:

@@ -324,7 +324,7 @@ def test_bounded_march_emits_the_samples_of_the_exhaustive_march(case):
         assert torch.equal(xa, xb) and torch.equal(da, db)
 
 
-@pytest.mark.parametrize("n_ch,bg_kind", [(1, "scalar"), (3, "scalar"), (3, "vector"), (3, "per_ray"), (4, "zero_dim")])
+@pytest.mark.parametrize("n_ch,bg_kind", [(1, "scalar"), (3, "scalar"), (3, "vector"), (3, "per_ray"), (4, "zero_dim"), (1, "one_by_one")])
 def test_finish_rays_is_the_aten_expression(n_ch, bg_kind):
     """renderer.py:397-398 as one kernel: forward bit-identical to the ATen expression, gradients to 1e-6"""
     g = torch.Generator(device=DEV).manual_seed(3)
@@ -336,7 +336,7 @@ def test_finish_rays_is_the_aten_expression(n_ch, bg_kind):
     fars = nears + torch.rand(N, device=DEV, generator=g) * 4 + 0.1
     nears[:5] = fars[:5] = 3.4028234663852886e38                       # rays that miss the box: 0 / 0
     bg = {"scalar": 1, "vector": torch.rand(n_ch, device=DEV, generator=g), "per_ray": torch.rand(N, n_ch, device=DEV, generator=g),
-          "zero_dim": torch.tensor(0.25, device=DEV)}[bg_kind]
+          "zero_dim": torch.tensor(0.25, device=DEV), "one_by_one": torch.rand(1, 1, 1, device=DEV, generator=g)}[bg_kind]
     gi, gd = torch.randn(N, n_ch, device=DEV, generator=g), torch.randn(N, device=DEV, generator=g)
     gd[:5] = 0
     outs = []
@@ -347,6 +347,7 @@ def test_finish_rays_is_the_aten_expression(n_ch, bg_kind):
             im, dp = rm.finish_rays(ws, depth, image, nears, fars, bg)
         else:
             im, dp = image + (1 - ws).unsqueeze(-1) * bg, torch.clamp(depth - nears, min=0) / (fars - nears)
+        im = im.reshape(N, n_ch)                                       # a [1, 1, 1] background broadcasts the ATen result to [1, N, n_ch]
         ((im * gi).sum() + (dp[5:] * gd[5:]).sum()).backward()
         outs.append((im.detach(), dp.detach(), ws.grad.clone(), depth.grad.clone(), image.grad.clone()))
     a, b = outs
