@@ -94,7 +94,7 @@ class _grid_encode(torch.autograd.Function):
         d_feats = d_feats.contiguous().to(table.dtype)                 # [B, L*C], read in place by the scatter kernel
         acc_dtype = table.dtype if _grad_accumulation == 'fp16' else torch.float32
         d_table = torch.zeros(table.shape, dtype=acc_dtype, device=table.device)
-        d_x = torch.zeros_like(x, dtype=table.dtype) if ctx.want_dx else table.new_zeros(1)
+        d_x = torch.zeros_like(x, dtype=table.dtype) if ctx.want_dx else table.new_empty(1)
         _backend.grid_encode_backward(d_feats, x, table, offsets, d_table, *ctx.geometry, ctx.want_dx, jac, d_x, ctx.gridtype, _ROW_LAYOUT, *ctx.xf)
         return (d_x.to(x.dtype) if ctx.want_dx else None, d_table.to(ctx.param_dtype)) + (None,) * 7
 
