@@ -37,11 +37,20 @@ sys.path.insert(0, ROOT)
 
 METRIC, UNIT = "train_rays_per_sec", "rays/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this workload (bytes)
-NCU_TRAFFIC_SRC = "profiles/r2_18_ncu_full_step_kernels.md (3.29 M samples/launch)"
-NCU_TRAFFIC = {"grid_encode_backward": 292.509440e6 + 5.846272e6, "grid_encode_forward": 62.280448e6 + 168.950016e6,
-               "march_rays_train": 0.846336e6 + 47.198976e6, "field_color_backward": 237.653248e6 + 166.174976e6,
-               "field_sigma_backward": 448.646144e6 + 182.492672e6, "field_sigma_forward": 250.628608e6 + 181.403392e6,
-               "field_color_forward": 211.133440e6 + 12.515328e6}
+NCU_TRAFFIC_SRC = "profiles/r2_31_ncu_full_step_kernels.md (3.29 M samples/launch)"
+NCU_TRAFFIC = {"grid_encode_backward": 293.150464e6 + 7.339264e6, "grid_encode_forward": 62.499584e6 + 167.187968e6,
+               "march_rays_train": 0.845824e6 + 46.140672e6, "field_color_backward": 237.678336e6 + 166.362368e6,
+               "field_sigma_backward": 448.601088e6 + 181.534464e6, "field_sigma_forward": 250.629888e6 + 180.148224e6,
+               "field_color_forward": 211.100672e6 + 11.883008e6}
+
+
+def canon(name):
+    """C-ABI entry point -> the name its roofline is booked under: `_xf` (positions mapped inside the hash-grid kernels) and `_bounded`
+    (march limited to the occupied box) are the same kernels called with extra arguments"""
+    for suffix in ("_xf", "_bounded"):
+        if name.endswith(suffix):
+            name = name[:-len(suffix)]
+    return name
 RAYS = 4096
 BOUND = 3
 N_BATCHES = 8            # distinct ray batches cycled through the timed region
@@ -539,6 +548,7 @@ def run_variant_bench(args, dev, K, peaks):
             "enerf_field_density_forward": ("tensor", 2.0 * (32 * 64 + 64 * 16) * S), "enerf_field_density_backward": ("tensor", 4.0 * (32 * 64 + 64 * 16) * S)}
     kernels = {}
     for name, (calls, tot_ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+        name = canon(name)
         e = {"ms_per_step": tot_ms / P, "calls_per_step": calls / P}
         if name in work and tot_ms > 0:
             bound_, amount = work[name]
@@ -694,6 +704,7 @@ def our_arm(args):
     }
     kernels = {}
     for name, (calls, tot_ms) in prof.items():
+        name = canon(name)
         per_step_ms = tot_ms / P
         entry = {"ms_per_step": per_step_ms, "calls_per_step": calls / P}
         if name in work and per_step_ms > 0:
