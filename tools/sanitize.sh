@@ -6,7 +6,7 @@
 tag=${1:-san}
 out=gpurun_out
 mkdir -p $out
-SEL='test_forward_inference_backward_vs_oracle and (1024 or 256-16) or test_density_head_matches_linear_chain and 128] or test_masked_color_matches_module_chain and 1-0.3 or test_grid_forward_hoisted_kernel_is_bit_identical_to_generic or test_near_far_bit_exact or test_march_rays_train_mean_count_overflow_drops_rays or test_inference_loop_primitives_match_oracle or test_density_grid_maintenance or test_composite_train or test_ordered_compaction_matches_nonzero and (4097 or 16]) or test_weighted_sum_and_row_moves or test_fused_field_matches_module_chain or test_sh_'
+SEL='test_forward_inference_backward_vs_oracle and (1024 or 256-16) or test_density_head_matches_linear_chain and 128] or test_masked_color_matches_module_chain and 1-0.3 or test_grid_forward_hoisted_kernel_is_bit_identical_to_generic or test_near_far_bit_exact or test_march_rays_train_mean_count_overflow_drops_rays or test_inference_loop_primitives_match_oracle or test_density_grid_maintenance or test_composite_train or test_ordered_compaction_matches_nonzero and (4097 or 16]) or test_weighted_sum_and_row_moves or test_fused_field_matches_module_chain or test_sh_ or test_bounded_march_emits_the_samples_of_the_exhaustive_march and (corner or sparse) or test_finish_rays_is_the_aten_expression and per_ray or test_grid_module_input_mapping_inside_the_kernels_is_bit_identical and 0.75'
 export ENERF_SANITIZER=1
 for tool in memcheck racecheck synccheck; do
   extra=""
