@@ -37,11 +37,11 @@ sys.path.insert(0, ROOT)
 
 METRIC, UNIT = "train_rays_per_sec", "rays/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this workload (bytes)
-NCU_TRAFFIC_SRC = "profiles/r2_31_ncu_full_step_kernels.md (3.29 M samples/launch)"
-NCU_TRAFFIC = {"grid_encode_backward": 293.150464e6 + 7.339264e6, "grid_encode_forward": 62.499584e6 + 167.187968e6,
-               "march_rays_train": 0.845824e6 + 46.140672e6, "field_color_backward": 237.678336e6 + 166.362368e6,
-               "field_sigma_backward": 448.601088e6 + 181.534464e6, "field_sigma_forward": 250.629888e6 + 180.148224e6,
-               "field_color_forward": 211.100672e6 + 11.883008e6}
+NCU_TRAFFIC_SRC = "profiles/r2_43_ncu_full_step_kernels.md (3.29 M samples/launch)"
+NCU_TRAFFIC = {"grid_encode_backward": 292.828672e6 + 6.303488e6, "grid_encode_forward": 62.323968e6 + 167.823360e6,
+               "march_rays_train": 0.622848e6 + 46.673664e6, "field_color_backward": 237.623808e6 + 168.468224e6,
+               "field_sigma_backward": 448.601344e6 + 182.442240e6, "field_sigma_forward": 250.630144e6 + 180.914176e6,
+               "field_color_forward": 211.083008e6 + 12.192256e6}
 
 
 def canon(name):
