@@ -49,8 +49,8 @@ class _Raymarching:
     @staticmethod
     def occupancy_bounds(grid, C, H):
         """extension: int32 [C, 6] box around the occupied cells of each cascade level, or None when H is not a power of two >= 4"""
-        if H < 4 or H & (H - 1):
-            return None
+        if H < 4 or H & (H - 1) or grid.data_ptr() % 16 or grid.numel() * 8 < C * H ** 3:
+            return None                                   # the marcher then probes every candidate, as the reference does
         need_cuda(grid)
         bounds = torch.empty(C, 6, dtype=torch.int32, device=grid.device)
         _lib.call("enerf_occupancy_bounds", ptr(grid), C, H, ptr(bounds), stream())
