@@ -76,13 +76,15 @@ def measure(n_rays=4096, iters=5, bound=3, out_path="", verbose=False):
 
     def march_ours():
         counter.zero_()
-        RB.march_rays_train(o, d, bits, float(bound), 0.0, 1024, N, cascade, 128, M, nears, fars, bx, bd, bdl, br, counter, 1)
+        # as the product calls it (raymarching.march_rays_train): the box around the occupied cells, then the bounded march
+        RB.march_rays_train(o, d, bits, float(bound), 0.0, 1024, N, cascade, 128, M, nears, fars, bx, bd, bdl, br, counter, 1,
+                            RB.occupancy_bounds(bits, cascade, 128))
 
     def march_ref():
         counter.zero_()
         R.march_rays_train(o, d, bits, float(bound), 0.0, 1024, N, cascade, 128, M, nears, fars, bx, bd, bdl, br, counter, 1)
 
-    row("march_rays_train", march_ours, march_ref if R else None)
+    row("march_rays_train", march_ours, march_ref if R else None, "ours: enerf_occupancy_bounds + enerf_march_rays_train_bounded (same samples, bit for bit)")
 
     # ---------------- compositing (K6/K7), 3 channels as in the reference
     sig = torch.rand(M, device=dev) * 20
