@@ -354,3 +354,41 @@ def test_finish_rays_is_the_aten_expression(n_ch, bg_kind):
     assert torch.equal(a[0], b[0]) and torch.equal(a[1][5:], b[1][5:]) and bool(torch.isnan(a[1][:5]).all()) and bool(torch.isnan(b[1][:5]).all())
     assert float((a[2] - b[2]).abs().max()) <= 1e-5 and torch.equal(a[4], b[4])
     assert float((a[3][5:] - b[3][5:]).abs().max()) <= 1e-6 * float(b[3][5:].abs().max())
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_bounded_march_on_random_grids(seed):
+    """random occupancy (salt of density 1e-5 .. 0.5, or one compact blob), bounds 1 / 2 / 3 / 0.75, rays that start anywhere in or around
+    the volume, some axis-parallel, jitter on and off, constant and growing steps: per ray the same sample count, positions and deltas"""
+    from enerf_b200.backends import raymarching_backend as RB
+    H, N = 128, 3000
+    rng = np.random.default_rng(seed)
+    bound = [1, 2, 3, 0.75][seed % 4]
+    C = 1 + int(np.ceil(np.log2(bound))) if bound > 1 else 1
+    grid = (rng.random((C, H ** 3)) < 10 ** rng.uniform(-5, -0.3)).astype(np.float32)
+    if seed % 5 == 0:
+        grid[:] = 0
+        c0 = rng.integers(10, 100, 3)
+        idx = np.stack(np.meshgrid(*[np.arange(c0[k], c0[k] + rng.integers(1, 20)) for k in range(3)], indexing="ij"), -1).reshape(-1, 3).astype(np.int32)
+        grid[rng.integers(0, C), oracle.morton3D(idx)] = 1
+    bits = t(oracle.packbits(grid, 0.5))
+    o = rng.uniform(-bound * 1.2, bound * 1.2, (N, 3)).astype(np.float32)
+    d = rng.normal(size=(N, 3)).astype(np.float32)
+    d[:20, rng.integers(0, 3)] = 0
+    d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    o, d = t(o), t(d)
+    nears, fars = rm.near_far_from_aabb(o, d, t(np.array([-bound] * 3 + [bound] * 3, np.float32)), 0.05)
+    dt_gamma, perturb = (0.0 if seed % 3 else 1.0 / 256), seed % 2
+    bounds = RB.occupancy_bounds(bits, C, H)
+    M, outs = N * 1024, []
+    for ob in (None, bounds):
+        xyzs, dirs, deltas = (torch.zeros(M, k, device=DEV) for k in (3, 3, 2))
+        rays = torch.empty(N, 3, dtype=torch.int32, device=DEV)
+        counter = torch.zeros(2, dtype=torch.int32, device=DEV)
+        RB.march_rays_train(o, d, bits, float(bound), dt_gamma, 1024, N, C, H, M, nears, fars, xyzs, dirs, deltas, rays, counter, perturb, ob)
+        r = rays[torch.argsort(rays[:, 0])]
+        total = int(counter[0])
+        starts = torch.cumsum(r[:, 2], 0) - r[:, 2]
+        src = torch.repeat_interleave(r[:, 1].long() - starts.long(), r[:, 2].long()) + torch.arange(total, device=DEV)      # ray-ordered rows
+        outs.append((r[:, 2].clone(), xyzs[src].clone(), deltas[src].clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
