@@ -271,5 +271,37 @@ __device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
     if (lane == 0) mbar_arrive(bar);
 }
 
+// ---- pieces shared by the fused-MLP kernels (ffmlp_tc.cu) and the fused inference field (field_infer.cu) ----
+// copy a row-major [rows, K] fp16 matrix into the canonical chunked layout tile[c][r] (16-B chunks)
+__device__ __forceinline__ void stage_matrix(uint8_t* dst, const __half* __restrict__ src, int rows, int K, int tid, int nthreads) {
+    const int cpr = K >> 3;   // chunks per row
+    for (int i = tid; i < rows * cpr; i += nthreads) {
+        const int r = i / cpr, c = i - r * cpr;
+        *reinterpret_cast<int4*>(dst + (size_t)c * rows * 16 + (size_t)r * 16) = __ldg(reinterpret_cast<const int4*>(src) + i);
+    }
+}
+
+// real spherical harmonics up to l = 3 of (x,y,z) — the basis of shencoder.cu:51-69, fp32
+__device__ __forceinline__ void sh_deg4(float x, float y, float z, float (&o)[16]) {
+    const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+    o[0] = 0.28209479177387814f;                         // 1/(2 sqrt(pi))
+    o[1] = -0.48860251190291987f * y;                    // sqrt(3/(4 pi))
+    o[2] = 0.48860251190291987f * z;
+    o[3] = -0.48860251190291987f * x;
+    o[4] = 1.0925484305920792f * xy;                     // sqrt(15/(4 pi))
+    o[5] = -1.0925484305920792f * yz;
+    o[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;   // sqrt(5/(16 pi)) (3 z^2 - 1)
+    o[7] = -1.0925484305920792f * xz;
+    o[8] = 0.54627421529603959f * (x2 - y2);             // sqrt(15/(16 pi))
+    o[9] = 0.59004358992664352f * y * (y2 - 3.0f * x2);  // sqrt(35/(32 pi))
+    o[10] = 2.8906114426405538f * xy * z;                // sqrt(105/(4 pi))
+    o[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2);   // sqrt(21/(32 pi))
+    o[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);    // sqrt(7/(16 pi))
+    o[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
+    o[14] = 1.4453057213202769f * z * (x2 - y2);         // sqrt(105/(16 pi))
+    o[15] = 0.59004358992664352f * x * (3.0f * y2 - x2);
+}
+__device__ __forceinline__ float f16_round(float v) { return __half2float(__float2half_rn(v)); }
+
 }  // namespace tc
 }  // namespace enerf

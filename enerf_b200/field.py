@@ -77,6 +77,37 @@ def fused_field(feat, dirs, w_sigma, w_color, nl_sigma, nl_color, n_ch, training
 
 
 # --------------------------------------------------------------------------------------------
+# Inference (torch.no_grad): encoder + both nets as ONE kernel (csrc/field_infer.cu).  The [S,32] feature rows and the [S,32]
+# colour-net input rows never reach HBM; sigma and rgb are the bits `encoder -> fused_field` produces.
+def infer_eligible(x, dirs, encoder, *shape_args):
+    """raw positions [S,3] fp32, directions [S,3], a hash / tiled GridEncoder of 16 levels x 2 features over 3-D inputs, FFMLP 2 + 3 layers"""
+    from .gridencoder.grid import GridEncoder
+    return (isinstance(encoder, GridEncoder) and encoder.input_dim == 3 and encoder.num_levels == 16 and encoder.level_dim == 2
+            and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.shape[1] == 3 and dirs.shape == x.shape
+            and shapes_eligible(*shape_args))
+
+
+@torch.no_grad()
+def fused_infer(x, dirs, encoder, bound, w_sigma, w_color, n_ch):
+    """x [S,3] in [-bound, bound], dirs [S,3] -> (sigma [S] fp32, rgb [S,n_ch] fp32); no autograd graph."""
+    import numpy as np
+    from .gridencoder.grid import _half_table
+    S = x.shape[0]
+    dev = x.device
+    x = x.contiguous()
+    dirs = dirs.contiguous().float()
+    table = encoder.embeddings if encoder.embeddings.dtype == torch.float16 else _half_table(encoder.embeddings)
+    ws, wc = w_sigma.detach().half().contiguous(), w_color.detach().half().contiguous()
+    sigma = torch.empty(S, dtype=torch.float32, device=dev)
+    rgb = torch.empty(S, n_ch, dtype=torch.float32, device=dev)
+    in_mul = float(np.float32(1.0) / np.float32(2 * bound))          # GridEncoder.forward's (x + bound) / (2 bound) in ATen's arithmetic
+    _lib.call("enerf_field_infer", ptr(x), float(bound), in_mul, ptr(dirs), ptr(table), ptr(encoder.offsets), encoder.num_levels, encoder.level_dim,
+              float(np.log2(encoder.per_level_scale)), int(encoder.base_resolution), int(encoder.gridtype_id), ptr(ws), 2, ptr(wc), 3, S, n_ch,
+              ptr(sigma), ptr(rgb), stream())
+    return sigma, rgb
+
+
+# --------------------------------------------------------------------------------------------
 # The torch-topology field of nerf/network.py:104-199 — what every shipped E-NeRF config runs (ff = False): sigma-net
 # Linear(32,64)-ReLU-Linear(64,16), colour-net Linear(31,64)-ReLU-Linear(64,64)-ReLU-Linear(64,C) on the `weights > 1e-4` samples.
 # Same tcgen05 kernels as the FFMLP path (one hidden-to-hidden matmul fewer per net); the weights are the nn.Linear matrices

@@ -24,6 +24,7 @@ class NeRFNetwork(NeRFRenderer):
         self.out_dim_color = out_dim_color
         self.disable_view_direction = disable_view_direction
         self.fuse_field = True      # fused sigma/colour heads (enerf_b200.field) when shapes allow; False = module chain
+        self.fuse_infer = True      # under torch.no_grad additionally: encoder + both nets as one kernel (field.fused_infer)
         self.encoder, self.in_dim = get_encoder(encoding, desired_resolution=2048 * bound)
         self.sigma_net = FFMLP(input_dim=self.in_dim, output_dim=1 + self.geo_feat_dim, hidden_dim=self.hidden_dim, num_layers=self.num_layers)
 
@@ -52,6 +53,10 @@ class NeRFNetwork(NeRFRenderer):
             shapes = (self.hidden_dim, self.hidden_dim_color, self.in_dim, self.in_dim_color, self.geo_feat_dim,
                       getattr(self.encoder_dir, 'degree', -1), self.out_dim_color, self.sigma_net.activation)
             training = self.training and torch.is_grad_enabled()
+            if (self.fuse_infer and not torch.is_grad_enabled() and self.num_layers == 2 and self.num_layers_color == 3
+                    and isinstance(self.bound, (int, float)) and field.infer_eligible(x, d, self.encoder, *shapes)):
+                # rendering: gather + sigma-net + colour-net in one kernel, features and colour-net inputs stay on the SM
+                return field.fused_infer(x, d, self.encoder, self.bound, self.sigma_net.weights, self.color_net.weights, self.out_dim_color)
             feat = self.encoder(x, bound=self.bound)
             if field.eligible(feat, d, *shapes):
                 return field.fused_field(feat, d, self.sigma_net.weights, self.color_net.weights, self.num_layers, self.num_layers_color,

@@ -260,6 +260,20 @@ int enerf_field_sigma_backward(const float* grad_sigma, const float* sigma, cons
                                void* stream);
 
 
+/* The same field under torch.no_grad as ONE kernel (no reference counterpart as a single call): hash-grid gather -> sigma-net ->
+ * trunc_exp / SH / colour-net input -> colour-net -> sigmoid, i.e. the chain gridencoder.h:12 grid_encode_forward -> ffmlp.h:13
+ * ffmlp_inference -> nerf/network_ff.py:58-73 -> ffmlp_inference that NeRFRenderer.run_cuda's inference loop (nerf/renderer.py:380-381)
+ * runs once per marching round.  Features and colour-net inputs stay in shared memory; sigma [B] fp32 and rgb [B, n_ch] fp32 are the
+ * bits the unfused calls produce.  raw_xyz [B,3] fp32 with x = (raw + in_add) * in_mul applied inside (in_mul == 0: already in [0,1]),
+ * dirs [B,3] fp32, embeddings: the fp16 table [entries, C]; L = 16, C = 2, D = 3, num_layers = 2, num_layers_color = 3 (E-NeRF's
+ * field) — other shapes are refused (-2) and take the unfused chain.  B is arbitrary (no multiple-of-128 rule). */
+int enerf_field_infer(const float* raw_xyz, float in_add, float in_mul, const float* dirs, const uint16_t* embeddings,
+                      const int32_t* offsets, uint32_t L, uint32_t C, float S, uint32_t H, uint32_t gridtype,
+                      const uint16_t* w_sigma, uint32_t num_layers, const uint16_t* w_color, uint32_t num_layers_color,
+                      uint32_t B, uint32_t n_ch, float* sigma, float* rgb, void* stream);
+/* Which (MLP slots, gather teams) instantiation enerf_field_infer launches (tools/field_infer_probe.py): 0 = default. */
+int enerf_field_infer_set_variant(int variant);
+
 /* The torch-topology field of nerf/network.py:104-199 (what every shipped E-NeRF config runs: sigma-net Linear(32,64)-ReLU-
  * Linear(64,16), colour-net Linear(31,64)-ReLU-Linear(64,64)-ReLU-Linear(64,C), no bias) on the same tcgen05 kernels.
  * Weights are the nn.Linear matrices ([out,in] row-major) concatenated in FFMLP order, the colour-net's first matrix padded with a
