@@ -30,32 +30,67 @@ static constexpr uint32_t kXBytes = kTile * 32 * 2;     // one [128 x 32] fp16 t
 static constexpr uint32_t kWBytes = 4096 + 8192 + 2048 + 4096 + 2 * 8192 + 2048;      // both nets, canonical layout
 
 // ---- one sample's 16 levels -> its 64-byte feature row in a 64-byte-swizzled tile (the layer-0 A operand) ----
-// Levels [0, ND) use the dense index form, the others the hashed power-of-two form (compile-time per unrolled level).  Two pairs of
-// levels are live at any time: the 16 corner loads of pair p+1 are issued before pair p is blended, so a warp keeps 16-32 independent
-// 4-byte gathers in flight while it computes — the dedicated gather kernel gets that overlap from 48 resident warps per SM, here
-// there are 8-16.  Four levels (two pairs) make one 16-byte chunk of the row.
-template <int ND>
+// The eight corner values of one (sample, level) between their loads and the blend: 8 registers (fp16 pairs as loaded).  The
+// interpolation weights are recomputed from the position at blend time — nine cheap instructions instead of six live registers per
+// level in flight, which is what lets a thread keep three pairs of levels (48 loads) outstanding.  Same operations in the same order
+// as LevelWork (grid_levels.cuh): bit-identical features.
+struct LevelLite {
+    uint32_t v[8];
+    template <int MODE>
+    __device__ __forceinline__ void fetch(const LevelTabW& lt, const __half* __restrict__ grid, const float (&x)[3]) {
+        const __half* __restrict__ tab = grid + (size_t)lt.offset * 2;
+        uint32_t pg[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) pg[d] = (uint32_t)floorf(__fmaf_rn(x[d], lt.scale, 0.5f));
+        uint32_t e[8];
+        corner_index<2, MODE>(lt, pg, e);
+#pragma unroll
+        for (int idx = 0; idx < 8; ++idx) v[idx] = __ldg(reinterpret_cast<const uint32_t*>(tab + e[idx]));
+    }
+    __device__ __forceinline__ uint32_t blend(const LevelTabW& lt, const float (&x)[3], bool zero) const {
+        float fr[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const float p = __fmaf_rn(x[d], lt.scale, 0.5f);
+            fr[d] = p - floorf(p);
+        }
+        const float wx0 = 1.0f - fr[0], wy0 = 1.0f - fr[1];
+        const float wxy[4] = {wx0 * wy0, fr[0] * wy0, wx0 * fr[1], fr[0] * fr[1]};
+        const float wz[2] = {1.0f - fr[2], fr[2]};
+        __half2 res2 = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+        for (int idx = 0; idx < 8; ++idx) {
+            const float w = wxy[idx & 3] * wz[idx >> 2];
+            const float2 g = __half22float2(*reinterpret_cast<const __half2*>(&v[idx]));
+            res2 = __hadd2(res2, __floats2half2_rn(w * g.x, w * g.y));
+        }
+        return zero ? 0u : *reinterpret_cast<const uint32_t*>(&res2);
+    }
+};
+
+// Levels [0, ND) use the dense index form, the others the hashed power-of-two form (compile-time per unrolled level).  PD pairs of
+// levels are live at any time: the 16 corner loads of pair p+PD-1 are issued before pair p is blended, so a warp keeps up to 16*PD
+// independent 4-byte gathers in flight while it computes — the dedicated gather kernel gets that overlap from 48 resident warps per
+// SM, here there are 16-20.  Four levels (two pairs) make one 16-byte chunk of the row.
+template <int ND, int PD>
 __device__ __forceinline__ void gather_row(const LevelTabW* ltab, const __half* __restrict__ grid, const float (&x)[3], bool oob, uint8_t* xb, uint32_t r) {
-    LevelWork<__half, 2> w[2][2];
+    LevelLite w[PD][2];
     auto fetch_pair = [&](int p) {
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
             const int level = 2 * p + i;
-            if (level < ND) w[p & 1][i].template fetch<1>(ltab[level], grid, x);
-            else w[p & 1][i].template fetch<0>(ltab[level], grid, x);
+            if (level < ND) w[p % PD][i].template fetch<1>(ltab[level], grid, x);
+            else w[p % PD][i].template fetch<0>(ltab[level], grid, x);
         }
     };
-    fetch_pair(0);
+#pragma unroll
+    for (int p = 0; p < PD - 1; ++p) fetch_pair(p);
     uint32_t o[4];
 #pragma unroll
     for (int p = 0; p < kLevels / 2; ++p) {
-        if (p + 1 < kLevels / 2) fetch_pair(p + 1);
+        if (p + PD - 1 < kLevels / 2) fetch_pair(p + PD - 1);
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            uint32_t ow[1];
-            w[p & 1][i].blend(ow, oob);
-            o[(2 * p + i) & 3] = ow[0];
-        }
+        for (int i = 0; i < 2; ++i) o[(2 * p + i) & 3] = w[p % PD][i].blend(ltab[2 * p + i], x, oob);
         if (p & 1) *reinterpret_cast<int4*>(xb + sw_off(r, (uint32_t)(p >> 1), 64)) = make_int4((int)o[0], (int)o[1], (int)o[2], (int)o[3]);
     }
 }
@@ -84,7 +119,7 @@ __device__ __forceinline__ void gather_row_generic(const LevelTabW* ltab, const 
 
 // NSLOTS tiles in flight in the MLP part, NGT gather teams of four warps, NX feature tiles in the ring (a multiple of NGT, so a ring
 // buffer is always filled by the same team and the parity of its "empty" barrier cannot be overrun)
-template <int NSLOTS, int NGT, int NX>
+template <int NSLOTS, int NGT, int NX, int PD>
 __global__ void __launch_bounds__(32 + NSLOTS * 128 + NGT * 128, 1)
 k_field_infer(const Inputs inputs, const float* __restrict__ dirs, const __half* __restrict__ grid, const int32_t* __restrict__ offsets, float S,
               uint32_t H, uint32_t gridtype, const __half* __restrict__ Ws, const __half* __restrict__ Wc, float* __restrict__ sigma,
@@ -162,8 +197,8 @@ k_field_infer(const Inputs inputs, const float* __restrict__ dirs, const __half*
                     if (t == 0) {
                         // ---- sigma-net layer 0: A = the gathered feature tile
                         const uint32_t j = tl * NSLOTS + (uint32_t)s, xbuf = j % NX, use = j / NX;
-                        if (tl > 0) mbar_wait(&a_ready[s], (ph - 1u) & 1u);      // the previous tile's last accumulator has been read
-                        mbar_wait(&x_full[xbuf], use & 1u);
+                        if (tl > 0) mbar_wait_sleep(&a_ready[s], (ph - 1u) & 1u);      // the previous tile's last accumulator has been read
+                        mbar_wait_sleep(&x_full[xbuf], use & 1u);
                         tc_fence_after();
                         if (elect_one()) {
                             const uint32_t xb = xr_b + xbuf * kXBytes;
@@ -174,7 +209,7 @@ k_field_infer(const Inputs inputs, const float* __restrict__ dirs, const __half*
                         }
                         __syncwarp();
                     } else {
-                        mbar_wait(&a_ready[s], (ph + (uint32_t)(t - 1)) & 1u);
+                        mbar_wait_sleep(&a_ready[s], (ph + (uint32_t)(t - 1)) & 1u);
                         tc_fence_after();
                         if (elect_one()) {
                             if (t == 3) {
@@ -219,7 +254,7 @@ k_field_infer(const Inputs inputs, const float* __restrict__ dirs, const __half*
             const uint32_t ph = tl * kStages;
 #pragma unroll
             for (int k = 0; k < kStages; ++k) {
-                mbar_wait(&d_full[s], (ph + (uint32_t)k) & 1u);
+                mbar_wait_sleep(&d_full[s], (ph + (uint32_t)k) & 1u);
                 tc_fence_after();
                 if (k == 2) {
                     // ---- sigma head: sigma = exp(fp16(y[0])) (trunc_exp), colour-net input row [SH_4(fp16(dir)) | y[1:16] | 0] -> shared memory
@@ -273,15 +308,17 @@ k_field_infer(const Inputs inputs, const float* __restrict__ dirs, const __half*
                             tmem_st16(a_t + h * 16, p);
                         }
                     } else {
+                        // 64 registers per thread with 29 warps: the row goes through in four 16-column pieces (the kernel is bound by the
+                        // gather, not by this chain)
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            uint32_t acc[32];
-                            tmem_ld32(d_t + h * 32, acc);
+                        for (int h = 0; h < 4; ++h) {
+                            uint32_t acc[16];
+                            tmem_ld16(d_t + h * 16, acc);
                             tc_wait_ld();
-                            uint32_t p[16];
+                            uint32_t p[8];
 #pragma unroll
-                            for (int e = 0; e < 16; ++e) p[e] = pack2_relu(__uint_as_float(acc[2 * e]), __uint_as_float(acc[2 * e + 1]));
-                            tmem_st16(a_t + h * 16, p);
+                            for (int e = 0; e < 8; ++e) p[e] = pack2_relu(__uint_as_float(acc[2 * e]), __uint_as_float(acc[2 * e + 1]));
+                            tmem_st8(a_t + h * 8, p);
                         }
                     }
                     tc_wait_st();
@@ -302,15 +339,15 @@ k_field_infer(const Inputs inputs, const float* __restrict__ dirs, const __half*
             bool oob = true;
             if (row < (size_t)B) oob = load_pos<3>(inputs, (uint32_t)row, x);
             if (oob) x[0] = x[1] = x[2] = 0.f;         // keep the address arithmetic in range; the result is zeroed below
-            if (use > 0) mbar_wait(&x_empty[xbuf], (use - 1u) & 1u);      // the layer-0 MMAs of the buffer's previous tile have read it
+            if (use > 0) mbar_wait_sleep(&x_empty[xbuf], (use - 1u) & 1u);      // the layer-0 MMAs of the buffer's previous tile have read it
             uint8_t* xb = xring + (size_t)xbuf * kXBytes;
             // the usual table is "n_dense dense levels, then hashed power-of-two levels": the level loop is then fully unrolled with
             // compile-time index forms and software-pipelined by pairs of levels (below); anything else walks the levels with a
             // (warp-uniform) branch per level
             switch (plan_nd) {
-                case 4: gather_row<4>(ltab, grid, x, oob, xb, r); break;
-                case 5: gather_row<5>(ltab, grid, x, oob, xb, r); break;
-                case 6: gather_row<6>(ltab, grid, x, oob, xb, r); break;
+                case 4: gather_row<4, PD>(ltab, grid, x, oob, xb, r); break;
+                case 5: gather_row<5, PD>(ltab, grid, x, oob, xb, r); break;
+                case 6: gather_row<6, PD>(ltab, grid, x, oob, xb, r); break;
                 default: gather_row_generic(ltab, grid, x, oob, xb, r); break;
             }
             fence_proxy_async_smem();
@@ -322,21 +359,19 @@ k_field_infer(const Inputs inputs, const float* __restrict__ dirs, const __half*
     if (warp == 0) tmem_dealloc(tmem0, kCols);
 }
 
-static int g_variant = 0;      // tools/field_infer_probe.py: which (slots, gather teams) instantiation runs; 0 = the default
-
-template <int NSLOTS, int NGT, int NX>
+template <int NSLOTS, int NGT, int NX, int PD>
 static int launch(const Inputs& in, const float* dirs, const __half* grid, const int32_t* offsets, float S, uint32_t H, uint32_t gridtype, const __half* Ws,
                   const __half* Wc, float* sigma, float* rgb, int n_ch, uint32_t B, cudaStream_t st) {
     size_t smem = 1024 + (size_t)(NX + NSLOTS) * kXBytes + kWBytes + (size_t)(2 * NSLOTS + 2 * NX) * 8 + 16;
     if (smem < 120 * 1024) smem = 120 * 1024;      // one CTA per SM: it owns the SM's tensor memory
     static bool configured = false;
     if (!configured) {
-        ENERF_CUDA(cudaFuncSetAttribute(k_field_infer<NSLOTS, NGT, NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "field_infer");
+        ENERF_CUDA(cudaFuncSetAttribute(k_field_infer<NSLOTS, NGT, NX, PD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "field_infer");
         configured = true;
     }
     const uint32_t n_tiles = ceil_div(B, (uint32_t)kTile);
     const uint32_t grid_x = n_tiles < (uint32_t)num_sms() ? n_tiles : (uint32_t)num_sms();
-    k_field_infer<NSLOTS, NGT, NX><<<grid_x, 32 + NSLOTS * 128 + NGT * 128, smem, st>>>(in, dirs, grid, offsets, S, H, gridtype, Ws, Wc, sigma, rgb, n_ch, B, n_tiles);
+    k_field_infer<NSLOTS, NGT, NX, PD><<<grid_x, 32 + NSLOTS * 128 + NGT * 128, smem, st>>>(in, dirs, grid, offsets, S, H, gridtype, Ws, Wc, sigma, rgb, n_ch, B, n_tiles);
     ENERF_CHECK_LAUNCH("field_infer");
     return 0;
 }
@@ -345,12 +380,6 @@ static int launch(const Inputs& in, const float* dirs, const __half* grid, const
 }  // namespace enerf
 
 using namespace enerf;
-
-extern "C" int enerf_field_infer_set_variant(int v) {
-    ENERF_REQUIRE(v >= 0 && v <= 3, "field_infer_set_variant", "variant must be in [0,3]");
-    fi::g_variant = v;
-    return 0;
-}
 
 extern "C" int enerf_field_infer(const float* raw_xyz, float in_add, float in_mul, const float* dirs, const uint16_t* embeddings, const int32_t* offsets,
                                  uint32_t L, uint32_t C, float S, uint32_t H, uint32_t gridtype, const uint16_t* w_sigma, uint32_t num_layers,
@@ -366,10 +395,10 @@ extern "C" int enerf_field_infer(const float* raw_xyz, float in_add, float in_mu
     const __half* Ws = reinterpret_cast<const __half*>(w_sigma);
     const __half* Wc = reinterpret_cast<const __half*>(w_color);
     cudaStream_t st = as_stream(stream);
-    switch (fi::g_variant) {
-        case 1: return fi::launch<3, 3, 6>(in, dirs, grid, offsets, S, H, gridtype, Ws, Wc, sigma, rgb, (int)n_ch, B, st);
-        case 2: return fi::launch<2, 4, 8>(in, dirs, grid, offsets, S, H, gridtype, Ws, Wc, sigma, rgb, (int)n_ch, B, st);
-        case 3: return fi::launch<3, 4, 8>(in, dirs, grid, offsets, S, H, gridtype, Ws, Wc, sigma, rgb, (int)n_ch, B, st);
-        default: return fi::launch<3, 2, 4>(in, dirs, grid, offsets, S, H, gridtype, Ws, Wc, sigma, rgb, (int)n_ch, B, st);
-    }
+    // Measured on B200 (3.29 M marcher-ordered samples; the unfused chain: 0.556 ms): 2 MLP slots + 4 gather teams, three pairs of levels
+    // in flight per thread 0.511 ms; 3 slots + 4 teams 0.515 (two pairs: 0.517); 2 slots + 5 teams 0.528; 3 slots + 2 / 3 teams with
+    // two pairs 0.608 / 0.564; without the software pipeline (four levels fetched, then blended) 0.72 / 0.63 / 0.55 with 2 / 3 / 4 teams
+    // (profiles/r2_50_field_infer_probe.json).  ncu (r2_49): the gather warps are bound by their own instruction stream (146
+    // instructions per sample-level, 4 warps per scheduler) — L1 data pipe 60 %, issue slots 56 %.
+    return fi::launch<2, 4, 8, 3>(in, dirs, grid, offsets, S, H, gridtype, Ws, Wc, sigma, rgb, (int)n_ch, B, st);
 }

@@ -52,6 +52,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// the same wait with a suspend-time hint (ns): the warp sleeps in the barrier unit (NANOSLEEP.SYNCS, woken by the phase completion)
+// instead of coming back every ~100 cycles to poll.  For kernels whose waiting warps share their schedulers with busy ones
+// (field_infer.cu: ncu r2_49 counted a third of the issued instructions in the polling loops of the thirteen waiting MLP warps;
+// removing them frees issue slots but did not change the kernel's time, 0.511 ms either way).
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t hint_ns = 20000u) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+            : "memory");
+    } while (!done);
+}
 
 // one lane of the (converged) warp; the same lane every time for the full mask.  MMA-issuing warps run their
 // control flow warp-uniformly and wrap only the issue itself in `if (elect_one())`: under a divergent

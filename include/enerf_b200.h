@@ -271,8 +271,6 @@ int enerf_field_infer(const float* raw_xyz, float in_add, float in_mul, const fl
                       const int32_t* offsets, uint32_t L, uint32_t C, float S, uint32_t H, uint32_t gridtype,
                       const uint16_t* w_sigma, uint32_t num_layers, const uint16_t* w_color, uint32_t num_layers_color,
                       uint32_t B, uint32_t n_ch, float* sigma, float* rgb, void* stream);
-/* Which (MLP slots, gather teams) instantiation enerf_field_infer launches (tools/field_infer_probe.py): 0 = default. */
-int enerf_field_infer_set_variant(int variant);
 
 /* The torch-topology field of nerf/network.py:104-199 (what every shipped E-NeRF config runs: sigma-net Linear(32,64)-ReLU-
  * Linear(64,16), colour-net Linear(31,64)-ReLU-Linear(64,64)-ReLU-Linear(64,C), no bias) on the same tcgen05 kernels.

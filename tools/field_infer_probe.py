@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """The fused inference field (csrc/field_infer.cu) against the chain it replaces: (a) one call on the marcher-ordered samples of the bench
-workload (4096 rays, ~3.29 M samples): grid_encode_forward + field_sigma_forward + field_color_forward vs enerf_field_infer in each
-instantiation; (b) the 800x800 frame of BASELINE configs[3] through both."""
+workload (4096 rays, ~3.29 M samples): grid_encode_forward + field_sigma_forward + field_color_forward vs enerf_field_infer;
+(b) the 800x800 frame of BASELINE configs[3] through both.  (While the kernel was being shaped this script also walked its
+instantiations — MLP slots x gather teams x level pairs in flight; those numbers are in profiles/r2_50_field_infer_probe.json.)"""
 import json
 import os
 import sys
@@ -10,9 +11,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
-from enerf_b200 import _lib, raymarching, synthetic  # noqa: E402
-
-VARIANTS = {0: "3 slots, 2 gather teams", 1: "3 slots, 3 teams", 2: "2 slots, 4 teams", 3: "3 slots, 4 teams"}
+from enerf_b200 import raymarching, synthetic  # noqa: E402
 
 
 def time_ms(fn, reps=10):
@@ -53,23 +52,16 @@ def main():
         ref = model(xyzs, dirs)
         out["per_call"]["unfused_chain_ms"] = time_ms(lambda: model(xyzs, dirs))
         model.fuse_infer = True
-        for v, name in VARIANTS.items():
-            _lib.call("enerf_field_infer_set_variant", v)
-            got = model(xyzs, dirs)
-            same = bool(torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1]))
-            out["per_call"][f"fused_v{v}"] = {"what": name, "ms": time_ms(lambda: model(xyzs, dirs)), "bit_identical": same}
-            print(json.dumps({f"fused_v{v}": out["per_call"][f"fused_v{v}"]}), flush=True)
-        _lib.call("enerf_field_infer_set_variant", 0)
+        got = model(xyzs, dirs)
+        out["per_call"]["fused_ms"] = time_ms(lambda: model(xyzs, dirs))
+        out["per_call"]["bit_identical"] = bool(torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1]))
 
     # (b) the full frame
     if frames:
-        for key, fuse, v in (("unfused", False, 0), ("fused_v0", True, 0), ("fused_v1", True, 1), ("fused_v2", True, 2), ("fused_v3", True, 3)):
+        for key, fuse in (("unfused", False), ("fused", True)):
             model.fuse_infer = fuse
-            _lib.call("enerf_field_infer_set_variant", v)
             r = bench.render_bench(model, dev, D, frames=2)
             out["frame"][key] = {"frame_ms": r["frame_ms"], "msamples_per_s": r["msamples_per_s"], "samples": r["samples_shaded"]}
-            print(json.dumps({key: out["frame"][key]}), flush=True)
-        _lib.call("enerf_field_infer_set_variant", 0)
     print(json.dumps({"field_infer_probe": out}))
 
 
