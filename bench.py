@@ -72,6 +72,8 @@ def parse():
     ap.add_argument("--no-render", action="store_true", help="same as --skip render")
     ap.add_argument("--nvtx", action="store_true", help="NVTX range around every C-ABI call (profiling; named after the entry point)")
     ap.add_argument("--only", default="", help="profiling aid: run ONE of event_step / run_variant alone and print its object (no headline line)")
+    ap.add_argument("--fuse-encoder", default="on", choices=["on", "off"],
+                    help="off: the inference render evaluates the field as three kernels (gather, sigma-net, colour-net) instead of one (csrc/field_infer.cu); diagnosis")
     ap.add_argument("--exchange", default="sharded", choices=["sharded", "allreduce", "none"],
                     help="gradient exchange at N > 1 (enerf_b200/parallel.py); none = no exchange at all (diagnosis only: the ranks diverge)")
     return ap.parse_args()
@@ -204,12 +206,16 @@ class Dist:
         return int(t[0]) == 1
 
 
+FUSE_ENCODER = True      # --fuse-encoder
+
+
 def make_ff_model(dev, bound):
     import torch
     from enerf_b200 import synthetic
     from enerf_b200.nerf.network_ff import NeRFNetwork
     model = NeRFNetwork(encoding="hashgrid", bound=bound, cuda_ray=True, density_scale=1, min_near=0.2, density_thresh=0.01, bg_radius=-1,
                         out_dim_color=1).to(dev)
+    model.fuse_infer = FUSE_ENCODER
     model.train()
     grid = synthetic.ball_density_grid(bound, model.cascade)
     model.density_grid.copy_(torch.from_numpy(grid))
@@ -622,6 +628,8 @@ def our_arm(args):
 
     from enerf_b200 import _lib, parallel
 
+    global FUSE_ENCODER
+    FUSE_ENCODER = args.fuse_encoder == "on"
     D = Dist()
     world, rank = D.world, D.rank
     if args.nvtx:
