@@ -1350,7 +1350,8 @@ static int launch_bwd_rc_n(const TmaDesc& tx, const __half* grad, const __half* 
 
 // backward from the network input alone (hidden activations recomputed per tile).
 // Measured on B200 (3.29 M samples).  2-layer nets: 0.255 ms with 3 slots x 4 epilogue warps (0.28 with 2 x 8; 0.33 with 4 slots and
-// the input tile aliased: 96 registers, spills).  3-layer nets: 0.343 ms with 3 slots, input tile aliased onto dead activation
+// the input tile aliased: 96 registers, spills; again with the ReLU masks in registers — 56-64 bytes of spills left at 96 registers —
+// the sigma-net backward takes 0.290 ms with 4 slots against 0.249 with 3).  3-layer nets: 0.343 ms with 3 slots, input tile aliased onto dead activation
 // buffers (XA); 0.355 with 2 slots x 8 epilogue warps; 0.386 with 2 x 4.  1-layer nets (torch topology sigma-net): 3 slots.
 template <int PRO>
 static int launch_bwd_rc(const __half* grad, const __half* x, const __half* W, __half* grad_inputs, float* dW, uint32_t B, int in_dim, int n_hidden_mm,
