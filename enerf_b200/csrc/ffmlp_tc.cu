@@ -1330,8 +1330,10 @@ template <int NSLOTS, int NH, int PRO, bool XA>
 static int launch_bwd_rc_n(const TmaDesc& tx, const __half* grad, const __half* W, __half* grad_inputs, float* dW, uint32_t B, ProArgs pro,
                            cudaStream_t st, const char* name) {
     constexpr bool GD = false;      // second G tile + early dgrad commit: measured +-0 %
-    constexpr int CH = 1;           // two epilogue threads per row: +8 % with 2 tiles in flight, nothing with 3
-    constexpr int NI = 1;           // second issuing warp: +-0 %
+    // two epilogue threads per row (8 warps per slot, 72 registers): since the ReLU masks live in registers this pays for the 3-layer
+    // nets — colour-net backward 0.339 -> 0.317 ms — and not for the 2-layer ones (sigma-net 0.251 -> 0.253)
+    constexpr int CH = (NH == 2) ? 2 : 1;
+    constexpr int NI = 1;           // second issuing warp: +-0 % in round 1; with two epilogue threads per row 0.374 vs 0.316 ms (worse)
     constexpr size_t kSlot = (XA ? 0 : 2 * (size_t)kTile * 32 * 2) + (size_t)(NH + 2 + (GD ? 1 : 0)) * kGBytes;
     size_t smem = 1024 + NSLOTS * kSlot + 32 * 128 + (size_t)NH * 8192 + 2048 + (5 * NSLOTS + 1) * 8 + 16;
     if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: it allocates all 512 TMEM columns
@@ -1352,7 +1354,7 @@ static int launch_bwd_rc_n(const TmaDesc& tx, const __half* grad, const __half* 
 // Measured on B200 (3.29 M samples).  2-layer nets: 0.255 ms with 3 slots x 4 epilogue warps (0.28 with 2 x 8; 0.33 with 4 slots and
 // the input tile aliased: 96 registers, spills; again with the ReLU masks in registers — 56-64 bytes of spills left at 96 registers —
 // the sigma-net backward takes 0.290 ms with 4 slots against 0.249 with 3).  3-layer nets: 0.343 ms with 3 slots, input tile aliased onto dead activation
-// buffers (XA); 0.355 with 2 slots x 8 epilogue warps; 0.386 with 2 x 4.  1-layer nets (torch topology sigma-net): 3 slots.
+// buffers (XA); 0.355 with 2 slots x 8 epilogue warps; 0.386 with 2 x 4; with the masks in registers 3 slots x 8 warps: 0.316 (shipped).  1-layer nets (torch topology sigma-net): 3 slots.
 template <int PRO>
 static int launch_bwd_rc(const __half* grad, const __half* x, const __half* W, __half* grad_inputs, float* dW, uint32_t B, int in_dim, int n_hidden_mm,
                          ProArgs pro, cudaStream_t st, const char* name) {
