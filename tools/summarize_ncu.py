@@ -23,6 +23,9 @@ METRICS = [
     ("launch__grid_size", "grid"),
     ("launch__block_size", "block"),
     ("smsp__inst_executed.sum", "warp_inst"),
+    ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1_pipe_%"),
+    ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2_%"),
+    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_%"),
 ]
 
 
