@@ -48,13 +48,15 @@ class _Raymarching:
 
     @staticmethod
     def occupancy_bounds(grid, C, H):
-        """extension: int32 [C, 6] box around the occupied cells of each cascade level, or None when H is not a power of two >= 4"""
+        """extension: int32 [C, 6] box around the occupied cells of each cascade level (a view of the buffer enerf_occupancy_bounds fills; pass it
+        on as it is), or None when H is not a power of two >= 4"""
         if H < 4 or H & (H - 1) or grid.data_ptr() % 16 or grid.numel() * 8 < C * H ** 3:
             return None                                   # the marcher then probes every candidate, as the reference does
         need_cuda(grid)
-        bounds = torch.empty(C, 6, dtype=torch.int32, device=grid.device)
-        _lib.call("enerf_occupancy_bounds", ptr(grid), C, H, ptr(bounds), stream())
-        return bounds
+        words = ((6 * C + 3) & ~3) + 8 * C                # ENERF_OCC_BOUNDS_WORDS: the integer rows, then the float rows the marchers read
+        buf = torch.empty(words, dtype=torch.int32, device=grid.device)
+        _lib.call("enerf_occupancy_bounds", ptr(grid), C, H, ptr(buf), stream())
+        return buf[:6 * C].view(C, 6)                     # same storage, same address: the float rows stay behind it
 
     @staticmethod
     def march_rays_train(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, xyzs, dirs, deltas, rays, counter, perturb,

@@ -37,7 +37,7 @@ const char* enerf_last_error(void) { return enerf::g_err; }
 // 2: recomputation (NULL forward_buffer), events / sampler / Adam; 3: CTA cap + scatter CTA size; 4: fp16 shadow in adam_step,
 // T_dist in composite_uniform_*; 5: device-side row / ray counts (n_rows_dev, n_alive_dev), grad_mul + fp16 gradients in adam_step,
 // torch-topology field, occupancy maintenance
-int enerf_abi_version(void) { return 7; }
+int enerf_abi_version(void) { return 8; }
 uint64_t enerf_launch_count(void) { return enerf::g_launches.load(std::memory_order_relaxed); }
 
 }

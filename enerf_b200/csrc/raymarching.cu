@@ -225,36 +225,55 @@ __device__ __forceinline__ float advance_batch(float tb, const MarchCfg& c) {
 struct TRange {
     float lo, hi;
 };
-__device__ __forceinline__ TRange occupied_range(const Ray& r, const MarchCfg& c, const int32_t* __restrict__ occ_bounds) {
+// The box around the occupied cells.  enerf_occupancy_bounds leaves it per cascade level, in units of the level's half extent
+// (`k_occupancy_bounds`: float rows behind the integer rows); a ray's warp scales the rows by mip_bound and unites them — two 16-byte
+// loads, six multiplies and six min / max per level where the integer rows took ~80 instructions per level, a third of what a ray
+// costs per inference round (ncu, `profiles/r2_60`).
+struct OccBox {
+    float lo[3], hi[3];
+    int state;                    // 0: no bounds given (march exhaustively), 1: box valid, 2: nothing occupied anywhere
+};
+__host__ __device__ __forceinline__ uint32_t occ_box_offset(uint32_t C) { return (6u * C + 3u) & ~3u; }   // in 4-byte words, 16-byte aligned
+__device__ __forceinline__ OccBox occupied_box(const MarchCfg& c, const int32_t* __restrict__ occ_bounds) {
+    OccBox box;
+    box.state = 0;
+    if (!occ_bounds) return box;
+    const float4* rows = reinterpret_cast<const float4*>(occ_bounds + occ_box_offset(c.C));
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+#pragma unroll 1
+    for (uint32_t l = 0; l < c.C; ++l) {
+        const float mb = fminf((float)(1u << l), c.bound);
+        const float4 a = __ldg(rows + 2 * l), b = __ldg(rows + 2 * l + 1);
+        if (a.w != 0.0f) {        // the level has occupied cells
+            lo[0] = fminf(lo[0], a.x * mb); lo[1] = fminf(lo[1], a.y * mb); lo[2] = fminf(lo[2], a.z * mb);
+            hi[0] = fmaxf(hi[0], b.x * mb); hi[1] = fmaxf(hi[1], b.y * mb); hi[2] = fmaxf(hi[2], b.z * mb);
+        }
+    }
+    // one cell of the finest level plus rounding of the cell index / the slab test: far more than either can be off by
+    const float margin = 2.0f * fminf(1.0f, c.bound) / c.Hf + 1e-3f * c.bound;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        box.lo[a] = lo[a] - margin;
+        box.hi[a] = hi[a] + margin;
+    }
+    box.state = (hi[0] < lo[0]) ? 2 : 1;
+    return box;
+}
+__device__ __forceinline__ TRange occupied_range(const Ray& r, const OccBox& box) {
     TRange o;
     o.lo = -FLT_MAX;
     o.hi = FLT_MAX;
-    if (!occ_bounds) return o;
-    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-    for (uint32_t l = 0; l < c.C; ++l) {
-        const float mb = fminf((float)(1u << l), c.bound);
-        const float cell = 2.0f * mb / c.Hf;
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            const int mn = __ldg(occ_bounds + l * 6 + a), mx = __ldg(occ_bounds + l * 6 + 3 + a);
-            if (mx >= mn) {
-                lo[a] = fminf(lo[a], (float)mn * cell - mb);
-                hi[a] = fmaxf(hi[a], (float)(mx + 1) * cell - mb);
-            }
-        }
-    }
-    if (hi[0] < lo[0]) {          // nothing occupied anywhere
+    if (box.state == 0) return o;
+    if (box.state == 2) {         // nothing occupied anywhere
         o.lo = FLT_MAX;
         o.hi = -FLT_MAX;
         return o;
     }
-    // one cell of the finest level plus rounding of the cell index / the slab test: far more than either can be off by
-    const float margin = 2.0f * fminf(1.0f, c.bound) / c.Hf + 1e-3f * c.bound;
     const float org[3] = {r.ox, r.oy, r.oz}, rd[3] = {r.rdx, r.rdy, r.rdz};
     float t_in = -FLT_MAX, t_out = FLT_MAX;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        const float ta = (lo[a] - margin - org[a]) * rd[a], tb = (hi[a] + margin - org[a]) * rd[a];
+        const float ta = (box.lo[a] - org[a]) * rd[a], tb = (box.hi[a] - org[a]) * rd[a];
         // a NaN (origin on a slab plane of an axis-parallel ray) leaves the axis unconstrained: fminf / fmaxf return the other operand
         t_in = fmaxf(t_in, fminf(ta, tb));
         t_out = fminf(t_out, fmaxf(ta, tb));
@@ -344,10 +363,12 @@ __device__ uint32_t march_warp(const Ray& r, const MarchCfg& c, const uint8_t* _
                 // maximal run of occupied in-range candidates starting at cur
                 const unsigned stop = (~(m_occ & m_range)) & (kFull << cur);
                 const int e = stop ? (__ffs(stop) - 1) : 32;
-                unsigned run = (e >= 32 ? kFull : ((1u << e) - 1u)) & (kFull << cur);
-                while ((uint32_t)__popc(run) > room) run &= ~(1u << (31 - __clz(run)));
+                // the run is the contiguous candidates [cur, e): when there is room for fewer, keep its first `room` (the later ones
+                // are dropped and `cur = e` ends the batch's scan either way, as when they were trimmed one bit at a time)
+                const int e_keep = (int)min((uint32_t)e, (uint32_t)cur + room);
+                const unsigned run = (e_keep >= 32 ? kFull : ((1u << e_keep) - 1u)) & (kFull << cur);
                 emit |= run;
-                room -= (uint32_t)__popc(run);
+                room -= (uint32_t)(e_keep - cur);
                 cur = e;
             } else {
                 const float target = __shfl_sync(kFull, tt, cur);
@@ -460,7 +481,7 @@ k_march_rays_train(const float* __restrict__ rays_o, const float* __restrict__ r
     if (n >= N) return;
     const unsigned lane = lane_id();
     const Ray r = load_ray(rays_o, rays_d, n);
-    const TRange occ = occupied_range(r, c, occ_bounds);
+    const TRange occ = occupied_range(r, occupied_box(c, occ_bounds));
     const float near = nears[n], far = fars[n];
     float t0 = near;
     if (perturb) {
@@ -510,9 +531,11 @@ k_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* __restrict__ rays
              float* __restrict__ dirs, float* __restrict__ deltas, uint32_t perturb, const int32_t* __restrict__ n_alive_dev,
              const int32_t* __restrict__ occ_bounds) {
     const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (n >= alive_count(n_alive, n_alive_dev)) return;
+    if (n >= n_alive) return;
+    // slot n exists in both arrays whatever the device-side count says: its loads go out together with the count's
     const uint32_t index = (uint32_t)rays_alive[n];
     float t = rays_t[n];
+    if (n >= alive_count(n_alive, n_alive_dev)) return;
     const Ray r = load_ray(rays_o, rays_d, index);
     const float far = fars[index];
     if (perturb) {
@@ -520,12 +543,12 @@ k_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* __restrict__ rays
         t = __fmaf_rn(c.dt_min, rng.next_float(), t);
     }
     const size_t base = (size_t)n * n_step;
-    march_warp<true>(r, c, grid, t, far, n_step, xyzs + base * 3, dirs + base * 3, deltas + base * 2, occupied_range(r, c, occ_bounds));
+    march_warp<true>(r, c, grid, t, far, n_step, xyzs + base * 3, dirs + base * 3, deltas + base * 2, occupied_range(r, occupied_box(c, occ_bounds)));
 }
 
 // Box around the occupied cells of each cascade level: one CTA per level scans the level's bits 128 at a time (128 consecutive Morton
 // codes = an aligned 8 x 4 x 4 block of cells, taken whole when any of its bits is set).  out: int32 [C][6] = min x, y, z, max x, y, z;
-// an empty level gets min = H, max = -1.
+// an empty level gets min = H, max = -1.  Behind them, from word occ_box_offset(C): float [C][8], the box the marchers read.
 __global__ void __launch_bounds__(1024)
 k_occupancy_bounds(const uint8_t* __restrict__ grid, uint32_t H, uint32_t words_per_level, int32_t* __restrict__ out) {
     const uint32_t level = blockIdx.x;
@@ -580,8 +603,19 @@ k_occupancy_bounds(const uint8_t* __restrict__ grid, uint32_t H, uint32_t words_
                 v1 = max(v1, __shfl_xor_sync(kFull, v1, k));
             }
             if (lane == 0) {
+                const int top = min(v1, (int)H - 1);
                 out[level * 6 + a] = v0;
-                out[level * 6 + 3 + a] = min(v1, (int)H - 1);
+                out[level * 6 + 3 + a] = top;
+                // the same box in units of the level's half extent ([-1, 1]; cell i spans [2 i / H - 1, 2 (i + 1) / H - 1]), w = 1 when
+                // the level has occupied cells: what the marchers read (occupied_box)
+                float* row = reinterpret_cast<float*>(out + occ_box_offset(gridDim.x)) + level * 8;
+                const float cell = 2.0f / (float)H;
+                row[a] = __fmaf_rn((float)v0, cell, -1.0f);
+                row[4 + a] = __fmaf_rn((float)(top + 1), cell, -1.0f);
+                if (a == 0) {
+                    row[3] = v1 >= v0 ? 1.0f : 0.0f;
+                    row[7] = 0.0f;
+                }
             }
         }
     }
@@ -860,10 +894,11 @@ k_composite_rays_warp(uint32_t n_alive, uint32_t n_step, const int32_t* __restri
                       float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image,
                       const int32_t* __restrict__ n_alive_dev) {
     const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (n >= alive_count(n_alive, n_alive_dev)) return;
+    if (n >= n_alive) return;
     const unsigned lane = lane_id();
-    const uint32_t index = (uint32_t)rays_alive[n];
+    const uint32_t index = (uint32_t)rays_alive[n];      // loads of slot n next to the load of the device-side count, not behind it
     float t = rays_t[n];
+    if (n >= alive_count(n_alive, n_alive_dev)) return;
     sigmas += (size_t)n * n_step;
     rgbs += (size_t)n * n_step * NCH;
     deltas += (size_t)n * n_step * 2;

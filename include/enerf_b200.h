@@ -115,8 +115,12 @@ int enerf_compact_rays_dev(uint32_t n_alive, int32_t* rays_alive, const int32_t*
 /* Marching bounded by the occupied region (no reference counterpart; the samples are those of raymarching.cu:313-480 / :700-813, bit for
  * bit).  The candidate parameters t0, t0 + dt, ... of a ray do not depend on the occupancy (an empty voxel is left by repeated
  * `t += dt`, raymarching.cu:390-398), so candidates outside the box around the occupied cells can be stepped over without a grid
- * lookup and the march can stop behind it.  enerf_occupancy_bounds: bounds = int32 [C][6] (min x, y, z, max x, y, z in cells of each
- * cascade level, rounded outwards to aligned 8 x 4 x 4 blocks; an empty level has min = H, max = -1); H a power of two >= 4.  occ_bounds == NULL: the exhaustive march. */
+ * lookup and the march can stop behind it.  enerf_occupancy_bounds: bounds = ENERF_OCC_BOUNDS_WORDS(C) 4-byte words, 16-byte aligned:
+ * int32 [C][6] (min x, y, z, max x, y, z in cells of each cascade level, rounded outwards to aligned 8 x 4 x 4 blocks; an empty level
+ * has min = H, max = -1), then, from the next multiple of four words, float [C][8] = the same box in units of the level's half extent
+ * (lo x, y, z, 1 if the level has occupied cells else 0, hi x, y, z, 0), which is what the marchers read (since ABI v8); H a power of
+ * two >= 4.  occ_bounds == NULL: the exhaustive march. */
+#define ENERF_OCC_BOUNDS_WORDS(C) ((((6u * (C)) + 3u) & ~3u) + 8u * (C))
 int enerf_occupancy_bounds(const uint8_t* grid, uint32_t C, uint32_t H, int32_t* bounds, void* stream);
 int enerf_march_rays_train_bounded(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound, float dt_gamma,
                                    uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float* nears,

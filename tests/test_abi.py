@@ -29,7 +29,7 @@ def test_header_is_plain_c():
 
 def test_abi_version_and_error_string():
     L = _lib.lib()
-    assert L.enerf_abi_version() == 7
+    assert L.enerf_abi_version() == 8
     assert isinstance(L.enerf_last_error(), bytes)
     assert _lib.launch_count() >= 0
 
