@@ -284,7 +284,18 @@ def test_bounded_march_emits_the_samples_of_the_exhaustive_march(case):
     nears, fars = oracle.near_far_from_aabb(o, d, aabb, 0.2)
     tb = t(bits)
     bounds = RB.occupancy_bounds(tb, C, H)
-    assert np.array_equal(n(bounds), _cell_box(bits, C, H))
+    box = _cell_box(bits, C, H)
+    assert np.array_equal(n(bounds), box)
+    # the float rows behind the integer rows (ENERF_OCC_BOUNDS_WORDS, include/enerf_b200.h): the same box in units of the level's half extent
+    off, words = (6 * C + 3) & ~3, ((6 * C + 3) & ~3) + 8 * C
+    flat = torch.empty(0, dtype=torch.int32, device=DEV).set_(bounds.untyped_storage(), 0, (words,))
+    rows = n(flat[off:].view(torch.float32)).reshape(C, 8)
+    want = np.zeros((C, 8), np.float32)
+    cell = np.float32(2.0) / np.float32(H)
+    want[:, 0:3] = box[:, :3].astype(np.float32) * cell - np.float32(1.0)       # exact: H is a power of two
+    want[:, 4:7] = (box[:, 3:] + 1).astype(np.float32) * cell - np.float32(1.0)
+    want[:, 3] = (box[:, 3] >= box[:, 0]).astype(np.float32)
+    assert np.array_equal(rows, want)
     dt_gamma = 1.0 / 128 if case == "dt_gamma" else 0.0
     res = []
     M = N * 1024
