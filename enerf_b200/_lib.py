@@ -55,6 +55,7 @@ _SIGS = {
     "enerf_field_color_backward": [_p, _p, _u32, _p, _p, _p, _u32, _u32, _p, _p, _p, _p],
     "enerf_field_sigma_backward": [_p, _p, _p, _p, _p, _p, _u32, _u32, _p, _p, _p],
     "enerf_field_infer": [_p, _f32, _f32, _p, _p, _p, _u32, _u32, _f32, _u32, _u32, _p, _u32, _p, _u32, _u32, _u32, _p, _p, _p],
+    "enerf_field_infer_alive": [_p, _f32, _f32, _p, _p, _p, _u32, _u32, _f32, _u32, _u32, _p, _u32, _p, _u32, _u32, _u32, _p, _p, _p, _u32, _p],
     "enerf_field_density_forward": [_p, _p, _u32, _u32, _p, _p, _p],
     "enerf_field_density_backward": [_p, _p, _p, _p, _p, _u32, _u32, _p, _p, _p],
     "enerf_field_color_inputs": [_p, _u32, _p, _p, _u32, _u32, _f32, _p, _p, _p],

@@ -123,8 +123,18 @@ template <int NSLOTS, int NGT, int NX, int PD>
 __global__ void __launch_bounds__(32 + NSLOTS * 128 + NGT * 128, 1)
 k_field_infer(const Inputs inputs, const float* __restrict__ dirs, const __half* __restrict__ grid, const int32_t* __restrict__ offsets, float S,
               uint32_t H, uint32_t gridtype, const __half* __restrict__ Ws, const __half* __restrict__ Wc, float* __restrict__ sigma,
-              float* __restrict__ rgb, int n_ch, uint32_t B, uint32_t n_tiles) {
+              float* __restrict__ rgb, int n_ch, uint32_t B, uint32_t n_tiles, const int32_t* __restrict__ n_units_dev, uint32_t rows_per_unit) {
     static_assert(NX % NGT == 0, "ring buffers per team");
+    if (n_units_dev) {
+        // only the first *n_units_dev * rows_per_unit rows are live (the alive rays of a marching round times its steps; the host sized
+        // the launch for an older, larger count): every thread reads the same word, so the CTA agrees on its number of tiles
+        const int32_t u = __ldg(n_units_dev);
+        const uint64_t rows = u > 0 ? (uint64_t)u * rows_per_unit : 0;
+        if (rows < (uint64_t)B) {
+            B = (uint32_t)rows;
+            n_tiles = (B + (uint32_t)kTile - 1u) / (uint32_t)kTile;
+        }
+    }
     static_assert(NSLOTS * kSlotCols <= 512, "TMEM budget");
     constexpr bool kBothHalves = (1 + 4 * NSLOTS + 4 * NGT) <= 24;      // 80 registers per thread up to 24 warps, 72 beyond
     extern __shared__ uint8_t smem_dyn[];
@@ -361,7 +371,7 @@ k_field_infer(const Inputs inputs, const float* __restrict__ dirs, const __half*
 
 template <int NSLOTS, int NGT, int NX, int PD>
 static int launch(const Inputs& in, const float* dirs, const __half* grid, const int32_t* offsets, float S, uint32_t H, uint32_t gridtype, const __half* Ws,
-                  const __half* Wc, float* sigma, float* rgb, int n_ch, uint32_t B, cudaStream_t st) {
+                  const __half* Wc, float* sigma, float* rgb, int n_ch, uint32_t B, const int32_t* n_units_dev, uint32_t rows_per_unit, cudaStream_t st) {
     size_t smem = 1024 + (size_t)(NX + NSLOTS) * kXBytes + kWBytes + (size_t)(2 * NSLOTS + 2 * NX) * 8 + 16;
     if (smem < 120 * 1024) smem = 120 * 1024;      // one CTA per SM: it owns the SM's tensor memory
     static bool configured = false;
@@ -371,7 +381,8 @@ static int launch(const Inputs& in, const float* dirs, const __half* grid, const
     }
     const uint32_t n_tiles = ceil_div(B, (uint32_t)kTile);
     const uint32_t grid_x = n_tiles < (uint32_t)num_sms() ? n_tiles : (uint32_t)num_sms();
-    k_field_infer<NSLOTS, NGT, NX, PD><<<grid_x, 32 + NSLOTS * 128 + NGT * 128, smem, st>>>(in, dirs, grid, offsets, S, H, gridtype, Ws, Wc, sigma, rgb, n_ch, B, n_tiles);
+    k_field_infer<NSLOTS, NGT, NX, PD><<<grid_x, 32 + NSLOTS * 128 + NGT * 128, smem, st>>>(in, dirs, grid, offsets, S, H, gridtype, Ws, Wc, sigma, rgb, n_ch, B, n_tiles,
+                                                                                            n_units_dev, rows_per_unit);
     ENERF_CHECK_LAUNCH("field_infer");
     return 0;
 }
@@ -381,9 +392,10 @@ static int launch(const Inputs& in, const float* dirs, const __half* grid, const
 
 using namespace enerf;
 
-extern "C" int enerf_field_infer(const float* raw_xyz, float in_add, float in_mul, const float* dirs, const uint16_t* embeddings, const int32_t* offsets,
-                                 uint32_t L, uint32_t C, float S, uint32_t H, uint32_t gridtype, const uint16_t* w_sigma, uint32_t num_layers,
-                                 const uint16_t* w_color, uint32_t num_layers_color, uint32_t B, uint32_t n_ch, float* sigma, float* rgb, void* stream) {
+extern "C" int enerf_field_infer_alive(const float* raw_xyz, float in_add, float in_mul, const float* dirs, const uint16_t* embeddings, const int32_t* offsets,
+                                       uint32_t L, uint32_t C, float S, uint32_t H, uint32_t gridtype, const uint16_t* w_sigma, uint32_t num_layers,
+                                       const uint16_t* w_color, uint32_t num_layers_color, uint32_t B, uint32_t n_ch, float* sigma, float* rgb,
+                                       const int32_t* n_units_dev, uint32_t rows_per_unit, void* stream) {
     ENERF_REQUIRE(L == (uint32_t)fi::kLevels && C == 2, "field_infer", "the fused field takes 16 levels of 2 fp16 features");
     ENERF_REQUIRE(num_layers == 2 && num_layers_color == 3, "field_infer", "the fused field takes the FFMLP 32-64-64-16 / 32-64-64-64-16 nets");
     ENERF_REQUIRE(n_ch >= 1 && n_ch <= 4, "field_infer", "n_ch must be in [1,4]");
@@ -400,5 +412,12 @@ extern "C" int enerf_field_infer(const float* raw_xyz, float in_add, float in_mu
     // two pairs 0.608 / 0.564; without the software pipeline (four levels fetched, then blended) 0.72 / 0.63 / 0.55 with 2 / 3 / 4 teams
     // (profiles/r2_50_field_infer_probe.json).  ncu (r2_49): the gather warps are bound by their own instruction stream (146
     // instructions per sample-level, 4 warps per scheduler) — L1 data pipe 60 %, issue slots 56 %.
-    return fi::launch<2, 4, 8, 3>(in, dirs, grid, offsets, S, H, gridtype, Ws, Wc, sigma, rgb, (int)n_ch, B, st);
+    return fi::launch<2, 4, 8, 3>(in, dirs, grid, offsets, S, H, gridtype, Ws, Wc, sigma, rgb, (int)n_ch, B, n_units_dev, rows_per_unit, st);
+}
+
+extern "C" int enerf_field_infer(const float* raw_xyz, float in_add, float in_mul, const float* dirs, const uint16_t* embeddings, const int32_t* offsets,
+                                 uint32_t L, uint32_t C, float S, uint32_t H, uint32_t gridtype, const uint16_t* w_sigma, uint32_t num_layers,
+                                 const uint16_t* w_color, uint32_t num_layers_color, uint32_t B, uint32_t n_ch, float* sigma, float* rgb, void* stream) {
+    return enerf_field_infer_alive(raw_xyz, in_add, in_mul, dirs, embeddings, offsets, L, C, S, H, gridtype, w_sigma, num_layers, w_color, num_layers_color, B, n_ch,
+                                   sigma, rgb, nullptr, 0, stream);
 }

@@ -523,7 +523,7 @@ __device__ __forceinline__ uint32_t alive_count(uint32_t n_alive, const int32_t*
 }
 
 // raymarching.cu:700-804.  One warp per alive ray, at most n_step samples from rays_t.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
 k_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* __restrict__ rays_alive,
              const float* __restrict__ rays_t, const float* __restrict__ rays_o,
              const float* __restrict__ rays_d, MarchCfg c, const uint8_t* __restrict__ grid,
@@ -532,9 +532,11 @@ k_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* __restrict__ rays
              const int32_t* __restrict__ occ_bounds) {
     const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (n >= n_alive) return;
-    // slot n exists in both arrays whatever the device-side count says: its loads go out together with the count's
+    // slot n exists in both arrays whatever the device-side count says: its loads go out together with the count's, and so do the
+    // rows of the box, which depend on neither
     const uint32_t index = (uint32_t)rays_alive[n];
     float t = rays_t[n];
+    const OccBox box = occupied_box(c, occ_bounds);
     if (n >= alive_count(n_alive, n_alive_dev)) return;
     const Ray r = load_ray(rays_o, rays_d, index);
     const float far = fars[index];
@@ -543,7 +545,7 @@ k_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* __restrict__ rays
         t = __fmaf_rn(c.dt_min, rng.next_float(), t);
     }
     const size_t base = (size_t)n * n_step;
-    march_warp<true>(r, c, grid, t, far, n_step, xyzs + base * 3, dirs + base * 3, deltas + base * 2, occupied_range(r, occupied_box(c, occ_bounds)));
+    march_warp<true>(r, c, grid, t, far, n_step, xyzs + base * 3, dirs + base * 3, deltas + base * 2, occupied_range(r, box));
 }
 
 // Box around the occupied cells of each cascade level: one CTA per level scans the level's bits 128 at a time (128 consecutive Morton

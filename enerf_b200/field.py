@@ -88,8 +88,11 @@ def infer_eligible(x, dirs, encoder, *shape_args):
 
 
 @torch.no_grad()
-def fused_infer(x, dirs, encoder, bound, w_sigma, w_color, n_ch):
-    """x [S,3] in [-bound, bound], dirs [S,3] -> (sigma [S] fp32, rgb [S,n_ch] fp32); no autograd graph."""
+def fused_infer(x, dirs, encoder, bound, w_sigma, w_color, n_ch, alive=None, out=None):
+    """x [S,3] in [-bound, bound], dirs [S,3] -> (sigma [S] fp32, rgb [S,n_ch] fp32); no autograd graph.
+    `alive` = (int32 device scalar u, rows_per_unit): only the first min(S, u * rows_per_unit) rows are evaluated and written (the
+    inference loop's alive rays x steps of the round); the other rows of the results are left as they are (uninitialised, or what
+    `out` = (sigma, rgb) — contiguous fp32 tensors to write into — held)."""
     import numpy as np
     from .gridencoder.grid import _half_table
     S = x.shape[0]
@@ -98,12 +101,21 @@ def fused_infer(x, dirs, encoder, bound, w_sigma, w_color, n_ch):
     dirs = dirs.contiguous().float()
     table = encoder.embeddings if encoder.embeddings.dtype == torch.float16 else _half_table(encoder.embeddings)
     ws, wc = w_sigma.detach().half().contiguous(), w_color.detach().half().contiguous()
-    sigma = torch.empty(S, dtype=torch.float32, device=dev)
-    rgb = torch.empty(S, n_ch, dtype=torch.float32, device=dev)
+    if out is not None:
+        sigma, rgb = out
+        if not (sigma.shape == (S,) and rgb.shape == (S, n_ch) and sigma.dtype == rgb.dtype == torch.float32 and sigma.is_contiguous()
+                and rgb.is_contiguous() and sigma.device == rgb.device == dev):
+            raise ValueError("fused_infer: out = (sigma [S], rgb [S, n_ch]), contiguous fp32 on the inputs' device")
+    else:
+        sigma = torch.empty(S, dtype=torch.float32, device=dev)
+        rgb = torch.empty(S, n_ch, dtype=torch.float32, device=dev)
     in_mul = float(np.float32(1.0) / np.float32(2 * bound))          # GridEncoder.forward's (x + bound) / (2 bound) in ATen's arithmetic
-    _lib.call("enerf_field_infer", ptr(x), float(bound), in_mul, ptr(dirs), ptr(table), ptr(encoder.offsets), encoder.num_levels, encoder.level_dim,
+    count, per_unit = alive if alive is not None else (None, 0)
+    if count is not None and not (count.is_cuda and count.dtype == torch.int32 and count.numel() == 1 and int(per_unit) > 0):
+        raise ValueError("fused_infer: alive = (int32 CUDA scalar, rows per unit > 0)")
+    _lib.call("enerf_field_infer_alive", ptr(x), float(bound), in_mul, ptr(dirs), ptr(table), ptr(encoder.offsets), encoder.num_levels, encoder.level_dim,
               float(np.log2(encoder.per_level_scale)), int(encoder.base_resolution), int(encoder.gridtype_id), ptr(ws), 2, ptr(wc), 3, S, n_ch,
-              ptr(sigma), ptr(rgb), stream())
+              ptr(sigma), ptr(rgb), ptr(count), int(per_unit), stream())
     return sigma, rgb
 
 

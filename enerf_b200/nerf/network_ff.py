@@ -56,7 +56,9 @@ class NeRFNetwork(NeRFRenderer):
             if (self.fuse_infer and not torch.is_grad_enabled() and self.num_layers == 2 and self.num_layers_color == 3
                     and isinstance(self.bound, (int, float)) and field.infer_eligible(x, d, self.encoder, *shapes)):
                 # rendering: gather + sigma-net + colour-net in one kernel, features and colour-net inputs stay on the SM
-                return field.fused_infer(x, d, self.encoder, self.bound, self.sigma_net.weights, self.color_net.weights, self.out_dim_color)
+                # `_alive_rows`: set by the inference loop of NeRFRenderer.run_cuda around this call (device-side alive count x steps)
+                return field.fused_infer(x, d, self.encoder, self.bound, self.sigma_net.weights, self.color_net.weights, self.out_dim_color,
+                                         alive=getattr(self, '_alive_rows', None))
             feat = self.encoder(x, bound=self.bound)
             if field.eligible(feat, d, *shapes):
                 return field.fused_field(feat, d, self.sigma_net.weights, self.color_net.weights, self.num_layers, self.num_layers_color,

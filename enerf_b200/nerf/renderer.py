@@ -234,7 +234,14 @@ class NeRFRenderer(nn.Module):
                 xyzs, dirs, deltas = raymarching.march_rays(n_bound, n_step, rays_alive[i % 2], rays_t[i % 2], rays_o, rays_d, self.bound,
                                                             self.density_bitfield, self.cascade, self.grid_size, nears, fars, 128, perturb,
                                                             dt_gamma, max_steps, count_dev, occ_bounds)
-                sigmas, rgbs = self(xyzs, dirs)
+                # rows of slots at or beyond the device-side alive count are read by nobody (composite_rays skips them): a field that can
+                # take the count on the device (network_ff's fused inference kernel) does not evaluate them — the host's `n_bound` lags the
+                # true count by up to `inference_sync_every` rounds (5.8 % of a frame's rows at 800 x 800)
+                self._alive_rows = (count_dev, n_step) if count_dev is not None else None
+                try:
+                    sigmas, rgbs = self(xyzs, dirs)
+                finally:
+                    self._alive_rows = None
                 if self.density_scale != 1:
                     sigmas = self.density_scale * sigmas
                 if image is None:

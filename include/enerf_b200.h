@@ -275,6 +275,15 @@ int enerf_field_infer(const float* raw_xyz, float in_add, float in_mul, const fl
                       const int32_t* offsets, uint32_t L, uint32_t C, float S, uint32_t H, uint32_t gridtype,
                       const uint16_t* w_sigma, uint32_t num_layers, const uint16_t* w_color, uint32_t num_layers_color,
                       uint32_t B, uint32_t n_ch, float* sigma, float* rgb, void* stream);
+/* The same with the number of live rows on the device: only the first min(B, *n_units_dev * rows_per_unit) rows are evaluated and
+ * written (n_units_dev: the int32 alive-ray count enerf_compact_rays_dev leaves, rows_per_unit: the round's n_step).  In the inference
+ * loop (nerf/renderer.py:364-391) the host then sizes a round by the last count it has read — an upper bound — without paying the field
+ * for the rays that died since.  n_units_dev == NULL: all B rows. */
+int enerf_field_infer_alive(const float* raw_xyz, float in_add, float in_mul, const float* dirs, const uint16_t* embeddings,
+                            const int32_t* offsets, uint32_t L, uint32_t C, float S, uint32_t H, uint32_t gridtype,
+                            const uint16_t* w_sigma, uint32_t num_layers, const uint16_t* w_color, uint32_t num_layers_color,
+                            uint32_t B, uint32_t n_ch, float* sigma, float* rgb, const int32_t* n_units_dev, uint32_t rows_per_unit,
+                            void* stream);
 
 /* The torch-topology field of nerf/network.py:104-199 (what every shipped E-NeRF config runs: sigma-net Linear(32,64)-ReLU-
  * Linear(64,16), colour-net Linear(31,64)-ReLU-Linear(64,64)-ReLU-Linear(64,C), no bias) on the same tcgen05 kernels.

@@ -152,3 +152,27 @@ def test_rendered_frame_is_identical():
     assert torch.equal(outs[0]["image"], outs[1]["image"])
     assert torch.equal(outs[0]["depth"], outs[1]["depth"])
     assert float(outs[0]["image"].std()) > 0
+
+
+@pytest.mark.parametrize("live_units", [0, 1, 37, 500, 10 ** 6])
+def test_device_side_row_count_limits_the_rows_evaluated(live_units):
+    """enerf_field_infer_alive: only the first min(S, *n_units_dev * rows_per_unit) rows are evaluated and written — the bits of the
+    full call — and nothing behind them is touched (the inference loop sizes a round by a stale, larger alive count)"""
+    from enerf_b200 import field
+    m = _model(bound=3, n_ch=3)
+    per_unit, units = 26, 500
+    S = units * per_unit                                   # 13 000 rows = 102 tiles: fewer tiles than CTAs once the count drops
+    x, d = _samples(S, 3, seed=11)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        s_full, c_full = field.fused_infer(x, d, m.encoder, m.bound, m.sigma_net.weights, m.color_net.weights, 3)
+        count = torch.tensor([live_units], dtype=torch.int32, device=DEV)
+        s_lim = torch.full((S,), -7.0, dtype=torch.float32, device=DEV)
+        c_lim = torch.full((S, 3), -7.0, dtype=torch.float32, device=DEV)
+        field.fused_infer(x, d, m.encoder, m.bound, m.sigma_net.weights, m.color_net.weights, 3, alive=(count, per_unit), out=(s_lim, c_lim))
+    torch.cuda.synchronize()
+    live = min(S, live_units * per_unit)
+    assert float(s_full.min()) >= 0.0 and float(c_full.min()) >= 0.0           # no result looks like the sentinel
+    assert torch.equal(s_lim[:live], s_full[:live]) and torch.equal(c_lim[:live], c_full[:live])
+    assert bool((s_lim[live:] == -7.0).all()) and bool((c_lim[live:] == -7.0).all())
+    with pytest.raises(ValueError):
+        field.fused_infer(x, d, m.encoder, m.bound, m.sigma_net.weights, m.color_net.weights, 3, alive=(count.long(), per_unit))
