@@ -522,6 +522,16 @@ __device__ __forceinline__ uint32_t alive_count(uint32_t n_alive, const int32_t*
     return v < 0 ? 0u : min(n_alive, (uint32_t)v);
 }
 
+// rows [from, to) of one slot's xyzs / dirs / deltas <- 0, by the slot's warp (consecutive floats, lane-strided)
+__device__ __forceinline__ void zero_rows(float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas, uint32_t from,
+                                          uint32_t to, unsigned lane) {
+    for (uint32_t j = from * 3u + lane; j < to * 3u; j += 32u) {
+        xyzs[j] = 0.0f;
+        dirs[j] = 0.0f;
+    }
+    for (uint32_t j = from * 2u + lane; j < to * 2u; j += 32u) deltas[j] = 0.0f;
+}
+
 // raymarching.cu:700-804.  One warp per alive ray, at most n_step samples from rays_t.
 __global__ void __launch_bounds__(256, 5)
 k_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* __restrict__ rays_alive,
@@ -537,15 +547,23 @@ k_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* __restrict__ rays
     const uint32_t index = (uint32_t)rays_alive[n];
     float t = rays_t[n];
     const OccBox box = occupied_box(c, occ_bounds);
-    if (n >= alive_count(n_alive, n_alive_dev)) return;
+    const size_t base = (size_t)n * n_step;
+    const unsigned lane = lane_id();
+    // Every row of the slot is written here, samples first and zeros behind them ("slots without a sample stay zero",
+    // raymarching.py:205-207; a zero delta is how composite_rays recognises the end of a ray's round), dead slots included: the caller
+    // does not have to clear n_alive * n_step * 32 bytes per round first.
+    if (n >= alive_count(n_alive, n_alive_dev)) {
+        zero_rows(xyzs + base * 3, dirs + base * 3, deltas + base * 2, 0u, n_step, lane);
+        return;
+    }
     const Ray r = load_ray(rays_o, rays_d, index);
     const float far = fars[index];
     if (perturb) {
         Pcg32 rng((uint64_t)n, (uint64_t)perturb);  // seeded by the alive SLOT, raymarching.cu:743
         t = __fmaf_rn(c.dt_min, rng.next_float(), t);
     }
-    const size_t base = (size_t)n * n_step;
-    march_warp<true>(r, c, grid, t, far, n_step, xyzs + base * 3, dirs + base * 3, deltas + base * 2, occupied_range(r, box));
+    const uint32_t emitted = march_warp<true>(r, c, grid, t, far, n_step, xyzs + base * 3, dirs + base * 3, deltas + base * 2, occupied_range(r, box));
+    zero_rows(xyzs + base * 3, dirs + base * 3, deltas + base * 2, emitted, n_step, lane);
 }
 
 // Box around the occupied cells of each cascade level: one CTA per level scans the level's bits 128 at a time (128 consecutive Morton

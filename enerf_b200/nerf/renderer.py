@@ -248,7 +248,10 @@ class NeRFRenderer(nn.Module):
                     n_ch = rgbs.shape[-1]
                     image = torch.zeros(N, n_ch, dtype=torch.float32, device=device)
                 raymarching.composite_rays(n_bound, n_step, rays_alive[i % 2], rays_t[i % 2], sigmas, rgbs, deltas, weights_sum, depth, image, count_dev)
-                shaded += (count_dev.long() if count_dev is not None else N) * n_step
+                if count_dev is not None:
+                    shaded.add_(count_dev, alpha=n_step)
+                else:
+                    shaded += N * n_step
                 step += n_step
                 i += 1
             # bookkeeping for bench.py (not in the reference): samples actually shaded (alive rays x steps), rounds, host reads of the counter

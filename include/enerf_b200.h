@@ -83,7 +83,9 @@ int enerf_composite_rays_train_backward(const float* grad_weights_sum, const flo
                                         const float* weights_sum, const float* image,
                                         uint32_t M, uint32_t N, uint32_t n_ch,
                                         float* grad_sigmas, float* grad_rgbs, void* stream);
-/* raymarching.h:16 march_rays (inference); raymarching.cu:700-813 */
+/* raymarching.h:16 march_rays (inference); raymarching.cu:700-813.  The reference's wrapper zero-fills xyzs / dirs / deltas first and the
+ * kernel writes the samples; here (and in the _dev / _bounded forms) the kernel writes every row of the n_alive * n_step it is launched
+ * for — samples, then zeros — so the buffers may come uninitialised (since ABI v8). */
 int enerf_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive,
                      const float* rays_t, const float* rays_o, const float* rays_d, float bound,
                      float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,

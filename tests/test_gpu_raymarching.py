@@ -206,6 +206,32 @@ def test_inference_loop_primitives_match_oracle():
         assert all(abs(got[k] - want[k]) < 1e-6 for k in want)
 
 
+@pytest.mark.parametrize("live", [700, 123, 0])
+def test_inference_march_writes_every_row_of_its_slots(live):
+    """k_march_rays leaves nothing of the n_alive * n_step rows to the caller: samples, zeros behind a ray's last sample (the padding
+    composite_rays stops at), zeros in the slots at or beyond the device-side alive count — on buffers that start out as NaN"""
+    from enerf_b200.backends import raymarching_backend as RB
+    bound, N, n_alive, n_step = 2, 999, 700, 26
+    sc = scene(N, bound, seed=5)
+    o, d, bits, nears, fars = t(sc["o"]), t(sc["d"]), t(sc["bits"]), t(sc["nears"]), t(sc["fars"])
+    alive_np = np.random.default_rng(3).permutation(N)[:n_alive].astype(np.int32)
+    t_np = sc["nears"][alive_np].copy()
+    t_np[::7] = sc["fars"][alive_np][::7] - np.float32(0.05)      # rays about to end: fewer than n_step samples, then padding
+    wx, wd, wdl = oracle.march_rays(live, n_step, alive_np, t_np, sc["o"], sc["d"], bound, sc["bits"], sc["cascade"], 128, sc["nears"], sc["fars"])
+    M = n_alive * n_step
+    xyzs, dirs, deltas = (torch.full((M, k), float("nan"), device=DEV) for k in (3, 3, 2))
+    count = torch.tensor([live], dtype=torch.int32, device=DEV)
+    for ob in (None, RB.occupancy_bounds(bits, sc["cascade"], 128)):
+        for buf in (xyzs, dirs, deltas):
+            buf.fill_(float("nan"))
+        RB.march_rays(n_alive, n_step, t(alive_np), t(t_np), o, d, float(bound), 0.0, 1024, sc["cascade"], 128, bits, nears, fars, xyzs, dirs, deltas, 0,
+                      count, ob)
+        m = live * n_step
+        assert np.array_equal(n(xyzs)[:m], wx) and np.array_equal(n(dirs)[:m], wd) and np.array_equal(n(deltas)[:m], wdl)
+        assert 0 < np.count_nonzero(wdl[:, 0] == 0) < max(m, 1) or live == 0      # the case has padding rows
+        assert bool((xyzs[m:] == 0).all()) and bool((dirs[m:] == 0).all()) and bool((deltas[m:] == 0).all())
+
+
 def test_full_size_properties_4096_rays_bound3():
     """BASELINE config-2 shape: size-independent invariants instead of an oracle pass."""
     sc = scene(4096, 3, seed=11)
