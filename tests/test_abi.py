@@ -74,3 +74,34 @@ def test_dropin_packages_expose_reference_names():
                        (backends.ffmlp_backend, ["ffmlp_forward", "ffmlp_inference", "ffmlp_backward", "allocate_splitk", "free_splitk"])]:
         for n in names:
             assert callable(getattr(obj, n)), n
+
+
+def test_inference_sample_buffers_clear_only_the_alignment_rows():
+    """host logic of raymarching.march_rays: the kernel writes rows [0, n_alive * n_step), the wrapper zeroes the rows the 128-row
+    alignment adds and nothing else; the three views share one allocation"""
+    from enerf_b200.raymarching.raymarching import _empty_samples, _pad_up
+    written = 700 * 26
+    M = _pad_up(written, 128)
+    assert M % 128 == 0 and 0 < M - written < 128
+    xyzs, dirs, deltas = _empty_samples(M, written, torch.device("cpu"))
+    assert xyzs.shape == (M, 3) and dirs.shape == (M, 3) and deltas.shape == (M, 2)
+    assert xyzs.untyped_storage().data_ptr() == dirs.untyped_storage().data_ptr() == deltas.untyped_storage().data_ptr()
+    for buf in (xyzs, dirs, deltas):
+        assert buf.is_contiguous() and bool((buf[written:] == 0).all())
+    xyzs2, _, _ = _empty_samples(written, written, torch.device("cpu"))       # no alignment rows: nothing to clear
+    assert xyzs2.shape == (written, 3)
+
+
+def test_occupancy_bounds_buffer_layout_matches_the_header():
+    """ENERF_OCC_BOUNDS_WORDS in include/enerf_b200.h and the allocation in backends.occupancy_bounds agree"""
+    import re
+    src = open(_lib.HEADER_PATH).read()
+    m = re.search(r"#define ENERF_OCC_BOUNDS_WORDS\(C\) \(\(\(\(6u \* \(C\)\) \+ 3u\) & ~3u\) \+ 8u \* \(C\)\)", src)
+    assert m, "the macro changed: update backends.occupancy_bounds and this test"
+    import inspect
+    from enerf_b200 import backends
+    body = inspect.getsource(backends.raymarching_backend.occupancy_bounds)
+    assert "((6 * C + 3) & ~3) + 8 * C" in body
+    for C in range(1, 17):
+        off = (6 * C + 3) & ~3
+        assert off % 4 == 0 and off >= 6 * C and off - 6 * C < 4          # float rows 16-byte aligned, right behind the integer rows
