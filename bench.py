@@ -481,7 +481,7 @@ def event_step_bench(args, dev, K):
            "event_pairs_per_step": pairs, "steps": K, "ms_per_step": ms, "event_pairs_per_s": pairs / (ms * 1e-3),
            "rendered_rays_per_s": 2 * pairs / (ms * 1e-3), "samples_per_render": [int(t) for t in totals],
            "samples_per_s": float(sum(totals)) / (ms * 1e-3), "launch": "cuda-graph replay" if graphed is not None else "eager",
-           "loss": float(loss), "loss_finite": bool(torch.isfinite(loss))}
+           "loss": float(loss.detach()), "loss_finite": bool(torch.isfinite(loss.detach()))}
     if graphed is not None:
         graphed.graph = None
     del model, optimizer, sampler
